@@ -1,0 +1,209 @@
+/*
+ * pdmpc_b200.h — C ABI of the B200-native drop-in for p-dmpc's per-vehicle
+ * trajectory optimizer (hlc/optimizer graph search over the motion-primitive
+ * automaton, MPA).
+ *
+ * This is the boundary a MATLAB MEX shim (see INTEGRATION.md and
+ * p-dmpc_b200/matlab/) binds.  It replaces, for the hot path only:
+ *
+ *   reference interface                                      file:line
+ *   -------------------------------------------------------  ------------------------------------------------------
+ *   OptimizerInterface.run_optimizer(veh, iter, mpa, opt, k) hlc/optimizer/OptimizerInterface.m:14
+ *   GraphSearch.do_graph_search / eval_edge_exact            hlc/optimizer/graph_search/GraphSearch.m:23-196
+ *   expand_node                                              hlc/optimizer/graph_search/expand_node.m:1-91
+ *   are_constraints_satisfied_sat / intersect_sat            hlc/optimizer/graph_search/are_constraints_satisfied_sat.m:1-68,
+ *                                                            hlc/optimizer/graph_search/intersect_sat.m:1-42
+ *   intersect_lanelet_boundary                               hlc/optimizer/common/intersect_lanelet_boundary.m:1-56
+ *   are_constraints_satisfied_interx / InterX                hlc/optimizer/graph_search/are_constraints_satisfied_interx.m:1-39,
+ *                                                            hlc/optimizer/graph_search/InterX.m:48-110
+ *   vectorize_all_obstacles                                  hlc/optimizer/graph_search/vectorize_all_obstacles.m:1-76
+ *   priority_queue_interface_mex (NEW/PUSH/POP)              hlc/optimizer/graph_search/priority_queue/priority_queue_interface_mex.cpp:19-108
+ *   return_path_to / return_path_area                        hlc/optimizer/graph_search/return_path_to.m:1-27, return_path_area.m:1-8
+ *
+ * Conventions
+ *   - plain C, no C++ types, no exceptions cross this boundary; every call
+ *     returns an int status (PDMPC_OK == 0) and pdmpc_last_error() gives text.
+ *   - all host buffers are caller-owned; the library owns device memory.
+ *   - trims and node ids are 1-BASED, exactly as MATLAB passes / expects them
+ *     (Tree.m:18,61: root id 1, parent(root) = 0).
+ *   - all floating point is IEEE double; the device path computes with the
+ *     same operation order as the reference and with FMA contraction off.
+ *   - one handle per host thread / process (MATLAB calls MEX from its main
+ *     thread; parallel_threads = separate processes, utility/get_parallel_pool.m:37).
+ *   - there is NO CPU fallback: without a CUDA device pdmpc_create fails with
+ *     PDMPC_ERR_CUDA.
+ */
+#ifndef PDMPC_B200_H
+#define PDMPC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDMPC_ABI_VERSION 1
+
+/* A maneuver area polygon has 5 (straight), 6 (turn, convex build) or 7 (turn,
+ * non-convex build) closed points: generate_maneuver.m:73-103.  Fixed stride. */
+#define PDMPC_AREA_STRIDE 8
+/* Upper bound on the prediction horizon accepted by the library (Config.m:33
+ * default 6; eval_phd.m:14-19 uses up to 10). */
+#define PDMPC_MAX_HP 16
+/* Upper bound on the number of trims (realistic MPA: 71). */
+#define PDMPC_MAX_TRIMS 128
+
+enum pdmpc_status {
+    PDMPC_OK = 0,
+    PDMPC_ERR_BAD_INPUT = 1,   /* null pointer, sizes out of range, malformed CSR, open polygon */
+    PDMPC_ERR_CUDA = 2,        /* CUDA runtime error (text in pdmpc_last_error) */
+    PDMPC_ERR_CAPACITY = 3,    /* a search outgrew the node arena / heap: never truncated silently */
+    PDMPC_ERR_NO_MPA = 4,      /* plan called before pdmpc_upload_mpa */
+    PDMPC_ERR_ALLOC = 5
+};
+
+/* Which constraint checker the search uses (OptimizerInterface.m:36-46,
+ * Config.m:71-87): SAT for circle / non-prioritized, InterX otherwise. */
+enum pdmpc_checker {
+    PDMPC_CHECKER_SAT = 0,
+    PDMPC_CHECKER_INTERX = 1
+};
+
+/* area kinds of one maneuver (generate_maneuver.m:39-64) */
+enum pdmpc_area_kind {
+    PDMPC_AREA_NORMAL = 0,         /* maneuver.area               (offset 0.01 all round) */
+    PDMPC_AREA_WITHOUT_OFFSET = 1, /* maneuver.area_without_offset                         */
+    PDMPC_AREA_LARGE_OFFSET = 2    /* maneuver.area_large_offset  (+0.05 in length)        */
+};
+
+typedef struct pdmpc_handle pdmpc_handle;
+
+/* ---- MPA tables: what the search reads of MotionPrimitiveAutomaton
+ *      (MotionPrimitiveAutomaton.m:5-17) ------------------------------------ */
+typedef struct pdmpc_mpa_desc {
+    int32_t n_trims;            /* numel(mpa.trims) */
+    int32_t Hp;                 /* size(transition_matrix_single, 3) */
+    int32_t n_edges;            /* number of non-empty mpa.maneuvers{t1,t2} */
+    /* transition_matrix_single(t1,t2,k) != 0, laid out [k-1][t1-1][t2-1] */
+    const uint8_t *transition;  /* Hp * n_trims * n_trims */
+    const int32_t *edge_from;   /* [n_edges] t1, 1-based */
+    const int32_t *edge_to;     /* [n_edges] t2, 1-based */
+    const double *edge_dx;      /* [n_edges] maneuver.dx   */
+    const double *edge_dy;      /* [n_edges] maneuver.dy   */
+    const double *edge_dyaw;    /* [n_edges] maneuver.dyaw */
+    const int32_t *area_npts;   /* [n_edges*3] points per area kind (closed: first == last) */
+    const double *area_x;       /* [n_edges*3*PDMPC_AREA_STRIDE] local-frame x */
+    const double *area_y;       /* [n_edges*3*PDMPC_AREA_STRIDE] local-frame y */
+} pdmpc_mpa_desc;
+
+/* ---- One batch of independent searches (vehicle x permutation x scenario).
+ *      Each search is what PrioritizedController.plan hands to run_optimizer
+ *      (PrioritizedController.m:297-341) reduced to the IterationData fields
+ *      the search reads (IterationData.m:4-33), nV == 1. -------------------- */
+typedef struct pdmpc_batch_in {
+    int32_t n_searches;
+    int32_t checker;            /* enum pdmpc_checker, same for the whole batch */
+    double dt_seconds;          /* options.dt_seconds */
+    const double *x0;           /* [n] iter.x0(:,1) */
+    const double *y0;           /* [n] iter.x0(:,2) */
+    const double *yaw0;         /* [n] iter.x0(:,3) */
+    const int32_t *trim0;       /* [n] iter.trim_indices, 1-based */
+    const double *ref_x;        /* [n*Hp] iter.reference_trajectory_points(1,k,1) */
+    const double *ref_y;        /* [n*Hp] iter.reference_trajectory_points(1,k,2) */
+    const double *v_ref;        /* [n*Hp] iter.v_ref(1,k) */
+    /* Obstacle polygons as a three-level CSR.  Slot s = search*(Hp+1) + k:
+     *   k = 0      -> iter.obstacles{:}               (static, checked at every step)
+     *   k = 1..Hp  -> iter.dynamic_obstacle_area{:,k} (checked at step k)
+     * slot_ptr[s]..slot_ptr[s+1] are polygon indices, poly_ptr[p]..poly_ptr[p+1]
+     * are vertex indices into vert_x/vert_y.  Polygons are closed (first vertex
+     * repeated last), as vectorize_all_obstacles.m:71-76 asserts. */
+    const int32_t *slot_ptr;    /* [n*(Hp+1)+1] */
+    const int32_t *poly_ptr;    /* [n_polys+1]  */
+    const double *vert_x;       /* [n_verts] */
+    const double *vert_y;       /* [n_verts] */
+    /* iter.predicted_lanelet_boundary{1,1:2}: open polylines.  lane_ptr[2*i] ..
+     * lane_ptr[2*i+1] = left bound of search i, lane_ptr[2*i+1]..lane_ptr[2*i+2]
+     * = right bound.  Empty ranges = no lanelets (circle scenario). */
+    const int32_t *lane_ptr;    /* [2n+1] */
+    const double *lane_x;       /* [n_lane_pts] */
+    const double *lane_y;       /* [n_lane_pts] */
+} pdmpc_batch_in;
+
+/* ---- Results, caller-allocated, SoA over the batch.  Field meaning follows
+ *      ControlResultsInfo (ControlResultsInfo.m:5-17) and the flat outputs
+ *      OptimizerInterface.create_control_results_info_from_mex consumes
+ *      (OptimizerInterface.m:63-101).  Any pointer may be NULL = not wanted,
+ *      except status. --------------------------------------------------------- */
+typedef struct pdmpc_batch_out {
+    int32_t *status;        /* [n] per-search pdmpc_status */
+    uint8_t *is_exhausted;  /* [n] info.is_exhausted */
+    int32_t *n_expanded;    /* [n] info.n_expanded == tree.size() at exit (GraphSearch.m:58,89) */
+    int32_t *n_pops;        /* [n] number of pq.pop() that returned a node */
+    uint64_t *pop_hash;     /* [n] FNV-1a over the popped node ids, in pop order (parity trace) */
+    int32_t *trims;         /* [n*(Hp+1)] current_and_predicted_trims, 1-based; zeros after col 1 if exhausted */
+    int32_t *tree_path;     /* [n*(Hp+1)] node ids root..goal in the full tree; zeros if exhausted */
+    double *y_predicted;    /* [n*Hp*3] (x,y,yaw) per step; NaN if exhausted */
+    double *g_path;         /* [n*(Hp+1)] tree.g along the path (cost to come); NaN if exhausted */
+    double *h_path;         /* [n*(Hp+1)] tree.h along the path; NaN if exhausted */
+    int32_t *shape_npts;    /* [n*Hp] points of info.shapes{1,k}; 0 if exhausted */
+    double *shape_x;        /* [n*Hp*PDMPC_AREA_STRIDE] */
+    double *shape_y;        /* [n*Hp*PDMPC_AREA_STRIDE] */
+} pdmpc_batch_out;
+
+/* Device-side counters of the last plan call (for roofline accounting,
+ * SURVEY.md §8(d)). */
+typedef struct pdmpc_stats {
+    double kernel_ms;        /* CUDA-event time of the search kernel(s) */
+    double h2d_ms;           /* host->device staging */
+    double d2h_ms;           /* device->host results */
+    int64_t h2d_bytes;
+    int64_t d2h_bytes;
+    int64_t total_pops;
+    int64_t total_nodes;
+    int64_t total_obstacle_cols; /* sum over pops of (V_k + L) columns tested */
+    int32_t kernel_launches;
+} pdmpc_stats;
+
+/* Create a planner bound to CUDA device `device_id`.  Fails (PDMPC_ERR_CUDA)
+ * when no such device exists: there is no CPU path. */
+int pdmpc_create(int device_id, pdmpc_handle **out);
+int pdmpc_destroy(pdmpc_handle *h);
+const char *pdmpc_last_error(const pdmpc_handle *h);
+int pdmpc_abi_version(void);
+
+/* Node-arena capacity (nodes per concurrently running search).  Default is the
+ * full-tree bound of the uploaded MPA when it is below 2^20, else 2^20.  A
+ * search that needs more returns PDMPC_ERR_CAPACITY in its status. */
+int pdmpc_set_node_capacity(pdmpc_handle *h, int32_t max_nodes_per_search);
+
+/* Stage the MPA tables in HBM (once per MPA; cached in the handle). */
+int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *mpa);
+
+/* Plan a batch whose inputs/outputs are HOST buffers: stage -> search -> fetch. */
+int pdmpc_plan_batch(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc_batch_out *out);
+
+/* Device-resident variant for throughput runs: stage once, run many, fetch once. */
+int pdmpc_stage_batch(pdmpc_handle *h, const pdmpc_batch_in *in);
+int pdmpc_run_staged(pdmpc_handle *h);                 /* launches on the handle's stream, no host sync */
+int pdmpc_sync(pdmpc_handle *h);
+int pdmpc_fetch_staged(pdmpc_handle *h, pdmpc_batch_out *out);
+
+int pdmpc_get_stats(pdmpc_handle *h, pdmpc_stats *out);
+
+/* Pinned host buffers for callers that want full-rate host<->device copies. */
+int pdmpc_host_alloc(void **p, size_t bytes);
+int pdmpc_host_free(void *p);
+
+/* Parity/debug aid: re-run the staged batch and record the node ids search
+ * `search` pops, in order (the reference's pq.pop() sequence, GraphSearch.m:55). */
+int pdmpc_trace_staged(pdmpc_handle *h, int32_t search, int64_t *ids, int64_t cap, int64_t *n_out);
+
+/* The CUDA stream the kernels are launched on (cudaStream_t as void*), so a
+ * host harness can record its own events on it. */
+void *pdmpc_stream(pdmpc_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDMPC_B200_H */

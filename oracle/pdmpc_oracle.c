@@ -1,0 +1,618 @@
+/*
+ * pdmpc_oracle.c — CPU oracle (TEST INFRASTRUCTURE, see pdmpc_oracle.h).
+ *
+ * Plain-C, IEEE-double restatement of the reference's per-vehicle graph search.
+ * Build: gcc -O2 -ffp-contract=off -fPIC -shared (oracle/Makefile).  Every
+ * function cites the reference file:line it follows (paths relative to the
+ * reference checkout).
+ */
+#include "pdmpc_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------- */
+/* sin / cos: the reference calls MATLAB's cos/sin (GraphSearch.m:155-156,
+ * expand_node.m:50-51), closed source.  Oracle and device path both use the
+ * algorithm below so that costs, and therefore pop order,
+ * agree bit for bit.  |error| < 1.5 ulp for |x| < 2^20 * pi/2.               */
+static const double SC_TWO_OVER_PI = 0x1.45f306dc9c883p-1;
+static const double SC_P1 = 0x1.921fb54400000p+0;  /* pi/2, leading 33 bits */
+static const double SC_P2 = 0x1.0b4611a600000p-34; /* next 33 bits          */
+static const double SC_P3 = 0x1.3198a2e037073p-69; /* remainder             */
+static const double SC_S[10] = {
+    -0x1.5555555555555p-3, 0x1.1111111111111p-7, -0x1.a01a01a01a01ap-13,
+    0x1.71de3a556c734p-19, -0x1.ae64567f544e4p-26, 0x1.6124613a86d09p-33,
+    -0x1.ae7f3e733b81fp-41, 0x1.952c77030ad4ap-49, -0x1.2f49b46814157p-57,
+    0x1.71b8ef6dcf572p-66};
+static const double SC_C[10] = {
+    -0x1.0000000000000p-1, 0x1.5555555555555p-5, -0x1.6c16c16c16c17p-10,
+    0x1.a01a01a01a01ap-16, -0x1.27e4fb7789f5cp-22, 0x1.1eed8eff8d898p-29,
+    -0x1.93974a8c07c9dp-37, 0x1.ae7f3e733b81fp-45, -0x1.6827863b97d97p-53,
+    0x1.e542ba4020225p-62};
+
+void oracle_sincos(double x, double *s, double *c) {
+    double n = rint(x * SC_TWO_OVER_PI);
+    double r = ((x - n * SC_P1) - n * SC_P2) - n * SC_P3;
+    double z = r * r;
+    double ps = SC_S[9];
+    double pc = SC_C[9];
+    for (int i = 8; i >= 0; --i) {
+        ps = ps * z + SC_S[i];
+        pc = pc * z + SC_C[i];
+    }
+    double sr = r + (r * z) * ps; /* sin(r) */
+    double cr = 1.0 + z * pc;     /* cos(r) */
+    long long q = (long long)n & 3LL;
+    switch (q) {
+    case 0: *s = sr; *c = cr; break;
+    case 1: *s = cr; *c = -sr; break;
+    case 2: *s = -sr; *c = -cr; break;
+    default: *s = -cr; *c = sr; break;
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* intersect_sat.m:17-42 (intersect_a_b)                                      */
+static int sat_a_b(const double *x1, const double *y1, int n1,
+                   const double *x2, const double *y2, int n2) {
+    /* :19 edge_vector = diff([shape1, shape1(:,1)],1,2) -> n1 edges incl. closing */
+    for (int e = 0; e < n1; ++e) {
+        int e1 = (e + 1 == n1) ? 0 : e + 1;
+        double ex = x1[e1] - x1[e];
+        double ey = y1[e1] - y1[e];
+        /* :21 axis = [-ey; ex]; :23 normed = axis ./ vecnorm(axis) */
+        double ax = -ey, ay = ex;
+        double nrm = sqrt(ax * ax + ay * ay);
+        double nx = ax / nrm, ny = ay / nrm; /* zero edge -> NaN axis */
+        /* :26-32 projections; MATLAB min/max skip NaN == C fmin/fmax */
+        double mn1 = NAN, mx1 = NAN, mn2 = NAN, mx2 = NAN;
+        for (int v = 0; v < n1; ++v) {
+            double d = nx * x1[v] + ny * y1[v];
+            mn1 = fmin(mn1, d);
+            mx1 = fmax(mx1, d);
+        }
+        for (int v = 0; v < n2; ++v) {
+            double d = nx * x2[v] + ny * y2[v];
+            mn2 = fmin(mn2, d);
+            mx2 = fmax(mx2, d);
+        }
+        /* :33-40 */
+        double d1 = mn1 - mx2;
+        double d2 = mn2 - mx1;
+        if (d1 > 0 || d2 > 0) return 0;
+    }
+    return 1;
+}
+
+/* intersect_sat.m:1-15 */
+int oracle_intersect_sat(const double *x1, const double *y1, int n1,
+                         const double *x2, const double *y2, int n2) {
+    if (!sat_a_b(x1, y1, n1, x2, y2, n2)) return 0;
+    if (!sat_a_b(x2, y2, n2, x1, y1, n1)) return 0;
+    return 1;
+}
+
+/* intersect_lanelets.m:1-22: per segment right bound first, then left bound */
+int oracle_intersect_lanelets(const double *sx, const double *sy, int ns,
+                              const double *rx, const double *ry,
+                              const double *lx, const double *ly, int n) {
+    for (int i = 0; i + 1 < n; ++i) {
+        if (oracle_intersect_sat(sx, sy, ns, rx + i, ry + i, 2)) return 1;
+        if (oracle_intersect_sat(sx, sy, ns, lx + i, ly + i, 2)) return 1;
+    }
+    return 0;
+}
+
+/* intersect_lanelet_boundary.m:1-56 */
+static int lanelet_side(const double *sx, const double *sy, int ns, double max_x,
+                        double min_x, double max_y, double min_y,
+                        const double *bx, const double *by, int nb) {
+    for (int n = 0; n + 1 < nb; ++n) {
+        double ax = bx[n], bx2 = bx[n + 1], ay = by[n], by2 = by[n + 1];
+        /* :20 / :40 all(max_x < seg_x) || all(min_x > seg_x) || ... */
+        if ((max_x < ax && max_x < bx2) || (min_x > ax && min_x > bx2) ||
+            (max_y < ay && max_y < by2) || (min_y > ay && min_y > by2))
+            continue;
+        if (oracle_intersect_sat(sx, sy, ns, bx + n, by + n, 2)) return 1;
+    }
+    return 0;
+}
+
+int oracle_intersect_lanelet_boundary(const double *sx, const double *sy, int ns,
+                                      const double *lx, const double *ly, int nl,
+                                      const double *rx, const double *ry, int nr) {
+    /* :11-14 max/min over shape (NaN-free input) */
+    double max_x = sx[0], min_x = sx[0], max_y = sy[0], min_y = sy[0];
+    for (int i = 1; i < ns; ++i) {
+        max_x = fmax(max_x, sx[i]);
+        min_x = fmin(min_x, sx[i]);
+        max_y = fmax(max_y, sy[i]);
+        min_y = fmin(min_y, sy[i]);
+    }
+    if (lanelet_side(sx, sy, ns, max_x, min_x, max_y, min_y, lx, ly, nl)) return 1;
+    if (lanelet_side(sx, sy, ns, max_x, min_x, max_y, min_y, rx, ry, nr)) return 1;
+    return 0;
+}
+
+/* InterX.m:48-85,108-110, isReturnPoints == false */
+int oracle_interx(const double *x1, const double *y1, int n1,
+                  const double *x2, const double *y2, int n2) {
+    if (n1 == 0 || n2 == 0) return 0; /* :48-52 */
+    for (int i = 0; i + 1 < n1; ++i) {
+        double dx1 = x1[i + 1] - x1[i]; /* :63 */
+        double dy1 = y1[i + 1] - y1[i];
+        double S1 = dx1 * y1[i] - dy1 * x1[i]; /* :67 */
+        for (int j = 0; j + 1 < n2; ++j) {
+            double dx2 = x2[j + 1] - x2[j]; /* :64 */
+            double dy2 = y2[j + 1] - y2[j];
+            double S2 = dx2 * y2[j] - dy2 * x2[j]; /* :68 */
+            /* :70  C1 = D(dx1*y2 - dy1*x2, S1) < 0 */
+            double a0 = (dx1 * y2[j] - dy1 * x2[j]) - S1;
+            double a1 = (dx1 * y2[j + 1] - dy1 * x2[j + 1]) - S1;
+            int c1 = (a0 * a1) < 0;
+            /* :71  C2 = (D((y1*dx2 - x1*dy2)', S2') < 0)' */
+            double b0 = (y1[i] * dx2 - x1[i] * dy2) - S2;
+            double b1 = (y1[i + 1] * dx2 - x1[i + 1] * dy2) - S2;
+            int c2 = (b0 * b1) < 0;
+            if (c1 && c2) return 1; /* :74-85 */
+        }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* priority queue: priority_queue_interface_mex.cpp:19-31 (min on value) on
+ * top of libstdc++ stl_heap.h (__push_heap :135-147, __adjust_heap :224-249). */
+typedef struct {
+    int64_t id;
+    double val;
+} pq_entry;
+struct oracle_pq {
+    pq_entry *a;
+    int64_t len, cap;
+};
+
+/* comp(a,b) of the reference: value(a) > value(b) */
+static inline int pq_comp(const pq_entry *a, const pq_entry *b) { return a->val > b->val; }
+
+static void pq_push_heap(pq_entry *first, int64_t hole, int64_t top, pq_entry value) {
+    int64_t parent = (hole - 1) / 2;
+    while (hole > top && pq_comp(first + parent, &value)) {
+        first[hole] = first[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    first[hole] = value;
+}
+
+static void pq_adjust_heap(pq_entry *first, int64_t hole, int64_t len, pq_entry value) {
+    const int64_t top = hole;
+    int64_t second = hole;
+    while (second < (len - 1) / 2) {
+        second = 2 * (second + 1);
+        if (pq_comp(first + second, first + (second - 1))) second--;
+        first[hole] = first[second];
+        hole = second;
+    }
+    if ((len & 1) == 0 && second == (len - 2) / 2) {
+        second = 2 * (second + 1);
+        first[hole] = first[second - 1];
+        hole = second - 1;
+    }
+    pq_push_heap(first, hole, top, value);
+}
+
+oracle_pq *oracle_pq_new(void) {
+    oracle_pq *q = (oracle_pq *)calloc(1, sizeof(*q));
+    return q;
+}
+void oracle_pq_free(oracle_pq *q) {
+    if (!q) return;
+    free(q->a);
+    free(q);
+}
+void oracle_pq_push(oracle_pq *q, int64_t id, double value) {
+    if (q->len == q->cap) {
+        q->cap = q->cap ? q->cap * 2 : 256;
+        q->a = (pq_entry *)realloc(q->a, (size_t)q->cap * sizeof(pq_entry));
+    }
+    pq_entry e = {id, value};
+    q->a[q->len++] = e;                       /* c.push_back(x) */
+    pq_push_heap(q->a, q->len - 1, 0, e);     /* std::push_heap */
+}
+int64_t oracle_pq_pop(oracle_pq *q, double *value) {
+    if (q->len == 0) return -1;               /* ...mex.cpp:87-94 */
+    pq_entry top = q->a[0];
+    if (q->len > 1) {                         /* std::pop_heap */
+        pq_entry last = q->a[q->len - 1];
+        q->a[q->len - 1] = q->a[0];
+        pq_adjust_heap(q->a, 0, q->len - 1, last);
+    }
+    q->len--;                                 /* c.pop_back() */
+    if (value) *value = top.val;
+    return top.id;
+}
+int64_t oracle_pq_size(const oracle_pq *q) { return q->len; }
+
+/* ------------------------------------------------------------------------- */
+/* Tree.m: SoA arena, ids 1-based (index 0 unused so ids index directly).     */
+typedef struct {
+    double *x, *y, *yaw, *g, *h;
+    int32_t *trim, *k, *parent;
+    int64_t size, cap; /* size == number of nodes == tree.size() */
+} tree_t;
+
+static void tree_reserve(tree_t *t, int64_t need) {
+    if (need + 1 <= t->cap) return;
+    int64_t cap = t->cap ? t->cap : 1024;
+    while (cap < need + 1) cap *= 2;
+    t->x = (double *)realloc(t->x, (size_t)cap * sizeof(double));
+    t->y = (double *)realloc(t->y, (size_t)cap * sizeof(double));
+    t->yaw = (double *)realloc(t->yaw, (size_t)cap * sizeof(double));
+    t->g = (double *)realloc(t->g, (size_t)cap * sizeof(double));
+    t->h = (double *)realloc(t->h, (size_t)cap * sizeof(double));
+    t->trim = (int32_t *)realloc(t->trim, (size_t)cap * sizeof(int32_t));
+    t->k = (int32_t *)realloc(t->k, (size_t)cap * sizeof(int32_t));
+    t->parent = (int32_t *)realloc(t->parent, (size_t)cap * sizeof(int32_t));
+    t->cap = cap;
+}
+static void tree_free(tree_t *t) {
+    free(t->x); free(t->y); free(t->yaw); free(t->g); free(t->h);
+    free(t->trim); free(t->k); free(t->parent);
+    memset(t, 0, sizeof(*t));
+}
+
+typedef struct {
+    tree_t tree;
+    oracle_pq pq;
+    double *ox, *oy; /* vectorize_all_obstacles scratch */
+    int64_t ocap;
+    int32_t *edge_of; /* n_trims*n_trims -> edge index or -1 */
+} work_t;
+
+static uint64_t fnv1a_u32(uint64_t h, uint32_t v) {
+    for (int b = 0; b < 4; ++b) {
+        h ^= (uint64_t)((v >> (8 * b)) & 0xffu);
+        h *= 0x100000001b3ULL;
+    }
+    return h;
+}
+
+/* rotate/translate a maneuver area: GraphSearch.m:158-159 (and :162-163,:168-169) */
+static void place_area(const pdmpc_mpa_desc *mpa, int edge, int kind, double c, double s,
+                       double px, double py, double *ox, double *oy, int *n) {
+    int np = mpa->area_npts[edge * 3 + kind];
+    const double *ax = mpa->area_x + (size_t)(edge * 3 + kind) * PDMPC_AREA_STRIDE;
+    const double *ay = mpa->area_y + (size_t)(edge * 3 + kind) * PDMPC_AREA_STRIDE;
+    for (int i = 0; i < np; ++i) {
+        ox[i] = c * ax[i] - s * ay[i] + px;
+        oy[i] = s * ax[i] + c * ay[i] + py;
+    }
+    *n = np;
+}
+
+/* are_constraints_satisfied_sat.m:1-68, nV == 1.  The HDV block (:55-66) is
+ * unreachable in the reference (`if ~any(adj)` then loop over find(adj)). */
+static int constraints_sat(const pdmpc_batch_in *in, int Hp, int si, int k,
+                           const double *sx, const double *sy, int ns,
+                           const double *bx, const double *by, int nb) {
+    const int32_t *slot = in->slot_ptr + (size_t)si * (Hp + 1);
+    /* :15-22 static obstacles, then :24-35 dynamic obstacles of step k */
+    for (int pass = 0; pass < 2; ++pass) {
+        int s = pass == 0 ? 0 : k;
+        for (int p = slot[s]; p < slot[s + 1]; ++p) {
+            int v0 = in->poly_ptr[p], v1 = in->poly_ptr[p + 1];
+            if (oracle_intersect_sat(sx, sy, ns, in->vert_x + v0, in->vert_y + v0, v1 - v0))
+                return 0;
+        }
+    }
+    /* :46-53 lanelet boundary with the boundary-check shape.  Empty boundary
+     * cells make both loops of intersect_lanelet_boundary run zero times. */
+    int l0 = in->lane_ptr[2 * si], l1 = in->lane_ptr[2 * si + 1], l2 = in->lane_ptr[2 * si + 2];
+    if (oracle_intersect_lanelet_boundary(bx, by, nb, in->lane_x + l0, in->lane_y + l0, l1 - l0,
+                                          in->lane_x + l1, in->lane_y + l1, l2 - l1))
+        return 0;
+    return 1;
+}
+
+/* vectorize_all_obstacles.m:36-63: [static..., dynamic(:,k)...], each polygon
+ * followed by a [NaN;NaN] column.  Returns the column count. */
+static int64_t vectorize_step(const pdmpc_batch_in *in, int Hp, int si, int k, work_t *w) {
+    const int32_t *slot = in->slot_ptr + (size_t)si * (Hp + 1);
+    int64_t need = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        int s = pass == 0 ? 0 : k;
+        for (int p = slot[s]; p < slot[s + 1]; ++p) need += in->poly_ptr[p + 1] - in->poly_ptr[p] + 1;
+    }
+    if (need > w->ocap) {
+        w->ocap = need * 2 + 64;
+        w->ox = (double *)realloc(w->ox, (size_t)w->ocap * sizeof(double));
+        w->oy = (double *)realloc(w->oy, (size_t)w->ocap * sizeof(double));
+    }
+    int64_t n = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        int s = pass == 0 ? 0 : k;
+        for (int p = slot[s]; p < slot[s + 1]; ++p) {
+            for (int v = in->poly_ptr[p]; v < in->poly_ptr[p + 1]; ++v) {
+                w->ox[n] = in->vert_x[v];
+                w->oy[n] = in->vert_y[v];
+                ++n;
+            }
+            w->ox[n] = NAN;
+            w->oy[n] = NAN;
+            ++n;
+        }
+    }
+    return n;
+}
+
+/* are_constraints_satisfied_interx.m:1-39, no HDVs (hdv_obstacles{k} empty ->
+ * is_hdv_obstacle false). */
+static int constraints_interx(const pdmpc_batch_in *in, int Hp, int si, int k, work_t *w,
+                              const double *sx, const double *sy, int ns,
+                              const double *bx, const double *by, int nb,
+                              const double *lanex, const double *laney, int nlane) {
+    int64_t nobs = vectorize_step(in, Hp, si, k, w);
+    if (oracle_interx(sx, sy, ns, w->ox, w->oy, (int)nobs)) return 0; /* :17 */
+    if (oracle_interx(bx, by, nb, lanex, laney, nlane)) return 0;      /* :34 */
+    return 1;
+}
+
+typedef struct {
+    int64_t *trace;
+    int64_t cap, n;
+} trace_t;
+
+/* GraphSearch.m:23-109 for search `si`. */
+static int search_one(const pdmpc_mpa_desc *mpa, const pdmpc_batch_in *in, pdmpc_batch_out *out,
+                      int si, work_t *w, trace_t *tr) {
+    const int Hp = mpa->Hp, nT = mpa->n_trims;
+    tree_t *t = &w->tree;
+    oracle_pq *pq = &w->pq;
+    pq->len = 0;
+    t->size = 0;
+    tree_reserve(t, 1);
+    /* :34-41 root */
+    t->size = 1;
+    t->x[1] = in->x0[si];
+    t->y[1] = in->y0[si];
+    t->yaw[1] = in->yaw0[si];
+    t->trim[1] = in->trim0[si];
+    t->k[1] = 0;
+    t->g[1] = 0;
+    t->h[1] = 0;
+    t->parent[1] = 0;
+    oracle_pq_push(pq, 1, 0.0); /* :45-46 */
+
+    /* :48-49 set_up_constraints: lanelet = [left, NaN, right, NaN]
+     * (vectorize_all_obstacles.m:27-30); built for both checkers, used by InterX */
+    int l0 = in->lane_ptr[2 * si], l1 = in->lane_ptr[2 * si + 1], l2 = in->lane_ptr[2 * si + 2];
+    int nlane = (l2 - l0) + 2;
+    double *lanex = (double *)malloc((size_t)nlane * sizeof(double));
+    double *laney = (double *)malloc((size_t)nlane * sizeof(double));
+    {
+        int n = 0;
+        for (int i = l0; i < l1; ++i) { lanex[n] = in->lane_x[i]; laney[n] = in->lane_y[i]; ++n; }
+        lanex[n] = NAN; laney[n] = NAN; ++n;
+        for (int i = l1; i < l2; ++i) { lanex[n] = in->lane_x[i]; laney[n] = in->lane_y[i]; ++n; }
+        lanex[n] = NAN; laney[n] = NAN; ++n;
+    }
+
+    const double *rx = in->ref_x + (size_t)si * Hp, *ry = in->ref_y + (size_t)si * Hp;
+    const double *vr = in->v_ref + (size_t)si * Hp;
+    int64_t n_pops = 0;
+    uint64_t hash = 0xcbf29ce484222325ULL;
+    int exhausted = 0;
+    int64_t goal = 0;
+
+    for (;;) {
+        int64_t id = oracle_pq_pop(pq, NULL); /* :55 */
+        if (id == -1) {                       /* :57-61 */
+            exhausted = 1;
+            break;
+        }
+        ++n_pops;
+        hash = fnv1a_u32(hash, (uint32_t)id);
+        if (tr && tr->n < tr->cap) tr->trace[tr->n++] = id;
+
+        /* :64-73 eval_edge_exact (:111-196) */
+        int is_valid = 1;
+        int32_t par = t->parent[id];
+        if (par) { /* :137-139 root is valid without any check */
+            double pX = t->x[par], pY = t->y[par], pYaw = t->yaw[par];
+            int t1 = t->trim[par], t2 = t->trim[id], cK = t->k[id];
+            int edge = w->edge_of[(t1 - 1) * nT + (t2 - 1)];
+            double c, s;
+            oracle_sincos(pYaw, &s, &c); /* :155-156 */
+            double sx[PDMPC_AREA_STRIDE], sy[PDMPC_AREA_STRIDE];
+            double bx[PDMPC_AREA_STRIDE], by[PDMPC_AREA_STRIDE];
+            int ns, nb;
+            place_area(mpa, edge, PDMPC_AREA_NORMAL, c, s, pX, pY, sx, sy, &ns); /* :158-160 */
+            /* :166-174 boundary shape: large offset at k == Hp, else without offset */
+            place_area(mpa, edge, cK == Hp ? PDMPC_AREA_LARGE_OFFSET : PDMPC_AREA_WITHOUT_OFFSET,
+                       c, s, pX, pY, bx, by, &nb);
+            if (in->checker == PDMPC_CHECKER_SAT)
+                is_valid = constraints_sat(in, Hp, si, cK, sx, sy, ns, bx, by, nb);
+            else
+                is_valid = constraints_interx(in, Hp, si, cK, w, sx, sy, ns, bx, by, nb, lanex,
+                                              laney, nlane);
+        }
+        if (!is_valid) continue; /* :75-77 */
+
+        if (t->k[id] == Hp) { /* :81-90 */
+            goal = id;
+            break;
+        }
+
+        /* :93-104 expand_node.m:1-91, nV == 1 */
+        {
+            double curX = t->x[id], curY = t->y[id], curYaw = t->yaw[id], curG = t->g[id];
+            int curTrim = t->trim[id];
+            int k_exp = t->k[id] + 1; /* :13 */
+            const uint8_t *row = mpa->transition + ((size_t)(k_exp - 1) * nT + (curTrim - 1)) * nT;
+            int time_steps_to_go = Hp - k_exp; /* :37 */
+            double c, s;
+            oracle_sincos(curYaw, &s, &c); /* :50-51 */
+            int64_t first_new = t->size + 1;
+            for (int j = 0; j < nT; ++j) { /* :18 find(...) ascending */
+                if (!row[j]) continue;
+                int edge = w->edge_of[(curTrim - 1) * nT + j];
+                double dx = mpa->edge_dx[edge], dy = mpa->edge_dy[edge], dyaw = mpa->edge_dyaw[edge];
+                double ex = c * dx - s * dy + curX; /* :53 */
+                double ey = s * dx + c * dy + curY; /* :54 */
+                double eyaw = curYaw + dyaw;        /* :55 */
+                /* :61 g + norm([..])^2, reference point k_exp */
+                double ddx = ex - rx[k_exp - 1], ddy = ey - ry[k_exp - 1];
+                double nrm = sqrt(ddx * ddx + ddy * ddy);
+                double eg = curG + nrm * nrm;
+                /* :66-73 */
+                double eh = 0, d_traveled_max = 0;
+                for (int it = 1; it <= time_steps_to_go; ++it) {
+                    d_traveled_max = d_traveled_max + in->dt_seconds * vr[k_exp + it - 1];
+                    double hx = ex - rx[k_exp + it - 1], hy = ey - ry[k_exp + it - 1];
+                    double hn = sqrt(hx * hx + hy * hy);
+                    double m = fmax(0.0, hn - d_traveled_max);
+                    eh = eh + m * m;
+                }
+                /* Tree.m:54-70 add_nodes */
+                tree_reserve(t, t->size + 1);
+                int64_t nid = ++t->size;
+                t->x[nid] = ex; t->y[nid] = ey; t->yaw[nid] = eyaw;
+                t->trim[nid] = j + 1; t->k[nid] = k_exp;
+                t->g[nid] = eg; t->h[nid] = eh; t->parent[nid] = (int32_t)id;
+            }
+            /* :100-104 push in order, value = g*1 + h*1 */
+            for (int64_t nid = first_new; nid <= t->size; ++nid)
+                oracle_pq_push(pq, nid, t->g[nid] * 1 + t->h[nid] * 1);
+        }
+    }
+    free(lanex);
+    free(laney);
+
+    /* results: GraphSearch.m:58-60 / :82-89 */
+    if (out->status) out->status[si] = PDMPC_OK;
+    if (out->is_exhausted) out->is_exhausted[si] = (uint8_t)exhausted;
+    if (out->n_expanded) out->n_expanded[si] = (int32_t)t->size;
+    if (out->n_pops) out->n_pops[si] = (int32_t)n_pops;
+    if (out->pop_hash) out->pop_hash[si] = hash;
+    int64_t path[PDMPC_MAX_HP + 1];
+    if (!exhausted) { /* Tree.m:44-52 path_to_root, flipped */
+        int64_t n = goal;
+        for (int d = Hp; d >= 0; --d) {
+            path[d] = n;
+            n = t->parent[n];
+        }
+    }
+    for (int d = 0; d <= Hp; ++d) {
+        size_t o = (size_t)si * (Hp + 1) + d;
+        if (out->trims) out->trims[o] = exhausted ? (d == 0 ? in->trim0[si] : 0) : t->trim[path[d]];
+        if (out->tree_path) out->tree_path[o] = exhausted ? 0 : (int32_t)path[d];
+        if (out->g_path) out->g_path[o] = exhausted ? NAN : t->g[path[d]];
+        if (out->h_path) out->h_path[o] = exhausted ? NAN : t->h[path[d]];
+    }
+    for (int d = 1; d <= Hp; ++d) {
+        size_t o = (size_t)si * Hp + (d - 1);
+        if (out->y_predicted) { /* return_path_to.m:11-25 */
+            out->y_predicted[o * 3 + 0] = exhausted ? NAN : t->x[path[d]];
+            out->y_predicted[o * 3 + 1] = exhausted ? NAN : t->y[path[d]];
+            out->y_predicted[o * 3 + 2] = exhausted ? NAN : t->yaw[path[d]];
+        }
+        if (out->shape_npts) { /* return_path_area.m:5-7: shapes stored at pop (GraphSearch.m:79) */
+            double sx[PDMPC_AREA_STRIDE], sy[PDMPC_AREA_STRIDE];
+            int ns = 0;
+            for (int i = 0; i < PDMPC_AREA_STRIDE; ++i) sx[i] = sy[i] = 0.0;
+            if (!exhausted) {
+                int64_t par = path[d - 1], ch = path[d];
+                int edge = w->edge_of[(t->trim[par] - 1) * nT + (t->trim[ch] - 1)];
+                double c, s;
+                oracle_sincos(t->yaw[par], &s, &c);
+                place_area(mpa, edge, PDMPC_AREA_NORMAL, c, s, t->x[par], t->y[par], sx, sy, &ns);
+            }
+            out->shape_npts[o] = ns;
+            if (out->shape_x && out->shape_y)
+                for (int i = 0; i < PDMPC_AREA_STRIDE; ++i) {
+                    out->shape_x[o * PDMPC_AREA_STRIDE + i] = sx[i];
+                    out->shape_y[o * PDMPC_AREA_STRIDE + i] = sy[i];
+                }
+        }
+    }
+    return 0;
+}
+
+static int32_t *build_edge_of(const pdmpc_mpa_desc *mpa) {
+    int nT = mpa->n_trims;
+    int32_t *e = (int32_t *)malloc((size_t)nT * nT * sizeof(int32_t));
+    for (int i = 0; i < nT * nT; ++i) e[i] = -1;
+    for (int i = 0; i < mpa->n_edges; ++i)
+        e[(mpa->edge_from[i] - 1) * nT + (mpa->edge_to[i] - 1)] = i;
+    return e;
+}
+
+typedef struct {
+    const pdmpc_mpa_desc *mpa;
+    const pdmpc_batch_in *in;
+    pdmpc_batch_out *out;
+    int32_t *edge_of;
+    int begin, end;
+} job_t;
+
+static void *job_main(void *p) {
+    job_t *j = (job_t *)p;
+    work_t w;
+    memset(&w, 0, sizeof(w));
+    w.edge_of = j->edge_of;
+    for (int si = j->begin; si < j->end; ++si) search_one(j->mpa, j->in, j->out, si, &w, NULL);
+    tree_free(&w.tree);
+    free(w.pq.a);
+    free(w.ox);
+    free(w.oy);
+    return NULL;
+}
+
+int oracle_plan_batch(const pdmpc_mpa_desc *mpa, const pdmpc_batch_in *in, pdmpc_batch_out *out,
+                      int n_threads) {
+    if (!mpa || !in || !out) return PDMPC_ERR_BAD_INPUT;
+    int n = in->n_searches;
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > n) n_threads = n > 0 ? n : 1;
+    int32_t *edge_of = build_edge_of(mpa);
+    job_t *jobs = (job_t *)calloc((size_t)n_threads, sizeof(job_t));
+    pthread_t *th = (pthread_t *)calloc((size_t)n_threads, sizeof(pthread_t));
+    for (int t = 0; t < n_threads; ++t) {
+        jobs[t].mpa = mpa; jobs[t].in = in; jobs[t].out = out; jobs[t].edge_of = edge_of;
+        jobs[t].begin = (int)((int64_t)n * t / n_threads);
+        jobs[t].end = (int)((int64_t)n * (t + 1) / n_threads);
+    }
+    if (n_threads == 1) {
+        job_main(&jobs[0]);
+    } else {
+        for (int t = 0; t < n_threads; ++t) pthread_create(&th[t], NULL, job_main, &jobs[t]);
+        for (int t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
+    }
+    free(jobs);
+    free(th);
+    free(edge_of);
+    return PDMPC_OK;
+}
+
+int oracle_plan_trace(const pdmpc_mpa_desc *mpa, const pdmpc_batch_in *in, int trace_search,
+                      int64_t *pop_trace, int64_t trace_cap, int64_t *n_trace) {
+    if (!mpa || !in || trace_search < 0 || trace_search >= in->n_searches) return PDMPC_ERR_BAD_INPUT;
+    work_t w;
+    memset(&w, 0, sizeof(w));
+    w.edge_of = build_edge_of(mpa);
+    trace_t tr = {pop_trace, trace_cap, 0};
+    pdmpc_batch_out out;
+    memset(&out, 0, sizeof(out));
+    search_one(mpa, in, &out, trace_search, &w, &tr);
+    if (n_trace) *n_trace = tr.n;
+    tree_free(&w.tree);
+    free(w.pq.a);
+    free(w.ox);
+    free(w.oy);
+    free(w.edge_of);
+    return PDMPC_OK;
+}

@@ -1,0 +1,251 @@
+"""ctypes binding of the C ABI in include/pdmpc_b200.h.
+
+This is the Python stand-in for the MEX shim (MATLAB/mex are absent from this
+image): tests, bench.py and the host harness go through exactly
+the entry points a MATLAB maintainer would bind.
+
+There is no CPU fallback: if ``libpdmpc_b200.so`` is missing or no CUDA device is
+visible, ``load_library`` / ``Planner`` raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from .mpa import MotionPrimitiveAutomaton
+from .records import BatchResult, SearchBatch
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "csrc", "libpdmpc_b200.so")
+
+PDMPC_OK = 0
+PDMPC_ERR_BAD_INPUT = 1
+PDMPC_ERR_CUDA = 2
+PDMPC_ERR_CAPACITY = 3
+PDMPC_ERR_NO_MPA = 4
+PDMPC_ERR_ALLOC = 5
+
+EXPORTED_SYMBOLS = (
+    "pdmpc_create", "pdmpc_destroy", "pdmpc_last_error", "pdmpc_abi_version",
+    "pdmpc_set_node_capacity", "pdmpc_upload_mpa", "pdmpc_plan_batch", "pdmpc_stage_batch",
+    "pdmpc_run_staged", "pdmpc_sync", "pdmpc_fetch_staged", "pdmpc_get_stats", "pdmpc_stream",
+)
+
+_p_u8 = C.POINTER(C.c_uint8)
+_p_i32 = C.POINTER(C.c_int32)
+_p_u64 = C.POINTER(C.c_uint64)
+_p_f64 = C.POINTER(C.c_double)
+
+
+class MpaDesc(C.Structure):
+    _fields_ = [
+        ("n_trims", C.c_int32), ("Hp", C.c_int32), ("n_edges", C.c_int32),
+        ("transition", _p_u8), ("edge_from", _p_i32), ("edge_to", _p_i32),
+        ("edge_dx", _p_f64), ("edge_dy", _p_f64), ("edge_dyaw", _p_f64),
+        ("area_npts", _p_i32), ("area_x", _p_f64), ("area_y", _p_f64),
+    ]
+
+
+class BatchIn(C.Structure):
+    _fields_ = [
+        ("n_searches", C.c_int32), ("checker", C.c_int32), ("dt_seconds", C.c_double),
+        ("x0", _p_f64), ("y0", _p_f64), ("yaw0", _p_f64), ("trim0", _p_i32),
+        ("ref_x", _p_f64), ("ref_y", _p_f64), ("v_ref", _p_f64),
+        ("slot_ptr", _p_i32), ("poly_ptr", _p_i32), ("vert_x", _p_f64), ("vert_y", _p_f64),
+        ("lane_ptr", _p_i32), ("lane_x", _p_f64), ("lane_y", _p_f64),
+    ]
+
+
+class BatchOut(C.Structure):
+    _fields_ = [
+        ("status", _p_i32), ("is_exhausted", _p_u8), ("n_expanded", _p_i32), ("n_pops", _p_i32),
+        ("pop_hash", _p_u64), ("trims", _p_i32), ("tree_path", _p_i32), ("y_predicted", _p_f64),
+        ("g_path", _p_f64), ("h_path", _p_f64), ("shape_npts", _p_i32),
+        ("shape_x", _p_f64), ("shape_y", _p_f64),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
+        ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("total_pops", C.c_int64),
+        ("total_nodes", C.c_int64), ("total_obstacle_cols", C.c_int64),
+        ("kernel_launches", C.c_int32),
+    ]
+
+
+def _ptr(a: np.ndarray, ty):
+    assert a.flags["C_CONTIGUOUS"], "array must be contiguous"
+    return a.ctypes.data_as(ty)
+
+
+def mpa_desc(mpa: MotionPrimitiveAutomaton):
+    """Returns (MpaDesc, keepalive) for an MPA table set."""
+    keep = dict(
+        transition=np.ascontiguousarray(mpa.transition, dtype=np.uint8),
+        edge_from=np.ascontiguousarray(mpa.edge_from, dtype=np.int32),
+        edge_to=np.ascontiguousarray(mpa.edge_to, dtype=np.int32),
+        edge_dx=np.ascontiguousarray(mpa.edge_dx, dtype=np.float64),
+        edge_dy=np.ascontiguousarray(mpa.edge_dy, dtype=np.float64),
+        edge_dyaw=np.ascontiguousarray(mpa.edge_dyaw, dtype=np.float64),
+        area_npts=np.ascontiguousarray(mpa.area_npts, dtype=np.int32),
+        area_x=np.ascontiguousarray(mpa.area_x, dtype=np.float64),
+        area_y=np.ascontiguousarray(mpa.area_y, dtype=np.float64),
+    )
+    d = MpaDesc(
+        n_trims=mpa.n_trims, Hp=mpa.Hp, n_edges=mpa.n_edges,
+        transition=_ptr(keep["transition"], _p_u8), edge_from=_ptr(keep["edge_from"], _p_i32),
+        edge_to=_ptr(keep["edge_to"], _p_i32), edge_dx=_ptr(keep["edge_dx"], _p_f64),
+        edge_dy=_ptr(keep["edge_dy"], _p_f64), edge_dyaw=_ptr(keep["edge_dyaw"], _p_f64),
+        area_npts=_ptr(keep["area_npts"], _p_i32), area_x=_ptr(keep["area_x"], _p_f64),
+        area_y=_ptr(keep["area_y"], _p_f64))
+    return d, keep
+
+
+def batch_in(b: SearchBatch) -> BatchIn:
+    return BatchIn(
+        n_searches=b.n, checker=b.checker, dt_seconds=b.dt_seconds,
+        x0=_ptr(b.x0, _p_f64), y0=_ptr(b.y0, _p_f64), yaw0=_ptr(b.yaw0, _p_f64),
+        trim0=_ptr(b.trim0, _p_i32), ref_x=_ptr(b.ref_x, _p_f64), ref_y=_ptr(b.ref_y, _p_f64),
+        v_ref=_ptr(b.v_ref, _p_f64), slot_ptr=_ptr(b.slot_ptr, _p_i32),
+        poly_ptr=_ptr(b.poly_ptr, _p_i32), vert_x=_ptr(b.vert_x, _p_f64),
+        vert_y=_ptr(b.vert_y, _p_f64), lane_ptr=_ptr(b.lane_ptr, _p_i32),
+        lane_x=_ptr(b.lane_x, _p_f64), lane_y=_ptr(b.lane_y, _p_f64))
+
+
+def batch_out(r: BatchResult) -> BatchOut:
+    return BatchOut(
+        status=_ptr(r.status, _p_i32), is_exhausted=_ptr(r.is_exhausted, _p_u8),
+        n_expanded=_ptr(r.n_expanded, _p_i32), n_pops=_ptr(r.n_pops, _p_i32),
+        pop_hash=_ptr(r.pop_hash, _p_u64), trims=_ptr(r.trims, _p_i32),
+        tree_path=_ptr(r.tree_path, _p_i32), y_predicted=_ptr(r.y_predicted, _p_f64),
+        g_path=_ptr(r.g_path, _p_f64), h_path=_ptr(r.h_path, _p_f64),
+        shape_npts=_ptr(r.shape_npts, _p_i32), shape_x=_ptr(r.shape_x, _p_f64),
+        shape_y=_ptr(r.shape_y, _p_f64))
+
+
+_LIB: Optional[C.CDLL] = None
+
+
+def load_library(path: str = LIB_PATH) -> C.CDLL:
+    """dlopen the C-ABI library and declare every prototype.  Raises if absent."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "There is no CPU fallback for the optimizer.")
+    lib = C.CDLL(path)
+    H = C.c_void_p
+    lib.pdmpc_create.argtypes = [C.c_int, C.POINTER(H)]
+    lib.pdmpc_create.restype = C.c_int
+    lib.pdmpc_destroy.argtypes = [H]
+    lib.pdmpc_destroy.restype = C.c_int
+    lib.pdmpc_last_error.argtypes = [H]
+    lib.pdmpc_last_error.restype = C.c_char_p
+    lib.pdmpc_abi_version.argtypes = []
+    lib.pdmpc_abi_version.restype = C.c_int
+    lib.pdmpc_set_node_capacity.argtypes = [H, C.c_int32]
+    lib.pdmpc_set_node_capacity.restype = C.c_int
+    lib.pdmpc_upload_mpa.argtypes = [H, C.POINTER(MpaDesc)]
+    lib.pdmpc_upload_mpa.restype = C.c_int
+    lib.pdmpc_plan_batch.argtypes = [H, C.POINTER(BatchIn), C.POINTER(BatchOut)]
+    lib.pdmpc_plan_batch.restype = C.c_int
+    lib.pdmpc_stage_batch.argtypes = [H, C.POINTER(BatchIn)]
+    lib.pdmpc_stage_batch.restype = C.c_int
+    lib.pdmpc_run_staged.argtypes = [H]
+    lib.pdmpc_run_staged.restype = C.c_int
+    lib.pdmpc_sync.argtypes = [H]
+    lib.pdmpc_sync.restype = C.c_int
+    lib.pdmpc_fetch_staged.argtypes = [H, C.POINTER(BatchOut)]
+    lib.pdmpc_fetch_staged.restype = C.c_int
+    lib.pdmpc_get_stats.argtypes = [H, C.POINTER(Stats)]
+    lib.pdmpc_get_stats.restype = C.c_int
+    lib.pdmpc_stream.argtypes = [H]
+    lib.pdmpc_stream.restype = C.c_void_p
+    _LIB = lib
+    return lib
+
+
+class PdmpcError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"pdmpc status {code}: {msg}")
+        self.code = code
+
+
+class Planner:
+    """Owns one pdmpc_handle (one CUDA device, one stream)."""
+
+    def __init__(self, device_id: int = 0):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        rc = self.lib.pdmpc_create(device_id, C.byref(self.h))
+        if rc != PDMPC_OK:
+            msg = self.lib.pdmpc_last_error(None)
+            raise PdmpcError(rc, (msg or b"pdmpc_create failed").decode())
+        self._mpa_keep = None
+        self._mpa = None
+        self._staged_n = 0
+        self._staged_Hp = 0
+
+    def _check(self, rc: int):
+        if rc != PDMPC_OK:
+            raise PdmpcError(rc, (self.lib.pdmpc_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if self.h:
+            self.lib.pdmpc_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_node_capacity(self, n: int):
+        self._check(self.lib.pdmpc_set_node_capacity(self.h, int(n)))
+
+    def upload_mpa(self, mpa: MotionPrimitiveAutomaton):
+        d, keep = mpa_desc(mpa)
+        self._check(self.lib.pdmpc_upload_mpa(self.h, C.byref(d)))
+        self._mpa_keep = keep
+        self._mpa = mpa
+
+    def plan_batch(self, b: SearchBatch, raise_on_search_error: bool = True) -> BatchResult:
+        r = BatchResult.empty(b.n, b.Hp)
+        bi, bo = batch_in(b), batch_out(r)
+        self._check(self.lib.pdmpc_plan_batch(self.h, C.byref(bi), C.byref(bo)))
+        if raise_on_search_error and b.n and int(r.status.max()) != PDMPC_OK:
+            bad = int(np.flatnonzero(r.status != PDMPC_OK)[0])
+            raise PdmpcError(int(r.status[bad]), f"search {bad} failed")
+        return r
+
+    def stage(self, b: SearchBatch):
+        bi = batch_in(b)
+        self._check(self.lib.pdmpc_stage_batch(self.h, C.byref(bi)))
+        self._staged_n, self._staged_Hp = b.n, b.Hp
+
+    def run_staged(self):
+        self._check(self.lib.pdmpc_run_staged(self.h))
+
+    def sync(self):
+        self._check(self.lib.pdmpc_sync(self.h))
+
+    def fetch(self) -> BatchResult:
+        r = BatchResult.empty(self._staged_n, self._staged_Hp)
+        bo = batch_out(r)
+        self._check(self.lib.pdmpc_fetch_staged(self.h, C.byref(bo)))
+        return r
+
+    def stats(self) -> Stats:
+        s = Stats()
+        self._check(self.lib.pdmpc_get_stats(self.h, C.byref(s)))
+        return s
+
+    def stream(self) -> int:
+        return int(self.lib.pdmpc_stream(self.h) or 0)

@@ -1,0 +1,562 @@
+// pdmpc_capi.cu — host side of the C ABI declared in include/pdmpc_b200.h.
+//
+// Stages the MPA tables and one batch of searches in HBM as SoA/CSR arrays,
+// launches the persistent search kernel (pdmpc_kernels.cuh) on the handle's
+// stream and copies the results back.  No CPU fallback exists: every entry
+// point fails with PDMPC_ERR_CUDA when the device is unusable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "pdmpc_kernels.cuh"
+
+using namespace pdmpc;
+
+namespace {
+
+constexpr int kHeapSmem = 256;  // heap entries kept in shared memory per CTA
+
+struct DBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+}  // namespace
+
+struct pdmpc_handle {
+    int device = 0;
+    int num_sms = 0;
+    int ctas_per_sm = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};   // 0/1 h2d, 2/3 kernel, 4/5 d2h
+    std::string err;
+
+    // MPA
+    bool has_mpa = false;
+    MpaDev mpa{};
+    DBuf m_succ_ptr, m_succ_trim, m_succ_edge, m_edge_of, m_dx, m_dy, m_dyaw, m_npts, m_ax, m_ay;
+    int full_tree_nodes = 0;
+    int user_node_cap = 0;
+
+    // staged batch
+    bool staged = false;
+    BatchDev batch{};
+    int n_polys = 0, n_verts = 0, n_lane = 0;
+    DBuf b_x0, b_y0, b_yaw0, b_trim0, b_refx, b_refy, b_vref, b_slot, b_poly, b_vx, b_vy, b_plx, b_ply,
+        b_lane, b_lx, b_ly, b_llx, b_lly;
+
+    // outputs
+    OutDev out{};
+    DBuf o_status, o_exh, o_nexp, o_npops, o_hash, o_trims, o_path, o_ypred, o_g, o_h, o_snp, o_sx, o_sy,
+        o_counters, work_counter;
+
+    // arena
+    ArenaDev arena{};
+    DBuf a_a, a_b, a_hf, a_hid;
+    int arena_slots = 0;
+
+    // trace (debug / parity tests)
+    DBuf t_ids, t_n;
+
+    pdmpc_stats stats{};
+    bool timing_pending_h2d = false, timing_pending_kernel = false, timing_pending_d2h = false;
+};
+
+static thread_local std::string g_create_error;
+
+static int fail(pdmpc_handle *h, int code, const std::string &msg) {
+    if (h) h->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+#define CU_TRY(h, expr)                                                                          \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess)                                                                   \
+            return fail(h, PDMPC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+extern "C" {
+
+int pdmpc_abi_version(void) { return PDMPC_ABI_VERSION; }
+
+const char *pdmpc_last_error(const pdmpc_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int pdmpc_create(int device_id, pdmpc_handle **out) {
+    if (!out) return fail(nullptr, PDMPC_ERR_BAD_INPUT, "pdmpc_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, PDMPC_ERR_CUDA,
+                    std::string("pdmpc_create: no CUDA device (") + cudaGetErrorString(e) +
+                        "); the optimizer has no CPU fallback");
+    if (device_id < 0 || device_id >= count)
+        return fail(nullptr, PDMPC_ERR_CUDA, "pdmpc_create: device id out of range");
+    pdmpc_handle *h = new (std::nothrow) pdmpc_handle();
+    if (!h) return fail(nullptr, PDMPC_ERR_ALLOC, "pdmpc_create: out of host memory");
+    h->device = device_id;
+    if ((e = cudaSetDevice(device_id)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        std::string msg = std::string("pdmpc_create: ") + cudaGetErrorString(e);
+        delete h;
+        return fail(nullptr, PDMPC_ERR_CUDA, msg);
+    }
+    for (auto &ev : h->ev) cudaEventCreate(&ev);
+    cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device_id);
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, search_kernel<kHeapSmem>, kWarp, 0);
+    if (e != cudaSuccess || occ < 1) {
+        std::string msg = std::string("pdmpc_create: search kernel is not launchable on this device (") +
+                          cudaGetErrorString(e) + "); built for sm_100a";
+        cudaStreamDestroy(h->stream);
+        delete h;
+        return fail(nullptr, PDMPC_ERR_CUDA, msg);
+    }
+    h->ctas_per_sm = occ;
+    *out = h;
+    return PDMPC_OK;
+}
+
+int pdmpc_destroy(pdmpc_handle *h) {
+    if (!h) return PDMPC_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    DBuf *bufs[] = {&h->m_succ_ptr, &h->m_succ_trim, &h->m_succ_edge, &h->m_edge_of, &h->m_dx, &h->m_dy,
+                    &h->m_dyaw, &h->m_npts, &h->m_ax, &h->m_ay, &h->b_x0, &h->b_y0, &h->b_yaw0, &h->b_trim0,
+                    &h->b_refx, &h->b_refy, &h->b_vref, &h->b_slot, &h->b_poly, &h->b_vx, &h->b_vy,
+                    &h->b_plx, &h->b_ply, &h->b_lane, &h->b_lx, &h->b_ly, &h->b_llx, &h->b_lly,
+                    &h->o_status, &h->o_exh, &h->o_nexp, &h->o_npops, &h->o_hash, &h->o_trims, &h->o_path,
+                    &h->o_ypred, &h->o_g, &h->o_h, &h->o_snp, &h->o_sx, &h->o_sy, &h->o_counters,
+                    &h->work_counter, &h->a_a, &h->a_b, &h->a_hf, &h->a_hid, &h->t_ids, &h->t_n};
+    for (DBuf *b : bufs) b->release();
+    for (auto &ev : h->ev)
+        if (ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return PDMPC_OK;
+}
+
+void *pdmpc_stream(pdmpc_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+int pdmpc_host_alloc(void **p, size_t bytes) {
+    if (!p) return PDMPC_ERR_BAD_INPUT;
+    return cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? PDMPC_OK : PDMPC_ERR_ALLOC;
+}
+int pdmpc_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+    return PDMPC_OK;
+}
+
+int pdmpc_set_node_capacity(pdmpc_handle *h, int32_t cap) {
+    if (!h) return PDMPC_ERR_BAD_INPUT;
+    if (cap != 0 && cap < 64) return fail(h, PDMPC_ERR_BAD_INPUT, "node capacity must be 0 (default) or >= 64");
+    h->user_node_cap = cap;
+    return PDMPC_OK;
+}
+
+}  // extern "C"
+
+template <class T>
+static int upload(pdmpc_handle *h, DBuf &buf, const T *src, size_t count) {
+    CU_TRY(h, buf.reserve(std::max<size_t>(count, 1) * sizeof(T)));
+    if (count) CU_TRY(h, cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    h->stats.h2d_bytes += (int64_t)(count * sizeof(T));
+    return PDMPC_OK;
+}
+#define UP(h, buf, src, count)                         \
+    do {                                               \
+        int _rc = upload(h, buf, src, (size_t)(count)); \
+        if (_rc != PDMPC_OK) return _rc;               \
+    } while (0)
+
+template <class T>
+static int download(pdmpc_handle *h, T *dst, const DBuf &buf, size_t count) {
+    if (!dst || !count) return PDMPC_OK;
+    CU_TRY(h, cudaMemcpyAsync(dst, buf.p, count * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+    h->stats.d2h_bytes += (int64_t)(count * sizeof(T));
+    return PDMPC_OK;
+}
+
+extern "C" {
+
+int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *d) {
+    if (!h) return PDMPC_ERR_BAD_INPUT;
+    if (!d || !d->transition || !d->edge_from || !d->edge_to || !d->edge_dx || !d->edge_dy || !d->edge_dyaw ||
+        !d->area_npts || !d->area_x || !d->area_y)
+        return fail(h, PDMPC_ERR_BAD_INPUT, "upload_mpa: NULL table pointer");
+    const int nT = d->n_trims, Hp = d->Hp, nE = d->n_edges;
+    if (nT < 1 || nT > PDMPC_MAX_TRIMS || Hp < 1 || Hp > PDMPC_MAX_HP || nE < 1 || nE > 32767)
+        return fail(h, PDMPC_ERR_BAD_INPUT, "upload_mpa: n_trims/Hp/n_edges out of range");
+    CU_TRY(h, cudaSetDevice(h->device));
+    std::vector<int16_t> edge_of((size_t)nT * nT, -1);
+    for (int e = 0; e < nE; ++e) {
+        int f = d->edge_from[e], t = d->edge_to[e];
+        if (f < 1 || f > nT || t < 1 || t > nT) return fail(h, PDMPC_ERR_BAD_INPUT, "upload_mpa: edge trim out of range");
+        edge_of[(size_t)(f - 1) * nT + (t - 1)] = (int16_t)e;
+        for (int k = 0; k < 3; ++k) {
+            int np = d->area_npts[e * 3 + k];
+            if (np < 2 || np > PDMPC_AREA_STRIDE) return fail(h, PDMPC_ERR_BAD_INPUT, "upload_mpa: area_npts out of range");
+        }
+    }
+    // successor lists: find(transition_matrix_single(t,:,k)) ascending (expand_node.m:18)
+    std::vector<int> succ_ptr((size_t)Hp * nT + 1, 0);
+    std::vector<int16_t> succ_trim, succ_edge;
+    for (int k = 0; k < Hp; ++k)
+        for (int t = 0; t < nT; ++t) {
+            const uint8_t *row = d->transition + ((size_t)k * nT + t) * nT;
+            for (int j = 0; j < nT; ++j)
+                if (row[j]) {
+                    int e = edge_of[(size_t)t * nT + j];
+                    if (e < 0) return fail(h, PDMPC_ERR_BAD_INPUT, "upload_mpa: transition without maneuver");
+                    succ_trim.push_back((int16_t)(j + 1));
+                    succ_edge.push_back((int16_t)e);
+                }
+            succ_ptr[(size_t)k * nT + t + 1] = (int)succ_trim.size();
+        }
+    // capacity bound: nodes of the full tree from the worst start trim
+    double worst = 1;
+    for (int t0 = 0; t0 < nT; ++t0) {
+        std::vector<double> cnt(nT, 0.0), nxt(nT);
+        cnt[t0] = 1;
+        double total = 1;
+        for (int k = 0; k < Hp; ++k) {
+            std::fill(nxt.begin(), nxt.end(), 0.0);
+            for (int t = 0; t < nT; ++t)
+                if (cnt[t] > 0) {
+                    const uint8_t *row = d->transition + ((size_t)k * nT + t) * nT;
+                    for (int j = 0; j < nT; ++j)
+                        if (row[j]) nxt[j] += cnt[t];
+                }
+            cnt.swap(nxt);
+            for (double c : cnt) total += c;
+        }
+        worst = std::max(worst, total);
+    }
+    h->full_tree_nodes = (int)std::min(worst, (double)(1 << 30));
+
+    int64_t keep = h->stats.h2d_bytes;
+    UP(h, h->m_succ_ptr, succ_ptr.data(), succ_ptr.size());
+    UP(h, h->m_succ_trim, succ_trim.data(), succ_trim.size());
+    UP(h, h->m_succ_edge, succ_edge.data(), succ_edge.size());
+    UP(h, h->m_edge_of, edge_of.data(), edge_of.size());
+    UP(h, h->m_dx, d->edge_dx, nE);
+    UP(h, h->m_dy, d->edge_dy, nE);
+    UP(h, h->m_dyaw, d->edge_dyaw, nE);
+    UP(h, h->m_npts, d->area_npts, nE * 3);
+    UP(h, h->m_ax, d->area_x, (size_t)nE * 3 * PDMPC_AREA_STRIDE);
+    UP(h, h->m_ay, d->area_y, (size_t)nE * 3 * PDMPC_AREA_STRIDE);
+    CU_TRY(h, cudaStreamSynchronize(h->stream));   // host vectors go out of scope
+    h->stats.h2d_bytes = keep;
+    MpaDev &m = h->mpa;
+    m.nT = nT; m.Hp = Hp; m.nE = nE;
+    m.succ_ptr = h->m_succ_ptr.as<int>();
+    m.succ_trim = h->m_succ_trim.as<int16_t>();
+    m.succ_edge = h->m_succ_edge.as<int16_t>();
+    m.edge_of = h->m_edge_of.as<int16_t>();
+    m.edge_dx = h->m_dx.as<double>(); m.edge_dy = h->m_dy.as<double>(); m.edge_dyaw = h->m_dyaw.as<double>();
+    m.area_npts = h->m_npts.as<int>();
+    m.area_x = h->m_ax.as<double>(); m.area_y = h->m_ay.as<double>();
+    h->has_mpa = true;
+    h->staged = false;
+    return PDMPC_OK;
+}
+
+static int validate_batch(pdmpc_handle *h, const pdmpc_batch_in *in) {
+    const int n = in->n_searches, Hp = h->mpa.Hp, nT = h->mpa.nT;
+    if (n < 0) return fail(h, PDMPC_ERR_BAD_INPUT, "plan: n_searches < 0");
+    if (in->checker != PDMPC_CHECKER_SAT && in->checker != PDMPC_CHECKER_INTERX)
+        return fail(h, PDMPC_ERR_BAD_INPUT, "plan: unknown checker");
+    if (!(in->dt_seconds > 0)) return fail(h, PDMPC_ERR_BAD_INPUT, "plan: dt_seconds must be > 0");
+    if (n == 0) return PDMPC_OK;
+    if (!in->x0 || !in->y0 || !in->yaw0 || !in->trim0 || !in->ref_x || !in->ref_y || !in->v_ref ||
+        !in->slot_ptr || !in->poly_ptr || !in->lane_ptr)
+        return fail(h, PDMPC_ERR_BAD_INPUT, "plan: NULL input pointer");
+    for (int i = 0; i < n; ++i)
+        if (in->trim0[i] < 1 || in->trim0[i] > nT) return fail(h, PDMPC_ERR_BAD_INPUT, "plan: trim0 out of range");
+    const size_t ns = (size_t)n * (Hp + 1);
+    if (in->slot_ptr[0] != 0 || in->poly_ptr[0] != 0 || in->lane_ptr[0] != 0)
+        return fail(h, PDMPC_ERR_BAD_INPUT, "plan: CSR offsets must start at 0");
+    for (size_t s = 0; s < ns; ++s)
+        if (in->slot_ptr[s + 1] < in->slot_ptr[s]) return fail(h, PDMPC_ERR_BAD_INPUT, "plan: slot_ptr not monotone");
+    const int np = in->slot_ptr[ns];
+    for (int p = 0; p < np; ++p) {
+        const int v0 = in->poly_ptr[p], v1 = in->poly_ptr[p + 1];
+        if (v1 - v0 < 2) return fail(h, PDMPC_ERR_BAD_INPUT, "plan: obstacle polygon with fewer than 2 vertices");
+        if (!in->vert_x || !in->vert_y) return fail(h, PDMPC_ERR_BAD_INPUT, "plan: NULL vertex arrays");
+        // vectorize_all_obstacles.m:71-76 check_closeness (asserted by the reference for InterX)
+        if (in->checker == PDMPC_CHECKER_INTERX &&
+            !(in->vert_x[v0] == in->vert_x[v1 - 1] && in->vert_y[v0] == in->vert_y[v1 - 1]))
+            return fail(h, PDMPC_ERR_BAD_INPUT, "plan: obstacle polygon is not closed");
+    }
+    for (int i = 0; i < 2 * n; ++i)
+        if (in->lane_ptr[i + 1] < in->lane_ptr[i]) return fail(h, PDMPC_ERR_BAD_INPUT, "plan: lane_ptr not monotone");
+    if (in->lane_ptr[2 * n] > 0 && (!in->lane_x || !in->lane_y))
+        return fail(h, PDMPC_ERR_BAD_INPUT, "plan: NULL lanelet arrays");
+    return PDMPC_OK;
+}
+
+static int ensure_outputs(pdmpc_handle *h, int n) {
+    const int Hp = h->mpa.Hp;
+    const size_t n1 = std::max(n, 1);
+    CU_TRY(h, h->o_status.reserve(n1 * sizeof(int)));
+    CU_TRY(h, h->o_exh.reserve(n1));
+    CU_TRY(h, h->o_nexp.reserve(n1 * sizeof(int)));
+    CU_TRY(h, h->o_npops.reserve(n1 * sizeof(int)));
+    CU_TRY(h, h->o_hash.reserve(n1 * sizeof(uint64_t)));
+    CU_TRY(h, h->o_trims.reserve(n1 * (Hp + 1) * sizeof(int)));
+    CU_TRY(h, h->o_path.reserve(n1 * (Hp + 1) * sizeof(int)));
+    CU_TRY(h, h->o_ypred.reserve(n1 * Hp * 3 * sizeof(double)));
+    CU_TRY(h, h->o_g.reserve(n1 * (Hp + 1) * sizeof(double)));
+    CU_TRY(h, h->o_h.reserve(n1 * (Hp + 1) * sizeof(double)));
+    CU_TRY(h, h->o_snp.reserve(n1 * Hp * sizeof(int)));
+    CU_TRY(h, h->o_sx.reserve(n1 * Hp * PDMPC_AREA_STRIDE * sizeof(double)));
+    CU_TRY(h, h->o_sy.reserve(n1 * Hp * PDMPC_AREA_STRIDE * sizeof(double)));
+    CU_TRY(h, h->o_counters.reserve(4 * sizeof(unsigned long long)));
+    CU_TRY(h, h->work_counter.reserve(sizeof(unsigned)));
+    OutDev &o = h->out;
+    o.status = h->o_status.as<int>();
+    o.is_exhausted = h->o_exh.as<uint8_t>();
+    o.n_expanded = h->o_nexp.as<int>();
+    o.n_pops = h->o_npops.as<int>();
+    o.pop_hash = h->o_hash.as<unsigned long long>();
+    o.trims = h->o_trims.as<int>();
+    o.tree_path = h->o_path.as<int>();
+    o.y_predicted = h->o_ypred.as<double>();
+    o.g_path = h->o_g.as<double>();
+    o.h_path = h->o_h.as<double>();
+    o.shape_npts = h->o_snp.as<int>();
+    o.shape_x = h->o_sx.as<double>();
+    o.shape_y = h->o_sy.as<double>();
+    o.counters = h->o_counters.as<unsigned long long>();
+    return PDMPC_OK;
+}
+
+int pdmpc_stage_batch(pdmpc_handle *h, const pdmpc_batch_in *in) {
+    if (!h) return PDMPC_ERR_BAD_INPUT;
+    if (!h->has_mpa) return fail(h, PDMPC_ERR_NO_MPA, "plan: call pdmpc_upload_mpa first");
+    if (!in) return fail(h, PDMPC_ERR_BAD_INPUT, "plan: batch is NULL");
+    int rc = validate_batch(h, in);
+    if (rc != PDMPC_OK) return rc;
+    CU_TRY(h, cudaSetDevice(h->device));
+    const int n = in->n_searches, Hp = h->mpa.Hp;
+    const size_t ns = (size_t)n * (Hp + 1);
+    const int np = n ? in->slot_ptr[ns] : 0;
+    const int nv = np ? in->poly_ptr[np] : 0;
+    const int nl = n ? in->lane_ptr[2 * n] : 0;
+    h->staged = false;
+    h->stats.h2d_bytes = 0;
+    CU_TRY(h, cudaEventRecord(h->ev[0], h->stream));
+    static const int zero1[1] = {0};
+    UP(h, h->b_x0, in->x0, n);
+    UP(h, h->b_y0, in->y0, n);
+    UP(h, h->b_yaw0, in->yaw0, n);
+    UP(h, h->b_trim0, in->trim0, n);
+    UP(h, h->b_refx, in->ref_x, (size_t)n * Hp);
+    UP(h, h->b_refy, in->ref_y, (size_t)n * Hp);
+    UP(h, h->b_vref, in->v_ref, (size_t)n * Hp);
+    UP(h, h->b_slot, n ? in->slot_ptr : zero1, ns + 1);
+    UP(h, h->b_poly, n ? in->poly_ptr : zero1, (size_t)np + 1);
+    UP(h, h->b_vx, in->vert_x, nv);
+    UP(h, h->b_vy, in->vert_y, nv);
+    UP(h, h->b_lane, n ? in->lane_ptr : zero1, (size_t)2 * n + 1);
+    UP(h, h->b_lx, in->lane_x, nl);
+    UP(h, h->b_ly, in->lane_y, nl);
+    CU_TRY(h, cudaEventRecord(h->ev[1], h->stream));
+    h->timing_pending_h2d = true;
+
+    BatchDev &b = h->batch;
+    b.n = n; b.checker = in->checker; b.dt = in->dt_seconds;
+    b.x0 = h->b_x0.as<double>(); b.y0 = h->b_y0.as<double>(); b.yaw0 = h->b_yaw0.as<double>();
+    b.trim0 = h->b_trim0.as<int>();
+    b.ref_x = h->b_refx.as<double>(); b.ref_y = h->b_refy.as<double>(); b.v_ref = h->b_vref.as<double>();
+    b.slot_ptr = h->b_slot.as<int>(); b.poly_ptr = h->b_poly.as<int>();
+    b.vert_x = h->b_vx.as<double>(); b.vert_y = h->b_vy.as<double>();
+    b.lane_ptr = h->b_lane.as<int>(); b.lane_x = h->b_lx.as<double>(); b.lane_y = h->b_ly.as<double>();
+    b.pl_x = b.pl_y = b.ll_x = b.ll_y = nullptr;
+    h->stats.kernel_launches = 0;
+    if (in->checker == PDMPC_CHECKER_INTERX) {
+        // NaN-separated polylines (vectorize_all_obstacles.m) built on the device
+        CU_TRY(h, h->b_plx.reserve(((size_t)nv + np + 1) * sizeof(double)));
+        CU_TRY(h, h->b_ply.reserve(((size_t)nv + np + 1) * sizeof(double)));
+        CU_TRY(h, h->b_llx.reserve(((size_t)nl + 2 * n + 1) * sizeof(double)));
+        CU_TRY(h, h->b_lly.reserve(((size_t)nl + 2 * n + 1) * sizeof(double)));
+        if (np) {
+            build_polyline_kernel<<<(np + 127) / 128, 128, 0, h->stream>>>(
+                np, b.poly_ptr, b.vert_x, b.vert_y, h->b_plx.as<double>(), h->b_ply.as<double>());
+            h->stats.kernel_launches++;
+        }
+        if (n) {
+            build_polyline_kernel<<<(2 * n + 127) / 128, 128, 0, h->stream>>>(
+                2 * n, b.lane_ptr, b.lane_x, b.lane_y, h->b_llx.as<double>(), h->b_lly.as<double>());
+            h->stats.kernel_launches++;
+        }
+        CU_TRY(h, cudaGetLastError());
+        b.pl_x = h->b_plx.as<double>(); b.pl_y = h->b_ply.as<double>();
+        b.ll_x = h->b_llx.as<double>(); b.ll_y = h->b_lly.as<double>();
+    }
+    h->n_polys = np; h->n_verts = nv; h->n_lane = nl;
+    rc = ensure_outputs(h, n);
+    if (rc != PDMPC_OK) return rc;
+    // Source buffers are caller-owned pageable/pinned memory: make the staging
+    // copies complete before returning so the caller may reuse them.
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    h->staged = true;
+    return PDMPC_OK;
+}
+
+static int ensure_arena(pdmpc_handle *h, int slots) {
+    int cap = h->user_node_cap ? h->user_node_cap : std::min(h->full_tree_nodes + 8, 1 << 20);
+    cap = std::max(cap, 64);
+    if (slots <= h->arena_slots && cap == h->arena.cap) return PDMPC_OK;
+    slots = std::max(slots, h->arena_slots);
+    const size_t tot = (size_t)slots * cap;
+    CU_TRY(h, h->a_a.reserve(tot * sizeof(NodeA)));
+    CU_TRY(h, h->a_b.reserve(tot * sizeof(NodeB)));
+    CU_TRY(h, h->a_hf.reserve(tot * sizeof(double)));
+    CU_TRY(h, h->a_hid.reserve(tot * sizeof(unsigned)));
+    h->arena.a = h->a_a.as<NodeA>();
+    h->arena.b = h->a_b.as<NodeB>();
+    h->arena.heap_f = h->a_hf.as<double>();
+    h->arena.heap_id = h->a_hid.as<unsigned>();
+    h->arena.cap = cap;
+    h->arena_slots = slots;
+    return PDMPC_OK;
+}
+
+static int launch_search(pdmpc_handle *h, const TraceDev &tr) {
+    const int n = h->batch.n;
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaMemsetAsync(h->o_counters.p, 0, 4 * sizeof(unsigned long long), h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->work_counter.p, 0, sizeof(unsigned), h->stream));
+    if (n == 0) return PDMPC_OK;
+    const int grid = std::min(n, h->num_sms * h->ctas_per_sm);
+    int rc = ensure_arena(h, grid);
+    if (rc != PDMPC_OK) return rc;
+    CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
+    search_kernel<kHeapSmem><<<grid, kWarp, 0, h->stream>>>(h->mpa, h->batch, h->out, h->arena,
+                                                           h->work_counter.as<unsigned>(), tr);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
+    h->timing_pending_kernel = true;
+    h->stats.kernel_launches++;
+    return PDMPC_OK;
+}
+
+int pdmpc_run_staged(pdmpc_handle *h) {
+    if (!h) return PDMPC_ERR_BAD_INPUT;
+    if (!h->staged) return fail(h, PDMPC_ERR_BAD_INPUT, "run_staged: no staged batch");
+    TraceDev tr{-1, nullptr, 0, nullptr};
+    return launch_search(h, tr);
+}
+
+int pdmpc_sync(pdmpc_handle *h) {
+    if (!h) return PDMPC_ERR_BAD_INPUT;
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return PDMPC_OK;
+}
+
+#define DOWN(h, dst, buf, count)                         \
+    do {                                                 \
+        int _rc = download(h, dst, buf, (size_t)(count)); \
+        if (_rc != PDMPC_OK) return _rc;                 \
+    } while (0)
+
+int pdmpc_fetch_staged(pdmpc_handle *h, pdmpc_batch_out *out) {
+    if (!h) return PDMPC_ERR_BAD_INPUT;
+    if (!h->staged) return fail(h, PDMPC_ERR_BAD_INPUT, "fetch: no staged batch");
+    if (!out || !out->status) return fail(h, PDMPC_ERR_BAD_INPUT, "fetch: out/status is NULL");
+    CU_TRY(h, cudaSetDevice(h->device));
+    const size_t n = (size_t)h->batch.n, Hp = (size_t)h->mpa.Hp;
+    h->stats.d2h_bytes = 0;
+    CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
+    DOWN(h, out->status, h->o_status, n);
+    DOWN(h, out->is_exhausted, h->o_exh, n);
+    DOWN(h, out->n_expanded, h->o_nexp, n);
+    DOWN(h, out->n_pops, h->o_npops, n);
+    DOWN(h, out->pop_hash, h->o_hash, n);
+    DOWN(h, out->trims, h->o_trims, n * (Hp + 1));
+    DOWN(h, out->tree_path, h->o_path, n * (Hp + 1));
+    DOWN(h, out->y_predicted, h->o_ypred, n * Hp * 3);
+    DOWN(h, out->g_path, h->o_g, n * (Hp + 1));
+    DOWN(h, out->h_path, h->o_h, n * (Hp + 1));
+    DOWN(h, out->shape_npts, h->o_snp, n * Hp);
+    DOWN(h, out->shape_x, h->o_sx, n * Hp * PDMPC_AREA_STRIDE);
+    DOWN(h, out->shape_y, h->o_sy, n * Hp * PDMPC_AREA_STRIDE);
+    unsigned long long counters[4] = {0, 0, 0, 0};
+    CU_TRY(h, cudaMemcpyAsync(counters, h->o_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    h->timing_pending_d2h = true;
+    h->stats.total_pops = (int64_t)counters[0];
+    h->stats.total_nodes = (int64_t)counters[1];
+    h->stats.total_obstacle_cols = (int64_t)counters[2];
+    return PDMPC_OK;
+}
+
+int pdmpc_plan_batch(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc_batch_out *out) {
+    int rc = pdmpc_stage_batch(h, in);
+    if (rc != PDMPC_OK) return rc;
+    rc = pdmpc_run_staged(h);
+    if (rc != PDMPC_OK) return rc;
+    return pdmpc_fetch_staged(h, out);
+}
+
+int pdmpc_trace_staged(pdmpc_handle *h, int32_t search, int64_t *ids, int64_t cap, int64_t *n_out) {
+    if (!h) return PDMPC_ERR_BAD_INPUT;
+    if (!h->staged) return fail(h, PDMPC_ERR_BAD_INPUT, "trace: no staged batch");
+    if (search < 0 || search >= h->batch.n || !ids || cap < 1 || !n_out)
+        return fail(h, PDMPC_ERR_BAD_INPUT, "trace: bad arguments");
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, h->t_ids.reserve((size_t)cap * sizeof(long long)));
+    CU_TRY(h, h->t_n.reserve(sizeof(long long)));
+    CU_TRY(h, cudaMemsetAsync(h->t_n.p, 0, sizeof(long long), h->stream));
+    TraceDev tr{search, h->t_ids.as<long long>(), (long long)cap, h->t_n.as<long long>()};
+    int rc = launch_search(h, tr);
+    if (rc != PDMPC_OK) return rc;
+    long long n = 0;
+    CU_TRY(h, cudaMemcpyAsync(&n, h->t_n.p, sizeof(n), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    const long long m = std::min<long long>(n, cap);
+    if (m > 0) CU_TRY(h, cudaMemcpy(ids, h->t_ids.p, (size_t)m * sizeof(long long), cudaMemcpyDeviceToHost));
+    *n_out = n;
+    return PDMPC_OK;
+}
+
+int pdmpc_get_stats(pdmpc_handle *h, pdmpc_stats *out) {
+    if (!h || !out) return PDMPC_ERR_BAD_INPUT;
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    if (h->timing_pending_h2d && cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->stats.h2d_ms = ms;
+    if (h->timing_pending_kernel && cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) h->stats.kernel_ms = ms;
+    if (h->timing_pending_d2h && cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]) == cudaSuccess) h->stats.d2h_ms = ms;
+    *out = h->stats;
+    return PDMPC_OK;
+}
+
+}  // extern "C"

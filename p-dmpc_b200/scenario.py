@@ -1,0 +1,567 @@
+"""Synthetic scenario harness: produces the search records of the BASELINE configs.
+
+Host-side Python (numpy) stand-in for the parts of the reference that FEED the
+hot path and stay MATLAB in the drop-in (SURVEY.md §2 "caller" rows): scenario
+set-up, reference-trajectory sampling, predicted lanelet boundary, coupling,
+prioritisation, computation levels, obstacle assembly, closed loop with the
+perfect `Simulation` plant.  It exists so that tests and bench.py have inputs of
+the named shapes without MATLAB; it is NOT part of the accelerated path.
+
+Follows (reference file:line), with documented simplifications marked [dev]:
+  * circle scenario ............... scenarios/free_space/Circle.m:16-42
+  * road network ................... scenarios/road_network/Commonroad.m:5-48,
+                                     get_reference_lanelets_loop.m:24-154,
+                                     generate_reference_path_loop.m:1-46
+  * lanelet boundary per lanelet ... RoadDataCommonRoad.get_lanelet_boundary :262-290
+                                     [dev] merging/forking extensions (:292-388) omitted
+  * reference trajectory ........... hlc/controller/common/get_reference_trajectory.m:1-48,
+                                     sample_reference_trajectory.m:1-103,
+                                     get_arc_distance_to_endpoint.m
+  * predicted lanelets / boundary .. get_predicted_lanelets.m:1-63, get_lanelets_boundary.m:1-75
+  * coupling ....................... [dev] corridor-distance proxy for ReachableSetCoupler.m:5-54
+                                     (polyshape intersection areas are not available here)
+  * priorities ..................... ConstantPrioritizer.m:6-18, ColoringPrioritizer.m:11-153,
+                                     Prioritizer.directed_coupling_from_priorities :62-74
+  * computation levels ............. utility/kahn.m:1-24
+  * obstacle assembly .............. PrioritizedController.m:297-324,449-566
+                                     (sequential predecessors -> predicted areas;
+                                      successors at standstill -> static obstacle)
+  * plant .......................... plant/Simulation.m:86-117
+  * exhaustion fallback ............ [dev] local only: PrioritizedController.m:568-621,678-718
+                                     (standstill plan / previous plan shifted); graph-wide
+                                     fallback propagation (:623-676) omitted
+"""
+from __future__ import annotations
+
+import dataclasses
+import os
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+from .mpa import VEH_LENGTH, VEH_WIDTH, MotionPrimitiveAutomaton
+from .records import CHECKER_INTERX, CHECKER_SAT, BatchResult, IterationData, SearchBatch
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "lab_map.npz")
+
+# get_reference_lanelets_loop.m:24-37 (lanelet ids, 1-based)
+_LOOPS = {
+    1: [4, 6, 8, 60, 58, 56, 54, 80, 82, 84, 86, 34, 32, 30, 28, 2],
+    2: [1, 3, 23, 10, 12, 17, 43, 38, 36, 49, 29, 27],
+    3: [64, 62, 75, 55, 53, 79, 81, 101, 88, 90, 95, 69],
+    4: [40, 45, 97, 92, 94, 100, 83, 85, 33, 31, 48, 42],
+    5: [5, 7, 59, 57, 74, 68, 66, 71, 19, 14, 16, 22],
+    6: [41, 39, 20, 63, 61, 57, 55, 67, 65, 98, 37, 35, 31, 29],
+    7: [3, 5, 9, 11, 72, 91, 93, 81, 83, 87, 89, 46, 13, 15],
+}
+# path id -> (loop, starting lanelet): get_reference_lanelets_loop.m:39-127 (ids 1..41)
+_PATH_START = {}
+for _loop, _starts, _first in (
+        (1, [4, 8, 58, 54, 82, 86, 32, 28], 1), (2, [1, 10, 17, 38, 49], 9),
+        (3, [64, 75, 79, 88, 95], 14), (4, [42, 45, 92, 100, 33], 19),
+        (5, [22, 59, 68, 19, 14], 24), (6, [39, 61, 55, 65, 35, 29], 29),
+        (7, [15, 5, 11, 93, 83, 89], 35)):
+    for _i, _s in enumerate(_starts):
+        _PATH_START[_first + _i] = (_loop, _s)
+_PATH_START[41] = (5, 71)
+
+
+class RoadMap:
+    """Lanelet geometry + the per-lanelet boundaries the planner is constrained by."""
+
+    def __init__(self, path: str = _DATA):
+        z = np.load(path)
+        ptr = z["ptr"]
+        self.n = ptr.size - 1
+        self.lanelets = []   # [n_pts, 6]: rx ry lx ly cx cy  (LaneletInfo.m)
+        for i in range(self.n):
+            a, b = ptr[i], ptr[i + 1]
+            rx, ry, lx, ly = z["rx"][a:b], z["ry"][a:b], z["lx"][a:b], z["ly"][a:b]
+            self.lanelets.append(np.column_stack([rx, ry, lx, ly, 0.5 * (lx + rx), 0.5 * (ly + ry)]))
+        self.pred, self.succ = z["pred"], z["succ"]
+        adj_left, adj_right = z["adj_left"], z["adj_right"]
+        left_same, right_same = z["adj_left_same"], z["adj_right_same"]
+        # RoadDataCommonRoad.m:262-290: widen to the same-direction neighbour's outer bound
+        self.boundary = []
+        for i in range(self.n):
+            L = self.lanelets[i]
+            left = L[:, 2:4]
+            right = L[:, 0:2]
+            if adj_left[i] and left_same[i]:
+                left = self.lanelets[adj_left[i] - 1][:, 2:4]
+            elif adj_right[i] and right_same[i]:
+                right = self.lanelets[adj_right[i] - 1][:, 0:2]
+            self.boundary.append((np.ascontiguousarray(left), np.ascontiguousarray(right)))
+
+    def is_longitudinal(self, a: int, b: int) -> bool:
+        """a, b 1-based: one is the other's predecessor (loop closure test, Commonroad.m:28-35)."""
+        return bool(self.pred[a - 1, b - 1] or self.pred[b - 1, a - 1])
+
+
+_MAP: Optional[RoadMap] = None
+
+
+def road_map() -> RoadMap:
+    global _MAP
+    if _MAP is None:
+        _MAP = RoadMap()
+    return _MAP
+
+
+@dataclasses.dataclass
+class Vehicle:
+    """scenarios/Vehicle.m:5-18"""
+
+    x_start: float
+    y_start: float
+    yaw_start: float
+    reference_path: np.ndarray
+    reference_speed: float
+    lanelets_index: Optional[np.ndarray] = None
+    points_index: Optional[np.ndarray] = None
+    is_loop: bool = True
+
+
+@dataclasses.dataclass
+class Scenario:
+    kind: str                      # "circle" | "commonroad"
+    vehicles: List[Vehicle]
+    mpa: MotionPrimitiveAutomaton
+    checker: int
+    priority: str                  # "constant" | "coloring"
+    road: Optional[RoadMap] = None
+
+    @property
+    def amount(self) -> int:
+        return len(self.vehicles)
+
+
+def circle_scenario(mpa: MotionPrimitiveAutomaton, amount: int = 4) -> Scenario:
+    """Circle.m:16-42; SAT checker, constant priorities (Config.m:71-79, :24)."""
+    radius = 2.0
+    vehicles = []
+    ref_speed = float(mpa.get_straight_speeds_of_mpa().max())
+    for i in range(amount):
+        yaw = np.pi * 2 / amount * i
+        s, c = np.sin(yaw), np.cos(yaw)
+        xs = -c * radius + 2.25
+        ys = -s * radius + 2.0
+        path = np.array([[xs, ys], [xs + c * 2 * radius, ys + s * 2 * radius]])
+        vehicles.append(Vehicle(xs, ys, yaw, path, ref_speed, is_loop=False))
+    return Scenario("circle", vehicles, mpa, CHECKER_SAT, "constant")
+
+
+def reference_path_loop(path_id: int, road: RoadMap):
+    """get_reference_lanelets_loop.m:146-154 + generate_reference_path_loop.m:15-46."""
+    loop, start = _PATH_START[path_id]
+    seq = _LOOPS[loop]
+    k = seq.index(start)
+    lanelets_index = np.array(seq[k:] + seq[:k])
+    parts = [road.lanelets[i - 1][:, 4:6] for i in lanelets_index]
+    path = np.vstack(parts)
+    d = np.diff(path, axis=0).sum(axis=1)
+    redundant = np.concatenate([[False], np.abs(d) <= 1e-4])   # ismembertol(..., 0, 1e-4) [dev: abs tol]
+    reduced = path[~redundant]
+    n_cum = np.cumsum([p.shape[0] for p in parts])
+    red_cum = np.cumsum(redundant)
+    points_index = n_cum - red_cum[n_cum - 1]
+    return lanelets_index, reduced, points_index
+
+
+def calculate_yaw_first(path: np.ndarray) -> float:
+    """utility/calculate_yaw.m: yaw(1)"""
+    return float(np.arctan2(path[1, 1] - path[0, 1], path[1, 0] - path[0, 0]))
+
+
+def commonroad_scenario(mpa: MotionPrimitiveAutomaton, amount: int = 20, seed: int = 1,
+                        allow_shared_paths: bool = False) -> Scenario:
+    """Commonroad.m:5-48 with path ids drawn from 9..41 (Config.m:135-150).
+
+    [dev] MATLAB's randsample / mt19937ar streams are replaced by numpy PCG64(seed).
+    With ``allow_shared_paths`` (config 4, 40 vehicles) ids repeat and the second
+    vehicle of an id starts half a loop further along the same path.
+    """
+    road = road_map()
+    rng = np.random.Generator(np.random.PCG64(seed))
+    pool = np.arange(9, 42)
+    if amount <= pool.size and not allow_shared_paths:
+        ids = rng.choice(pool, size=amount, replace=False)
+        offs = np.zeros(amount)
+    else:
+        ids = np.concatenate([rng.permutation(pool) for _ in range((amount + pool.size - 1) // pool.size)])[:amount]
+        offs = (np.arange(amount) // pool.size) * 0.5
+    speeds = mpa.get_straight_speeds_of_mpa()
+    vehicles = []
+    for pid, off in zip(ids, offs):
+        lan_idx, path, pts_idx = reference_path_loop(int(pid), road)
+        is_loop = road.is_longitudinal(int(lan_idx[0]), int(lan_idx[-1]))
+        if off > 0:
+            seglen = np.hypot(*np.diff(path, axis=0).T)
+            cum = np.concatenate([[0], np.cumsum(seglen)])
+            j = int(np.searchsorted(cum, off * cum[-1]))
+            j = min(max(j, 1), path.shape[0] - 2)
+            x, y = path[j]
+            yaw = float(np.arctan2(path[j + 1, 1] - path[j - 1, 1], path[j + 1, 0] - path[j - 1, 0]))
+        else:
+            x, y = path[0]
+            yaw = calculate_yaw_first(path)
+        vehicles.append(Vehicle(float(x), float(y), yaw, path, float(speeds[rng.integers(speeds.size)]),
+                                lanelets_index=lan_idx, points_index=pts_idx, is_loop=is_loop))
+    return Scenario("commonroad", vehicles, mpa, CHECKER_INTERX, "coloring", road=road)
+
+
+# --------------------------------------------------------------------------- reference trajectory
+def _projection_2d(x1, y1, x2, y2, px, py):
+    dx, dy = x2 - x1, y2 - y1
+    lam = ((px - x1) * dx + (py - y1) * dy) / (dx * dx + dy * dy)
+    xp, yp = x1 + lam * dx, y1 + lam * dy
+    return xp, yp, lam
+
+
+def _closest_point(path: np.ndarray, x: float, y: float):
+    """get_arc_distance_to_endpoint.m: projected point and idx_next (1-based)."""
+    n = path.shape[0]
+    d2 = (path[:, 0] - x) ** 2 + (path[:, 1] - y) ** 2
+    ic = int(np.argmin(d2)) + 1
+    if ic == 1:
+        a, b = 1, 2
+    elif ic == n:
+        a, b = n - 1, n
+    else:
+        if d2[ic - 2] <= d2[ic]:
+            a, b = ic - 1, ic
+        else:
+            a, b = ic, ic + 1
+    xp, yp, lam = _projection_2d(path[a - 1, 0], path[a - 1, 1], path[b - 1, 0], path[b - 1, 1], x, y)
+    idx_next = ic
+    if (0 <= lam <= 0.5) or lam >= 1:
+        idx_next = ic + 1 if ic < n else 1
+    return xp, yp, max(2, idx_next)
+
+
+def sample_reference_trajectory(n_samples: int, path: np.ndarray, x: float, y: float, step_distances):
+    """sample_reference_trajectory.m:24-97 -> (points [n,2], points_index [n], current_point_index)."""
+    out = np.zeros((n_samples, 2))
+    out_idx = np.zeros(n_samples, dtype=np.int64)
+    xp, yp, point_index = _closest_point(path, x, y)
+    current_point_index = point_index
+    n_pts = path.shape[0]
+    cur = np.array([xp, yp])
+    is_loop = np.hypot(*(path[0] - path[-1])) < 1e-8
+    point_index_last = point_index - 1
+    if is_loop and point_index == n_pts:
+        point_index = 1
+
+    def unit(v):
+        return v / np.hypot(v[0], v[1])
+
+    for i in range(n_samples):
+        remaining = np.hypot(*(cur - path[point_index - 1]))
+        if remaining > step_distances[i] or point_index == n_pts:
+            while (path[point_index - 1, 0] == path[point_index_last - 1, 0]
+                   and path[point_index - 1, 1] == path[point_index_last - 1, 1] and point_index_last > 1):
+                point_index_last -= 1
+            cur = cur + step_distances[i] * unit(path[point_index - 1] - path[point_index_last - 1])
+        else:
+            reflength = remaining
+            while remaining < step_distances[i]:
+                reflength = remaining
+                cur = path[point_index - 1].copy()
+                point_index_last = point_index
+                point_index = min(point_index + 1, n_pts)
+                if is_loop and point_index == n_pts:
+                    point_index = 1
+                remaining = remaining + np.hypot(*(cur - path[point_index - 1]))
+            cur = cur + (step_distances[i] - reflength) * unit(path[point_index - 1] - path[point_index_last - 1])
+        out[i] = cur
+        out_idx[i] = point_index
+    return out, out_idx, current_point_index
+
+
+def get_reference_trajectory(mpa, veh: Vehicle, x, y, trim_current, dt):
+    """get_reference_trajectory.m:28-46"""
+    Hp = mpa.Hp
+    v_ref = np.ones(Hp) * veh.reference_speed
+    v_cur = mpa.trim_speed[trim_current - 1]
+    v_mid = (np.concatenate([[v_cur], v_ref[:-1]]) + v_ref) / 2
+    pts, idx, cur_idx = sample_reference_trajectory(Hp, veh.reference_path, x, y, v_mid * dt)
+    return pts, v_ref, idx, cur_idx
+
+
+def get_predicted_lanelets(veh: Vehicle, ref_idx: np.ndarray) -> np.ndarray:
+    """get_predicted_lanelets.m:34-62"""
+    n_total = veh.reference_path.shape[0]
+    add = ref_idx[-1] + 4
+    if add > n_total:
+        add -= n_total
+    idxs = np.concatenate([ref_idx, [add]])
+    lan = np.array([int((i > veh.points_index).sum()) + 1 for i in idxs])
+    _, first = np.unique(lan, return_index=True)
+    lan = lan[np.sort(first)]
+    if lan.size == 1:
+        nxt = lan[0] + 1
+        if nxt > veh.lanelets_index.size:
+            nxt = 1
+        lan = np.array([lan[0], nxt])
+    return veh.lanelets_index[lan - 1]
+
+
+def get_lanelets_boundary(predicted: np.ndarray, road: RoadMap, veh: Vehicle):
+    """get_lanelets_boundary.m:19-68 -> (left [2,nL], right [2,nR])"""
+    lefts = [road.boundary[i - 1][0][:-1] for i in predicted] + [road.boundary[predicted[-1] - 1][0][-1:]]
+    rights = [road.boundary[i - 1][1][:-1] for i in predicted] + [road.boundary[predicted[-1] - 1][1][-1:]]
+    pos = int(np.flatnonzero(veh.lanelets_index == predicted[0])[0])
+    if pos != 0:
+        pre = int(veh.lanelets_index[pos - 1])
+    elif veh.is_loop:
+        pre = int(veh.lanelets_index[-1])
+    else:
+        pre = 0
+    if pre:
+        pl, pr = road.boundary[pre - 1]
+        k = min(4, min(pr.shape[0] - 1, pl.shape[0] - 1))
+        lefts.insert(0, pl[-1 - k:-1])
+        rights.insert(0, pr[-1 - k:-1])
+    return np.ascontiguousarray(np.vstack(lefts).T), np.ascontiguousarray(np.vstack(rights).T)
+
+
+# --------------------------------------------------------------------------- coupling / priorities
+def occupied_area(x, y, yaw, offset=0.01) -> np.ndarray:
+    """get_occupied_areas.m:21-25 (normal_offset, closed 5-point rectangle)"""
+    xl = np.array([-1, -1, 1, 1, -1]) * (VEH_LENGTH / 2 + offset)
+    yl = np.array([-1, 1, 1, -1, -1]) * (VEH_WIDTH / 2 + offset)
+    c, s = np.cos(yaw), np.sin(yaw)
+    return np.vstack([c * xl - s * yl + x, s * xl + c * yl + y])
+
+
+def kahn(A: np.ndarray) -> np.ndarray:
+    """utility/kahn.m:1-24: computation level (1-based) of each vertex of a DAG."""
+    A = A.copy().astype(np.int64)
+    n = A.shape[0]
+    L = np.zeros(n, dtype=np.int64)
+    done = np.zeros(n, dtype=bool)
+    in_d = A.sum(axis=0)
+    level = 1
+    while not done.all():
+        src = (in_d == 0)
+        if not src.any():
+            raise ValueError("coupling graph is not a DAG")
+        L[src] = level
+        A[src, :] = 0
+        done |= src
+        in_d = A.sum(axis=0)
+        in_d[done] = 1
+        level += 1
+    return L
+
+
+def coloring_priorities(adjacency: np.ndarray) -> np.ndarray:
+    """ColoringPrioritizer.m:11-153 -> directed coupling (row = higher priority)."""
+    A = adjacency.astype(np.int64)
+    n = A.shape[0]
+    degree = A.sum(axis=0)
+    color = np.zeros(n, dtype=np.int64)
+    color[degree == 0] = 1
+    while (color == 0).any():
+        best, idx = -1, -1
+        for i in np.flatnonzero(color == 0):
+            d = np.unique(color[A[i] == 1])
+            d = int((d != 0).sum())
+            if d > best:
+                best, idx = d, i
+            if d == best and degree[i] > degree[idx]:
+                idx = i
+        used = set(np.unique(color[A[idx] == 1]).tolist())
+        c = 1
+        while c in used:
+            c += 1
+        color[idx] = c
+    used_col = np.unique(color)
+    levels = [np.flatnonzero(color == c) for c in used_col]
+    # order_topo :96-131: repeatedly take the level holding the highest-degree vertex
+    deg = A.sum(axis=0).astype(np.int64)
+    if deg.sum() == 0:
+        order = [0]
+    else:
+        order = []
+        while deg.sum() != 0:
+            max_idx = int(np.argmax(deg))   # first maximum, as the reference's strict '>' scan
+            lvl = next(j for j, m in enumerate(levels) if max_idx in m)
+            order.append(lvl)
+            deg[levels[lvl]] = 0
+    ordered = [levels[j] for j in order] + [levels[j] for j in range(len(levels)) if j not in order]
+    prio = np.zeros(n, dtype=np.int64)
+    for lvl, members in enumerate(ordered):
+        prio[members] = lvl + 1
+    # directed: edge i -> j iff adjacent and level(i) < level(j)
+    return (A > 0) & (prio[:, None] < prio[None, :])
+
+
+def constant_priorities(adjacency: np.ndarray) -> np.ndarray:
+    """ConstantPrioritizer.m:6-18: priority = vehicle index; lower index first."""
+    n = adjacency.shape[0]
+    idx = np.arange(n)
+    return (adjacency > 0) & (idx[:, None] < idx[None, :])
+
+
+def _corridor(veh: Vehicle, x, y, reach: float) -> np.ndarray:
+    """Sample points of the reference path from the projection of (x, y) forward by `reach`."""
+    path = veh.reference_path
+    xp, yp, nxt = _closest_point(path, x, y)
+    pts = [np.array([xp, yp])]
+    left = reach
+    i = nxt - 1
+    n = path.shape[0]
+    guard = 0
+    while left > 0 and guard < 4 * n:
+        guard += 1
+        seg = path[i] - pts[-1]
+        L = np.hypot(*seg)
+        if L > 1e-12:
+            step = min(L, left)
+            m = max(1, int(np.ceil(step / 0.05)))
+            base = pts[-1]
+            for t in range(1, m + 1):
+                pts.append(base + seg / L * (step * t / m))
+            left -= step
+            if step < L:
+                break
+        i += 1
+        if i >= n:
+            if not veh.is_loop:
+                break
+            i = 1
+    return np.array(pts)
+
+
+def couple(sc: Scenario, poses: np.ndarray, all_coupled: bool = False) -> np.ndarray:
+    """[dev] stand-in for ReachableSetCoupler.m:5-54: vehicles are coupled when the
+    corridors they can reach within Hp steps come closer than one lane width.  In
+    the circle scenario every pair is coupled."""
+    n = sc.amount
+    if sc.kind == "circle" or all_coupled:
+        return np.ones((n, n), dtype=np.int64) - np.eye(n, dtype=np.int64)
+    reach = sc.mpa.get_max_speed_of_mpa() * sc.mpa.dt_seconds * sc.mpa.Hp + VEH_LENGTH
+    cors = [_corridor(v, poses[i, 0], poses[i, 1], reach) for i, v in enumerate(sc.vehicles)]
+    A = np.zeros((n, n), dtype=np.int64)
+    for i in range(n):
+        for j in range(i + 1, n):
+            if np.hypot(*(poses[i, :2] - poses[j, :2])) > 2 * reach + 0.5:
+                continue
+            d = cors[i][:, None, :] - cors[j][None, :, :]
+            if (d[..., 0] ** 2 + d[..., 1] ** 2).min() < 0.25 ** 2:
+                A[i, j] = A[j, i] = 1
+    return A
+
+
+# --------------------------------------------------------------------------- closed loop
+PlanFn = Callable[[SearchBatch], BatchResult]
+
+
+@dataclasses.dataclass
+class StepRecord:
+    step: int
+    level: int
+    vehicles: np.ndarray       # vehicle indices planned in this (step, level)
+    batch: SearchBatch
+    result: BatchResult
+
+
+class ScenarioRunner:
+    """HighLevelController.main_control_loop (HighLevelController.m:334-373) for the
+    sequential prioritized controller, with the optimizer call batched per
+    computation level (vehicles of one level are independent,
+    PrioritizedSequentialController.m:83-92)."""
+
+    def __init__(self, sc: Scenario, plan_fn: PlanFn, max_num_CLs: int = 99):
+        self.sc = sc
+        self.plan_fn = plan_fn
+        self.mpa = sc.mpa
+        n = sc.amount
+        self.pose = np.array([[v.x_start, v.y_start, v.yaw_start] for v in sc.vehicles])
+        self.trim = np.array([sc.mpa.trim_from_values(0.0, 0.0)] * n)   # start at standstill
+        self.prev_shapes: List[Optional[List[np.ndarray]]] = [None] * n
+        self.prev_traj: List[Optional[np.ndarray]] = [None] * n
+        self.prev_trims: List[Optional[np.ndarray]] = [None] * n
+        self.k = 0
+        self.records: List[StepRecord] = []
+        self.n_fallbacks = 0
+
+    def _iter_for(self, i: int) -> IterationData:
+        sc, mpa = self.sc, self.mpa
+        v = sc.vehicles[i]
+        x, y, yaw = self.pose[i]
+        pts, v_ref, ref_idx, _ = get_reference_trajectory(mpa, v, x, y, int(self.trim[i]), mpa.dt_seconds)
+        if sc.kind == "commonroad":
+            pred_lan = get_predicted_lanelets(v, ref_idx)
+            boundary = get_lanelets_boundary(pred_lan, sc.road, v)
+        else:
+            boundary = (np.zeros((2, 0)), np.zeros((2, 0)))
+        return IterationData(x0=np.array([x, y, yaw, mpa.trim_speed[self.trim[i] - 1]]),
+                             trim_indices=int(self.trim[i]), reference_trajectory_points=pts, v_ref=v_ref,
+                             predicted_lanelet_boundary=boundary)
+
+    def step(self) -> List[StepRecord]:
+        sc, mpa = self.sc, self.mpa
+        n, Hp = sc.amount, mpa.Hp
+        self.k += 1
+        iters = [self._iter_for(i) for i in range(n)]
+        A = couple(sc, self.pose)
+        D = constant_priorities(A) if sc.priority == "constant" else coloring_priorities(A)
+        levels = kahn(D.astype(np.int64))
+        shapes_now: List[Optional[List[np.ndarray]]] = [None] * n
+        new_pose = self.pose.copy()
+        new_trim = self.trim.copy()
+        out: List[StepRecord] = []
+        for lvl in range(1, int(levels.max()) + 1):
+            members = np.flatnonzero(levels == lvl)
+            its = []
+            for i in members:
+                it = iters[i]
+                # consider_predecessors (sequential): PrioritizedController.m:449-506
+                for j in np.flatnonzero(D[:, i]):
+                    it.dynamic_obstacle_area.append(shapes_now[j])
+                # consider_successors, area_of_standstill: :508-540
+                for j in np.flatnonzero(D[i, :]):
+                    if abs(mpa.trim_speed[self.trim[j] - 1]) < 0.01:
+                        it.obstacles.append(occupied_area(*self.pose[j]))
+                its.append(it)
+            batch = SearchBatch.from_iters(its, Hp, sc.checker, mpa.dt_seconds)
+            res = self.plan_fn(batch)
+            for b, i in enumerate(members):
+                if not res.is_exhausted[b]:
+                    shapes_now[i] = res.shapes(b)
+                    self.prev_traj[i] = res.y_predicted[b].copy()
+                    self.prev_trims[i] = res.trims[b, 1:].copy()
+                else:
+                    # [dev] local fallback: PrioritizedController.m:568-621,678-718
+                    self.n_fallbacks += 1
+                    if self.prev_shapes[i] is None or abs(mpa.trim_speed[self.trim[i] - 1]) < 0.01:
+                        stand = occupied_area(*self.pose[i])
+                        shapes_now[i] = [stand] * Hp
+                        self.prev_traj[i] = np.tile(self.pose[i], (Hp, 1))
+                        self.prev_trims[i] = np.full(Hp, self.trim[i])
+                    else:
+                        ps = self.prev_shapes[i]
+                        shapes_now[i] = ps[1:] + [ps[-1]]
+                        self.prev_traj[i] = np.vstack([self.prev_traj[i][1:], self.prev_traj[i][-1:]])
+                        self.prev_trims[i] = np.concatenate([self.prev_trims[i][1:], self.prev_trims[i][-1:]])
+                # Simulation.apply: plant/Simulation.m:93-98
+                new_pose[i] = self.prev_traj[i][0]
+                new_trim[i] = self.prev_trims[i][0]
+            out.append(StepRecord(self.k, lvl, members, batch, res))
+        self.prev_shapes = shapes_now
+        self.pose, self.trim = new_pose, new_trim
+        self.records.extend(out)
+        return out
+
+    def run(self, n_steps: int) -> List[StepRecord]:
+        for _ in range(n_steps):
+            self.step()
+        return self.records
+
+
+def roll_out(sc: Scenario, plan_fn: PlanFn, n_steps: int) -> SearchBatch:
+    """Closed-loop roll-out; returns every search record of the run as one flat batch."""
+    recs = ScenarioRunner(sc, plan_fn).run(n_steps)
+    return SearchBatch.concat([r.batch for r in recs])
