@@ -1,0 +1,388 @@
+#!/usr/bin/env python3
+"""bench.py — vehicle-plans/sec of the MPA graph-search optimizer on B200.
+
+Workload at N=1 (BASELINE.json configs[1]): CPM Lab road network, 20 vehicles,
+coloring-based prioritisation, triple_speed MPA, Hp 6, InterX checker, 35 time
+steps per scenario, R scenarios planned concurrently ("parallel_threads
+equivalent on 1 B200").  Scenarios are rolled out closed loop once (untimed) with
+the GPU planner so that every (scenario, step, vehicle) search record is fixed;
+one bench "step" = one pass of the hot path over all records of the rank.
+
+  value     : records already resident in HBM, search kernel timed with CUDA
+              events on the library's stream, L2 flushed between steps.
+  e2e       : same records through the C-ABI call pdmpc_plan_batch with HOST
+              (pinned) buffers: H2D staging + kernels + D2H results inside the
+              timed region.
+  roofline  : algorithmic bytes of the search kernel (SURVEY.md §8d formula from
+              the kernel's own counters) / its CUDA-event time vs measured HBM peak;
+              plus the FP64-pipe figure, which is the bound that actually bites.
+  cpu_baseline : the C oracle (a port of the reference; MATLAB is not available)
+              timed on this box's host cores on a bounded sample of the same records.
+
+`--impl reference` times that CPU implementation alone (all host threads).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scenarios", type=int, default=int(os.environ.get("PDMPC_BENCH_SCENARIOS", "64")),
+                    help="scenarios per GPU (weak scaling)")
+    ap.add_argument("--sim-steps", type=int, default=35)
+    ap.add_argument("--vehicles", type=int, default=20)
+    ap.add_argument("--mpa", default="triple_speed")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="searches in the CPU sample (0 = auto)")
+    return ap.parse_args()
+
+
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), \
+        int(os.environ.get("WORLD_SIZE", "1"))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_records(planner, mpa, n_scen: int, seed0: int, vehicles: int, sim_steps: int):
+    """Closed-loop roll-out of n_scen road-network scenarios with the GPU planner (untimed)."""
+    from pdmpc_b200 import scenario
+    from pdmpc_b200.records import SearchBatch
+    batches, per_step = [], []
+    for s in range(n_scen):
+        sc = scenario.commonroad_scenario(mpa, vehicles, seed=seed0 + s)
+        runner = scenario.ScenarioRunner(sc, planner.plan_batch)
+        recs = runner.run(sim_steps)
+        batches.extend(r.batch for r in recs)
+        if s == 0:
+            per_step = recs
+    return SearchBatch.concat(batches), per_step
+
+
+def algorithmic_bytes(batch, stats, Hp: int) -> float:
+    """B_in + 80*M + 80*P + B_out per search, summed over the batch.
+    The per-pop obstacle re-read term is counted separately (obstacle columns are
+    L1/L2 resident, not HBM traffic)."""
+    b_in = batch.input_bytes()
+    b_out = batch.n * (8 * (Hp * (4 + 2 * 7)) + 16)
+    return float(b_in + 80 * stats.total_nodes + 80 * stats.total_pops + b_out)
+
+
+def fp64_ops(batch, stats, Hp: int) -> float:
+    """FP64 instructions (mul/add/sqrt, no FMA) the algorithm needs: per pop the
+    sin/cos (2 x ~45) and shape placement (~6 pts x 2 shapes x 6), per obstacle
+    column tested ~6 edges x 5 ops (C1 pass of InterX), per created node pose+g+h
+    (~12 + 8 + 9*(Hp-1)/2)."""
+    return float(stats.total_pops * (90 + 72) + stats.total_obstacle_cols * 30 +
+                 stats.total_nodes * (20 + 9 * (Hp - 1) / 2))
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU implementation of the path (oracle port; the
+    MATLAB reference cannot run here) on all host threads, bounded sample."""
+    if rank != 0:
+        return
+    from oracle import oracle_py
+    from pdmpc_b200 import scenario
+    from pdmpc_b200.mpa import get_mpa
+    from pdmpc_b200.records import SearchBatch
+    mpa = get_mpa(args.mpa, non_convex=True)
+    cores = os.cpu_count() or 1
+    plan = lambda b: oracle_py.plan_batch(mpa, b, cores)
+    batches = []
+    for s in range(2):
+        sc = scenario.commonroad_scenario(mpa, args.vehicles, seed=1 + s)
+        batches.append(scenario.roll_out(sc, plan, args.sim_steps))
+    base = SearchBatch.concat(batches)
+    # bounded sample: replicate the two scenarios until one step is ~2 s of wall time
+    t0 = time.perf_counter()
+    oracle_py.plan_batch(mpa, base, cores)
+    dt = max(time.perf_counter() - t0, 1e-4)
+    reps = int(min(max(1, round(2.0 / dt)), 256))
+    sample = SearchBatch.concat([base] * reps)
+    for _ in range(args.warmup):
+        oracle_py.plan_batch(mpa, sample, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_py.plan_batch(mpa, sample, cores)
+    el = time.perf_counter() - t0
+    val = sample.n * args.steps / el
+    desc = f"{sample.n} searches/step = {reps}x the records of 2 scenarios x {args.sim_steps} steps x {args.vehicles} vehicles"
+    print(json.dumps({
+        "impl": "reference", "metric": "vehicle-plans/sec", "value": val, "unit": "plans/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"CPM Lab road network, {args.vehicles} vehicles, coloring priorities, "
+                               f"{args.mpa} MPA, Hp 6, InterX checker", "cpu_threads": cores},
+        "cpu_baseline": {"value": val, "unit": "plans/s", "cores": cores, "kind": "port", "sample": desc,
+                         "note": "C oracle (gcc -O2, no FMA contraction) restating the MATLAB reference; "
+                                 "MATLAB R2023a itself is unavailable in this image"},
+        "e2e": {"value": val, "unit": "plans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    args = parse_args()
+    rank, local_rank, world = dist_env()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+    if rank == 0:
+        entry.build()
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    from pdmpc_b200 import capi
+    from pdmpc_b200.mpa import get_mpa
+    from pdmpc_b200.records import BatchResult
+
+    dev = local_rank if world > 1 else 0
+    torch.cuda.set_device(dev)
+    planner = capi.Planner(dev)        # raises if the CUDA library / device is missing
+    mpa = get_mpa(args.mpa, non_convex=True)
+    planner.upload_mpa(mpa)
+    Hp = mpa.Hp
+
+    t_gen = time.perf_counter()
+    batch, step_recs = build_records(planner, mpa, args.scenarios, 1 + rank * args.scenarios,
+                                     args.vehicles, args.sim_steps)
+    t_gen = time.perf_counter() - t_gen
+    n = batch.n
+
+    stream = torch.cuda.ExternalStream(planner.stream(), device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{dev}")   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") ------------------------------------
+    planner.stage(batch)
+    for _ in range(max(args.warmup, 3)):
+        planner.run_staged()
+    planner.sync()
+    sampler = ClockSampler(dev)
+    barrier()
+    sampler.start()
+    kernel_ms = []
+    t_wall = time.perf_counter()
+    for _ in range(args.steps):
+        with torch.cuda.stream(stream):
+            flush.zero_()                     # L2 flush, outside the per-step events
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            planner.run_staged()
+            e1.record(stream)
+        e1.synchronize()
+        kernel_ms.append(e0.elapsed_time(e1))
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    res = planner.fetch()
+    stats = planner.stats()
+    ms_step = float(np.mean(kernel_ms))
+    t_local = torch.tensor([sum(kernel_ms)], dtype=torch.float64, device=f"cuda:{dev}")
+    if world > 1:
+        dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
+    total_ms = float(t_local.item())
+    value = n * world * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers ("e2e") ------------------
+    import dataclasses
+    pinned = []   # keep the pinned torch storages alive
+
+    def pinned_like(a: np.ndarray) -> np.ndarray:
+        t = torch.empty(max(a.nbytes, 1), dtype=torch.uint8, pin_memory=True)
+        pinned.append(t)
+        return t.numpy()[: a.nbytes].view(a.dtype).reshape(a.shape)
+
+    host_in = {}
+    for f in dataclasses.fields(batch):
+        a = getattr(batch, f.name)
+        if isinstance(a, np.ndarray):
+            host_in[f.name] = pinned_like(a)
+            host_in[f.name][...] = a
+    hb = dataclasses.replace(batch, **host_in)
+    out = BatchResult.empty(n, Hp)
+    for f in dataclasses.fields(out):
+        a = getattr(out, f.name)
+        if isinstance(a, np.ndarray):
+            setattr(out, f.name, pinned_like(a))
+    import ctypes as C
+    bi, bo = capi.batch_in(hb), capi.batch_out(out)
+    for _ in range(2):
+        planner._check(planner.lib.pdmpc_plan_batch(planner.h, C.byref(bi), C.byref(bo)))
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        planner._check(planner.lib.pdmpc_plan_batch(planner.h, C.byref(bi), C.byref(bo)))
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{dev}")
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_val = n * world * e2e_steps / float(t_e2e.item())
+    st2 = planner.stats()
+    assert np.array_equal(out.pop_hash, res.pop_hash), "e2e path and staged path disagree"
+
+    # ---- per-time-step latency (levels sequential, host buffers) -----------------
+    lat = []
+    if rank == 0:
+        by_step = {}
+        for r in step_recs:
+            by_step.setdefault(r.step, []).append(r.batch)
+        for rep in range(3):
+            for k, levels in sorted(by_step.items()):
+                t0 = time.perf_counter()
+                for lb in levels:
+                    planner.plan_batch(lb)
+                if rep:
+                    lat.append((time.perf_counter() - t0) * 1e3)
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------
+    cpu = None
+    if rank == 0 and world == 1:
+        from oracle import oracle_py, parity
+        cores = os.cpu_count() or 1
+        m = args.cpu_sample or min(n, 14000)
+        sample = batch.select(np.arange(m))
+        t0 = time.perf_counter()
+        ref = oracle_py.plan_batch(mpa, sample, cores)
+        t_cpu = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        oracle_py.plan_batch(mpa, batch.select(np.arange(min(m, 2000))), 1)
+        t_cpu1 = time.perf_counter() - t0
+        # parity of the timed outputs against the checker, on the sample
+        sub = dataclasses.replace(res, **{f.name: getattr(res, f.name)[:m] for f in dataclasses.fields(res)
+                                          if isinstance(getattr(res, f.name), np.ndarray)})
+        parity.compare(sub, ref)
+        cpu = {"value": m / t_cpu, "unit": "plans/s", "cores": cores, "kind": "port",
+               "sample": f"first {m} of the {n} timed search records, one pass, {cores} threads",
+               "single_thread_plans_per_s": min(m, 2000) / t_cpu1,
+               "parity_checked": True,
+               "note": "C oracle restating the MATLAB reference (MATLAB R2023a unavailable here)"}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        alg_bytes = algorithmic_bytes(batch, stats, Hp)
+        achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+        f64 = fp64_ops(batch, stats, Hp)
+        line = {
+            "metric": "vehicle-plans/sec", "value": value, "unit": "plans/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"CPM Lab road network (BASELINE configs[1]), {args.vehicles} vehicles, "
+                                   f"coloring priorities, {args.mpa} MPA, Hp {Hp}, InterX checker, "
+                                   f"{args.scenarios} scenarios/GPU x {args.sim_steps} steps, pre-rolled closed loop",
+                       "searches_per_step_per_gpu": n, "l2": "flushed between timed steps (256 MiB write)",
+                       "record_generation_s": round(t_gen, 1)},
+            "e2e": {"value": e2e_val, "unit": "plans/s", "h2d_bytes_per_step": int(st2.h2d_bytes),
+                    "d2h_bytes_per_step": int(st2.d2h_bytes), "steps": e2e_steps,
+                    "h2d_ms": st2.h2d_ms, "kernel_ms": st2.kernel_ms, "d2h_ms": st2.d2h_ms},
+            "gpu_launches": int(args.steps * 1),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None,
+                         "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                         "kernel": "pdmpc::search_kernel", "algorithmic_bytes_per_launch": alg_bytes,
+                         "fp64": {"ops_per_launch": f64, "achieved_tops": f64 / (ms_step * 1e-3) / 1e12,
+                                  "note": "mul/add/sqrt without FMA; latency-bound serial search, see DESIGN.md"}},
+            "cpu_baseline": cpu,
+            "search_stats": {"pops_per_plan": stats.total_pops / max(n, 1),
+                             "nodes_per_plan": stats.total_nodes / max(n, 1),
+                             "exhausted_frac": float(res.is_exhausted.mean()),
+                             "obstacle_cols_per_pop": stats.total_obstacle_cols / max(stats.total_pops, 1)},
+            "latency_ms_per_timestep": ({"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
+                                         "n": len(lat), "what": "all levels of one 20-vehicle step, host buffers"}
+                                        if lat else None),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    planner.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -556,7 +556,8 @@ typedef struct {
     const pdmpc_batch_in *in;
     pdmpc_batch_out *out;
     int32_t *edge_of;
-    int begin, end;
+    int n;
+    int *next; /* shared work counter: dynamic chunks, so a heavy search does not idle 7 cores */
 } job_t;
 
 static void *job_main(void *p) {
@@ -564,7 +565,12 @@ static void *job_main(void *p) {
     work_t w;
     memset(&w, 0, sizeof(w));
     w.edge_of = j->edge_of;
-    for (int si = j->begin; si < j->end; ++si) search_one(j->mpa, j->in, j->out, si, &w, NULL);
+    for (;;) {
+        int b = __atomic_fetch_add(j->next, 16, __ATOMIC_RELAXED);
+        if (b >= j->n) break;
+        int e = b + 16 < j->n ? b + 16 : j->n;
+        for (int si = b; si < e; ++si) search_one(j->mpa, j->in, j->out, si, &w, NULL);
+    }
     tree_free(&w.tree);
     free(w.pq.a);
     free(w.ox);
@@ -579,12 +585,13 @@ int oracle_plan_batch(const pdmpc_mpa_desc *mpa, const pdmpc_batch_in *in, pdmpc
     if (n_threads < 1) n_threads = 1;
     if (n_threads > n) n_threads = n > 0 ? n : 1;
     int32_t *edge_of = build_edge_of(mpa);
+    int next = 0;
     job_t *jobs = (job_t *)calloc((size_t)n_threads, sizeof(job_t));
     pthread_t *th = (pthread_t *)calloc((size_t)n_threads, sizeof(pthread_t));
     for (int t = 0; t < n_threads; ++t) {
         jobs[t].mpa = mpa; jobs[t].in = in; jobs[t].out = out; jobs[t].edge_of = edge_of;
-        jobs[t].begin = (int)((int64_t)n * t / n_threads);
-        jobs[t].end = (int)((int64_t)n * (t + 1) / n_threads);
+        jobs[t].n = n;
+        jobs[t].next = &next;
     }
     if (n_threads == 1) {
         job_main(&jobs[0]);

@@ -59,7 +59,7 @@ int64_t oracle_pq_pop(oracle_pq *q, double *value); /* -1 when empty */
 int64_t oracle_pq_size(const oracle_pq *q);
 
 /* GraphSearch.do_graph_search for every search of the batch, n_threads host
- * threads (static block partition).  Optional trace: if pop_trace != NULL it
+ * threads (dynamic chunks of 16 searches).  Optional trace: if pop_trace != NULL it
  * receives the popped node ids of search `trace_search` (up to trace_cap). */
 int oracle_plan_batch(const pdmpc_mpa_desc *mpa, const pdmpc_batch_in *in,
                       pdmpc_batch_out *out, int n_threads);

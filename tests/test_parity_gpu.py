@@ -1,0 +1,199 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.
+
+Bar: bit-exact trims / flags / node counts / pop order, doubles bit-identical
+(and a fortiori within the 1e-9 relative tolerance BASELINE.json states)."""
+import ctypes as C
+import dataclasses
+
+import numpy as np
+import pytest
+
+from oracle import oracle_py, parity
+from pdmpc_b200 import capi
+from pdmpc_b200.mpa import build_mpa, get_mpa
+from pdmpc_b200.records import CHECKER_INTERX, CHECKER_SAT, SearchBatch
+
+from helpers import circle_records, rect, road_records, straight_iter
+
+pytestmark = pytest.mark.gpu
+
+
+def check(planner, mpa, batch, **kw):
+    planner.upload_mpa(mpa)
+    dev = planner.plan_batch(batch, raise_on_search_error=False)
+    ref = oracle_py.plan_batch(mpa, batch)
+    return parity.compare(dev, ref, **kw), dev, ref
+
+
+def test_circle_config0_sat(planner):
+    mpa, batch = circle_records(30)
+    info, dev, _ = check(planner, mpa, batch)
+    assert info["n"] == batch.n and info["pops"] > 1000
+
+
+@pytest.mark.parametrize("mpa_type", ["single_speed", "triple_speed"])
+def test_road_config1_interx(planner, mpa_type):
+    mpa, batch = road_records(mpa_type, 8)
+    info, dev, _ = check(planner, mpa, batch)
+    assert info["n"] == batch.n
+
+
+def test_road_realistic_mpa(planner):
+    mpa, batch = road_records("realistic", 3, amount=10, seed=5)
+    check(planner, mpa, batch)
+
+
+def test_sat_checker_on_road_records(planner):
+    """SAT + lanelet-boundary path (used when not prioritized, OptimizerInterface.m:36-46)."""
+    mpa = get_mpa("single_speed", non_convex=False)
+    _, b = road_records("single_speed", 4)
+    b = dataclasses.replace(b, checker=CHECKER_SAT)
+    check(planner, mpa, b)
+
+
+def test_pop_trace_identical(planner):
+    mpa, batch = road_records("triple_speed", 8)
+    planner.upload_mpa(mpa)
+    planner.stage(batch)
+    ref_pops = oracle_py.plan_batch(mpa, batch).n_pops
+    lib = planner.lib
+    lib.pdmpc_trace_staged.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64)]
+    lib.pdmpc_trace_staged.restype = C.c_int
+    for si in (0, int(np.argmax(ref_pops)), batch.n - 1):
+        want = oracle_py.plan_trace(mpa, batch, si)
+        got = np.zeros(want.size + 8, dtype=np.int64)
+        n = C.c_int64()
+        rc = lib.pdmpc_trace_staged(planner.h, si, got.ctypes.data_as(C.POINTER(C.c_int64)), got.size, C.byref(n))
+        assert rc == 0 and n.value == want.size
+        assert np.array_equal(got[: want.size], want)
+
+
+def test_empty_batch(planner):
+    mpa = get_mpa("single_speed", non_convex=False)
+    planner.upload_mpa(mpa)
+    b = SearchBatch.from_iters([], mpa.Hp, CHECKER_SAT, mpa.dt_seconds)
+    r = planner.plan_batch(b)
+    assert r.status.size == 0
+
+
+@pytest.mark.parametrize("checker", [CHECKER_SAT, CHECKER_INTERX])
+def test_free_space_straight_plan(planner, checker):
+    """No obstacles, no lanelets: the search walks straight down the tree."""
+    mpa = get_mpa("single_speed", non_convex=(checker == CHECKER_INTERX))
+    b = SearchBatch.from_iters([straight_iter(mpa)], mpa.Hp, checker, mpa.dt_seconds)
+    info, dev, ref = check(planner, mpa, b)
+    assert not dev.is_exhausted[0] and dev.n_pops[0] >= mpa.Hp + 1
+    assert dev.trims[0, -1] == 1     # recursive feasibility: last trim is the equilibrium
+
+
+@pytest.mark.parametrize("checker", [CHECKER_SAT, CHECKER_INTERX])
+def test_blocked_world_exhausts_with_countable_tree(planner, checker):
+    """A static obstacle on top of the vehicle invalidates every depth-1 node:
+    pops = 1 + #children(root), tree = root + children, is_exhausted."""
+    mpa = get_mpa("single_speed", non_convex=(checker == CHECKER_INTERX))
+    # SAT: a big box covering everything; InterX: only crossings count, so use a thin
+    # long sliver across the vehicle's footprint
+    obs = rect(0.0, 0.0, 5.0, 5.0) if checker == CHECKER_SAT else rect(0.05, 0.0, 0.001, 3.0)
+    it = straight_iter(mpa, obstacles=[obs])
+    b = SearchBatch.from_iters([it], mpa.Hp, checker, mpa.dt_seconds)
+    info, dev, ref = check(planner, mpa, b)
+    n_children = int(mpa.transition[0, it.trim_indices - 1].sum())
+    assert dev.is_exhausted[0] == 1
+    assert dev.n_expanded[0] == 1 + n_children
+    assert dev.n_pops[0] == 1 + n_children
+    assert np.isnan(dev.y_predicted[0]).all() and (dev.trims[0, 1:] == 0).all()
+
+
+def test_dynamic_obstacle_only_at_its_step(planner):
+    """An obstacle at step 3 only (GraphSearch.m:147,176: index = child's depth)."""
+    mpa = get_mpa("single_speed", non_convex=False)
+    Hp = mpa.Hp
+    far = rect(50, 50, 0.1, 0.1)
+    row = [far] * Hp
+    row[2] = rect(0.45, 0.0, 0.05, 1.0)
+    it = straight_iter(mpa, dynamic_obstacle_area=[row])
+    b = SearchBatch.from_iters([it], Hp, CHECKER_SAT, mpa.dt_seconds)
+    check(planner, mpa, b)
+
+
+def test_heap_overflow_beyond_shared_memory(planner):
+    """An exhausted road search holds far more than 256 open nodes: exercises the HBM heap overflow."""
+    mpa, batch = road_records("triple_speed", 8)
+    ref = oracle_py.plan_batch(mpa, batch)
+    big = int(np.argmax(ref.n_expanded))
+    assert ref.n_expanded[big] > 1500
+    check(planner, mpa, batch.select([big]))
+
+
+def test_capacity_error_is_loud(planner):
+    mpa, batch = road_records("triple_speed", 8)
+    ref = oracle_py.plan_batch(mpa, batch)
+    big = int(np.argmax(ref.n_expanded))
+    planner.upload_mpa(mpa)
+    planner.set_node_capacity(256)
+    try:
+        r = planner.plan_batch(batch.select([big, 0]), raise_on_search_error=False)
+        assert r.status[0] == capi.PDMPC_ERR_CAPACITY and r.is_exhausted[0] == 1
+        with pytest.raises(capi.PdmpcError):
+            planner.plan_batch(batch.select([big]))
+    finally:
+        planner.set_node_capacity(0)
+    check(planner, mpa, batch.select([big, 0]))
+
+
+def test_bad_inputs_rejected(planner):
+    mpa, batch = road_records("triple_speed", 8)
+    planner.upload_mpa(mpa)
+    bad = dataclasses.replace(batch, trim0=np.zeros_like(batch.trim0))
+    with pytest.raises(capi.PdmpcError) as e:
+        planner.plan_batch(bad)
+    assert e.value.code == capi.PDMPC_ERR_BAD_INPUT
+    vx = batch.vert_x.copy()
+    vx[0] += 1.0        # first polygon no longer closed (vectorize_all_obstacles.m:71-76)
+    with pytest.raises(capi.PdmpcError):
+        planner.plan_batch(dataclasses.replace(batch, vert_x=vx))
+    fresh = capi.Planner(0)
+    with pytest.raises(capi.PdmpcError) as e:
+        fresh.plan_batch(batch)
+    assert e.value.code == capi.PDMPC_ERR_NO_MPA
+    fresh.close()
+
+
+def test_short_and_long_horizon(planner):
+    for Hp in (3, 8):
+        mpa = build_mpa("single_speed", Hp=Hp, non_convex=False)
+        its = [straight_iter(mpa), straight_iter(mpa, obstacles=[rect(0.6, 0.0, 0.05, 0.3)])]
+        b = SearchBatch.from_iters(its, Hp, CHECKER_SAT, mpa.dt_seconds)
+        check(planner, mpa, b)
+
+
+def test_staged_path_equals_plan_batch_and_is_deterministic(planner):
+    mpa, batch = road_records("triple_speed", 8)
+    planner.upload_mpa(mpa)
+    a = planner.plan_batch(batch)
+    planner.stage(batch)
+    planner.run_staged()
+    planner.run_staged()
+    b = planner.fetch()
+    parity.compare(a, b)
+    st = planner.stats()
+    assert st.total_pops == int(a.n_pops.sum()) and st.total_nodes == int(a.n_expanded.sum())
+
+
+def test_full_size_properties(planner):
+    """BASELINE-size batch (tiled road records): per-search results are independent of
+    batch position and of which CTA/slot ran them (permutation + concatenation invariance)."""
+    mpa, batch = road_records("triple_speed", 8)
+    rng = np.random.default_rng(0)
+    reps = 60
+    big = SearchBatch.concat([batch] * reps)            # ~9600 searches, > resident CTA slots
+    perm = rng.permutation(big.n)
+    shuffled = big.select(perm)
+    planner.upload_mpa(mpa)
+    r0 = planner.plan_batch(batch)
+    r1 = planner.plan_batch(shuffled)
+    for name in ("status", "is_exhausted", "n_expanded", "n_pops", "pop_hash"):
+        base = np.tile(getattr(r0, name), reps)
+        assert np.array_equal(getattr(r1, name), base[perm]), name
+    assert np.array_equal(r1.trims, np.tile(r0.trims, (reps, 1))[perm])
+    assert np.array_equal(r1.y_predicted.view(np.uint64), np.tile(r0.y_predicted, (reps, 1, 1))[perm].view(np.uint64))
