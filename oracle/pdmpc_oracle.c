@@ -273,13 +273,8 @@ typedef struct {
     int32_t *edge_of; /* n_trims*n_trims -> edge index or -1 */
 } work_t;
 
-static uint64_t fnv1a_u32(uint64_t h, uint32_t v) {
-    for (int b = 0; b < 4; ++b) {
-        h ^= (uint64_t)((v >> (8 * b)) & 0xffu);
-        h *= 0x100000001b3ULL;
-    }
-    return h;
-}
+/* FNV-1a over the popped ids taken as 32-bit words (parity trace of the pop order) */
+static uint64_t fnv1a_u32(uint64_t h, uint32_t v) { return (h ^ (uint64_t)v) * 0x100000001b3ULL; }
 
 /* rotate/translate a maneuver area: GraphSearch.m:158-159 (and :162-163,:168-169) */
 static void place_area(const pdmpc_mpa_desc *mpa, int edge, int kind, double c, double s,

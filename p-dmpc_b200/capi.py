@@ -30,7 +30,8 @@ PDMPC_ERR_ALLOC = 5
 
 EXPORTED_SYMBOLS = (
     "pdmpc_create", "pdmpc_destroy", "pdmpc_last_error", "pdmpc_abi_version",
-    "pdmpc_set_node_capacity", "pdmpc_upload_mpa", "pdmpc_plan_batch", "pdmpc_stage_batch",
+    "pdmpc_set_node_capacity", "pdmpc_set_tile", "pdmpc_host_alloc", "pdmpc_host_free",
+    "pdmpc_trace_staged", "pdmpc_upload_mpa", "pdmpc_plan_batch", "pdmpc_stage_batch",
     "pdmpc_run_staged", "pdmpc_sync", "pdmpc_fetch_staged", "pdmpc_get_stats", "pdmpc_stream",
 )
 
@@ -151,6 +152,14 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.pdmpc_abi_version.restype = C.c_int
     lib.pdmpc_set_node_capacity.argtypes = [H, C.c_int32]
     lib.pdmpc_set_node_capacity.restype = C.c_int
+    lib.pdmpc_set_tile.argtypes = [H, C.c_int32]
+    lib.pdmpc_set_tile.restype = C.c_int
+    lib.pdmpc_trace_staged.argtypes = [H, C.c_int32, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64)]
+    lib.pdmpc_trace_staged.restype = C.c_int
+    lib.pdmpc_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+    lib.pdmpc_host_alloc.restype = C.c_int
+    lib.pdmpc_host_free.argtypes = [C.c_void_p]
+    lib.pdmpc_host_free.restype = C.c_int
     lib.pdmpc_upload_mpa.argtypes = [H, C.POINTER(MpaDesc)]
     lib.pdmpc_upload_mpa.restype = C.c_int
     lib.pdmpc_plan_batch.argtypes = [H, C.POINTER(BatchIn), C.POINTER(BatchOut)]
@@ -209,6 +218,18 @@ class Planner:
 
     def set_node_capacity(self, n: int):
         self._check(self.lib.pdmpc_set_node_capacity(self.h, int(n)))
+
+    def set_tile(self, lanes_per_search: int):
+        """32 / 16 / 8 lanes per search, 0 = auto (pdmpc_set_tile)."""
+        self._check(self.lib.pdmpc_set_tile(self.h, int(lanes_per_search)))
+
+    def trace(self, search: int, cap: int = 1 << 20) -> np.ndarray:
+        """Node ids popped by staged search `search`, in order (pdmpc_trace_staged)."""
+        ids = np.zeros(cap, dtype=np.int64)
+        n = C.c_int64()
+        self._check(self.lib.pdmpc_trace_staged(self.h, int(search), ids.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                cap, C.byref(n)))
+        return ids[: min(n.value, cap)].copy()
 
     def upload_mpa(self, mpa: MotionPrimitiveAutomaton):
         d, keep = mpa_desc(mpa)

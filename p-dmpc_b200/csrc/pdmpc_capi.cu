@@ -20,7 +20,10 @@ using namespace pdmpc;
 
 namespace {
 
-constexpr int kHeapSmem = 256;  // heap entries kept in shared memory per CTA
+// Kernel variants: searches per warp (tile width) and heap entries kept in shared
+// memory per search.  Wide tiles minimise per-search latency, narrow tiles share
+// the warp's instruction stream between searches and maximise throughput.
+constexpr int kHeapSmem32 = 512, kHeapSmem16 = 256, kHeapSmem8 = 128;
 
 struct DBuf {
     void *p = nullptr;
@@ -48,7 +51,8 @@ struct DBuf {
 struct pdmpc_handle {
     int device = 0;
     int num_sms = 0;
-    int ctas_per_sm = 0;
+    int ctas_per_sm[3] = {0, 0, 0};   // per tile variant 32 / 16 / 8
+    int tile_mode = 0;                // 0 = auto, else 32 / 16 / 8
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {};   // 0/1 h2d, 2/3 kernel, 4/5 d2h
     std::string err;
@@ -74,7 +78,7 @@ struct pdmpc_handle {
 
     // arena
     ArenaDev arena{};
-    DBuf a_a, a_b, a_hf, a_hid;
+    DBuf a_a, a_b, a_cs, a_heap;
     int arena_slots = 0;
 
     // trace (debug / parity tests)
@@ -127,16 +131,20 @@ int pdmpc_create(int device_id, pdmpc_handle **out) {
     }
     for (auto &ev : h->ev) cudaEventCreate(&ev);
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device_id);
-    int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, search_kernel<kHeapSmem>, kWarp, 0);
-    if (e != cudaSuccess || occ < 1) {
+    int occ[3] = {0, 0, 0};
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], search_kernel<kHeapSmem32, 32>, kWarp, 0);
+    if (e == cudaSuccess)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], search_kernel<kHeapSmem16, 16>, kWarp, 0);
+    if (e == cudaSuccess)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], search_kernel<kHeapSmem8, 8>, kWarp, 0);
+    if (e != cudaSuccess || occ[0] < 1 || occ[1] < 1 || occ[2] < 1) {
         std::string msg = std::string("pdmpc_create: search kernel is not launchable on this device (") +
                           cudaGetErrorString(e) + "); built for sm_100a";
         cudaStreamDestroy(h->stream);
         delete h;
         return fail(nullptr, PDMPC_ERR_CUDA, msg);
     }
-    h->ctas_per_sm = occ;
+    for (int i = 0; i < 3; ++i) h->ctas_per_sm[i] = occ[i];
     *out = h;
     return PDMPC_OK;
 }
@@ -151,7 +159,7 @@ int pdmpc_destroy(pdmpc_handle *h) {
                     &h->b_plx, &h->b_ply, &h->b_lane, &h->b_lx, &h->b_ly, &h->b_llx, &h->b_lly,
                     &h->o_status, &h->o_exh, &h->o_nexp, &h->o_npops, &h->o_hash, &h->o_trims, &h->o_path,
                     &h->o_ypred, &h->o_g, &h->o_h, &h->o_snp, &h->o_sx, &h->o_sy, &h->o_counters,
-                    &h->work_counter, &h->a_a, &h->a_b, &h->a_hf, &h->a_hid, &h->t_ids, &h->t_n};
+                    &h->work_counter, &h->a_a, &h->a_b, &h->a_cs, &h->a_heap, &h->t_ids, &h->t_n};
     for (DBuf *b : bufs) b->release();
     for (auto &ev : h->ev)
         if (ev) cudaEventDestroy(ev);
@@ -168,6 +176,14 @@ int pdmpc_host_alloc(void **p, size_t bytes) {
 }
 int pdmpc_host_free(void *p) {
     if (p) cudaFreeHost(p);
+    return PDMPC_OK;
+}
+
+int pdmpc_set_tile(pdmpc_handle *h, int32_t lanes_per_search) {
+    if (!h) return PDMPC_ERR_BAD_INPUT;
+    if (lanes_per_search != 0 && lanes_per_search != 8 && lanes_per_search != 16 && lanes_per_search != 32)
+        return fail(h, PDMPC_ERR_BAD_INPUT, "lanes per search must be 0 (auto), 8, 16 or 32");
+    h->tile_mode = lanes_per_search;
     return PDMPC_OK;
 }
 
@@ -335,7 +351,7 @@ static int ensure_outputs(pdmpc_handle *h, int n) {
     CU_TRY(h, h->o_snp.reserve(n1 * Hp * sizeof(int)));
     CU_TRY(h, h->o_sx.reserve(n1 * Hp * PDMPC_AREA_STRIDE * sizeof(double)));
     CU_TRY(h, h->o_sy.reserve(n1 * Hp * PDMPC_AREA_STRIDE * sizeof(double)));
-    CU_TRY(h, h->o_counters.reserve(4 * sizeof(unsigned long long)));
+    CU_TRY(h, h->o_counters.reserve(16 * sizeof(unsigned long long)));
     CU_TRY(h, h->work_counter.reserve(sizeof(unsigned)));
     OutDev &o = h->out;
     o.status = h->o_status.as<int>();
@@ -436,12 +452,12 @@ static int ensure_arena(pdmpc_handle *h, int slots) {
     const size_t tot = (size_t)slots * cap;
     CU_TRY(h, h->a_a.reserve(tot * sizeof(NodeA)));
     CU_TRY(h, h->a_b.reserve(tot * sizeof(NodeB)));
-    CU_TRY(h, h->a_hf.reserve(tot * sizeof(double)));
-    CU_TRY(h, h->a_hid.reserve(tot * sizeof(unsigned)));
+    CU_TRY(h, h->a_cs.reserve(tot * sizeof(NodeCS)));
+    CU_TRY(h, h->a_heap.reserve(tot * sizeof(HEnt)));
     h->arena.a = h->a_a.as<NodeA>();
     h->arena.b = h->a_b.as<NodeB>();
-    h->arena.heap_f = h->a_hf.as<double>();
-    h->arena.heap_id = h->a_hid.as<unsigned>();
+    h->arena.cs = h->a_cs.as<NodeCS>();
+    h->arena.heap = h->a_heap.as<HEnt>();
     h->arena.cap = cap;
     h->arena_slots = slots;
     return PDMPC_OK;
@@ -450,15 +466,29 @@ static int ensure_arena(pdmpc_handle *h, int slots) {
 static int launch_search(pdmpc_handle *h, const TraceDev &tr) {
     const int n = h->batch.n;
     CU_TRY(h, cudaSetDevice(h->device));
-    CU_TRY(h, cudaMemsetAsync(h->o_counters.p, 0, 4 * sizeof(unsigned long long), h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->o_counters.p, 0, 16 * sizeof(unsigned long long), h->stream));
     CU_TRY(h, cudaMemsetAsync(h->work_counter.p, 0, sizeof(unsigned), h->stream));
     if (n == 0) return PDMPC_OK;
-    const int grid = std::min(n, h->num_sms * h->ctas_per_sm);
-    int rc = ensure_arena(h, grid);
+    // tile selection: a batch that cannot fill the machine with one search per warp
+    // runs wide (latency); a large batch runs 4 searches per warp (throughput)
+    int tile = h->tile_mode;
+    if (tile == 0) {
+        const int wide_slots = h->num_sms * h->ctas_per_sm[0];
+        tile = n <= wide_slots ? 32 : (n <= 2 * wide_slots ? 16 : 8);
+    }
+    const int variant = tile == 32 ? 0 : (tile == 16 ? 1 : 2);
+    const int per_cta = kWarp / tile;
+    const int grid = std::min((n + per_cta - 1) / per_cta, h->num_sms * h->ctas_per_sm[variant]);
+    int rc = ensure_arena(h, grid * per_cta);
     if (rc != PDMPC_OK) return rc;
+    unsigned *wc = h->work_counter.as<unsigned>();
     CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
-    search_kernel<kHeapSmem><<<grid, kWarp, 0, h->stream>>>(h->mpa, h->batch, h->out, h->arena,
-                                                           h->work_counter.as<unsigned>(), tr);
+    if (tile == 32)
+        search_kernel<kHeapSmem32, 32><<<grid, kWarp, 0, h->stream>>>(h->mpa, h->batch, h->out, h->arena, wc, tr);
+    else if (tile == 16)
+        search_kernel<kHeapSmem16, 16><<<grid, kWarp, 0, h->stream>>>(h->mpa, h->batch, h->out, h->arena, wc, tr);
+    else
+        search_kernel<kHeapSmem8, 8><<<grid, kWarp, 0, h->stream>>>(h->mpa, h->batch, h->out, h->arena, wc, tr);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
     h->timing_pending_kernel = true;
@@ -507,7 +537,7 @@ int pdmpc_fetch_staged(pdmpc_handle *h, pdmpc_batch_out *out) {
     DOWN(h, out->shape_npts, h->o_snp, n * Hp);
     DOWN(h, out->shape_x, h->o_sx, n * Hp * PDMPC_AREA_STRIDE);
     DOWN(h, out->shape_y, h->o_sy, n * Hp * PDMPC_AREA_STRIDE);
-    unsigned long long counters[4] = {0, 0, 0, 0};
+    unsigned long long counters[16] = {0};
     CU_TRY(h, cudaMemcpyAsync(counters, h->o_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -515,6 +545,17 @@ int pdmpc_fetch_staged(pdmpc_handle *h, pdmpc_batch_out *out) {
     h->stats.total_pops = (int64_t)counters[0];
     h->stats.total_nodes = (int64_t)counters[1];
     h->stats.total_obstacle_cols = (int64_t)counters[2];
+#ifdef PDMPC_PROFILE
+    {
+        static const char *names[8] = {"setup", "heap_pop", "loads+place", "check", "expand", "heap_push", "-", "loop"};
+        double tot = 0;
+        for (int i = 0; i < 8; ++i) tot += (double)counters[8 + i];
+        fprintf(stderr, "[pdmpc profile] cycles per pop:");
+        for (int i = 0; i < 8; ++i)
+            fprintf(stderr, " %s=%.0f", names[i], (double)counters[8 + i] / (double)std::max<unsigned long long>(counters[0], 1));
+        fprintf(stderr, " total=%.0f\n", tot / (double)std::max<unsigned long long>(counters[0], 1));
+    }
+#endif
     return PDMPC_OK;
 }
 

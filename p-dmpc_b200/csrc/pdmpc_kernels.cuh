@@ -1,6 +1,8 @@
 // pdmpc_kernels.cuh — device code of the B200-native MPA graph search.
 //
-// One CTA (one warp) runs one search (vehicle x permutation x scenario) and
+// Each search (vehicle x permutation x scenario) is run by one TILE of a warp
+// (TILE = 32: one search per one-warp CTA, lowest latency; TILE = 16 / 8: 2 / 4
+// searches share the warp's instruction stream, highest throughput) and
 // reproduces the reference's best-first loop exactly:
 //   GraphSearch.do_graph_search      hlc/optimizer/graph_search/GraphSearch.m:23-109
 //   eval_edge_exact                  GraphSearch.m:111-196
@@ -12,6 +14,22 @@
 // Bit-exactness rules: IEEE double everywhere, compiled with --fmad=false (no
 // contraction), the same operation order as the reference's expressions, and
 // the sin/cos algorithm of DESIGN.md §sincos.
+//
+// Design notes (the search is a serial pop -> check -> expand -> push chain; ncu
+// shows it is bound by the number of warp instructions per pop, so everything
+// here minimises uniform/scalar work per pop):
+//   * the binary heap is walked by the whole tile: one round of loads fetches the
+//     next LV levels under the hole (2+4+..+2^LV contiguous entries), sibling
+//     pairs decide locally (one shfl.xor), one ballot gives the whole path.
+//     Pushes of all children go through a one-round fast path when no child has
+//     to sift up.  The resulting array is identical to what libstdc++'s
+//     sequential routines produce.
+//   * heap entries carry (f, id, parent id): everything a pop needs is fetched in
+//     ONE round of independent loads (own record + parent record).
+//   * sin/cos of a node's yaw is computed once, when the node is expanded, and
+//     cached for the edge checks of its children.
+//   * InterX: lanes are (point slot, shape edge) pairs, so a lane keeps ONE
+//     edge's constants in registers; C2 is evaluated only where C1 holds.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -19,10 +37,30 @@
 
 #include "../../include/pdmpc_b200.h"
 
+// Optional per-phase cycle accounting (build with -DPDMPC_PROFILE; profiling builds only)
+#ifdef PDMPC_PROFILE
+#define PROF_DECL long long prof_t0 = clock64(), prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define PROF_MARK(i)                      \
+    do {                                  \
+        long long _t = clock64();         \
+        prof_acc[i] += _t - prof_t0;      \
+        prof_t0 = _t;                     \
+    } while (0)
+#define PROF_FLUSH(o, lane0)                                                              \
+    do {                                                                                  \
+        if (lane0)                                                                        \
+            for (int _i = 0; _i < 8; ++_i) atomicAdd((o).counters + 8 + _i, (unsigned long long)prof_acc[_i]); \
+        for (int _i = 0; _i < 8; ++_i) prof_acc[_i] = 0;                                  \
+    } while (0)
+#else
+#define PROF_DECL
+#define PROF_MARK(i)
+#define PROF_FLUSH(o, lane0)
+#endif
+
 namespace pdmpc {
 
 constexpr int kWarp = 32;
-constexpr unsigned kFull = 0xffffffffu;
 constexpr int kAreaStride = PDMPC_AREA_STRIDE;
 constexpr int kMaxHp = PDMPC_MAX_HP;
 
@@ -69,21 +107,28 @@ struct OutDev {
     unsigned long long *counters;  // [0] pops, [1] nodes, [2] obstacle columns tested
 };
 
-// Node arena + heap overflow of one resident CTA ("slot"), all in HBM.
-struct __align__(16) NodeA {  // 32 B: pose + cost to come
+// Node arena + heap overflow of one resident tile ("slot"), all in HBM.
+struct __align__(16) NodeA {  // 32 B: pose + cost to come, written when the node is created
     double x, y, yaw, g;
 };
-struct __align__(16) NodeB {  // 16 B
+struct __align__(16) NodeB {  // 16 B, written when the node is created
     double h;
     unsigned parent;          // 1-based, 0 for the root (Tree.m:18)
     unsigned short trim;      // 1-based
     unsigned short k;
 };
+struct __align__(16) NodeCS {  // 16 B, written when the node is expanded
+    double c, s;               // cos / sin of the node's yaw
+};
+struct __align__(16) HEnt {    // heap entry
+    double f;
+    unsigned id, pid;          // node id and its parent's id
+};
 struct ArenaDev {
     NodeA *a;                 // [slots * cap]; index 0 of each slot unused (ids are 1-based)
     NodeB *b;
-    double *heap_f;           // [slots * cap] overflow of the shared-memory heap top
-    unsigned *heap_id;
+    NodeCS *cs;
+    HEnt *heap;               // [slots * cap] overflow of the shared-memory heap top
     int cap;                  // nodes per slot
 };
 
@@ -92,6 +137,27 @@ struct TraceDev {
     long long *ids;
     long long cap;
     long long *n;
+};
+
+// ---- tile helpers -------------------------------------------------------------
+template <int TILE>
+struct Tile {
+    unsigned mask;   // lanes of this tile within the warp
+    int shift;       // first lane of the tile
+    int lane;        // lane within the tile
+    static constexpr unsigned kBits = TILE == 32 ? 0xffffffffu : ((1u << TILE) - 1u);
+
+    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+    __device__ __forceinline__ unsigned ballot(bool p) const {
+        return (__ballot_sync(mask, p) >> shift) & kBits;
+    }
+    __device__ __forceinline__ bool any(bool p) const { return __any_sync(mask, p) != 0; }
+    template <class T> __device__ __forceinline__ T shfl(T v, int src) const {
+        return __shfl_sync(mask, v, src, TILE);
+    }
+    template <class T> __device__ __forceinline__ T shfl_xor(T v, int m) const {
+        return __shfl_xor_sync(mask, v, m, TILE);
+    }
 };
 
 // ---- sin / cos (oracle/pdmpc_oracle.c holds the CPU twin) --
@@ -124,123 +190,202 @@ __device__ __forceinline__ void sincos_ref(double x, double &s, double &c) {
     else { s = -cr; c = sr; }
 }
 
-// ---- priority queue: libstdc++ heap on (f, id), min on f, ties by heap mechanics.
-// Entries [0, HS) live in shared memory (the top levels of the array heap = the
-// hottest ones), the rest in the slot's HBM overflow.  Run by lane 0 only.
-template <int HS>
+// ---- priority queue ---------------------------------------------------------
+// libstdc++ heap on (f, id), min on f, ties by heap mechanics (stl_heap.h
+// __push_heap :135-147, __adjust_heap :224-249), executed by the whole tile.
+// Entries [0, HS) live in shared memory (the top levels of the array heap are
+// the hottest), the rest in the slot's HBM overflow.  `len` is tile-uniform.
+template <int HS, int TILE>
 struct Heap {
-    double *sf;
-    unsigned *sid;
-    double *gf;
-    unsigned *gid;
+    static constexpr int LV = TILE == 32 ? 4 : (TILE == 16 ? 3 : 2);   // levels fetched per round
+    static constexpr int NL = (2 << LV) - 2;                           // lanes used per round
+    HEnt *sm;
+    HEnt *gl;
     int len;
 
-    __device__ __forceinline__ double f(int i) const { return i < HS ? sf[i] : gf[i]; }
-    __device__ __forceinline__ unsigned id(int i) const { return i < HS ? sid[i] : gid[i]; }
-    __device__ __forceinline__ void set(int i, double fv, unsigned iv) {
-        if (i < HS) { sf[i] = fv; sid[i] = iv; }
-        else { gf[i] = fv; gid[i] = iv; }
+    __device__ __forceinline__ HEnt load(int i) const { return i < HS ? sm[i] : gl[i]; }
+    __device__ __forceinline__ void store(int i, const HEnt &e) {
+        if (i < HS) sm[i] = e;
+        else gl[i] = e;
     }
-    // stl_heap.h:135-147 __push_heap, comp(parent, value) == f(parent) > value
-    __device__ __forceinline__ void sift_up(int hole, int top, double fv, unsigned iv) {
-        int parent = (hole - 1) / 2;
-        while (hole > top) {
-            double pf = f(parent);
-            if (!(pf > fv)) break;
-            set(hole, pf, id(parent));
-            hole = parent;
-            parent = (hole - 1) / 2;
+
+    // __push_heap(first, p, 0, v): ancestors of p with f > v.f move down one level,
+    // v lands above them.  All lanes hold v; entries are consistent in memory.
+    __device__ __forceinline__ void sift_up_at(int p, const HEnt &v, const Tile<TILE> &t) {
+        const int D = 31 - __clz(p + 1);               // number of ancestors of position p
+        int base = 0, T = 0;
+        for (;;) {
+            const int a = base + t.lane + 1;           // this lane's ancestor, `a` levels up
+            const bool anc = a <= D;
+            HEnt e;
+            e.f = 0.0; e.id = 0; e.pid = 0;
+            if (anc) e = load(((p + 1) >> a) - 1);
+            const unsigned gt = t.ballot(anc && e.f > v.f);
+            const int run = (gt == Tile<TILE>::kBits) ? TILE : (__ffs(~gt) - 1);   // leading run of greater parents
+            t.sync();
+            if (t.lane < run) store(((p + 1) >> (a - 1)) - 1, e);
+            T = base + run;
+            if (run < TILE || base + TILE >= D) break;
+            base += TILE;
+            t.sync();
         }
-        set(hole, fv, iv);
+        if (t.lane == 0) store(((p + 1) >> T) - 1, v);
     }
-    __device__ __forceinline__ void push(double fv, unsigned iv) {  // push_back + push_heap
-        int hole = len++;
-        sift_up(hole, 0, fv, iv);
-    }
-    // pop_heap + pop_back; stl_heap.h:224-249 __adjust_heap
-    __device__ __forceinline__ unsigned pop() {
-        unsigned top_id = id(0);
-        if (len > 1) {
-            int n = len - 1;
-            double vf = f(n);
-            unsigned vi = id(n);
-            int hole = 0, second = 0;
-            while (second < (n - 1) / 2) {
-                second = 2 * (second + 1);
-                double fr = f(second), fl = f(second - 1);
-                if (fr > fl) { second--; fr = fl; }   // comp(right, left) -> take left
-                set(hole, fr, id(second));
-                hole = second;
+
+    // pq.pop(): returns the top entry; caller guarantees len > 0.
+    __device__ __forceinline__ HEnt pop(const Tile<TILE> &t) {
+        const HEnt top = load(0);
+        const int n = len - 1;   // heap size after the pop; entry[n] is re-inserted
+        if (n > 0) {
+            const HEnt v = load(n);
+            t.sync();            // every lane has read top / v before any entry moves
+            // lane -> descendant (level d = 1..LV below the hole, offset o) for lanes 0..NL-1
+            const int d = 31 - __clz(t.lane + 2);
+            const int o = t.lane + 2 - (1 << d);
+            int hole = 0;
+            double lastf = 0.0;
+            bool moved = false;
+            const int lim = (n - 1) / 2;
+            while (hole < lim) {
+                const int idx = ((hole + 1) << d) - 1 + o;
+                HEnt e;
+                e.f = 0.0; e.id = 0; e.pid = 0;
+                if (t.lane < NL && idx < n) e = load(idx);
+                // sibling pairs are lanes (2r, 2r+1): the right one is taken unless f_right > f_left
+                const double fs = t.shfl_xor(e.f, 1);
+                const bool pick = (t.lane & 1) ? !(e.f > fs) : (fs > e.f);
+                const unsigned picks = t.ballot(pick);
+                int rel = 0, sel = 0;
+                bool on = false;
+#pragma unroll
+                for (int lv = 1; lv <= LV; ++lv) {
+                    if (hole < lim) {   // both children exist
+                        const int left_lane = (1 << lv) - 2 + 2 * rel;
+                        const int right = (picks >> (left_lane + 1)) & 1;
+                        sel = left_lane + right;
+                        on = on || (t.lane == sel);
+                        hole = 2 * hole + 1 + right;
+                        rel = 2 * rel + right;
+                    }
+                }
+                if (on) store((idx - 1) >> 1, e);      // picked child moves into its parent's place
+                lastf = t.shfl(e.f, sel);
+                moved = true;
             }
-            if ((n & 1) == 0 && second == (n - 2) / 2) {
-                second = 2 * (second + 1);
-                set(hole, f(second - 1), id(second - 1));
-                hole = second - 1;
+            if ((n & 1) == 0 && hole == (n - 2) / 2) {   // single (left) child at n-1
+                const HEnt e = load(n - 1);
+                if (t.lane == 0) store(hole, e);
+                lastf = e.f;
+                hole = n - 1;
+                moved = true;
             }
-            sift_up(hole, 0, vf, vi);
+            if (!moved || !(lastf > v.f)) {
+                if (t.lane == 0) store(hole, v);
+            } else {
+                t.sync();
+                sift_up_at(hole, v, t);
+            }
         }
-        --len;
-        return top_id;
+        len = n;
+        t.sync();
+        return top;
+    }
+
+    // pq.push of m <= TILE entries in lane order (lane q holds entry q).  Children
+    // that need no sift-up are appended together; the first one that does is
+    // pushed on its own, then the rest is retried.
+    __device__ __forceinline__ void push_many(const HEnt &mine, int m, const Tile<TILE> &t) {
+        int done = 0;
+        while (done < m) {
+            const bool act = t.lane >= done && t.lane < m;
+            const int p = len + (t.lane - done);
+            const int par = (p - 1) >> 1;
+            bool need = false;
+            const int src = done + max(par - len, 0);
+            const double nf = t.shfl(mine.f, src & (TILE - 1));
+            if (act && p > 0) {
+                const double pf = (par < len) ? load(par).f : nf;
+                need = pf > mine.f;
+            }
+            const unsigned mask = t.ballot(need);
+            const int nfast = mask ? (__ffs(mask) - 1 - done) : (m - done);
+            if (act && t.lane < done + nfast) store(p, mine);
+            len += nfast;
+            done += nfast;
+            t.sync();
+            if (done < m) {
+                HEnt v;
+                v.f = t.shfl(mine.f, done);
+                v.id = t.shfl(mine.id, done);
+                v.pid = t.shfl(mine.pid, done);
+                sift_up_at(len, v, t);
+                ++len;
+                ++done;
+                t.sync();
+            }
+        }
     }
 };
 
-// ---- InterX (InterX.m:63-85,108-110) of a shape with NE segments against the
-// NaN-separated polyline points [lo, hi).  Lanes own contiguous runs of
-// segments; C1 (shape edge i separates the two obstacle points) is evaluated for
-// every pair, C2 only where C1 holds.  The boolean any(C1 & C2) is the same as
-// the reference's dense evaluation.
-template <int NE>
-__device__ __forceinline__ bool interx_range(const double *__restrict__ px, const double *__restrict__ py,
-                                             int lo, int hi, const double *shx, const double *shy,
-                                             int lane) {
-    const int nseg = hi - lo - 1;
-    if (nseg < 1) return false;   // InterX.m:48-52 and single-column inputs
-    double dx1[NE], dy1[NE], S1[NE];
-#pragma unroll
-    for (int i = 0; i < NE; ++i) {
-        dx1[i] = shx[i + 1] - shx[i];
-        dy1[i] = shy[i + 1] - shy[i];
-        S1[i] = dx1[i] * shy[i] - dy1[i] * shx[i];
-    }
-    const int per = (nseg + kWarp - 1) / kWarp;
-    int j0 = lo + lane * per;
-    int j1 = min(j0 + per, lo + nseg);
+// ---- InterX (InterX.m:63-85,108-110) ---------------------------------------
+// Shape (NE segments, points in shared memory) against the NaN-separated polyline
+// points [lo, hi) of (px, py).  Lane = (slot, edge i): the lane keeps edge i's
+// constants in registers and walks the slot's contiguous run of obstacle
+// segments; C1 (edge i separates the two obstacle points) is evaluated for every
+// pair, C2 only where C1 holds.  any(C1 & C2) is the reference's boolean.
+template <int NE, int TILE>
+__device__ __forceinline__ bool interx_ranges(const double *__restrict__ px, const double *__restrict__ py,
+                                              int lo0, int hi0, int lo1, int hi1, const double *shx,
+                                              const double *shy, const Tile<TILE> &t) {
+    constexpr int S = TILE / NE;                 // point slots
+    const int i = t.lane % NE, slot = t.lane / NE;
+    const bool lane_on = slot < S;
+    const double x1a = shx[i], y1a = shy[i], x1b = shx[i + 1], y1b = shy[i + 1];
+    const double dx1 = x1b - x1a, dy1 = y1b - y1a;
+    const double S1 = dx1 * y1a - dy1 * x1a;
     bool hit = false;
-    if (j0 < j1) {
-        double x = __ldg(px + j0), y = __ldg(py + j0);
-        double a[NE];
-#pragma unroll
-        for (int i = 0; i < NE; ++i) a[i] = (dx1[i] * y - dy1[i] * x) - S1[i];
-        for (int j = j0; j < j1; ++j) {
-            double xn = __ldg(px + j + 1), yn = __ldg(py + j + 1);
-#pragma unroll
-            for (int i = 0; i < NE; ++i) {
-                double an = (dx1[i] * yn - dy1[i] * xn) - S1[i];
-                if (a[i] * an < 0) {                       // C1(i,j)
-                    double dx2 = xn - x, dy2 = yn - y;
-                    double S2 = dx2 * y - dy2 * x;
-                    double b0 = (shy[i] * dx2 - shx[i] * dy2) - S2;
-                    double b1 = (shy[i + 1] * dx2 - shx[i + 1] * dy2) - S2;
-                    if (b0 * b1 < 0) hit = true;           // C2(i,j)
+#pragma unroll 1
+    for (int r = 0; r < 2; ++r) {
+        const int lo = r ? lo1 : lo0, hi = r ? hi1 : hi0;
+        const int nseg = hi - lo - 1;
+        if (nseg < 1) continue;                  // InterX.m:48-52 and single-column inputs
+        const int per = (nseg + S - 1) / S;
+        const int j0 = lo + slot * per;
+        const int j1 = min(j0 + per, lo + nseg);
+        if (lane_on && j0 < j1) {
+            double x = __ldg(px + j0), y = __ldg(py + j0);
+            double a = (dx1 * y - dy1 * x) - S1;
+            for (int j = j0; j < j1; ++j) {
+                const double xn = __ldg(px + j + 1), yn = __ldg(py + j + 1);
+                const double an = (dx1 * yn - dy1 * xn) - S1;
+                if (a * an < 0) {                                 // C1(i,j)
+                    const double dx2 = xn - x, dy2 = yn - y;
+                    const double S2 = dx2 * y - dy2 * x;
+                    const double b0 = (y1a * dx2 - x1a * dy2) - S2;
+                    const double b1 = (y1b * dx2 - x1b * dy2) - S2;
+                    if (b0 * b1 < 0) hit = true;                  // C2(i,j)
                 }
-                a[i] = an;
+                a = an;
+                x = xn;
+                y = yn;
             }
-            x = xn;
-            y = yn;
         }
     }
-    return __any_sync(kFull, hit);
+    return t.any(hit);
 }
 
-__device__ __forceinline__ bool interx_dispatch(int ns, const double *px, const double *py, int lo, int hi,
-                                                const double *shx, const double *shy, int lane) {
+template <int TILE>
+__device__ __forceinline__ bool interx_dispatch(int ns, const double *px, const double *py, int lo0, int hi0,
+                                                int lo1, int hi1, const double *shx, const double *shy,
+                                                const Tile<TILE> &t) {
     switch (ns) {   // ns points -> ns-1 segments; maneuver areas have 5, 6 or 7 points
-    case 5: return interx_range<4>(px, py, lo, hi, shx, shy, lane);
-    case 6: return interx_range<5>(px, py, lo, hi, shx, shy, lane);
-    case 7: return interx_range<6>(px, py, lo, hi, shx, shy, lane);
+    case 5: return interx_ranges<4, TILE>(px, py, lo0, hi0, lo1, hi1, shx, shy, t);
+    case 6: return interx_ranges<5, TILE>(px, py, lo0, hi0, lo1, hi1, shx, shy, t);
+    case 7: return interx_ranges<6, TILE>(px, py, lo0, hi0, lo1, hi1, shx, shy, t);
     default: {
         bool hit = false;   // generic (never taken with MPA areas): one shape segment at a time
-        for (int i = 0; i + 1 < ns && !hit; ++i) hit = interx_range<1>(px, py, lo, hi, shx + i, shy + i, lane);
+        for (int i = 0; i + 1 < ns && !hit; ++i)
+            hit = interx_ranges<1, TILE>(px, py, lo0, hi0, lo1, hi1, shx + i, shy + i, t);
         return hit;
     }
     }
@@ -248,11 +393,12 @@ __device__ __forceinline__ bool interx_dispatch(int ns, const double *px, const 
 
 // ---- SAT (intersect_sat.m:1-42): polygon 1 in shared memory, polygon 2 in
 // global memory.  Lanes own axes (edges of both polygons incl. the closing one).
+template <int TILE>
 __device__ __forceinline__ bool sat_collide(const double *x1, const double *y1, int n1,
                                             const double *__restrict__ x2, const double *__restrict__ y2,
-                                            int n2, int lane) {
+                                            int n2, const Tile<TILE> &t) {
     bool sep = false;
-    for (int e = lane; e < n1 + n2; e += kWarp) {
+    for (int e = t.lane; e < n1 + n2; e += TILE) {
         double ex, ey;
         if (e < n1) {
             int e1 = (e + 1 == n1) ? 0 : e + 1;
@@ -280,13 +426,14 @@ __device__ __forceinline__ bool sat_collide(const double *x1, const double *y1, 
         // d1/d2 of intersect_a_b; which polygon owns the axis only swaps them
         if ((mn1 - mx2 > 0) || (mn2 - mx1 > 0)) sep = true;
     }
-    return !__any_sync(kFull, sep);
+    return !t.any(sep);
 }
 
 // ---- intersect_lanelet_boundary.m:1-56 for one side; lanes own boundary segments.
+template <int TILE>
 __device__ __forceinline__ bool lanelet_side_sat(const double *sx, const double *sy, int ns,
                                                  const double *__restrict__ bx, const double *__restrict__ by,
-                                                 int nb, int lane) {
+                                                 int nb, const Tile<TILE> &t) {
     if (nb < 2) return false;
     double max_x = sx[0], min_x = sx[0], max_y = sy[0], min_y = sy[0];
     for (int i = 1; i < ns; ++i) {
@@ -296,7 +443,7 @@ __device__ __forceinline__ bool lanelet_side_sat(const double *sx, const double 
         min_y = fmin(min_y, sy[i]);
     }
     bool hit = false;
-    for (int n = lane; n + 1 < nb; n += kWarp) {
+    for (int n = t.lane; n + 1 < nb; n += TILE) {
         double ax = __ldg(bx + n), bx2 = __ldg(bx + n + 1), ay = __ldg(by + n), by2 = __ldg(by + n + 1);
         if ((max_x < ax && max_x < bx2) || (min_x > ax && min_x > bx2) || (max_y < ay && max_y < by2) ||
             (min_y > ay && min_y > by2))
@@ -330,19 +477,15 @@ __device__ __forceinline__ bool lanelet_side_sat(const double *sx, const double 
         }
         if (!sep) hit = true;
     }
-    return __any_sync(kFull, hit);
+    return t.any(hit);
 }
 
-__device__ __forceinline__ unsigned long long fnv1a_u32(unsigned long long h, unsigned v) {
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        h ^= (unsigned long long)((v >> (8 * b)) & 0xffu);
-        h *= 0x100000001b3ULL;
-    }
-    return h;
+// FNV-1a over the popped ids taken as 32-bit words (parity trace of the pop order)
+__device__ __forceinline__ unsigned long long hash_step(unsigned long long h, unsigned v) {
+    return (h ^ (unsigned long long)v) * 0x100000001b3ULL;
 }
 
-// Rotate/translate one maneuver area into smem: GraphSearch.m:158-159.
+// Rotate/translate one maneuver area point: GraphSearch.m:158-159.
 __device__ __forceinline__ void place_point(const MpaDev &m, int edge, int kind, int i, double c, double s,
                                             double px, double py, double &ox, double &oy) {
     const int base = (edge * 3 + kind) * kAreaStride + i;
@@ -351,248 +494,285 @@ __device__ __forceinline__ void place_point(const MpaDev &m, int edge, int kind,
     oy = s * ax + c * ay + py;
 }
 
-// ============================================================================
-// The search kernel.  Persistent: CTA `blockIdx.x` owns arena slot blockIdx.x
-// and pulls search indices from a global counter until the batch is drained.
 template <int HS>
+struct __align__(16) TileSmem {
+    HEnt heap[HS];
+    double refx[kMaxHp], refy[kMaxHp], vref[kMaxHp];
+    double shx[kAreaStride], shy[kAreaStride];   // shape (normal offset)
+    double bhx[kAreaStride], bhy[kAreaStride];   // boundary-check shape
+    unsigned path[kMaxHp + 1];
+};
+
+// ============================================================================
+// The search kernel.  Persistent: every tile owns one arena slot and pulls
+// search indices from a global counter until the batch is drained.  The body is
+// ONE loop (a small state machine) so that the tiles of a warp stay converged:
+// an iteration is "finish / fetch a search if needed, then one pop".
+template <int HS, int TILE>
 __global__ void __launch_bounds__(kWarp) search_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar,
                                                        unsigned *work_counter, TraceDev tr) {
-    __shared__ double s_heap_f[HS];
-    __shared__ unsigned s_heap_id[HS];
-    __shared__ double s_refx[kMaxHp], s_refy[kMaxHp], s_vref[kMaxHp];
-    __shared__ double s_shx[kAreaStride], s_shy[kAreaStride];   // shape (normal offset)
-    __shared__ double s_bhx[kAreaStride], s_bhy[kAreaStride];   // boundary-check shape
-    __shared__ double s_f[kWarp];                               // children's f, push order
+    constexpr int NT = kWarp / TILE;
+    __shared__ TileSmem<HS> s_tiles[NT];
 
-    const int lane = threadIdx.x;
+    Tile<TILE> t;
+    t.shift = (threadIdx.x / TILE) * TILE;
+    t.lane = threadIdx.x % TILE;
+    t.mask = Tile<TILE>::kBits << t.shift;
+    TileSmem<HS> &sm = s_tiles[threadIdx.x / TILE];
+
     const int Hp = m.Hp, nT = m.nT;
-    const size_t slot_base = (size_t)blockIdx.x * (size_t)ar.cap;
+    const size_t slot_base = ((size_t)blockIdx.x * NT + threadIdx.x / TILE) * (size_t)ar.cap;
     NodeA *__restrict__ na = ar.a + slot_base;
     NodeB *__restrict__ nb = ar.b + slot_base;
-    Heap<HS> heap;
-    heap.sf = s_heap_f;
-    heap.sid = s_heap_id;
-    heap.gf = ar.heap_f + slot_base;
-    heap.gid = ar.heap_id + slot_base;
+    NodeCS *__restrict__ ncs = ar.cs + slot_base;
+    Heap<HS, TILE> heap;
+    heap.sm = sm.heap;
+    heap.gl = ar.heap + slot_base;
+    heap.len = 0;
+
+    enum { IDLE = 0, RUN = 1, DONE = 2 };
+    int phase = IDLE;
+    PROF_DECL
+    int si = 0, trim0 = 0;
+    const int *slot = nullptr;
+    int st_lo = 0, st_hi = 0, ll_lo = 0, ll_hi = 0, sp0 = 0, sp1 = 0, lp0 = 0, lp1 = 0, lp2 = 0;
+    int n_nodes = 0, n_pops = 0, status = PDMPC_OK;
+    unsigned long long hash = 0, cols = 0;
+    bool exhausted = false;
+    unsigned goal = 0;
 
     for (;;) {
-        unsigned si_u = 0;
-        if (lane == 0) si_u = atomicAdd(work_counter, 1u);
-        si_u = __shfl_sync(kFull, si_u, 0);
-        if (si_u >= (unsigned)b.n) break;
-        const int si = (int)si_u;
-
-        // ---- per-search set-up ------------------------------------------------
-        __syncwarp();
-        if (lane < Hp) {
-            s_refx[lane] = __ldg(b.ref_x + (size_t)si * Hp + lane);
-            s_refy[lane] = __ldg(b.ref_y + (size_t)si * Hp + lane);
-            s_vref[lane] = __ldg(b.v_ref + (size_t)si * Hp + lane);
-        }
-        const int *slot = b.slot_ptr + (size_t)si * (Hp + 1);
-        const int trim0 = __ldg(b.trim0 + si);
-        if (lane == 0) {   // root: GraphSearch.m:34-46
-            NodeA ra;
-            ra.x = __ldg(b.x0 + si); ra.y = __ldg(b.y0 + si); ra.yaw = __ldg(b.yaw0 + si); ra.g = 0.0;
-            NodeB rb;
-            rb.h = 0.0; rb.parent = 0; rb.trim = (unsigned short)trim0; rb.k = 0;
-            na[1] = ra;
-            nb[1] = rb;
-            heap.len = 0;
-            heap.push(0.0, 1u);
-        }
-        __syncwarp();
-        // static-obstacle polyline range and lanelet polyline range (InterX layout)
-        const int sp0 = __ldg(slot + 0), sp1 = __ldg(slot + 1);
-        const int st_lo = __ldg(b.poly_ptr + sp0) + sp0, st_hi = __ldg(b.poly_ptr + sp1) + sp1;
-        const int lp0 = __ldg(b.lane_ptr + 2 * si), lp1 = __ldg(b.lane_ptr + 2 * si + 1),
-                  lp2 = __ldg(b.lane_ptr + 2 * si + 2);
-        const int ll_lo = lp0 + 2 * si, ll_hi = lp2 + 2 * si + 2;
-
-        int n_nodes = 1, n_pops = 0;
-        unsigned long long hash = 0xcbf29ce484222325ULL, cols = 0;
-        int status = PDMPC_OK;
-        bool exhausted = false;
-        unsigned goal = 0;
-        const bool tracing = (tr.search == si);
-
-        // ---- best-first loop: GraphSearch.m:53-107 ------------------------------
-        for (;;) {
-            unsigned id = 0;
-            if (lane == 0) {
-                if (heap.len > 0) id = heap.pop();   // 0 == the reference's -1 (empty)
+        PROF_MARK(7);
+        if (phase == DONE) {
+            PROF_FLUSH(o, t.lane == 0);
+            // ---- results: GraphSearch.m:58-60 / :82-89 --------------------------
+            t.sync();
+            if (status != PDMPC_OK) exhausted = true;   // outputs take the "no plan" defaults
+            if (t.lane == 0) {
+                unsigned cur = goal;
+                for (int d = Hp; d >= 0; --d) {           // Tree.m:44-52 path_to_root, flipped
+                    sm.path[d] = exhausted ? 0u : cur;
+                    if (!exhausted && d > 0) cur = nb[cur].parent;
+                }
+                o.status[si] = status;
+                if (o.is_exhausted) o.is_exhausted[si] = exhausted ? 1 : 0;
+                if (o.n_expanded) o.n_expanded[si] = n_nodes;
+                if (o.n_pops) o.n_pops[si] = n_pops;
+                if (o.pop_hash) o.pop_hash[si] = hash;
+                atomicAdd(o.counters + 0, (unsigned long long)n_pops);
+                atomicAdd(o.counters + 1, (unsigned long long)n_nodes);
+                atomicAdd(o.counters + 2, cols);
             }
-            id = __shfl_sync(kFull, id, 0);
-            if (id == 0) { exhausted = true; break; }   // :57-61
-            ++n_pops;
-            hash = fnv1a_u32(hash, id);
-            if (tracing && lane == 0) {
-                if (n_pops <= tr.cap) tr.ids[n_pops - 1] = (long long)id;
-                *tr.n = n_pops;
-            }
-
-            const NodeB cb = nb[id];
-            const NodeA ca = na[id];
-            const unsigned par = cb.parent;
-            const int cK = cb.k;
-            bool valid = true;
-            if (par != 0) {   // eval_edge_exact :137-192 (root is valid unchecked)
-                const NodeA pa = na[par];
-                const int t1 = nb[par].trim, t2 = cb.trim;
-                const int edge = __ldg(m.edge_of + (t1 - 1) * nT + (t2 - 1));
-                double s, c;
-                sincos_ref(pa.yaw, s, c);   // :155-156
-                const int ns = __ldg(m.area_npts + edge * 3 + PDMPC_AREA_NORMAL);
-                const int bkind = (cK == Hp) ? PDMPC_AREA_LARGE_OFFSET : PDMPC_AREA_WITHOUT_OFFSET;  // :166-174
-                const int nbs = __ldg(m.area_npts + edge * 3 + bkind);
-                __syncwarp();
-                if (lane < ns) place_point(m, edge, PDMPC_AREA_NORMAL, lane, c, s, pa.x, pa.y, s_shx[lane], s_shy[lane]);
-                else if (lane >= 8 && lane - 8 < nbs)
-                    place_point(m, edge, bkind, lane - 8, c, s, pa.x, pa.y, s_bhx[lane - 8], s_bhy[lane - 8]);
-                __syncwarp();
-
-                const int dp0 = __ldg(slot + cK), dp1 = __ldg(slot + cK + 1);
-                if (b.checker == PDMPC_CHECKER_INTERX) {
-                    // are_constraints_satisfied_interx.m:17,34 (no HDVs)
-                    const int dy_lo = __ldg(b.poly_ptr + dp0) + dp0, dy_hi = __ldg(b.poly_ptr + dp1) + dp1;
-                    cols += (unsigned long long)((st_hi - st_lo) + (dy_hi - dy_lo) + (ll_hi - ll_lo));
-                    if (interx_dispatch(ns, b.pl_x, b.pl_y, st_lo, st_hi, s_shx, s_shy, lane)) valid = false;
-                    else if (interx_dispatch(ns, b.pl_x, b.pl_y, dy_lo, dy_hi, s_shx, s_shy, lane)) valid = false;
-                    else if (interx_dispatch(nbs, b.ll_x, b.ll_y, ll_lo, ll_hi, s_bhx, s_bhy, lane)) valid = false;
-                } else {
-                    // are_constraints_satisfied_sat.m:15-53 (nV == 1; HDV block unreachable)
-                    for (int pass = 0; pass < 2 && valid; ++pass) {
-                        const int q0 = pass == 0 ? sp0 : dp0, q1 = pass == 0 ? sp1 : dp1;
-                        for (int p = q0; p < q1 && valid; ++p) {
-                            const int v0 = __ldg(b.poly_ptr + p), v1 = __ldg(b.poly_ptr + p + 1);
-                            cols += (unsigned long long)(v1 - v0);
-                            if (sat_collide(s_shx, s_shy, ns, b.vert_x + v0, b.vert_y + v0, v1 - v0, lane))
-                                valid = false;
+            t.sync();
+            const double qnan = nan("");
+            for (int d = t.lane; d <= Hp; d += TILE) {
+                const unsigned pid = sm.path[d];
+                NodeA pa = {qnan, qnan, qnan, qnan};
+                NodeB pb;
+                pb.h = qnan; pb.parent = 0; pb.trim = 0; pb.k = 0;
+                if (!exhausted) { pa = na[pid]; pb = nb[pid]; }
+                const size_t oo = (size_t)si * (Hp + 1) + d;
+                if (o.trims) o.trims[oo] = exhausted ? (d == 0 ? trim0 : 0) : (int)pb.trim;
+                if (o.tree_path) o.tree_path[oo] = (int)pid;
+                if (o.g_path) o.g_path[oo] = pa.g;
+                if (o.h_path) o.h_path[oo] = pb.h;
+                if (d >= 1) {
+                    const size_t os = (size_t)si * Hp + (d - 1);
+                    if (o.y_predicted) {                   // return_path_to.m:11-25
+                        o.y_predicted[os * 3 + 0] = pa.x;
+                        o.y_predicted[os * 3 + 1] = pa.y;
+                        o.y_predicted[os * 3 + 2] = pa.yaw;
+                    }
+                    if (o.shape_npts) {                    // return_path_area.m:5-7
+                        int edge = 0, ns = 0;
+                        NodeA qa = {0.0, 0.0, 0.0, 0.0};
+                        NodeCS qcs = {0.0, 0.0};
+                        if (!exhausted) {
+                            const unsigned qid = sm.path[d - 1];   // parent on the path (was expanded)
+                            qa = na[qid];
+                            qcs = ncs[qid];
+                            edge = __ldg(m.edge_of + ((int)nb[qid].trim - 1) * nT + ((int)pb.trim - 1));
+                            ns = __ldg(m.area_npts + edge * 3 + PDMPC_AREA_NORMAL);
+                        }
+                        o.shape_npts[os] = ns;
+                        if (o.shape_x && o.shape_y) {
+                            for (int i = 0; i < kAreaStride; ++i) {
+                                double ox = 0.0, oy = 0.0;
+                                if (i < ns) place_point(m, edge, PDMPC_AREA_NORMAL, i, qcs.c, qcs.s, qa.x, qa.y, ox, oy);
+                                o.shape_x[os * kAreaStride + i] = ox;
+                                o.shape_y[os * kAreaStride + i] = oy;
+                            }
                         }
                     }
-                    if (valid) {
-                        cols += (unsigned long long)(lp2 - lp0);
-                        if (lanelet_side_sat(s_bhx, s_bhy, nbs, b.lane_x + lp0, b.lane_y + lp0, lp1 - lp0, lane))
-                            valid = false;
-                        else if (lanelet_side_sat(s_bhx, s_bhy, nbs, b.lane_x + lp1, b.lane_y + lp1, lp2 - lp1, lane))
-                            valid = false;
-                    }
                 }
             }
-            if (!valid) continue;                      // :75-77
-            if (cK == Hp) { goal = id; break; }        // :81-90
+            phase = IDLE;
+        }
+        if (phase == IDLE) {
+            unsigned si_u = 0;
+            if (t.lane == 0) si_u = atomicAdd(work_counter, 1u);
+            si_u = t.shfl(si_u, 0);
+            if (si_u >= (unsigned)b.n) break;
+            si = (int)si_u;
+            // ---- per-search set-up ------------------------------------------------
+            t.sync();
+            for (int k = t.lane; k < Hp; k += TILE) {
+                sm.refx[k] = __ldg(b.ref_x + (size_t)si * Hp + k);
+                sm.refy[k] = __ldg(b.ref_y + (size_t)si * Hp + k);
+                sm.vref[k] = __ldg(b.v_ref + (size_t)si * Hp + k);
+            }
+            slot = b.slot_ptr + (size_t)si * (Hp + 1);
+            trim0 = __ldg(b.trim0 + si);
+            if (t.lane == 0) {   // root: GraphSearch.m:34-46
+                NodeA ra;
+                ra.x = __ldg(b.x0 + si); ra.y = __ldg(b.y0 + si); ra.yaw = __ldg(b.yaw0 + si); ra.g = 0.0;
+                NodeB rb;
+                rb.h = 0.0; rb.parent = 0; rb.trim = (unsigned short)trim0; rb.k = 0;
+                na[1] = ra;
+                nb[1] = rb;
+                HEnt re;
+                re.f = 0.0; re.id = 1u; re.pid = 0u;
+                heap.store(0, re);
+            }
+            heap.len = 1;
+            // static-obstacle polyline range and lanelet polyline range (InterX layout)
+            sp0 = __ldg(slot + 0); sp1 = __ldg(slot + 1);
+            st_lo = __ldg(b.poly_ptr + sp0) + sp0; st_hi = __ldg(b.poly_ptr + sp1) + sp1;
+            lp0 = __ldg(b.lane_ptr + 2 * si); lp1 = __ldg(b.lane_ptr + 2 * si + 1);
+            lp2 = __ldg(b.lane_ptr + 2 * si + 2);
+            ll_lo = lp0 + 2 * si; ll_hi = lp2 + 2 * si + 2;
+            n_nodes = 1; n_pops = 0;
+            hash = 0xcbf29ce484222325ULL; cols = 0;
+            status = PDMPC_OK;
+            exhausted = false;
+            goal = 0;
+            phase = RUN;
+            t.sync();
+        }
+        PROF_MARK(0);   // finalize + fetch + set-up
 
-            // ---- expand_node.m:1-91 (nV == 1) ----------------------------------
-            const int k_exp = cK + 1;
-            const int sbase = __ldg(m.succ_ptr + (k_exp - 1) * nT + (cb.trim - 1));
-            const int nchild = __ldg(m.succ_ptr + (k_exp - 1) * nT + (cb.trim - 1) + 1) - sbase;
-            if (n_nodes + nchild >= ar.cap) { status = PDMPC_ERR_CAPACITY; break; }
-            double s, c;
-            sincos_ref(ca.yaw, s, c);                   // :50-51
-            const int to_go = Hp - k_exp;               // :37
-            for (int c0 = 0; c0 < nchild; c0 += kWarp) {
-                const int ci = c0 + lane;
-                const unsigned nid = (unsigned)(n_nodes + 1 + ci);
-                if (ci < nchild) {
-                    const int t2 = __ldg(m.succ_trim + sbase + ci);
-                    const int edge = __ldg(m.succ_edge + sbase + ci);
-                    const double dx = __ldg(m.edge_dx + edge), dy = __ldg(m.edge_dy + edge),
-                                 dyaw = __ldg(m.edge_dyaw + edge);
-                    NodeA ea;
-                    ea.x = c * dx - s * dy + ca.x;      // :53
-                    ea.y = s * dx + c * dy + ca.y;      // :54
-                    ea.yaw = ca.yaw + dyaw;             // :55
-                    const double ddx = ea.x - s_refx[k_exp - 1], ddy = ea.y - s_refy[k_exp - 1];
-                    const double nrm = sqrt(ddx * ddx + ddy * ddy);
-                    ea.g = ca.g + nrm * nrm;            // :61
-                    double eh = 0.0, d_max = 0.0;       // :66-73
-                    for (int it = 1; it <= to_go; ++it) {
-                        d_max = d_max + b.dt * s_vref[k_exp + it - 1];
-                        const double hx = ea.x - s_refx[k_exp + it - 1], hy = ea.y - s_refy[k_exp + it - 1];
-                        const double hn = sqrt(hx * hx + hy * hy);
-                        const double mm = fmax(0.0, hn - d_max);
-                        eh = eh + mm * mm;
-                    }
-                    NodeB eb;
-                    eb.h = eh; eb.parent = id; eb.trim = (unsigned short)t2; eb.k = (unsigned short)k_exp;
-                    na[nid] = ea;                       // Tree.m:54-70 add_nodes
-                    nb[nid] = eb;
-                    s_f[lane] = ea.g + eh;              // GraphSearch.m:102 (weights 1)
-                }
-                __syncwarp();
-                if (lane == 0) {                        // :104, one push per child in order
-                    const int cnt = min(kWarp, nchild - c0);
-                    for (int q = 0; q < cnt; ++q) heap.push(s_f[q], (unsigned)(n_nodes + 1 + c0 + q));
-                }
-                __syncwarp();
-            }
-            n_nodes += nchild;
+        // ---- one iteration of the best-first loop: GraphSearch.m:53-107 ----------
+        if (heap.len == 0) { exhausted = true; phase = DONE; continue; }   // :57-61
+        const HEnt top = heap.pop(t);
+        PROF_MARK(1);   // heap pop
+        const unsigned id = top.id, par = top.pid;
+        ++n_pops;
+        hash = hash_step(hash, id);
+        if (tr.search == si && t.lane == 0) {
+            if (n_pops <= tr.cap) tr.ids[n_pops - 1] = (long long)id;
+            *tr.n = n_pops;
         }
 
-        // ---- results: GraphSearch.m:58-60 / :82-89 ------------------------------
-        __syncwarp();
-        if (status != PDMPC_OK) exhausted = true;   // outputs take the "no plan" defaults
-        unsigned path_id = 0;     // lane d holds path[d], d = 0..Hp
-        {
-            unsigned cur = goal;
-            for (int d = Hp; d >= 0; --d) {           // Tree.m:44-52 path_to_root, flipped
-                if (lane == d) path_id = cur;
-                if (!exhausted && d > 0) cur = nb[cur].parent;
+        // one round of independent loads: own record and the parent's
+        const NodeB cb = nb[id];
+        const NodeA ca = na[id];
+        const int cK = cb.k;
+        bool valid = true;
+        if (par != 0) {   // eval_edge_exact :137-192 (root is valid unchecked)
+            const NodeA pa = na[par];
+            const NodeCS pcs = ncs[par];              // cos/sin(parent yaw), :155-156
+            const int t1 = nb[par].trim, t2 = cb.trim;
+            const int edge = __ldg(m.edge_of + (t1 - 1) * nT + (t2 - 1));
+            const int ns = __ldg(m.area_npts + edge * 3 + PDMPC_AREA_NORMAL);
+            const int bkind = (cK == Hp) ? PDMPC_AREA_LARGE_OFFSET : PDMPC_AREA_WITHOUT_OFFSET;  // :166-174
+            const int nbs = __ldg(m.area_npts + edge * 3 + bkind);
+            t.sync();
+            if (TILE >= 16) {
+                if (t.lane < ns)
+                    place_point(m, edge, PDMPC_AREA_NORMAL, t.lane, pcs.c, pcs.s, pa.x, pa.y, sm.shx[t.lane], sm.shy[t.lane]);
+                else if (t.lane >= 8 && t.lane - 8 < nbs)
+                    place_point(m, edge, bkind, t.lane - 8, pcs.c, pcs.s, pa.x, pa.y, sm.bhx[t.lane - 8], sm.bhy[t.lane - 8]);
+            } else {
+                if (t.lane < ns)
+                    place_point(m, edge, PDMPC_AREA_NORMAL, t.lane, pcs.c, pcs.s, pa.x, pa.y, sm.shx[t.lane], sm.shy[t.lane]);
+                if (t.lane < nbs)
+                    place_point(m, edge, bkind, t.lane, pcs.c, pcs.s, pa.x, pa.y, sm.bhx[t.lane], sm.bhy[t.lane]);
             }
-        }
-        if (lane == 0) {
-            o.status[si] = status;
-            if (o.is_exhausted) o.is_exhausted[si] = exhausted ? 1 : 0;
-            if (o.n_expanded) o.n_expanded[si] = n_nodes;
-            if (o.n_pops) o.n_pops[si] = n_pops;
-            if (o.pop_hash) o.pop_hash[si] = hash;
-            atomicAdd(o.counters + 0, (unsigned long long)n_pops);
-            atomicAdd(o.counters + 1, (unsigned long long)n_nodes);
-            atomicAdd(o.counters + 2, cols);
-        }
-        const double qnan = nan("");
-        NodeA pa_l = {qnan, qnan, qnan, qnan};
-        NodeB pb_l;
-        pb_l.h = qnan; pb_l.parent = 0; pb_l.trim = 0; pb_l.k = 0;
-        if (lane <= Hp && !exhausted) { pa_l = na[path_id]; pb_l = nb[path_id]; }
-        if (lane <= Hp) {
-            const size_t oo = (size_t)si * (Hp + 1) + lane;
-            if (o.trims) o.trims[oo] = exhausted ? (lane == 0 ? trim0 : 0) : (int)pb_l.trim;
-            if (o.tree_path) o.tree_path[oo] = exhausted ? 0 : (int)path_id;
-            if (o.g_path) o.g_path[oo] = pa_l.g;
-            if (o.h_path) o.h_path[oo] = pb_l.h;
-            if (lane >= 1 && o.y_predicted) {          // return_path_to.m:11-25
-                const size_t oy = ((size_t)si * Hp + (lane - 1)) * 3;
-                o.y_predicted[oy + 0] = pa_l.x;
-                o.y_predicted[oy + 1] = pa_l.y;
-                o.y_predicted[oy + 2] = pa_l.yaw;
-            }
-        }
-        if (o.shape_npts) {                            // return_path_area.m:5-7
-            // lane d (1..Hp) needs its parent's pose/trim = lane d-1's values
-            const double ppx = __shfl_up_sync(kFull, pa_l.x, 1), ppy = __shfl_up_sync(kFull, pa_l.y, 1),
-                         ppyaw = __shfl_up_sync(kFull, pa_l.yaw, 1);
-            const int ptrim = __shfl_up_sync(kFull, (int)pb_l.trim, 1);
-            int edge = 0, ns = 0;
-            double s = 0.0, c = 0.0;
-            if (lane >= 1 && lane <= Hp && !exhausted) {
-                edge = __ldg(m.edge_of + (ptrim - 1) * nT + ((int)pb_l.trim - 1));
-                ns = __ldg(m.area_npts + edge * 3 + PDMPC_AREA_NORMAL);
-                sincos_ref(ppyaw, s, c);
-            }
-            if (lane >= 1 && lane <= Hp) {
-                const size_t os = (size_t)si * Hp + (lane - 1);
-                o.shape_npts[os] = ns;
-                if (o.shape_x && o.shape_y) {
-                    for (int i = 0; i < kAreaStride; ++i) {
-                        double ox = 0.0, oy = 0.0;
-                        if (i < ns) place_point(m, edge, PDMPC_AREA_NORMAL, i, c, s, ppx, ppy, ox, oy);
-                        o.shape_x[os * kAreaStride + i] = ox;
-                        o.shape_y[os * kAreaStride + i] = oy;
+            t.sync();
+            PROF_MARK(2);   // record loads + shape placement
+
+            const int dp0 = __ldg(slot + cK), dp1 = __ldg(slot + cK + 1);
+            if (b.checker == PDMPC_CHECKER_INTERX) {
+                // are_constraints_satisfied_interx.m:17,34 (no HDVs)
+                const int dy_lo = __ldg(b.poly_ptr + dp0) + dp0, dy_hi = __ldg(b.poly_ptr + dp1) + dp1;
+                cols += (unsigned long long)((st_hi - st_lo) + (dy_hi - dy_lo) + (ll_hi - ll_lo));
+                if (interx_dispatch<TILE>(ns, b.pl_x, b.pl_y, st_lo, st_hi, dy_lo, dy_hi, sm.shx, sm.shy, t))
+                    valid = false;
+                else if (interx_dispatch<TILE>(nbs, b.ll_x, b.ll_y, ll_lo, ll_hi, 0, 0, sm.bhx, sm.bhy, t))
+                    valid = false;
+            } else {
+                // are_constraints_satisfied_sat.m:15-53 (nV == 1; HDV block unreachable)
+                for (int pass = 0; pass < 2 && valid; ++pass) {
+                    const int q0 = pass == 0 ? sp0 : dp0, q1 = pass == 0 ? sp1 : dp1;
+                    for (int p = q0; p < q1 && valid; ++p) {
+                        const int v0 = __ldg(b.poly_ptr + p), v1 = __ldg(b.poly_ptr + p + 1);
+                        cols += (unsigned long long)(v1 - v0);
+                        if (sat_collide<TILE>(sm.shx, sm.shy, ns, b.vert_x + v0, b.vert_y + v0, v1 - v0, t))
+                            valid = false;
                     }
+                }
+                if (valid) {
+                    cols += (unsigned long long)(lp2 - lp0);
+                    if (lanelet_side_sat<TILE>(sm.bhx, sm.bhy, nbs, b.lane_x + lp0, b.lane_y + lp0, lp1 - lp0, t))
+                        valid = false;
+                    else if (lanelet_side_sat<TILE>(sm.bhx, sm.bhy, nbs, b.lane_x + lp1, b.lane_y + lp1, lp2 - lp1, t))
+                        valid = false;
                 }
             }
         }
+        PROF_MARK(3);   // constraint check
+        if (!valid) continue;                                   // :75-77
+        if (cK == Hp) { goal = id; phase = DONE; continue; }    // :81-90
+
+        // ---- expand_node.m:1-91 (nV == 1) --------------------------------------
+        const int k_exp = cK + 1;
+        const int sbase = __ldg(m.succ_ptr + (k_exp - 1) * nT + (cb.trim - 1));
+        const int nchild = __ldg(m.succ_ptr + (k_exp - 1) * nT + (cb.trim - 1) + 1) - sbase;
+        if (n_nodes + nchild >= ar.cap) { status = PDMPC_ERR_CAPACITY; phase = DONE; continue; }
+        double s, c;
+        sincos_ref(ca.yaw, s, c);                   // :50-51, cached for the children's edge checks
+        if (t.lane == 0) {
+            NodeCS e;
+            e.c = c; e.s = s;
+            ncs[id] = e;
+        }
+        const int to_go = Hp - k_exp;               // :37
+        for (int c0 = 0; c0 < nchild; c0 += TILE) {
+            const int ci = c0 + t.lane;
+            const int cnt = min(TILE, nchild - c0);
+            HEnt he;
+            he.f = 0.0; he.id = (unsigned)(n_nodes + 1 + ci); he.pid = id;
+            if (ci < nchild) {
+                const int t2 = __ldg(m.succ_trim + sbase + ci);
+                const int edge = __ldg(m.succ_edge + sbase + ci);
+                const double dx = __ldg(m.edge_dx + edge), dy = __ldg(m.edge_dy + edge),
+                             dyaw = __ldg(m.edge_dyaw + edge);
+                NodeA ea;
+                ea.x = c * dx - s * dy + ca.x;      // :53
+                ea.y = s * dx + c * dy + ca.y;      // :54
+                ea.yaw = ca.yaw + dyaw;             // :55
+                const double ddx = ea.x - sm.refx[k_exp - 1], ddy = ea.y - sm.refy[k_exp - 1];
+                const double nrm = sqrt(ddx * ddx + ddy * ddy);
+                ea.g = ca.g + nrm * nrm;            // :61
+                double eh = 0.0, d_max = 0.0;       // :66-73
+                for (int it = 1; it <= to_go; ++it) {
+                    d_max = d_max + b.dt * sm.vref[k_exp + it - 1];
+                    const double hx = ea.x - sm.refx[k_exp + it - 1], hy = ea.y - sm.refy[k_exp + it - 1];
+                    const double hn = sqrt(hx * hx + hy * hy);
+                    const double mm = fmax(0.0, hn - d_max);
+                    eh = eh + mm * mm;
+                }
+                NodeB eb;
+                eb.h = eh; eb.parent = id; eb.trim = (unsigned short)t2; eb.k = (unsigned short)k_exp;
+                na[he.id] = ea;                     // Tree.m:54-70 add_nodes
+                nb[he.id] = eb;
+                he.f = ea.g + eh;                   // GraphSearch.m:102 (weights 1)
+            }
+            PROF_MARK(4);   // successor generation
+            heap.push_many(he, cnt, t);             // :104, one push per child, in order
+            PROF_MARK(5);   // heap pushes
+        }
+        n_nodes += nchild;
     }
 }
 

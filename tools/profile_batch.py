@@ -8,6 +8,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from pdmpc_b200 import capi  # noqa: E402
+if os.environ.get('PDMPC_LIB'):
+    capi.LIB_PATH = os.environ['PDMPC_LIB']
+    capi.load_library.__defaults__ = (capi.LIB_PATH,)
 from pdmpc_b200.mpa import get_mpa  # noqa: E402
 from pdmpc_b200.records import SearchBatch  # noqa: E402
 
@@ -16,6 +19,7 @@ def main():
     path = sys.argv[1]
     runs = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+    tile = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     mpa_type = "triple_speed" if "triple" in path else "single_speed"
     mpa = get_mpa(mpa_type, non_convex=True)
     b = SearchBatch.load(path)
@@ -23,12 +27,13 @@ def main():
         b = SearchBatch.concat([b] * reps)
     p = capi.Planner(0)
     p.upload_mpa(mpa)
+    p.set_tile(tile)
     p.stage(b)
     for i in range(runs):
         p.run_staged()
         p.sync()
         st = p.stats()
-        print(f"run {i}: {b.n} searches kernel {st.kernel_ms:.3f} ms -> {b.n / st.kernel_ms * 1e3:.0f} plans/s")
+        print(f"tile {tile} run {i}: {b.n} searches kernel {st.kernel_ms:.3f} ms -> {b.n / st.kernel_ms * 1e3:.0f} plans/s")
     r = p.fetch()
     st = p.stats()
     print("pops", st.total_pops, "nodes", st.total_nodes, "cols", st.total_obstacle_cols,
