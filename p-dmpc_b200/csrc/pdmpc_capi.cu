@@ -24,6 +24,11 @@ namespace {
 // memory per search.  Wide tiles minimise per-search latency, narrow tiles share
 // the warp's instruction stream between searches and maximise throughput.
 constexpr int kHeapSmem32 = 512, kHeapSmem16 = 256, kHeapSmem8 = 128;
+// polyline points (lanelet bounds + obstacles of all steps) staged in shared memory per search
+constexpr int kPts32 = 320, kPts16 = 256, kPts8 = 192;
+#define KERNEL32 search_kernel<kHeapSmem32, kPts32, 32>
+#define KERNEL16 search_kernel<kHeapSmem16, kPts16, 16>
+#define KERNEL8 search_kernel<kHeapSmem8, kPts8, 8>
 
 struct DBuf {
     void *p = nullptr;
@@ -60,7 +65,7 @@ struct pdmpc_handle {
     // MPA
     bool has_mpa = false;
     MpaDev mpa{};
-    DBuf m_succ_ptr, m_succ_trim, m_succ_edge, m_edge_of, m_dx, m_dy, m_dyaw, m_npts, m_ax, m_ay;
+    DBuf m_succ_ptr, m_succ, m_npts, m_ax, m_ay;
     int full_tree_nodes = 0;
     int user_node_cap = 0;
 
@@ -132,11 +137,11 @@ int pdmpc_create(int device_id, pdmpc_handle **out) {
     for (auto &ev : h->ev) cudaEventCreate(&ev);
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device_id);
     int occ[3] = {0, 0, 0};
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], search_kernel<kHeapSmem32, 32>, kWarp, 0);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], KERNEL32, kWarp, 0);
     if (e == cudaSuccess)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], search_kernel<kHeapSmem16, 16>, kWarp, 0);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], KERNEL16, kWarp, 0);
     if (e == cudaSuccess)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], search_kernel<kHeapSmem8, 8>, kWarp, 0);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], KERNEL8, kWarp, 0);
     if (e != cudaSuccess || occ[0] < 1 || occ[1] < 1 || occ[2] < 1) {
         std::string msg = std::string("pdmpc_create: search kernel is not launchable on this device (") +
                           cudaGetErrorString(e) + "); built for sm_100a";
@@ -153,8 +158,7 @@ int pdmpc_destroy(pdmpc_handle *h) {
     if (!h) return PDMPC_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DBuf *bufs[] = {&h->m_succ_ptr, &h->m_succ_trim, &h->m_succ_edge, &h->m_edge_of, &h->m_dx, &h->m_dy,
-                    &h->m_dyaw, &h->m_npts, &h->m_ax, &h->m_ay, &h->b_x0, &h->b_y0, &h->b_yaw0, &h->b_trim0,
+    DBuf *bufs[] = {&h->m_succ_ptr, &h->m_succ, &h->m_npts, &h->m_ax, &h->m_ay, &h->b_x0, &h->b_y0, &h->b_yaw0, &h->b_trim0,
                     &h->b_refx, &h->b_refy, &h->b_vref, &h->b_slot, &h->b_poly, &h->b_vx, &h->b_vy,
                     &h->b_plx, &h->b_ply, &h->b_lane, &h->b_lx, &h->b_ly, &h->b_llx, &h->b_lly,
                     &h->o_status, &h->o_exh, &h->o_nexp, &h->o_npops, &h->o_hash, &h->o_trims, &h->o_path,
@@ -225,7 +229,7 @@ int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *d) {
         !d->area_npts || !d->area_x || !d->area_y)
         return fail(h, PDMPC_ERR_BAD_INPUT, "upload_mpa: NULL table pointer");
     const int nT = d->n_trims, Hp = d->Hp, nE = d->n_edges;
-    if (nT < 1 || nT > PDMPC_MAX_TRIMS || Hp < 1 || Hp > PDMPC_MAX_HP || nE < 1 || nE > 32767)
+    if (nT < 1 || nT > PDMPC_MAX_TRIMS || nT > 255 || Hp < 1 || Hp > PDMPC_MAX_HP || nE < 1 || nE >= kMaxEdges)
         return fail(h, PDMPC_ERR_BAD_INPUT, "upload_mpa: n_trims/Hp/n_edges out of range");
     CU_TRY(h, cudaSetDevice(h->device));
     std::vector<int16_t> edge_of((size_t)nT * nT, -1);
@@ -240,7 +244,7 @@ int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *d) {
     }
     // successor lists: find(transition_matrix_single(t,:,k)) ascending (expand_node.m:18)
     std::vector<int> succ_ptr((size_t)Hp * nT + 1, 0);
-    std::vector<int16_t> succ_trim, succ_edge;
+    std::vector<SuccRec> succ;
     for (int k = 0; k < Hp; ++k)
         for (int t = 0; t < nT; ++t) {
             const uint8_t *row = d->transition + ((size_t)k * nT + t) * nT;
@@ -248,10 +252,12 @@ int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *d) {
                 if (row[j]) {
                     int e = edge_of[(size_t)t * nT + j];
                     if (e < 0) return fail(h, PDMPC_ERR_BAD_INPUT, "upload_mpa: transition without maneuver");
-                    succ_trim.push_back((int16_t)(j + 1));
-                    succ_edge.push_back((int16_t)e);
+                    SuccRec r;
+                    r.dx = d->edge_dx[e]; r.dy = d->edge_dy[e]; r.dyaw = d->edge_dyaw[e];
+                    r.trim = (int16_t)(j + 1); r.edge = (int16_t)e; r.pad = 0;
+                    succ.push_back(r);
                 }
-            succ_ptr[(size_t)k * nT + t + 1] = (int)succ_trim.size();
+            succ_ptr[(size_t)k * nT + t + 1] = (int)succ.size();
         }
     // capacity bound: nodes of the full tree from the worst start trim
     double worst = 1;
@@ -276,24 +282,23 @@ int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *d) {
 
     int64_t keep = h->stats.h2d_bytes;
     UP(h, h->m_succ_ptr, succ_ptr.data(), succ_ptr.size());
-    UP(h, h->m_succ_trim, succ_trim.data(), succ_trim.size());
-    UP(h, h->m_succ_edge, succ_edge.data(), succ_edge.size());
-    UP(h, h->m_edge_of, edge_of.data(), edge_of.size());
-    UP(h, h->m_dx, d->edge_dx, nE);
-    UP(h, h->m_dy, d->edge_dy, nE);
-    UP(h, h->m_dyaw, d->edge_dyaw, nE);
+    UP(h, h->m_succ, succ.data(), succ.size());
     UP(h, h->m_npts, d->area_npts, nE * 3);
-    UP(h, h->m_ax, d->area_x, (size_t)nE * 3 * PDMPC_AREA_STRIDE);
-    UP(h, h->m_ay, d->area_y, (size_t)nE * 3 * PDMPC_AREA_STRIDE);
+    // area points zero padded to the fixed stride (the kernel places all 8 columns)
+    std::vector<double> ax((size_t)nE * 3 * PDMPC_AREA_STRIDE, 0.0), ay(ax.size(), 0.0);
+    for (int e = 0; e < nE * 3; ++e)
+        for (int i = 0; i < d->area_npts[e]; ++i) {
+            ax[(size_t)e * PDMPC_AREA_STRIDE + i] = d->area_x[(size_t)e * PDMPC_AREA_STRIDE + i];
+            ay[(size_t)e * PDMPC_AREA_STRIDE + i] = d->area_y[(size_t)e * PDMPC_AREA_STRIDE + i];
+        }
+    UP(h, h->m_ax, ax.data(), ax.size());
+    UP(h, h->m_ay, ay.data(), ay.size());
     CU_TRY(h, cudaStreamSynchronize(h->stream));   // host vectors go out of scope
     h->stats.h2d_bytes = keep;
     MpaDev &m = h->mpa;
     m.nT = nT; m.Hp = Hp; m.nE = nE;
     m.succ_ptr = h->m_succ_ptr.as<int>();
-    m.succ_trim = h->m_succ_trim.as<int16_t>();
-    m.succ_edge = h->m_succ_edge.as<int16_t>();
-    m.edge_of = h->m_edge_of.as<int16_t>();
-    m.edge_dx = h->m_dx.as<double>(); m.edge_dy = h->m_dy.as<double>(); m.edge_dyaw = h->m_dyaw.as<double>();
+    m.succ = h->m_succ.as<SuccRec>();
     m.area_npts = h->m_npts.as<int>();
     m.area_x = h->m_ax.as<double>(); m.area_y = h->m_ay.as<double>();
     h->has_mpa = true;
@@ -446,6 +451,7 @@ int pdmpc_stage_batch(pdmpc_handle *h, const pdmpc_batch_in *in) {
 
 static int ensure_arena(pdmpc_handle *h, int slots) {
     int cap = h->user_node_cap ? h->user_node_cap : std::min(h->full_tree_nodes + 8, 1 << 20);
+    cap = std::min(cap, kMaxNodeCap - 1);
     cap = std::max(cap, 64);
     if (slots <= h->arena_slots && cap == h->arena.cap) return PDMPC_OK;
     slots = std::max(slots, h->arena_slots);
@@ -484,11 +490,11 @@ static int launch_search(pdmpc_handle *h, const TraceDev &tr) {
     unsigned *wc = h->work_counter.as<unsigned>();
     CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
     if (tile == 32)
-        search_kernel<kHeapSmem32, 32><<<grid, kWarp, 0, h->stream>>>(h->mpa, h->batch, h->out, h->arena, wc, tr);
+        KERNEL32<<<grid, kWarp, 0, h->stream>>>(h->mpa, h->batch, h->out, h->arena, wc, tr);
     else if (tile == 16)
-        search_kernel<kHeapSmem16, 16><<<grid, kWarp, 0, h->stream>>>(h->mpa, h->batch, h->out, h->arena, wc, tr);
+        KERNEL16<<<grid, kWarp, 0, h->stream>>>(h->mpa, h->batch, h->out, h->arena, wc, tr);
     else
-        search_kernel<kHeapSmem8, 8><<<grid, kWarp, 0, h->stream>>>(h->mpa, h->batch, h->out, h->arena, wc, tr);
+        KERNEL8<<<grid, kWarp, 0, h->stream>>>(h->mpa, h->batch, h->out, h->arena, wc, tr);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
     h->timing_pending_kernel = true;

@@ -28,8 +28,10 @@
 //     ONE round of independent loads (own record + parent record).
 //   * sin/cos of a node's yaw is computed once, when the node is expanded, and
 //     cached for the edge checks of its children.
-//   * InterX: lanes are (point slot, shape edge) pairs, so a lane keeps ONE
-//     edge's constants in registers; C2 is evaluated only where C1 holds.
+//   * the per-search obstacle polylines (lanelet bounds + all steps' obstacle
+//     polygons) are staged once into shared memory; InterX then runs out of smem.
+//   * InterX: lanes are (point slot, pair of shape edges), so a lane keeps two
+//     edges' constants in registers; C2 is evaluated only where C1 holds.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -63,17 +65,21 @@ namespace pdmpc {
 constexpr int kWarp = 32;
 constexpr int kAreaStride = PDMPC_AREA_STRIDE;
 constexpr int kMaxHp = PDMPC_MAX_HP;
+constexpr int kParentCache = 32;   // entries, power of two
 
 // ---- device views -----------------------------------------------------------
+struct __align__(16) SuccRec {   // one allowed transition (t -> trim) at a given step
+    double dx, dy, dyaw;         // maneuver displacement in the parent frame
+    int16_t trim;                // 1-based end trim
+    int16_t edge;                // maneuver index (area tables)
+    int32_t pad;
+};
 struct MpaDev {
     int nT, Hp, nE;
     const int *succ_ptr;        // [Hp*nT + 1] successors of (step k, trim t) at (k-1)*nT + (t-1)
-    const int16_t *succ_trim;   // 1-based end trim, ascending (expand_node.m:18)
-    const int16_t *succ_edge;   // edge index of (t, succ_trim)
-    const int16_t *edge_of;     // [nT*nT] -> edge or -1
-    const double *edge_dx, *edge_dy, *edge_dyaw;
+    const SuccRec *succ;        // ascending end trim (expand_node.m:18)
     const int *area_npts;       // [nE*3]
-    const double *area_x, *area_y;  // [nE*3*8]
+    const double *area_x, *area_y;  // [nE*3*8], zero padded
 };
 
 struct BatchDev {
@@ -114,16 +120,29 @@ struct __align__(16) NodeA {  // 32 B: pose + cost to come, written when the nod
 struct __align__(16) NodeB {  // 16 B, written when the node is created
     double h;
     unsigned parent;          // 1-based, 0 for the root (Tree.m:18)
-    unsigned short trim;      // 1-based
-    unsigned short k;
+    unsigned short edge;      // maneuver (parent trim -> trim) that leads to this node
+    unsigned char trim;       // 1-based
+    unsigned char k;
 };
-struct __align__(16) NodeCS {  // 16 B, written when the node is expanded
+struct __align__(16) NodeCS {  // 16 B, written when the node is created
     double c, s;               // cos / sin of the node's yaw
 };
 struct __align__(16) HEnt {    // heap entry
     double f;
-    unsigned id, pid;          // node id and its parent's id
+    // id:21 | parent id:21 | edge:10 | k:5 — everything the edge check of a popped
+    // node needs, so that no load depends on the node's own record
+    unsigned long long w;
+    __device__ __forceinline__ static unsigned long long pack(unsigned id, unsigned pid, unsigned edge, unsigned k) {
+        return (unsigned long long)id | ((unsigned long long)pid << 21) | ((unsigned long long)edge << 42) |
+               ((unsigned long long)k << 52);
+    }
+    __device__ __forceinline__ unsigned id() const { return (unsigned)(w & 0x1fffffu); }
+    __device__ __forceinline__ unsigned pid() const { return (unsigned)((w >> 21) & 0x1fffffu); }
+    __device__ __forceinline__ unsigned edge() const { return (unsigned)((w >> 42) & 0x3ffu); }
+    __device__ __forceinline__ unsigned k() const { return (unsigned)((w >> 52) & 0x1fu); }
 };
+constexpr int kMaxNodeCap = 1 << 21;   // ids must fit 21 bits
+constexpr int kMaxEdges = 1 << 10;
 struct ArenaDev {
     NodeA *a;                 // [slots * cap]; index 0 of each slot unused (ids are 1-based)
     NodeB *b;
@@ -197,8 +216,9 @@ __device__ __forceinline__ void sincos_ref(double x, double &s, double &c) {
 // the hottest), the rest in the slot's HBM overflow.  `len` is tile-uniform.
 template <int HS, int TILE>
 struct Heap {
-    static constexpr int LV = TILE == 32 ? 4 : (TILE == 16 ? 3 : 2);   // levels fetched per round
-    static constexpr int NL = (2 << LV) - 2;                           // lanes used per round
+    static constexpr int LV = 4;                   // levels fetched per round: 2+4+8+16 entries
+    static constexpr int NL = 30;
+    static constexpr int Q = kWarp / TILE;         // entries per lane and round (positions q*TILE + lane)
     HEnt *sm;
     HEnt *gl;
     int len;
@@ -218,7 +238,7 @@ struct Heap {
             const int a = base + t.lane + 1;           // this lane's ancestor, `a` levels up
             const bool anc = a <= D;
             HEnt e;
-            e.f = 0.0; e.id = 0; e.pid = 0;
+            e.f = 0.0; e.w = 0;
             if (anc) e = load(((p + 1) >> a) - 1);
             const unsigned gt = t.ballot(anc && e.f > v.f);
             const int run = (gt == Tile<TILE>::kBits) ? TILE : (__ffs(~gt) - 1);   // leading run of greater parents
@@ -239,39 +259,55 @@ struct Heap {
         if (n > 0) {
             const HEnt v = load(n);
             t.sync();            // every lane has read top / v before any entry moves
-            // lane -> descendant (level d = 1..LV below the hole, offset o) for lanes 0..NL-1
-            const int d = 31 - __clz(t.lane + 2);
-            const int o = t.lane + 2 - (1 << d);
-            int hole = 0;
-            double lastf = 0.0;
+            int hole = 0, sel_lane = 0;
+            double lastf = 0.0, fsel = 0.0;
             bool moved = false;
             const int lim = (n - 1) / 2;
             while (hole < lim) {
-                const int idx = ((hole + 1) << d) - 1 + o;
-                HEnt e;
-                e.f = 0.0; e.id = 0; e.pid = 0;
-                if (t.lane < NL && idx < n) e = load(idx);
-                // sibling pairs are lanes (2r, 2r+1): the right one is taken unless f_right > f_left
-                const double fs = t.shfl_xor(e.f, 1);
-                const bool pick = (t.lane & 1) ? !(e.f > fs) : (fs > e.f);
-                const unsigned picks = t.ballot(pick);
+                // position pos = q*TILE + lane of the round <-> descendant (level d, offset o)
+                HEnt e[Q];
+                int idx[Q];
+                unsigned picks = 0;
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const int pos = q * TILE + t.lane;
+                    const int d = 31 - __clz(pos + 2);
+                    idx[q] = ((hole + 1) << d) - 1 + (pos + 2 - (1 << d));
+                    e[q].f = 0.0; e[q].w = 0;
+                    if (pos < NL && idx[q] < n) e[q] = load(idx[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    // sibling pairs are positions (2r, 2r+1): the right one is taken unless f_right > f_left
+                    const double fs = t.shfl_xor(e[q].f, 1);
+                    const bool pick = (t.lane & 1) ? !(e[q].f > fs) : (fs > e[q].f);
+                    picks |= t.ballot(pick) << (q * TILE);
+                }
                 int rel = 0, sel = 0;
-                bool on = false;
 #pragma unroll
                 for (int lv = 1; lv <= LV; ++lv) {
                     if (hole < lim) {   // both children exist
-                        const int left_lane = (1 << lv) - 2 + 2 * rel;
-                        const int right = (picks >> (left_lane + 1)) & 1;
-                        sel = left_lane + right;
-                        on = on || (t.lane == sel);
+                        const int left_pos = (1 << lv) - 2 + 2 * rel;
+                        const int right = (picks >> (left_pos + 1)) & 1;
+                        sel = left_pos + right;
+                        const int q = sel / TILE;
+                        if (t.lane == sel % TILE) {
+#pragma unroll
+                            for (int qq = 0; qq < Q; ++qq)
+                                if (qq == q) store((idx[qq] - 1) >> 1, e[qq]);   // picked child moves up
+                        }
                         hole = 2 * hole + 1 + right;
                         rel = 2 * rel + right;
                     }
                 }
-                if (on) store((idx - 1) >> 1, e);      // picked child moves into its parent's place
-                lastf = t.shfl(e.f, sel);
+                fsel = e[0].f;
+#pragma unroll
+                for (int qq = 1; qq < Q; ++qq)
+                    if (qq == sel / TILE) fsel = e[qq].f;
+                sel_lane = sel % TILE;
                 moved = true;
             }
+            if (moved) lastf = t.shfl(fsel, sel_lane);   // f of the last entry that moved up
             if ((n & 1) == 0 && hole == (n - 2) / 2) {   // single (left) child at n-1
                 const HEnt e = load(n - 1);
                 if (t.lane == 0) store(hole, e);
@@ -316,8 +352,7 @@ struct Heap {
             if (done < m) {
                 HEnt v;
                 v.f = t.shfl(mine.f, done);
-                v.id = t.shfl(mine.id, done);
-                v.pid = t.shfl(mine.pid, done);
+                v.w = t.shfl(mine.w, done);
                 sift_up_at(len, v, t);
                 ++len;
                 ++done;
@@ -329,43 +364,51 @@ struct Heap {
 
 // ---- InterX (InterX.m:63-85,108-110) ---------------------------------------
 // Shape (NE segments, points in shared memory) against the NaN-separated polyline
-// points [lo, hi) of (px, py).  Lane = (slot, edge i): the lane keeps edge i's
-// constants in registers and walks the slot's contiguous run of obstacle
-// segments; C1 (edge i separates the two obstacle points) is evaluated for every
-// pair, C2 only where C1 holds.  any(C1 & C2) is the reference's boolean.
+// points [lo, hi) of (px, py) (shared or global memory).  Every lane keeps the
+// constants of all NE shape edges in registers and owns a short contiguous run of
+// obstacle segments, so a range takes ceil(nseg / TILE) iterations with NE
+// independent dependency chains each (the search is latency bound, not FP64
+// bound).  C1(i,j): obstacle points j, j+1 on opposite sides of edge i's line;
+// C2(i,j): edge i's end points on opposite sides of segment j's line; both are
+// evaluated branch-free.  any(C1 & C2) is the reference's boolean.
 template <int NE, int TILE>
-__device__ __forceinline__ bool interx_ranges(const double *__restrict__ px, const double *__restrict__ py,
-                                              int lo0, int hi0, int lo1, int hi1, const double *shx,
-                                              const double *shy, const Tile<TILE> &t) {
-    constexpr int S = TILE / NE;                 // point slots
-    const int i = t.lane % NE, slot = t.lane / NE;
-    const bool lane_on = slot < S;
-    const double x1a = shx[i], y1a = shy[i], x1b = shx[i + 1], y1b = shy[i + 1];
-    const double dx1 = x1b - x1a, dy1 = y1b - y1a;
-    const double S1 = dx1 * y1a - dy1 * x1a;
+__device__ __forceinline__ bool interx_ranges(const double *px, const double *py, int lo0, int hi0, int lo1,
+                                              int hi1, const double *shx, const double *shy,
+                                              const Tile<TILE> &t) {
+    double dx1[NE], dy1[NE], S1[NE];
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+        dx1[i] = shx[i + 1] - shx[i];
+        dy1[i] = shy[i + 1] - shy[i];
+        S1[i] = dx1[i] * shy[i] - dy1[i] * shx[i];
+    }
     bool hit = false;
 #pragma unroll 1
     for (int r = 0; r < 2; ++r) {
         const int lo = r ? lo1 : lo0, hi = r ? hi1 : hi0;
         const int nseg = hi - lo - 1;
         if (nseg < 1) continue;                  // InterX.m:48-52 and single-column inputs
-        const int per = (nseg + S - 1) / S;
-        const int j0 = lo + slot * per;
+        const int per = (nseg + TILE - 1) / TILE;
+        const int j0 = lo + t.lane * per;
         const int j1 = min(j0 + per, lo + nseg);
-        if (lane_on && j0 < j1) {
-            double x = __ldg(px + j0), y = __ldg(py + j0);
-            double a = (dx1 * y - dy1 * x) - S1;
+        if (j0 < j1) {
+            double x = px[j0], y = py[j0];
+            double a[NE];
+#pragma unroll
+            for (int i = 0; i < NE; ++i) a[i] = (dx1[i] * y - dy1[i] * x) - S1[i];
             for (int j = j0; j < j1; ++j) {
-                const double xn = __ldg(px + j + 1), yn = __ldg(py + j + 1);
-                const double an = (dx1 * yn - dy1 * xn) - S1;
-                if (a * an < 0) {                                 // C1(i,j)
-                    const double dx2 = xn - x, dy2 = yn - y;
-                    const double S2 = dx2 * y - dy2 * x;
-                    const double b0 = (y1a * dx2 - x1a * dy2) - S2;
-                    const double b1 = (y1b * dx2 - x1b * dy2) - S2;
-                    if (b0 * b1 < 0) hit = true;                  // C2(i,j)
+                const double xn = px[j + 1], yn = py[j + 1];
+                const double dx2 = xn - x, dy2 = yn - y;
+                const double S2 = dx2 * y - dy2 * x;
+                double bprev = (shy[0] * dx2 - shx[0] * dy2) - S2;
+#pragma unroll
+                for (int i = 0; i < NE; ++i) {
+                    const double an = (dx1[i] * yn - dy1[i] * xn) - S1[i];
+                    const double bn = (shy[i + 1] * dx2 - shx[i + 1] * dy2) - S2;
+                    hit = hit || ((a[i] * an < 0) && (bprev * bn < 0));
+                    a[i] = an;
+                    bprev = bn;
                 }
-                a = an;
                 x = xn;
                 y = yn;
             }
@@ -494,13 +537,19 @@ __device__ __forceinline__ void place_point(const MpaDev &m, int edge, int kind,
     oy = s * ax + c * ay + py;
 }
 
-template <int HS>
+template <int HS, int SP>
 struct __align__(16) TileSmem {
     HEnt heap[HS];
+    double pts_x[SP], pts_y[SP];                 // staged polylines: [lanelet bounds][obstacle slots 0..Hp]
     double refx[kMaxHp], refy[kMaxHp], vref[kMaxHp];
     double shx[kAreaStride], shy[kAreaStride];   // shape (normal offset)
     double bhx[kAreaStride], bhy[kAreaStride];   // boundary-check shape
+    int rng[kMaxHp + 2];                         // polyline offset of obstacle slot s (static, steps 1..Hp)
     unsigned path[kMaxHp + 1];
+    // direct-mapped cache of expanded nodes' (x, y, cos, sin): the parent record a popped
+    // child needs for its edge check (children are usually popped soon after the expansion)
+    unsigned pc_id[kParentCache];
+    double pc_x[kParentCache], pc_y[kParentCache], pc_c[kParentCache], pc_s[kParentCache];
 };
 
 // ============================================================================
@@ -508,17 +557,17 @@ struct __align__(16) TileSmem {
 // search indices from a global counter until the batch is drained.  The body is
 // ONE loop (a small state machine) so that the tiles of a warp stay converged:
 // an iteration is "finish / fetch a search if needed, then one pop".
-template <int HS, int TILE>
+template <int HS, int SP, int TILE>
 __global__ void __launch_bounds__(kWarp) search_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar,
                                                        unsigned *work_counter, TraceDev tr) {
     constexpr int NT = kWarp / TILE;
-    __shared__ TileSmem<HS> s_tiles[NT];
+    __shared__ TileSmem<HS, SP> s_tiles[NT];
 
     Tile<TILE> t;
     t.shift = (threadIdx.x / TILE) * TILE;
     t.lane = threadIdx.x % TILE;
     t.mask = Tile<TILE>::kBits << t.shift;
-    TileSmem<HS> &sm = s_tiles[threadIdx.x / TILE];
+    TileSmem<HS, SP> &sm = s_tiles[threadIdx.x / TILE];
 
     const int Hp = m.Hp, nT = m.nT;
     const size_t slot_base = ((size_t)blockIdx.x * NT + threadIdx.x / TILE) * (size_t)ar.cap;
@@ -535,11 +584,17 @@ __global__ void __launch_bounds__(kWarp) search_kernel(MpaDev m, BatchDev b, Out
     PROF_DECL
     int si = 0, trim0 = 0;
     const int *slot = nullptr;
-    int st_lo = 0, st_hi = 0, ll_lo = 0, ll_hi = 0, sp0 = 0, sp1 = 0, lp0 = 0, lp1 = 0, lp2 = 0;
+    int sp0 = 0, sp1 = 0, lp0 = 0, lp1 = 0, lp2 = 0;
+    // InterX polylines of the current search: obstacles (slot ranges via sm.rng) and lanelet bounds
+    const double *opx = nullptr, *opy = nullptr, *lpx = nullptr, *lpy = nullptr;
+    int obase = 0, llo = 0, lhi = 0;
     int n_nodes = 0, n_pops = 0, status = PDMPC_OK;
     unsigned long long hash = 0, cols = 0;
     bool exhausted = false;
     unsigned goal = 0;
+    // the parent record of the last pop (siblings are usually popped back to back)
+    unsigned last_par = 0;
+    double ppx = 0.0, ppy = 0.0, pc = 0.0, ps = 0.0;
 
     for (;;) {
         PROF_MARK(7);
@@ -569,7 +624,7 @@ __global__ void __launch_bounds__(kWarp) search_kernel(MpaDev m, BatchDev b, Out
                 const unsigned pid = sm.path[d];
                 NodeA pa = {qnan, qnan, qnan, qnan};
                 NodeB pb;
-                pb.h = qnan; pb.parent = 0; pb.trim = 0; pb.k = 0;
+                pb.h = qnan; pb.parent = 0; pb.edge = 0; pb.trim = 0; pb.k = 0;
                 if (!exhausted) { pa = na[pid]; pb = nb[pid]; }
                 const size_t oo = (size_t)si * (Hp + 1) + d;
                 if (o.trims) o.trims[oo] = exhausted ? (d == 0 ? trim0 : 0) : (int)pb.trim;
@@ -591,7 +646,7 @@ __global__ void __launch_bounds__(kWarp) search_kernel(MpaDev m, BatchDev b, Out
                             const unsigned qid = sm.path[d - 1];   // parent on the path (was expanded)
                             qa = na[qid];
                             qcs = ncs[qid];
-                            edge = __ldg(m.edge_of + ((int)nb[qid].trim - 1) * nT + ((int)pb.trim - 1));
+                            edge = pb.edge;
                             ns = __ldg(m.area_npts + edge * 3 + PDMPC_AREA_NORMAL);
                         }
                         o.shape_npts[os] = ns;
@@ -623,29 +678,63 @@ __global__ void __launch_bounds__(kWarp) search_kernel(MpaDev m, BatchDev b, Out
             }
             slot = b.slot_ptr + (size_t)si * (Hp + 1);
             trim0 = __ldg(b.trim0 + si);
+            for (int k = t.lane; k < kParentCache; k += TILE) sm.pc_id[k] = 0u;
             if (t.lane == 0) {   // root: GraphSearch.m:34-46
                 NodeA ra;
                 ra.x = __ldg(b.x0 + si); ra.y = __ldg(b.y0 + si); ra.yaw = __ldg(b.yaw0 + si); ra.g = 0.0;
+                NodeCS rcs;
+                sincos_ref(ra.yaw, rcs.s, rcs.c);
+                ncs[1] = rcs;
                 NodeB rb;
-                rb.h = 0.0; rb.parent = 0; rb.trim = (unsigned short)trim0; rb.k = 0;
+                rb.h = 0.0; rb.parent = 0; rb.edge = 0xffff; rb.trim = (unsigned char)trim0; rb.k = 0;
                 na[1] = ra;
                 nb[1] = rb;
                 HEnt re;
-                re.f = 0.0; re.id = 1u; re.pid = 0u;
+                re.f = 0.0; re.w = HEnt::pack(1u, 0u, 0u, 0u);
                 heap.store(0, re);
             }
             heap.len = 1;
-            // static-obstacle polyline range and lanelet polyline range (InterX layout)
             sp0 = __ldg(slot + 0); sp1 = __ldg(slot + 1);
-            st_lo = __ldg(b.poly_ptr + sp0) + sp0; st_hi = __ldg(b.poly_ptr + sp1) + sp1;
             lp0 = __ldg(b.lane_ptr + 2 * si); lp1 = __ldg(b.lane_ptr + 2 * si + 1);
             lp2 = __ldg(b.lane_ptr + 2 * si + 2);
-            ll_lo = lp0 + 2 * si; ll_hi = lp2 + 2 * si + 2;
+            if (b.checker == PDMPC_CHECKER_INTERX) {
+                // polyline layout (vectorize_all_obstacles.m): obstacle slot s of this search
+                // covers [ob_lo + rng[s], ob_lo + rng[s+1]); lanelets [ll_lo, ll_hi)
+                const int spE = __ldg(slot + Hp + 1);
+                const int ob_lo = __ldg(b.poly_ptr + sp0) + sp0, ob_hi = __ldg(b.poly_ptr + spE) + spE;
+                const int ll_lo = lp0 + 2 * si, ll_hi = lp2 + 2 * si + 2;
+                for (int k = t.lane; k <= Hp + 1; k += TILE) {
+                    const int q = __ldg(slot + k);
+                    sm.rng[k] = __ldg(b.poly_ptr + q) + q - ob_lo;
+                }
+                const int nl = ll_hi - ll_lo, no = ob_hi - ob_lo;
+                int used = 0;
+                if (nl <= SP) {      // stage the lanelet polyline
+                    for (int j = t.lane; j < nl; j += TILE) {
+                        sm.pts_x[j] = __ldg(b.ll_x + ll_lo + j);
+                        sm.pts_y[j] = __ldg(b.ll_y + ll_lo + j);
+                    }
+                    lpx = sm.pts_x; lpy = sm.pts_y; llo = 0; lhi = nl;
+                    used = nl;
+                } else {
+                    lpx = b.ll_x; lpy = b.ll_y; llo = ll_lo; lhi = ll_hi;
+                }
+                if (used + no <= SP) {   // stage the obstacle polylines of all steps
+                    for (int j = t.lane; j < no; j += TILE) {
+                        sm.pts_x[used + j] = __ldg(b.pl_x + ob_lo + j);
+                        sm.pts_y[used + j] = __ldg(b.pl_y + ob_lo + j);
+                    }
+                    opx = sm.pts_x; opy = sm.pts_y; obase = used;
+                } else {
+                    opx = b.pl_x; opy = b.pl_y; obase = ob_lo;
+                }
+            }
             n_nodes = 1; n_pops = 0;
             hash = 0xcbf29ce484222325ULL; cols = 0;
             status = PDMPC_OK;
             exhausted = false;
             goal = 0;
+            last_par = 0;
             phase = RUN;
             t.sync();
         }
@@ -655,7 +744,8 @@ __global__ void __launch_bounds__(kWarp) search_kernel(MpaDev m, BatchDev b, Out
         if (heap.len == 0) { exhausted = true; phase = DONE; continue; }   // :57-61
         const HEnt top = heap.pop(t);
         PROF_MARK(1);   // heap pop
-        const unsigned id = top.id, par = top.pid;
+        const unsigned id = top.id(), par = top.pid();
+        const int cK = (int)top.k();
         ++n_pops;
         hash = hash_step(hash, id);
         if (tr.search == si && t.lane == 0) {
@@ -663,45 +753,53 @@ __global__ void __launch_bounds__(kWarp) search_kernel(MpaDev m, BatchDev b, Out
             *tr.n = n_pops;
         }
 
-        // one round of independent loads: own record and the parent's
+        // one round of independent loads: own record (for the expansion), the parent's
+        // record (unless cached) and the maneuver areas (edge and depth ride in the heap entry)
         const NodeB cb = nb[id];
         const NodeA ca = na[id];
-        const int cK = cb.k;
         bool valid = true;
         if (par != 0) {   // eval_edge_exact :137-192 (root is valid unchecked)
-            const NodeA pa = na[par];
-            const NodeCS pcs = ncs[par];              // cos/sin(parent yaw), :155-156
-            const int t1 = nb[par].trim, t2 = cb.trim;
-            const int edge = __ldg(m.edge_of + (t1 - 1) * nT + (t2 - 1));
-            const int ns = __ldg(m.area_npts + edge * 3 + PDMPC_AREA_NORMAL);
+            if (par != last_par) {
+                const int cslot = par & (kParentCache - 1);
+                if (sm.pc_id[cslot] == par) {
+                    ppx = sm.pc_x[cslot]; ppy = sm.pc_y[cslot]; pc = sm.pc_c[cslot]; ps = sm.pc_s[cslot];
+                } else {
+                    const NodeA pa = na[par];
+                    const NodeCS pcs = ncs[par];              // cos/sin(parent yaw), :155-156
+                    ppx = pa.x; ppy = pa.y; pc = pcs.c; ps = pcs.s;
+                }
+                last_par = par;
+            }
+            const int edge = (int)top.edge();
             const int bkind = (cK == Hp) ? PDMPC_AREA_LARGE_OFFSET : PDMPC_AREA_WITHOUT_OFFSET;  // :166-174
+            const int ns = __ldg(m.area_npts + edge * 3 + PDMPC_AREA_NORMAL);
             const int nbs = __ldg(m.area_npts + edge * 3 + bkind);
             t.sync();
+            // all 8 (zero padded) points of both areas are placed; only the first ns / nbs are used
             if (TILE >= 16) {
-                if (t.lane < ns)
-                    place_point(m, edge, PDMPC_AREA_NORMAL, t.lane, pcs.c, pcs.s, pa.x, pa.y, sm.shx[t.lane], sm.shy[t.lane]);
-                else if (t.lane >= 8 && t.lane - 8 < nbs)
-                    place_point(m, edge, bkind, t.lane - 8, pcs.c, pcs.s, pa.x, pa.y, sm.bhx[t.lane - 8], sm.bhy[t.lane - 8]);
+                if (t.lane < 8)
+                    place_point(m, edge, PDMPC_AREA_NORMAL, t.lane, pc, ps, ppx, ppy, sm.shx[t.lane], sm.shy[t.lane]);
+                else if (t.lane < 16)
+                    place_point(m, edge, bkind, t.lane - 8, pc, ps, ppx, ppy, sm.bhx[t.lane - 8], sm.bhy[t.lane - 8]);
             } else {
-                if (t.lane < ns)
-                    place_point(m, edge, PDMPC_AREA_NORMAL, t.lane, pcs.c, pcs.s, pa.x, pa.y, sm.shx[t.lane], sm.shy[t.lane]);
-                if (t.lane < nbs)
-                    place_point(m, edge, bkind, t.lane, pcs.c, pcs.s, pa.x, pa.y, sm.bhx[t.lane], sm.bhy[t.lane]);
+                place_point(m, edge, PDMPC_AREA_NORMAL, t.lane, pc, ps, ppx, ppy, sm.shx[t.lane], sm.shy[t.lane]);
+                place_point(m, edge, bkind, t.lane, pc, ps, ppx, ppy, sm.bhx[t.lane], sm.bhy[t.lane]);
             }
             t.sync();
             PROF_MARK(2);   // record loads + shape placement
 
-            const int dp0 = __ldg(slot + cK), dp1 = __ldg(slot + cK + 1);
             if (b.checker == PDMPC_CHECKER_INTERX) {
                 // are_constraints_satisfied_interx.m:17,34 (no HDVs)
-                const int dy_lo = __ldg(b.poly_ptr + dp0) + dp0, dy_hi = __ldg(b.poly_ptr + dp1) + dp1;
-                cols += (unsigned long long)((st_hi - st_lo) + (dy_hi - dy_lo) + (ll_hi - ll_lo));
-                if (interx_dispatch<TILE>(ns, b.pl_x, b.pl_y, st_lo, st_hi, dy_lo, dy_hi, sm.shx, sm.shy, t))
+                const int st_lo = obase + sm.rng[0], st_hi = obase + sm.rng[1];
+                const int dy_lo = obase + sm.rng[cK], dy_hi = obase + sm.rng[cK + 1];
+                cols += (unsigned long long)((st_hi - st_lo) + (dy_hi - dy_lo) + (lhi - llo));
+                if (interx_dispatch<TILE>(ns, opx, opy, st_lo, st_hi, dy_lo, dy_hi, sm.shx, sm.shy, t))
                     valid = false;
-                else if (interx_dispatch<TILE>(nbs, b.ll_x, b.ll_y, ll_lo, ll_hi, 0, 0, sm.bhx, sm.bhy, t))
+                else if (interx_dispatch<TILE>(nbs, lpx, lpy, llo, lhi, 0, 0, sm.bhx, sm.bhy, t))
                     valid = false;
             } else {
                 // are_constraints_satisfied_sat.m:15-53 (nV == 1; HDV block unreachable)
+                const int dp0 = __ldg(slot + cK), dp1 = __ldg(slot + cK + 1);
                 for (int pass = 0; pass < 2 && valid; ++pass) {
                     const int q0 = pass == 0 ? sp0 : dp0, q1 = pass == 0 ? sp1 : dp1;
                     for (int p = q0; p < q1 && valid; ++p) {
@@ -726,47 +824,62 @@ __global__ void __launch_bounds__(kWarp) search_kernel(MpaDev m, BatchDev b, Out
 
         // ---- expand_node.m:1-91 (nV == 1) --------------------------------------
         const int k_exp = cK + 1;
-        const int sbase = __ldg(m.succ_ptr + (k_exp - 1) * nT + (cb.trim - 1));
-        const int nchild = __ldg(m.succ_ptr + (k_exp - 1) * nT + (cb.trim - 1) + 1) - sbase;
+        const int sbase = __ldg(m.succ_ptr + (k_exp - 1) * nT + ((int)cb.trim - 1));
+        const int nchild = __ldg(m.succ_ptr + (k_exp - 1) * nT + ((int)cb.trim - 1) + 1) - sbase;
         if (n_nodes + nchild >= ar.cap) { status = PDMPC_ERR_CAPACITY; phase = DONE; continue; }
-        double s, c;
-        sincos_ref(ca.yaw, s, c);                   // :50-51, cached for the children's edge checks
+        // :50-51 cos/sin of this node's yaw were computed when the node was created
+        const NodeCS ccs = ncs[id];
+        const double s = ccs.s, c = ccs.c;
         if (t.lane == 0) {
-            NodeCS e;
-            e.c = c; e.s = s;
-            ncs[id] = e;
+            const int cslot = id & (kParentCache - 1);
+            sm.pc_id[cslot] = id;
+            sm.pc_x[cslot] = ca.x; sm.pc_y[cslot] = ca.y; sm.pc_c[cslot] = c; sm.pc_s[cslot] = s;
         }
         const int to_go = Hp - k_exp;               // :37
         for (int c0 = 0; c0 < nchild; c0 += TILE) {
             const int ci = c0 + t.lane;
             const int cnt = min(TILE, nchild - c0);
             HEnt he;
-            he.f = 0.0; he.id = (unsigned)(n_nodes + 1 + ci); he.pid = id;
+            he.f = 0.0; he.w = 0;
+            const unsigned nid = (unsigned)(n_nodes + 1 + ci);
             if (ci < nchild) {
-                const int t2 = __ldg(m.succ_trim + sbase + ci);
-                const int edge = __ldg(m.succ_edge + sbase + ci);
-                const double dx = __ldg(m.edge_dx + edge), dy = __ldg(m.edge_dy + edge),
-                             dyaw = __ldg(m.edge_dyaw + edge);
+                const SuccRec sr = m.succ[sbase + ci];
                 NodeA ea;
-                ea.x = c * dx - s * dy + ca.x;      // :53
-                ea.y = s * dx + c * dy + ca.y;      // :54
-                ea.yaw = ca.yaw + dyaw;             // :55
+                ea.x = c * sr.dx - s * sr.dy + ca.x;      // :53
+                ea.y = s * sr.dx + c * sr.dy + ca.y;      // :54
+                ea.yaw = ca.yaw + sr.dyaw;                // :55
                 const double ddx = ea.x - sm.refx[k_exp - 1], ddy = ea.y - sm.refy[k_exp - 1];
                 const double nrm = sqrt(ddx * ddx + ddy * ddy);
                 ea.g = ca.g + nrm * nrm;            // :61
                 double eh = 0.0, d_max = 0.0;       // :66-73
-                for (int it = 1; it <= to_go; ++it) {
-                    d_max = d_max + b.dt * sm.vref[k_exp + it - 1];
-                    const double hx = ea.x - sm.refx[k_exp + it - 1], hy = ea.y - sm.refy[k_exp + it - 1];
-                    const double hn = sqrt(hx * hx + hy * hy);
-                    const double mm = fmax(0.0, hn - d_max);
-                    eh = eh + mm * mm;
+                for (int it0 = 1; it0 <= to_go; it0 += 4) {
+                    // the square roots of four steps are independent: issue them together
+                    double hn[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int kk = min(k_exp + it0 + u - 1, Hp - 1);
+                        const double hx = ea.x - sm.refx[kk], hy = ea.y - sm.refy[kk];
+                        hn[u] = sqrt(hx * hx + hy * hy);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (it0 + u <= to_go) {
+                            d_max = d_max + b.dt * sm.vref[k_exp + it0 + u - 1];
+                            const double mm = fmax(0.0, hn[u] - d_max);
+                            eh = eh + mm * mm;
+                        }
+                    }
                 }
                 NodeB eb;
-                eb.h = eh; eb.parent = id; eb.trim = (unsigned short)t2; eb.k = (unsigned short)k_exp;
-                na[he.id] = ea;                     // Tree.m:54-70 add_nodes
-                nb[he.id] = eb;
+                eb.h = eh; eb.parent = id; eb.edge = (unsigned short)sr.edge;
+                eb.trim = (unsigned char)sr.trim; eb.k = (unsigned char)k_exp;
+                NodeCS ecs;                         // for the child's own expansion (off the critical path)
+                sincos_ref(ea.yaw, ecs.s, ecs.c);
+                na[nid] = ea;                       // Tree.m:54-70 add_nodes
+                nb[nid] = eb;
+                ncs[nid] = ecs;
                 he.f = ea.g + eh;                   // GraphSearch.m:102 (weights 1)
+                he.w = HEnt::pack(nid, id, (unsigned)sr.edge, (unsigned)k_exp);
             }
             PROF_MARK(4);   // successor generation
             heap.push_many(he, cnt, t);             // :104, one push per child, in order
