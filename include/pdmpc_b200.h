@@ -177,10 +177,11 @@ int pdmpc_abi_version(void);
  * search that needs more returns PDMPC_ERR_CAPACITY in its status. */
 int pdmpc_set_node_capacity(pdmpc_handle *h, int32_t max_nodes_per_search);
 
-/* Lanes of a warp that cooperate on one search: 32 (one search per warp, lowest
- * latency), 16 or 8 (2 / 4 searches share a warp, highest throughput), 0 = choose
- * from the batch size (default).  Results do not depend on it. */
-int pdmpc_set_tile(pdmpc_handle *h, int32_t lanes_per_search);
+/* Launch shape of the search kernel: 0 = choose from the batch size (default),
+ * 1 = latency (one warp-CTA per search slot, tables through L1/L2), 2 = throughput
+ * (one 16-warp CTA per SM, MPA tables TMA-staged in shared memory; falls back to 1
+ * when the tables do not fit).  Results do not depend on it. */
+int pdmpc_set_variant(pdmpc_handle *h, int32_t variant);
 
 /* Stage the MPA tables in HBM (once per MPA; cached in the handle). */
 int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *mpa);

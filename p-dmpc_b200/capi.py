@@ -30,7 +30,7 @@ PDMPC_ERR_ALLOC = 5
 
 EXPORTED_SYMBOLS = (
     "pdmpc_create", "pdmpc_destroy", "pdmpc_last_error", "pdmpc_abi_version",
-    "pdmpc_set_node_capacity", "pdmpc_set_tile", "pdmpc_host_alloc", "pdmpc_host_free",
+    "pdmpc_set_node_capacity", "pdmpc_set_variant", "pdmpc_host_alloc", "pdmpc_host_free",
     "pdmpc_trace_staged", "pdmpc_upload_mpa", "pdmpc_plan_batch", "pdmpc_stage_batch",
     "pdmpc_run_staged", "pdmpc_sync", "pdmpc_fetch_staged", "pdmpc_get_stats", "pdmpc_stream",
 )
@@ -152,8 +152,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.pdmpc_abi_version.restype = C.c_int
     lib.pdmpc_set_node_capacity.argtypes = [H, C.c_int32]
     lib.pdmpc_set_node_capacity.restype = C.c_int
-    lib.pdmpc_set_tile.argtypes = [H, C.c_int32]
-    lib.pdmpc_set_tile.restype = C.c_int
+    lib.pdmpc_set_variant.argtypes = [H, C.c_int32]
+    lib.pdmpc_set_variant.restype = C.c_int
     lib.pdmpc_trace_staged.argtypes = [H, C.c_int32, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64)]
     lib.pdmpc_trace_staged.restype = C.c_int
     lib.pdmpc_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
@@ -219,9 +219,9 @@ class Planner:
     def set_node_capacity(self, n: int):
         self._check(self.lib.pdmpc_set_node_capacity(self.h, int(n)))
 
-    def set_tile(self, lanes_per_search: int):
-        """32 / 16 / 8 lanes per search, 0 = auto (pdmpc_set_tile)."""
-        self._check(self.lib.pdmpc_set_tile(self.h, int(lanes_per_search)))
+    def set_variant(self, variant: int):
+        """0 = auto, 1 = latency shape, 2 = throughput shape (pdmpc_set_variant)."""
+        self._check(self.lib.pdmpc_set_variant(self.h, int(variant)))
 
     def trace(self, search: int, cap: int = 1 << 20) -> np.ndarray:
         """Node ids popped by staged search `search`, in order (pdmpc_trace_staged)."""

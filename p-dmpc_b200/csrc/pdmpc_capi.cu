@@ -20,15 +20,16 @@ using namespace pdmpc;
 
 namespace {
 
-// Kernel variants: searches per warp (tile width) and heap entries kept in shared
-// memory per search.  Wide tiles minimise per-search latency, narrow tiles share
-// the warp's instruction stream between searches and maximise throughput.
-constexpr int kHeapSmem32 = 512, kHeapSmem16 = 256, kHeapSmem8 = 128;
-// polyline points (lanelet bounds + obstacles of all steps) staged in shared memory per search
-constexpr int kPts32 = 320, kPts16 = 256, kPts8 = 192;
-#define KERNEL32 search_kernel<kHeapSmem32, kPts32, 32>
-#define KERNEL16 search_kernel<kHeapSmem16, kPts16, 16>
-#define KERNEL8 search_kernel<kHeapSmem8, kPts8, 8>
+// Launch shapes of the search kernel (pdmpc_kernels.cuh): "latency" = one warp
+// per CTA, tables through L1/L2; "throughput" = one 16-warp CTA per SM with the
+// MPA tables TMA-staged into shared memory.
+constexpr int kHeapSmem = 256;   // heap entries kept in shared memory per search
+constexpr int kPts = 256;        // polyline points (lanelet bounds + obstacles of all steps) staged per search
+constexpr int kWarpsThroughput = 16;
+#define KERNEL_LAT search_kernel<kHeapSmem, kPts, 1, false>
+#define KERNEL_THR search_kernel<kHeapSmem, kPts, kWarpsThroughput, true>
+using WarpSmem = TileSmem<kHeapSmem, kPts>;
+constexpr size_t kSmemLimit = 227 * 1024;
 
 struct DBuf {
     void *p = nullptr;
@@ -56,8 +57,10 @@ struct DBuf {
 struct pdmpc_handle {
     int device = 0;
     int num_sms = 0;
-    int ctas_per_sm[3] = {0, 0, 0};   // per tile variant 32 / 16 / 8
-    int tile_mode = 0;                // 0 = auto, else 32 / 16 / 8
+    int lat_ctas_per_sm = 0;          // occupancy of the latency shape
+    bool thr_ok = false;              // throughput shape usable with the uploaded MPA (tables fit in smem)
+    size_t thr_smem = 0;
+    int variant_mode = 0;             // 0 = auto, 1 = latency, 2 = throughput
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {};   // 0/1 h2d, 2/3 kernel, 4/5 d2h
     std::string err;
@@ -65,7 +68,7 @@ struct pdmpc_handle {
     // MPA
     bool has_mpa = false;
     MpaDev mpa{};
-    DBuf m_succ_ptr, m_succ, m_npts, m_ax, m_ay;
+    DBuf m_succ_ptr, m_succ_te, m_edge_d, m_npts, m_ax, m_ay;
     int full_tree_nodes = 0;
     int user_node_cap = 0;
 
@@ -74,7 +77,7 @@ struct pdmpc_handle {
     BatchDev batch{};
     int n_polys = 0, n_verts = 0, n_lane = 0;
     DBuf b_x0, b_y0, b_yaw0, b_trim0, b_refx, b_refy, b_vref, b_slot, b_poly, b_vx, b_vy, b_plx, b_ply,
-        b_lane, b_lx, b_ly, b_llx, b_lly;
+        b_lane, b_lx, b_ly, b_llx, b_lly, b_order;
 
     // outputs
     OutDev out{};
@@ -136,20 +139,18 @@ int pdmpc_create(int device_id, pdmpc_handle **out) {
     }
     for (auto &ev : h->ev) cudaEventCreate(&ev);
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device_id);
-    int occ[3] = {0, 0, 0};
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], KERNEL32, kWarp, 0);
+    int occ = 0;
+    e = cudaFuncSetAttribute(KERNEL_LAT, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem));
     if (e == cudaSuccess)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], KERNEL16, kWarp, 0);
-    if (e == cudaSuccess)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], KERNEL8, kWarp, 0);
-    if (e != cudaSuccess || occ[0] < 1 || occ[1] < 1 || occ[2] < 1) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, KERNEL_LAT, kWarp, sizeof(WarpSmem));
+    if (e != cudaSuccess || occ < 1) {
         std::string msg = std::string("pdmpc_create: search kernel is not launchable on this device (") +
                           cudaGetErrorString(e) + "); built for sm_100a";
         cudaStreamDestroy(h->stream);
         delete h;
         return fail(nullptr, PDMPC_ERR_CUDA, msg);
     }
-    for (int i = 0; i < 3; ++i) h->ctas_per_sm[i] = occ[i];
+    h->lat_ctas_per_sm = occ;
     *out = h;
     return PDMPC_OK;
 }
@@ -158,7 +159,7 @@ int pdmpc_destroy(pdmpc_handle *h) {
     if (!h) return PDMPC_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DBuf *bufs[] = {&h->m_succ_ptr, &h->m_succ, &h->m_npts, &h->m_ax, &h->m_ay, &h->b_x0, &h->b_y0, &h->b_yaw0, &h->b_trim0,
+    DBuf *bufs[] = {&h->m_succ_ptr, &h->m_succ_te, &h->m_edge_d, &h->m_npts, &h->m_ax, &h->m_ay, &h->b_order, &h->b_x0, &h->b_y0, &h->b_yaw0, &h->b_trim0,
                     &h->b_refx, &h->b_refy, &h->b_vref, &h->b_slot, &h->b_poly, &h->b_vx, &h->b_vy,
                     &h->b_plx, &h->b_ply, &h->b_lane, &h->b_lx, &h->b_ly, &h->b_llx, &h->b_lly,
                     &h->o_status, &h->o_exh, &h->o_nexp, &h->o_npops, &h->o_hash, &h->o_trims, &h->o_path,
@@ -183,11 +184,10 @@ int pdmpc_host_free(void *p) {
     return PDMPC_OK;
 }
 
-int pdmpc_set_tile(pdmpc_handle *h, int32_t lanes_per_search) {
+int pdmpc_set_variant(pdmpc_handle *h, int32_t variant) {
     if (!h) return PDMPC_ERR_BAD_INPUT;
-    if (lanes_per_search != 0 && lanes_per_search != 8 && lanes_per_search != 16 && lanes_per_search != 32)
-        return fail(h, PDMPC_ERR_BAD_INPUT, "lanes per search must be 0 (auto), 8, 16 or 32");
-    h->tile_mode = lanes_per_search;
+    if (variant < 0 || variant > 2) return fail(h, PDMPC_ERR_BAD_INPUT, "variant must be 0 (auto), 1 (latency) or 2 (throughput)");
+    h->variant_mode = variant;
     return PDMPC_OK;
 }
 
@@ -244,7 +244,7 @@ int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *d) {
     }
     // successor lists: find(transition_matrix_single(t,:,k)) ascending (expand_node.m:18)
     std::vector<int> succ_ptr((size_t)Hp * nT + 1, 0);
-    std::vector<SuccRec> succ;
+    std::vector<int> succ_te;
     for (int k = 0; k < Hp; ++k)
         for (int t = 0; t < nT; ++t) {
             const uint8_t *row = d->transition + ((size_t)k * nT + t) * nT;
@@ -252,12 +252,9 @@ int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *d) {
                 if (row[j]) {
                     int e = edge_of[(size_t)t * nT + j];
                     if (e < 0) return fail(h, PDMPC_ERR_BAD_INPUT, "upload_mpa: transition without maneuver");
-                    SuccRec r;
-                    r.dx = d->edge_dx[e]; r.dy = d->edge_dy[e]; r.dyaw = d->edge_dyaw[e];
-                    r.trim = (int16_t)(j + 1); r.edge = (int16_t)e; r.pad = 0;
-                    succ.push_back(r);
+                    succ_te.push_back((e << 8) | j);
                 }
-            succ_ptr[(size_t)k * nT + t + 1] = (int)succ.size();
+            succ_ptr[(size_t)k * nT + t + 1] = (int)succ_te.size();
         }
     // capacity bound: nodes of the full tree from the worst start trim
     double worst = 1;
@@ -281,9 +278,18 @@ int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *d) {
     h->full_tree_nodes = (int)std::min(worst, (double)(1 << 30));
 
     int64_t keep = h->stats.h2d_bytes;
-    UP(h, h->m_succ_ptr, succ_ptr.data(), succ_ptr.size());
-    UP(h, h->m_succ, succ.data(), succ.size());
-    UP(h, h->m_npts, d->area_npts, nE * 3);
+    auto pad16 = [](size_t bytes) { return (bytes + 15) / 16 * 16; };
+    auto padded = [&](auto &v, size_t elem) { v.resize(pad16(v.size() * elem) / elem); };
+    padded(succ_ptr, sizeof(int));
+    padded(succ_te, sizeof(int));
+    std::vector<double> edge_d((size_t)nE * 4, 0.0);
+    for (int e = 0; e < nE; ++e) {
+        edge_d[(size_t)e * 4 + 0] = d->edge_dx[e];
+        edge_d[(size_t)e * 4 + 1] = d->edge_dy[e];
+        edge_d[(size_t)e * 4 + 2] = d->edge_dyaw[e];
+    }
+    std::vector<int> npts(d->area_npts, d->area_npts + (size_t)nE * 3);
+    padded(npts, sizeof(int));
     // area points zero padded to the fixed stride (the kernel places all 8 columns)
     std::vector<double> ax((size_t)nE * 3 * PDMPC_AREA_STRIDE, 0.0), ay(ax.size(), 0.0);
     for (int e = 0; e < nE * 3; ++e)
@@ -291,6 +297,10 @@ int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *d) {
             ax[(size_t)e * PDMPC_AREA_STRIDE + i] = d->area_x[(size_t)e * PDMPC_AREA_STRIDE + i];
             ay[(size_t)e * PDMPC_AREA_STRIDE + i] = d->area_y[(size_t)e * PDMPC_AREA_STRIDE + i];
         }
+    UP(h, h->m_succ_ptr, succ_ptr.data(), succ_ptr.size());
+    UP(h, h->m_succ_te, succ_te.data(), succ_te.size());
+    UP(h, h->m_edge_d, edge_d.data(), edge_d.size());
+    UP(h, h->m_npts, npts.data(), npts.size());
     UP(h, h->m_ax, ax.data(), ax.size());
     UP(h, h->m_ay, ay.data(), ay.size());
     CU_TRY(h, cudaStreamSynchronize(h->stream));   // host vectors go out of scope
@@ -298,9 +308,21 @@ int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *d) {
     MpaDev &m = h->mpa;
     m.nT = nT; m.Hp = Hp; m.nE = nE;
     m.succ_ptr = h->m_succ_ptr.as<int>();
-    m.succ = h->m_succ.as<SuccRec>();
+    m.succ_te = h->m_succ_te.as<int>();
+    m.edge_d = h->m_edge_d.as<double>();
     m.area_npts = h->m_npts.as<int>();
     m.area_x = h->m_ax.as<double>(); m.area_y = h->m_ay.as<double>();
+    m.bytes_succ_ptr = (unsigned)(succ_ptr.size() * sizeof(int));
+    m.bytes_succ_te = (unsigned)(succ_te.size() * sizeof(int));
+    m.bytes_edge_d = (unsigned)(edge_d.size() * sizeof(double));
+    m.bytes_area_npts = (unsigned)(npts.size() * sizeof(int));
+    m.bytes_area = (unsigned)(ax.size() * sizeof(double));
+    m.table_bytes = m.bytes_succ_ptr + m.bytes_succ_te + m.bytes_edge_d + m.bytes_area_npts + 2 * m.bytes_area;
+    // throughput shape: tables + 16 warps' private state must fit the 227 KB of one SM
+    h->thr_smem = 16 + (size_t)m.table_bytes + (size_t)kWarpsThroughput * sizeof(WarpSmem);
+    h->thr_ok = h->thr_smem <= kSmemLimit;
+    if (h->thr_ok)
+        CU_TRY(h, cudaFuncSetAttribute(KERNEL_THR, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->thr_smem));
     h->has_mpa = true;
     h->staged = false;
     return PDMPC_OK;
@@ -418,6 +440,25 @@ int pdmpc_stage_batch(pdmpc_handle *h, const pdmpc_batch_in *in) {
     b.vert_x = h->b_vx.as<double>(); b.vert_y = h->b_vy.as<double>();
     b.lane_ptr = h->b_lane.as<int>(); b.lane_x = h->b_lx.as<double>(); b.lane_y = h->b_ly.as<double>();
     b.pl_x = b.pl_y = b.ll_x = b.ll_y = nullptr;
+    // work order: searches with the most obstacle polygons first (they are the ones most
+    // likely to run long / exhaust), so the tail of the batch is made of short searches
+    b.order = nullptr;
+    if (n > 1) {
+        std::vector<int> key(n), order(n);
+        int kmax = 0;
+        for (int i = 0; i < n; ++i) {
+            key[i] = in->slot_ptr[(size_t)(i + 1) * (Hp + 1)] - in->slot_ptr[(size_t)i * (Hp + 1)];
+            kmax = std::max(kmax, key[i]);
+        }
+        std::vector<int> cnt(kmax + 2, 0);
+        for (int i = 0; i < n; ++i) cnt[kmax - key[i] + 1]++;          // counting sort, descending key, stable
+        for (int k = 0; k <= kmax; ++k) cnt[k + 1] += cnt[k];
+        for (int i = 0; i < n; ++i) order[cnt[kmax - key[i]]++] = i;
+        int rc2 = upload(h, h->b_order, order.data(), (size_t)n);
+        if (rc2 != PDMPC_OK) return rc2;
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        b.order = h->b_order.as<int>();
+    }
     h->stats.kernel_launches = 0;
     if (in->checker == PDMPC_CHECKER_INTERX) {
         // NaN-separated polylines (vectorize_all_obstacles.m) built on the device
@@ -475,26 +516,25 @@ static int launch_search(pdmpc_handle *h, const TraceDev &tr) {
     CU_TRY(h, cudaMemsetAsync(h->o_counters.p, 0, 16 * sizeof(unsigned long long), h->stream));
     CU_TRY(h, cudaMemsetAsync(h->work_counter.p, 0, sizeof(unsigned), h->stream));
     if (n == 0) return PDMPC_OK;
-    // tile selection: a batch that cannot fill the machine with one search per warp
-    // runs wide (latency); a large batch runs 4 searches per warp (throughput)
-    int tile = h->tile_mode;
-    if (tile == 0) {
-        const int wide_slots = h->num_sms * h->ctas_per_sm[0];
-        tile = n <= wide_slots ? 32 : (n <= 2 * wide_slots ? 16 : 8);
-    }
-    const int variant = tile == 32 ? 0 : (tile == 16 ? 1 : 2);
-    const int per_cta = kWarp / tile;
-    const int grid = std::min((n + per_cta - 1) / per_cta, h->num_sms * h->ctas_per_sm[variant]);
-    int rc = ensure_arena(h, grid * per_cta);
-    if (rc != PDMPC_OK) return rc;
+    // shape selection: a batch that cannot give every SM several searches runs one warp per
+    // CTA (latency); a large batch runs one 16-warp CTA per SM with smem-resident tables
+    int variant = h->variant_mode;
+    if (variant == 0) variant = (h->thr_ok && n >= 4 * h->num_sms) ? 2 : 1;
+    if (variant == 2 && !h->thr_ok) variant = 1;
     unsigned *wc = h->work_counter.as<unsigned>();
-    CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
-    if (tile == 32)
-        KERNEL32<<<grid, kWarp, 0, h->stream>>>(h->mpa, h->batch, h->out, h->arena, wc, tr);
-    else if (tile == 16)
-        KERNEL16<<<grid, kWarp, 0, h->stream>>>(h->mpa, h->batch, h->out, h->arena, wc, tr);
-    else
-        KERNEL8<<<grid, kWarp, 0, h->stream>>>(h->mpa, h->batch, h->out, h->arena, wc, tr);
+    if (variant == 2) {
+        const int grid = std::min((n + kWarpsThroughput - 1) / kWarpsThroughput, h->num_sms);
+        int rc = ensure_arena(h, grid * kWarpsThroughput);
+        if (rc != PDMPC_OK) return rc;
+        CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
+        KERNEL_THR<<<grid, kWarpsThroughput * kWarp, h->thr_smem, h->stream>>>(h->mpa, h->batch, h->out, h->arena, wc, tr);
+    } else {
+        const int grid = std::min(n, h->num_sms * h->lat_ctas_per_sm);
+        int rc = ensure_arena(h, grid);
+        if (rc != PDMPC_OK) return rc;
+        CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
+        KERNEL_LAT<<<grid, kWarp, sizeof(WarpSmem), h->stream>>>(h->mpa, h->batch, h->out, h->arena, wc, tr);
+    }
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
     h->timing_pending_kernel = true;

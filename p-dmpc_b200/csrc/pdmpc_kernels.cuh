@@ -68,23 +68,24 @@ constexpr int kMaxHp = PDMPC_MAX_HP;
 constexpr int kParentCache = 32;   // entries, power of two
 
 // ---- device views -----------------------------------------------------------
-struct __align__(16) SuccRec {   // one allowed transition (t -> trim) at a given step
-    double dx, dy, dyaw;         // maneuver displacement in the parent frame
-    int16_t trim;                // 1-based end trim
-    int16_t edge;                // maneuver index (area tables)
-    int32_t pad;
-};
+// MPA tables as the kernel reads them.  All arrays are 16-byte aligned and their
+// byte sizes are multiples of 16 so that one TMA bulk copy each stages them in
+// shared memory (throughput variant); the latency variant reads them from global.
 struct MpaDev {
     int nT, Hp, nE;
     const int *succ_ptr;        // [Hp*nT + 1] successors of (step k, trim t) at (k-1)*nT + (t-1)
-    const SuccRec *succ;        // ascending end trim (expand_node.m:18)
-    const int *area_npts;       // [nE*3]
+    const int *succ_te;         // per successor: (edge << 8) | (end trim - 1), ascending end trim (expand_node.m:18)
+    const double *edge_d;       // [nE*4] maneuver dx, dy, dyaw, 0
+    const int *area_npts;       // [nE*3 (+pad)]
     const double *area_x, *area_y;  // [nE*3*8], zero padded
+    unsigned bytes_succ_ptr, bytes_succ_te, bytes_edge_d, bytes_area_npts, bytes_area;   // multiples of 16
+    unsigned table_bytes;       // sum of the above (area counted twice)
 };
 
 struct BatchDev {
     int n, checker;
     double dt;
+    const int *order;           // work item -> search index (heaviest-looking searches first), or null
     const double *x0, *y0, *yaw0;
     const int *trim0;
     const double *ref_x, *ref_y, *v_ref;
@@ -129,17 +130,19 @@ struct __align__(16) NodeCS {  // 16 B, written when the node is created
 };
 struct __align__(16) HEnt {    // heap entry
     double f;
-    // id:21 | parent id:21 | edge:10 | k:5 — everything the edge check of a popped
-    // node needs, so that no load depends on the node's own record
+    // id:21 | parent id:21 | edge:10 | k:5 | trim-1:7 — everything the edge check and the
+    // expansion of a popped node need, so that no table lookup depends on a node record
     unsigned long long w;
-    __device__ __forceinline__ static unsigned long long pack(unsigned id, unsigned pid, unsigned edge, unsigned k) {
+    __device__ __forceinline__ static unsigned long long pack(unsigned id, unsigned pid, unsigned edge, unsigned k,
+                                                              unsigned trim) {
         return (unsigned long long)id | ((unsigned long long)pid << 21) | ((unsigned long long)edge << 42) |
-               ((unsigned long long)k << 52);
+               ((unsigned long long)k << 52) | ((unsigned long long)(trim - 1u) << 57);
     }
     __device__ __forceinline__ unsigned id() const { return (unsigned)(w & 0x1fffffu); }
     __device__ __forceinline__ unsigned pid() const { return (unsigned)((w >> 21) & 0x1fffffu); }
     __device__ __forceinline__ unsigned edge() const { return (unsigned)((w >> 42) & 0x3ffu); }
     __device__ __forceinline__ unsigned k() const { return (unsigned)((w >> 52) & 0x1fu); }
+    __device__ __forceinline__ unsigned trim() const { return (unsigned)(w >> 57) + 1u; }
 };
 constexpr int kMaxNodeCap = 1 << 21;   // ids must fit 21 bits
 constexpr int kMaxEdges = 1 << 10;
@@ -218,7 +221,6 @@ template <int HS, int TILE>
 struct Heap {
     static constexpr int LV = 4;                   // levels fetched per round: 2+4+8+16 entries
     static constexpr int NL = 30;
-    static constexpr int Q = kWarp / TILE;         // entries per lane and round (positions q*TILE + lane)
     HEnt *sm;
     HEnt *gl;
     int len;
@@ -254,60 +256,46 @@ struct Heap {
 
     // pq.pop(): returns the top entry; caller guarantees len > 0.
     __device__ __forceinline__ HEnt pop(const Tile<TILE> &t) {
+        static_assert(TILE == kWarp, "one warp per search");
         const HEnt top = load(0);
         const int n = len - 1;   // heap size after the pop; entry[n] is re-inserted
         if (n > 0) {
             const HEnt v = load(n);
             t.sync();            // every lane has read top / v before any entry moves
-            int hole = 0, sel_lane = 0;
-            double lastf = 0.0, fsel = 0.0;
+            // lane <-> descendant of the hole (level d = 1..4 below it, offset o) for lanes 0..29
+            const int d = 31 - __clz(t.lane + 2);
+            const int o = t.lane + 2 - (1 << d);
+            int hole = 0, sel = 0;
+            double fsel = 0.0;
             bool moved = false;
             const int lim = (n - 1) / 2;
             while (hole < lim) {
-                // position pos = q*TILE + lane of the round <-> descendant (level d, offset o)
-                HEnt e[Q];
-                int idx[Q];
-                unsigned picks = 0;
-#pragma unroll
-                for (int q = 0; q < Q; ++q) {
-                    const int pos = q * TILE + t.lane;
-                    const int d = 31 - __clz(pos + 2);
-                    idx[q] = ((hole + 1) << d) - 1 + (pos + 2 - (1 << d));
-                    e[q].f = 0.0; e[q].w = 0;
-                    if (pos < NL && idx[q] < n) e[q] = load(idx[q]);
-                }
-#pragma unroll
-                for (int q = 0; q < Q; ++q) {
-                    // sibling pairs are positions (2r, 2r+1): the right one is taken unless f_right > f_left
-                    const double fs = t.shfl_xor(e[q].f, 1);
-                    const bool pick = (t.lane & 1) ? !(e[q].f > fs) : (fs > e[q].f);
-                    picks |= t.ballot(pick) << (q * TILE);
-                }
-                int rel = 0, sel = 0;
+                const int idx = ((hole + 1) << d) - 1 + o;
+                HEnt e;
+                e.f = 0.0; e.w = 0;
+                if (t.lane < NL && idx < n) e = load(idx);
+                // sibling pairs are lanes (2r, 2r+1): the right one is taken unless f_right > f_left
+                const double fs = t.shfl_xor(e.f, 1);
+                const bool pick = (t.lane & 1) ? !(e.f > fs) : (fs > e.f);
+                const unsigned picks = t.ballot(pick);
+                int rel = 0;
+                bool on = false;
 #pragma unroll
                 for (int lv = 1; lv <= LV; ++lv) {
                     if (hole < lim) {   // both children exist
-                        const int left_pos = (1 << lv) - 2 + 2 * rel;
-                        const int right = (picks >> (left_pos + 1)) & 1;
-                        sel = left_pos + right;
-                        const int q = sel / TILE;
-                        if (t.lane == sel % TILE) {
-#pragma unroll
-                            for (int qq = 0; qq < Q; ++qq)
-                                if (qq == q) store((idx[qq] - 1) >> 1, e[qq]);   // picked child moves up
-                        }
+                        const int left = (1 << lv) - 2 + 2 * rel;
+                        const int right = (picks >> (left + 1)) & 1;
+                        sel = left + right;
+                        on = on || (t.lane == sel);
                         hole = 2 * hole + 1 + right;
                         rel = 2 * rel + right;
                     }
                 }
-                fsel = e[0].f;
-#pragma unroll
-                for (int qq = 1; qq < Q; ++qq)
-                    if (qq == sel / TILE) fsel = e[qq].f;
-                sel_lane = sel % TILE;
+                if (on) store((idx - 1) >> 1, e);      // every picked child moves into its parent's place
+                fsel = e.f;
                 moved = true;
             }
-            if (moved) lastf = t.shfl(fsel, sel_lane);   // f of the last entry that moved up
+            double lastf = moved ? t.shfl(fsel, sel) : 0.0;   // f of the last entry that moved up
             if ((n & 1) == 0 && hole == (n - 2) / 2) {   // single (left) child at n-1
                 const HEnt e = load(n - 1);
                 if (t.lane == 0) store(hole, e);
@@ -375,12 +363,17 @@ template <int NE, int TILE>
 __device__ __forceinline__ bool interx_ranges(const double *px, const double *py, int lo0, int hi0, int lo1,
                                               int hi1, const double *shx, const double *shy,
                                               const Tile<TILE> &t) {
-    double dx1[NE], dy1[NE], S1[NE];
+    double vx[NE + 1], vy[NE + 1], dx1[NE], dy1[NE], S1[NE];
+#pragma unroll
+    for (int i = 0; i <= NE; ++i) {
+        vx[i] = shx[i];
+        vy[i] = shy[i];
+    }
 #pragma unroll
     for (int i = 0; i < NE; ++i) {
-        dx1[i] = shx[i + 1] - shx[i];
-        dy1[i] = shy[i + 1] - shy[i];
-        S1[i] = dx1[i] * shy[i] - dy1[i] * shx[i];
+        dx1[i] = vx[i + 1] - vx[i];
+        dy1[i] = vy[i + 1] - vy[i];
+        S1[i] = dx1[i] * vy[i] - dy1[i] * vx[i];
     }
     bool hit = false;
 #pragma unroll 1
@@ -396,15 +389,16 @@ __device__ __forceinline__ bool interx_ranges(const double *px, const double *py
             double a[NE];
 #pragma unroll
             for (int i = 0; i < NE; ++i) a[i] = (dx1[i] * y - dy1[i] * x) - S1[i];
+#pragma unroll 1
             for (int j = j0; j < j1; ++j) {
                 const double xn = px[j + 1], yn = py[j + 1];
                 const double dx2 = xn - x, dy2 = yn - y;
                 const double S2 = dx2 * y - dy2 * x;
-                double bprev = (shy[0] * dx2 - shx[0] * dy2) - S2;
+                double bprev = (vy[0] * dx2 - vx[0] * dy2) - S2;
 #pragma unroll
                 for (int i = 0; i < NE; ++i) {
                     const double an = (dx1[i] * yn - dy1[i] * xn) - S1[i];
-                    const double bn = (shy[i + 1] * dx2 - shx[i + 1] * dy2) - S2;
+                    const double bn = (vy[i + 1] * dx2 - vx[i + 1] * dy2) - S2;
                     hit = hit || ((a[i] * an < 0) && (bprev * bn < 0));
                     a[i] = an;
                     bprev = bn;
@@ -528,13 +522,46 @@ __device__ __forceinline__ unsigned long long hash_step(unsigned long long h, un
     return (h ^ (unsigned long long)v) * 0x100000001b3ULL;
 }
 
+// Table pointers as seen by the kernel body (shared-memory copies or the global arrays).
+struct Tables {
+    const int *succ_ptr, *succ_te, *area_npts;
+    const double *edge_d, *area_x, *area_y;
+};
+
 // Rotate/translate one maneuver area point: GraphSearch.m:158-159.
-__device__ __forceinline__ void place_point(const MpaDev &m, int edge, int kind, int i, double c, double s,
+__device__ __forceinline__ void place_point(const Tables &tb, int edge, int kind, int i, double c, double s,
                                             double px, double py, double &ox, double &oy) {
     const int base = (edge * 3 + kind) * kAreaStride + i;
-    double ax = __ldg(m.area_x + base), ay = __ldg(m.area_y + base);
+    const double ax = tb.area_x[base], ay = tb.area_y[base];
     ox = c * ax - s * ay + px;
     oy = s * ax + c * ay + py;
+}
+
+// ---- TMA bulk copy (global -> shared) + mbarrier, sm_90+/sm_100 PTX -----------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_%=;\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
 }
 
 template <int HS, int SP>
@@ -553,24 +580,63 @@ struct __align__(16) TileSmem {
 };
 
 // ============================================================================
-// The search kernel.  Persistent: every tile owns one arena slot and pulls
-// search indices from a global counter until the batch is drained.  The body is
-// ONE loop (a small state machine) so that the tiles of a warp stay converged:
-// an iteration is "finish / fetch a search if needed, then one pop".
-template <int HS, int SP, int TILE>
-__global__ void __launch_bounds__(kWarp) search_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar,
-                                                       unsigned *work_counter, TraceDev tr) {
-    constexpr int NT = kWarp / TILE;
-    __shared__ TileSmem<HS, SP> s_tiles[NT];
+// The search kernel.  Persistent: every warp owns one arena slot and pulls work
+// items from a global counter until the batch is drained.  The body is ONE loop
+// (a small state machine): an iteration is "finish / fetch a search if needed,
+// then one pop".
+//
+// Two launch shapes of the same code:
+//   latency    (WARPS = 1, SMEM_TABLES = false): one warp per CTA, MPA tables read
+//              through L1/L2; used when the batch cannot fill the GPU anyway.
+//   throughput (WARPS = 16, SMEM_TABLES = true): one 16-warp CTA per SM; the MPA
+//              tables are staged once per CTA into shared memory by TMA bulk copies
+//              (cp.async.bulk + mbarrier), each warp still runs its own searches.
+template <int HS, int SP, int WARPS, bool SMEM_TABLES>
+__global__ void __launch_bounds__(WARPS *kWarp) search_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar,
+                                                              unsigned *work_counter, TraceDev tr) {
+    constexpr int TILE = kWarp;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Tables tb;
+    unsigned char *warp_base = smem_raw;
+    if (SMEM_TABLES) {
+        // [mbarrier | succ_ptr | succ_te | edge_d | area_npts | area_x | area_y | per-warp state]
+        unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem_raw);
+        unsigned char *q = smem_raw + 16;
+        int *s_succ_ptr = reinterpret_cast<int *>(q); q += m.bytes_succ_ptr;
+        int *s_succ_te = reinterpret_cast<int *>(q); q += m.bytes_succ_te;
+        double *s_edge_d = reinterpret_cast<double *>(q); q += m.bytes_edge_d;
+        int *s_area_npts = reinterpret_cast<int *>(q); q += m.bytes_area_npts;
+        double *s_area_x = reinterpret_cast<double *>(q); q += m.bytes_area;
+        double *s_area_y = reinterpret_cast<double *>(q); q += m.bytes_area;
+        warp_base = q;
+        if (threadIdx.x == 0) {
+            mbar_init(bar, 1);
+            mbar_expect_tx(bar, m.table_bytes);
+            tma_bulk_g2s(s_succ_ptr, m.succ_ptr, m.bytes_succ_ptr, bar);
+            tma_bulk_g2s(s_succ_te, m.succ_te, m.bytes_succ_te, bar);
+            tma_bulk_g2s(s_edge_d, m.edge_d, m.bytes_edge_d, bar);
+            tma_bulk_g2s(s_area_npts, m.area_npts, m.bytes_area_npts, bar);
+            tma_bulk_g2s(s_area_x, m.area_x, m.bytes_area, bar);
+            tma_bulk_g2s(s_area_y, m.area_y, m.bytes_area, bar);
+        }
+        __syncthreads();          // barrier initialised before anyone polls it
+        mbar_wait(bar, 0);        // all table bytes have landed
+        tb.succ_ptr = s_succ_ptr; tb.succ_te = s_succ_te; tb.edge_d = s_edge_d;
+        tb.area_npts = s_area_npts; tb.area_x = s_area_x; tb.area_y = s_area_y;
+    } else {
+        tb.succ_ptr = m.succ_ptr; tb.succ_te = m.succ_te; tb.edge_d = m.edge_d;
+        tb.area_npts = m.area_npts; tb.area_x = m.area_x; tb.area_y = m.area_y;
+    }
+    const int warp_id = threadIdx.x / kWarp;
+    TileSmem<HS, SP> &sm = reinterpret_cast<TileSmem<HS, SP> *>(warp_base)[warp_id];
 
     Tile<TILE> t;
-    t.shift = (threadIdx.x / TILE) * TILE;
-    t.lane = threadIdx.x % TILE;
-    t.mask = Tile<TILE>::kBits << t.shift;
-    TileSmem<HS, SP> &sm = s_tiles[threadIdx.x / TILE];
+    t.shift = 0;
+    t.lane = threadIdx.x % kWarp;
+    t.mask = 0xffffffffu;
 
     const int Hp = m.Hp, nT = m.nT;
-    const size_t slot_base = ((size_t)blockIdx.x * NT + threadIdx.x / TILE) * (size_t)ar.cap;
+    const size_t slot_base = ((size_t)blockIdx.x * WARPS + warp_id) * (size_t)ar.cap;
     NodeA *__restrict__ na = ar.a + slot_base;
     NodeB *__restrict__ nb = ar.b + slot_base;
     NodeCS *__restrict__ ncs = ar.cs + slot_base;
@@ -647,13 +713,13 @@ __global__ void __launch_bounds__(kWarp) search_kernel(MpaDev m, BatchDev b, Out
                             qa = na[qid];
                             qcs = ncs[qid];
                             edge = pb.edge;
-                            ns = __ldg(m.area_npts + edge * 3 + PDMPC_AREA_NORMAL);
+                            ns = tb.area_npts[edge * 3 + PDMPC_AREA_NORMAL];
                         }
                         o.shape_npts[os] = ns;
                         if (o.shape_x && o.shape_y) {
                             for (int i = 0; i < kAreaStride; ++i) {
                                 double ox = 0.0, oy = 0.0;
-                                if (i < ns) place_point(m, edge, PDMPC_AREA_NORMAL, i, qcs.c, qcs.s, qa.x, qa.y, ox, oy);
+                                if (i < ns) place_point(tb, edge, PDMPC_AREA_NORMAL, i, qcs.c, qcs.s, qa.x, qa.y, ox, oy);
                                 o.shape_x[os * kAreaStride + i] = ox;
                                 o.shape_y[os * kAreaStride + i] = oy;
                             }
@@ -668,7 +734,7 @@ __global__ void __launch_bounds__(kWarp) search_kernel(MpaDev m, BatchDev b, Out
             if (t.lane == 0) si_u = atomicAdd(work_counter, 1u);
             si_u = t.shfl(si_u, 0);
             if (si_u >= (unsigned)b.n) break;
-            si = (int)si_u;
+            si = b.order ? __ldg(b.order + si_u) : (int)si_u;
             // ---- per-search set-up ------------------------------------------------
             t.sync();
             for (int k = t.lane; k < Hp; k += TILE) {
@@ -690,7 +756,7 @@ __global__ void __launch_bounds__(kWarp) search_kernel(MpaDev m, BatchDev b, Out
                 na[1] = ra;
                 nb[1] = rb;
                 HEnt re;
-                re.f = 0.0; re.w = HEnt::pack(1u, 0u, 0u, 0u);
+                re.f = 0.0; re.w = HEnt::pack(1u, 0u, 0u, 0u, (unsigned)trim0);
                 heap.store(0, re);
             }
             heap.len = 1;
@@ -753,10 +819,18 @@ __global__ void __launch_bounds__(kWarp) search_kernel(MpaDev m, BatchDev b, Out
             *tr.n = n_pops;
         }
 
-        // one round of independent loads: own record (for the expansion), the parent's
-        // record (unless cached) and the maneuver areas (edge and depth ride in the heap entry)
-        const NodeB cb = nb[id];
+        // one round of independent loads: own record (needed by the expansion only, its
+        // latency hides behind the edge check), the parent's record (unless cached) and the
+        // maneuver areas / successor list (edge, depth and trim ride in the heap entry)
         const NodeA ca = na[id];
+        const NodeCS ccs = ncs[id];
+        const int ctrim = (int)top.trim();
+        const int k_exp = cK + 1;
+        int sbase = 0, nchild = 0;
+        if (cK < Hp) {
+            sbase = tb.succ_ptr[(k_exp - 1) * nT + (ctrim - 1)];
+            nchild = tb.succ_ptr[(k_exp - 1) * nT + (ctrim - 1) + 1] - sbase;
+        }
         bool valid = true;
         if (par != 0) {   // eval_edge_exact :137-192 (root is valid unchecked)
             if (par != last_par) {
@@ -772,19 +846,15 @@ __global__ void __launch_bounds__(kWarp) search_kernel(MpaDev m, BatchDev b, Out
             }
             const int edge = (int)top.edge();
             const int bkind = (cK == Hp) ? PDMPC_AREA_LARGE_OFFSET : PDMPC_AREA_WITHOUT_OFFSET;  // :166-174
-            const int ns = __ldg(m.area_npts + edge * 3 + PDMPC_AREA_NORMAL);
-            const int nbs = __ldg(m.area_npts + edge * 3 + bkind);
-            t.sync();
+            const int ns = tb.area_npts[edge * 3 + PDMPC_AREA_NORMAL];
+            const int nbs = tb.area_npts[edge * 3 + bkind];
+            // (no barrier needed before the writes: the vote that ended the previous edge check
+            // ordered all lanes' reads of the shape arrays)
             // all 8 (zero padded) points of both areas are placed; only the first ns / nbs are used
-            if (TILE >= 16) {
-                if (t.lane < 8)
-                    place_point(m, edge, PDMPC_AREA_NORMAL, t.lane, pc, ps, ppx, ppy, sm.shx[t.lane], sm.shy[t.lane]);
-                else if (t.lane < 16)
-                    place_point(m, edge, bkind, t.lane - 8, pc, ps, ppx, ppy, sm.bhx[t.lane - 8], sm.bhy[t.lane - 8]);
-            } else {
-                place_point(m, edge, PDMPC_AREA_NORMAL, t.lane, pc, ps, ppx, ppy, sm.shx[t.lane], sm.shy[t.lane]);
-                place_point(m, edge, bkind, t.lane, pc, ps, ppx, ppy, sm.bhx[t.lane], sm.bhy[t.lane]);
-            }
+            if (t.lane < 8)
+                place_point(tb, edge, PDMPC_AREA_NORMAL, t.lane, pc, ps, ppx, ppy, sm.shx[t.lane], sm.shy[t.lane]);
+            else if (t.lane < 16)
+                place_point(tb, edge, bkind, t.lane - 8, pc, ps, ppx, ppy, sm.bhx[t.lane - 8], sm.bhy[t.lane - 8]);
             t.sync();
             PROF_MARK(2);   // record loads + shape placement
 
@@ -823,12 +893,8 @@ __global__ void __launch_bounds__(kWarp) search_kernel(MpaDev m, BatchDev b, Out
         if (cK == Hp) { goal = id; phase = DONE; continue; }    // :81-90
 
         // ---- expand_node.m:1-91 (nV == 1) --------------------------------------
-        const int k_exp = cK + 1;
-        const int sbase = __ldg(m.succ_ptr + (k_exp - 1) * nT + ((int)cb.trim - 1));
-        const int nchild = __ldg(m.succ_ptr + (k_exp - 1) * nT + ((int)cb.trim - 1) + 1) - sbase;
         if (n_nodes + nchild >= ar.cap) { status = PDMPC_ERR_CAPACITY; phase = DONE; continue; }
         // :50-51 cos/sin of this node's yaw were computed when the node was created
-        const NodeCS ccs = ncs[id];
         const double s = ccs.s, c = ccs.c;
         if (t.lane == 0) {
             const int cslot = id & (kParentCache - 1);
@@ -843,11 +909,14 @@ __global__ void __launch_bounds__(kWarp) search_kernel(MpaDev m, BatchDev b, Out
             he.f = 0.0; he.w = 0;
             const unsigned nid = (unsigned)(n_nodes + 1 + ci);
             if (ci < nchild) {
-                const SuccRec sr = m.succ[sbase + ci];
+                const int te = tb.succ_te[sbase + ci];
+                const int cedge = te >> 8, t2 = (te & 0xff) + 1;
+                const double mdx = tb.edge_d[cedge * 4 + 0], mdy = tb.edge_d[cedge * 4 + 1],
+                             mdyaw = tb.edge_d[cedge * 4 + 2];
                 NodeA ea;
-                ea.x = c * sr.dx - s * sr.dy + ca.x;      // :53
-                ea.y = s * sr.dx + c * sr.dy + ca.y;      // :54
-                ea.yaw = ca.yaw + sr.dyaw;                // :55
+                ea.x = c * mdx - s * mdy + ca.x;          // :53
+                ea.y = s * mdx + c * mdy + ca.y;          // :54
+                ea.yaw = ca.yaw + mdyaw;                  // :55
                 const double ddx = ea.x - sm.refx[k_exp - 1], ddy = ea.y - sm.refy[k_exp - 1];
                 const double nrm = sqrt(ddx * ddx + ddy * ddy);
                 ea.g = ca.g + nrm * nrm;            // :61
@@ -871,15 +940,15 @@ __global__ void __launch_bounds__(kWarp) search_kernel(MpaDev m, BatchDev b, Out
                     }
                 }
                 NodeB eb;
-                eb.h = eh; eb.parent = id; eb.edge = (unsigned short)sr.edge;
-                eb.trim = (unsigned char)sr.trim; eb.k = (unsigned char)k_exp;
+                eb.h = eh; eb.parent = id; eb.edge = (unsigned short)cedge;
+                eb.trim = (unsigned char)t2; eb.k = (unsigned char)k_exp;
                 NodeCS ecs;                         // for the child's own expansion (off the critical path)
                 sincos_ref(ea.yaw, ecs.s, ecs.c);
                 na[nid] = ea;                       // Tree.m:54-70 add_nodes
                 nb[nid] = eb;
                 ncs[nid] = ecs;
                 he.f = ea.g + eh;                   // GraphSearch.m:102 (weights 1)
-                he.w = HEnt::pack(nid, id, (unsigned)sr.edge, (unsigned)k_exp);
+                he.w = HEnt::pack(nid, id, (unsigned)cedge, (unsigned)k_exp, (unsigned)t2);
             }
             PROF_MARK(4);   // successor generation
             heap.push_many(he, cnt, t);             // :104, one push per child, in order

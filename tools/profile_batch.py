@@ -27,13 +27,13 @@ def main():
         b = SearchBatch.concat([b] * reps)
     p = capi.Planner(0)
     p.upload_mpa(mpa)
-    p.set_tile(tile)
+    p.set_variant(tile)
     p.stage(b)
     for i in range(runs):
         p.run_staged()
         p.sync()
         st = p.stats()
-        print(f"tile {tile} run {i}: {b.n} searches kernel {st.kernel_ms:.3f} ms -> {b.n / st.kernel_ms * 1e3:.0f} plans/s")
+        print(f"variant {tile} run {i}: {b.n} searches kernel {st.kernel_ms:.3f} ms -> {b.n / st.kernel_ms * 1e3:.0f} plans/s")
     r = p.fetch()
     st = p.stats()
     print("pops", st.total_pops, "nodes", st.total_nodes, "cols", st.total_obstacle_cols,
