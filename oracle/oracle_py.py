@@ -168,6 +168,12 @@ class ReferencePQ:
                                      int(ids.size))
 
     def pop(self):
+        # The reference answers -1 for an empty queue (mex.cpp:87-94) but then still calls
+        # std::priority_queue::pop() on it (:96-99), which is undefined behaviour in libstdc++
+        # (the vector's size underflows).  The search never touches the queue again after that
+        # (GraphSearch.m:57-61), a test harness does: answer -1 without executing the UB.
+        if self.size() == 0:
+            return -1, -1.0
         v = C.c_double()
         i = ReferencePQ._lib.pq_ref_pop(self.obj, C.byref(v))
         return int(i), v.value

@@ -43,3 +43,30 @@ def straight_iter(mpa, x=0.0, y=0.0, yaw=0.0, speed=None, **kw) -> IterationData
     ref = np.column_stack([x + np.cos(yaw) * d, y + np.sin(yaw) * d])
     return IterationData(x0=np.array([x, y, yaw, 0.0]), trim_indices=mpa.trim_from_values(0.0, 0.0),
                          reference_trajectory_points=ref, v_ref=np.full(Hp, v), **kw)
+
+
+GOLDEN_DIR = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "golden")
+GOLDEN_CASES = ("circle_sat_single_speed", "road_interx_single_speed", "road_interx_triple_speed")
+
+
+def load_golden(name: str):
+    """tests/golden/<name>.npz (tools/make_golden.py) -> (mpa, batch, expected BatchResult)."""
+    import dataclasses
+    import os
+
+    from pdmpc_b200.mpa import MotionPrimitiveAutomaton
+    from pdmpc_b200.records import BatchResult
+
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+
+    def build(cls, prefix):
+        kw = {}
+        for f in dataclasses.fields(cls):
+            a = z[prefix + f.name]
+            kw[f.name] = a.item() if a.ndim == 0 else a
+        return cls(**kw)
+
+    mpa = build(MotionPrimitiveAutomaton, "mpa__")
+    batch = build(SearchBatch, "in__")
+    exp = build(BatchResult, "out__")
+    return mpa, batch, exp

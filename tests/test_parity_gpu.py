@@ -12,7 +12,7 @@ from pdmpc_b200 import capi
 from pdmpc_b200.mpa import build_mpa, get_mpa
 from pdmpc_b200.records import CHECKER_INTERX, CHECKER_SAT, SearchBatch
 
-from helpers import circle_records, rect, road_records, straight_iter
+from helpers import GOLDEN_CASES, circle_records, load_golden, rect, road_records, straight_iter
 
 pytestmark = pytest.mark.gpu
 
@@ -32,6 +32,21 @@ def check(planner, mpa, batch, variants=VARIANTS, **kw):
     finally:
         planner.set_variant(0)
     return info, dev, ref
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden_fixture(planner, name):
+    """CUDA path through the C ABI against the committed fixtures (tests/golden, made by
+    tools/make_golden.py after both CPU restatements agreed): no oracle involved at run time."""
+    mpa, batch, exp = load_golden(name)
+    planner.upload_mpa(mpa)
+    try:
+        for variant in VARIANTS:
+            planner.set_variant(variant)
+            dev = planner.plan_batch(batch, raise_on_search_error=False)
+            parity.compare(dev, exp)
+    finally:
+        planner.set_variant(0)
 
 
 def test_circle_config0_sat(planner):
