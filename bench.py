@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--sim-steps", type=int, default=35)
     ap.add_argument("--vehicles", type=int, default=20)
     ap.add_argument("--mpa", default="triple_speed")
+    ap.add_argument("--no-cache", action="store_true", help="do not read/write the record cache under build/")
     ap.add_argument("--cpu-sample", type=int, default=0, help="searches in the CPU sample (0 = auto)")
     return ap.parse_args()
 
@@ -111,19 +112,29 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_records(planner, mpa, n_scen: int, seed0: int, vehicles: int, sim_steps: int):
-    """Closed-loop roll-out of n_scen road-network scenarios with the GPU planner (untimed)."""
+def build_records(planner, mpa, n_scen: int, seed0: int, vehicles: int, sim_steps: int, cache: str = ""):
+    """Closed-loop roll-out of n_scen road-network scenarios with the GPU planner (untimed).
+    Returns (flat batch of every search record, [(step, level, n_searches)] of the first
+    scenario, whose records come first in the batch).  Cached under build/ (git-ignored) so
+    that profiler runs of the same command skip the generation launches."""
     from pdmpc_b200 import scenario
     from pdmpc_b200.records import SearchBatch
-    batches, per_step = [], []
+    if cache and os.path.exists(cache) and os.path.exists(cache + ".levels.npy"):
+        return SearchBatch.load(cache), np.load(cache + ".levels.npy")
+    batches, levels = [], []
     for s in range(n_scen):
         sc = scenario.commonroad_scenario(mpa, vehicles, seed=seed0 + s)
         runner = scenario.ScenarioRunner(sc, planner.plan_batch)
         recs = runner.run(sim_steps)
         batches.extend(r.batch for r in recs)
         if s == 0:
-            per_step = recs
-    return SearchBatch.concat(batches), per_step
+            levels = np.array([(r.step, r.level, r.batch.n) for r in recs], dtype=np.int64)
+    batch = SearchBatch.concat(batches)
+    if cache:
+        os.makedirs(os.path.dirname(cache), exist_ok=True)
+        batch.save(cache)
+        np.save(cache + ".levels.npy", levels)
+    return batch, levels
 
 
 def algorithmic_bytes(batch, stats, Hp: int) -> float:
@@ -217,8 +228,10 @@ def main():
     Hp = mpa.Hp
 
     t_gen = time.perf_counter()
+    cache = os.path.join(ROOT, "build", f"bench_{args.mpa}_{args.vehicles}v_{args.scenarios}s_{args.sim_steps}t_seed"
+                                        f"{1 + rank * args.scenarios}.npz")
     batch, step_recs = build_records(planner, mpa, args.scenarios, 1 + rank * args.scenarios,
-                                     args.vehicles, args.sim_steps)
+                                     args.vehicles, args.sim_steps, "" if args.no_cache else cache)
     t_gen = time.perf_counter() - t_gen
     n = batch.n
 
@@ -303,9 +316,10 @@ def main():
     # ---- per-time-step latency (levels sequential, host buffers) -----------------
     lat = []
     if rank == 0:
-        by_step = {}
-        for r in step_recs:
-            by_step.setdefault(r.step, []).append(r.batch)
+        by_step, off = {}, 0
+        for step, _level, cnt in step_recs:
+            by_step.setdefault(int(step), []).append(batch.select(np.arange(off, off + int(cnt))))
+            off += int(cnt)
         for rep in range(3):
             for k, levels in sorted(by_step.items()):
                 t0 = time.perf_counter()

@@ -1,0 +1,122 @@
+classdef GraphSearchCuda < OptimizerInterface
+    % GRAPHSEARCHCUDA  B200 drop-in for GraphSearch (hlc/optimizer/graph_search/GraphSearch.m).
+    %
+    %   Same call surface as every optimizer of the reference
+    %   (OptimizerInterface.m:14): info = run_optimizer(obj, veh_index, iter, mpa, options, time_step)
+    %   returns a ControlResultsInfo with the fields PrioritizedController.plan and
+    %   Simulation.apply consume (ControlResultsInfo.m:5-17).  The search itself runs on the
+    %   GPU through the C ABI of include/pdmpc_b200.h, bound by pdmpc_b200_mex.cpp.
+    %   There is no CPU fallback: without a CUDA device the constructor errors.
+    %
+    %   Selected by OptimizerType.CudaOptimal (see INTEGRATION.md for the two-line patch to
+    %   config/enums/OptimizerType.m and OptimizerInterface.get_optimizer).
+
+    properties (Constant, Hidden = true)
+        CREATE = 0;
+        DESTROY = 1;
+        UPLOAD_MPA = 2;
+        PLAN = 3;
+        STATS = 4;
+    end
+
+    properties (SetAccess = private, Hidden = true)
+        handle = uint64(0); % pdmpc_handle* owned by the MEX
+        mpa_key = ''; % which MPA tables are resident in HBM
+        checker (1, 1) double = 1; % 0 = SAT, 1 = InterX (OptimizerInterface.m:36-46)
+    end
+
+    methods
+
+        function obj = GraphSearchCuda(options, device_id)
+
+            arguments
+                options (1, 1) Config
+                device_id (1, 1) double = 0
+            end
+
+            obj = obj@OptimizerInterface();
+            obj.handle = pdmpc_b200_mex(GraphSearchCuda.CREATE, device_id);
+            % same selection rule as OptimizerInterface.set_constraint_checker
+            obj.checker = double(options.are_any_obstacles_non_convex);
+        end
+
+        function delete(obj)
+
+            if obj.handle ~= 0
+                pdmpc_b200_mex(GraphSearchCuda.DESTROY, obj.handle);
+                obj.handle = uint64(0);
+            end
+
+        end
+
+        function info = run_optimizer(obj, ~, iter, mpa, options, ~)
+            assert(iter.amount == 1, 'GraphSearchCuda plans one vehicle per call (prioritized controllers)');
+            obj.upload_mpa_once(mpa, options);
+
+            % iter.predicted_lanelet_boundary{1, 1:2}: left / right bound, 2 x n (may be empty)
+            left = zeros(2, 0); right = zeros(2, 0);
+
+            if ~isempty(iter.predicted_lanelet_boundary)
+                left = iter.predicted_lanelet_boundary{1, 1};
+                right = iter.predicted_lanelet_boundary{1, 2};
+            end
+
+            [is_exhausted, n_expanded, trims, y_pred, g_path, h_path, shapes] = pdmpc_b200_mex( ...
+                GraphSearchCuda.PLAN, obj.handle, ...
+                iter.x0(1, 1:3), iter.trim_indices(1), ...
+                squeeze(iter.reference_trajectory_points(1, :, :)), iter.v_ref(1, :), ...
+                iter.obstacles, iter.dynamic_obstacle_area, left, right, ...
+                obj.checker, options.dt_seconds);
+
+            info = ControlResultsInfo(iter.amount, options.Hp);
+            info.is_exhausted = is_exhausted; % read by the helper below (:84)
+            info.n_expanded = n_expanded;
+
+            if is_exhausted
+                % GraphSearch.m:57-61: only n_expanded, is_exhausted and the tree are set
+                info.tree = OptimizerInterface.create_tree(iter);
+                return
+            end
+
+            % NodeInfo order [x y yaw trim g h k exactEval] (NodeInfo.m:4-14)
+            next_nodes = cell(1, options.Hp);
+
+            for k = 1:options.Hp
+                next_nodes{k} = [y_pred(1, k), y_pred(2, k), y_pred(3, k), trims(k + 1), ...
+                                     g_path(k + 1), h_path(k + 1), k, 1];
+            end
+
+            y_full = {[y_pred', trims(2:end)']}; % one row per step: the helper takes the last row of each step
+            info = OptimizerInterface.create_control_results_info_from_mex( ...
+                info, iter, options, next_nodes, trims, y_full);
+            info.shapes = shapes; % 1 x Hp cell of 2 x n (return_path_area.m:5-7)
+            info.needs_fallback = false; % GraphSearch.m:88
+        end
+
+        function s = stats(obj)
+            % device-side counters of the last call: kernel_ms, pops, nodes, obstacle columns
+            s = pdmpc_b200_mex(GraphSearchCuda.STATS, obj.handle);
+        end
+
+    end
+
+    methods (Access = private)
+
+        function upload_mpa_once(obj, mpa, options)
+            % the analogue of the reference's library/*.mat cache key
+            % (MotionPrimitiveAutomaton.m:59-79): tables are staged in HBM once per MPA
+            key = sprintf('%s_Hp%d_T%g_nc%d', string(options.mpa_type), options.Hp, ...
+                options.dt_seconds, options.are_any_obstacles_non_convex);
+
+            if strcmp(key, obj.mpa_key)
+                return
+            end
+
+            pdmpc_b200_mex(GraphSearchCuda.UPLOAD_MPA, obj.handle, ...
+                double(mpa.transition_matrix_single), mpa.maneuvers);
+            obj.mpa_key = key;
+        end
+
+    end
+
+end

@@ -1,0 +1,292 @@
+// pdmpc_b200_mex.cpp — thin MEX shim: MATLAB arrays <-> the C ABI of include/pdmpc_b200.h.
+//
+// Plays the role priority_queue_interface_mex.cpp plays in the reference
+// (hlc/optimizer/graph_search/priority_queue/priority_queue_interface_mex.cpp:33-108):
+// a command dispatcher, first argument = command, handles owned by the MEX.  It only
+// marshals; every computation happens behind pdmpc_* on the GPU.  Called by
+// GraphSearchCuda.m; built by compile_pdmpc_b200.m (mex -R2018a, C Matrix API).
+//
+//   h = mex(CREATE, device_id)
+//       mex(DESTROY, h)
+//       mex(UPLOAD_MPA, h, transition_matrix_single [nT x nT x Hp], maneuvers {nT x nT})
+//   [is_exhausted, n_expanded, trims, y_pred, g_path, h_path, shapes] =
+//       mex(PLAN, h, x0 [1x3], trim, ref [Hp x 2], v_ref [1 x Hp], obstacles {n_s},
+//           dynamic_obstacle_area {n_d x Hp}, left [2 x nL], right [2 x nR], checker, dt)
+//   s = mex(STATS, h)
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mex.h"
+#include "pdmpc_b200.h"
+
+namespace {
+
+enum Command { CREATE = 0, DESTROY = 1, UPLOAD_MPA = 2, PLAN = 3, STATS = 4 };
+
+std::vector<pdmpc_handle *> g_handles;   // released at `clear mex` (HighLevelController.m:284-303)
+bool g_at_exit_registered = false;
+
+void release_all() {
+    for (pdmpc_handle *h : g_handles)
+        if (h) pdmpc_destroy(h);
+    g_handles.clear();
+}
+
+[[noreturn]] void fail(const char *id, const std::string &msg) {
+    mexErrMsgIdAndTxt(id, "%s", msg.c_str());
+    throw 0;   // not reached: mexErrMsgIdAndTxt does not return
+}
+
+pdmpc_handle *handle_of(const mxArray *a) {
+    const uint64_t idx = static_cast<uint64_t>(mxGetScalar(a));
+    if (idx == 0 || idx > g_handles.size() || !g_handles[idx - 1]) fail("pdmpc:handle", "invalid planner handle");
+    return g_handles[idx - 1];
+}
+
+void check(pdmpc_handle *h, int rc, const char *what) {
+    if (rc == PDMPC_OK) return;
+    const char *txt = pdmpc_last_error(h);
+    fail("pdmpc:status", std::string(what) + " failed (" + std::to_string(rc) + "): " + (txt ? txt : ""));
+}
+
+// Append a 2 x n polygon (column-major: x0 y0 x1 y1 ...) to the vertex pool.
+void append_polygon(const mxArray *p, std::vector<double> &vx, std::vector<double> &vy, std::vector<int32_t> &poly_ptr) {
+    if (!p || mxIsEmpty(p)) return;   // empty cells contribute nothing (SearchBatch.from_iters does the same)
+    if (mxGetM(p) != 2) fail("pdmpc:input", "obstacle polygons must be 2 x n");
+    const double *d = mxGetDoubles(p);
+    const size_t n = mxGetN(p);
+    for (size_t i = 0; i < n; ++i) {
+        vx.push_back(d[2 * i]);
+        vy.push_back(d[2 * i + 1]);
+    }
+    poly_ptr.push_back(static_cast<int32_t>(vx.size()));
+}
+
+void upload_mpa(pdmpc_handle *h, const mxArray *trans, const mxArray *maneuvers) {
+    // mpa.transition_matrix_single: nT x nT x Hp, column-major (t1, t2, k)
+    const mwSize nd = mxGetNumberOfDimensions(trans);
+    const mwSize *dims = mxGetDimensions(trans);
+    const int nT = static_cast<int>(dims[0]);
+    const int Hp = nd >= 3 ? static_cast<int>(dims[2]) : 1;
+    if (static_cast<int>(dims[1]) != nT) fail("pdmpc:input", "transition_matrix_single must be nT x nT x Hp");
+    const double *t = mxGetDoubles(trans);
+    std::vector<uint8_t> transition(static_cast<size_t>(Hp) * nT * nT);
+    for (int k = 0; k < Hp; ++k)
+        for (int t1 = 0; t1 < nT; ++t1)
+            for (int t2 = 0; t2 < nT; ++t2)
+                transition[(static_cast<size_t>(k) * nT + t1) * nT + t2] =
+                    t[t1 + static_cast<size_t>(nT) * t2 + static_cast<size_t>(nT) * nT * k] != 0.0;
+    // mpa.maneuvers{t1, t2}: struct with dx, dy, dyaw, area, area_without_offset, area_large_offset
+    std::vector<int32_t> from, to, npts;
+    std::vector<double> dx, dy, dyaw, ax, ay;
+    static const char *kAreas[3] = {"area", "area_without_offset", "area_large_offset"};
+    for (int t1 = 0; t1 < nT; ++t1)
+        for (int t2 = 0; t2 < nT; ++t2) {
+            const mxArray *m = mxGetCell(maneuvers, t1 + static_cast<size_t>(nT) * t2);
+            if (!m || mxIsEmpty(m)) continue;
+            from.push_back(t1 + 1);
+            to.push_back(t2 + 1);
+            // maneuvers are structs (generate_maneuver.m) or objects with the same property names
+            auto get = [&](const char *name) -> const mxArray * {
+                const mxArray *f = mxIsStruct(m) ? mxGetField(m, 0, name) : mxGetProperty(m, 0, name);
+                if (!f) fail("pdmpc:input", std::string("maneuver without field ") + name);
+                return f;
+            };
+            dx.push_back(mxGetScalar(get("dx")));
+            dy.push_back(mxGetScalar(get("dy")));
+            dyaw.push_back(mxGetScalar(get("dyaw")));
+            for (const char *name : kAreas) {
+                const mxArray *a = get(name);
+                const size_t n = mxGetN(a);
+                if (mxGetM(a) != 2 || n > PDMPC_AREA_STRIDE) fail("pdmpc:input", "maneuver area must be 2 x n, n <= 8");
+                const double *d = mxGetDoubles(a);
+                npts.push_back(static_cast<int32_t>(n));
+                for (size_t i = 0; i < PDMPC_AREA_STRIDE; ++i) {
+                    ax.push_back(i < n ? d[2 * i] : 0.0);
+                    ay.push_back(i < n ? d[2 * i + 1] : 0.0);
+                }
+            }
+        }
+    pdmpc_mpa_desc d;
+    d.n_trims = nT;
+    d.Hp = Hp;
+    d.n_edges = static_cast<int32_t>(from.size());
+    d.transition = transition.data();
+    d.edge_from = from.data();
+    d.edge_to = to.data();
+    d.edge_dx = dx.data();
+    d.edge_dy = dy.data();
+    d.edge_dyaw = dyaw.data();
+    d.area_npts = npts.data();
+    d.area_x = ax.data();
+    d.area_y = ay.data();
+    check(h, pdmpc_upload_mpa(h, &d), "pdmpc_upload_mpa");
+}
+
+void plan(pdmpc_handle *h, int nlhs, mxArray *plhs[], const mxArray *prhs[]) {
+    const mxArray *x0 = prhs[2], *ref = prhs[4], *vref = prhs[5], *obst = prhs[6], *dyn = prhs[7];
+    const mxArray *left = prhs[8], *right = prhs[9];
+    const int Hp = static_cast<int>(mxGetNumberOfElements(vref));
+    if (mxGetNumberOfElements(x0) < 3 || mxGetNumberOfElements(ref) != static_cast<size_t>(2 * Hp))
+        fail("pdmpc:input", "x0 must hold (x, y, yaw) and ref must be Hp x 2");
+    const double *px0 = mxGetDoubles(x0);
+    const double *pref = mxGetDoubles(ref);   // Hp x 2 column-major: x(1..Hp), y(1..Hp)
+    const double *pv = mxGetDoubles(vref);
+    int32_t trim0 = static_cast<int32_t>(mxGetScalar(prhs[3]));
+
+    // obstacle CSR, slot 0 = iter.obstacles, slot k = iter.dynamic_obstacle_area(:, k)
+    std::vector<int32_t> slot_ptr(1, 0), poly_ptr(1, 0);
+    std::vector<double> vx, vy;
+    const size_t n_static = mxIsCell(obst) ? mxGetNumberOfElements(obst) : 0;
+    for (size_t i = 0; i < n_static; ++i) append_polygon(mxGetCell(obst, i), vx, vy, poly_ptr);
+    slot_ptr.push_back(static_cast<int32_t>(poly_ptr.size() - 1));
+    const size_t n_rows = mxIsCell(dyn) ? mxGetM(dyn) : 0;
+    const size_t n_cols = mxIsCell(dyn) ? mxGetN(dyn) : 0;
+    for (int k = 0; k < Hp; ++k) {
+        if (static_cast<size_t>(k) < n_cols)   // vectorize_all_obstacles.m:39-43
+            for (size_t r = 0; r < n_rows; ++r) append_polygon(mxGetCell(dyn, r + n_rows * k), vx, vy, poly_ptr);
+        slot_ptr.push_back(static_cast<int32_t>(poly_ptr.size() - 1));
+    }
+    // lanelet bounds: open polylines
+    std::vector<int32_t> lane_ptr(1, 0);
+    std::vector<double> lx, ly;
+    for (const mxArray *side : {left, right}) {
+        if (side && !mxIsEmpty(side)) {
+            if (mxGetM(side) != 2) fail("pdmpc:input", "lanelet bounds must be 2 x n");
+            const double *d = mxGetDoubles(side);
+            for (size_t i = 0; i < mxGetN(side); ++i) {
+                lx.push_back(d[2 * i]);
+                ly.push_back(d[2 * i + 1]);
+            }
+        }
+        lane_ptr.push_back(static_cast<int32_t>(lx.size()));
+    }
+
+    pdmpc_batch_in in;
+    std::memset(&in, 0, sizeof(in));
+    in.n_searches = 1;
+    in.checker = static_cast<int32_t>(mxGetScalar(prhs[10]));
+    in.dt_seconds = mxGetScalar(prhs[11]);
+    in.x0 = &px0[0];
+    in.y0 = &px0[1];
+    in.yaw0 = &px0[2];
+    in.trim0 = &trim0;
+    in.ref_x = pref;
+    in.ref_y = pref + Hp;
+    in.v_ref = pv;
+    in.slot_ptr = slot_ptr.data();
+    in.poly_ptr = poly_ptr.data();
+    in.vert_x = vx.data();
+    in.vert_y = vy.data();
+    in.lane_ptr = lane_ptr.data();
+    in.lane_x = lx.data();
+    in.lane_y = ly.data();
+
+    int32_t status = -1, n_expanded = 0;
+    uint8_t exhausted = 0;
+    std::vector<int32_t> trims(Hp + 1), shape_npts(Hp);
+    std::vector<double> ypred(3 * Hp), g(Hp + 1), hh(Hp + 1), sx(Hp * PDMPC_AREA_STRIDE), sy(Hp * PDMPC_AREA_STRIDE);
+    pdmpc_batch_out out;
+    std::memset(&out, 0, sizeof(out));
+    out.status = &status;
+    out.is_exhausted = &exhausted;
+    out.n_expanded = &n_expanded;
+    out.trims = trims.data();
+    out.y_predicted = ypred.data();
+    out.g_path = g.data();
+    out.h_path = hh.data();
+    out.shape_npts = shape_npts.data();
+    out.shape_x = sx.data();
+    out.shape_y = sy.data();
+    check(h, pdmpc_plan_batch(h, &in, &out), "pdmpc_plan_batch");
+    if (status != PDMPC_OK)   // e.g. PDMPC_ERR_CAPACITY: loud, never a silently truncated search
+        fail("pdmpc:search", "search failed with status " + std::to_string(status));
+
+    plhs[0] = mxCreateLogicalScalar(exhausted != 0);
+    if (nlhs > 1) plhs[1] = mxCreateDoubleScalar(n_expanded);
+    if (nlhs > 2) {
+        plhs[2] = mxCreateDoubleMatrix(1, Hp + 1, mxREAL);
+        for (int k = 0; k <= Hp; ++k) mxGetDoubles(plhs[2])[k] = trims[k];
+    }
+    if (nlhs > 3) {   // 3 x Hp: (x, y, yaw) per step, the layout of info.y_predicted(:, :, 1)
+        plhs[3] = mxCreateDoubleMatrix(3, Hp, mxREAL);
+        std::memcpy(mxGetDoubles(plhs[3]), ypred.data(), sizeof(double) * 3 * Hp);
+    }
+    if (nlhs > 4) {
+        plhs[4] = mxCreateDoubleMatrix(1, Hp + 1, mxREAL);
+        std::memcpy(mxGetDoubles(plhs[4]), g.data(), sizeof(double) * (Hp + 1));
+    }
+    if (nlhs > 5) {
+        plhs[5] = mxCreateDoubleMatrix(1, Hp + 1, mxREAL);
+        std::memcpy(mxGetDoubles(plhs[5]), hh.data(), sizeof(double) * (Hp + 1));
+    }
+    if (nlhs > 6) {   // info.shapes: 1 x Hp cell of 2 x n
+        plhs[6] = mxCreateCellMatrix(1, Hp);
+        for (int k = 0; k < Hp; ++k) {
+            const int n = shape_npts[k];
+            mxArray *s = mxCreateDoubleMatrix(2, n, mxREAL);
+            double *d = mxGetDoubles(s);
+            for (int i = 0; i < n; ++i) {
+                d[2 * i] = sx[k * PDMPC_AREA_STRIDE + i];
+                d[2 * i + 1] = sy[k * PDMPC_AREA_STRIDE + i];
+            }
+            mxSetCell(plhs[6], k, s);
+        }
+    }
+}
+
+}  // namespace
+
+void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
+    if (nrhs < 1) fail("pdmpc:usage", "first argument must be the command");
+    if (!g_at_exit_registered) {
+        mexAtExit(release_all);
+        g_at_exit_registered = true;
+    }
+    const int cmd = static_cast<int>(mxGetScalar(prhs[0]));
+    if (cmd == CREATE) {
+        const int dev = nrhs > 1 ? static_cast<int>(mxGetScalar(prhs[1])) : 0;
+        pdmpc_handle *h = nullptr;
+        const int rc = pdmpc_create(dev, &h);
+        if (rc != PDMPC_OK) {
+            const char *txt = pdmpc_last_error(nullptr);
+            fail("pdmpc:create", std::string("pdmpc_create failed: ") + (txt ? txt : ""));
+        }
+        g_handles.push_back(h);
+        plhs[0] = mxCreateNumericMatrix(1, 1, mxUINT64_CLASS, mxREAL);
+        *static_cast<uint64_t *>(mxGetData(plhs[0])) = g_handles.size();   // 1-based; 0 = none
+        return;
+    }
+    if (nrhs < 2) fail("pdmpc:usage", "second argument must be the planner handle");
+    pdmpc_handle *h = handle_of(prhs[1]);
+    switch (cmd) {
+    case DESTROY: {
+        const uint64_t idx = static_cast<uint64_t>(mxGetScalar(prhs[1]));
+        pdmpc_destroy(h);
+        g_handles[idx - 1] = nullptr;
+        return;
+    }
+    case UPLOAD_MPA:
+        if (nrhs < 4) fail("pdmpc:usage", "UPLOAD_MPA needs transition_matrix_single and maneuvers");
+        upload_mpa(h, prhs[2], prhs[3]);
+        return;
+    case PLAN:
+        if (nrhs < 12) fail("pdmpc:usage", "PLAN needs 12 arguments");
+        plan(h, nlhs, plhs, prhs);
+        return;
+    case STATS: {
+        pdmpc_stats st;
+        check(h, pdmpc_get_stats(h, &st), "pdmpc_get_stats");
+        static const char *names[] = {"kernel_ms", "h2d_ms", "d2h_ms", "total_pops", "total_nodes", "total_obstacle_cols"};
+        plhs[0] = mxCreateStructMatrix(1, 1, 6, names);
+        const double vals[] = {st.kernel_ms, st.h2d_ms, st.d2h_ms, static_cast<double>(st.total_pops),
+                               static_cast<double>(st.total_nodes), static_cast<double>(st.total_obstacle_cols)};
+        for (int i = 0; i < 6; ++i) mxSetField(plhs[0], 0, names[i], mxCreateDoubleScalar(vals[i]));
+        return;
+    }
+    default:
+        fail("pdmpc:usage", "unknown command");
+    }
+}

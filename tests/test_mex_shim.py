@@ -1,0 +1,71 @@
+"""The MEX shim (p-dmpc_b200/matlab/pdmpc_b200_mex.cpp) compiled UNMODIFIED against a fake MATLAB
+C Matrix API and driven the way GraphSearchCuda.m drives it.  CPU part: it builds, dispatches
+commands and reports a missing device loudly.  GPU part: full marshalling parity against the
+golden fixtures, one run_optimizer-equivalent call per search."""
+import numpy as np
+import pytest
+
+import mexfake
+from helpers import GOLDEN_CASES, load_golden
+from test_oracle_cpu import _iters_from_batch
+
+
+@pytest.fixture(scope="module")
+def matlab(built):
+    return mexfake.FakeMatlab()
+
+
+def test_shim_builds_and_fails_loudly_without_device(matlab):
+    import torch
+    with pytest.raises(mexfake.MexError, match="pdmpc:usage"):
+        matlab.call(0)
+    with pytest.raises(mexfake.MexError, match="pdmpc:handle"):
+        matlab.call(0, mexfake.PLAN, 99.0)
+    if not torch.cuda.is_available():
+        with pytest.raises(mexfake.MexError, match="no CPU fallback"):
+            matlab.call(1, mexfake.CREATE, 0.0)
+
+
+def test_matlab_side_sources_present():
+    """The MATLAB class keeps the reference's call surface (OptimizerInterface.m:14)."""
+    import os
+    src = open(os.path.join(mexfake.ROOT, "p-dmpc_b200", "matlab", "GraphSearchCuda.m")).read()
+    assert "classdef GraphSearchCuda < OptimizerInterface" in src
+    assert "function info = run_optimizer(obj, ~, iter, mpa, options, ~)" in src
+    assert "create_control_results_info_from_mex" in src
+    comp = open(os.path.join(mexfake.ROOT, "p-dmpc_b200", "matlab", "compile_pdmpc_b200.m")).read()
+    assert "mex(" in comp and "pdmpc_b200_mex.cpp" in comp
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_mex_path_matches_golden(matlab, name):
+    mpa, batch, exp = load_golden(name)
+    (h,) = matlab.call(1, mexfake.CREATE, 0.0)
+    try:
+        trans, man = mexfake.matlab_mpa(mpa)
+        matlab.call(0, mexfake.UPLOAD_MPA, float(h), trans, man)
+        Hp = mpa.Hp
+        step = max(1, batch.n // 40)
+        picks = sorted(set(range(0, batch.n, step)) | set(np.flatnonzero(exp.is_exhausted).tolist()))
+        for i in picks:
+            it = _iters_from_batch(batch, i)
+            exh, n_exp, trims, ypred, g, hh, shapes = matlab.call(
+                7, mexfake.PLAN, float(h), it.x0[:3], float(it.trim_indices), it.reference_trajectory_points,
+                it.v_ref, list(it.obstacles), [list(r) for r in it.dynamic_obstacle_area] or [],
+                it.predicted_lanelet_boundary[0], it.predicted_lanelet_boundary[1], float(batch.checker),
+                float(batch.dt_seconds))
+            assert exh == bool(exp.is_exhausted[i]) and int(n_exp) == exp.n_expanded[i]
+            if not exh:
+                assert trims.reshape(-1).astype(int).tolist() == exp.trims[i].tolist()
+                assert np.array_equal(ypred.T.view(np.uint64), exp.y_predicted[i].view(np.uint64))
+                assert np.array_equal(g.reshape(-1).view(np.uint64), exp.g_path[i].view(np.uint64))
+                for k in range(Hp):
+                    n = int(exp.shape_npts[i, k])
+                    assert shapes[k].shape == (2, n)
+                    assert np.array_equal(shapes[k][0].view(np.uint64), exp.shape_x[i, k, :n].view(np.uint64))
+        (st,) = matlab.call(1, mexfake.STATS, float(h), raw=True)
+        assert matlab.field(st, "total_pops").reshape(-1)[0] >= 1
+    finally:
+        matlab.call(0, mexfake.DESTROY, float(h))
+        matlab.clear_mex()
