@@ -55,7 +55,7 @@ def test_mex_path_matches_golden(matlab, name):
                 it.v_ref, list(it.obstacles), [list(r) for r in it.dynamic_obstacle_area] or [],
                 it.predicted_lanelet_boundary[0], it.predicted_lanelet_boundary[1], float(batch.checker),
                 float(batch.dt_seconds))
-            assert exh == bool(exp.is_exhausted[i]) and int(n_exp) == exp.n_expanded[i]
+            assert exh == bool(exp.is_exhausted[i]) and int(np.asarray(n_exp).reshape(-1)[0]) == exp.n_expanded[i]
             if not exh:
                 assert trims.reshape(-1).astype(int).tolist() == exp.trims[i].tolist()
                 assert np.array_equal(ypred.T.view(np.uint64), exp.y_predicted[i].view(np.uint64))
