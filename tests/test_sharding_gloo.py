@@ -1,0 +1,96 @@
+"""N>1 host logic on CPU: world_size-2 gloo (one process per would-be GPU)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from oracle import oracle_py
+    from pdmpc_b200 import sharding
+    from helpers import road_records
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        # (1) scenario sharding: disjoint cover, no collective on the data path
+        mine = sharding.shard_block_cyclic(7, rank, world)
+        # (2) every rank plans ITS searches only; results must equal the single-process run
+        mpa, batch = road_records("single_speed", 3)
+        idx = sharding.shard_block_cyclic(batch.n, rank, world, block=4)
+        res = oracle_py.plan_batch(mpa, batch.select(idx))      # CPU stand-in for the per-rank planner
+        counters = sharding.gather_counters([idx.size, int(res.n_pops.sum())])
+        # (3) permutation choice: 5 permutations over 2 ranks, 6 vehicles in 2 sub-graphs
+        rng = np.random.default_rng(7)
+        cost = rng.random((5, 6))
+        cost[3] = cost[1]                                        # exact tie between permutations 1 and 3
+        cost[:, 3:] += 1e-10 * rng.random((5, 3))                # differences below the 1e-8 rounding
+        bel = np.array([1, 1, 1, 2, 2, 2])
+        pid = sharding.shard_block_cyclic(5, rank, world)
+        chosen, sc = sharding.choose_permutation(cost[pid], pid, 5, bel)
+        plans = np.arange(5 * 6 * 3, dtype=np.float64).reshape(5, 6, 3)
+        win = sharding.gather_winner_plans(plans[pid], pid, 5, chosen, bel)
+        q.put((rank, mine.tolist(), idx.tolist(), res.pop_hash.tolist(), counters.tolist(), chosen.tolist(),
+               sc.tolist(), win.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharding_and_permutation_choice():
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import oracle_py
+    from pdmpc_b200 import sharding
+    from helpers import road_records
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    (r0, mine0, idx0, h0, c0, ch0, sc0, w0), (r1, mine1, idx1, h1, c1, ch1, sc1, w1) = out
+    assert sorted(mine0 + mine1) == list(range(7)) and not set(mine0) & set(mine1)
+    mpa, batch = road_records("single_speed", 3)
+    ref = oracle_py.plan_batch(mpa, batch)
+    assert sorted(idx0 + idx1) == list(range(batch.n))
+    assert h0 == ref.pop_hash[idx0].tolist() and h1 == ref.pop_hash[idx1].tolist()
+    assert c0 == c1 and sum(row[0] for row in c0) == batch.n and sum(row[1] for row in c0) == int(ref.n_pops.sum())
+    # both ranks reach the same decision, equal to the single-process computation
+    rng = np.random.default_rng(7)
+    cost = rng.random((5, 6))
+    cost[3] = cost[1]
+    cost[:, 3:] += 1e-10 * rng.random((5, 3))
+    bel = np.array([1, 1, 1, 2, 2, 2])
+    chosen, sc = sharding.choose_permutation(cost, np.arange(5), 5, bel)
+    assert ch0 == ch1 == chosen.tolist() and sc0 == sc1 == sc.tolist()
+    plans = np.arange(5 * 6 * 3, dtype=np.float64).reshape(5, 6, 3)
+    assert w0 == w1 == sharding.gather_winner_plans(plans, np.arange(5), 5, chosen, bel).tolist()
+
+
+def test_first_minimum_and_rounding_rule():
+    from pdmpc_b200 import sharding
+    # PrioritizedExplorativeController.m:153-154: ties after round(., 8) go to the FIRST permutation
+    cost = np.array([[0.5, 0.2], [0.5 - 4e-9, 0.2], [0.4, 0.1 + 1e-12], [0.4 + 3e-9, 0.1]])
+    chosen, sc = sharding.choose_permutation(cost, np.arange(4), 4, np.array([1, 2]))
+    assert chosen.tolist() == [2, 2]
+    assert sharding.matlab_round(np.array([0.123456785, -0.123456785, 2.5e-9]), 8).tolist() == \
+        pytest.approx([0.12345679, -0.12345679, 0.0], abs=1e-15)
+    with pytest.raises(ValueError):
+        sharding.choose_permutation(cost[:2], [0, 1], 4, np.array([1, 2]))
