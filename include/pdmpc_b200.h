@@ -163,6 +163,8 @@ typedef struct pdmpc_stats {
     int64_t total_nodes;
     int64_t total_obstacle_cols; /* sum over pops of (V_k + L) columns tested */
     int32_t kernel_launches;
+    int32_t handed_over;     /* shape 3: searches the threads handed to the warp-per-search stage */
+    double lanes_ms;         /* shape 3: CUDA-event time of the first (lane-per-search) launch alone */
 } pdmpc_stats;
 
 /* Create a planner bound to CUDA device `device_id`.  Fails (PDMPC_ERR_CUDA)
@@ -180,8 +182,15 @@ int pdmpc_set_node_capacity(pdmpc_handle *h, int32_t max_nodes_per_search);
 /* Launch shape of the search kernel: 0 = choose from the batch size (default),
  * 1 = latency (one warp-CTA per search slot, tables through L1/L2), 2 = throughput
  * (one 16-warp CTA per SM, MPA tables TMA-staged in shared memory; falls back to 1
- * when the tables do not fit).  Results do not depend on it. */
+ * when the tables do not fit), 3 = lanes (one THREAD per search for large InterX
+ * batches; searches that outgrow a thread's slot or pop budget are re-run by shape 1
+ * in a second launch; falls back to 2 for SAT batches).  Results do not depend on it. */
 int pdmpc_set_variant(pdmpc_handle *h, int32_t variant);
+
+/* Shape 3 only: nodes per thread slot (0 = default 4096) and the number of pops after
+ * which a thread hands its search over to the warp-per-search kernel (0 = default 1024).
+ * Tuning knobs: results do not depend on them. */
+int pdmpc_set_lane_limits(pdmpc_handle *h, int32_t nodes_per_thread, int32_t pop_limit);
 
 /* Stage the MPA tables in HBM (once per MPA; cached in the handle). */
 int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *mpa);

@@ -30,7 +30,7 @@ PDMPC_ERR_ALLOC = 5
 
 EXPORTED_SYMBOLS = (
     "pdmpc_create", "pdmpc_destroy", "pdmpc_last_error", "pdmpc_abi_version",
-    "pdmpc_set_node_capacity", "pdmpc_set_variant", "pdmpc_host_alloc", "pdmpc_host_free",
+    "pdmpc_set_node_capacity", "pdmpc_set_variant", "pdmpc_set_lane_limits", "pdmpc_host_alloc", "pdmpc_host_free",
     "pdmpc_trace_staged", "pdmpc_upload_mpa", "pdmpc_plan_batch", "pdmpc_stage_batch",
     "pdmpc_run_staged", "pdmpc_sync", "pdmpc_fetch_staged", "pdmpc_get_stats", "pdmpc_stream",
 )
@@ -74,7 +74,7 @@ class Stats(C.Structure):
         ("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("total_pops", C.c_int64),
         ("total_nodes", C.c_int64), ("total_obstacle_cols", C.c_int64),
-        ("kernel_launches", C.c_int32),
+        ("kernel_launches", C.c_int32), ("handed_over", C.c_int32), ("lanes_ms", C.c_double),
     ]
 
 
@@ -154,6 +154,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.pdmpc_set_node_capacity.restype = C.c_int
     lib.pdmpc_set_variant.argtypes = [H, C.c_int32]
     lib.pdmpc_set_variant.restype = C.c_int
+    lib.pdmpc_set_lane_limits.argtypes = [H, C.c_int32, C.c_int32]
+    lib.pdmpc_set_lane_limits.restype = C.c_int
     lib.pdmpc_trace_staged.argtypes = [H, C.c_int32, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64)]
     lib.pdmpc_trace_staged.restype = C.c_int
     lib.pdmpc_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
@@ -220,8 +222,12 @@ class Planner:
         self._check(self.lib.pdmpc_set_node_capacity(self.h, int(n)))
 
     def set_variant(self, variant: int):
-        """0 = auto, 1 = latency shape, 2 = throughput shape (pdmpc_set_variant)."""
+        """0 = auto, 1 = latency shape, 2 = throughput shape, 3 = lanes (pdmpc_set_variant)."""
         self._check(self.lib.pdmpc_set_variant(self.h, int(variant)))
+
+    def set_lane_limits(self, nodes_per_thread: int = 0, pop_limit: int = 0):
+        """Shape 3 tuning knobs (pdmpc_set_lane_limits); results do not depend on them."""
+        self._check(self.lib.pdmpc_set_lane_limits(self.h, int(nodes_per_thread), int(pop_limit)))
 
     def trace(self, search: int, cap: int = 1 << 20) -> np.ndarray:
         """Node ids popped by staged search `search`, in order (pdmpc_trace_staged)."""

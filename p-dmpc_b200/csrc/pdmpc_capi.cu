@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "pdmpc_kernels.cuh"
+#include "pdmpc_lanes.cuh"
 
 using namespace pdmpc;
 
@@ -30,6 +31,13 @@ constexpr int kWarpsThroughput = 16;
 #define KERNEL_THR search_kernel<kHeapSmem, kPts, kWarpsThroughput, true>
 using WarpSmem = TileSmem<kHeapSmem, kPts>;
 constexpr size_t kSmemLimit = 227 * 1024;
+// "lanes" = one THREAD per search (pdmpc_lanes.cuh), one CTA per SM; searches that outgrow a
+// thread's slot or pop budget are re-run by the warp-per-search kernel in a second launch
+constexpr int kLaneThreads = 256;
+#define KERNEL_LANES_SMEM search_lanes_kernel<kLaneThreads, true>
+#define KERNEL_LANES_GMEM search_lanes_kernel<kLaneThreads, false>
+constexpr int kLaneNodeCapDefault = 4096;
+constexpr int kLanePopLimitDefault = 1024;
 
 struct DBuf {
     void *p = nullptr;
@@ -60,15 +68,19 @@ struct pdmpc_handle {
     int lat_ctas_per_sm = 0;          // occupancy of the latency shape
     bool thr_ok = false;              // throughput shape usable with the uploaded MPA (tables fit in smem)
     size_t thr_smem = 0;
-    int variant_mode = 0;             // 0 = auto, 1 = latency, 2 = throughput
+    int variant_mode = 0;             // 0 = auto, 1 = latency, 2 = throughput, 3 = lanes (+ warp second stage)
+    bool lanes_ok = false;            // every maneuver area has <= 7 points
+    bool lanes_smem_ok = false;       // MPA tables fit in shared memory next to nothing else
+    size_t lanes_smem = 0;
+    int lane_node_cap = kLaneNodeCapDefault, lane_pop_limit = kLanePopLimitDefault;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[6] = {};   // 0/1 h2d, 2/3 kernel, 4/5 d2h
+    cudaEvent_t ev[7] = {};   // 0/1 h2d, 2/3 kernel, 4/5 d2h, 6 end of the lane-per-search launch
     std::string err;
 
     // MPA
     bool has_mpa = false;
     MpaDev mpa{};
-    DBuf m_succ_ptr, m_succ_te, m_edge_d, m_npts, m_ax, m_ay;
+    DBuf m_succ_ptr, m_succ_te, m_edge_d, m_npts, m_ax, m_ay, m_apx, m_apy;
     int full_tree_nodes = 0;
     int user_node_cap = 0;
 
@@ -77,7 +89,7 @@ struct pdmpc_handle {
     BatchDev batch{};
     int n_polys = 0, n_verts = 0, n_lane = 0;
     DBuf b_x0, b_y0, b_yaw0, b_trim0, b_refx, b_refy, b_vref, b_slot, b_poly, b_vx, b_vy, b_plx, b_ply,
-        b_lane, b_lx, b_ly, b_llx, b_lly, b_order;
+        b_lane, b_lx, b_ly, b_llx, b_lly, b_order, b_plxy, b_llxy, b_rng;
 
     // outputs
     OutDev out{};
@@ -88,12 +100,17 @@ struct pdmpc_handle {
     ArenaDev arena{};
     DBuf a_a, a_b, a_cs, a_heap;
     int arena_slots = 0;
+    // lane-per-search arena (small slots, one per thread) and the hand-over list
+    ArenaDev larena{};
+    DBuf la_a, la_b, la_cs, la_heap, ov_count, ov_list, work_counter2;
+    int larena_slots = 0;
 
     // trace (debug / parity tests)
     DBuf t_ids, t_n;
 
     pdmpc_stats stats{};
-    bool timing_pending_h2d = false, timing_pending_kernel = false, timing_pending_d2h = false;
+    bool timing_pending_h2d = false, timing_pending_kernel = false, timing_pending_d2h = false,
+         timing_pending_lanes = false;
 };
 
 static thread_local std::string g_create_error;
@@ -159,7 +176,9 @@ int pdmpc_destroy(pdmpc_handle *h) {
     if (!h) return PDMPC_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DBuf *bufs[] = {&h->m_succ_ptr, &h->m_succ_te, &h->m_edge_d, &h->m_npts, &h->m_ax, &h->m_ay, &h->b_order, &h->b_x0, &h->b_y0, &h->b_yaw0, &h->b_trim0,
+    DBuf *bufs[] = {&h->m_succ_ptr, &h->m_succ_te, &h->m_edge_d, &h->m_npts, &h->m_ax, &h->m_ay, &h->b_order,
+                    &h->m_apx, &h->m_apy, &h->b_plxy, &h->b_llxy, &h->b_rng, &h->la_a, &h->la_b, &h->la_cs,
+                    &h->la_heap, &h->ov_count, &h->ov_list, &h->work_counter2, &h->b_x0, &h->b_y0, &h->b_yaw0, &h->b_trim0,
                     &h->b_refx, &h->b_refy, &h->b_vref, &h->b_slot, &h->b_poly, &h->b_vx, &h->b_vy,
                     &h->b_plx, &h->b_ply, &h->b_lane, &h->b_lx, &h->b_ly, &h->b_llx, &h->b_lly,
                     &h->o_status, &h->o_exh, &h->o_nexp, &h->o_npops, &h->o_hash, &h->o_trims, &h->o_path,
@@ -186,8 +205,18 @@ int pdmpc_host_free(void *p) {
 
 int pdmpc_set_variant(pdmpc_handle *h, int32_t variant) {
     if (!h) return PDMPC_ERR_BAD_INPUT;
-    if (variant < 0 || variant > 2) return fail(h, PDMPC_ERR_BAD_INPUT, "variant must be 0 (auto), 1 (latency) or 2 (throughput)");
+    if (variant < 0 || variant > 3)
+        return fail(h, PDMPC_ERR_BAD_INPUT, "variant must be 0 (auto), 1 (latency), 2 (throughput) or 3 (lanes)");
     h->variant_mode = variant;
+    return PDMPC_OK;
+}
+
+int pdmpc_set_lane_limits(pdmpc_handle *h, int32_t node_cap, int32_t pop_limit) {
+    if (!h) return PDMPC_ERR_BAD_INPUT;
+    if (node_cap < 0 || pop_limit < 0 || (node_cap != 0 && node_cap < 64))
+        return fail(h, PDMPC_ERR_BAD_INPUT, "lane limits: node_cap must be 0 (default) or >= 64, pop_limit >= 0");
+    h->lane_node_cap = node_cap ? (node_cap + 1) / 2 * 2 : kLaneNodeCapDefault;
+    h->lane_pop_limit = pop_limit ? pop_limit : kLanePopLimitDefault;
     return PDMPC_OK;
 }
 
@@ -303,6 +332,20 @@ int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *d) {
     UP(h, h->m_npts, npts.data(), npts.size());
     UP(h, h->m_ax, ax.data(), ax.size());
     UP(h, h->m_ay, ay.data(), ay.size());
+    // lane-per-search kernel: areas padded by repeating the last point (zero-length edges
+    // never satisfy InterX's strict inequalities), so every shape is a 7-point polyline
+    std::vector<double> apx(ax), apy(ay);
+    bool lanes_ok = true;
+    for (int e = 0; e < nE * 3; ++e) {
+        const int np = d->area_npts[e];
+        if (np > kLanePts) lanes_ok = false;
+        for (int i = np; i < PDMPC_AREA_STRIDE; ++i) {
+            apx[(size_t)e * PDMPC_AREA_STRIDE + i] = apx[(size_t)e * PDMPC_AREA_STRIDE + np - 1];
+            apy[(size_t)e * PDMPC_AREA_STRIDE + i] = apy[(size_t)e * PDMPC_AREA_STRIDE + np - 1];
+        }
+    }
+    UP(h, h->m_apx, apx.data(), apx.size());
+    UP(h, h->m_apy, apy.data(), apy.size());
     CU_TRY(h, cudaStreamSynchronize(h->stream));   // host vectors go out of scope
     h->stats.h2d_bytes = keep;
     MpaDev &m = h->mpa;
@@ -323,6 +366,12 @@ int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *d) {
     h->thr_ok = h->thr_smem <= kSmemLimit;
     if (h->thr_ok)
         CU_TRY(h, cudaFuncSetAttribute(KERNEL_THR, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->thr_smem));
+    h->lanes_ok = lanes_ok;
+    h->lanes_smem = 16 + (size_t)m.table_bytes;
+    h->lanes_smem_ok = h->lanes_smem <= kSmemLimit;
+    if (h->lanes_smem_ok)
+        CU_TRY(h, cudaFuncSetAttribute(KERNEL_LANES_SMEM, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)h->lanes_smem));
     h->has_mpa = true;
     h->staged = false;
     return PDMPC_OK;
@@ -440,6 +489,8 @@ int pdmpc_stage_batch(pdmpc_handle *h, const pdmpc_batch_in *in) {
     b.vert_x = h->b_vx.as<double>(); b.vert_y = h->b_vy.as<double>();
     b.lane_ptr = h->b_lane.as<int>(); b.lane_x = h->b_lx.as<double>(); b.lane_y = h->b_ly.as<double>();
     b.pl_x = b.pl_y = b.ll_x = b.ll_y = nullptr;
+    b.pl_xy = b.ll_xy = nullptr;
+    b.rng = nullptr;
     // work order: searches with the most obstacle polygons first (they are the ones most
     // likely to run long / exhaust), so the tail of the batch is made of short searches
     b.order = nullptr;
@@ -476,6 +527,25 @@ int pdmpc_stage_batch(pdmpc_handle *h, const pdmpc_batch_in *in) {
                 2 * n, b.lane_ptr, b.lane_x, b.lane_y, h->b_llx.as<double>(), h->b_lly.as<double>());
             h->stats.kernel_launches++;
         }
+        b.pl_xy = b.ll_xy = nullptr;
+        b.rng = nullptr;
+        if (h->lanes_ok && n) {
+            CU_TRY(h, h->b_plxy.reserve(((size_t)nv + np + 1) * sizeof(double2)));
+            CU_TRY(h, h->b_llxy.reserve(((size_t)nl + 2 * n + 1) * sizeof(double2)));
+            CU_TRY(h, h->b_rng.reserve((size_t)n * (Hp + 2) * sizeof(int)));
+            if (np) {
+                build_polyline_xy_kernel<<<(np + 127) / 128, 128, 0, h->stream>>>(
+                    np, b.poly_ptr, b.vert_x, b.vert_y, h->b_plxy.as<double2>());
+                h->stats.kernel_launches++;
+            }
+            build_polyline_xy_kernel<<<(2 * n + 127) / 128, 128, 0, h->stream>>>(
+                2 * n, b.lane_ptr, b.lane_x, b.lane_y, h->b_llxy.as<double2>());
+            build_ranges_kernel<<<(n * (Hp + 2) + 127) / 128, 128, 0, h->stream>>>(
+                n, Hp, b.slot_ptr, b.poly_ptr, h->b_rng.as<int>());
+            h->stats.kernel_launches += 2;
+            b.pl_xy = h->b_plxy.as<double2>(); b.ll_xy = h->b_llxy.as<double2>();
+            b.rng = h->b_rng.as<int>();
+        }
         CU_TRY(h, cudaGetLastError());
         b.pl_x = h->b_plx.as<double>(); b.pl_y = h->b_ply.as<double>();
         b.ll_x = h->b_llx.as<double>(); b.ll_y = h->b_lly.as<double>();
@@ -510,30 +580,93 @@ static int ensure_arena(pdmpc_handle *h, int slots) {
     return PDMPC_OK;
 }
 
+static int ensure_lane_arena(pdmpc_handle *h, int slots) {
+    const int cap = h->lane_node_cap;
+    if (slots <= h->larena_slots && cap == h->larena.cap) return PDMPC_OK;
+    slots = std::max(slots, h->larena_slots);
+    const size_t tot = (size_t)slots * cap;
+    CU_TRY(h, h->la_a.reserve(tot * sizeof(NodeA)));
+    CU_TRY(h, h->la_b.reserve(tot * sizeof(NodeB)));
+    CU_TRY(h, h->la_cs.reserve(tot * sizeof(NodeCS)));
+    CU_TRY(h, h->la_heap.reserve(tot * sizeof(HEnt)));
+    h->larena.a = h->la_a.as<NodeA>();
+    h->larena.b = h->la_b.as<NodeB>();
+    h->larena.cs = h->la_cs.as<NodeCS>();
+    h->larena.heap = h->la_heap.as<HEnt>();
+    h->larena.cap = cap;
+    h->larena_slots = slots;
+    return PDMPC_OK;
+}
+
+// Launches the search of the staged batch.  Shapes (results are identical for all):
+//   1 latency    one warp-CTA per search slot, MPA tables through L1/L2
+//   2 throughput one 16-warp CTA per SM, tables TMA-staged in shared memory
+//   3 lanes      one THREAD per search (pdmpc_lanes.cuh), then shape 1 over the searches the
+//                threads handed over (count known only on the device)
 static int launch_search(pdmpc_handle *h, const TraceDev &tr) {
     const int n = h->batch.n;
     CU_TRY(h, cudaSetDevice(h->device));
     CU_TRY(h, cudaMemsetAsync(h->o_counters.p, 0, 16 * sizeof(unsigned long long), h->stream));
     CU_TRY(h, cudaMemsetAsync(h->work_counter.p, 0, sizeof(unsigned), h->stream));
     if (n == 0) return PDMPC_OK;
-    // shape selection: a batch that cannot give every SM several searches runs one warp per
-    // CTA (latency); a large batch runs one 16-warp CTA per SM with smem-resident tables
+    const bool lanes_possible = h->lanes_ok && h->batch.checker == PDMPC_CHECKER_INTERX && h->batch.rng;
     int variant = h->variant_mode;
-    if (variant == 0) variant = (h->thr_ok && n >= 4 * h->num_sms) ? 2 : 1;
+    if (tr.search >= 0) variant = 1;   // pop traces come from the warp kernel
+    if (variant == 0) {
+        // a batch that gives every SM a few hundred searches is throughput work: one thread per
+        // search; below that the warp-per-search shapes finish sooner
+        if (lanes_possible && n >= 32 * h->num_sms) variant = 3;
+        else variant = (h->thr_ok && n >= 4 * h->num_sms) ? 2 : 1;
+    }
+    if (variant == 3 && !lanes_possible) variant = 2;
     if (variant == 2 && !h->thr_ok) variant = 1;
     unsigned *wc = h->work_counter.as<unsigned>();
-    if (variant == 2) {
+    h->timing_pending_lanes = false;
+    h->stats.lanes_ms = 0.0;
+    h->stats.handed_over = 0;
+    if (variant == 3) {
+        const int grid = std::min((n + kLaneThreads - 1) / kLaneThreads, h->num_sms);
+        int rc = ensure_lane_arena(h, grid * kLaneThreads);
+        if (rc != PDMPC_OK) return rc;
+        const int grid2 = std::min(n, h->num_sms * h->lat_ctas_per_sm);
+        rc = ensure_arena(h, grid2);
+        if (rc != PDMPC_OK) return rc;
+        CU_TRY(h, h->ov_count.reserve(sizeof(unsigned)));
+        CU_TRY(h, h->ov_list.reserve((size_t)n * sizeof(int)));
+        CU_TRY(h, h->work_counter2.reserve(sizeof(unsigned)));
+        CU_TRY(h, cudaMemsetAsync(h->ov_count.p, 0, sizeof(unsigned), h->stream));
+        CU_TRY(h, cudaMemsetAsync(h->work_counter2.p, 0, sizeof(unsigned), h->stream));
+        LaneLimits lim{h->lane_pop_limit, h->ov_count.as<unsigned>(), h->ov_list.as<int>()};
+        CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
+        if (h->lanes_smem_ok)
+            KERNEL_LANES_SMEM<<<grid, kLaneThreads, h->lanes_smem, h->stream>>>(
+                h->mpa, h->m_apx.as<double>(), h->m_apy.as<double>(), h->batch, h->out, h->larena, wc, lim);
+        else
+            KERNEL_LANES_GMEM<<<grid, kLaneThreads, 0, h->stream>>>(
+                h->mpa, h->m_apx.as<double>(), h->m_apy.as<double>(), h->batch, h->out, h->larena, wc, lim);
+        CU_TRY(h, cudaGetLastError());
+        CU_TRY(h, cudaEventRecord(h->ev[6], h->stream));
+        h->timing_pending_lanes = true;
+        // second stage: the handed-over searches, from scratch, with full-tree arenas
+        BatchDev b2 = h->batch;
+        b2.order = h->ov_list.as<int>();
+        KERNEL_LAT<<<grid2, kWarp, sizeof(WarpSmem), h->stream>>>(h->mpa, b2, h->out, h->arena,
+                                                                 h->work_counter2.as<unsigned>(), tr,
+                                                                 h->ov_count.as<unsigned>());
+        h->stats.kernel_launches++;
+    } else if (variant == 2) {
         const int grid = std::min((n + kWarpsThroughput - 1) / kWarpsThroughput, h->num_sms);
         int rc = ensure_arena(h, grid * kWarpsThroughput);
         if (rc != PDMPC_OK) return rc;
         CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
-        KERNEL_THR<<<grid, kWarpsThroughput * kWarp, h->thr_smem, h->stream>>>(h->mpa, h->batch, h->out, h->arena, wc, tr);
+        KERNEL_THR<<<grid, kWarpsThroughput * kWarp, h->thr_smem, h->stream>>>(h->mpa, h->batch, h->out, h->arena, wc,
+                                                                             tr, nullptr);
     } else {
         const int grid = std::min(n, h->num_sms * h->lat_ctas_per_sm);
         int rc = ensure_arena(h, grid);
         if (rc != PDMPC_OK) return rc;
         CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
-        KERNEL_LAT<<<grid, kWarp, sizeof(WarpSmem), h->stream>>>(h->mpa, h->batch, h->out, h->arena, wc, tr);
+        KERNEL_LAT<<<grid, kWarp, sizeof(WarpSmem), h->stream>>>(h->mpa, h->batch, h->out, h->arena, wc, tr, nullptr);
     }
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
@@ -642,6 +775,12 @@ int pdmpc_get_stats(pdmpc_handle *h, pdmpc_stats *out) {
     if (h->timing_pending_h2d && cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->stats.h2d_ms = ms;
     if (h->timing_pending_kernel && cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) h->stats.kernel_ms = ms;
     if (h->timing_pending_d2h && cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]) == cudaSuccess) h->stats.d2h_ms = ms;
+    if (h->timing_pending_lanes) {
+        if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[6]) == cudaSuccess) h->stats.lanes_ms = ms;
+        unsigned ov = 0;
+        if (cudaMemcpy(&ov, h->ov_count.p, sizeof(ov), cudaMemcpyDeviceToHost) == cudaSuccess)
+            h->stats.handed_over = (int32_t)ov;
+    }
     *out = h->stats;
     return PDMPC_OK;
 }

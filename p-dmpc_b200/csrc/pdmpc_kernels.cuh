@@ -100,6 +100,10 @@ struct BatchDev {
     const int *lane_ptr;
     const double *lane_x, *lane_y;
     const double *ll_x, *ll_y;
+    // the same polylines as (x, y) pairs and the per-search polyline offsets of obstacle
+    // slots 0..Hp+1 (lane-per-search kernel, pdmpc_lanes.cuh)
+    const double2 *pl_xy, *ll_xy;
+    const int *rng;
 };
 
 struct OutDev {
@@ -593,8 +597,12 @@ struct __align__(16) TileSmem {
 //              (cp.async.bulk + mbarrier), each warp still runs its own searches.
 template <int HS, int SP, int WARPS, bool SMEM_TABLES>
 __global__ void __launch_bounds__(WARPS *kWarp) search_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar,
-                                                              unsigned *work_counter, TraceDev tr) {
+                                                              unsigned *work_counter, TraceDev tr,
+                                                              const unsigned *n_work_dev) {
     constexpr int TILE = kWarp;
+    // number of work items: the whole batch, or (second stage after the lane-per-search
+    // kernel) the length of the hand-over list b.order, known only on the device
+    const unsigned n_work = n_work_dev ? *n_work_dev : (unsigned)b.n;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Tables tb;
     unsigned char *warp_base = smem_raw;
@@ -733,7 +741,7 @@ __global__ void __launch_bounds__(WARPS *kWarp) search_kernel(MpaDev m, BatchDev
             unsigned si_u = 0;
             if (t.lane == 0) si_u = atomicAdd(work_counter, 1u);
             si_u = t.shfl(si_u, 0);
-            if (si_u >= (unsigned)b.n) break;
+            if (si_u >= n_work) break;
             si = b.order ? __ldg(b.order + si_u) : (int)si_u;
             // ---- per-search set-up ------------------------------------------------
             t.sync();

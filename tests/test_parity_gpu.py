@@ -17,7 +17,7 @@ from helpers import GOLDEN_CASES, circle_records, load_golden, rect, road_record
 pytestmark = pytest.mark.gpu
 
 
-VARIANTS = (1, 2)   # latency / throughput launch shapes: both must give identical results
+VARIANTS = (1, 2, 3)   # latency / throughput / lane-per-search launch shapes: identical results required
 
 
 def check(planner, mpa, batch, variants=VARIANTS, **kw):
@@ -90,6 +90,28 @@ def test_pop_trace_identical(planner):
                 assert np.array_equal(got, want), (tile, si)
     finally:
         planner.set_variant(0)
+
+
+@pytest.mark.parametrize("nodes,pops", [(64, 0), (0, 6), (128, 40), (0, 0)])
+def test_lane_shape_hand_over(planner, nodes, pops):
+    """Shape 3: threads hand searches that outgrow their slot / pop budget over to the
+    warp-per-search kernel (second launch).  Any split must give the oracle's results."""
+    mpa, batch = road_records("triple_speed", 8)
+    planner.set_lane_limits(nodes, pops)
+    try:
+        info, dev, ref = check(planner, mpa, batch, variants=(3,))
+        assert info["n"] == batch.n
+        st = planner.stats()
+        assert st.total_pops == int(ref.n_pops.sum()) and st.total_nodes == int(ref.n_expanded.sum())
+    finally:
+        planner.set_lane_limits(0, 0)
+
+
+def test_lane_shape_single_speed_and_realistic(planner):
+    """5-/6-/7-point maneuver areas all run the padded 6-edge InterX of shape 3."""
+    for mpa_type, kw in (("single_speed", {}), ("realistic", dict(amount=10, seed=5))):
+        mpa, batch = road_records(mpa_type, 3, **kw)
+        check(planner, mpa, batch, variants=(3,))
 
 
 def test_empty_batch(planner):

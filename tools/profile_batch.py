@@ -28,12 +28,16 @@ def main():
     p = capi.Planner(0)
     p.upload_mpa(mpa)
     p.set_variant(tile)
+    if os.environ.get('PDMPC_LANE_LIMITS'):
+        nodes, pops = (int(x) for x in os.environ['PDMPC_LANE_LIMITS'].split(','))
+        p.set_lane_limits(nodes, pops)
     p.stage(b)
     for i in range(runs):
         p.run_staged()
         p.sync()
         st = p.stats()
-        print(f"variant {tile} run {i}: {b.n} searches kernel {st.kernel_ms:.3f} ms -> {b.n / st.kernel_ms * 1e3:.0f} plans/s")
+        print(f"variant {tile} run {i}: {b.n} searches kernel {st.kernel_ms:.3f} ms -> {b.n / st.kernel_ms * 1e3:.0f} plans/s"
+              f" (lane stage {st.lanes_ms:.3f} ms, handed over {st.handed_over})")
     r = p.fetch()
     st = p.stats()
     print("pops", st.total_pops, "nodes", st.total_nodes, "cols", st.total_obstacle_cols,
