@@ -43,8 +43,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scenarios", type=int, default=int(os.environ.get("PDMPC_BENCH_SCENARIOS", "64")),
+    ap.add_argument("--scenarios", type=int, default=int(os.environ.get("PDMPC_BENCH_SCENARIOS", "256")),
                     help="scenarios per GPU (weak scaling)")
+    ap.add_argument("--gen-workers", type=int, default=0,
+                    help="processes that roll the scenarios out (0 = auto: host cores / ranks, at most 12)")
     ap.add_argument("--sim-steps", type=int, default=35)
     ap.add_argument("--vehicles", type=int, default=20)
     ap.add_argument("--mpa", default="triple_speed")
@@ -112,24 +114,55 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_records(planner, mpa, n_scen: int, seed0: int, vehicles: int, sim_steps: int, cache: str = ""):
-    """Closed-loop roll-out of n_scen road-network scenarios with the GPU planner (untimed).
-    Returns (flat batch of every search record, [(step, level, n_searches)] of the first
-    scenario, whose records come first in the batch).  Cached under build/ (git-ignored) so
-    that profiler runs of the same command skip the generation launches."""
-    from pdmpc_b200 import scenario
+def _roll_chunk(job):
+    """Worker process: roll a chunk of scenarios out closed loop with its OWN GPU planner."""
+    dev, mpa_type, vehicles, sim_steps, seeds, out_path = job
+    from pdmpc_b200 import capi, scenario
+    from pdmpc_b200.mpa import get_mpa
+    from pdmpc_b200.records import SearchBatch
+    mpa = get_mpa(mpa_type, non_convex=True)
+    planner = capi.Planner(dev)
+    planner.upload_mpa(mpa)
+    batches, levels = [], []
+    for s in seeds:
+        sc = scenario.commonroad_scenario(mpa, vehicles, seed=s)
+        recs = scenario.ScenarioRunner(sc, planner.plan_batch).run(sim_steps)
+        batches.extend(r.batch for r in recs)
+        if not levels:
+            levels = [(r.step, r.level, r.batch.n) for r in recs]
+    planner.close()
+    SearchBatch.concat(batches).save(out_path)
+    return out_path, levels
+
+
+def build_records(dev, mpa_type, n_scen: int, seed0: int, vehicles: int, sim_steps: int, cache: str = "",
+                  workers: int = 1):
+    """Closed-loop roll-out of n_scen road-network scenarios with the GPU planner (untimed),
+    spread over `workers` processes (the scenario logic around the planner is host-side
+    Python).  Returns (flat batch of every search record, [(step, level, n_searches)] of the
+    first scenario, whose records come first in the batch).  Cached under build/
+    (git-ignored) so that profiler runs of the same command skip the generation launches."""
     from pdmpc_b200.records import SearchBatch
     if cache and os.path.exists(cache) and os.path.exists(cache + ".levels.npy"):
         return SearchBatch.load(cache), np.load(cache + ".levels.npy")
-    batches, levels = [], []
-    for s in range(n_scen):
-        sc = scenario.commonroad_scenario(mpa, vehicles, seed=seed0 + s)
-        runner = scenario.ScenarioRunner(sc, planner.plan_batch)
-        recs = runner.run(sim_steps)
-        batches.extend(r.batch for r in recs)
-        if s == 0:
-            levels = np.array([(r.step, r.level, r.batch.n) for r in recs], dtype=np.int64)
-    batch = SearchBatch.concat(batches)
+    import multiprocessing as mp
+    import tempfile
+    workers = max(1, min(workers, n_scen))
+    tmp = tempfile.mkdtemp(prefix="pdmpc_gen_")
+    seeds = [seed0 + s for s in range(n_scen)]
+    per = (n_scen + workers - 1) // workers
+    jobs = [(dev, mpa_type, vehicles, sim_steps, seeds[i * per:(i + 1) * per], os.path.join(tmp, f"c{i}.npz"))
+            for i in range(workers) if seeds[i * per:(i + 1) * per]]
+    if len(jobs) == 1:
+        results = [_roll_chunk(jobs[0])]
+    else:
+        with mp.get_context("spawn").Pool(len(jobs)) as pool:
+            results = pool.map(_roll_chunk, jobs)
+    batch = SearchBatch.concat([SearchBatch.load(pth) for pth, _ in results])
+    levels = np.array(results[0][1], dtype=np.int64)
+    for pth, _ in results:
+        os.remove(pth)
+    os.rmdir(tmp)
     if cache:
         os.makedirs(os.path.dirname(cache), exist_ok=True)
         batch.save(cache)
@@ -230,8 +263,9 @@ def main():
     t_gen = time.perf_counter()
     cache = os.path.join(ROOT, "build", f"bench_{args.mpa}_{args.vehicles}v_{args.scenarios}s_{args.sim_steps}t_seed"
                                         f"{1 + rank * args.scenarios}.npz")
-    batch, step_recs = build_records(planner, mpa, args.scenarios, 1 + rank * args.scenarios,
-                                     args.vehicles, args.sim_steps, "" if args.no_cache else cache)
+    workers = args.gen_workers or max(1, min(12, (os.cpu_count() or 1) // max(world, 1)))
+    batch, step_recs = build_records(dev, args.mpa, args.scenarios, 1 + rank * args.scenarios,
+                                     args.vehicles, args.sim_steps, "" if args.no_cache else cache, workers)
     t_gen = time.perf_counter() - t_gen
     n = batch.n
 
@@ -358,6 +392,15 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        # DRAM traffic of the dominant kernel: one `ncu --set full` capture of this same launch
+        # (same records, same shape), summarised under profiles/; null when the workload differs
+        traffic = None
+        try:
+            cap = json.load(open(os.path.join(ROOT, "profiles", "search_kernel_traffic.json")))
+            if int(cap.get("searches", -1)) == n and cap.get("mpa") == args.mpa:
+                traffic = float(cap["dram_bytes_read"]) + float(cap["dram_bytes_write"])
+        except Exception:
+            pass
         alg_bytes = algorithmic_bytes(batch, stats, Hp)
         achieved = alg_bytes / (ms_step * 1e-3) / 1e9
         f64 = fp64_ops(batch, stats, Hp)
@@ -374,10 +417,10 @@ def main():
             "e2e": {"value": e2e_val, "unit": "plans/s", "h2d_bytes_per_step": int(st2.h2d_bytes),
                     "d2h_bytes_per_step": int(st2.d2h_bytes), "steps": e2e_steps,
                     "h2d_ms": st2.h2d_ms, "kernel_ms": st2.kernel_ms, "d2h_ms": st2.d2h_ms},
-            "gpu_launches": int(args.steps * 1),
+            "gpu_launches": int(args.steps * 1),   # one persistent search kernel per timed step (staged path)
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None,
+                         "frac": achieved / hbm_peak, "traffic": traffic,
                          "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                          "kernel": "pdmpc::search_kernel", "algorithmic_bytes_per_launch": alg_bytes,
                          "fp64": {"ops_per_launch": f64, "achieved_tops": f64 / (ms_step * 1e-3) / 1e12,

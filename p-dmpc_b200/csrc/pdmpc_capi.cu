@@ -613,10 +613,10 @@ static int launch_search(pdmpc_handle *h, const TraceDev &tr) {
     int variant = h->variant_mode;
     if (tr.search >= 0) variant = 1;   // pop traces come from the warp kernel
     if (variant == 0) {
-        // a batch that gives every SM a few hundred searches is throughput work: one thread per
-        // search; below that the warp-per-search shapes finish sooner
-        if (lanes_possible && n >= 32 * h->num_sms) variant = 3;
-        else variant = (h->thr_ok && n >= 4 * h->num_sms) ? 2 : 1;
+        // measured on B200 (profiles/r01b_variants.txt): the warp-per-search shapes beat the
+        // lane-per-search shape at every batch size of the BASELINE configs (the hand-over
+        // stage costs more than the lane stage saves), so shape 3 is opt-in only
+        variant = (h->thr_ok && n >= 4 * h->num_sms) ? 2 : 1;
     }
     if (variant == 3 && !lanes_possible) variant = 2;
     if (variant == 2 && !h->thr_ok) variant = 1;
