@@ -19,6 +19,7 @@
  *   vectorize_all_obstacles                                  hlc/optimizer/graph_search/vectorize_all_obstacles.m:1-76
  *   priority_queue_interface_mex (NEW/PUSH/POP)              hlc/optimizer/graph_search/priority_queue/priority_queue_interface_mex.cpp:19-108
  *   return_path_to / return_path_area                        hlc/optimizer/graph_search/return_path_to.m:1-27, return_path_area.m:1-8
+ *   MonteCarloTreeSearch.run_optimizer / do_graph_search     hlc/optimizer/graph_search/MonteCarloTreeSearch.m:29-251
  *
  * Conventions
  *   - plain C, no C++ types, no exceptions cross this boundary; every call
@@ -205,6 +206,32 @@ int pdmpc_sync(pdmpc_handle *h);
 int pdmpc_fetch_staged(pdmpc_handle *h, pdmpc_batch_out *out);
 
 int pdmpc_get_stats(pdmpc_handle *h, pdmpc_stats *out);
+
+/* ---- OptimizerType.MatlabSampled: MonteCarloTreeSearch.run_optimizer
+ *      (hlc/optimizer/graph_search/MonteCarloTreeSearch.m:29-251), selected by
+ *      OptimizerInterface.get_optimizer (hlc/optimizer/OptimizerInterface.m:28-30).
+ *      Same per-search inputs and the same constraint checkers as the graph
+ *      search; random roll-outs from the root, at most n_expansions_max node
+ *      expansions, the cheapest valid leaf at depth Hp wins. ------------------ */
+typedef struct pdmpc_mcts_params {
+    int32_t n_expansions_max;   /* MonteCarloTreeSearch.m:8 (default 250); 1 .. PDMPC_MCTS_MAX_EXPANSIONS */
+    const uint32_t *seed;       /* [n] RandStream('mt19937ar', Seed = time_step + vehicle_index), :31 */
+} pdmpc_mcts_params;
+#define PDMPC_MCTS_MAX_EXPANSIONS 1023
+#define PDMPC_MCTS_MAX_BRANCH 16   /* mpa.maximum_branching_factor() accepted by the sampled optimizer */
+
+/* Host buffers in, host buffers out (like pdmpc_plan_batch).  Output fields as
+ * for the graph search with these differences, all following the reference:
+ *   n_expanded  = n_expansions (:199)            n_pops = n_traversals (random numbers consumed)
+ *   pop_hash    = FNV-1a over ((node_id << 8) | child_position) of every roll-out step taken
+ *   tree_path   = node ids in the sampled tree (root 1, ids in order of creation, :177)
+ *   g_path      = -1 except the goal leaf, which carries the solution cost (:211,239); h_path = -1
+ * A search whose roll-outs would read past the Hp * n_expansions_max random numbers drawn at
+ * :52 (MATLAB raises an index error there) reports PDMPC_ERR_CAPACITY. */
+int pdmpc_mcts_plan_batch(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_mcts_params *prm,
+                          pdmpc_batch_out *out);
+/* Device-resident form: inputs staged with pdmpc_stage_batch, results read with pdmpc_fetch_staged. */
+int pdmpc_mcts_run_staged(pdmpc_handle *h, const pdmpc_mcts_params *prm);
 
 /* Pinned host buffers for callers that want full-rate host<->device copies. */
 int pdmpc_host_alloc(void **p, size_t bytes);

@@ -280,3 +280,148 @@ def do_graph_search(it, mpa, checker: int, trig: str = "spec", use_reference_pq:
             new_vals.append(float(eg) * 1 + float(eh) * 1)                        # GraphSearch.m:100-102
         if new_ids:
             pq.push(new_ids, new_vals)                                            # :104
+
+
+# ---------------------------------------------------------------- MonteCarloTreeSearch.m:29-251
+def do_mcts(it, mpa, checker: int, seed: int, n_expansions_max: int = 250, trig: str = "spec",
+            use_reference_pq: bool = True) -> Info:
+    """MonteCarloTreeSearch.run_optimizer + do_graph_search for one vehicle, in the
+    reference's own array form: `children` is the (max branching x nodes) uint32 matrix of
+    :64, poses are 3-vectors updated with the 3x3 `transform` of :127-132, and the random
+    stream is numpy's RandomState (MT19937 + 53-bit doubles == MATLAB's 'mt19937ar' rand,
+    an implementation independent of the oracle's)."""
+    Hp = mpa.Hp
+    rs = np.random.RandomState(int(seed) if int(seed) != 0 else 5489)
+    random_numbers = rs.random_sample(Hp * n_expansions_max)                 # :52
+    B = int(mpa.transition.sum(axis=2).max())                                 # :53 maximum_branching_factor
+    succ_of = lambda trim, step: np.flatnonzero(mpa.transition[step - 1, trim - 1]) + 1   # successor_trims{trim, step}
+    info = Info()
+    trims = np.zeros(n_expansions_max + Hp + 2, dtype=np.int64)                    # MATLAB grows on assignment
+    parents = np.zeros(n_expansions_max + Hp + 2, dtype=np.int64)
+    children = np.zeros((B, n_expansions_max + Hp + 2), dtype=np.int64)            # column j <-> node j+1
+    root_pose = np.array([float(it.x0[0]), float(it.x0[1]), float(it.x0[2])])
+    trims[0] = int(it.trim_indices)
+    children[:succ_of(trims[0], 1).size, 0] = 1                               # :69
+    n_nodes = 1
+    pq = _new_pq(use_reference_pq)
+    shapes_tmp = {}
+    if checker == 1:
+        veh_obs, lanelet = vectorize_all_obstacles(it, Hp)
+    ref = np.asarray(it.reference_trajectory_points, float).T                 # 2 x Hp  (:83)
+    n_expansions = 0
+    n_traversals = 0
+    is_finished = False
+    steps = []
+
+    def check(shape, bshape, k):
+        if checker == 1:
+            if interx(shape, veh_obs[k - 1]):
+                return False
+            return not interx(bshape, lanelet)
+        for o in it.obstacles:
+            if intersect_sat(shape, np.asarray(o, float)):
+                return False
+        for row in it.dynamic_obstacle_area:
+            if intersect_sat(shape, np.asarray(row[k - 1], float)):
+                return False
+        left, right = it.predicted_lanelet_boundary[:2]
+        return not intersect_lanelet_boundary(bshape, np.asarray(left, float).reshape(2, -1),
+                                              np.asarray(right, float).reshape(2, -1))
+
+    def area(edge, kind):
+        n = int(mpa.area_npts[edge, kind])
+        return np.vstack([mpa.area_x[edge, kind, :n], mpa.area_y[edge, kind, :n]])
+
+    def rot_apply(c, s, pts, start):
+        # transform(1:2,1:2) * area + start_pose(1:2): row i = c*ax + (-s)*ay + px (2-term product sums)
+        return np.vstack([c * pts[0] + (-s) * pts[1] + start[0], s * pts[0] + c * pts[1] + start[1]])
+
+    while n_expansions < n_expansions_max and not is_finished:                # :86
+        node_id = 1
+        solution_cost = 0.0
+        node_pose = root_pose.copy()
+        is_valid = False
+        child_position = node_parent = None
+        for i_step in range(1, Hp + 1):                                       # :92
+            is_valid = False
+            n_traversals += 1
+            trim_positions = np.flatnonzero(children[:, node_id - 1]) + 1     # :97
+            n_trims = trim_positions.size
+            if n_trims != 0:
+                child_position = int(trim_positions[int(np.ceil(random_numbers[n_traversals - 1] * n_trims)) - 1])
+            else:
+                if node_id != 1:                                              # :106-109
+                    parent_id = int(parents[node_id - 1])
+                    children[children[:, parent_id - 1] == node_id, parent_id - 1] = 0
+                    break
+                is_finished = True                                            # :110-113
+                break
+            steps.append((node_id << 8) | child_position)
+            parent_trim = int(trims[node_id - 1])
+            goal_trim = int(succ_of(parent_trim, i_step)[child_position - 1])
+            edge = int(mpa.edge_index[parent_trim - 1, goal_trim - 1])
+            c, s = _trig(float(node_pose[2]), trig)
+            dpose = np.array([mpa.edge_dx[edge], mpa.edge_dy[edge], mpa.edge_dyaw[edge]])
+            start_pose = node_pose.copy()
+            # :132 node_pose + transform * dpose, rows of the 3x3 product written out left to right
+            tp = np.array([c * dpose[0] + (-s) * dpose[1] + 0.0 * dpose[2],
+                           s * dpose[0] + c * dpose[1] + 0.0 * dpose[2],
+                           0.0 * dpose[0] + 0.0 * dpose[1] + 1.0 * dpose[2]])
+            node_pose = node_pose + tp
+            v = node_pose[:2] - ref[:, i_step - 1]
+            nrm = float(np.sqrt(v[0] * v[0] + v[1] * v[1]))
+            solution_cost = solution_cost + nrm * nrm                         # :137
+            if children[child_position - 1, node_id - 1] != 1:                # :139-144
+                node_id = int(children[child_position - 1, node_id - 1])
+                continue
+            n_expansions += 1
+            node_parent = node_id
+            shape = rot_apply(c, s, area(edge, 0), start_pose)                # :151
+            if i_step != Hp:                                                  # :153-159
+                bshape = rot_apply(c, s, area(edge, 1), start_pose)
+                child_succ = succ_of(goal_trim, i_step + 1)
+            else:
+                bshape = rot_apply(c, s, area(edge, 2), start_pose)
+                child_succ = np.zeros(0, dtype=np.int64)
+            is_valid = check(shape, bshape, i_step)                           # :161-170
+            if not is_valid:
+                children[child_position - 1, node_parent - 1] = 0             # :174
+                break
+            n_nodes += 1                                                      # :177-184
+            parents[n_nodes - 1] = node_parent
+            trims[n_nodes - 1] = goal_trim
+            children[:child_succ.size, n_nodes - 1] = 1
+            children[child_position - 1, node_parent - 1] = n_nodes
+            shapes_tmp[n_nodes] = shape
+            node_id = n_nodes
+        if is_valid:                                                          # :189-193
+            pq.push([node_id], [solution_cost])
+            children[child_position - 1, node_parent - 1] = 0
+    best, cost = pq.pop()                                                     # :197
+    info.n_expanded = n_expansions
+    info.pops = steps
+    info.n_traversals = n_traversals
+    if best == -1:
+        info.is_exhausted = True
+        return info
+    path = []
+    n = int(best)
+    while n:
+        path.append(n)
+        n = int(parents[n - 1])
+    path = path[::-1]
+    pose = np.zeros((3, len(path)))
+    pose[:, 0] = root_pose
+    for i in range(1, len(path)):                                             # :220-232
+        edge = int(mpa.edge_index[trims[path[i - 1] - 1] - 1, trims[path[i] - 1] - 1])
+        c, s = _trig(float(pose[2, i - 1]), trig)
+        d = np.array([mpa.edge_dx[edge], mpa.edge_dy[edge], mpa.edge_dyaw[edge]])
+        pose[:, i] = pose[:, i - 1] + np.array([c * d[0] + (-s) * d[1] + 0.0 * d[2],
+                                                s * d[0] + c * d[1] + 0.0 * d[2],
+                                                0.0 * d[0] + 0.0 * d[1] + 1.0 * d[2]])
+    info.tree_path = path
+    info.predicted_trims = [int(trims[q - 1]) for q in path[1:]]
+    info.y_predicted = pose[:, 1:].T.copy()
+    info.shapes = [shapes_tmp[q] for q in path[1:]]
+    info.cost = float(cost)
+    return info

@@ -73,6 +73,11 @@ def lib() -> C.CDLL:
         L.oracle_plan_trace.argtypes = [C.POINTER(capi.MpaDesc), C.POINTER(capi.BatchIn), C.c_int,
                                         _p_i64, C.c_int64, _p_i64]
         L.oracle_plan_trace.restype = C.c_int
+        L.oracle_mcts_plan_batch.argtypes = [C.POINTER(capi.MpaDesc), C.POINTER(capi.BatchIn),
+                                             C.POINTER(capi.MctsParams), C.POINTER(capi.BatchOut), C.c_int]
+        L.oracle_mcts_plan_batch.restype = C.c_int
+        L.oracle_mt19937_rand.argtypes = [C.c_uint32, _p_f64, C.c_int]
+        L.oracle_mt19937_rand.restype = None
         _LIB = L
     return _LIB
 
@@ -205,3 +210,23 @@ def plan_trace(mpa, batch: SearchBatch, search: int, cap: int = 1 << 20) -> np.n
         raise RuntimeError(f"oracle_plan_trace failed: {rc}")
     del keep
     return tr[: n.value].copy()
+
+
+def mcts_plan_batch(mpa, batch: SearchBatch, seeds, n_expansions_max: int = 250, n_threads: int = 1) -> BatchResult:
+    """MonteCarloTreeSearch.do_graph_search for every search of the batch on the CPU."""
+    d, keep = capi.mpa_desc(mpa)
+    r = BatchResult.empty(batch.n, batch.Hp)
+    bi, bo = capi.batch_in(batch), capi.batch_out(r)
+    prm, keep2 = capi.mcts_params(seeds, n_expansions_max, batch.n)
+    rc = lib().oracle_mcts_plan_batch(C.byref(d), C.byref(bi), C.byref(prm), C.byref(bo), int(n_threads))
+    if rc != 0:
+        raise RuntimeError(f"oracle_mcts_plan_batch failed: {rc}")
+    del keep, keep2
+    return r
+
+
+def mt19937_rand(seed: int, n: int) -> np.ndarray:
+    """rand(RandStream('mt19937ar', Seed = seed), 1, n) as the oracle restates it."""
+    out = np.zeros(n)
+    lib().oracle_mt19937_rand(int(seed), out.ctypes.data_as(_p_f64), int(n))
+    return out

@@ -618,3 +618,328 @@ int oracle_plan_trace(const pdmpc_mpa_desc *mpa, const pdmpc_batch_in *in, int t
     free(w.edge_of);
     return PDMPC_OK;
 }
+
+/* ========================================================================= */
+/* MonteCarloTreeSearch (OptimizerType.MatlabSampled), SURVEY.md §8 a10.      */
+/* hlc/optimizer/graph_search/MonteCarloTreeSearch.m:29-251                   */
+
+/* MATLAB RandStream('mt19937ar', Seed = s) + rand: the published MT19937
+ * (Matsumoto & Nishimura, mt19937ar.c: init_genrand, genrand_int32,
+ * genrand_res53).  Third-party arithmetic that is not under /root/reference;
+ * pinned in tests/ against numpy.random.RandomState (the same published
+ * algorithm, independent implementation).  MATLAB maps Seed = 0 to the
+ * generator's default seed 5489 (unpinned; time_step + vehicle_index >= 2 in
+ * the reference's only call site, MonteCarloTreeSearch.m:31). */
+typedef struct {
+    uint32_t mt[624];
+    int idx;
+} mt_t;
+
+static void mt_seed(mt_t *m, uint32_t s) {
+    if (s == 0) s = 5489u;
+    m->mt[0] = s;
+    for (int i = 1; i < 624; ++i)
+        m->mt[i] = 1812433253u * (m->mt[i - 1] ^ (m->mt[i - 1] >> 30)) + (uint32_t)i;
+    m->idx = 624;
+}
+
+static uint32_t mt_next(mt_t *m) {
+    if (m->idx >= 624) {
+        uint32_t *mt = m->mt;
+        for (int kk = 0; kk < 624; ++kk) {
+            uint32_t y = (mt[kk] & 0x80000000u) | (mt[(kk + 1) % 624] & 0x7fffffffu);
+            mt[kk] = mt[(kk + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        m->idx = 0;
+    }
+    uint32_t y = m->mt[m->idx++];
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+}
+
+static double mt_rand(mt_t *m) { /* genrand_res53 */
+    uint32_t a = mt_next(m) >> 5, b = mt_next(m) >> 6;
+    return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0);
+}
+
+void oracle_mt19937_rand(uint32_t seed, double *out, int n) {
+    mt_t m;
+    mt_seed(&m, seed);
+    for (int i = 0; i < n; ++i) out[i] = mt_rand(&m);
+}
+
+/* successor_trims{t, k} = find(transition_matrix_single(t, :, k))
+ * (MotionPrimitiveAutomaton.m:150); returns the count, fills succ[] 1-based trims */
+static int successors_of(const pdmpc_mpa_desc *mpa, int trim, int k, int *succ) {
+    const int nT = mpa->n_trims;
+    const uint8_t *row = mpa->transition + ((size_t)(k - 1) * nT + (trim - 1)) * nT;
+    int n = 0;
+    for (int j = 0; j < nT; ++j)
+        if (row[j]) succ[n++] = j + 1;
+    return n;
+}
+
+/* MonteCarloTreeSearch.do_graph_search (:40-251) for search `si`. */
+static int mcts_one(const pdmpc_mpa_desc *mpa, const pdmpc_batch_in *in, const pdmpc_mcts_params *prm,
+                    pdmpc_batch_out *out, int si, work_t *w) {
+    const int Hp = mpa->Hp, nT = mpa->n_trims;
+    const int nmax = prm->n_expansions_max;
+    int status = PDMPC_OK;
+    /* :53 maximum_branching_factor = max(sum(transition_matrix_single, 2), [], 'all') */
+    int B = 0;
+    for (size_t r = 0; r < (size_t)Hp * nT; ++r) {
+        int c = 0;
+        for (int j = 0; j < nT; ++j) c += mpa->transition[r * nT + j] != 0;
+        if (c > B) B = c;
+    }
+    /* :31,52 */
+    const int n_rand = Hp * nmax;
+    double *rnd = (double *)malloc((size_t)(n_rand > 0 ? n_rand : 1) * sizeof(double));
+    {
+        mt_t m;
+        mt_seed(&m, prm->seed[si]);
+        for (int i = 0; i < n_rand; ++i) rnd[i] = mt_rand(&m);
+    }
+    /* :59-70 (MATLAB grows the arrays on assignment).  The budget is only tested between
+     * roll-outs (:86), so the last roll-out may overshoot: n_expansions <= nmax + Hp - 1 */
+    const int cap = nmax + Hp + 2;
+    int32_t *trims = (int32_t *)calloc((size_t)cap, sizeof(int32_t));
+    int32_t *parents = (int32_t *)calloc((size_t)cap, sizeof(int32_t));
+    int32_t *children = (int32_t *)calloc((size_t)cap * (B > 0 ? B : 1), sizeof(int32_t)); /* [node][position] */
+    double *shx = (double *)calloc((size_t)cap * PDMPC_AREA_STRIDE, sizeof(double));        /* shapes_tmp */
+    double *shy = (double *)calloc((size_t)cap * PDMPC_AREA_STRIDE, sizeof(double));
+    int32_t *shn = (int32_t *)calloc((size_t)cap, sizeof(int32_t));
+    int *succ = (int *)malloc((size_t)nT * sizeof(int));
+    const double root_pose[3] = {in->x0[si], in->y0[si], in->yaw0[si]};
+    trims[1] = in->trim0[si];
+    parents[1] = 0;
+    {
+        int n = successors_of(mpa, trims[1], 1, succ);
+        for (int i = 0; i < n; ++i) children[1 * B + i] = 1;
+    }
+    int n_nodes = 1;
+    oracle_pq *pq = &w->pq; /* valid_nodes_at_hp */
+    pq->len = 0;
+
+    /* :75-76 set_up_constraints: lanelet = [left, NaN, right, NaN] */
+    int l0 = in->lane_ptr[2 * si], l1 = in->lane_ptr[2 * si + 1], l2 = in->lane_ptr[2 * si + 2];
+    int nlane = (l2 - l0) + 2;
+    double *lanex = (double *)malloc((size_t)nlane * sizeof(double));
+    double *laney = (double *)malloc((size_t)nlane * sizeof(double));
+    {
+        int n = 0;
+        for (int i = l0; i < l1; ++i) { lanex[n] = in->lane_x[i]; laney[n] = in->lane_y[i]; ++n; }
+        lanex[n] = NAN; laney[n] = NAN; ++n;
+        for (int i = l1; i < l2; ++i) { lanex[n] = in->lane_x[i]; laney[n] = in->lane_y[i]; ++n; }
+        lanex[n] = NAN; laney[n] = NAN; ++n;
+    }
+    const double *rx = in->ref_x + (size_t)si * Hp, *ry = in->ref_y + (size_t)si * Hp;
+
+    int n_expansions = 0, n_traversals = 0, is_finished = 0;
+    uint64_t hash = 0xcbf29ce484222325ULL;
+
+    while (n_expansions < nmax && !is_finished && status == PDMPC_OK) { /* :86 */
+        int node_id = 1;
+        double solution_cost = 0;
+        double node_pose[3] = {root_pose[0], root_pose[1], root_pose[2]};
+        int is_valid = 0, child_position = 0, node_parent = 0;
+        for (int i_step = 1; i_step <= Hp; ++i_step) { /* :92 */
+            is_valid = 0;
+            n_traversals = n_traversals + 1;
+            /* :97-98 trim_positions = find(children(:, node_id)) */
+            int n_trims = 0;
+            for (int p = 0; p < B; ++p) n_trims += children[node_id * B + p] != 0;
+            if (n_trims != 0) {
+                if (n_traversals > n_rand) { status = PDMPC_ERR_CAPACITY; break; } /* MATLAB: index out of bounds */
+                /* :102 trim_positions(ceil(r * n_trims)) */
+                int pick = (int)ceil(rnd[n_traversals - 1] * (double)n_trims);
+                int seen = 0;
+                for (int p = 0; p < B; ++p)
+                    if (children[node_id * B + p] != 0 && ++seen == pick) { child_position = p + 1; break; }
+            } else {
+                if (node_id != 1) { /* :106-109 remove edge to node without children */
+                    int parent_id = parents[node_id];
+                    for (int p = 0; p < B; ++p)
+                        if (children[parent_id * B + p] == node_id) children[parent_id * B + p] = 0;
+                    break;
+                } else { /* :110-113 */
+                    is_finished = 1;
+                    break;
+                }
+            }
+            hash = fnv1a_u32(hash, ((uint32_t)node_id << 8) | (uint32_t)child_position);
+            /* :117-122 */
+            int parent_trim = trims[node_id];
+            successors_of(mpa, parent_trim, i_step, succ);
+            int goal_trim = succ[child_position - 1];
+            int edge = w->edge_of[(parent_trim - 1) * nT + (goal_trim - 1)];
+            double c, s;
+            oracle_sincos(node_pose[2], &s, &c); /* :124-125 */
+            double start_pose[3] = {node_pose[0], node_pose[1], node_pose[2]};
+            /* :127-132 node_pose + [c -s 0; s c 0; 0 0 1] * dpose (the zero products add exact zeros) */
+            double dx = mpa->edge_dx[edge], dy = mpa->edge_dy[edge], dyaw = mpa->edge_dyaw[edge];
+            node_pose[0] = node_pose[0] + (c * dx - s * dy);
+            node_pose[1] = node_pose[1] + (s * dx + c * dy);
+            node_pose[2] = node_pose[2] + dyaw;
+            /* :137 */
+            {
+                double ddx = node_pose[0] - rx[i_step - 1], ddy = node_pose[1] - ry[i_step - 1];
+                double nrm = sqrt(ddx * ddx + ddy * ddy);
+                solution_cost = solution_cost + nrm * nrm;
+            }
+            /* :139-144 */
+            if (children[node_id * B + child_position - 1] != 1) {
+                node_id = children[node_id * B + child_position - 1];
+                continue;
+            }
+            n_expansions = n_expansions + 1; /* :146 */
+            node_parent = node_id;
+            /* :150-159 */
+            double sx[PDMPC_AREA_STRIDE], sy[PDMPC_AREA_STRIDE], bx[PDMPC_AREA_STRIDE], by[PDMPC_AREA_STRIDE];
+            int ns, nb, n_child_succ = 0;
+            place_area(mpa, edge, PDMPC_AREA_NORMAL, c, s, start_pose[0], start_pose[1], sx, sy, &ns);
+            if (i_step != Hp) {
+                place_area(mpa, edge, PDMPC_AREA_WITHOUT_OFFSET, c, s, start_pose[0], start_pose[1], bx, by, &nb);
+                n_child_succ = successors_of(mpa, goal_trim, i_step + 1, succ);
+            } else {
+                place_area(mpa, edge, PDMPC_AREA_LARGE_OFFSET, c, s, start_pose[0], start_pose[1], bx, by, &nb);
+            }
+            /* :161-170 */
+            if (in->checker == PDMPC_CHECKER_SAT)
+                is_valid = constraints_sat(in, Hp, si, i_step, sx, sy, ns, bx, by, nb);
+            else
+                is_valid = constraints_interx(in, Hp, si, i_step, w, sx, sy, ns, bx, by, nb, lanex, laney, nlane);
+            if (!is_valid) { /* :172-175 remove edge */
+                children[node_parent * B + child_position - 1] = 0;
+                break;
+            } else { /* :176-185 add node */
+                n_nodes = n_nodes + 1;
+                parents[n_nodes] = node_parent;
+                trims[n_nodes] = goal_trim;
+                for (int i = 0; i < n_child_succ; ++i) children[n_nodes * B + i] = 1;
+                children[node_parent * B + child_position - 1] = n_nodes;
+                shn[n_nodes] = ns;
+                for (int i = 0; i < ns; ++i) {
+                    shx[(size_t)n_nodes * PDMPC_AREA_STRIDE + i] = sx[i];
+                    shy[(size_t)n_nodes * PDMPC_AREA_STRIDE + i] = sy[i];
+                }
+                node_id = n_nodes;
+            }
+        }
+        if (is_valid) { /* :189-193 */
+            oracle_pq_push(pq, node_id, solution_cost);
+            children[node_parent * B + child_position - 1] = 0; /* avoid double exploration */
+        }
+    }
+
+    double cost = 0;
+    int64_t best = oracle_pq_pop(pq, &cost); /* :197 */
+    int exhausted = (best == -1) || status != PDMPC_OK; /* :202-205 */
+
+    if (out->status) out->status[si] = status;
+    if (out->is_exhausted) out->is_exhausted[si] = (uint8_t)exhausted;
+    if (out->n_expanded) out->n_expanded[si] = n_expansions; /* :199 */
+    if (out->n_pops) out->n_pops[si] = n_traversals;
+    if (out->pop_hash) out->pop_hash[si] = hash;
+    int64_t path[PDMPC_MAX_HP + 1];
+    double pose[PDMPC_MAX_HP + 1][3];
+    if (!exhausted) { /* :215-232 */
+        int64_t n = best;
+        for (int d = Hp; d >= 0; --d) {
+            path[d] = n;
+            n = parents[n];
+        }
+        pose[0][0] = root_pose[0]; pose[0][1] = root_pose[1]; pose[0][2] = root_pose[2];
+        for (int i = 1; i <= Hp; ++i) {
+            int edge = w->edge_of[(trims[path[i - 1]] - 1) * nT + (trims[path[i]] - 1)];
+            double c, s;
+            oracle_sincos(pose[i - 1][2], &s, &c);
+            double dx = mpa->edge_dx[edge], dy = mpa->edge_dy[edge], dyaw = mpa->edge_dyaw[edge];
+            pose[i][0] = pose[i - 1][0] + (c * dx - s * dy);
+            pose[i][1] = pose[i - 1][1] + (s * dx + c * dy);
+            pose[i][2] = pose[i - 1][2] + dyaw;
+        }
+    }
+    for (int d = 0; d <= Hp; ++d) {
+        size_t o = (size_t)si * (Hp + 1) + d;
+        if (out->trims) out->trims[o] = exhausted ? (d == 0 ? in->trim0[si] : 0) : trims[path[d]];
+        if (out->tree_path) out->tree_path[o] = exhausted ? 0 : (int32_t)path[d];
+        /* :211-213,239 tree.g = -1 except the best leaf, tree.h = -1 */
+        if (out->g_path) out->g_path[o] = exhausted ? NAN : (d == Hp ? cost : -1.0);
+        if (out->h_path) out->h_path[o] = exhausted ? NAN : -1.0;
+    }
+    for (int d = 1; d <= Hp; ++d) {
+        size_t o = (size_t)si * Hp + (d - 1);
+        if (out->y_predicted) /* :242 */
+            for (int c3 = 0; c3 < 3; ++c3) out->y_predicted[o * 3 + c3] = exhausted ? NAN : pose[d][c3];
+        if (out->shape_npts) { /* :243 return_path_area(shapes_tmp, ...) */
+            out->shape_npts[o] = exhausted ? 0 : shn[path[d]];
+            if (out->shape_x && out->shape_y)
+                for (int i = 0; i < PDMPC_AREA_STRIDE; ++i) {
+                    out->shape_x[o * PDMPC_AREA_STRIDE + i] =
+                        exhausted ? 0.0 : shx[(size_t)path[d] * PDMPC_AREA_STRIDE + i];
+                    out->shape_y[o * PDMPC_AREA_STRIDE + i] =
+                        exhausted ? 0.0 : shy[(size_t)path[d] * PDMPC_AREA_STRIDE + i];
+                }
+        }
+    }
+    free(rnd); free(trims); free(parents); free(children); free(shx); free(shy); free(shn); free(succ);
+    free(lanex); free(laney);
+    return 0;
+}
+
+typedef struct {
+    const pdmpc_mpa_desc *mpa;
+    const pdmpc_batch_in *in;
+    const pdmpc_mcts_params *prm;
+    pdmpc_batch_out *out;
+    int32_t *edge_of;
+    int n;
+    int *next;
+} mjob_t;
+
+static void *mjob_main(void *p) {
+    mjob_t *j = (mjob_t *)p;
+    work_t w;
+    memset(&w, 0, sizeof(w));
+    w.edge_of = j->edge_of;
+    for (;;) {
+        int b = __atomic_fetch_add(j->next, 16, __ATOMIC_RELAXED);
+        if (b >= j->n) break;
+        int e = b + 16 < j->n ? b + 16 : j->n;
+        for (int si = b; si < e; ++si) mcts_one(j->mpa, j->in, j->prm, j->out, si, &w);
+    }
+    free(w.pq.a);
+    free(w.ox);
+    free(w.oy);
+    return NULL;
+}
+
+int oracle_mcts_plan_batch(const pdmpc_mpa_desc *mpa, const pdmpc_batch_in *in, const pdmpc_mcts_params *prm,
+                           pdmpc_batch_out *out, int n_threads) {
+    if (!mpa || !in || !prm || !out || !prm->seed || prm->n_expansions_max < 1) return PDMPC_ERR_BAD_INPUT;
+    int n = in->n_searches;
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > n) n_threads = n > 0 ? n : 1;
+    int32_t *edge_of = build_edge_of(mpa);
+    int next = 0;
+    mjob_t *jobs = (mjob_t *)calloc((size_t)n_threads, sizeof(mjob_t));
+    pthread_t *th = (pthread_t *)calloc((size_t)n_threads, sizeof(pthread_t));
+    for (int t = 0; t < n_threads; ++t) {
+        jobs[t].mpa = mpa; jobs[t].in = in; jobs[t].prm = prm; jobs[t].out = out;
+        jobs[t].edge_of = edge_of; jobs[t].n = n; jobs[t].next = &next;
+    }
+    if (n_threads == 1) {
+        mjob_main(&jobs[0]);
+    } else {
+        for (int t = 0; t < n_threads; ++t) pthread_create(&th[t], NULL, mjob_main, &jobs[t]);
+        for (int t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
+    }
+    free(jobs);
+    free(th);
+    free(edge_of);
+    return PDMPC_OK;
+}

@@ -67,6 +67,12 @@ int oracle_plan_trace(const pdmpc_mpa_desc *mpa, const pdmpc_batch_in *in,
                       int trace_search, int64_t *pop_trace, int64_t trace_cap,
                       int64_t *n_trace);
 
+/* MonteCarloTreeSearch.do_graph_search (MonteCarloTreeSearch.m:40-251) for every search. */
+int oracle_mcts_plan_batch(const pdmpc_mpa_desc *mpa, const pdmpc_batch_in *in,
+                           const pdmpc_mcts_params *prm, pdmpc_batch_out *out, int n_threads);
+/* rand(RandStream('mt19937ar', Seed = seed), 1, n): MT19937 + genrand_res53 */
+void oracle_mt19937_rand(uint32_t seed, double *out, int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = (
     "pdmpc_set_node_capacity", "pdmpc_set_variant", "pdmpc_set_lane_limits", "pdmpc_host_alloc", "pdmpc_host_free",
     "pdmpc_trace_staged", "pdmpc_upload_mpa", "pdmpc_plan_batch", "pdmpc_stage_batch",
     "pdmpc_run_staged", "pdmpc_sync", "pdmpc_fetch_staged", "pdmpc_get_stats", "pdmpc_stream",
+    "pdmpc_mcts_plan_batch", "pdmpc_mcts_run_staged",
 )
 
 _p_u8 = C.POINTER(C.c_uint8)
@@ -58,6 +59,10 @@ class BatchIn(C.Structure):
         ("slot_ptr", _p_i32), ("poly_ptr", _p_i32), ("vert_x", _p_f64), ("vert_y", _p_f64),
         ("lane_ptr", _p_i32), ("lane_x", _p_f64), ("lane_y", _p_f64),
     ]
+
+
+class MctsParams(C.Structure):
+    _fields_ = [("n_expansions_max", C.c_int32), ("seed", C.POINTER(C.c_uint32))]
 
 
 class BatchOut(C.Structure):
@@ -115,6 +120,13 @@ def batch_in(b: SearchBatch) -> BatchIn:
         poly_ptr=_ptr(b.poly_ptr, _p_i32), vert_x=_ptr(b.vert_x, _p_f64),
         vert_y=_ptr(b.vert_y, _p_f64), lane_ptr=_ptr(b.lane_ptr, _p_i32),
         lane_x=_ptr(b.lane_x, _p_f64), lane_y=_ptr(b.lane_y, _p_f64))
+
+
+def mcts_params(seeds, n_expansions_max: int, n: int):
+    """Returns (MctsParams, keepalive): seed[i] = time_step + vehicle_index (MonteCarloTreeSearch.m:31)."""
+    seeds = np.ascontiguousarray(np.broadcast_to(np.asarray(seeds, dtype=np.uint32), (n,)))
+    return MctsParams(n_expansions_max=int(n_expansions_max),
+                      seed=seeds.ctypes.data_as(C.POINTER(C.c_uint32))), seeds
 
 
 def batch_out(r: BatchResult) -> BatchOut:
@@ -176,6 +188,10 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.pdmpc_fetch_staged.restype = C.c_int
     lib.pdmpc_get_stats.argtypes = [H, C.POINTER(Stats)]
     lib.pdmpc_get_stats.restype = C.c_int
+    lib.pdmpc_mcts_plan_batch.argtypes = [H, C.POINTER(BatchIn), C.POINTER(MctsParams), C.POINTER(BatchOut)]
+    lib.pdmpc_mcts_plan_batch.restype = C.c_int
+    lib.pdmpc_mcts_run_staged.argtypes = [H, C.POINTER(MctsParams)]
+    lib.pdmpc_mcts_run_staged.restype = C.c_int
     lib.pdmpc_stream.argtypes = [H]
     lib.pdmpc_stream.restype = C.c_void_p
     _LIB = lib
@@ -251,6 +267,24 @@ class Planner:
             bad = int(np.flatnonzero(r.status != PDMPC_OK)[0])
             raise PdmpcError(int(r.status[bad]), f"search {bad} failed")
         return r
+
+    def mcts_plan_batch(self, b: SearchBatch, seeds, n_expansions_max: int = 250,
+                        raise_on_search_error: bool = True) -> BatchResult:
+        """MonteCarloTreeSearch.run_optimizer for every search (pdmpc_mcts_plan_batch)."""
+        r = BatchResult.empty(b.n, b.Hp)
+        bi, bo = batch_in(b), batch_out(r)
+        prm, keep = mcts_params(seeds, n_expansions_max, b.n)
+        self._check(self.lib.pdmpc_mcts_plan_batch(self.h, C.byref(bi), C.byref(prm), C.byref(bo)))
+        del keep
+        if raise_on_search_error and b.n and int(r.status.max()) != PDMPC_OK:
+            bad = int(np.flatnonzero(r.status != PDMPC_OK)[0])
+            raise PdmpcError(int(r.status[bad]), f"search {bad} failed")
+        return r
+
+    def mcts_run_staged(self, seeds, n_expansions_max: int = 250):
+        prm, keep = mcts_params(seeds, n_expansions_max, self._staged_n)
+        self._check(self.lib.pdmpc_mcts_run_staged(self.h, C.byref(prm)))
+        del keep
 
     def stage(self, b: SearchBatch):
         bi = batch_in(b)

@@ -16,6 +16,7 @@
 
 #include "pdmpc_kernels.cuh"
 #include "pdmpc_lanes.cuh"
+#include "pdmpc_mcts.cuh"
 
 using namespace pdmpc;
 
@@ -24,8 +25,14 @@ namespace {
 // Launch shapes of the search kernel (pdmpc_kernels.cuh): "latency" = one warp
 // per CTA, tables through L1/L2; "throughput" = one 16-warp CTA per SM with the
 // MPA tables TMA-staged into shared memory.
-constexpr int kHeapSmem = 256;   // heap entries kept in shared memory per search
-constexpr int kPts = 256;        // polyline points (lanelet bounds + obstacles of all steps) staged per search
+#ifndef PDMPC_HEAP_SMEM
+#define PDMPC_HEAP_SMEM 256
+#endif
+#ifndef PDMPC_PTS_SMEM
+#define PDMPC_PTS_SMEM 256
+#endif
+constexpr int kHeapSmem = PDMPC_HEAP_SMEM;   // heap entries kept in shared memory per search
+constexpr int kPts = PDMPC_PTS_SMEM;         // polyline points (lanelet bounds + obstacles of all steps) staged per search
 constexpr int kWarpsThroughput = 16;
 #define KERNEL_LAT search_kernel<kHeapSmem, kPts, 1, false>
 #define KERNEL_THR search_kernel<kHeapSmem, kPts, kWarpsThroughput, true>
@@ -83,13 +90,14 @@ struct pdmpc_handle {
     DBuf m_succ_ptr, m_succ_te, m_edge_d, m_npts, m_ax, m_ay, m_apx, m_apy;
     int full_tree_nodes = 0;
     int user_node_cap = 0;
+    int max_branch = 0;               // mpa.maximum_branching_factor()
 
     // staged batch
     bool staged = false;
     BatchDev batch{};
     int n_polys = 0, n_verts = 0, n_lane = 0;
     DBuf b_x0, b_y0, b_yaw0, b_trim0, b_refx, b_refy, b_vref, b_slot, b_poly, b_vx, b_vy, b_plx, b_ply,
-        b_lane, b_lx, b_ly, b_llx, b_lly, b_order, b_plxy, b_llxy, b_rng;
+        b_lane, b_lx, b_ly, b_llx, b_lly, b_order, b_plxy, b_llxy, b_rng, b_seed;
 
     // outputs
     OutDev out{};
@@ -183,7 +191,7 @@ int pdmpc_destroy(pdmpc_handle *h) {
                     &h->b_plx, &h->b_ply, &h->b_lane, &h->b_lx, &h->b_ly, &h->b_llx, &h->b_lly,
                     &h->o_status, &h->o_exh, &h->o_nexp, &h->o_npops, &h->o_hash, &h->o_trims, &h->o_path,
                     &h->o_ypred, &h->o_g, &h->o_h, &h->o_snp, &h->o_sx, &h->o_sy, &h->o_counters,
-                    &h->work_counter, &h->a_a, &h->a_b, &h->a_cs, &h->a_heap, &h->t_ids, &h->t_n};
+                    &h->work_counter, &h->b_seed, &h->a_a, &h->a_b, &h->a_cs, &h->a_heap, &h->t_ids, &h->t_n};
     for (DBuf *b : bufs) b->release();
     for (auto &ev : h->ev)
         if (ev) cudaEventDestroy(ev);
@@ -274,6 +282,7 @@ int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *d) {
     // successor lists: find(transition_matrix_single(t,:,k)) ascending (expand_node.m:18)
     std::vector<int> succ_ptr((size_t)Hp * nT + 1, 0);
     std::vector<int> succ_te;
+    h->max_branch = 0;
     for (int k = 0; k < Hp; ++k)
         for (int t = 0; t < nT; ++t) {
             const uint8_t *row = d->transition + ((size_t)k * nT + t) * nT;
@@ -284,6 +293,7 @@ int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *d) {
                     succ_te.push_back((e << 8) | j);
                 }
             succ_ptr[(size_t)k * nT + t + 1] = (int)succ_te.size();
+            h->max_branch = std::max(h->max_branch, succ_ptr[(size_t)k * nT + t + 1] - succ_ptr[(size_t)k * nT + t]);
         }
     // capacity bound: nodes of the full tree from the worst start trim
     double worst = 1;
@@ -742,6 +752,56 @@ int pdmpc_plan_batch(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc_batch_out 
     int rc = pdmpc_stage_batch(h, in);
     if (rc != PDMPC_OK) return rc;
     rc = pdmpc_run_staged(h);
+    if (rc != PDMPC_OK) return rc;
+    return pdmpc_fetch_staged(h, out);
+}
+
+// MonteCarloTreeSearch over the staged batch: one warp per search (pdmpc_mcts.cuh).
+int pdmpc_mcts_run_staged(pdmpc_handle *h, const pdmpc_mcts_params *prm) {
+    if (!h) return PDMPC_ERR_BAD_INPUT;
+    if (!h->staged) return fail(h, PDMPC_ERR_BAD_INPUT, "mcts: no staged batch");
+    if (!prm || prm->n_expansions_max < 1 || prm->n_expansions_max > PDMPC_MCTS_MAX_EXPANSIONS)
+        return fail(h, PDMPC_ERR_BAD_INPUT, "mcts: n_expansions_max out of range");
+    const int n = h->batch.n;
+    if (n && !prm->seed) return fail(h, PDMPC_ERR_BAD_INPUT, "mcts: seed is NULL");
+    if (h->max_branch > PDMPC_MCTS_MAX_BRANCH)
+        return fail(h, PDMPC_ERR_BAD_INPUT, "mcts: branching factor of the MPA exceeds PDMPC_MCTS_MAX_BRANCH");
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaMemsetAsync(h->o_counters.p, 0, 16 * sizeof(unsigned long long), h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->work_counter.p, 0, sizeof(unsigned), h->stream));
+    h->stats.kernel_launches = 0;
+    if (n == 0) return PDMPC_OK;
+    {
+        int rc = upload(h, h->b_seed, prm->seed, (size_t)n);
+        if (rc != PDMPC_OK) return rc;
+        CU_TRY(h, cudaStreamSynchronize(h->stream));   // the seeds are caller-owned
+    }
+    MctsDev mc;
+    mc.n_max = prm->n_expansions_max;
+    mc.node_cap = prm->n_expansions_max + h->mpa.Hp + 1;
+    mc.seed = h->b_seed.as<unsigned>();
+    const size_t smem = mcts_smem_bytes(mc.node_cap);
+    if (smem > kSmemLimit) return fail(h, PDMPC_ERR_CAPACITY, "mcts: sampled tree does not fit in shared memory");
+    CU_TRY(h, cudaFuncSetAttribute(mcts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mcts_kernel, kWarp, smem));
+    if (occ < 1) return fail(h, PDMPC_ERR_CUDA, "mcts: kernel is not launchable on this device");
+    const int grid = std::min(n, h->num_sms * occ);
+    CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
+    mcts_kernel<<<grid, kWarp, smem, h->stream>>>(h->mpa, h->batch, h->out, mc, h->work_counter.as<unsigned>());
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
+    h->timing_pending_kernel = true;
+    h->timing_pending_lanes = false;
+    h->stats.kernel_launches++;
+    return PDMPC_OK;
+}
+
+int pdmpc_mcts_plan_batch(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_mcts_params *prm,
+                          pdmpc_batch_out *out) {
+    int rc = pdmpc_stage_batch(h, in);
+    if (rc != PDMPC_OK) return rc;
+    rc = pdmpc_mcts_run_staged(h, prm);
     if (rc != PDMPC_OK) return rc;
     return pdmpc_fetch_staged(h, out);
 }

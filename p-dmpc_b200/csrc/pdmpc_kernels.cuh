@@ -595,8 +595,11 @@ struct __align__(16) TileSmem {
 //   throughput (WARPS = 16, SMEM_TABLES = true): one 16-warp CTA per SM; the MPA
 //              tables are staged once per CTA into shared memory by TMA bulk copies
 //              (cp.async.bulk + mbarrier), each warp still runs its own searches.
+#ifndef PDMPC_MIN_CTAS_LAT
+#define PDMPC_MIN_CTAS_LAT 1   // resident one-warp CTAs per SM the latency shape is compiled for (register cap)
+#endif
 template <int HS, int SP, int WARPS, bool SMEM_TABLES>
-__global__ void __launch_bounds__(WARPS *kWarp) search_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar,
+__global__ void __launch_bounds__(WARPS *kWarp, WARPS == 1 ? PDMPC_MIN_CTAS_LAT : 1) search_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar,
                                                               unsigned *work_counter, TraceDev tr,
                                                               const unsigned *n_work_dev) {
     constexpr int TILE = kWarp;

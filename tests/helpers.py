@@ -70,3 +70,19 @@ def load_golden(name: str):
     batch = build(SearchBatch, "in__")
     exp = build(BatchResult, "out__")
     return mpa, batch, exp
+
+
+def load_golden_mcts(name: str):
+    """tests/golden/mcts_expected.npz (tools/make_golden_mcts.py) -> (seeds, n_max, expected BatchResult)
+    of the sampled optimizer on the records of fixture `name`."""
+    import dataclasses
+    import os
+
+    from pdmpc_b200.records import BatchResult
+
+    z = np.load(os.path.join(GOLDEN_DIR, "mcts_expected.npz"))
+    kw = {}
+    for f in dataclasses.fields(BatchResult):
+        a = z[f"{name}__out__{f.name}"]
+        kw[f.name] = a.item() if a.ndim == 0 else a
+    return z[name + "__seeds"], int(z[name + "__n_max"]), BatchResult(**kw)
