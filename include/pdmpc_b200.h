@@ -185,7 +185,10 @@ int pdmpc_set_node_capacity(pdmpc_handle *h, int32_t max_nodes_per_search);
  * (one 16-warp CTA per SM, MPA tables TMA-staged in shared memory; falls back to 1
  * when the tables do not fit), 3 = lanes (one THREAD per search for large InterX
  * batches; searches that outgrow a thread's slot or pop budget are re-run by shape 1
- * in a second launch; falls back to 2 for SAT batches).  Results do not depend on it. */
+ * in a second launch; falls back to 2 for SAT batches), 4 = cta (one 13-warp CTA per search: a
+ * master warp owns queue and tree, checker warps validate the children of every expansion
+ * ahead of their pop; chosen automatically for batches of at most one search per SM; falls
+ * back to 1 when the full search tree of the MPA exceeds 32768 nodes).  Results do not depend on it. */
 int pdmpc_set_variant(pdmpc_handle *h, int32_t variant);
 
 /* Shape 3 only: nodes per thread slot (0 = default 4096) and the number of pops after

@@ -17,6 +17,7 @@
 #include "pdmpc_kernels.cuh"
 #include "pdmpc_lanes.cuh"
 #include "pdmpc_mcts.cuh"
+#include "pdmpc_cta.cuh"
 
 using namespace pdmpc;
 
@@ -43,6 +44,9 @@ constexpr size_t kSmemLimit = 227 * 1024;
 constexpr int kLaneThreads = 256;
 #define KERNEL_LANES_SMEM search_lanes_kernel<kLaneThreads, true>
 #define KERNEL_LANES_GMEM search_lanes_kernel<kLaneThreads, false>
+// "cta" = one 13-warp CTA per search (pdmpc_cta.cuh): master warp + checker warps, lowest latency
+#define KERNEL_CTA search_cta_kernel<kCtaHeap, kCtaPts, kCtaHelpers>
+using CtaSmemT = CtaSmem<kCtaHeap, kCtaPts, kCtaHelpers>;
 constexpr int kLaneNodeCapDefault = 4096;
 constexpr int kLanePopLimitDefault = 1024;
 
@@ -75,7 +79,8 @@ struct pdmpc_handle {
     int lat_ctas_per_sm = 0;          // occupancy of the latency shape
     bool thr_ok = false;              // throughput shape usable with the uploaded MPA (tables fit in smem)
     size_t thr_smem = 0;
-    int variant_mode = 0;             // 0 = auto, 1 = latency, 2 = throughput, 3 = lanes (+ warp second stage)
+    int variant_mode = 0;             // 0 = auto, 1 = latency, 2 = throughput, 3 = lanes (+ warp second stage), 4 = cta
+    bool cta_ok = false;              // the CTA-per-search kernel is launchable (shared memory opt-in granted)
     bool lanes_ok = false;            // every maneuver area has <= 7 points
     bool lanes_smem_ok = false;       // MPA tables fit in shared memory next to nothing else
     size_t lanes_smem = 0;
@@ -176,6 +181,9 @@ int pdmpc_create(int device_id, pdmpc_handle **out) {
         return fail(nullptr, PDMPC_ERR_CUDA, msg);
     }
     h->lat_ctas_per_sm = occ;
+    h->cta_ok = cudaFuncSetAttribute(KERNEL_CTA, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(CtaSmemT)) == cudaSuccess;
+    cudaGetLastError();
     *out = h;
     return PDMPC_OK;
 }
@@ -213,8 +221,8 @@ int pdmpc_host_free(void *p) {
 
 int pdmpc_set_variant(pdmpc_handle *h, int32_t variant) {
     if (!h) return PDMPC_ERR_BAD_INPUT;
-    if (variant < 0 || variant > 3)
-        return fail(h, PDMPC_ERR_BAD_INPUT, "variant must be 0 (auto), 1 (latency), 2 (throughput) or 3 (lanes)");
+    if (variant < 0 || variant > 4)
+        return fail(h, PDMPC_ERR_BAD_INPUT, "variant must be 0 (auto), 1 (latency), 2 (throughput), 3 (lanes) or 4 (cta)");
     h->variant_mode = variant;
     return PDMPC_OK;
 }
@@ -627,6 +635,13 @@ static int launch_search(pdmpc_handle *h, const TraceDev &tr) {
         // lane-per-search shape at every batch size of the BASELINE configs (the hand-over
         // stage costs more than the lane stage saves), so shape 3 is opt-in only
         variant = (h->thr_ok && n >= 4 * h->num_sms) ? 2 : 1;
+        // fewer searches than SMs (one computation level of a time step): one CTA per search,
+        // edge checks spread over checker warps (profiles/r01e_cta_latency.txt)
+        if (n <= h->num_sms) variant = 4;
+    }
+    if (variant == 4) {
+        const int cap = h->user_node_cap ? h->user_node_cap : std::min(h->full_tree_nodes + 8, 1 << 20);
+        if (!h->cta_ok || cap > kCtaFlags) variant = 1;   // validity flags of a whole tree must fit in shared memory
     }
     if (variant == 3 && !lanes_possible) variant = 2;
     if (variant == 2 && !h->thr_ok) variant = 1;
@@ -664,6 +679,13 @@ static int launch_search(pdmpc_handle *h, const TraceDev &tr) {
                                                                  h->work_counter2.as<unsigned>(), tr,
                                                                  h->ov_count.as<unsigned>());
         h->stats.kernel_launches++;
+    } else if (variant == 4) {
+        const int grid = std::min(n, h->num_sms);
+        int rc = ensure_arena(h, grid);
+        if (rc != PDMPC_OK) return rc;
+        CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
+        KERNEL_CTA<<<grid, (kCtaHelpers + 1) * kWarp, sizeof(CtaSmemT), h->stream>>>(h->mpa, h->batch, h->out,
+                                                                                    h->arena, wc);
     } else if (variant == 2) {
         const int grid = std::min((n + kWarpsThroughput - 1) / kWarpsThroughput, h->num_sms);
         int rc = ensure_arena(h, grid * kWarpsThroughput);

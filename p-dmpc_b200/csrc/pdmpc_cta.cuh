@@ -1,0 +1,445 @@
+// pdmpc_cta.cuh — "one CTA per search" launch shape of the graph search: the lowest
+// single-search latency, used when a batch has fewer searches than the GPU has SMs (one
+// computation level of one 20-vehicle time step).
+//
+// Same algorithm and bit-identical results as search_kernel (pdmpc_kernels.cuh):
+//   GraphSearch.do_graph_search / eval_edge_exact   hlc/optimizer/graph_search/GraphSearch.m:23-196
+//   expand_node                                      hlc/optimizer/graph_search/expand_node.m:1-91
+//   priority queue                                   .../priority_queue/priority_queue_interface_mex.cpp:19-108
+//
+// The reference validates an edge lazily, when its end node is popped (GraphSearch.m:64-77).
+// Whether an edge is valid is a pure function of the node (parent pose, maneuver, depth), so
+// the answer can be computed EARLY without changing any result:
+//   * warp 0 ("master") owns the priority queue and the tree: pop -> read the node's validity
+//     flag -> expand -> push.  Pop order, node ids and n_expanded are exactly the reference's:
+//     invalid nodes are still pushed, popped and counted.
+//   * warps 1..NH ("checkers") validate the children of every expansion as soon as they are
+//     created, one child per warp (placement of the maneuver areas, InterX / SAT against the
+//     staged obstacle polylines), compute cos/sin of a valid child's yaw for its own later
+//     expansion, and publish a per-node flag in shared memory.
+// The master therefore never runs an edge check; checks of nodes that are never popped are
+// wasted work on SMs that would otherwise idle.
+//
+// Hand-over: a ring of kRing job descriptors in shared memory; job j is published with
+// bar.arrive on named barrier 1 + j % kRing, the checkers wait for it in bar.sync (no
+// issue slots are spent spinning).  Node records the master needs again when a child is
+// popped are kept in a direct-mapped shared-memory cache next to the HBM arena.
+#pragma once
+
+#include "pdmpc_kernels.cuh"
+
+namespace pdmpc {
+
+constexpr int kRing = 8;            // job descriptors in flight (named barriers 1..kRing)
+constexpr int kCtaHelpers = 12;     // checker warps (max branching of the single/triple-speed MPAs)
+constexpr int kCtaHeap = 4096;      // heap entries in shared memory
+constexpr int kCtaPts = 512;        // staged polyline points
+constexpr int kCtaCache = 1024;     // node-record cache entries (direct mapped by id)
+constexpr int kCtaFlags = 32768;    // validity flags (1 byte per node id) — searches need cap <= this
+
+struct __align__(16) CtaJob {       // one expansion: children nid0 .. nid0 + nchild - 1
+    double px, py, pyaw, c, s;      // pose and cos/sin(yaw) of the expanded node
+    unsigned nid0;
+    int nchild, sbase, k;           // successor list base, depth of the children
+    int terminate, pad;
+};
+
+template <int HS, int SP, int NH>
+struct __align__(16) CtaSmem {
+    HEnt heap[HS];
+    double pts_x[SP], pts_y[SP];
+    double refx[kMaxHp], refy[kMaxHp], vref[kMaxHp];
+    NodeA c_a[kCtaCache];
+    NodeCS c_cs[kCtaCache];
+    unsigned c_tag[kCtaCache];      // id whose (x, y, yaw, g) sits in c_a
+    unsigned cs_tag[kCtaCache];     // id whose (cos, sin) sits in c_cs
+    double shx[NH][kAreaStride], shy[NH][kAreaStride], bhx[NH][kAreaStride], bhy[NH][kAreaStride];
+    CtaJob ring[kRing];
+    int rng[kMaxHp + 2];
+    unsigned path[kMaxHp + 1];
+    unsigned done[NH];
+    int abort_flag;
+    unsigned next_search;
+    int clear_upto;                 // highest node id of the previous search (flags to clear)
+    unsigned char flag[kCtaFlags];  // 0 pending, 1 valid, 2 invalid
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+template <int HS, int SP, int NH>
+__global__ void __launch_bounds__((NH + 1) * kWarp, 1)
+search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_counter) {
+    // ids whose checks can be in flight: kRing jobs x at most PDMPC_MAX_TRIMS - 1 children each, so the
+    // checkers of two nodes that share a cache slot (ids kCtaCache apart) never run at the same time
+    static_assert(kRing * PDMPC_MAX_TRIMS <= kCtaCache, "a late checker must never alias a newer cache entry");
+    constexpr int TILE = kWarp;
+    constexpr int kThreads = (NH + 1) * kWarp;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CtaSmem<HS, SP, NH> &sm = *reinterpret_cast<CtaSmem<HS, SP, NH> *>(smem_raw);
+    Tables tb;
+    tb.succ_ptr = m.succ_ptr; tb.succ_te = m.succ_te; tb.edge_d = m.edge_d;
+    tb.area_npts = m.area_npts; tb.area_x = m.area_x; tb.area_y = m.area_y;
+
+    const int warp_id = threadIdx.x / kWarp;
+    Tile<TILE> t;
+    t.shift = 0; t.lane = threadIdx.x % kWarp; t.mask = 0xffffffffu;
+    const int Hp = m.Hp, nT = m.nT;
+    const size_t slot_base = (size_t)blockIdx.x * (size_t)ar.cap;
+    NodeA *__restrict__ na = ar.a + slot_base;
+    NodeB *__restrict__ nb = ar.b + slot_base;
+    NodeCS *__restrict__ ncs = ar.cs + slot_base;
+    volatile unsigned char *vflag = sm.flag;
+    volatile unsigned *vdone = sm.done;
+    volatile int *vabort = &sm.abort_flag;
+    volatile unsigned *vcs_tag = sm.cs_tag;
+    if (threadIdx.x == 0) sm.clear_upto = kCtaFlags - 1;   // all flags, the first time
+
+    for (;;) {
+        // ---- fetch a search; cooperative set-up ------------------------------------------
+        __syncthreads();
+        if (threadIdx.x == 0) sm.next_search = atomicAdd(work_counter, 1u);
+        __syncthreads();
+        const unsigned si_u = sm.next_search;
+        if (si_u >= (unsigned)b.n) break;
+        const int si = b.order ? __ldg(b.order + si_u) : (int)si_u;
+        const int clear_upto = sm.clear_upto;
+        for (int i = threadIdx.x; i <= clear_upto / 4; i += kThreads) reinterpret_cast<unsigned *>(sm.flag)[i] = 0u;
+        for (int i = threadIdx.x; i < kCtaCache; i += kThreads) { sm.c_tag[i] = 0u; sm.cs_tag[i] = 0u; }
+        if (threadIdx.x < NH) sm.done[threadIdx.x] = 0u;
+        if (threadIdx.x == 0) sm.abort_flag = 0;
+        for (int k = threadIdx.x; k < Hp; k += kThreads) {
+            sm.refx[k] = __ldg(b.ref_x + (size_t)si * Hp + k);
+            sm.refy[k] = __ldg(b.ref_y + (size_t)si * Hp + k);
+            sm.vref[k] = __ldg(b.v_ref + (size_t)si * Hp + k);
+        }
+        const int *slot = b.slot_ptr + (size_t)si * (Hp + 1);
+        const int trim0 = __ldg(b.trim0 + si);
+        const int sp0 = __ldg(slot + 0), sp1 = __ldg(slot + 1);
+        const int lp0 = __ldg(b.lane_ptr + 2 * si), lp1 = __ldg(b.lane_ptr + 2 * si + 1),
+                  lp2 = __ldg(b.lane_ptr + 2 * si + 2);
+        const double *opx = nullptr, *opy = nullptr, *lpx = nullptr, *lpy = nullptr;
+        int obase = 0, llo = 0, lhi = 0;
+        if (b.checker == PDMPC_CHECKER_INTERX) {
+            const int spE = __ldg(slot + Hp + 1);
+            const int ob_lo = __ldg(b.poly_ptr + sp0) + sp0, ob_hi = __ldg(b.poly_ptr + spE) + spE;
+            const int ll_lo = lp0 + 2 * si, ll_hi = lp2 + 2 * si + 2;
+            for (int k = threadIdx.x; k <= Hp + 1; k += kThreads) {
+                const int q = __ldg(slot + k);
+                sm.rng[k] = __ldg(b.poly_ptr + q) + q - ob_lo;
+            }
+            const int nl = ll_hi - ll_lo, no = ob_hi - ob_lo;
+            int used = 0;
+            if (nl <= SP) {
+                for (int j = threadIdx.x; j < nl; j += kThreads) {
+                    sm.pts_x[j] = __ldg(b.ll_x + ll_lo + j);
+                    sm.pts_y[j] = __ldg(b.ll_y + ll_lo + j);
+                }
+                lpx = sm.pts_x; lpy = sm.pts_y; llo = 0; lhi = nl;
+                used = nl;
+            } else {
+                lpx = b.ll_x; lpy = b.ll_y; llo = ll_lo; lhi = ll_hi;
+            }
+            if (used + no <= SP) {
+                for (int j = threadIdx.x; j < no; j += kThreads) {
+                    sm.pts_x[used + j] = __ldg(b.pl_x + ob_lo + j);
+                    sm.pts_y[used + j] = __ldg(b.pl_y + ob_lo + j);
+                }
+                opx = sm.pts_x; opy = sm.pts_y; obase = used;
+            } else {
+                opx = b.pl_x; opy = b.pl_y; obase = ob_lo;
+            }
+        }
+        __syncthreads();
+
+        if (warp_id != 0) {
+            // =================== checker warps: eval_edge_exact, eagerly ===================
+            const int w = warp_id - 1;
+            double *shx = sm.shx[w], *shy = sm.shy[w], *bhx = sm.bhx[w], *bhy = sm.bhy[w];
+            unsigned long long cols = 0;
+            for (unsigned j = 0;; ++j) {
+                named_bar_sync(1 + (int)(j % kRing), kThreads);          // job j is published
+                const CtaJob &jb = sm.ring[j % kRing];
+                if (jb.terminate) break;
+                const int nchild = jb.nchild, cK = jb.k;
+                if (!*vabort) {
+                    const double ppx = jb.px, ppy = jb.py, pc = jb.c, ps = jb.s, pyaw = jb.pyaw;
+                    const unsigned nid0 = jb.nid0;
+                    const int sbase = jb.sbase;
+                    for (int ci = w; ci < nchild; ci += NH) {
+                        const int te = tb.succ_te[sbase + ci];
+                        const int edge = te >> 8;
+                        const unsigned nid = nid0 + (unsigned)ci;
+                        const int bkind = (cK == Hp) ? PDMPC_AREA_LARGE_OFFSET : PDMPC_AREA_WITHOUT_OFFSET;  // GraphSearch.m:166-174
+                        const int ns = tb.area_npts[edge * 3 + PDMPC_AREA_NORMAL];
+                        const int nbs = tb.area_npts[edge * 3 + bkind];
+                        if (t.lane < 8)
+                            place_point(tb, edge, PDMPC_AREA_NORMAL, t.lane, pc, ps, ppx, ppy, shx[t.lane], shy[t.lane]);
+                        else if (t.lane < 16)
+                            place_point(tb, edge, bkind, t.lane - 8, pc, ps, ppx, ppy, bhx[t.lane - 8], bhy[t.lane - 8]);
+                        t.sync();
+                        bool valid = true;
+                        if (b.checker == PDMPC_CHECKER_INTERX) {
+                            const int st_lo = obase + sm.rng[0], st_hi = obase + sm.rng[1];
+                            const int dy_lo = obase + sm.rng[cK], dy_hi = obase + sm.rng[cK + 1];
+                            cols += (unsigned long long)((st_hi - st_lo) + (dy_hi - dy_lo) + (lhi - llo));
+                            if (interx_dispatch<TILE>(ns, opx, opy, st_lo, st_hi, dy_lo, dy_hi, shx, shy, t))
+                                valid = false;
+                            else if (interx_dispatch<TILE>(nbs, lpx, lpy, llo, lhi, 0, 0, bhx, bhy, t))
+                                valid = false;
+                        } else {
+                            const int dp0 = __ldg(slot + cK), dp1 = __ldg(slot + cK + 1);
+                            for (int pass = 0; pass < 2 && valid; ++pass) {
+                                const int q0 = pass == 0 ? sp0 : dp0, q1 = pass == 0 ? sp1 : dp1;
+                                for (int p = q0; p < q1 && valid; ++p) {
+                                    const int v0 = __ldg(b.poly_ptr + p), v1 = __ldg(b.poly_ptr + p + 1);
+                                    cols += (unsigned long long)(v1 - v0);
+                                    if (sat_collide<TILE>(shx, shy, ns, b.vert_x + v0, b.vert_y + v0, v1 - v0, t))
+                                        valid = false;
+                                }
+                            }
+                            if (valid) {
+                                cols += (unsigned long long)(lp2 - lp0);
+                                if (lanelet_side_sat<TILE>(bhx, bhy, nbs, b.lane_x + lp0, b.lane_y + lp0, lp1 - lp0, t))
+                                    valid = false;
+                                else if (lanelet_side_sat<TILE>(bhx, bhy, nbs, b.lane_x + lp1, b.lane_y + lp1, lp2 - lp1, t))
+                                    valid = false;
+                            }
+                        }
+                        if (t.lane == 0) {
+                            if (valid && cK < Hp) {
+                                // cos/sin of the child's yaw for ITS expansion (expand_node.m:50-51);
+                                // yaw' = yaw + dyaw exactly as the master computes it (:55)
+                                NodeCS ecs;
+                                sincos_ref(pyaw + tb.edge_d[edge * 4 + 2], ecs.s, ecs.c);
+                                ncs[nid] = ecs;
+                                // cache entry, seqlock style: the master may be reading this slot for
+                                // an older node (id - kCtaCache) right now
+                                const int cslot = nid & (kCtaCache - 1);
+                                vcs_tag[cslot] = 0u;
+                                __threadfence_block();
+                                sm.c_cs[cslot] = ecs;
+                                __threadfence_block();
+                                vcs_tag[cslot] = nid;
+                            }
+                            __threadfence_block();
+                            vflag[nid] = valid ? 1 : 2;
+                        }
+                        t.sync();   // shapes are rewritten by the next child
+                    }
+                }
+                t.sync();   // every lane is done with the descriptor
+                if (t.lane == 0) vdone[w] = j + 1u;
+            }
+            if (t.lane == 0 && cols) atomicAdd(o.counters + 2, cols);
+            continue;   // next search (meets the master at the __syncthreads on top)
+        }
+
+        // =================== master warp: queue + tree ==========================================
+        Heap<HS, TILE> heap;
+        heap.sm = sm.heap;
+        heap.gl = ar.heap + slot_base;
+        heap.len = 1;
+        int n_nodes = 1, n_pops = 0, status = PDMPC_OK;
+        unsigned long long hash = 0xcbf29ce484222325ULL;
+        bool exhausted = false;
+        unsigned goal = 0, n_jobs = 0;
+        if (t.lane == 0) {   // root: GraphSearch.m:34-46
+            NodeA ra;
+            ra.x = __ldg(b.x0 + si); ra.y = __ldg(b.y0 + si); ra.yaw = __ldg(b.yaw0 + si); ra.g = 0.0;
+            NodeCS rcs;
+            sincos_ref(ra.yaw, rcs.s, rcs.c);
+            NodeB rb;
+            rb.h = 0.0; rb.parent = 0; rb.edge = 0xffff; rb.trim = (unsigned char)trim0; rb.k = 0;
+            na[1] = ra; nb[1] = rb; ncs[1] = rcs;
+            sm.c_a[1] = ra; sm.c_tag[1] = 1u; sm.c_cs[1] = rcs; sm.cs_tag[1] = 1u;
+            HEnt re;
+            re.f = 0.0; re.w = HEnt::pack(1u, 0u, 0u, 0u, (unsigned)trim0);
+            heap.store(0, re);
+        }
+        t.sync();
+
+        for (;;) {   // GraphSearch.m:53-107
+            if (heap.len == 0) { exhausted = true; break; }               // :57-61
+            const HEnt top = heap.pop(t);
+            const unsigned id = top.id(), par = top.pid();
+            const int cK = (int)top.k();
+            ++n_pops;
+            hash = hash_step(hash, id);
+            if (par != 0) {   // eval_edge_exact's answer, computed by a checker warp
+                unsigned f;
+                do { f = vflag[id]; } while (f == 0u);
+                __threadfence_block();
+                if (f != 1u) continue;                                    // :75-77
+            }
+            if (cK == Hp) { goal = id; break; }                           // :81-90
+
+            // ---- expand_node.m:1-91 (nV == 1) ----------------------------------------------
+            const int ctrim = (int)top.trim();
+            const int k_exp = cK + 1;
+            const int sbase = tb.succ_ptr[(k_exp - 1) * nT + (ctrim - 1)];
+            const int nchild = tb.succ_ptr[(k_exp - 1) * nT + (ctrim - 1) + 1] - sbase;
+            if (n_nodes + nchild >= ar.cap || n_nodes + nchild >= kCtaFlags) { status = PDMPC_ERR_CAPACITY; break; }
+            const int cslot = id & (kCtaCache - 1);
+            NodeA ca;
+            NodeCS ccs;
+            if (sm.c_tag[cslot] == id) ca = sm.c_a[cslot]; else ca = na[id];
+            {
+                const unsigned t1 = vcs_tag[cslot];
+                __threadfence_block();
+                const volatile double *vcs = reinterpret_cast<const volatile double *>(&sm.c_cs[cslot]);
+                ccs.c = vcs[0]; ccs.s = vcs[1];
+                __threadfence_block();
+                const unsigned t2 = vcs_tag[cslot];
+                if (t1 != id || t2 != id) ccs = ncs[id];   // evicted (or being replaced): HBM arena copy
+            }
+            const double s = ccs.s, c = ccs.c;
+            // publish the job first: the checkers work while the master computes costs and pushes
+            {
+                while (true) {   // ring slot free: every checker is done with job n_jobs - kRing
+                    const unsigned d = t.lane < NH ? vdone[t.lane] : n_jobs;   // jobs completed by checker `lane`
+                    if (__all_sync(0xffffffffu, d + kRing > n_jobs)) break;
+                }
+                if (t.lane == 0) {
+                    CtaJob &jb = sm.ring[n_jobs % kRing];
+                    jb.px = ca.x; jb.py = ca.y; jb.pyaw = ca.yaw; jb.c = c; jb.s = s;
+                    jb.nid0 = (unsigned)(n_nodes + 1); jb.nchild = nchild; jb.sbase = sbase; jb.k = k_exp;
+                    jb.terminate = 0;
+                }
+                __threadfence_block();
+                t.sync();
+                named_bar_arrive(1 + (int)(n_jobs % kRing), kThreads);
+                ++n_jobs;
+            }
+            const int to_go = Hp - k_exp;               // :37
+            for (int c0 = 0; c0 < nchild; c0 += TILE) {
+                const int ci = c0 + t.lane;
+                const int cnt = min(TILE, nchild - c0);
+                HEnt he;
+                he.f = 0.0; he.w = 0;
+                const unsigned nid = (unsigned)(n_nodes + 1 + ci);
+                if (ci < nchild) {
+                    const int te = tb.succ_te[sbase + ci];
+                    const int cedge = te >> 8, t2 = (te & 0xff) + 1;
+                    const double mdx = tb.edge_d[cedge * 4 + 0], mdy = tb.edge_d[cedge * 4 + 1],
+                                 mdyaw = tb.edge_d[cedge * 4 + 2];
+                    NodeA ea;
+                    ea.x = c * mdx - s * mdy + ca.x;          // :53
+                    ea.y = s * mdx + c * mdy + ca.y;          // :54
+                    ea.yaw = ca.yaw + mdyaw;                  // :55
+                    const double ddx = ea.x - sm.refx[k_exp - 1], ddy = ea.y - sm.refy[k_exp - 1];
+                    const double nrm = sqrt(ddx * ddx + ddy * ddy);
+                    ea.g = ca.g + nrm * nrm;            // :61
+                    double eh = 0.0, d_max = 0.0;       // :66-73
+                    for (int it0 = 1; it0 <= to_go; it0 += 4) {
+                        double hn[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int kk = min(k_exp + it0 + u - 1, Hp - 1);
+                            const double hx = ea.x - sm.refx[kk], hy = ea.y - sm.refy[kk];
+                            hn[u] = sqrt(hx * hx + hy * hy);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (it0 + u <= to_go) {
+                                d_max = d_max + b.dt * sm.vref[k_exp + it0 + u - 1];
+                                const double mm = fmax(0.0, hn[u] - d_max);
+                                eh = eh + mm * mm;
+                            }
+                        }
+                    }
+                    NodeB eb;
+                    eb.h = eh; eb.parent = id; eb.edge = (unsigned short)cedge;
+                    eb.trim = (unsigned char)t2; eb.k = (unsigned char)k_exp;
+                    na[nid] = ea;                       // Tree.m:54-70 add_nodes
+                    nb[nid] = eb;
+                    const int nslot = nid & (kCtaCache - 1);
+                    sm.c_a[nslot] = ea;
+                    sm.c_tag[nslot] = nid;
+                    he.f = ea.g + eh;                   // GraphSearch.m:102 (weights 1)
+                    he.w = HEnt::pack(nid, id, (unsigned)cedge, (unsigned)k_exp, (unsigned)t2);
+                }
+                heap.push_many(he, cnt, t);             // :104, one push per child, in order
+            }
+            n_nodes += nchild;
+        }
+
+        // ---- release the checkers, then write the results (GraphSearch.m:58-60 / :82-89) ------
+        if (t.lane == 0) *vabort = 1;
+        {
+            while (true) {
+                const unsigned d = t.lane < NH ? vdone[t.lane] : n_jobs;   // jobs completed by checker `lane`
+                if (__all_sync(0xffffffffu, d + kRing > n_jobs)) break;
+            }
+            if (t.lane == 0) sm.ring[n_jobs % kRing].terminate = 1;
+            __threadfence_block();
+            t.sync();
+            named_bar_arrive(1 + (int)(n_jobs % kRing), kThreads);
+        }
+        if (status != PDMPC_OK) exhausted = true;
+        if (t.lane == 0) {
+            unsigned cur = goal;
+            for (int d = Hp; d >= 0; --d) {           // Tree.m:44-52 path_to_root, flipped
+                sm.path[d] = exhausted ? 0u : cur;
+                if (!exhausted && d > 0) cur = nb[cur].parent;
+            }
+            o.status[si] = status;
+            if (o.is_exhausted) o.is_exhausted[si] = exhausted ? 1 : 0;
+            if (o.n_expanded) o.n_expanded[si] = n_nodes;
+            if (o.n_pops) o.n_pops[si] = n_pops;
+            if (o.pop_hash) o.pop_hash[si] = hash;
+            atomicAdd(o.counters + 0, (unsigned long long)n_pops);
+            atomicAdd(o.counters + 1, (unsigned long long)n_nodes);
+        }
+        t.sync();
+        const double qnan = nan("");
+        for (int d = t.lane; d <= Hp; d += TILE) {
+            const unsigned pid = sm.path[d];
+            NodeA pa = {qnan, qnan, qnan, qnan};
+            NodeB pb;
+            pb.h = qnan; pb.parent = 0; pb.edge = 0; pb.trim = 0; pb.k = 0;
+            if (!exhausted) { pa = na[pid]; pb = nb[pid]; }
+            const size_t oo = (size_t)si * (Hp + 1) + d;
+            if (o.trims) o.trims[oo] = exhausted ? (d == 0 ? trim0 : 0) : (int)pb.trim;
+            if (o.tree_path) o.tree_path[oo] = (int)pid;
+            if (o.g_path) o.g_path[oo] = pa.g;
+            if (o.h_path) o.h_path[oo] = pb.h;
+            if (d >= 1) {
+                const size_t os = (size_t)si * Hp + (d - 1);
+                if (o.y_predicted) {                   // return_path_to.m:11-25
+                    o.y_predicted[os * 3 + 0] = pa.x;
+                    o.y_predicted[os * 3 + 1] = pa.y;
+                    o.y_predicted[os * 3 + 2] = pa.yaw;
+                }
+                if (o.shape_npts) {                    // return_path_area.m:5-7
+                    int edge = 0, ns = 0;
+                    NodeA qa = {0.0, 0.0, 0.0, 0.0};
+                    NodeCS qcs = {0.0, 0.0};
+                    if (!exhausted) {
+                        const unsigned qid = sm.path[d - 1];   // parent on the path (valid, depth < Hp)
+                        qa = na[qid];
+                        qcs = ncs[qid];
+                        edge = pb.edge;
+                        ns = tb.area_npts[edge * 3 + PDMPC_AREA_NORMAL];
+                    }
+                    o.shape_npts[os] = ns;
+                    if (o.shape_x && o.shape_y) {
+                        for (int i = 0; i < kAreaStride; ++i) {
+                            double ox = 0.0, oy = 0.0;
+                            if (i < ns) place_point(tb, edge, PDMPC_AREA_NORMAL, i, qcs.c, qcs.s, qa.x, qa.y, ox, oy);
+                            o.shape_x[os * kAreaStride + i] = ox;
+                            o.shape_y[os * kAreaStride + i] = oy;
+                        }
+                    }
+                }
+            }
+        }
+        if (t.lane == 0) sm.clear_upto = n_nodes;
+    }
+}
+
+}  // namespace pdmpc

@@ -17,7 +17,7 @@ from helpers import GOLDEN_CASES, circle_records, load_golden, rect, road_record
 pytestmark = pytest.mark.gpu
 
 
-VARIANTS = (1, 2, 3)   # latency / throughput / lane-per-search launch shapes: identical results required
+VARIANTS = (1, 2, 3, 4)   # latency / throughput / lane-per-search / CTA-per-search launch shapes: identical results required
 
 
 def check(planner, mpa, batch, variants=VARIANTS, **kw):

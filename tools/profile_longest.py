@@ -18,17 +18,31 @@ mpa = get_mpa("triple_speed" if "triple" in path else "single_speed", non_convex
 b = SearchBatch.load(path)
 p = capi.Planner(0)
 p.upload_mpa(mpa)
+p.set_variant(1)
 r = p.plan_batch(b)
 order = np.argsort(r.n_pops)[::-1]
+variants = [int(v) for v in os.environ.get("PDMPC_VARIANTS", "1,4").split(",")]
 for rank in (0, len(order) // 2):
     i = int(order[rank])
     one = b.select([i])
-    p.stage(one)
+    for variant in variants:
+        p.set_variant(variant)
+        p.stage(one)
+        for _ in range(3):
+            p.run_staged()
+        p.sync()
+        st = p.stats()
+        rr = p.fetch()
+        assert rr.pop_hash[0] == r.pop_hash[i] and rr.n_expanded[0] == r.n_expanded[i]
+        print(f"variant {variant} search {i}: pops {int(rr.n_pops[0])} nodes {int(rr.n_expanded[0])} exhausted {int(rr.is_exhausted[0])} "
+              f"polys {int(one.poly_ptr.size - 1)} verts {int(one.vert_x.size)} lane pts {int(one.lane_x.size)} "
+              f"kernel {st.kernel_ms:.3f} ms -> {st.kernel_ms * 1e3 / max(int(rr.n_pops[0]), 1):.2f} us/pop")
+# one whole time step's worth: the 20 longest searches of the file as one batch
+top = b.select(order[:20])
+for variant in variants:
+    p.set_variant(variant)
+    p.stage(top)
     for _ in range(3):
         p.run_staged()
     p.sync()
-    st = p.stats()
-    rr = p.fetch()
-    print(f"search {i}: pops {int(rr.n_pops[0])} nodes {int(rr.n_expanded[0])} exhausted {int(rr.is_exhausted[0])} "
-          f"polys {int(one.poly_ptr.size - 1)} verts {int(one.vert_x.size)} lane pts {int(one.lane_x.size)} "
-          f"kernel {st.kernel_ms:.3f} ms -> {st.kernel_ms * 1e3 / max(int(rr.n_pops[0]), 1):.2f} us/pop")
+    print(f"variant {variant}: 20 longest searches as one batch: kernel {p.stats().kernel_ms:.3f} ms")
