@@ -196,6 +196,10 @@ int pdmpc_set_variant(pdmpc_handle *h, int32_t variant);
  * Tuning knobs: results do not depend on them. */
 int pdmpc_set_lane_limits(pdmpc_handle *h, int32_t nodes_per_thread, int32_t pop_limit);
 
+/* Shape 4 only: heap entries kept in shared memory (0 = default 4096, even); the rest of the
+ * queue spills to the HBM arena.  Tuning/test knob: results do not depend on it. */
+int pdmpc_set_cta_heap_smem(pdmpc_handle *h, int32_t entries);
+
 /* Stage the MPA tables in HBM (once per MPA; cached in the handle). */
 int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *mpa);
 

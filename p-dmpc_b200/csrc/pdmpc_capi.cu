@@ -80,6 +80,7 @@ struct pdmpc_handle {
     bool thr_ok = false;              // throughput shape usable with the uploaded MPA (tables fit in smem)
     size_t thr_smem = 0;
     int variant_mode = 0;             // 0 = auto, 1 = latency, 2 = throughput, 3 = lanes (+ warp second stage), 4 = cta
+    int cta_heap_smem = kCtaHeap;     // heap entries the CTA shape keeps in shared memory (tuning/test knob)
     bool cta_ok = false;              // the CTA-per-search kernel is launchable (shared memory opt-in granted)
     bool lanes_ok = false;            // every maneuver area has <= 7 points
     bool lanes_smem_ok = false;       // MPA tables fit in shared memory next to nothing else
@@ -224,6 +225,14 @@ int pdmpc_set_variant(pdmpc_handle *h, int32_t variant) {
     if (variant < 0 || variant > 4)
         return fail(h, PDMPC_ERR_BAD_INPUT, "variant must be 0 (auto), 1 (latency), 2 (throughput), 3 (lanes) or 4 (cta)");
     h->variant_mode = variant;
+    return PDMPC_OK;
+}
+
+int pdmpc_set_cta_heap_smem(pdmpc_handle *h, int32_t entries) {
+    if (!h) return PDMPC_ERR_BAD_INPUT;
+    if (entries < 0 || entries > kCtaHeap || (entries & 1))
+        return fail(h, PDMPC_ERR_BAD_INPUT, "cta heap: entries must be 0 (default) or an even number <= 4096");
+    h->cta_heap_smem = entries ? entries : kCtaHeap;
     return PDMPC_OK;
 }
 
@@ -684,8 +693,8 @@ static int launch_search(pdmpc_handle *h, const TraceDev &tr) {
         int rc = ensure_arena(h, grid);
         if (rc != PDMPC_OK) return rc;
         CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
-        KERNEL_CTA<<<grid, (kCtaHelpers + 1) * kWarp, sizeof(CtaSmemT), h->stream>>>(h->mpa, h->batch, h->out,
-                                                                                    h->arena, wc);
+        KERNEL_CTA<<<grid, (kCtaHelpers + kCtaHelpers / 3) * kWarp, sizeof(CtaSmemT), h->stream>>>(h->mpa, h->batch, h->out,
+                                                                                    h->arena, wc, h->cta_heap_smem);
     } else if (variant == 2) {
         const int grid = std::min((n + kWarpsThroughput - 1) / kWarpsThroughput, h->num_sms);
         int rc = ensure_arena(h, grid * kWarpsThroughput);

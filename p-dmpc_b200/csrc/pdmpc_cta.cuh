@@ -46,7 +46,8 @@ struct __align__(16) CtaJob {       // one expansion: children nid0 .. nid0 + nc
 
 template <int HS, int SP, int NH>
 struct __align__(16) CtaSmem {
-    HEnt heap[HS];
+    double hf[HS + 2];               // heap costs, entry i at hf[i + 1] (pdmpc_heap_split.cuh)
+    unsigned long long hw[HS];       // heap payloads
     double pts_x[SP], pts_y[SP];
     double refx[kMaxHp], refy[kMaxHp], vref[kMaxHp];
     NodeA c_a[kCtaCache];
@@ -64,6 +65,12 @@ struct __align__(16) CtaSmem {
     unsigned char flag[kCtaFlags];  // 0 pending, 1 valid, 2 invalid
 };
 
+// Ordering between the master and the checkers (all flags, descriptors and cache entries live in
+// shared memory; the only global data handed over is cos/sin of a node, same SM).  An acquire-
+// release fence at CTA scope is enough; __threadfence_block() compiles to the sequentially
+// consistent MEMBAR.SC.CTA, which drains the master's outstanding arena stores on every pop.
+__device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
@@ -71,14 +78,20 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
+// Warps of a CTA are spread round-robin over the SM's four schedulers, so warps 4, 8, 12, ...
+// share the master's.  They are left idle (parked at the CTA barrier): the master's dependent
+// instruction chain then never waits for an issue slot behind a checker's FP64 stream
+// (profiles/r01e_cta_latency.txt).
 template <int HS, int SP, int NH>
-__global__ void __launch_bounds__((NH + 1) * kWarp, 1)
-search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_counter) {
+__global__ void __launch_bounds__((NH + NH / 3) * kWarp, 1)
+search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_counter, int heap_smem) {
     // ids whose checks can be in flight: kRing jobs x at most PDMPC_MAX_TRIMS - 1 children each, so the
     // checkers of two nodes that share a cache slot (ids kCtaCache apart) never run at the same time
     static_assert(kRing * PDMPC_MAX_TRIMS <= kCtaCache, "a late checker must never alias a newer cache entry");
     constexpr int TILE = kWarp;
-    constexpr int kThreads = (NH + 1) * kWarp;
+    static_assert(NH % 3 == 0, "three checker warps per scheduler group");
+    constexpr int kThreads = (NH + NH / 3) * kWarp;        // launched: master + checkers + parked warps
+    constexpr int kBarThreads = (NH + 1) * kWarp;          // master + checkers: the named barriers' count
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CtaSmem<HS, SP, NH> &sm = *reinterpret_cast<CtaSmem<HS, SP, NH> *>(smem_raw);
     Tables tb;
@@ -98,6 +111,7 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
     volatile int *vabort = &sm.abort_flag;
     volatile unsigned *vcs_tag = sm.cs_tag;
     if (threadIdx.x == 0) sm.clear_upto = kCtaFlags - 1;   // all flags, the first time
+    const unsigned hf_addr = shared_base_once(sm.hf), hw_addr = shared_base_once(sm.hw);
 
     for (;;) {
         // ---- fetch a search; cooperative set-up ------------------------------------------
@@ -156,13 +170,14 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
         }
         __syncthreads();
 
+        if (warp_id != 0 && (warp_id & 3) == 0) continue;   // parked warp: back to the CTA barrier
         if (warp_id != 0) {
             // =================== checker warps: eval_edge_exact, eagerly ===================
-            const int w = warp_id - 1;
+            const int w = warp_id - 1 - (warp_id >> 2);
             double *shx = sm.shx[w], *shy = sm.shy[w], *bhx = sm.bhx[w], *bhy = sm.bhy[w];
             unsigned long long cols = 0;
             for (unsigned j = 0;; ++j) {
-                named_bar_sync(1 + (int)(j % kRing), kThreads);          // job j is published
+                named_bar_sync(1 + (int)(j % kRing), kBarThreads);          // job j is published
                 const CtaJob &jb = sm.ring[j % kRing];
                 if (jb.terminate) break;
                 const int nchild = jb.nchild, cK = jb.k;
@@ -221,12 +236,12 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
                                 // an older node (id - kCtaCache) right now
                                 const int cslot = nid & (kCtaCache - 1);
                                 vcs_tag[cslot] = 0u;
-                                __threadfence_block();
+                                fence_cta();
                                 sm.c_cs[cslot] = ecs;
-                                __threadfence_block();
+                                fence_cta();
                                 vcs_tag[cslot] = nid;
                             }
-                            __threadfence_block();
+                            fence_cta();
                             vflag[nid] = valid ? 1 : 2;
                         }
                         t.sync();   // shapes are rewritten by the next child
@@ -240,9 +255,10 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
         }
 
         // =================== master warp: queue + tree ==========================================
-        Heap<HS, TILE> heap;
-        heap.sm = sm.heap;
+        HeapSplit heap;
+        heap.sf = hf_addr; heap.sw = hw_addr;
         heap.gl = ar.heap + slot_base;
+        heap.hs = heap_smem;       // <= HS; smaller values only exercise the arena overflow (tests)
         heap.len = 1;
         int n_nodes = 1, n_pops = 0, status = PDMPC_OK;
         unsigned long long hash = 0xcbf29ce484222325ULL;
@@ -259,13 +275,16 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
             sm.c_a[1] = ra; sm.c_tag[1] = 1u; sm.c_cs[1] = rcs; sm.cs_tag[1] = 1u;
             HEnt re;
             re.f = 0.0; re.w = HEnt::pack(1u, 0u, 0u, 0u, (unsigned)trim0);
-            heap.store(0, re);
+            heap.st(0, re);
         }
         t.sync();
 
+        PROF_DECL
         for (;;) {   // GraphSearch.m:53-107
+            PROF_MARK(7);
             if (heap.len == 0) { exhausted = true; break; }               // :57-61
-            const HEnt top = heap.pop(t);
+            const HEnt top = heap.pop(t.lane);
+            PROF_MARK(1);   // heap pop
             const unsigned id = top.id(), par = top.pid();
             const int cK = (int)top.k();
             ++n_pops;
@@ -273,7 +292,8 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
             if (par != 0) {   // eval_edge_exact's answer, computed by a checker warp
                 unsigned f;
                 do { f = vflag[id]; } while (f == 0u);
-                __threadfence_block();
+                fence_cta();
+                PROF_MARK(2);   // wait for the checker's answer
                 if (f != 1u) continue;                                    // :75-77
             }
             if (cK == Hp) { goal = id; break; }                           // :81-90
@@ -290,10 +310,10 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
             if (sm.c_tag[cslot] == id) ca = sm.c_a[cslot]; else ca = na[id];
             {
                 const unsigned t1 = vcs_tag[cslot];
-                __threadfence_block();
+                fence_cta();
                 const volatile double *vcs = reinterpret_cast<const volatile double *>(&sm.c_cs[cslot]);
                 ccs.c = vcs[0]; ccs.s = vcs[1];
-                __threadfence_block();
+                fence_cta();
                 const unsigned t2 = vcs_tag[cslot];
                 if (t1 != id || t2 != id) ccs = ncs[id];   // evicted (or being replaced): HBM arena copy
             }
@@ -310,11 +330,12 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
                     jb.nid0 = (unsigned)(n_nodes + 1); jb.nchild = nchild; jb.sbase = sbase; jb.k = k_exp;
                     jb.terminate = 0;
                 }
-                __threadfence_block();
+                fence_cta();
                 t.sync();
-                named_bar_arrive(1 + (int)(n_jobs % kRing), kThreads);
+                named_bar_arrive(1 + (int)(n_jobs % kRing), kBarThreads);
                 ++n_jobs;
             }
+            PROF_MARK(3);   // node record + job hand-over
             const int to_go = Hp - k_exp;               // :37
             for (int c0 = 0; c0 < nchild; c0 += TILE) {
                 const int ci = c0 + t.lane;
@@ -363,10 +384,13 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
                     he.f = ea.g + eh;                   // GraphSearch.m:102 (weights 1)
                     he.w = HEnt::pack(nid, id, (unsigned)cedge, (unsigned)k_exp, (unsigned)t2);
                 }
-                heap.push_many(he, cnt, t);             // :104, one push per child, in order
+                PROF_MARK(4);   // successor generation
+                heap.push_many(he, cnt, t.lane);        // :104, one push per child, in order
+                PROF_MARK(5);   // heap pushes
             }
             n_nodes += nchild;
         }
+        PROF_FLUSH(o, t.lane == 0);
 
         // ---- release the checkers, then write the results (GraphSearch.m:58-60 / :82-89) ------
         if (t.lane == 0) *vabort = 1;
@@ -376,9 +400,9 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
                 if (__all_sync(0xffffffffu, d + kRing > n_jobs)) break;
             }
             if (t.lane == 0) sm.ring[n_jobs % kRing].terminate = 1;
-            __threadfence_block();
+            fence_cta();
             t.sync();
-            named_bar_arrive(1 + (int)(n_jobs % kRing), kThreads);
+            named_bar_arrive(1 + (int)(n_jobs % kRing), kBarThreads);
         }
         if (status != PDMPC_OK) exhausted = true;
         if (t.lane == 0) {

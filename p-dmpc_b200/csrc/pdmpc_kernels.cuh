@@ -18,12 +18,12 @@
 // Design notes (the search is a serial pop -> check -> expand -> push chain; ncu
 // shows it is bound by the number of warp instructions per pop, so everything
 // here minimises uniform/scalar work per pop):
-//   * the binary heap is walked by the whole tile: one round of loads fetches the
-//     next LV levels under the hole (2+4+..+2^LV contiguous entries), sibling
-//     pairs decide locally (one shfl.xor), one ballot gives the whole path.
-//     Pushes of all children go through a one-round fast path when no child has
-//     to sift up.  The resulting array is identical to what libstdc++'s
-//     sequential routines produce.
+//   * the binary heap (pdmpc_heap_split.cuh): the pop's hole walk is a minimal uniform
+//     loop (one aligned pair load + one compare per level), the moves along the path are
+//     done by the lanes in parallel.  Pushes of all children go through a one-round fast
+//     path when no child has to sift up.  The resulting array is identical to what
+//     libstdc++'s sequential routines produce.  (`Heap` below is the earlier cooperative
+//     4-level look-ahead walk, kept for the microbenchmark: 2.2x slower per pop.)
 //   * heap entries carry (f, id, parent id): everything a pop needs is fetched in
 //     ONE round of independent loads (own record + parent record).
 //   * sin/cos of a node's yaw is computed once, when the node is expanded, and
@@ -354,6 +354,10 @@ struct Heap {
     }
 };
 
+}  // namespace pdmpc
+#include "pdmpc_heap_split.cuh"   // HeapSplit: the layout + pop the kernels use (2x faster pop than Heap)
+namespace pdmpc {
+
 // ---- InterX (InterX.m:63-85,108-110) ---------------------------------------
 // Shape (NE segments, points in shared memory) against the NaN-separated polyline
 // points [lo, hi) of (px, py) (shared or global memory).  Every lane keeps the
@@ -570,7 +574,8 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 
 template <int HS, int SP>
 struct __align__(16) TileSmem {
-    HEnt heap[HS];
+    double hf[HS + 2];                           // heap costs, entry i at hf[i + 1] (pdmpc_heap_split.cuh)
+    unsigned long long hw[HS];                   // heap payloads
     double pts_x[SP], pts_y[SP];                 // staged polylines: [lanelet bounds][obstacle slots 0..Hp]
     double refx[kMaxHp], refy[kMaxHp], vref[kMaxHp];
     double shx[kAreaStride], shy[kAreaStride];   // shape (normal offset)
@@ -596,7 +601,7 @@ struct __align__(16) TileSmem {
 //              tables are staged once per CTA into shared memory by TMA bulk copies
 //              (cp.async.bulk + mbarrier), each warp still runs its own searches.
 #ifndef PDMPC_MIN_CTAS_LAT
-#define PDMPC_MIN_CTAS_LAT 1   // resident one-warp CTAs per SM the latency shape is compiled for (register cap)
+#define PDMPC_MIN_CTAS_LAT 12  // resident one-warp CTAs per SM the latency shape is compiled for (register cap)
 #endif
 template <int HS, int SP, int WARPS, bool SMEM_TABLES>
 __global__ void __launch_bounds__(WARPS *kWarp, WARPS == 1 ? PDMPC_MIN_CTAS_LAT : 1) search_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar,
@@ -651,9 +656,11 @@ __global__ void __launch_bounds__(WARPS *kWarp, WARPS == 1 ? PDMPC_MIN_CTAS_LAT 
     NodeA *__restrict__ na = ar.a + slot_base;
     NodeB *__restrict__ nb = ar.b + slot_base;
     NodeCS *__restrict__ ncs = ar.cs + slot_base;
-    Heap<HS, TILE> heap;
-    heap.sm = sm.heap;
+    HeapSplit heap;
+    heap.sf = shared_base_once(sm.hf);
+    heap.sw = shared_base_once(sm.hw);
     heap.gl = ar.heap + slot_base;
+    heap.hs = HS;
     heap.len = 0;
 
     enum { IDLE = 0, RUN = 1, DONE = 2 };
@@ -768,7 +775,7 @@ __global__ void __launch_bounds__(WARPS *kWarp, WARPS == 1 ? PDMPC_MIN_CTAS_LAT 
                 nb[1] = rb;
                 HEnt re;
                 re.f = 0.0; re.w = HEnt::pack(1u, 0u, 0u, 0u, (unsigned)trim0);
-                heap.store(0, re);
+                heap.st(0, re);
             }
             heap.len = 1;
             sp0 = __ldg(slot + 0); sp1 = __ldg(slot + 1);
@@ -819,7 +826,7 @@ __global__ void __launch_bounds__(WARPS *kWarp, WARPS == 1 ? PDMPC_MIN_CTAS_LAT 
 
         // ---- one iteration of the best-first loop: GraphSearch.m:53-107 ----------
         if (heap.len == 0) { exhausted = true; phase = DONE; continue; }   // :57-61
-        const HEnt top = heap.pop(t);
+        const HEnt top = heap.pop(t.lane);
         PROF_MARK(1);   // heap pop
         const unsigned id = top.id(), par = top.pid();
         const int cK = (int)top.k();
@@ -962,7 +969,7 @@ __global__ void __launch_bounds__(WARPS *kWarp, WARPS == 1 ? PDMPC_MIN_CTAS_LAT 
                 he.w = HEnt::pack(nid, id, (unsigned)cedge, (unsigned)k_exp, (unsigned)t2);
             }
             PROF_MARK(4);   // successor generation
-            heap.push_many(he, cnt, t);             // :104, one push per child, in order
+            heap.push_many(he, cnt, t.lane);        // :104, one push per child, in order
             PROF_MARK(5);   // heap pushes
         }
         n_nodes += nchild;

@@ -107,6 +107,31 @@ def test_lane_shape_hand_over(planner, nodes, pops):
         planner.set_lane_limits(0, 0)
 
 
+@pytest.mark.parametrize("entries", [2, 16, 64, 0])
+def test_cta_shape_heap_spills_to_arena(planner, entries):
+    """Shape 4: whatever part of the queue lives in shared memory (two-level look-ahead walk)
+    or in the HBM arena (single-level walk), the pop order is the oracle's."""
+    mpa, batch = road_records("triple_speed", 8)
+    planner.set_cta_heap_smem(entries)
+    try:
+        info, dev, ref = check(planner, mpa, batch, variants=(4,))
+        st = planner.stats()
+        assert st.total_pops == int(ref.n_pops.sum()) and st.total_nodes == int(ref.n_expanded.sum())
+    finally:
+        planner.set_cta_heap_smem(0)
+
+
+def test_cta_shape_is_the_default_for_one_level(planner):
+    """A batch with at most one search per SM (one computation level of a time step) takes the
+    CTA-per-search shape automatically; many CTAs' worth of searches (more than SMs) still work
+    when the shape is forced (each CTA pulls several searches one after the other)."""
+    mpa, batch = road_records("single_speed", 6)
+    check(planner, mpa, batch.select(np.arange(20)), variants=(0,))
+    check(planner, mpa, batch, variants=(4,))
+    mpa_c, batch_c = circle_records(30)
+    check(planner, mpa_c, batch_c, variants=(4,))
+
+
 def test_lane_shape_single_speed_and_realistic(planner):
     """5-/6-/7-point maneuver areas all run the padded 6-edge InterX of shape 3."""
     for mpa_type, kw in (("single_speed", {}), ("realistic", dict(amount=10, seed=5))):
