@@ -105,10 +105,20 @@ struct pdmpc_handle {
     DBuf b_x0, b_y0, b_yaw0, b_trim0, b_refx, b_refy, b_vref, b_slot, b_poly, b_vx, b_vy, b_plx, b_ply,
         b_lane, b_lx, b_ly, b_llx, b_lly, b_order, b_plxy, b_llxy, b_rng, b_seed;
 
+    // small batches (one computation level of a time step): every input array in ONE pinned
+    // staging buffer -> one H2D copy; every output array in one device block -> one D2H copy
+    DBuf d_in_pack, d_out_pack;
+    void *pin_in = nullptr, *pin_out = nullptr;
+    size_t pin_in_cap = 0, pin_out_cap = 0;
+    cudaEvent_t ev_pack = nullptr;    // completion of the last packed H2D (the pinned buffer is reused)
+    bool pack_in_flight = false;
+    bool out_packed = false;
+    size_t out_off[14] = {};          // byte offsets of the output arrays (+ counters) inside d_out_pack
+    size_t out_bytes = 0;
+
     // outputs
     OutDev out{};
-    DBuf o_status, o_exh, o_nexp, o_npops, o_hash, o_trims, o_path, o_ypred, o_g, o_h, o_snp, o_sx, o_sy,
-        o_counters, work_counter;
+    DBuf work_counter;
 
     // arena
     ArenaDev arena{};
@@ -169,6 +179,7 @@ int pdmpc_create(int device_id, pdmpc_handle **out) {
         return fail(nullptr, PDMPC_ERR_CUDA, msg);
     }
     for (auto &ev : h->ev) cudaEventCreate(&ev);
+    cudaEventCreateWithFlags(&h->ev_pack, cudaEventDisableTiming);
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device_id);
     int occ = 0;
     e = cudaFuncSetAttribute(KERNEL_LAT, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem));
@@ -198,10 +209,13 @@ int pdmpc_destroy(pdmpc_handle *h) {
                     &h->la_heap, &h->ov_count, &h->ov_list, &h->work_counter2, &h->b_x0, &h->b_y0, &h->b_yaw0, &h->b_trim0,
                     &h->b_refx, &h->b_refy, &h->b_vref, &h->b_slot, &h->b_poly, &h->b_vx, &h->b_vy,
                     &h->b_plx, &h->b_ply, &h->b_lane, &h->b_lx, &h->b_ly, &h->b_llx, &h->b_lly,
-                    &h->o_status, &h->o_exh, &h->o_nexp, &h->o_npops, &h->o_hash, &h->o_trims, &h->o_path,
-                    &h->o_ypred, &h->o_g, &h->o_h, &h->o_snp, &h->o_sx, &h->o_sy, &h->o_counters,
                     &h->work_counter, &h->b_seed, &h->a_a, &h->a_b, &h->a_cs, &h->a_heap, &h->t_ids, &h->t_n};
     for (DBuf *b : bufs) b->release();
+    h->d_in_pack.release();
+    h->d_out_pack.release();
+    if (h->pin_in) cudaFreeHost(h->pin_in);
+    if (h->pin_out) cudaFreeHost(h->pin_out);
+    if (h->ev_pack) cudaEventDestroy(h->ev_pack);
     for (auto &ev : h->ev)
         if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(h->stream);
@@ -438,39 +452,57 @@ static int validate_batch(pdmpc_handle *h, const pdmpc_batch_in *in) {
     return PDMPC_OK;
 }
 
+constexpr size_t kPackLimit = 1u << 20;   // batches whose arrays total at most 1 MiB take the packed path
+
+static int ensure_pinned(pdmpc_handle *h, void **p, size_t *cap, size_t bytes) {
+    if (bytes <= *cap) return PDMPC_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr;
+    *cap = 0;
+    const size_t want = bytes + bytes / 4 + 4096;
+    if (cudaHostAlloc(p, want, cudaHostAllocDefault) != cudaSuccess) {
+        *p = nullptr;
+        return fail(h, PDMPC_ERR_ALLOC, "pinned staging buffer allocation failed");
+    }
+    *cap = want;
+    return PDMPC_OK;
+}
+
+// All output arrays live in one device block (d_out_pack) so that a small batch needs a single
+// device->host copy; the order is the one of pdmpc_batch_out, the counters come last.
 static int ensure_outputs(pdmpc_handle *h, int n) {
-    const int Hp = h->mpa.Hp;
+    const size_t Hp = (size_t)h->mpa.Hp;
     const size_t n1 = std::max(n, 1);
-    CU_TRY(h, h->o_status.reserve(n1 * sizeof(int)));
-    CU_TRY(h, h->o_exh.reserve(n1));
-    CU_TRY(h, h->o_nexp.reserve(n1 * sizeof(int)));
-    CU_TRY(h, h->o_npops.reserve(n1 * sizeof(int)));
-    CU_TRY(h, h->o_hash.reserve(n1 * sizeof(uint64_t)));
-    CU_TRY(h, h->o_trims.reserve(n1 * (Hp + 1) * sizeof(int)));
-    CU_TRY(h, h->o_path.reserve(n1 * (Hp + 1) * sizeof(int)));
-    CU_TRY(h, h->o_ypred.reserve(n1 * Hp * 3 * sizeof(double)));
-    CU_TRY(h, h->o_g.reserve(n1 * (Hp + 1) * sizeof(double)));
-    CU_TRY(h, h->o_h.reserve(n1 * (Hp + 1) * sizeof(double)));
-    CU_TRY(h, h->o_snp.reserve(n1 * Hp * sizeof(int)));
-    CU_TRY(h, h->o_sx.reserve(n1 * Hp * PDMPC_AREA_STRIDE * sizeof(double)));
-    CU_TRY(h, h->o_sy.reserve(n1 * Hp * PDMPC_AREA_STRIDE * sizeof(double)));
-    CU_TRY(h, h->o_counters.reserve(16 * sizeof(unsigned long long)));
+    const size_t sizes[14] = {
+        n1 * sizeof(int), n1, n1 * sizeof(int), n1 * sizeof(int), n1 * sizeof(uint64_t),
+        n1 * (Hp + 1) * sizeof(int), n1 * (Hp + 1) * sizeof(int), n1 * Hp * 3 * sizeof(double),
+        n1 * (Hp + 1) * sizeof(double), n1 * (Hp + 1) * sizeof(double), n1 * Hp * sizeof(int),
+        n1 * Hp * PDMPC_AREA_STRIDE * sizeof(double), n1 * Hp * PDMPC_AREA_STRIDE * sizeof(double),
+        16 * sizeof(unsigned long long)};
+    size_t off = 0;
+    for (int i = 0; i < 14; ++i) {
+        h->out_off[i] = off;
+        off = (off + sizes[i] + 15) / 16 * 16;
+    }
+    h->out_bytes = off;
+    CU_TRY(h, h->d_out_pack.reserve(off));
     CU_TRY(h, h->work_counter.reserve(sizeof(unsigned)));
+    unsigned char *base = h->d_out_pack.as<unsigned char>();
     OutDev &o = h->out;
-    o.status = h->o_status.as<int>();
-    o.is_exhausted = h->o_exh.as<uint8_t>();
-    o.n_expanded = h->o_nexp.as<int>();
-    o.n_pops = h->o_npops.as<int>();
-    o.pop_hash = h->o_hash.as<unsigned long long>();
-    o.trims = h->o_trims.as<int>();
-    o.tree_path = h->o_path.as<int>();
-    o.y_predicted = h->o_ypred.as<double>();
-    o.g_path = h->o_g.as<double>();
-    o.h_path = h->o_h.as<double>();
-    o.shape_npts = h->o_snp.as<int>();
-    o.shape_x = h->o_sx.as<double>();
-    o.shape_y = h->o_sy.as<double>();
-    o.counters = h->o_counters.as<unsigned long long>();
+    o.status = reinterpret_cast<int *>(base + h->out_off[0]);
+    o.is_exhausted = reinterpret_cast<uint8_t *>(base + h->out_off[1]);
+    o.n_expanded = reinterpret_cast<int *>(base + h->out_off[2]);
+    o.n_pops = reinterpret_cast<int *>(base + h->out_off[3]);
+    o.pop_hash = reinterpret_cast<unsigned long long *>(base + h->out_off[4]);
+    o.trims = reinterpret_cast<int *>(base + h->out_off[5]);
+    o.tree_path = reinterpret_cast<int *>(base + h->out_off[6]);
+    o.y_predicted = reinterpret_cast<double *>(base + h->out_off[7]);
+    o.g_path = reinterpret_cast<double *>(base + h->out_off[8]);
+    o.h_path = reinterpret_cast<double *>(base + h->out_off[9]);
+    o.shape_npts = reinterpret_cast<int *>(base + h->out_off[10]);
+    o.shape_x = reinterpret_cast<double *>(base + h->out_off[11]);
+    o.shape_y = reinterpret_cast<double *>(base + h->out_off[12]);
+    o.counters = reinterpret_cast<unsigned long long *>(base + h->out_off[13]);
     return PDMPC_OK;
 }
 
@@ -490,39 +522,12 @@ int pdmpc_stage_batch(pdmpc_handle *h, const pdmpc_batch_in *in) {
     h->stats.h2d_bytes = 0;
     CU_TRY(h, cudaEventRecord(h->ev[0], h->stream));
     static const int zero1[1] = {0};
-    UP(h, h->b_x0, in->x0, n);
-    UP(h, h->b_y0, in->y0, n);
-    UP(h, h->b_yaw0, in->yaw0, n);
-    UP(h, h->b_trim0, in->trim0, n);
-    UP(h, h->b_refx, in->ref_x, (size_t)n * Hp);
-    UP(h, h->b_refy, in->ref_y, (size_t)n * Hp);
-    UP(h, h->b_vref, in->v_ref, (size_t)n * Hp);
-    UP(h, h->b_slot, n ? in->slot_ptr : zero1, ns + 1);
-    UP(h, h->b_poly, n ? in->poly_ptr : zero1, (size_t)np + 1);
-    UP(h, h->b_vx, in->vert_x, nv);
-    UP(h, h->b_vy, in->vert_y, nv);
-    UP(h, h->b_lane, n ? in->lane_ptr : zero1, (size_t)2 * n + 1);
-    UP(h, h->b_lx, in->lane_x, nl);
-    UP(h, h->b_ly, in->lane_y, nl);
-    CU_TRY(h, cudaEventRecord(h->ev[1], h->stream));
-    h->timing_pending_h2d = true;
-
-    BatchDev &b = h->batch;
-    b.n = n; b.checker = in->checker; b.dt = in->dt_seconds;
-    b.x0 = h->b_x0.as<double>(); b.y0 = h->b_y0.as<double>(); b.yaw0 = h->b_yaw0.as<double>();
-    b.trim0 = h->b_trim0.as<int>();
-    b.ref_x = h->b_refx.as<double>(); b.ref_y = h->b_refy.as<double>(); b.v_ref = h->b_vref.as<double>();
-    b.slot_ptr = h->b_slot.as<int>(); b.poly_ptr = h->b_poly.as<int>();
-    b.vert_x = h->b_vx.as<double>(); b.vert_y = h->b_vy.as<double>();
-    b.lane_ptr = h->b_lane.as<int>(); b.lane_x = h->b_lx.as<double>(); b.lane_y = h->b_ly.as<double>();
-    b.pl_x = b.pl_y = b.ll_x = b.ll_y = nullptr;
-    b.pl_xy = b.ll_xy = nullptr;
-    b.rng = nullptr;
     // work order: searches with the most obstacle polygons first (they are the ones most
     // likely to run long / exhaust), so the tail of the batch is made of short searches
-    b.order = nullptr;
+    std::vector<int> order;
     if (n > 1) {
-        std::vector<int> key(n), order(n);
+        std::vector<int> key(n);
+        order.resize(n);
         int kmax = 0;
         for (int i = 0; i < n; ++i) {
             key[i] = in->slot_ptr[(size_t)(i + 1) * (Hp + 1)] - in->slot_ptr[(size_t)i * (Hp + 1)];
@@ -532,11 +537,66 @@ int pdmpc_stage_batch(pdmpc_handle *h, const pdmpc_batch_in *in) {
         for (int i = 0; i < n; ++i) cnt[kmax - key[i] + 1]++;          // counting sort, descending key, stable
         for (int k = 0; k <= kmax; ++k) cnt[k + 1] += cnt[k];
         for (int i = 0; i < n; ++i) order[cnt[kmax - key[i]]++] = i;
-        int rc2 = upload(h, h->b_order, order.data(), (size_t)n);
-        if (rc2 != PDMPC_OK) return rc2;
-        CU_TRY(h, cudaStreamSynchronize(h->stream));
-        b.order = h->b_order.as<int>();
     }
+    const void *srcs[15] = {in->x0, in->y0, in->yaw0, in->trim0, in->ref_x, in->ref_y, in->v_ref,
+                            n ? in->slot_ptr : zero1, n ? in->poly_ptr : zero1, in->vert_x, in->vert_y,
+                            n ? in->lane_ptr : zero1, in->lane_x, in->lane_y, order.data()};
+    const size_t nbytes[15] = {n * sizeof(double), n * sizeof(double), n * sizeof(double), n * sizeof(int),
+                               (size_t)n * Hp * sizeof(double), (size_t)n * Hp * sizeof(double),
+                               (size_t)n * Hp * sizeof(double), (ns + 1) * sizeof(int), ((size_t)np + 1) * sizeof(int),
+                               (size_t)nv * sizeof(double), (size_t)nv * sizeof(double),
+                               ((size_t)2 * n + 1) * sizeof(int), (size_t)nl * sizeof(double),
+                               (size_t)nl * sizeof(double), order.size() * sizeof(int)};
+    size_t in_off[15], in_total = 0;
+    for (int i = 0; i < 15; ++i) {
+        in_off[i] = in_total;
+        in_total = (in_total + nbytes[i] + 15) / 16 * 16;
+    }
+    const void *dptr[15];
+    if (in_total <= kPackLimit) {
+        // one pinned staging block, one host->device copy (a level of a time step is a few KB:
+        // fifteen separate pageable copies cost more than the search itself)
+        if (h->pack_in_flight) {
+            CU_TRY(h, cudaEventSynchronize(h->ev_pack));
+            h->pack_in_flight = false;
+        }
+        int rc2 = ensure_pinned(h, &h->pin_in, &h->pin_in_cap, std::max<size_t>(in_total, 16));
+        if (rc2 != PDMPC_OK) return rc2;
+        CU_TRY(h, h->d_in_pack.reserve(std::max<size_t>(in_total, 16)));
+        unsigned char *pin = static_cast<unsigned char *>(h->pin_in);
+        for (int i = 0; i < 15; ++i) {
+            if (nbytes[i]) memcpy(pin + in_off[i], srcs[i], nbytes[i]);
+            dptr[i] = h->d_in_pack.as<unsigned char>() + in_off[i];
+        }
+        if (in_total) CU_TRY(h, cudaMemcpyAsync(h->d_in_pack.p, pin, in_total, cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(h, cudaEventRecord(h->ev_pack, h->stream));
+        h->pack_in_flight = true;
+        h->stats.h2d_bytes += (int64_t)in_total;
+    } else {
+        DBuf *bufs[15] = {&h->b_x0, &h->b_y0, &h->b_yaw0, &h->b_trim0, &h->b_refx, &h->b_refy, &h->b_vref, &h->b_slot,
+                          &h->b_poly, &h->b_vx, &h->b_vy, &h->b_lane, &h->b_lx, &h->b_ly, &h->b_order};
+        for (int i = 0; i < 15; ++i) {
+            int rc2 = upload(h, *bufs[i], static_cast<const unsigned char *>(srcs[i]), nbytes[i]);
+            if (rc2 != PDMPC_OK) return rc2;
+            dptr[i] = bufs[i]->p;
+        }
+        CU_TRY(h, cudaStreamSynchronize(h->stream));   // `order` goes out of scope; callers may reuse their buffers
+    }
+    CU_TRY(h, cudaEventRecord(h->ev[1], h->stream));
+    h->timing_pending_h2d = true;
+
+    BatchDev &b = h->batch;
+    b.n = n; b.checker = in->checker; b.dt = in->dt_seconds;
+    b.x0 = (const double *)dptr[0]; b.y0 = (const double *)dptr[1]; b.yaw0 = (const double *)dptr[2];
+    b.trim0 = (const int *)dptr[3];
+    b.ref_x = (const double *)dptr[4]; b.ref_y = (const double *)dptr[5]; b.v_ref = (const double *)dptr[6];
+    b.slot_ptr = (const int *)dptr[7]; b.poly_ptr = (const int *)dptr[8];
+    b.vert_x = (const double *)dptr[9]; b.vert_y = (const double *)dptr[10];
+    b.lane_ptr = (const int *)dptr[11]; b.lane_x = (const double *)dptr[12]; b.lane_y = (const double *)dptr[13];
+    b.order = n > 1 ? (const int *)dptr[14] : nullptr;
+    b.pl_x = b.pl_y = b.ll_x = b.ll_y = nullptr;
+    b.pl_xy = b.ll_xy = nullptr;
+    b.rng = nullptr;
     h->stats.kernel_launches = 0;
     if (in->checker == PDMPC_CHECKER_INTERX) {
         // NaN-separated polylines (vectorize_all_obstacles.m) built on the device
@@ -556,7 +616,7 @@ int pdmpc_stage_batch(pdmpc_handle *h, const pdmpc_batch_in *in) {
         }
         b.pl_xy = b.ll_xy = nullptr;
         b.rng = nullptr;
-        if (h->lanes_ok && n) {
+        if (h->lanes_ok && n && h->variant_mode == 3) {   // only the lane-per-search shape reads these
             CU_TRY(h, h->b_plxy.reserve(((size_t)nv + np + 1) * sizeof(double2)));
             CU_TRY(h, h->b_llxy.reserve(((size_t)nl + 2 * n + 1) * sizeof(double2)));
             CU_TRY(h, h->b_rng.reserve((size_t)n * (Hp + 2) * sizeof(int)));
@@ -580,9 +640,8 @@ int pdmpc_stage_batch(pdmpc_handle *h, const pdmpc_batch_in *in) {
     h->n_polys = np; h->n_verts = nv; h->n_lane = nl;
     rc = ensure_outputs(h, n);
     if (rc != PDMPC_OK) return rc;
-    // Source buffers are caller-owned pageable/pinned memory: make the staging
-    // copies complete before returning so the caller may reuse them.
-    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    // (caller-owned source buffers were either copied into the pinned block or their copies
+    // have completed above: the caller may reuse them)
     h->staged = true;
     return PDMPC_OK;
 }
@@ -633,7 +692,7 @@ static int ensure_lane_arena(pdmpc_handle *h, int slots) {
 static int launch_search(pdmpc_handle *h, const TraceDev &tr) {
     const int n = h->batch.n;
     CU_TRY(h, cudaSetDevice(h->device));
-    CU_TRY(h, cudaMemsetAsync(h->o_counters.p, 0, 16 * sizeof(unsigned long long), h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->out.counters, 0, 16 * sizeof(unsigned long long), h->stream));
     CU_TRY(h, cudaMemsetAsync(h->work_counter.p, 0, sizeof(unsigned), h->stream));
     if (n == 0) return PDMPC_OK;
     const bool lanes_possible = h->lanes_ok && h->batch.checker == PDMPC_CHECKER_INTERX && h->batch.rng;
@@ -743,24 +802,38 @@ int pdmpc_fetch_staged(pdmpc_handle *h, pdmpc_batch_out *out) {
     CU_TRY(h, cudaSetDevice(h->device));
     const size_t n = (size_t)h->batch.n, Hp = (size_t)h->mpa.Hp;
     h->stats.d2h_bytes = 0;
-    CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
-    DOWN(h, out->status, h->o_status, n);
-    DOWN(h, out->is_exhausted, h->o_exh, n);
-    DOWN(h, out->n_expanded, h->o_nexp, n);
-    DOWN(h, out->n_pops, h->o_npops, n);
-    DOWN(h, out->pop_hash, h->o_hash, n);
-    DOWN(h, out->trims, h->o_trims, n * (Hp + 1));
-    DOWN(h, out->tree_path, h->o_path, n * (Hp + 1));
-    DOWN(h, out->y_predicted, h->o_ypred, n * Hp * 3);
-    DOWN(h, out->g_path, h->o_g, n * (Hp + 1));
-    DOWN(h, out->h_path, h->o_h, n * (Hp + 1));
-    DOWN(h, out->shape_npts, h->o_snp, n * Hp);
-    DOWN(h, out->shape_x, h->o_sx, n * Hp * PDMPC_AREA_STRIDE);
-    DOWN(h, out->shape_y, h->o_sy, n * Hp * PDMPC_AREA_STRIDE);
     unsigned long long counters[16] = {0};
-    CU_TRY(h, cudaMemcpyAsync(counters, h->o_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
-    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    void *dsts[13] = {out->status, out->is_exhausted, out->n_expanded, out->n_pops, out->pop_hash, out->trims,
+                      out->tree_path, out->y_predicted, out->g_path, out->h_path, out->shape_npts, out->shape_x,
+                      out->shape_y};
+    const size_t bytes[13] = {n * sizeof(int), n, n * sizeof(int), n * sizeof(int), n * sizeof(uint64_t),
+                              n * (Hp + 1) * sizeof(int), n * (Hp + 1) * sizeof(int), n * Hp * 3 * sizeof(double),
+                              n * (Hp + 1) * sizeof(double), n * (Hp + 1) * sizeof(double), n * Hp * sizeof(int),
+                              n * Hp * PDMPC_AREA_STRIDE * sizeof(double), n * Hp * PDMPC_AREA_STRIDE * sizeof(double)};
+    const unsigned char *dbase = h->d_out_pack.as<unsigned char>();
+    CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
+    if (h->out_bytes <= kPackLimit) {
+        // one copy of the whole output block into pinned memory, then scatter on the host
+        int rc = ensure_pinned(h, &h->pin_out, &h->pin_out_cap, h->out_bytes);
+        if (rc != PDMPC_OK) return rc;
+        CU_TRY(h, cudaMemcpyAsync(h->pin_out, dbase, h->out_bytes, cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        const unsigned char *src = static_cast<const unsigned char *>(h->pin_out);
+        for (int i = 0; i < 13; ++i)
+            if (dsts[i] && bytes[i]) memcpy(dsts[i], src + h->out_off[i], bytes[i]);
+        memcpy(counters, src + h->out_off[13], sizeof(counters));
+        h->stats.d2h_bytes = (int64_t)h->out_bytes;
+    } else {
+        for (int i = 0; i < 13; ++i)
+            if (dsts[i] && bytes[i]) {
+                CU_TRY(h, cudaMemcpyAsync(dsts[i], dbase + h->out_off[i], bytes[i], cudaMemcpyDeviceToHost, h->stream));
+                h->stats.d2h_bytes += (int64_t)bytes[i];
+            }
+        CU_TRY(h, cudaMemcpyAsync(counters, dbase + h->out_off[13], sizeof(counters), cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+    }
     h->timing_pending_d2h = true;
     h->stats.total_pops = (int64_t)counters[0];
     h->stats.total_nodes = (int64_t)counters[1];
@@ -798,7 +871,7 @@ int pdmpc_mcts_run_staged(pdmpc_handle *h, const pdmpc_mcts_params *prm) {
     if (h->max_branch > PDMPC_MCTS_MAX_BRANCH)
         return fail(h, PDMPC_ERR_BAD_INPUT, "mcts: branching factor of the MPA exceeds PDMPC_MCTS_MAX_BRANCH");
     CU_TRY(h, cudaSetDevice(h->device));
-    CU_TRY(h, cudaMemsetAsync(h->o_counters.p, 0, 16 * sizeof(unsigned long long), h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->out.counters, 0, 16 * sizeof(unsigned long long), h->stream));
     CU_TRY(h, cudaMemsetAsync(h->work_counter.p, 0, sizeof(unsigned), h->stream));
     h->stats.kernel_launches = 0;
     if (n == 0) return PDMPC_OK;
