@@ -12,6 +12,8 @@
 //   [is_exhausted, n_expanded, trims, y_pred, g_path, h_path, shapes] =
 //       mex(PLAN, h, x0 [1x3], trim, ref [Hp x 2], v_ref [1 x Hp], obstacles {n_s},
 //           dynamic_obstacle_area {n_d x Hp}, left [2 x nL], right [2 x nR], checker, dt)
+//   [same outputs] = mex(PLAN_SAMPLED, h, <the ten PLAN arguments>, seed, n_expansions_max)
+//       MonteCarloTreeSearch.run_optimizer: seed = time_step + vehicle_index (MonteCarloTreeSearch.m:31)
 //   s = mex(STATS, h)
 #include <cstdint>
 #include <cstring>
@@ -23,7 +25,7 @@
 
 namespace {
 
-enum Command { CREATE = 0, DESTROY = 1, UPLOAD_MPA = 2, PLAN = 3, STATS = 4 };
+enum Command { CREATE = 0, DESTROY = 1, UPLOAD_MPA = 2, PLAN = 3, STATS = 4, PLAN_SAMPLED = 5 };
 
 std::vector<pdmpc_handle *> g_handles;   // released at `clear mex` (HighLevelController.m:284-303)
 bool g_at_exit_registered = false;
@@ -125,7 +127,9 @@ void upload_mpa(pdmpc_handle *h, const mxArray *trans, const mxArray *maneuvers)
     check(h, pdmpc_upload_mpa(h, &d), "pdmpc_upload_mpa");
 }
 
-void plan(pdmpc_handle *h, int nlhs, mxArray *plhs[], const mxArray *prhs[]) {
+// PLAN (sampled == false): GraphSearch; PLAN_SAMPLED: MonteCarloTreeSearch with two more
+// arguments, the RandStream seed (time_step + vehicle_index) and n_expansions_max.
+void plan(pdmpc_handle *h, int nlhs, mxArray *plhs[], const mxArray *prhs[], bool sampled) {
     const mxArray *x0 = prhs[2], *ref = prhs[4], *vref = prhs[5], *obst = prhs[6], *dyn = prhs[7];
     const mxArray *left = prhs[8], *right = prhs[9];
     const int Hp = static_cast<int>(mxGetNumberOfElements(vref));
@@ -200,7 +204,15 @@ void plan(pdmpc_handle *h, int nlhs, mxArray *plhs[], const mxArray *prhs[]) {
     out.shape_npts = shape_npts.data();
     out.shape_x = sx.data();
     out.shape_y = sy.data();
-    check(h, pdmpc_plan_batch(h, &in, &out), "pdmpc_plan_batch");
+    if (sampled) {
+        const uint32_t seed = static_cast<uint32_t>(mxGetScalar(prhs[12]));
+        pdmpc_mcts_params prm;
+        prm.n_expansions_max = static_cast<int32_t>(mxGetScalar(prhs[13]));
+        prm.seed = &seed;
+        check(h, pdmpc_mcts_plan_batch(h, &in, &prm, &out), "pdmpc_mcts_plan_batch");
+    } else {
+        check(h, pdmpc_plan_batch(h, &in, &out), "pdmpc_plan_batch");
+    }
     if (status != PDMPC_OK)   // e.g. PDMPC_ERR_CAPACITY: loud, never a silently truncated search
         fail("pdmpc:search", "search failed with status " + std::to_string(status));
 
@@ -274,7 +286,11 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         return;
     case PLAN:
         if (nrhs < 12) fail("pdmpc:usage", "PLAN needs 12 arguments");
-        plan(h, nlhs, plhs, prhs);
+        plan(h, nlhs, plhs, prhs, false);
+        return;
+    case PLAN_SAMPLED:
+        if (nrhs < 14) fail("pdmpc:usage", "PLAN_SAMPLED needs 14 arguments");
+        plan(h, nlhs, plhs, prhs, true);
         return;
     case STATS: {
         pdmpc_stats st;

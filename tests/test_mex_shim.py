@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import mexfake
-from helpers import GOLDEN_CASES, load_golden
+from helpers import GOLDEN_CASES, load_golden, load_golden_mcts
 from test_oracle_cpu import _iters_from_batch
 
 
@@ -33,6 +33,10 @@ def test_matlab_side_sources_present():
     assert "classdef GraphSearchCuda < OptimizerInterface" in src
     assert "function info = run_optimizer(obj, ~, iter, mpa, options, ~)" in src
     assert "create_control_results_info_from_mex" in src
+    smp = open(os.path.join(mexfake.ROOT, "p-dmpc_b200", "matlab", "MonteCarloTreeSearchCuda.m")).read()
+    assert "classdef MonteCarloTreeSearchCuda < OptimizerInterface" in smp
+    assert "function info_v = run_optimizer(obj, vehicle_index, iter, mpa, options, time_step)" in smp
+    assert "time_step + vehicle_index" in smp
     comp = open(os.path.join(mexfake.ROOT, "p-dmpc_b200", "matlab", "compile_pdmpc_b200.m")).read()
     assert "mex(" in comp and "pdmpc_b200_mex.cpp" in comp
 
@@ -66,6 +70,33 @@ def test_mex_path_matches_golden(matlab, name):
                     assert np.array_equal(shapes[k][0].view(np.uint64), exp.shape_x[i, k, :n].view(np.uint64))
         (st,) = matlab.call(1, mexfake.STATS, float(h), raw=True)
         assert matlab.field(st, "total_pops").reshape(-1)[0] >= 1
+    finally:
+        matlab.call(0, mexfake.DESTROY, float(h))
+        matlab.clear_mex()
+
+
+@pytest.mark.gpu
+def test_mex_sampled_path_matches_golden(matlab):
+    """PLAN_SAMPLED (MonteCarloTreeSearchCuda.m) through the shim against the committed fixture."""
+    name = "road_interx_triple_speed"
+    mpa, batch, _ = load_golden(name)
+    seeds, n_max, exp = load_golden_mcts(name)
+    (h,) = matlab.call(1, mexfake.CREATE, 0.0)
+    try:
+        trans, man = mexfake.matlab_mpa(mpa)
+        matlab.call(0, mexfake.UPLOAD_MPA, float(h), trans, man)
+        for i in range(0, batch.n, 7):
+            it = _iters_from_batch(batch, i)
+            exh, n_exp, trims, ypred, g, hh, shapes = matlab.call(
+                7, mexfake.PLAN_SAMPLED, float(h), it.x0[:3], float(it.trim_indices), it.reference_trajectory_points,
+                it.v_ref, list(it.obstacles), [list(r) for r in it.dynamic_obstacle_area] or [],
+                it.predicted_lanelet_boundary[0], it.predicted_lanelet_boundary[1], float(batch.checker),
+                float(batch.dt_seconds), float(seeds[i]), float(n_max))
+            assert exh == bool(exp.is_exhausted[i]) and int(np.asarray(n_exp).reshape(-1)[0]) == exp.n_expanded[i]
+            if not exh:
+                assert trims.reshape(-1).astype(int).tolist() == exp.trims[i].tolist()
+                assert np.array_equal(ypred.T.view(np.uint64), exp.y_predicted[i].view(np.uint64))
+                assert g.reshape(-1)[-1] == exp.g_path[i, -1]
     finally:
         matlab.call(0, mexfake.DESTROY, float(h))
         matlab.clear_mex()

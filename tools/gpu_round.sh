@@ -13,6 +13,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 2 --warmup 1 > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
 REC=$(ls build/bench_triple_speed_20v_*s_35t_seed1.npz | head -1)
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:search_kernel -s 1 -c 1 \
-    -o gpurun_out/prof_search_${TAG} -f python tools/profile_batch.py $REC 2 1 2 > gpurun_out/prof_search_${TAG}.log 2>&1
+    -o gpurun_out/prof_search_${TAG} -f python tools/profile_batch.py $REC 2 1 0 > gpurun_out/prof_search_${TAG}.log 2>&1
 tail -5 gpurun_out/prof_search_${TAG}.log
 ls -la gpurun_out
