@@ -223,9 +223,19 @@ void oracle_pq_push(oracle_pq *q, int64_t id, double value) {
     q->a[q->len++] = e;                       /* c.push_back(x) */
     pq_push_heap(q->a, q->len - 1, 0, e);     /* std::push_heap */
 }
+/* diagnostic: pops whose minimum was not unique (a child of the root had the same value) */
+static int64_t g_tie_pops = 0;
+int64_t oracle_tie_pops(int reset) {
+    int64_t v = __atomic_load_n(&g_tie_pops, __ATOMIC_RELAXED);
+    if (reset) __atomic_store_n(&g_tie_pops, 0, __ATOMIC_RELAXED);
+    return v;
+}
+
 int64_t oracle_pq_pop(oracle_pq *q, double *value) {
     if (q->len == 0) return -1;               /* ...mex.cpp:87-94 */
     pq_entry top = q->a[0];
+    if ((q->len > 1 && q->a[1].val == top.val) || (q->len > 2 && q->a[2].val == top.val))
+        __atomic_fetch_add(&g_tie_pops, 1, __ATOMIC_RELAXED);
     if (q->len > 1) {                         /* std::pop_heap */
         pq_entry last = q->a[q->len - 1];
         q->a[q->len - 1] = q->a[0];

@@ -57,6 +57,8 @@ void oracle_pq_free(oracle_pq *q);
 void oracle_pq_push(oracle_pq *q, int64_t id, double value);
 int64_t oracle_pq_pop(oracle_pq *q, double *value); /* -1 when empty */
 int64_t oracle_pq_size(const oracle_pq *q);
+/* diagnostic: number of pops (since the last reset) whose minimum was not unique */
+int64_t oracle_tie_pops(int reset);
 
 /* GraphSearch.do_graph_search for every search of the batch, n_threads host
  * threads (dynamic chunks of 16 searches).  Optional trace: if pop_trace != NULL it

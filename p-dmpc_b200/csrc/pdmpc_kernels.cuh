@@ -656,12 +656,23 @@ __global__ void __launch_bounds__(WARPS *kWarp, WARPS == 1 ? PDMPC_MIN_CTAS_LAT 
     NodeA *__restrict__ na = ar.a + slot_base;
     NodeB *__restrict__ nb = ar.b + slot_base;
     NodeCS *__restrict__ ncs = ar.cs + slot_base;
+#ifdef PDMPC_COOP_HEAP   // comparison builds only: the earlier cooperative look-ahead heap
+    struct CoopHeap : Heap<HS, TILE> {
+        __device__ __forceinline__ void st(int i, const HEnt &e) { this->store(i, e); }
+        __device__ __forceinline__ HEnt pop(int) { Tile<TILE> tt; tt.shift = 0; tt.lane = threadIdx.x % kWarp; tt.mask = 0xffffffffu; return Heap<HS, TILE>::pop(tt); }
+        __device__ __forceinline__ void push_many(const HEnt &m_, int c_, int) { Tile<TILE> tt; tt.shift = 0; tt.lane = threadIdx.x % kWarp; tt.mask = 0xffffffffu; Heap<HS, TILE>::push_many(m_, c_, tt); }
+    } heap;
+    heap.sm = reinterpret_cast<HEnt *>(sm.hf);
+    heap.gl = ar.heap + slot_base;
+    heap.len = 0;
+#else
     HeapSplit heap;
     heap.sf = shared_base_once(sm.hf);
     heap.sw = shared_base_once(sm.hw);
     heap.gl = ar.heap + slot_base;
     heap.hs = HS;
     heap.len = 0;
+#endif
 
     enum { IDLE = 0, RUN = 1, DONE = 2 };
     int phase = IDLE;

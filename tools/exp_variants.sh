@@ -7,5 +7,4 @@ mkdir -p gpurun_out
 for lib in build/libs/*.so; do
   echo "### $lib"
   PDMPC_LIB=$lib python tools/profile_batch.py $REC 3 $REPS 1 | tail -2
-  PDMPC_LIB=$lib python tools/profile_longest.py $REC | tail -2
 done
