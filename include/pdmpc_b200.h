@@ -141,7 +141,8 @@ typedef struct pdmpc_batch_out {
     uint8_t *is_exhausted;  /* [n] info.is_exhausted */
     int32_t *n_expanded;    /* [n] info.n_expanded == tree.size() at exit (GraphSearch.m:58,89) */
     int32_t *n_pops;        /* [n] number of pq.pop() that returned a node */
-    uint64_t *pop_hash;     /* [n] FNV-1a over the popped node ids, in pop order (parity trace) */
+    uint64_t *pop_hash;     /* [n] FNV-1a over the popped node ids, in pop order (parity trace; launch shape 5:
+                             *     over the popped ids that passed their edge check, see pdmpc_set_variant) */
     int32_t *trims;         /* [n*(Hp+1)] current_and_predicted_trims, 1-based; zeros after col 1 if exhausted */
     int32_t *tree_path;     /* [n*(Hp+1)] node ids root..goal in the full tree; zeros if exhausted */
     double *y_predicted;    /* [n*Hp*3] (x,y,yaw) per step; NaN if exhausted */
@@ -164,7 +165,8 @@ typedef struct pdmpc_stats {
     int64_t total_nodes;
     int64_t total_obstacle_cols; /* sum over pops of (V_k + L) columns tested */
     int32_t kernel_launches;
-    int32_t handed_over;     /* shape 3: searches the threads handed to the warp-per-search stage */
+    int32_t handed_over;     /* shape 3: searches the threads handed to the warp-per-search stage;
+                              * shape 5: searches re-run with the exact queue after a non-unique minimum */
     double lanes_ms;         /* shape 3: CUDA-event time of the first (lane-per-search) launch alone */
 } pdmpc_stats;
 
@@ -188,7 +190,14 @@ int pdmpc_set_node_capacity(pdmpc_handle *h, int32_t max_nodes_per_search);
  * in a second launch; falls back to 2 for SAT batches), 4 = cta (one 13-warp CTA per search: a
  * master warp owns queue and tree, checker warps validate the children of every expansion
  * ahead of their pop; chosen automatically for batches of at most one search per SM; falls
- * back to 1 when the full search tree of the MPA exceeds 32768 nodes).  Results do not depend on it. */
+ * back to 1 when the full search tree of the MPA exceeds 32768 nodes), 5 = shape 4 with a
+ * VALID-ONLY QUEUE: children whose edge check failed are not pushed; before every pop the
+ * minimum must be unique, otherwise the search is re-run with the exact queue (p-dmpc_b200/csrc/
+ * pdmpc_cta.cuh has the argument why every output then equals the reference's); opt-in only — it
+ * trades the pops of invalid nodes for waiting on the checkers and measured no faster than shape 4.
+ * Results do not depend on the shape, with ONE exception: pop_hash, a parity trace that is not
+ * part of the reference's ControlResultsInfo, covers the popped nodes that passed their edge
+ * check only in shape 5 (n_pops is exact in every shape). */
 int pdmpc_set_variant(pdmpc_handle *h, int32_t variant);
 
 /* Shape 3 only: nodes per thread slot (0 = default 4096) and the number of pops after

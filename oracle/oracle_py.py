@@ -78,6 +78,8 @@ def lib() -> C.CDLL:
         L.oracle_mcts_plan_batch.restype = C.c_int
         L.oracle_mt19937_rand.argtypes = [C.c_uint32, _p_f64, C.c_int]
         L.oracle_mt19937_rand.restype = None
+        L.oracle_set_hash_valid_pops_only.argtypes = [C.c_int]
+        L.oracle_set_hash_valid_pops_only.restype = None
         _LIB = L
     return _LIB
 
@@ -187,12 +189,17 @@ class ReferencePQ:
         return int(ReferencePQ._lib.pq_ref_size(self.obj))
 
 
-def plan_batch(mpa, batch: SearchBatch, n_threads: int = 1) -> BatchResult:
-    """GraphSearch.do_graph_search for every search of the batch on the CPU."""
+def plan_batch(mpa, batch: SearchBatch, n_threads: int = 1, hash_valid_pops_only: bool = False) -> BatchResult:
+    """GraphSearch.do_graph_search for every search of the batch on the CPU.
+    hash_valid_pops_only: pop_hash as CUDA launch shape 5 reports it (include/pdmpc_b200.h)."""
     d, keep = capi.mpa_desc(mpa)
     r = BatchResult.empty(batch.n, batch.Hp)
     bi, bo = capi.batch_in(batch), capi.batch_out(r)
-    rc = lib().oracle_plan_batch(C.byref(d), C.byref(bi), C.byref(bo), int(n_threads))
+    lib().oracle_set_hash_valid_pops_only(1 if hash_valid_pops_only else 0)
+    try:
+        rc = lib().oracle_plan_batch(C.byref(d), C.byref(bi), C.byref(bo), int(n_threads))
+    finally:
+        lib().oracle_set_hash_valid_pops_only(0)
     if rc != 0:
         raise RuntimeError(f"oracle_plan_batch failed: {rc}")
     del keep

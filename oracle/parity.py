@@ -16,12 +16,15 @@ def _bits(a: np.ndarray) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
 
 
-def compare(dev, ref, require_bit_identical: bool = True) -> dict:
-    """Raises AssertionError on the first violated field; returns summary counts."""
+def compare(dev, ref, require_bit_identical: bool = True, skip=()) -> dict:
+    """Raises AssertionError on the first violated field; returns summary counts.
+    skip: field names left out (pop_hash of launch shape 5 against a fixture that hashed every pop)."""
     n = ref.status.size
     assert dev.status.size == n
     for name in ("status", "is_exhausted", "n_expanded", "n_pops", "pop_hash", "trims", "tree_path",
                  "shape_npts"):
+        if name in skip:
+            continue
         a, b = getattr(dev, name), getattr(ref, name)
         if not np.array_equal(a, b):
             bad = np.argwhere(a != b)[0]

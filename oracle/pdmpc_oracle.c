@@ -371,6 +371,11 @@ typedef struct {
     int64_t cap, n;
 } trace_t;
 
+/* Parity-trace option: hash only the popped nodes that pass their edge check (what launch
+ * shape 5 of the CUDA path reports, include/pdmpc_b200.h).  Default: every popped node. */
+static int g_hash_valid_only = 0;
+void oracle_set_hash_valid_pops_only(int on) { g_hash_valid_only = on; }
+
 /* GraphSearch.m:23-109 for search `si`. */
 static int search_one(const pdmpc_mpa_desc *mpa, const pdmpc_batch_in *in, pdmpc_batch_out *out,
                       int si, work_t *w, trace_t *tr) {
@@ -420,7 +425,7 @@ static int search_one(const pdmpc_mpa_desc *mpa, const pdmpc_batch_in *in, pdmpc
             break;
         }
         ++n_pops;
-        hash = fnv1a_u32(hash, (uint32_t)id);
+        if (!g_hash_valid_only) hash = fnv1a_u32(hash, (uint32_t)id);
         if (tr && tr->n < tr->cap) tr->trace[tr->n++] = id;
 
         /* :64-73 eval_edge_exact (:111-196) */
@@ -446,6 +451,7 @@ static int search_one(const pdmpc_mpa_desc *mpa, const pdmpc_batch_in *in, pdmpc
                                               laney, nlane);
         }
         if (!is_valid) continue; /* :75-77 */
+        if (g_hash_valid_only) hash = fnv1a_u32(hash, (uint32_t)id);
 
         if (t->k[id] == Hp) { /* :81-90 */
             goal = id;

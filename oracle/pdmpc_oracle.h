@@ -69,6 +69,9 @@ int oracle_plan_trace(const pdmpc_mpa_desc *mpa, const pdmpc_batch_in *in,
                       int trace_search, int64_t *pop_trace, int64_t trace_cap,
                       int64_t *n_trace);
 
+/* pop_hash over the popped nodes that passed their edge check only (CUDA launch shape 5); default off */
+void oracle_set_hash_valid_pops_only(int on);
+
 /* MonteCarloTreeSearch.do_graph_search (MonteCarloTreeSearch.m:40-251) for every search. */
 int oracle_mcts_plan_batch(const pdmpc_mpa_desc *mpa, const pdmpc_batch_in *in,
                            const pdmpc_mcts_params *prm, pdmpc_batch_out *out, int n_threads);

@@ -236,8 +236,9 @@ int pdmpc_host_free(void *p) {
 
 int pdmpc_set_variant(pdmpc_handle *h, int32_t variant) {
     if (!h) return PDMPC_ERR_BAD_INPUT;
-    if (variant < 0 || variant > 4)
-        return fail(h, PDMPC_ERR_BAD_INPUT, "variant must be 0 (auto), 1 (latency), 2 (throughput), 3 (lanes) or 4 (cta)");
+    if (variant < 0 || variant > 5)
+        return fail(h, PDMPC_ERR_BAD_INPUT,
+                    "variant must be 0 (auto), 1 (latency), 2 (throughput), 3 (lanes), 4 (cta) or 5 (cta, valid-only queue)");
     h->variant_mode = variant;
     return PDMPC_OK;
 }
@@ -705,9 +706,9 @@ static int launch_search(pdmpc_handle *h, const TraceDev &tr) {
         variant = (h->thr_ok && n >= 4 * h->num_sms) ? 2 : 1;
         // fewer searches than SMs (one computation level of a time step): one CTA per search,
         // edge checks spread over checker warps (profiles/r01e_cta_latency.txt)
-        if (n <= h->num_sms) variant = 4;
+        if (n <= h->num_sms) variant = 4;   // (shape 5, the valid-only queue, measured no faster: opt-in)
     }
-    if (variant == 4) {
+    if (variant == 4 || variant == 5) {
         const int cap = h->user_node_cap ? h->user_node_cap : std::min(h->full_tree_nodes + 8, 1 << 20);
         if (!h->cta_ok || cap > kCtaFlags) variant = 1;   // validity flags of a whole tree must fit in shared memory
     }
@@ -747,13 +748,14 @@ static int launch_search(pdmpc_handle *h, const TraceDev &tr) {
                                                                  h->work_counter2.as<unsigned>(), tr,
                                                                  h->ov_count.as<unsigned>());
         h->stats.kernel_launches++;
-    } else if (variant == 4) {
+    } else if (variant == 4 || variant == 5) {
         const int grid = std::min(n, h->num_sms);
         int rc = ensure_arena(h, grid);
         if (rc != PDMPC_OK) return rc;
         CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
         KERNEL_CTA<<<grid, (kCtaHelpers + kCtaHelpers / 3) * kWarp, sizeof(CtaSmemT), h->stream>>>(h->mpa, h->batch, h->out,
-                                                                                    h->arena, wc, h->cta_heap_smem);
+                                                                                    h->arena, wc, h->cta_heap_smem,
+                                                                                    variant == 5 ? 1 : 0);
     } else if (variant == 2) {
         const int grid = std::min((n + kWarpsThroughput - 1) / kWarpsThroughput, h->num_sms);
         int rc = ensure_arena(h, grid * kWarpsThroughput);
@@ -838,15 +840,19 @@ int pdmpc_fetch_staged(pdmpc_handle *h, pdmpc_batch_out *out) {
     h->stats.total_pops = (int64_t)counters[0];
     h->stats.total_nodes = (int64_t)counters[1];
     h->stats.total_obstacle_cols = (int64_t)counters[2];
+    if (counters[3]) h->stats.handed_over = (int32_t)counters[3];   // shape 5: searches re-run with the exact queue
 #ifdef PDMPC_PROFILE
     {
-        static const char *names[8] = {"setup", "heap_pop", "loads+place", "check", "expand", "heap_push", "-", "loop"};
+        static const char *names[8] = {"setup", "heap_pop", "loads+place", "check", "expand", "heap_push", "wait_children", "loop"};
         double tot = 0;
         for (int i = 0; i < 8; ++i) tot += (double)counters[8 + i];
         fprintf(stderr, "[pdmpc profile] cycles per pop:");
         for (int i = 0; i < 8; ++i)
             fprintf(stderr, " %s=%.0f", names[i], (double)counters[8 + i] / (double)std::max<unsigned long long>(counters[0], 1));
         fprintf(stderr, " total=%.0f\n", tot / (double)std::max<unsigned long long>(counters[0], 1));
+        if (counters[5])
+            fprintf(stderr, "[pdmpc profile] checker 0: %.0f cycles per job over %llu jobs\n",
+                    (double)counters[4] / (double)counters[5], counters[5]);
     }
 #endif
     return PDMPC_OK;

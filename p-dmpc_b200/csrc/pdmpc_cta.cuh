@@ -20,6 +20,26 @@
 // The master therefore never runs an edge check; checks of nodes that are never popped are
 // wasted work on SMs that would otherwise idle.
 //
+// VALID-ONLY QUEUE (`fast` launch argument, launch shape 5).  With the answers known early, an
+// invalid child need not enter the queue at all, provided no pop ever has to break a tie:
+//   * the reference's next VALID pop is a minimum of the whole queue, hence a minimum of the valid
+//     entries; if that minimum is unique among the valid entries it is the same node whatever
+//     invalid entries surround it, so the sequence of valid pops — and with it every expansion,
+//     node id, n_expanded, the goal and the path — equals the reference's;
+//   * the master therefore waits for the flags of the children it has just created, pushes the
+//     valid ones only, and before every pop checks that the minimum is strictly below both
+//     children of the root.  On the first non-unique minimum the search is RE-RUN from scratch
+//     with the exact queue (never observed on road-network records: 0 of 4 M pops; 14 of 80
+//     searches of the symmetric circle scenario);
+//   * n_pops is recovered exactly: an invalid node was popped by the reference iff its f is below
+//     the goal's (an equal f re-runs the search); all nodes are popped when the search exhausts.
+//     pop_hash covers the valid pops only in this shape (documented in include/pdmpc_b200.h).
+// A search then costs one heap pop per EXPANSION instead of one per created node cheaper than the
+// goal, but the master has to wait for the checkers (about 5 400 cycles per job) where shape 4
+// overlaps them with its pops (about 1 100 cycles each, 3 per expansion on the longest search of
+// the sample): measured equal on the long searches and 1.6x slower on median ones
+// (profiles/r01g_valid_only_queue.txt), so the shape is opt-in and shape 4 stays the default.
+//
 // Hand-over: a ring of kRing job descriptors in shared memory; job j is published with
 // bar.arrive on named barrier 1 + j % kRing, the checkers wait for it in bar.sync (no
 // issue slots are spent spinning).  Node records the master needs again when a child is
@@ -62,6 +82,8 @@ struct __align__(16) CtaSmem {
     int abort_flag;
     unsigned next_search;
     int clear_upto;                 // highest node id of the previous search (flags to clear)
+    int redo_exact;                 // the valid-only queue met a tie: run the same search again, exact queue
+    int mode_exact;
     unsigned char flag[kCtaFlags];  // 0 pending, 1 valid, 2 invalid
 };
 
@@ -84,7 +106,7 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) {
 // (profiles/r01e_cta_latency.txt).
 template <int HS, int SP, int NH>
 __global__ void __launch_bounds__((NH + NH / 3) * kWarp, 1)
-search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_counter, int heap_smem) {
+search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_counter, int heap_smem, int fast) {
     // ids whose checks can be in flight: kRing jobs x at most PDMPC_MAX_TRIMS - 1 children each, so the
     // checkers of two nodes that share a cache slot (ids kCtaCache apart) never run at the same time
     static_assert(kRing * PDMPC_MAX_TRIMS <= kCtaCache, "a late checker must never alias a newer cache entry");
@@ -110,15 +132,19 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
     volatile unsigned *vdone = sm.done;
     volatile int *vabort = &sm.abort_flag;
     volatile unsigned *vcs_tag = sm.cs_tag;
-    if (threadIdx.x == 0) sm.clear_upto = kCtaFlags - 1;   // all flags, the first time
+    if (threadIdx.x == 0) { sm.clear_upto = kCtaFlags - 1; sm.redo_exact = 0; }   // all flags, the first time
     const unsigned hf_addr = shared_base_once(sm.hf), hw_addr = shared_base_once(sm.hw);
 
     for (;;) {
         // ---- fetch a search; cooperative set-up ------------------------------------------
         __syncthreads();
-        if (threadIdx.x == 0) sm.next_search = atomicAdd(work_counter, 1u);
+        if (threadIdx.x == 0) {
+            if (sm.redo_exact) { sm.redo_exact = 0; sm.mode_exact = 1; }   // same search again
+            else { sm.next_search = atomicAdd(work_counter, 1u); sm.mode_exact = fast ? 0 : 1; }
+        }
         __syncthreads();
         const unsigned si_u = sm.next_search;
+        const bool exact = sm.mode_exact != 0;
         if (si_u >= (unsigned)b.n) break;
         const int si = b.order ? __ldg(b.order + si_u) : (int)si_u;
         const int clear_upto = sm.clear_upto;
@@ -178,6 +204,9 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
             unsigned long long cols = 0;
             for (unsigned j = 0;; ++j) {
                 named_bar_sync(1 + (int)(j % kRing), kBarThreads);          // job j is published
+#ifdef PDMPC_PROFILE
+                const long long ck0 = clock64();
+#endif
                 const CtaJob &jb = sm.ring[j % kRing];
                 if (jb.terminate) break;
                 const int nchild = jb.nchild, cK = jb.k;
@@ -248,6 +277,9 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
                     }
                 }
                 t.sync();   // every lane is done with the descriptor
+#ifdef PDMPC_PROFILE
+                if (t.lane == 0 && w == 0) { atomicAdd(o.counters + 4, (unsigned long long)(clock64() - ck0)); atomicAdd(o.counters + 5, 1ULL); }
+#endif
                 if (t.lane == 0) vdone[w] = j + 1u;
             }
             if (t.lane == 0 && cols) atomicAdd(o.counters + 2, cols);
@@ -262,8 +294,9 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
         heap.len = 1;
         int n_nodes = 1, n_pops = 0, status = PDMPC_OK;
         unsigned long long hash = 0xcbf29ce484222325ULL;
-        bool exhausted = false;
+        bool exhausted = false, tie = false;
         unsigned goal = 0, n_jobs = 0;
+        double f_last = 0.0;
         if (t.lane == 0) {   // root: GraphSearch.m:34-46
             NodeA ra;
             ra.x = __ldg(b.x0 + si); ra.y = __ldg(b.y0 + si); ra.yaw = __ldg(b.yaw0 + si); ra.g = 0.0;
@@ -283,19 +316,22 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
         for (;;) {   // GraphSearch.m:53-107
             PROF_MARK(7);
             if (heap.len == 0) { exhausted = true; break; }               // :57-61
+            if (!exact && !heap.min_is_unique()) { tie = true; break; }   // tie mechanics would matter: re-run exact
             const HEnt top = heap.pop(t.lane);
             PROF_MARK(1);   // heap pop
             const unsigned id = top.id(), par = top.pid();
             const int cK = (int)top.k();
             ++n_pops;
-            hash = hash_step(hash, id);
-            if (par != 0) {   // eval_edge_exact's answer, computed by a checker warp
+            if (!fast) hash = hash_step(hash, id);   // shape 4: every pop; shape 5: valid pops only (below)
+            f_last = top.f;
+            if (exact && par != 0) {   // eval_edge_exact's answer, computed by a checker warp
                 unsigned f;
                 do { f = vflag[id]; } while (f == 0u);
                 fence_cta();
                 PROF_MARK(2);   // wait for the checker's answer
                 if (f != 1u) continue;                                    // :75-77
             }
+            if (fast) hash = hash_step(hash, id);
             if (cK == Hp) { goal = id; break; }                           // :81-90
 
             // ---- expand_node.m:1-91 (nV == 1) ----------------------------------------------
@@ -385,7 +421,33 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
                     he.w = HEnt::pack(nid, id, (unsigned)cedge, (unsigned)k_exp, (unsigned)t2);
                 }
                 PROF_MARK(4);   // successor generation
-                heap.push_many(he, cnt, t.lane);        // :104, one push per child, in order
+                if (exact) {
+                    heap.push_many(he, cnt, t.lane);    // :104, one push per child, in order
+                } else {
+                    // valid-only queue: wait for the checkers' answers on these children, push the valid
+                    // ones (in order); an invalid child's f is parked in its unused cos/sin record
+                    // (one uniform poll of the checkers' job counters with a back-off: lanes spinning on
+                    // their own flags starve the checkers' shared-memory traffic, 3x slower jobs measured)
+                    while (true) {
+                        const unsigned d = t.lane < NH ? vdone[t.lane] : n_jobs;
+                        if (__all_sync(0xffffffffu, d >= n_jobs)) break;
+                        __nanosleep(32);
+                    }
+                    fence_cta();
+                    const unsigned fl = ci < nchild ? vflag[nid] : 1u;
+                    PROF_MARK(6);   // wait for the children's answers
+                    const bool ok = ci < nchild && fl == 1u;
+                    if (ci < nchild && !ok) { NodeCS park; park.c = he.f; park.s = 0.0; ncs[nid] = park; }
+                    const unsigned vm = __ballot_sync(0xffffffffu, ok);
+                    const int mv = __popc(vm);
+                    unsigned mm = vm;
+                    for (int i = 0; i < t.lane && i < mv; ++i) mm &= mm - 1u;
+                    const int src = t.lane < mv ? __ffs(mm) - 1 : 0;
+                    HEnt hv;
+                    hv.f = __shfl_sync(0xffffffffu, he.f, src);
+                    hv.w = __shfl_sync(0xffffffffu, he.w, src);
+                    if (mv) heap.push_many(hv, mv, t.lane);
+                }
                 PROF_MARK(5);   // heap pushes
             }
             n_nodes += nchild;
@@ -405,6 +467,30 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
             named_bar_arrive(1 + (int)(n_jobs % kRing), kBarThreads);
         }
         if (status != PDMPC_OK) exhausted = true;
+        if (!exact && !tie && status == PDMPC_OK) {
+            // pops of the reference's queue = valid pops + the invalid nodes it met on the way:
+            // all of them if the search exhausted, those cheaper than the goal otherwise
+            int extra = 0;
+            bool amb = false;
+            for (int i0 = 2; i0 <= n_nodes; i0 += TILE) {
+                const int i = i0 + t.lane;
+                if (i <= n_nodes && vflag[i] == 2u) {
+                    if (exhausted) ++extra;
+                    else {
+                        const double fi = ncs[i].c;
+                        if (fi < f_last) ++extra;
+                        else if (fi == f_last) amb = true;
+                    }
+                }
+            }
+            for (int d = 16; d > 0; d >>= 1) extra += __shfl_xor_sync(0xffffffffu, extra, d);
+            if (__any_sync(0xffffffffu, amb)) tie = true;
+            n_pops += extra;
+        }
+        if (tie) {   // undecidable without the reference's tie mechanics: same search again, exact queue
+            if (t.lane == 0) { sm.redo_exact = 1; sm.clear_upto = n_nodes; atomicAdd(o.counters + 3, 1ULL); }
+            continue;
+        }
         if (t.lane == 0) {
             unsigned cur = goal;
             for (int d = Hp; d >= 0; --d) {           // Tree.m:44-52 path_to_root, flipped

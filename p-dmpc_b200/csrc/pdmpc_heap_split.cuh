@@ -95,6 +95,16 @@ struct HeapSplit {
         if (lane == 0) st(((p + 1) >> T) - 1, v);
     }
 
+    // Is the minimum unique (strictly below both children of the root)?  When it is, WHICH entry a
+    // pop returns does not depend on the heap's tie mechanics.
+    __device__ __forceinline__ bool min_is_unique() const {
+        if (len <= 1) return true;
+        const double top = f_at(0);
+        if (!(top < f_at(1))) return false;
+        if (len > 2 && !(top < f_at(2))) return false;
+        return true;
+    }
+
     // pq.pop(); caller guarantees len > 0
     __device__ __forceinline__ HEnt pop(int lane) {
         const int n = len - 1;   // heap size after the pop; entry[n] is re-inserted
