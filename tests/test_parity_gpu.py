@@ -281,3 +281,48 @@ def test_full_size_properties(planner):
         assert np.array_equal(getattr(r1, name), base[perm]), name
     assert np.array_equal(r1.trims, np.tile(r0.trims, (reps, 1))[perm])
     assert np.array_equal(r1.y_predicted.view(np.uint64), np.tile(r0.y_predicted, (reps, 1, 1))[perm].view(np.uint64))
+
+
+def test_packed_and_unpacked_staging_agree(planner):
+    """Batches of at most 1 MiB go through one pinned staging block and one copy each way, larger ones
+    through per-array copies: the same searches must give the same outputs either way, and in any
+    mix of calls on one handle."""
+    mpa, batch = road_records("triple_speed", 8)
+    planner.upload_mpa(mpa)
+    small = batch.select(np.arange(12))
+    assert small.input_bytes() < (1 << 20)
+    big = SearchBatch.concat([batch] * 6)
+    assert big.input_bytes() > (1 << 20)
+    ref = oracle_py.plan_batch(mpa, batch, 4)
+    a = planner.plan_batch(small)
+    b = planner.plan_batch(big)
+    c = planner.plan_batch(small)
+    first = lambda r, n: dataclasses.replace(r, **{f.name: getattr(r, f.name)[:n] for f in dataclasses.fields(r)
+                                                   if isinstance(getattr(r, f.name), np.ndarray)})
+    parity.compare(a, first(ref, 12))
+    parity.compare(c, first(ref, 12))
+    parity.compare(first(b, batch.n), ref)
+    parity.compare(dataclasses.replace(b, **{f.name: getattr(b, f.name)[-batch.n:] for f in dataclasses.fields(b)
+                                             if isinstance(getattr(b, f.name), np.ndarray)}), ref)
+
+
+def test_restage_before_fetch_and_knob_validation(planner):
+    """The pinned staging block is reused by the next stage call: staging again while the previous
+    copy may still be in flight must not corrupt either batch."""
+    mpa, batch = road_records("single_speed", 6)
+    planner.upload_mpa(mpa)
+    a, b = batch.select(np.arange(0, 10)), batch.select(np.arange(10, 30))
+    planner.stage(a)
+    planner.run_staged()
+    planner.stage(b)          # no fetch in between
+    planner.run_staged()
+    parity.compare(planner.fetch(), oracle_py.plan_batch(mpa, b))
+    planner.stage(a)
+    planner.run_staged()
+    parity.compare(planner.fetch(), oracle_py.plan_batch(mpa, a))
+    for bad in (3, 5000, -2):
+        with pytest.raises(capi.PdmpcError):
+            planner.set_cta_heap_smem(bad)
+    with pytest.raises(capi.PdmpcError):
+        planner.set_variant(9)
+    planner.set_variant(0)
