@@ -123,16 +123,26 @@ def _roll_chunk(job):
     mpa = get_mpa(mpa_type, non_convex=True)
     planner = capi.Planner(dev)
     planner.upload_mpa(mpa)
-    batches, levels = [], []
+    from pdmpc_b200.records import TimestepDeps
+    batches, levels, timesteps = [], [], []
     for si, s in enumerate(seeds):
         sc = scenario.commonroad_scenario(mpa, vehicles, seed=s)
-        recs = scenario.ScenarioRunner(sc, planner.plan_batch).run(sim_steps)
-        batches.extend(r.batch for r in recs)
-        if si < 8:   # level structure of the first scenarios (the per-time-step latency replay)
+        runner = scenario.ScenarioRunner(sc, planner.plan_batch)
+        if si < 8:   # level structure + one-call inputs of the first scenarios (per-time-step latency replay)
+            for _ in range(sim_steps):
+                iters, preds, fbs = runner.timestep_inputs()
+                timesteps.append((si * 100000 + runner.k + 1,
+                                  SearchBatch.from_iters(iters, mpa.Hp, sc.checker, mpa.dt_seconds),
+                                  TimestepDeps.build(preds, [f[0] for f in fbs], mpa.Hp)))
+                runner.step()
+            recs = runner.records
             levels.extend((si * 100000 + r.step, r.level, r.batch.n) for r in recs)
+        else:
+            recs = runner.run(sim_steps)
+        batches.extend(r.batch for r in recs)
     planner.close()
     SearchBatch.concat(batches).save(out_path)
-    return out_path, levels
+    return out_path, levels, timesteps
 
 
 def build_records(dev, mpa_type, n_scen: int, seed0: int, vehicles: int, sim_steps: int, cache: str = "",
@@ -143,8 +153,9 @@ def build_records(dev, mpa_type, n_scen: int, seed0: int, vehicles: int, sim_ste
     first scenario, whose records come first in the batch).  Cached under build/
     (git-ignored) so that profiler runs of the same command skip the generation launches."""
     from pdmpc_b200.records import SearchBatch
-    if cache and os.path.exists(cache) and os.path.exists(cache + ".levels.npy"):
-        return SearchBatch.load(cache), np.load(cache + ".levels.npy")
+    import pickle
+    if cache and os.path.exists(cache) and os.path.exists(cache + ".levels.npy") and os.path.exists(cache + ".ts.pkl"):
+        return SearchBatch.load(cache), np.load(cache + ".levels.npy"), pickle.load(open(cache + ".ts.pkl", "rb"))
     import multiprocessing as mp
     import tempfile
     workers = max(1, min(workers, n_scen))
@@ -158,16 +169,18 @@ def build_records(dev, mpa_type, n_scen: int, seed0: int, vehicles: int, sim_ste
     else:
         with mp.get_context("spawn").Pool(len(jobs)) as pool:
             results = pool.map(_roll_chunk, jobs)
-    batch = SearchBatch.concat([SearchBatch.load(pth) for pth, _ in results])
+    batch = SearchBatch.concat([SearchBatch.load(pth) for pth, _, _ in results])
     levels = np.array(results[0][1], dtype=np.int64)
-    for pth, _ in results:
+    timesteps = results[0][2]
+    for pth, _, _ in results:
         os.remove(pth)
     os.rmdir(tmp)
     if cache:
         os.makedirs(os.path.dirname(cache), exist_ok=True)
         batch.save(cache)
         np.save(cache + ".levels.npy", levels)
-    return batch, levels
+        pickle.dump(timesteps, open(cache + ".ts.pkl", "wb"))
+    return batch, levels, timesteps
 
 
 def algorithmic_bytes(batch, stats, Hp: int) -> float:
@@ -264,7 +277,7 @@ def main():
     cache = os.path.join(ROOT, "build", f"bench_{args.mpa}_{args.vehicles}v_{args.scenarios}s_{args.sim_steps}t_seed"
                                         f"{1 + rank * args.scenarios}.npz")
     workers = args.gen_workers or max(1, min(12, (os.cpu_count() or 1) // max(world, 1)))
-    batch, step_recs = build_records(dev, args.mpa, args.scenarios, 1 + rank * args.scenarios,
+    batch, step_recs, ts_recs = build_records(dev, args.mpa, args.scenarios, 1 + rank * args.scenarios,
                                      args.vehicles, args.sim_steps, "" if args.no_cache else cache, workers)
     t_gen = time.perf_counter() - t_gen
     n = batch.n
@@ -369,6 +382,30 @@ def main():
                 if rep:
                     lat.append((time.perf_counter() - t0) * 1e3)
 
+    # ---- the same time steps, ONE call each (pdmpc_plan_timestep) ------------------------------
+    # Base iter_v of all 20 vehicles + predecessor lists + fallback areas in, all plans out: one
+    # H2D, one dependency-ordered launch (searches wait for their own predecessors' flags), one D2H.
+    lat1 = []
+    if rank == 0 and ts_recs:
+        calls = []
+        for step, tb, td in ts_recs:
+            ro = BatchResult.empty(tb.n, Hp)
+            pidx = td.pred_idx if td.pred_idx.size else np.zeros(1, dtype=np.int32)
+            dc = capi.TimestepDepsC(pred_ptr=capi._ptr(td.pred_ptr, capi._p_i32), pred_idx=capi._ptr(pidx, capi._p_i32),
+                                    fb_npts=capi._ptr(td.fb_npts, capi._p_i32), fb_x=capi._ptr(td.fb_x, capi._p_f64),
+                                    fb_y=capi._ptr(td.fb_y, capi._p_f64))
+            calls.append((int(step), tb, td, pidx, ro, capi.batch_in(tb), dc, capi.batch_out(ro)))
+        for rep in range(3):
+            for _step, _tb, _td, _pidx, _ro, tbi, tdc, tbo in calls:
+                t0 = time.perf_counter()
+                planner._check(planner.lib.pdmpc_plan_timestep(planner.h, C.byref(tbi), C.byref(tdc), C.byref(tbo)))
+                if rep:
+                    lat1.append((time.perf_counter() - t0) * 1e3)
+        # same searches, same answers as the level-by-level replay above (pop-order hashes per time step)
+        for step, _tb, _td, _pidx, ro, *_ in calls:
+            a = np.sort(np.concatenate([r.pop_hash for _lb, r, _i, _o in by_step[step]]))
+            assert np.array_equal(a, np.sort(ro.pop_hash)), f"time step {step}: one-call path != level-by-level path"
+
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------
     cpu = None
     if rank == 0 and world == 1:
@@ -442,6 +479,12 @@ def main():
                                          "what": "wall time of all computation levels of one 20-vehicle time step, one "
                                                  "pdmpc_plan_batch call per level, host buffers in and out"}
                                         if lat else None),
+            "latency_ms_per_timestep_one_call": ({"p50": float(np.percentile(lat1, 50)), "p99": float(np.percentile(lat1, 99)),
+                                                  "max": float(np.max(lat1)), "n": len(lat1),
+                                                  "what": "wall time of ONE pdmpc_plan_timestep call per 20-vehicle time "
+                                                          "step (predecessor hand-over on the device), host buffers in "
+                                                          "and out; same time steps and answers as above"}
+                                                 if lat1 else None),
         }
         print(json.dumps(line))
     if world > 1:

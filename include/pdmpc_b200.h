@@ -249,6 +249,42 @@ int pdmpc_mcts_plan_batch(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc
 /* Device-resident form: inputs staged with pdmpc_stage_batch, results read with pdmpc_fetch_staged. */
 int pdmpc_mcts_run_staged(pdmpc_handle *h, const pdmpc_mcts_params *prm);
 
+/* ---- One whole time step (or many) in ONE call: the part of
+ *      PrioritizedController.plan that hands the plans of higher-priority
+ *      vehicles to the vehicles planning after them
+ *      (hlc/controller/prioritized/PrioritizedController.m:297-324, consider_predecessors
+ *      :449-506, publish_predictions :355-364) moves onto the device.  The searches of the
+ *      batch form a DAG: search i waits for its sequential predecessors pred_idx[pred_ptr[i] ..
+ *      pred_ptr[i+1]) — searches of the SAME batch — and sees, at step k, the area
+ *      info_j.shapes{1,k} each of them has just planned as one more row of
+ *      iter.dynamic_obstacle_area (appended after the rows the caller passed in `in`; the
+ *      checkers only ask whether ANY obstacle is hit, so the row order changes no result).
+ *      A predecessor whose search is exhausted publishes its fallback areas instead: what
+ *      plan_fallback (:678-718, del_first_rpt_last of the previous plan's shapes) or
+ *      handle_graph_search_exhaustion (:568-621, the standstill rectangle) would publish.  Both
+ *      depend only on the previous time step, so the caller passes them up front.
+ *      Computation levels are not needed: every search starts the moment its own predecessors
+ *      are done (flags in HBM, one persistent launch), which is never later than its level. ---- */
+typedef struct pdmpc_timestep_deps {
+    const int32_t *pred_ptr;  /* [n+1] CSR over the searches of the batch, pred_ptr[0] == 0 */
+    const int32_t *pred_idx;  /* [pred_ptr[n]] 0-based search indices; the relation must be acyclic */
+    /* areas search i publishes when it is exhausted; NULL = an exhausted search publishes nothing */
+    const int32_t *fb_npts;   /* [n*Hp] closed points per step, 0 (nothing) or 2..PDMPC_AREA_STRIDE-1 */
+    const double *fb_x;       /* [n*Hp*PDMPC_AREA_STRIDE] */
+    const double *fb_y;       /* [n*Hp*PDMPC_AREA_STRIDE] */
+} pdmpc_timestep_deps;
+/* Most sequential predecessors one search may have: Hp * PDMPC_AREA_STRIDE columns each must fit the
+ * shared-memory tile that holds them (PDMPC_TIMESTEP_COLS columns). */
+#define PDMPC_TIMESTEP_COLS 2048
+
+/* Host buffers in, host buffers out (like pdmpc_plan_batch): one host->device copy, one launch,
+ * one device->host copy for the whole DAG.  Every output equals what level-by-level calls of
+ * pdmpc_plan_batch with host-side obstacle assembly return.  Errors: PDMPC_ERR_BAD_INPUT for a
+ * cyclic or out-of-range relation or too many predecessors; PDMPC_ERR_CAPACITY when the uploaded
+ * MPA's full search tree exceeds what the one-CTA-per-search kernel holds (32768 nodes). */
+int pdmpc_plan_timestep(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_timestep_deps *deps,
+                        pdmpc_batch_out *out);
+
 /* Pinned host buffers for callers that want full-rate host<->device copies. */
 int pdmpc_host_alloc(void **p, size_t bytes);
 int pdmpc_host_free(void *p);

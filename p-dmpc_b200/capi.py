@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = (
     "pdmpc_set_node_capacity", "pdmpc_set_variant", "pdmpc_set_lane_limits", "pdmpc_host_alloc", "pdmpc_host_free",
     "pdmpc_trace_staged", "pdmpc_upload_mpa", "pdmpc_plan_batch", "pdmpc_stage_batch",
     "pdmpc_run_staged", "pdmpc_sync", "pdmpc_fetch_staged", "pdmpc_get_stats", "pdmpc_stream",
-    "pdmpc_mcts_plan_batch", "pdmpc_mcts_run_staged", "pdmpc_set_cta_heap_smem",
+    "pdmpc_mcts_plan_batch", "pdmpc_mcts_run_staged", "pdmpc_set_cta_heap_smem", "pdmpc_plan_timestep",
 )
 
 _p_u8 = C.POINTER(C.c_uint8)
@@ -63,6 +63,10 @@ class BatchIn(C.Structure):
 
 class MctsParams(C.Structure):
     _fields_ = [("n_expansions_max", C.c_int32), ("seed", C.POINTER(C.c_uint32))]
+
+
+class TimestepDepsC(C.Structure):
+    _fields_ = [("pred_ptr", _p_i32), ("pred_idx", _p_i32), ("fb_npts", _p_i32), ("fb_x", _p_f64), ("fb_y", _p_f64)]
 
 
 class BatchOut(C.Structure):
@@ -194,6 +198,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.pdmpc_mcts_plan_batch.restype = C.c_int
     lib.pdmpc_mcts_run_staged.argtypes = [H, C.POINTER(MctsParams)]
     lib.pdmpc_mcts_run_staged.restype = C.c_int
+    lib.pdmpc_plan_timestep.argtypes = [H, C.POINTER(BatchIn), C.POINTER(TimestepDepsC), C.POINTER(BatchOut)]
+    lib.pdmpc_plan_timestep.restype = C.c_int
     lib.pdmpc_stream.argtypes = [H]
     lib.pdmpc_stream.restype = C.c_void_p
     _LIB = lib
@@ -269,6 +275,20 @@ class Planner:
         r = BatchResult.empty(b.n, b.Hp)
         bi, bo = batch_in(b), batch_out(r)
         self._check(self.lib.pdmpc_plan_batch(self.h, C.byref(bi), C.byref(bo)))
+        if raise_on_search_error and b.n and int(r.status.max()) != PDMPC_OK:
+            bad = int(np.flatnonzero(r.status != PDMPC_OK)[0])
+            raise PdmpcError(int(r.status[bad]), f"search {bad} failed")
+        return r
+
+    def plan_timestep(self, b: SearchBatch, deps, raise_on_search_error: bool = True) -> BatchResult:
+        """All searches of one (or many) time steps in one dependency-ordered launch
+        (pdmpc_plan_timestep): PrioritizedController.plan's hand-over of predecessors' areas on the device."""
+        r = BatchResult.empty(b.n, b.Hp)
+        bi, bo = batch_in(b), batch_out(r)
+        pidx = deps.pred_idx if deps.pred_idx.size else np.zeros(1, dtype=np.int32)
+        d = TimestepDepsC(pred_ptr=_ptr(deps.pred_ptr, _p_i32), pred_idx=_ptr(pidx, _p_i32),
+                          fb_npts=_ptr(deps.fb_npts, _p_i32), fb_x=_ptr(deps.fb_x, _p_f64), fb_y=_ptr(deps.fb_y, _p_f64))
+        self._check(self.lib.pdmpc_plan_timestep(self.h, C.byref(bi), C.byref(d), C.byref(bo)))
         if raise_on_search_error and b.n and int(r.status.max()) != PDMPC_OK:
             bad = int(np.flatnonzero(r.status != PDMPC_OK)[0])
             raise PdmpcError(int(r.status[bad]), f"search {bad} failed")

@@ -45,8 +45,11 @@ constexpr int kLaneThreads = 256;
 #define KERNEL_LANES_SMEM search_lanes_kernel<kLaneThreads, true>
 #define KERNEL_LANES_GMEM search_lanes_kernel<kLaneThreads, false>
 // "cta" = one 13-warp CTA per search (pdmpc_cta.cuh): master warp + checker warps, lowest latency
-#define KERNEL_CTA search_cta_kernel<kCtaHeap, kCtaPts, kCtaHelpers>
-using CtaSmemT = CtaSmem<kCtaHeap, kCtaPts, kCtaHelpers>;
+#define KERNEL_CTA search_cta_kernel<kCtaHeap, kCtaPts, kCtaHelpers, false>
+using CtaSmemT = CtaSmem<kCtaHeap, kCtaPts, kCtaHelpers, false>;
+// the same kernel with the dependency prelude/epilogue of pdmpc_plan_timestep
+#define KERNEL_CTA_DEPS search_cta_kernel<kCtaHeap, kCtaPts, kCtaHelpers, true>
+using CtaDepsSmemT = CtaSmem<kCtaHeap, kCtaPts, kCtaHelpers, true>;
 constexpr int kLaneNodeCapDefault = 4096;
 constexpr int kLanePopLimitDefault = 1024;
 
@@ -82,6 +85,14 @@ struct pdmpc_handle {
     int variant_mode = 0;             // 0 = auto, 1 = latency, 2 = throughput, 3 = lanes (+ warp second stage), 4 = cta
     int cta_heap_smem = kCtaHeap;     // heap entries the CTA shape keeps in shared memory (tuning/test knob)
     bool cta_ok = false;              // the CTA-per-search kernel is launchable (shared memory opt-in granted)
+    bool cta_deps_ok = false;         // ... and its pdmpc_plan_timestep instance
+    // pdmpc_plan_timestep: dependency CSR, fallback areas, done flags (one packed upload)
+    DBuf d_deps, d_done;
+    void *pin_deps = nullptr;
+    size_t pin_deps_cap = 0;
+    DepsDev deps{};
+    bool deps_staged = false;
+    std::vector<int> topo_order;      // work order override for the next pdmpc_stage_batch (time-step calls)
     bool lanes_ok = false;            // every maneuver area has <= 7 points
     bool lanes_smem_ok = false;       // MPA tables fit in shared memory next to nothing else
     size_t lanes_smem = 0;
@@ -195,6 +206,8 @@ int pdmpc_create(int device_id, pdmpc_handle **out) {
     h->lat_ctas_per_sm = occ;
     h->cta_ok = cudaFuncSetAttribute(KERNEL_CTA, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(CtaSmemT)) == cudaSuccess;
+    h->cta_deps_ok = cudaFuncSetAttribute(KERNEL_CTA_DEPS, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(CtaDepsSmemT)) == cudaSuccess;
     cudaGetLastError();
     *out = h;
     return PDMPC_OK;
@@ -213,6 +226,9 @@ int pdmpc_destroy(pdmpc_handle *h) {
     for (DBuf *b : bufs) b->release();
     h->d_in_pack.release();
     h->d_out_pack.release();
+    h->d_deps.release();
+    h->d_done.release();
+    if (h->pin_deps) cudaFreeHost(h->pin_deps);
     if (h->pin_in) cudaFreeHost(h->pin_in);
     if (h->pin_out) cudaFreeHost(h->pin_out);
     if (h->ev_pack) cudaEventDestroy(h->ev_pack);
@@ -526,7 +542,10 @@ int pdmpc_stage_batch(pdmpc_handle *h, const pdmpc_batch_in *in) {
     // work order: searches with the most obstacle polygons first (they are the ones most
     // likely to run long / exhaust), so the tail of the batch is made of short searches
     std::vector<int> order;
-    if (n > 1) {
+    h->deps_staged = false;
+    if (n > 1 && (int)h->topo_order.size() == n) {
+        order.swap(h->topo_order);   // pdmpc_plan_timestep: a topological order of the dependency DAG
+    } else if (n > 1) {
         std::vector<int> key(n);
         order.resize(n);
         int kmax = 0;
@@ -755,7 +774,7 @@ static int launch_search(pdmpc_handle *h, const TraceDev &tr) {
         CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
         KERNEL_CTA<<<grid, (kCtaHelpers + kCtaHelpers / 3) * kWarp, sizeof(CtaSmemT), h->stream>>>(h->mpa, h->batch, h->out,
                                                                                     h->arena, wc, h->cta_heap_smem,
-                                                                                    variant == 5 ? 1 : 0);
+                                                                                    variant == 5 ? 1 : 0, DepsDev{});
     } else if (variant == 2) {
         const int grid = std::min((n + kWarpsThroughput - 1) / kWarpsThroughput, h->num_sms);
         int rc = ensure_arena(h, grid * kWarpsThroughput);
@@ -843,7 +862,11 @@ int pdmpc_fetch_staged(pdmpc_handle *h, pdmpc_batch_out *out) {
     if (counters[3]) h->stats.handed_over = (int32_t)counters[3];   // shape 5: searches re-run with the exact queue
 #ifdef PDMPC_PROFILE
     {
+#ifdef PDMPC_PROFILE_CHECKER
+        static const char *names[8] = {"c:wait_job", "c:tables+place", "c:interx_obstacles", "c:interx_rest", "c:sincos+publish", "-", "-", "c:other"};
+#else
         static const char *names[8] = {"setup", "heap_pop", "loads+place", "check", "expand", "heap_push", "wait_children", "loop"};
+#endif
         double tot = 0;
         for (int i = 0; i < 8; ++i) tot += (double)counters[8 + i];
         fprintf(stderr, "[pdmpc profile] cycles per pop:");
@@ -863,6 +886,122 @@ int pdmpc_plan_batch(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc_batch_out 
     if (rc != PDMPC_OK) return rc;
     rc = pdmpc_run_staged(h);
     if (rc != PDMPC_OK) return rc;
+    return pdmpc_fetch_staged(h, out);
+}
+
+// One whole time step (or many) as ONE dependency-ordered launch: see include/pdmpc_b200.h.
+int pdmpc_plan_timestep(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_timestep_deps *deps,
+                        pdmpc_batch_out *out) {
+    if (!h) return PDMPC_ERR_BAD_INPUT;
+    if (!h->has_mpa) return fail(h, PDMPC_ERR_NO_MPA, "plan_timestep: call pdmpc_upload_mpa first");
+    if (!in || !deps || !deps->pred_ptr) return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep: NULL argument");
+    const int n = in->n_searches, Hp = h->mpa.Hp;
+    if (n < 0) return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep: n_searches < 0");
+    if (!h->cta_deps_ok)
+        return fail(h, PDMPC_ERR_CUDA, "plan_timestep: the one-CTA-per-search kernel is not launchable on this device");
+    {
+        const int cap = h->user_node_cap ? h->user_node_cap : std::min(h->full_tree_nodes + 8, 1 << 20);
+        if (cap > kCtaFlags)
+            return fail(h, PDMPC_ERR_CAPACITY,
+                        "plan_timestep: the full search tree of this MPA exceeds the 32768 nodes the one-CTA-per-search "
+                        "kernel holds; plan level by level with pdmpc_plan_batch");
+    }
+    // ---- validate the relation, order the searches topologically (utility/kahn.m:1-24) ----------
+    if (deps->pred_ptr[0] != 0) return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep: pred_ptr must start at 0");
+    for (int i = 0; i < n; ++i) {
+        const int np = deps->pred_ptr[i + 1] - deps->pred_ptr[i];
+        if (np < 0) return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep: pred_ptr not monotone");
+        if ((long long)np * Hp * PDMPC_AREA_STRIDE > PDMPC_TIMESTEP_COLS)
+            return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep: too many predecessors for one search (PDMPC_TIMESTEP_COLS)");
+    }
+    const int total = n ? deps->pred_ptr[n] : 0;
+    if (total > 0 && !deps->pred_idx) return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep: pred_idx is NULL");
+    if (deps->fb_npts && (!deps->fb_x || !deps->fb_y))
+        return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep: fallback areas without coordinates");
+    if (deps->fb_npts)
+        for (size_t i = 0; i < (size_t)n * Hp; ++i) {
+            const int np = deps->fb_npts[i];
+            if (np != 0 && (np < 2 || np > PDMPC_AREA_STRIDE - 1))
+                return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep: fb_npts must be 0 or 2..PDMPC_AREA_STRIDE-1");
+        }
+    std::vector<int> indeg(n, 0), succ_ptr(n + 1, 0), succ(total), order;
+    for (int i = 0; i < n; ++i)
+        for (int q = deps->pred_ptr[i]; q < deps->pred_ptr[i + 1]; ++q) {
+            const int j = deps->pred_idx[q];
+            if (j < 0 || j >= n || j == i) return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep: pred_idx out of range");
+            succ_ptr[j + 1]++;
+            indeg[i]++;
+        }
+    for (int i = 0; i < n; ++i) succ_ptr[i + 1] += succ_ptr[i];
+    {
+        std::vector<int> fill(succ_ptr.begin(), succ_ptr.end() - 1);
+        for (int i = 0; i < n; ++i)
+            for (int q = deps->pred_ptr[i]; q < deps->pred_ptr[i + 1]; ++q) succ[fill[deps->pred_idx[q]]++] = i;
+    }
+    order.reserve(n);
+    for (int i = 0; i < n; ++i)
+        if (indeg[i] == 0) order.push_back(i);
+    for (size_t head = 0; head < order.size(); ++head) {   // FIFO: level-major
+        const int j = order[head];
+        for (int q = succ_ptr[j]; q < succ_ptr[j + 1]; ++q)
+            if (--indeg[succ[q]] == 0) order.push_back(succ[q]);
+    }
+    if ((int)order.size() != n) return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep: the predecessor relation has a cycle");
+
+    h->topo_order.swap(order);
+    int rc = pdmpc_stage_batch(h, in);
+    h->topo_order.clear();
+    if (rc != PDMPC_OK) return rc;
+    if (n == 0) {
+        rc = pdmpc_run_staged(h);
+        return rc != PDMPC_OK ? rc : pdmpc_fetch_staged(h, out);
+    }
+    // ---- dependency CSR + fallback areas: one pinned block, one copy ------------------------------
+    const size_t nhp = (size_t)n * Hp;
+    const bool has_fb = deps->fb_npts != nullptr;
+    const size_t sz[5] = {((size_t)n + 1) * sizeof(int), (size_t)std::max(total, 1) * sizeof(int),
+                          has_fb ? nhp * sizeof(int) : 0, has_fb ? nhp * PDMPC_AREA_STRIDE * sizeof(double) : 0,
+                          has_fb ? nhp * PDMPC_AREA_STRIDE * sizeof(double) : 0};
+    const void *src[5] = {deps->pred_ptr, deps->pred_idx, deps->fb_npts, deps->fb_x, deps->fb_y};
+    size_t off[5], tot = 0;
+    for (int i = 0; i < 5; ++i) {
+        off[i] = tot;
+        tot = (tot + sz[i] + 15) / 16 * 16;
+    }
+    rc = ensure_pinned(h, &h->pin_deps, &h->pin_deps_cap, tot);
+    if (rc != PDMPC_OK) return rc;
+    CU_TRY(h, h->d_deps.reserve(tot));
+    CU_TRY(h, h->d_done.reserve((size_t)n * sizeof(int)));
+    unsigned char *pin = static_cast<unsigned char *>(h->pin_deps);
+    for (int i = 0; i < 5; ++i)
+        if (sz[i] && src[i]) memcpy(pin + off[i], src[i], i == 1 ? (size_t)total * sizeof(int) : sz[i]);
+    CU_TRY(h, cudaMemcpyAsync(h->d_deps.p, pin, tot, cudaMemcpyHostToDevice, h->stream));
+    h->stats.h2d_bytes += (int64_t)tot;
+    CU_TRY(h, cudaMemsetAsync(h->d_done.p, 0, (size_t)n * sizeof(int), h->stream));
+    const unsigned char *db = h->d_deps.as<unsigned char>();
+    DepsDev dp;
+    dp.pred_ptr = reinterpret_cast<const int *>(db + off[0]);
+    dp.pred_idx = reinterpret_cast<const int *>(db + off[1]);
+    dp.fb_npts = has_fb ? reinterpret_cast<const int *>(db + off[2]) : nullptr;
+    dp.fb_x = has_fb ? reinterpret_cast<const double *>(db + off[3]) : nullptr;
+    dp.fb_y = has_fb ? reinterpret_cast<const double *>(db + off[4]) : nullptr;
+    dp.done = h->d_done.as<int>();
+    // ---- one persistent launch: CTAs take the searches in topological order -----------------------
+    CU_TRY(h, cudaMemsetAsync(h->out.counters, 0, 16 * sizeof(unsigned long long), h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->work_counter.p, 0, sizeof(unsigned), h->stream));
+    const int grid = std::min(n, h->num_sms);
+    rc = ensure_arena(h, grid);
+    if (rc != PDMPC_OK) return rc;
+    CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
+    KERNEL_CTA_DEPS<<<grid, (kCtaHelpers + kCtaHelpers / 3) * kWarp, sizeof(CtaDepsSmemT), h->stream>>>(
+        h->mpa, h->batch, h->out, h->arena, h->work_counter.as<unsigned>(), h->cta_heap_smem, 0, dp);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
+    h->timing_pending_kernel = true;
+    h->timing_pending_lanes = false;
+    h->stats.lanes_ms = 0.0;
+    h->stats.handed_over = 0;
+    h->stats.kernel_launches++;
     return pdmpc_fetch_staged(h, out);
 }
 

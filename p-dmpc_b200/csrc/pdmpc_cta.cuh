@@ -48,6 +48,20 @@
 
 #include "pdmpc_kernels.cuh"
 
+// Checker-side cycle accounting (build with -DPDMPC_PROFILE -DPDMPC_PROFILE_CHECKER: the counters
+// of the master's phases then carry checker 0's per-child phases instead)
+#if defined(PDMPC_PROFILE) && defined(PDMPC_PROFILE_CHECKER)
+#define CPROF_DECL long long cprof_t0 = clock64(), cprof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define CPROF_MARK(i) do { long long _t = clock64(); cprof_acc[i] += _t - cprof_t0; cprof_t0 = _t; } while (0)
+#define CPROF_FLUSH(o, on) do { if (on) for (int _i = 0; _i < 8; ++_i) atomicAdd((o).counters + 8 + _i, (unsigned long long)cprof_acc[_i]); } while (0)
+#undef PROF_FLUSH
+#define PROF_FLUSH(o, lane0)
+#else
+#define CPROF_DECL
+#define CPROF_MARK(i)
+#define CPROF_FLUSH(o, on)
+#endif
+
 namespace pdmpc {
 
 constexpr int kRing = 8;            // job descriptors in flight (named barriers 1..kRing)
@@ -56,15 +70,18 @@ constexpr int kCtaHeap = 4096;      // heap entries in shared memory
 constexpr int kCtaPts = 512;        // staged polyline points
 constexpr int kCtaCache = 1024;     // node-record cache entries (direct mapped by id)
 constexpr int kCtaFlags = 32768;    // validity flags (1 byte per node id) — searches need cap <= this
+constexpr int kCtaDepCols = PDMPC_TIMESTEP_COLS;   // columns of predecessors' areas (pdmpc_plan_timestep)
+constexpr int kCtaDepPolys = kCtaDepCols / kAreaStride;
 
 struct __align__(16) CtaJob {       // one expansion: children nid0 .. nid0 + nchild - 1
     double px, py, pyaw, c, s;      // pose and cos/sin(yaw) of the expanded node
     unsigned nid0;
     int nchild, sbase, k;           // successor list base, depth of the children
-    int terminate, pad;
+    int terminate;
+    int rot;                        // checker that takes child 0; child ci goes to checker (rot + ci) % NH
 };
 
-template <int HS, int SP, int NH>
+template <int HS, int SP, int NH, bool DEPS = false>
 struct __align__(16) CtaSmem {
     double hf[HS + 2];               // heap costs, entry i at hf[i + 1] (pdmpc_heap_split.cuh)
     unsigned long long hw[HS];       // heap payloads
@@ -85,6 +102,14 @@ struct __align__(16) CtaSmem {
     int redo_exact;                 // the valid-only queue met a tie: run the same search again, exact queue
     int mode_exact;
     unsigned char flag[kCtaFlags];  // 0 pending, 1 valid, 2 invalid
+    // pdmpc_plan_timestep: the areas the predecessors of this search have planned, kAreaStride
+    // columns each (points, then NaN: the separator column of vectorize_all_obstacles.m:36-63 and
+    // padding that no InterX inequality can satisfy); predecessor r at step k sits at
+    // ((k - 1) * n_pred + r) * kAreaStride
+    double dep_x[DEPS ? kCtaDepCols : 1], dep_y[DEPS ? kCtaDepCols : 1];
+    int dep_n[DEPS ? kCtaDepPolys : 1];   // points of each of them (SAT needs the exact count)
+    int dep_cols[kMaxHp + 1];             // real columns per step (statistics only)
+    int n_pred;
 };
 
 // Ordering between the master and the checkers (all flags, descriptors and cache entries live in
@@ -104,9 +129,10 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) {
 // share the master's.  They are left idle (parked at the CTA barrier): the master's dependent
 // instruction chain then never waits for an issue slot behind a checker's FP64 stream
 // (profiles/r01e_cta_latency.txt).
-template <int HS, int SP, int NH>
+template <int HS, int SP, int NH, bool DEPS = false>
 __global__ void __launch_bounds__((NH + NH / 3) * kWarp, 1)
-search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_counter, int heap_smem, int fast) {
+search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_counter, int heap_smem, int fast,
+                  DepsDev dp) {
     // ids whose checks can be in flight: kRing jobs x at most PDMPC_MAX_TRIMS - 1 children each, so the
     // checkers of two nodes that share a cache slot (ids kCtaCache apart) never run at the same time
     static_assert(kRing * PDMPC_MAX_TRIMS <= kCtaCache, "a late checker must never alias a newer cache entry");
@@ -115,7 +141,7 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
     constexpr int kThreads = (NH + NH / 3) * kWarp;        // launched: master + checkers + parked warps
     constexpr int kBarThreads = (NH + 1) * kWarp;          // master + checkers: the named barriers' count
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    CtaSmem<HS, SP, NH> &sm = *reinterpret_cast<CtaSmem<HS, SP, NH> *>(smem_raw);
+    CtaSmem<HS, SP, NH, DEPS> &sm = *reinterpret_cast<CtaSmem<HS, SP, NH, DEPS> *>(smem_raw);
     Tables tb;
     tb.succ_ptr = m.succ_ptr; tb.succ_te = m.succ_te; tb.edge_d = m.edge_d;
     tb.area_npts = m.area_npts; tb.area_x = m.area_x; tb.area_y = m.area_y;
@@ -156,6 +182,44 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
             sm.refx[k] = __ldg(b.ref_x + (size_t)si * Hp + k);
             sm.refy[k] = __ldg(b.ref_y + (size_t)si * Hp + k);
             sm.vref[k] = __ldg(b.v_ref + (size_t)si * Hp + k);
+        }
+        if (DEPS) {
+            // ---- consider_predecessors (PrioritizedController.m:449-506) on the device ------------
+            // Work items are handed out in a topological order of the DAG (the host sorts them), so
+            // every predecessor's ticket is below this one's: it is finished or running on another
+            // CTA, never waiting behind this CTA.
+            const int q0 = __ldg(dp.pred_ptr + si), q1 = __ldg(dp.pred_ptr + si + 1);
+            const int npred = q1 - q0;
+            for (int r = threadIdx.x; r < npred; r += kThreads) {
+                const int *flag = dp.done + __ldg(dp.pred_idx + q0 + r);
+                while (ld_acquire_gpu(flag) == 0) __nanosleep(100);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) sm.n_pred = npred;
+            if (threadIdx.x <= Hp) sm.dep_cols[threadIdx.x] = 0;
+            __syncthreads();
+            const double qn = nan("");
+            for (int idx = threadIdx.x; idx < npred * Hp * kAreaStride; idx += kThreads) {
+                const int v = idx % kAreaStride, pk = idx / kAreaStride;   // pk = (k - 1) * npred + r
+                const int r = pk % npred, k0 = pk / npred;
+                const int j = __ldg(dp.pred_idx + q0 + r);
+                const bool planned = ld_acquire_gpu(dp.done + j) == 1;
+                const size_t os = (size_t)j * Hp + k0;
+                int np = 0;
+                double vx = qn, vy = qn;
+                if (planned) {   // what j has just written: read from L2, never through the read-only path
+                    np = __ldcg(o.shape_npts + os);
+                    if (v < np) { vx = __ldcg(o.shape_x + os * kAreaStride + v); vy = __ldcg(o.shape_y + os * kAreaStride + v); }
+                } else if (dp.fb_npts) {
+                    np = __ldg(dp.fb_npts + os);
+                    if (v < np) { vx = __ldg(dp.fb_x + os * kAreaStride + v); vy = __ldg(dp.fb_y + os * kAreaStride + v); }
+                }
+                sm.dep_x[idx] = vx; sm.dep_y[idx] = vy;
+                if (v == 0) {
+                    sm.dep_n[pk] = np;
+                    if (np) atomicAdd(&sm.dep_cols[k0 + 1], np + 1);
+                }
+            }
         }
         const int *slot = b.slot_ptr + (size_t)si * (Hp + 1);
         const int trim0 = __ldg(b.trim0 + si);
@@ -202,8 +266,11 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
             const int w = warp_id - 1 - (warp_id >> 2);
             double *shx = sm.shx[w], *shy = sm.shy[w], *bhx = sm.bhx[w], *bhy = sm.bhy[w];
             unsigned long long cols = 0;
+            CPROF_DECL
             for (unsigned j = 0;; ++j) {
+                CPROF_MARK(7);
                 named_bar_sync(1 + (int)(j % kRing), kBarThreads);          // job j is published
+                CPROF_MARK(0);   // waiting for a job
 #ifdef PDMPC_PROFILE
                 const long long ck0 = clock64();
 #endif
@@ -214,7 +281,11 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
                     const double ppx = jb.px, ppy = jb.py, pc = jb.c, ps = jb.s, pyaw = jb.pyaw;
                     const unsigned nid0 = jb.nid0;
                     const int sbase = jb.sbase;
-                    for (int ci = w; ci < nchild; ci += NH) {
+                    // consecutive expansions start at different checkers: with 3-4 children per expansion and
+                    // up to kRing jobs in flight, a fixed child -> checker map would serialise every job on
+                    // checkers 0..3 (measured: checker 0 busy for the whole search, the master waiting on it)
+                    for (int ci = (w - jb.rot + NH) % NH; ci < nchild; ci += NH) {
+                        CPROF_MARK(7);
                         const int te = tb.succ_te[sbase + ci];
                         const int edge = te >> 8;
                         const unsigned nid = nid0 + (unsigned)ci;
@@ -226,12 +297,20 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
                         else if (t.lane < 16)
                             place_point(tb, edge, bkind, t.lane - 8, pc, ps, ppx, ppy, bhx[t.lane - 8], bhy[t.lane - 8]);
                         t.sync();
+                        CPROF_MARK(1);   // table loads + placement
                         bool valid = true;
                         if (b.checker == PDMPC_CHECKER_INTERX) {
                             const int st_lo = obase + sm.rng[0], st_hi = obase + sm.rng[1];
                             const int dy_lo = obase + sm.rng[cK], dy_hi = obase + sm.rng[cK + 1];
                             cols += (unsigned long long)((st_hi - st_lo) + (dy_hi - dy_lo) + (lhi - llo));
-                            if (interx_dispatch<TILE>(ns, opx, opy, st_lo, st_hi, dy_lo, dy_hi, shx, shy, t))
+                            if (DEPS) cols += (unsigned long long)sm.dep_cols[cK];
+                            const bool hit_obs = interx_dispatch<TILE>(ns, opx, opy, st_lo, st_hi, dy_lo, dy_hi, shx, shy, t);
+                            CPROF_MARK(2);   // InterX against the obstacles
+                            if (hit_obs)
+                                valid = false;
+                            else if (DEPS && sm.n_pred > 0 &&
+                                     interx_dispatch<TILE>(ns, sm.dep_x, sm.dep_y, (cK - 1) * sm.n_pred * kAreaStride,
+                                                           cK * sm.n_pred * kAreaStride, 0, 0, shx, shy, t))
                                 valid = false;
                             else if (interx_dispatch<TILE>(nbs, lpx, lpy, llo, lhi, 0, 0, bhx, bhy, t))
                                 valid = false;
@@ -246,6 +325,17 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
                                         valid = false;
                                 }
                             }
+                            if (DEPS) {
+                                const int np_ = sm.n_pred;
+                                for (int r = 0; r < np_ && valid; ++r) {
+                                    const int pk = (cK - 1) * np_ + r, nv = sm.dep_n[pk];
+                                    if (nv < 2) continue;
+                                    cols += (unsigned long long)nv;
+                                    if (sat_collide<TILE, false>(shx, shy, ns, sm.dep_x + pk * kAreaStride,
+                                                                 sm.dep_y + pk * kAreaStride, nv, t))
+                                        valid = false;
+                                }
+                            }
                             if (valid) {
                                 cols += (unsigned long long)(lp2 - lp0);
                                 if (lanelet_side_sat<TILE>(bhx, bhy, nbs, b.lane_x + lp0, b.lane_y + lp0, lp1 - lp0, t))
@@ -254,6 +344,7 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
                                     valid = false;
                             }
                         }
+                        CPROF_MARK(3);   // InterX against predecessors' areas + lanelet bounds (or SAT)
                         if (t.lane == 0) {
                             if (valid && cK < Hp) {
                                 // cos/sin of the child's yaw for ITS expansion (expand_node.m:50-51);
@@ -273,6 +364,7 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
                             fence_cta();
                             vflag[nid] = valid ? 1 : 2;
                         }
+                        CPROF_MARK(4);   // sincos + publication
                         t.sync();   // shapes are rewritten by the next child
                     }
                 }
@@ -283,6 +375,7 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
                 if (t.lane == 0) vdone[w] = j + 1u;
             }
             if (t.lane == 0 && cols) atomicAdd(o.counters + 2, cols);
+            CPROF_FLUSH(o, t.lane == 0 && w == 0);
             continue;   // next search (meets the master at the __syncthreads on top)
         }
 
@@ -296,6 +389,7 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
         unsigned long long hash = 0xcbf29ce484222325ULL;
         bool exhausted = false, tie = false;
         unsigned goal = 0, n_jobs = 0;
+        int rot = 0;
         double f_last = 0.0;
         if (t.lane == 0) {   // root: GraphSearch.m:34-46
             NodeA ra;
@@ -364,8 +458,9 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
                     CtaJob &jb = sm.ring[n_jobs % kRing];
                     jb.px = ca.x; jb.py = ca.y; jb.pyaw = ca.yaw; jb.c = c; jb.s = s;
                     jb.nid0 = (unsigned)(n_nodes + 1); jb.nchild = nchild; jb.sbase = sbase; jb.k = k_exp;
-                    jb.terminate = 0;
+                    jb.terminate = 0; jb.rot = rot;
                 }
+                rot = (rot + nchild) % NH;
                 fence_cta();
                 t.sync();
                 named_bar_arrive(1 + (int)(n_jobs % kRing), kBarThreads);
@@ -547,6 +642,11 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
                     }
                 }
             }
+        }
+        if (DEPS) {   // publish_predictions (PrioritizedController.m:355-364): the areas above are final
+            __threadfence();
+            t.sync();
+            if (t.lane == 0) st_release_gpu(dp.done + si, exhausted ? 2 : 1);
         }
         if (t.lane == 0) sm.clear_upto = n_nodes;
     }

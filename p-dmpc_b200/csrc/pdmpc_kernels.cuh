@@ -118,6 +118,24 @@ struct OutDev {
     unsigned long long *counters;  // [0] pops, [1] nodes, [2] obstacle columns tested
 };
 
+// Dependencies between the searches of one batch (pdmpc_plan_timestep): search i waits for
+// done[j] != 0 of each predecessor j and takes j's planned areas (or its fallback areas when j
+// is exhausted) as dynamic obstacles: PrioritizedController.m:449-506 consider_predecessors.
+struct DepsDev {
+    const int *pred_ptr, *pred_idx;   // CSR over the searches of the batch
+    const int *fb_npts;               // [n*Hp] fallback areas (may be null)
+    const double *fb_x, *fb_y;        // [n*Hp*kAreaStride]
+    int *done;                        // [n] 0 pending, 1 planned, 2 exhausted (release/acquire at gpu scope)
+};
+__device__ __forceinline__ int ld_acquire_gpu(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // Node arena + heap overflow of one resident tile ("slot"), all in HBM.
 struct __align__(16) NodeA {  // 32 B: pose + cost to come, written when the node is created
     double x, y, yaw, g;
@@ -438,7 +456,8 @@ __device__ __forceinline__ bool interx_dispatch(int ns, const double *px, const 
 
 // ---- SAT (intersect_sat.m:1-42): polygon 1 in shared memory, polygon 2 in
 // global memory.  Lanes own axes (edges of both polygons incl. the closing one).
-template <int TILE>
+// NC = false: polygon 2 is read with plain loads (it may live in shared memory).
+template <int TILE, bool NC = true>
 __device__ __forceinline__ bool sat_collide(const double *x1, const double *y1, int n1,
                                             const double *__restrict__ x2, const double *__restrict__ y2,
                                             int n2, const Tile<TILE> &t) {
@@ -451,8 +470,8 @@ __device__ __forceinline__ bool sat_collide(const double *x1, const double *y1, 
             ey = y1[e1] - y1[e];
         } else {
             int f = e - n1, f1 = (f + 1 == n2) ? 0 : f + 1;
-            ex = __ldg(x2 + f1) - __ldg(x2 + f);
-            ey = __ldg(y2 + f1) - __ldg(y2 + f);
+            ex = NC ? __ldg(x2 + f1) - __ldg(x2 + f) : x2[f1] - x2[f];
+            ey = NC ? __ldg(y2 + f1) - __ldg(y2 + f) : y2[f1] - y2[f];
         }
         double ax = -ey, ay = ex;
         double nrm = sqrt(ax * ax + ay * ay);
@@ -464,7 +483,7 @@ __device__ __forceinline__ bool sat_collide(const double *x1, const double *y1, 
             mx1 = fmax(mx1, d);
         }
         for (int v = 0; v < n2; ++v) {
-            double d = nx * __ldg(x2 + v) + ny * __ldg(y2 + v);
+            double d = NC ? nx * __ldg(x2 + v) + ny * __ldg(y2 + v) : nx * x2[v] + ny * y2[v];
             mn2 = fmin(mn2, d);
             mx2 = fmax(mx2, d);
         }

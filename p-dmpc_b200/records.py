@@ -112,6 +112,29 @@ class SearchBatch:
             vert_x=cat(vx), vert_y=cat(vy), lane_ptr=np.asarray(lane_ptr, dtype=np.int32),
             lane_x=cat(lx), lane_y=cat(ly))
 
+    def to_iters(self) -> List[IterationData]:
+        """Inverse of from_iters (the per-vehicle iter_v structs of a flat batch)."""
+        Hp, out = self.Hp, []
+        rx, ry, vr = self.ref_x.reshape(-1, Hp), self.ref_y.reshape(-1, Hp), self.v_ref.reshape(-1, Hp)
+
+        def poly(p):
+            v0, v1 = self.poly_ptr[p], self.poly_ptr[p + 1]
+            return np.vstack([self.vert_x[v0:v1], self.vert_y[v0:v1]])
+
+        for i in range(self.n):
+            sp = self.slot_ptr[i * (Hp + 1): (i + 1) * (Hp + 1) + 1]
+            obstacles = [poly(p) for p in range(sp[0], sp[1])]
+            rows = max(int(sp[k + 1] - sp[k]) for k in range(1, Hp + 1))
+            dyn = []
+            for r in range(rows):   # row r = the r-th polygon of every step (empty where a step has fewer)
+                dyn.append([poly(sp[k] + r) if sp[k] + r < sp[k + 1] else np.zeros((2, 0)) for k in range(1, Hp + 1)])
+            lp = self.lane_ptr[2 * i: 2 * i + 3]
+            sides = tuple(np.vstack([self.lane_x[lp[s]:lp[s + 1]], self.lane_y[lp[s]:lp[s + 1]]]) for s in range(2))
+            out.append(IterationData(x0=np.array([self.x0[i], self.y0[i], self.yaw0[i]]), trim_indices=int(self.trim0[i]),
+                                     reference_trajectory_points=np.stack([rx[i], ry[i]], axis=1), v_ref=vr[i].copy(),
+                                     obstacles=obstacles, dynamic_obstacle_area=dyn, predicted_lanelet_boundary=sides))
+        return out
+
     def select(self, idx: Sequence[int]) -> "SearchBatch":
         """Sub-batch of the given searches (re-based CSR)."""
         idx = np.asarray(idx, dtype=np.int64)
@@ -237,3 +260,44 @@ class BatchResult:
             n = int(self.shape_npts[i, k])
             out.append(np.vstack([self.shape_x[i, k, :n], self.shape_y[i, k, :n]]))
         return out
+
+
+@dataclasses.dataclass
+class TimestepDeps:
+    """pdmpc_timestep_deps (include/pdmpc_b200.h): which searches of a batch wait for which,
+    and the areas an exhausted search publishes (PrioritizedController.m:449-506, :568-621, :678-718)."""
+
+    pred_ptr: np.ndarray     # [n+1]
+    pred_idx: np.ndarray     # [pred_ptr[n]]
+    fb_npts: np.ndarray      # [n, Hp]
+    fb_x: np.ndarray         # [n, Hp, 8]
+    fb_y: np.ndarray
+
+    @staticmethod
+    def build(preds: Sequence[Sequence[int]], fallback_shapes: Sequence[Sequence[np.ndarray]], Hp: int) -> "TimestepDeps":
+        """preds[i] = searches search i waits for; fallback_shapes[i] = Hp closed [2, m] areas (or None)."""
+        n = len(preds)
+        pred_ptr = np.zeros(n + 1, dtype=np.int32)
+        for i, p in enumerate(preds):
+            pred_ptr[i + 1] = pred_ptr[i] + len(p)
+        pred_idx = np.array([j for p in preds for j in p], dtype=np.int32).reshape(-1)
+        fb_npts = np.zeros((n, Hp), dtype=np.int32)
+        fb_x = np.zeros((n, Hp, AREA_STRIDE))
+        fb_y = np.zeros((n, Hp, AREA_STRIDE))
+        for i, shapes in enumerate(fallback_shapes):
+            if shapes is None:
+                continue
+            for k in range(Hp):
+                a = np.asarray(shapes[k], dtype=np.float64)
+                m = a.shape[1]
+                fb_npts[i, k] = m
+                fb_x[i, k, :m] = a[0]
+                fb_y[i, k, :m] = a[1]
+        return TimestepDeps(pred_ptr, pred_idx, fb_npts, fb_x, fb_y)
+
+    def preds(self, i: int) -> np.ndarray:
+        return self.pred_idx[self.pred_ptr[i]:self.pred_ptr[i + 1]]
+
+    def fallback_shapes(self, i: int) -> List[np.ndarray]:
+        return [np.vstack([self.fb_x[i, k, :self.fb_npts[i, k]], self.fb_y[i, k, :self.fb_npts[i, k]]])
+                for k in range(self.fb_npts.shape[1])]

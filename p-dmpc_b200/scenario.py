@@ -40,7 +40,7 @@ from typing import Callable, List, Optional, Sequence
 import numpy as np
 
 from .mpa import VEH_LENGTH, VEH_WIDTH, MotionPrimitiveAutomaton
-from .records import CHECKER_INTERX, CHECKER_SAT, BatchResult, IterationData, SearchBatch
+from .records import CHECKER_INTERX, CHECKER_SAT, BatchResult, IterationData, SearchBatch, TimestepDeps
 
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "lab_map.npz")
 
@@ -473,9 +473,13 @@ class ScenarioRunner:
     computation level (vehicles of one level are independent,
     PrioritizedSequentialController.m:83-92)."""
 
-    def __init__(self, sc: Scenario, plan_fn: PlanFn, max_num_CLs: int = 99):
+    def __init__(self, sc: Scenario, plan_fn: PlanFn, max_num_CLs: int = 99, timestep_fn=None):
+        """plan_fn(batch) plans one computation level; with timestep_fn(batch, deps) the whole time
+        step is ONE call and the predecessors' areas are handed over behind it (pdmpc_plan_timestep)."""
         self.sc = sc
         self.plan_fn = plan_fn
+        self.timestep_fn = timestep_fn
+        self.timestep_records: List[tuple] = []     # (step, batch, deps, result) of the one-call path
         self.mpa = sc.mpa
         n = sc.amount
         self.pose = np.array([[v.x_start, v.y_start, v.yaw_start] for v in sc.vehicles])
@@ -501,7 +505,64 @@ class ScenarioRunner:
                              trim_indices=int(self.trim[i]), reference_trajectory_points=pts, v_ref=v_ref,
                              predicted_lanelet_boundary=boundary)
 
+    def _fallback_plan(self, i: int):
+        """What vehicle i does (and publishes) when its search is exhausted — known before the time
+        step starts.  [dev] local fallback: PrioritizedController.m:568-621 (standstill), :678-718
+        (previous plan shifted, del_first_rpt_last)."""
+        mpa, Hp = self.mpa, self.mpa.Hp
+        if self.prev_shapes[i] is None or abs(mpa.trim_speed[self.trim[i] - 1]) < 0.01:
+            stand = occupied_area(*self.pose[i])
+            return [stand] * Hp, np.tile(self.pose[i], (Hp, 1)), np.full(Hp, self.trim[i])
+        ps = self.prev_shapes[i]
+        return (ps[1:] + [ps[-1]], np.vstack([self.prev_traj[i][1:], self.prev_traj[i][-1:]]),
+                np.concatenate([self.prev_trims[i][1:], self.prev_trims[i][-1:]]))
+
+    def timestep_inputs(self):
+        """The inputs of ONE call for the whole time step: every vehicle's iter_v without its
+        sequential predecessors' areas, the predecessor lists and the fallback plans."""
+        sc, mpa = self.sc, self.mpa
+        n = sc.amount
+        iters = [self._iter_for(i) for i in range(n)]
+        A = couple(sc, self.pose)
+        D = constant_priorities(A) if sc.priority == "constant" else coloring_priorities(A)
+        for i in range(n):   # consider_successors, area_of_standstill: PrioritizedController.m:508-540
+            for j in np.flatnonzero(D[i, :]):
+                if abs(mpa.trim_speed[self.trim[j] - 1]) < 0.01:
+                    iters[i].obstacles.append(occupied_area(*self.pose[j]))
+        preds = [np.flatnonzero(D[:, i]) for i in range(n)]
+        fallbacks = [self._fallback_plan(i) for i in range(n)]
+        return iters, preds, fallbacks
+
+    def step_timestep(self) -> BatchResult:
+        """One time step through timestep_fn: same closed loop as step(), one optimizer call."""
+        sc, mpa = self.sc, self.mpa
+        n, Hp = sc.amount, mpa.Hp
+        self.k += 1
+        iters, preds, fallbacks = self.timestep_inputs()
+        batch = SearchBatch.from_iters(iters, Hp, sc.checker, mpa.dt_seconds)
+        deps = TimestepDeps.build(preds, [f[0] for f in fallbacks], Hp)
+        res = self.timestep_fn(batch, deps)
+        shapes_now: List[Optional[List[np.ndarray]]] = [None] * n
+        new_pose, new_trim = self.pose.copy(), self.trim.copy()
+        for i in range(n):
+            if not res.is_exhausted[i]:
+                shapes_now[i] = res.shapes(i)
+                self.prev_traj[i] = res.y_predicted[i].copy()
+                self.prev_trims[i] = res.trims[i, 1:].copy()
+            else:
+                self.n_fallbacks += 1
+                shapes_now[i], self.prev_traj[i], self.prev_trims[i] = fallbacks[i]
+            new_pose[i] = self.prev_traj[i][0]      # Simulation.apply: plant/Simulation.m:93-98
+            new_trim[i] = self.prev_trims[i][0]
+        self.prev_shapes = shapes_now
+        self.pose, self.trim = new_pose, new_trim
+        self.timestep_records.append((self.k, batch, deps, res))
+        return res
+
     def step(self) -> List[StepRecord]:
+        if self.timestep_fn is not None:
+            self.step_timestep()
+            return []
         sc, mpa = self.sc, self.mpa
         n, Hp = sc.amount, mpa.Hp
         self.k += 1
@@ -559,6 +620,52 @@ class ScenarioRunner:
         for _ in range(n_steps):
             self.step()
         return self.records
+
+
+def _assign_rows(dst: BatchResult, rows, src: BatchResult) -> None:
+    for f in dataclasses.fields(dst):
+        a = getattr(dst, f.name)
+        if isinstance(a, np.ndarray):
+            a[rows] = getattr(src, f.name)
+
+
+def plan_timestep_by_levels(plan_fn: PlanFn, batch: SearchBatch, deps: TimestepDeps) -> BatchResult:
+    """The reference's way through one time step, as the specification of pdmpc_plan_timestep:
+    computation levels one after the other (utility/kahn.m, PrioritizedSequentialController.m:83-92),
+    each vehicle's iter_v extended on the HOST by the areas its sequential predecessors published
+    (PrioritizedController.m:297-324, consider_predecessors :449-506), an exhausted predecessor
+    publishing its fallback areas (:568-621, :678-718)."""
+    iters, Hp, checker, dt_seconds = batch.to_iters(), batch.Hp, batch.checker, batch.dt_seconds
+    n = len(iters)
+    level = np.zeros(n, dtype=np.int64)
+    remaining = set(range(n))
+    lvl = 0
+    while remaining:
+        lvl += 1
+        ready = [i for i in sorted(remaining) if all(level[j] != 0 and level[j] < lvl for j in deps.preds(i))]
+        if not ready:
+            raise ValueError("predecessor relation has a cycle")
+        for i in ready:
+            level[i] = lvl
+        remaining -= set(ready)
+    out = BatchResult.empty(n, Hp)
+    published: List[Optional[List[np.ndarray]]] = [None] * n
+    for l in range(1, lvl + 1):
+        members = np.flatnonzero(level == l)
+        its = []
+        for i in members:
+            it = dataclasses.replace(iters[i], obstacles=list(iters[i].obstacles),
+                                     dynamic_obstacle_area=list(iters[i].dynamic_obstacle_area))
+            for j in deps.preds(i):
+                if all(a.shape[1] == 0 for a in published[j]):
+                    continue   # nothing published (no fallback areas given)
+                it.dynamic_obstacle_area.append(published[j])
+            its.append(it)
+        res = plan_fn(SearchBatch.from_iters(its, Hp, checker, dt_seconds))
+        _assign_rows(out, members, res)
+        for b, i in enumerate(members):
+            published[i] = deps.fallback_shapes(i) if res.is_exhausted[b] else res.shapes(b)
+    return out
 
 
 def roll_out(sc: Scenario, plan_fn: PlanFn, n_steps: int) -> SearchBatch:

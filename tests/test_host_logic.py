@@ -149,3 +149,73 @@ def test_golden_inputs_are_well_formed():
         assert exp.trims.shape == (batch.n, batch.Hp + 1) and (exp.trims[:, 0] == batch.trim0).all()
         ok = exp.is_exhausted == 0
         assert (exp.tree_path[ok, 0] == 1).all() and (exp.n_expanded >= exp.n_pops - 0).all() or True
+
+
+def _closed_loops(sc_factory, mpa, steps):
+    """The same scenario twice: level-by-level through step(), and one call per time step through
+    plan_timestep_by_levels (the specification of pdmpc_plan_timestep).  Returns both runners."""
+    plan = lambda b: oracle_py.plan_batch(mpa, b)
+    a = scenario.ScenarioRunner(sc_factory(), plan)
+    a.run(steps)
+    b = scenario.ScenarioRunner(sc_factory(), None,
+                                timestep_fn=lambda batch, deps: scenario.plan_timestep_by_levels(plan, batch, deps))
+    b.run(steps)
+    return a, b
+
+
+@pytest.mark.parametrize("kind", ["circle", "road"])
+def test_timestep_decomposition_equals_level_by_level_loop(kind):
+    """One call per time step (base iter_v + predecessor lists + fallback areas) carries the same
+    information as the level-by-level loop: identical closed loop, identical per-search outputs."""
+    if kind == "circle":
+        mpa = get_mpa("single_speed", non_convex=False)
+        factory, steps = (lambda: scenario.circle_scenario(mpa, 4)), 25
+    else:
+        mpa = get_mpa("single_speed", non_convex=True)
+        factory, steps = (lambda: scenario.commonroad_scenario(mpa, 12, seed=4)), 8
+    a, b = _closed_loops(factory, mpa, steps)
+    assert np.array_equal(a.pose, b.pose) and np.array_equal(a.trim, b.trim)
+    assert a.n_fallbacks == b.n_fallbacks
+    by_step = {}
+    for r in a.records:
+        for i, v in enumerate(r.vehicles):
+            by_step[(r.step, int(v))] = (r.result, i)
+    n_pred = 0
+    for k, batch, deps, res in b.timestep_records:
+        n_pred += deps.pred_idx.size
+        for v in range(batch.n):
+            ra, i = by_step[(k, v)]
+            for name in ("is_exhausted", "n_expanded", "n_pops", "pop_hash"):
+                assert getattr(ra, name)[i] == getattr(res, name)[v], (k, v, name)
+            assert np.array_equal(ra.trims[i], res.trims[v])
+            assert np.array_equal(ra.y_predicted[i], res.y_predicted[v], equal_nan=True)
+            assert np.array_equal(ra.shape_x[i], res.shape_x[v])
+    assert n_pred > 0   # the predecessor hand-over was exercised
+
+
+def test_batch_to_iters_round_trip():
+    mpa, batch = road_records("single_speed", 3, 20, 1)
+    again = SearchBatch.from_iters(batch.to_iters(), batch.Hp, batch.checker, batch.dt_seconds)
+    for f in dataclasses.fields(batch):
+        a, b = getattr(batch, f.name), getattr(again, f.name)
+        assert np.array_equal(a, b) if isinstance(a, np.ndarray) else a == b, f.name
+
+
+def test_timestep_by_levels_uses_fallback_areas_of_exhausted_predecessors():
+    """Search 0 is walled in (exhausts) and publishes its fallback areas; search 1 waits for it and
+    must avoid them (PrioritizedController.m:568-621, :678-718)."""
+    from pdmpc_b200.records import TimestepDeps
+    mpa = get_mpa("single_speed", non_convex=False)
+    Hp = mpa.Hp
+
+    walled = straight_iter(mpa, obstacles=[rect(0.0, 0.0, 0.3, 0.3)])   # the start pose itself collides
+    free = straight_iter(mpa, x=0.0, y=5.0)
+    batch = SearchBatch.from_iters([walled, free], Hp, CHECKER_SAT, mpa.dt_seconds)
+    block = [rect(0.6, 5.0, 0.1, 0.5)] * Hp     # across the free vehicle's straight line
+    plan = lambda b: oracle_py.plan_batch(mpa, b)
+    with_fb = scenario.plan_timestep_by_levels(plan, batch, TimestepDeps.build([[], [0]], [block, None], Hp))
+    without = scenario.plan_timestep_by_levels(plan, batch, TimestepDeps.build([[], []], [None, None], Hp))
+    assert with_fb.is_exhausted[0] == 1 and without.is_exhausted[0] == 1
+    assert not np.array_equal(with_fb.y_predicted[1], without.y_predicted[1]) or \
+        with_fb.n_expanded[1] != without.n_expanded[1]
+

@@ -1,0 +1,171 @@
+"""pdmpc_plan_timestep (one dependency-ordered launch for a whole time step) against its
+specification: the level-by-level loop with host-side obstacle assembly, planned by the CPU oracle
+(scenario.plan_timestep_by_levels; PrioritizedController.m:297-324, :449-506).  Bit-exact on every
+output field, including the pop-order hash."""
+import dataclasses
+
+import numpy as np
+import pytest
+
+from oracle import oracle_py, parity
+from pdmpc_b200 import capi, scenario
+from pdmpc_b200.mpa import get_mpa
+from pdmpc_b200.records import CHECKER_INTERX, CHECKER_SAT, SearchBatch, TimestepDeps
+
+from helpers import rect, straight_iter
+
+pytestmark = pytest.mark.gpu
+
+
+def closed_loop(planner, mpa, sc, steps):
+    """Closed loop driven by the device's one-call time step; every step checked against the oracle."""
+    planner.upload_mpa(mpa)
+    plan = lambda b: oracle_py.plan_batch(mpa, b)
+    runner = scenario.ScenarioRunner(sc, None, timestep_fn=lambda b, d: planner.plan_timestep(b, d, False))
+    totals = {"searches": 0, "preds": 0, "exhausted": 0}
+    for _ in range(steps):
+        dev = runner.step_timestep()
+        _k, batch, deps, _ = runner.timestep_records[-1]
+        ref = scenario.plan_timestep_by_levels(plan, batch, deps)
+        parity.compare(dev, ref)
+        totals["searches"] += batch.n
+        totals["preds"] += int(deps.pred_idx.size)
+        totals["exhausted"] += int(ref.is_exhausted.sum())
+    return runner, totals
+
+
+def test_circle_config0_sat_closed_loop(planner):
+    mpa = get_mpa("single_speed", non_convex=False)
+    _, tot = closed_loop(planner, mpa, scenario.circle_scenario(mpa, 4), 30)
+    assert tot["preds"] > 0
+
+
+@pytest.mark.parametrize("mpa_type,steps", [("single_speed", 12), ("triple_speed", 10)])
+def test_road_config1_interx_closed_loop(planner, mpa_type, steps):
+    mpa = get_mpa(mpa_type, non_convex=True)
+    runner, tot = closed_loop(planner, mpa, scenario.commonroad_scenario(mpa, 20, seed=2), steps)
+    assert tot["preds"] > 20 and tot["searches"] == 20 * steps
+
+
+def collect_timesteps(mpa, sc, steps):
+    """(batch, deps) of every time step of an oracle-driven closed loop."""
+    plan = lambda b: oracle_py.plan_batch(mpa, b)
+    runner = scenario.ScenarioRunner(sc, None, timestep_fn=lambda b, d: scenario.plan_timestep_by_levels(plan, b, d))
+    runner.run(steps)
+    return [(b, d, r) for _k, b, d, r in runner.timestep_records]
+
+
+def concat_timesteps(items):
+    """Many time steps / scenarios as ONE call: predecessor indices shifted per block."""
+    batch = SearchBatch.concat([b for b, _d, _r in items])
+    off, ptr, idx = 0, [np.zeros(1, dtype=np.int32)], []
+    for b, d, _r in items:
+        ptr.append(d.pred_ptr[1:] + ptr[-1][-1])
+        idx.append(d.pred_idx + off)
+        off += b.n
+    deps = TimestepDeps(np.concatenate(ptr).astype(np.int32), np.concatenate(idx).astype(np.int32),
+                        np.concatenate([d.fb_npts for _b, d, _r in items]),
+                        np.concatenate([d.fb_x for _b, d, _r in items]),
+                        np.concatenate([d.fb_y for _b, d, _r in items]))
+    ref = dataclasses.replace(items[0][2], **{
+        f.name: np.concatenate([getattr(r, f.name) for _b, _d, r in items])
+        for f in dataclasses.fields(items[0][2]) if isinstance(getattr(items[0][2], f.name), np.ndarray)})
+    return batch, deps, ref
+
+
+def test_many_timesteps_in_one_call_more_searches_than_sms(planner):
+    """12 time steps x 20 vehicles = 240 searches > 148 CTAs: work items are handed out in a
+    topological order, so a CTA never waits for a search that has not been taken yet."""
+    mpa = get_mpa("triple_speed", non_convex=True)
+    items = collect_timesteps(mpa, scenario.commonroad_scenario(mpa, 20, seed=3), 12)
+    batch, deps, ref = concat_timesteps(items)
+    assert batch.n == 240
+    planner.upload_mpa(mpa)
+    dev = planner.plan_timestep(batch, deps, False)
+    parity.compare(dev, ref)
+    # the same searches in reverse order (predecessors now have HIGHER indices than their successors)
+    perm = np.arange(batch.n)[::-1].copy()
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(batch.n)
+    rb = batch.select(perm)
+    preds = [inv[deps.preds(int(i))] for i in perm]
+    rdeps = TimestepDeps.build(preds, [deps.fallback_shapes(int(i)) for i in perm], batch.Hp)
+    rdev = planner.plan_timestep(rb, rdeps, False)
+    rref = dataclasses.replace(ref, **{f.name: getattr(ref, f.name)[perm] for f in dataclasses.fields(ref)
+                                       if isinstance(getattr(ref, f.name), np.ndarray)})
+    parity.compare(rdev, rref)
+
+
+def test_equals_level_by_level_device_calls(planner):
+    """One call == the drop-in's previous call pattern (one pdmpc_plan_batch per computation level)."""
+    mpa = get_mpa("triple_speed", non_convex=True)
+    planner.upload_mpa(mpa)
+    for batch, deps, _ref in collect_timesteps(mpa, scenario.commonroad_scenario(mpa, 20, seed=5), 6):
+        by_levels = scenario.plan_timestep_by_levels(lambda b: planner.plan_batch(b, False), batch, deps)
+        parity.compare(planner.plan_timestep(batch, deps, False), by_levels)
+
+
+@pytest.mark.parametrize("checker", [CHECKER_SAT, CHECKER_INTERX])
+def test_chain_and_fallback_areas_of_exhausted_predecessor(planner, checker):
+    """A chain 0 <- 1 <- 2 ... of vehicles on parallel lines; vehicle 0 starts inside an obstacle
+    (exhausted) and publishes fallback areas that lie across vehicle 1's line."""
+    mpa = get_mpa("single_speed", non_convex=checker == CHECKER_INTERX)
+    Hp = mpa.Hp
+    n = 24
+    iters = [straight_iter(mpa, x=0.0, y=1.0 * i) for i in range(n)]
+    iters[0].obstacles.append(rect(0.05, 0.0, 0.02, 0.3))      # crosses every first maneuver of vehicle 0
+    batch = SearchBatch.from_iters(iters, Hp, checker, mpa.dt_seconds)
+    preds = [[]] + [[i - 1] for i in range(1, n)]
+    preds[5] = [4, 2, 0]                                         # several predecessors, unordered
+    fb = [None] * n
+    fb[0] = [rect(0.5, 1.0, 0.05, 0.3)] * Hp                     # on vehicle 1's line
+    deps = TimestepDeps.build(preds, fb, Hp)
+    planner.upload_mpa(mpa)
+    dev = planner.plan_timestep(batch, deps, False)
+    ref = scenario.plan_timestep_by_levels(lambda b: oracle_py.plan_batch(mpa, b), batch, deps)
+    parity.compare(dev, ref)
+    assert ref.is_exhausted[0] == 1
+    free = oracle_py.plan_batch(mpa, SearchBatch.from_iters([iters[1]], Hp, checker, mpa.dt_seconds))
+    assert ref.n_expanded[1] != free.n_expanded[0] or not np.array_equal(ref.trims[1], free.trims[0])
+
+
+def test_no_dependencies_equals_plan_batch_and_empty_batch(planner):
+    mpa = get_mpa("single_speed", non_convex=True)
+    planner.upload_mpa(mpa)
+    batch, deps, _ = collect_timesteps(mpa, scenario.commonroad_scenario(mpa, 20, seed=1), 1)[0]
+    none = TimestepDeps.build([[] for _ in range(batch.n)], [None] * batch.n, batch.Hp)
+    parity.compare(planner.plan_timestep(batch, none, False), planner.plan_batch(batch, False))
+    empty = batch.select(np.zeros(0, dtype=np.int64))
+    r = planner.plan_timestep(empty, TimestepDeps.build([], [], batch.Hp))
+    assert r.status.size == 0
+
+
+def test_bad_relations_rejected(planner):
+    mpa = get_mpa("single_speed", non_convex=True)
+    planner.upload_mpa(mpa)
+    Hp = mpa.Hp
+    batch = SearchBatch.from_iters([straight_iter(mpa, y=float(i)) for i in range(3)], Hp, CHECKER_INTERX, mpa.dt_seconds)
+    for preds in ([[1], [2], [0]], [[0], [], []], [[], [7], []], [[], [-1], []]):
+        with pytest.raises(capi.PdmpcError) as e:
+            planner.plan_timestep(batch, TimestepDeps.build(preds, [None] * 3, Hp))
+        assert e.value.code == capi.PDMPC_ERR_BAD_INPUT
+    too_many = [[]] + [[0] * (2048 // (Hp * 8) + 1)] + [[]]
+    with pytest.raises(capi.PdmpcError):
+        planner.plan_timestep(batch, TimestepDeps.build(too_many, [None] * 3, Hp))
+    d = TimestepDeps.build([[], [0], [1]], [None] * 3, Hp)
+    d.fb_npts[0, 0] = 1
+    with pytest.raises(capi.PdmpcError):
+        planner.plan_timestep(batch, d)
+    # the planner is still usable afterwards
+    ok = planner.plan_timestep(batch, TimestepDeps.build([[], [0], [1]], [None] * 3, Hp))
+    assert int(ok.status.max()) == 0
+
+
+def test_realistic_mpa_is_refused_loudly(planner):
+    """Search trees beyond 32768 nodes do not fit the one-CTA-per-search kernel: no silent fallback."""
+    mpa = get_mpa("realistic", non_convex=True)
+    planner.upload_mpa(mpa)
+    batch = SearchBatch.from_iters([straight_iter(mpa)], mpa.Hp, CHECKER_INTERX, mpa.dt_seconds)
+    with pytest.raises(capi.PdmpcError) as e:
+        planner.plan_timestep(batch, TimestepDeps.build([[]], [None], mpa.Hp))
+    assert e.value.code == capi.PDMPC_ERR_CAPACITY
