@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--mpa", default="triple_speed")
     ap.add_argument("--no-cache", action="store_true", help="do not read/write the record cache under build/")
     ap.add_argument("--cpu-sample", type=int, default=0, help="searches in the CPU sample (0 = auto)")
+    ap.add_argument("--pipeline-chunks", type=int, default=0,
+                    help="chunks of the e2e call's copy/search pipeline (0 = library default, 1 = off)")
     return ap.parse_args()
 
 
@@ -345,20 +347,27 @@ def main():
             setattr(out, f.name, pinned_like(a))
     import ctypes as C
     bi, bo = capi.batch_in(hb), capi.batch_out(out)
-    for _ in range(2):
-        planner._check(planner.lib.pdmpc_plan_batch(planner.h, C.byref(bi), C.byref(bo)))
-    barrier()
-    t0 = time.perf_counter()
     e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(e2e_steps):
-        planner._check(planner.lib.pdmpc_plan_batch(planner.h, C.byref(bi), C.byref(bo)))
-    torch.cuda.synchronize()
-    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{dev}")
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_val = n * world * e2e_steps / float(t_e2e.item())
+
+    def time_e2e(chunks: int, steps: int) -> float:
+        planner.set_pipeline_chunks(chunks)
+        for _ in range(2):
+            planner._check(planner.lib.pdmpc_plan_batch(planner.h, C.byref(bi), C.byref(bo)))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            planner._check(planner.lib.pdmpc_plan_batch(planner.h, C.byref(bi), C.byref(bo)))
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{dev}")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        assert np.array_equal(out.pop_hash, res.pop_hash), "e2e path and staged path disagree"
+        return n * world * steps / float(t.item())
+
+    e2e_serial = time_e2e(1, 3)                     # copy in, search, copy out, one after the other
+    e2e_val = time_e2e(args.pipeline_chunks, e2e_steps)   # the library's default: chunked pipeline
     st2 = planner.stats()
-    assert np.array_equal(out.pop_hash, res.pop_hash), "e2e path and staged path disagree"
+    planner.set_pipeline_chunks(0)
 
     # ---- per-time-step latency (levels sequential, host buffers) -----------------
     # What the drop-in does for one 20-vehicle time step: one pdmpc_plan_batch call per
@@ -460,6 +469,9 @@ def main():
                        "record_generation_s": round(t_gen, 1)},
             "e2e": {"value": e2e_val, "unit": "plans/s", "h2d_bytes_per_step": int(st2.h2d_bytes),
                     "d2h_bytes_per_step": int(st2.d2h_bytes), "steps": e2e_steps,
+                    "pipeline": "chunked copy/search overlap inside pdmpc_plan_batch (pdmpc_set_pipeline_chunks "
+                                f"{args.pipeline_chunks}: 0 = library default)",
+                    "value_without_pipeline": e2e_serial,
                     "h2d_ms": st2.h2d_ms, "kernel_ms": st2.kernel_ms, "d2h_ms": st2.d2h_ms},
             "gpu_launches": int(args.steps * 1),   # one persistent search kernel per timed step (staged path)
             "clocks": clocks,

@@ -209,6 +209,12 @@ int pdmpc_set_lane_limits(pdmpc_handle *h, int32_t nodes_per_thread, int32_t pop
  * queue spills to the HBM arena.  Tuning/test knob: results do not depend on it. */
 int pdmpc_set_cta_heap_smem(pdmpc_handle *h, int32_t entries);
 
+/* pdmpc_plan_batch on large host batches (>= 16384 searches, launch shapes 0..2) runs as a chunked
+ * pipeline: host->device copies, searches and device->host copies of consecutive chunks overlap.
+ * chunks: 0 = choose from the batch size (default), 1 = off, 2..16 = that many chunks for any batch
+ * of at least 2*chunks searches.  Tuning/test knob: results do not depend on it. */
+int pdmpc_set_pipeline_chunks(pdmpc_handle *h, int32_t chunks);
+
 /* Stage the MPA tables in HBM (once per MPA; cached in the handle). */
 int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *mpa);
 

@@ -93,6 +93,14 @@ struct pdmpc_handle {
     DepsDev deps{};
     bool deps_staged = false;
     std::vector<int> topo_order;      // work order override for the next pdmpc_stage_batch (time-step calls)
+    // pipelined pdmpc_plan_batch (large host batches): copy-in, two compute and copy-out streams
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_comp[7] = {};   // + the handle's stream
+    std::vector<cudaEvent_t> ev_chunk;   // 2 per chunk: inputs landed, searches done
+    cudaEvent_t ev_fork = nullptr;
+    void *pin_order = nullptr;
+    size_t pin_order_cap = 0;
+    DBuf wc_chunks;
+    int pipeline_chunks = 0;          // 0 = auto, 1 = off (tuning/test knob, pdmpc_set_pipeline_chunks)
     bool lanes_ok = false;            // every maneuver area has <= 7 points
     bool lanes_smem_ok = false;       // MPA tables fit in shared memory next to nothing else
     size_t lanes_smem = 0;
@@ -228,6 +236,14 @@ int pdmpc_destroy(pdmpc_handle *h) {
     h->d_out_pack.release();
     h->d_deps.release();
     h->d_done.release();
+    h->wc_chunks.release();
+    if (h->pin_order) cudaFreeHost(h->pin_order);
+    for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    for (cudaStream_t st : h->s_comp)
+        if (st) cudaStreamDestroy(st);
+    for (cudaStream_t st : {h->s_in, h->s_out})
+        if (st) cudaStreamDestroy(st);
     if (h->pin_deps) cudaFreeHost(h->pin_deps);
     if (h->pin_in) cudaFreeHost(h->pin_in);
     if (h->pin_out) cudaFreeHost(h->pin_out);
@@ -435,8 +451,8 @@ int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *d) {
     return PDMPC_OK;
 }
 
-static int validate_batch(pdmpc_handle *h, const pdmpc_batch_in *in) {
-    const int n = in->n_searches, Hp = h->mpa.Hp, nT = h->mpa.nT;
+static int validate_header(pdmpc_handle *h, const pdmpc_batch_in *in) {
+    const int n = in->n_searches;
     if (n < 0) return fail(h, PDMPC_ERR_BAD_INPUT, "plan: n_searches < 0");
     if (in->checker != PDMPC_CHECKER_SAT && in->checker != PDMPC_CHECKER_INTERX)
         return fail(h, PDMPC_ERR_BAD_INPUT, "plan: unknown checker");
@@ -445,15 +461,20 @@ static int validate_batch(pdmpc_handle *h, const pdmpc_batch_in *in) {
     if (!in->x0 || !in->y0 || !in->yaw0 || !in->trim0 || !in->ref_x || !in->ref_y || !in->v_ref ||
         !in->slot_ptr || !in->poly_ptr || !in->lane_ptr)
         return fail(h, PDMPC_ERR_BAD_INPUT, "plan: NULL input pointer");
-    for (int i = 0; i < n; ++i)
-        if (in->trim0[i] < 1 || in->trim0[i] > nT) return fail(h, PDMPC_ERR_BAD_INPUT, "plan: trim0 out of range");
-    const size_t ns = (size_t)n * (Hp + 1);
     if (in->slot_ptr[0] != 0 || in->poly_ptr[0] != 0 || in->lane_ptr[0] != 0)
         return fail(h, PDMPC_ERR_BAD_INPUT, "plan: CSR offsets must start at 0");
-    for (size_t s = 0; s < ns; ++s)
+    return PDMPC_OK;
+}
+
+// searches [s0, s1) of the batch (validate_header has passed)
+static int validate_range(pdmpc_handle *h, const pdmpc_batch_in *in, int s0, int s1) {
+    const int Hp = h->mpa.Hp, nT = h->mpa.nT;
+    for (int i = s0; i < s1; ++i)
+        if (in->trim0[i] < 1 || in->trim0[i] > nT) return fail(h, PDMPC_ERR_BAD_INPUT, "plan: trim0 out of range");
+    for (size_t s = (size_t)s0 * (Hp + 1); s < (size_t)s1 * (Hp + 1); ++s)
         if (in->slot_ptr[s + 1] < in->slot_ptr[s]) return fail(h, PDMPC_ERR_BAD_INPUT, "plan: slot_ptr not monotone");
-    const int np = in->slot_ptr[ns];
-    for (int p = 0; p < np; ++p) {
+    const int np0 = in->slot_ptr[(size_t)s0 * (Hp + 1)], np = in->slot_ptr[(size_t)s1 * (Hp + 1)];
+    for (int p = np0; p < np; ++p) {
         const int v0 = in->poly_ptr[p], v1 = in->poly_ptr[p + 1];
         if (v1 - v0 < 2) return fail(h, PDMPC_ERR_BAD_INPUT, "plan: obstacle polygon with fewer than 2 vertices");
         if (!in->vert_x || !in->vert_y) return fail(h, PDMPC_ERR_BAD_INPUT, "plan: NULL vertex arrays");
@@ -462,11 +483,17 @@ static int validate_batch(pdmpc_handle *h, const pdmpc_batch_in *in) {
             !(in->vert_x[v0] == in->vert_x[v1 - 1] && in->vert_y[v0] == in->vert_y[v1 - 1]))
             return fail(h, PDMPC_ERR_BAD_INPUT, "plan: obstacle polygon is not closed");
     }
-    for (int i = 0; i < 2 * n; ++i)
+    for (int i = 2 * s0; i < 2 * s1; ++i)
         if (in->lane_ptr[i + 1] < in->lane_ptr[i]) return fail(h, PDMPC_ERR_BAD_INPUT, "plan: lane_ptr not monotone");
-    if (in->lane_ptr[2 * n] > 0 && (!in->lane_x || !in->lane_y))
+    if (in->lane_ptr[2 * s1] > in->lane_ptr[2 * s0] && (!in->lane_x || !in->lane_y))
         return fail(h, PDMPC_ERR_BAD_INPUT, "plan: NULL lanelet arrays");
     return PDMPC_OK;
+}
+
+static int validate_batch(pdmpc_handle *h, const pdmpc_batch_in *in) {
+    int rc = validate_header(h, in);
+    if (rc != PDMPC_OK || in->n_searches == 0) return rc;
+    return validate_range(h, in, 0, in->n_searches);
 }
 
 constexpr size_t kPackLimit = 1u << 20;   // batches whose arrays total at most 1 MiB take the packed path
@@ -881,7 +908,254 @@ int pdmpc_fetch_staged(pdmpc_handle *h, pdmpc_batch_out *out) {
     return PDMPC_OK;
 }
 
+// ---- large host batches: chunked pipeline ---------------------------------------------------------
+// The searches are cut into C contiguous chunks.  Chunk c's input slices go host->device on a copy
+// stream while earlier chunks are searched; the chunks' persistent search kernels rotate over up to
+// eight compute streams (each with its own node arena): a chunk's kernel is pending as soon as its
+// inputs have landed, so its long searches start early and its one-warp CTAs take over the SMs as the
+// searches of the other chunks drain; results come back on another copy stream.  CSR offsets stay global (every array is allocated for
+// the whole batch), so the device ends up holding exactly what pdmpc_stage_batch would have staged.
+constexpr int kPipelineMinSearches = 16384;
+constexpr int kPipelineMaxChunks = 16;
+
+static int pipeline_sync_all(pdmpc_handle *h) {
+    cudaError_t e = cudaSuccess, e2;
+    for (cudaStream_t st : h->s_comp)
+        if (st && (e2 = cudaStreamSynchronize(st)) != cudaSuccess) e = e2;
+    for (cudaStream_t st : {h->s_in, h->s_out, h->stream})
+        if (st && (e2 = cudaStreamSynchronize(st)) != cudaSuccess) e = e2;
+    return e == cudaSuccess ? PDMPC_OK : fail(h, PDMPC_ERR_CUDA, std::string("pipeline sync: ") + cudaGetErrorString(e));
+}
+
+static int plan_batch_pipelined(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc_batch_out *out, int C) {
+    int rc = validate_header(h, in);
+    if (rc != PDMPC_OK) return rc;
+    if (!out || !out->status) return fail(h, PDMPC_ERR_BAD_INPUT, "fetch: out/status is NULL");
+    CU_TRY(h, cudaSetDevice(h->device));
+    const int n = in->n_searches, Hp = h->mpa.Hp;
+    const size_t ns = (size_t)n * (Hp + 1);
+    const int np = in->slot_ptr[ns];
+    if (np < 0 || (np > 0 && (!in->vert_x || !in->vert_y)))
+        return fail(h, PDMPC_ERR_BAD_INPUT, "plan: malformed obstacle CSR");
+    const int nv = np ? in->poly_ptr[np] : 0, nl = in->lane_ptr[2 * n];
+    if (nv < 0 || nl < 0) return fail(h, PDMPC_ERR_BAD_INPUT, "plan: malformed CSR totals");
+    const bool interx = in->checker == PDMPC_CHECKER_INTERX;
+    h->staged = false;
+    h->deps_staged = false;
+    if (!h->s_in) {
+        CU_TRY(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+        for (auto &st : h->s_comp) CU_TRY(h, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        CU_TRY(h, cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+        CU_TRY(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    }
+    while ((int)h->ev_chunk.size() < 2 * C) {
+        cudaEvent_t e;
+        CU_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->ev_chunk.push_back(e);
+    }
+    // ---- device arrays for the whole batch ----------------------------------------------------
+    struct Arr { DBuf *buf; const void *src; size_t elem; };
+    Arr arr[15] = {{&h->b_x0, in->x0, 8}, {&h->b_y0, in->y0, 8}, {&h->b_yaw0, in->yaw0, 8}, {&h->b_trim0, in->trim0, 4},
+                   {&h->b_refx, in->ref_x, 8}, {&h->b_refy, in->ref_y, 8}, {&h->b_vref, in->v_ref, 8},
+                   {&h->b_slot, in->slot_ptr, 4}, {&h->b_poly, in->poly_ptr, 4}, {&h->b_vx, in->vert_x, 8},
+                   {&h->b_vy, in->vert_y, 8}, {&h->b_lane, in->lane_ptr, 4}, {&h->b_lx, in->lane_x, 8},
+                   {&h->b_ly, in->lane_y, 8}, {&h->b_order, nullptr, 4}};
+    const size_t total[15] = {(size_t)n, (size_t)n, (size_t)n, (size_t)n, (size_t)n * Hp, (size_t)n * Hp, (size_t)n * Hp,
+                              ns + 1, (size_t)np + 1, (size_t)nv, (size_t)nv, (size_t)2 * n + 1, (size_t)nl, (size_t)nl,
+                              (size_t)n};
+    for (int i = 0; i < 15; ++i) CU_TRY(h, arr[i].buf->reserve(std::max<size_t>(total[i], 1) * arr[i].elem));
+    if (interx) {
+        CU_TRY(h, h->b_plx.reserve(((size_t)nv + np + 1) * sizeof(double)));
+        CU_TRY(h, h->b_ply.reserve(((size_t)nv + np + 1) * sizeof(double)));
+        CU_TRY(h, h->b_llx.reserve(((size_t)nl + 2 * n + 1) * sizeof(double)));
+        CU_TRY(h, h->b_lly.reserve(((size_t)nl + 2 * n + 1) * sizeof(double)));
+    }
+    rc = ensure_outputs(h, n);
+    if (rc != PDMPC_OK) return rc;
+    rc = ensure_pinned(h, &h->pin_order, &h->pin_order_cap, (size_t)n * sizeof(int));
+    if (rc != PDMPC_OK) return rc;
+    CU_TRY(h, h->wc_chunks.reserve(kPipelineMaxChunks * sizeof(unsigned)));
+    // one-warp CTAs leave an SM one by one as their searches end, so the next chunk's CTAs move in early; the
+    // 16-warp shape holds its SM until its slowest warp is done (only on request)
+    const bool thr = h->thr_ok && h->variant_mode == 2;
+    constexpr int kLanes = 8;   // most concurrent chunk kernels (streams, arenas)
+    const int per_chunk = (n + C - 1) / C;
+    const int grid = thr ? std::min((per_chunk + kWarpsThroughput - 1) / kWarpsThroughput, h->num_sms)
+                         : std::min(per_chunk, h->num_sms * h->lat_ctas_per_sm);
+    const int slots = thr ? grid * kWarpsThroughput : grid;
+    int lanes = std::min(C, kLanes);
+    {   // node arenas of all lanes within 32 GiB
+        const int cap = std::max(64, std::min(h->user_node_cap ? h->user_node_cap : std::min(h->full_tree_nodes + 8, 1 << 20),
+                                              kMaxNodeCap - 1));
+        const double per_lane = (double)slots * cap * (sizeof(NodeA) + sizeof(NodeB) + sizeof(NodeCS) + sizeof(HEnt));
+        lanes = std::max(2, std::min(lanes, (int)(32.0 * 1024 * 1024 * 1024 / per_lane)));
+    }
+    rc = ensure_arena(h, lanes * slots);
+    if (rc != PDMPC_OK) return rc;
+    ArenaDev ar[kLanes];
+    cudaStream_t comp[kLanes] = {h->stream, h->s_comp[0], h->s_comp[1], h->s_comp[2],
+                                 h->s_comp[3], h->s_comp[4], h->s_comp[5], h->s_comp[6]};
+    for (int i = 0; i < lanes; ++i) {
+        const size_t off = (size_t)i * (size_t)slots * (size_t)h->arena.cap;
+        ar[i] = h->arena;
+        ar[i].a += off; ar[i].b += off; ar[i].cs += off; ar[i].heap += off;
+    }
+    BatchDev &b = h->batch;
+    b.n = n; b.checker = in->checker; b.dt = in->dt_seconds;
+    b.x0 = h->b_x0.as<double>(); b.y0 = h->b_y0.as<double>(); b.yaw0 = h->b_yaw0.as<double>();
+    b.trim0 = h->b_trim0.as<int>();
+    b.ref_x = h->b_refx.as<double>(); b.ref_y = h->b_refy.as<double>(); b.v_ref = h->b_vref.as<double>();
+    b.slot_ptr = h->b_slot.as<int>(); b.poly_ptr = h->b_poly.as<int>();
+    b.vert_x = h->b_vx.as<double>(); b.vert_y = h->b_vy.as<double>();
+    b.lane_ptr = h->b_lane.as<int>(); b.lane_x = h->b_lx.as<double>(); b.lane_y = h->b_ly.as<double>();
+    b.order = h->b_order.as<int>();
+    b.pl_x = interx ? h->b_plx.as<double>() : nullptr; b.pl_y = interx ? h->b_ply.as<double>() : nullptr;
+    b.ll_x = interx ? h->b_llx.as<double>() : nullptr; b.ll_y = interx ? h->b_lly.as<double>() : nullptr;
+    b.pl_xy = b.ll_xy = nullptr;
+    b.rng = nullptr;
+    h->n_polys = np; h->n_verts = nv; h->n_lane = nl;
+    h->stats.h2d_bytes = 0;
+    h->stats.d2h_bytes = 0;
+    h->stats.kernel_launches = 0;
+    h->stats.lanes_ms = 0.0;
+    h->stats.handed_over = 0;
+    h->timing_pending_lanes = false;
+
+    CU_TRY(h, cudaMemsetAsync(h->out.counters, 0, 16 * sizeof(unsigned long long), h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->wc_chunks.p, 0, kPipelineMaxChunks * sizeof(unsigned), h->stream));
+    CU_TRY(h, cudaEventRecord(h->ev_fork, h->stream));
+    for (auto &st : h->s_comp) CU_TRY(h, cudaStreamWaitEvent(st, h->ev_fork, 0));
+    CU_TRY(h, cudaStreamWaitEvent(h->s_in, h->ev_fork, 0));
+    CU_TRY(h, cudaEventRecord(h->ev[0], h->s_in));
+    CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
+    bool d2h_started = false;
+    int *pin_order = static_cast<int *>(h->pin_order);
+    const TraceDev tr{-1, nullptr, 0, nullptr};
+    void *dsts[13] = {out->status, out->is_exhausted, out->n_expanded, out->n_pops, out->pop_hash, out->trims,
+                      out->tree_path, out->y_predicted, out->g_path, out->h_path, out->shape_npts, out->shape_x,
+                      out->shape_y};
+    const size_t per_search[13] = {sizeof(int), 1, sizeof(int), sizeof(int), sizeof(uint64_t),
+                                   ((size_t)Hp + 1) * sizeof(int), ((size_t)Hp + 1) * sizeof(int),
+                                   (size_t)Hp * 3 * sizeof(double), ((size_t)Hp + 1) * sizeof(double),
+                                   ((size_t)Hp + 1) * sizeof(double), (size_t)Hp * sizeof(int),
+                                   (size_t)Hp * PDMPC_AREA_STRIDE * sizeof(double),
+                                   (size_t)Hp * PDMPC_AREA_STRIDE * sizeof(double)};
+    const unsigned char *dbase = h->d_out_pack.as<unsigned char>();
+    auto bail = [&](int code) {
+        pipeline_sync_all(h);
+        return code;
+    };
+    for (int c = 0; c < C; ++c) {
+        const int s0 = (int)((long long)n * c / C), s1 = (int)((long long)n * (c + 1) / C);
+        if (s1 == s0) continue;
+        rc = validate_range(h, in, s0, s1);
+        if (rc != PDMPC_OK) return bail(rc);
+        const int p0 = in->slot_ptr[(size_t)s0 * (Hp + 1)], p1 = in->slot_ptr[(size_t)s1 * (Hp + 1)];
+        const int v0 = in->poly_ptr[p0], v1 = in->poly_ptr[p1];
+        const int l0 = in->lane_ptr[2 * s0], l1 = in->lane_ptr[2 * s1];
+        if (p0 < 0 || p1 > np || v0 < 0 || v1 > nv || l0 < 0 || l1 > nl)   // the arrays were sized from the totals
+            return bail(fail(h, PDMPC_ERR_BAD_INPUT, "plan: CSR offsets exceed their totals"));
+        {   // work order inside the chunk: most obstacle polygons first (counting sort, stable)
+            int kmax = 0;
+            for (int i = s0; i < s1; ++i)
+                kmax = std::max(kmax, in->slot_ptr[(size_t)(i + 1) * (Hp + 1)] - in->slot_ptr[(size_t)i * (Hp + 1)]);
+            std::vector<int> cnt(kmax + 2, 0);
+            for (int i = s0; i < s1; ++i)
+                cnt[kmax - (in->slot_ptr[(size_t)(i + 1) * (Hp + 1)] - in->slot_ptr[(size_t)i * (Hp + 1)]) + 1]++;
+            for (int k = 0; k <= kmax; ++k) cnt[k + 1] += cnt[k];
+            for (int i = s0; i < s1; ++i)
+                pin_order[s0 + cnt[kmax - (in->slot_ptr[(size_t)(i + 1) * (Hp + 1)] - in->slot_ptr[(size_t)i * (Hp + 1)])]++] = i;
+        }
+        // slices [lo, hi) of every input array that belong to this chunk (offset arrays: one more entry)
+        const size_t lo[15] = {(size_t)s0, (size_t)s0, (size_t)s0, (size_t)s0, (size_t)s0 * Hp, (size_t)s0 * Hp, (size_t)s0 * Hp,
+                               (size_t)s0 * (Hp + 1), (size_t)p0, (size_t)v0, (size_t)v0, (size_t)2 * s0, (size_t)l0, (size_t)l0,
+                               (size_t)s0};
+        const size_t hi[15] = {(size_t)s1, (size_t)s1, (size_t)s1, (size_t)s1, (size_t)s1 * Hp, (size_t)s1 * Hp, (size_t)s1 * Hp,
+                               (size_t)s1 * (Hp + 1) + 1, (size_t)p1 + 1, (size_t)v1, (size_t)v1, (size_t)2 * s1 + 1, (size_t)l1,
+                               (size_t)l1, (size_t)s1};
+        for (int i = 0; i < 15; ++i) {
+            if (hi[i] <= lo[i]) continue;
+            const unsigned char *src = static_cast<const unsigned char *>(i == 14 ? (const void *)pin_order : arr[i].src);
+            const size_t bytes = (hi[i] - lo[i]) * arr[i].elem;
+            if (cudaMemcpyAsync(arr[i].buf->as<unsigned char>() + lo[i] * arr[i].elem, src + lo[i] * arr[i].elem, bytes,
+                                cudaMemcpyHostToDevice, h->s_in) != cudaSuccess)
+                return bail(fail(h, PDMPC_ERR_CUDA, std::string("pipeline H2D: ") + cudaGetErrorString(cudaGetLastError())));
+            h->stats.h2d_bytes += (int64_t)bytes;
+        }
+        cudaEvent_t ev_in = h->ev_chunk[2 * c], ev_done = h->ev_chunk[2 * c + 1];
+        cudaStream_t S = comp[c % lanes];
+        if (cudaEventRecord(ev_in, h->s_in) != cudaSuccess || cudaStreamWaitEvent(S, ev_in, 0) != cudaSuccess)
+            return bail(fail(h, PDMPC_ERR_CUDA, "pipeline: event"));
+        if (interx) {
+            if (p1 > p0) {
+                build_polyline_kernel<<<(p1 - p0 + 127) / 128, 128, 0, S>>>(p1 - p0, b.poly_ptr, b.vert_x, b.vert_y,
+                                                                          h->b_plx.as<double>(), h->b_ply.as<double>(), p0);
+                h->stats.kernel_launches++;
+            }
+            build_polyline_kernel<<<(2 * (s1 - s0) + 127) / 128, 128, 0, S>>>(2 * (s1 - s0), b.lane_ptr, b.lane_x, b.lane_y,
+                                                                          h->b_llx.as<double>(), h->b_lly.as<double>(), 2 * s0);
+            h->stats.kernel_launches++;
+        }
+        BatchDev bc = b;
+        bc.n = s1 - s0;
+        bc.order = h->b_order.as<int>() + s0;
+        unsigned *wc = h->wc_chunks.as<unsigned>() + c;
+        if (thr) {
+            const int g = std::min((bc.n + kWarpsThroughput - 1) / kWarpsThroughput, h->num_sms);
+            KERNEL_THR<<<g, kWarpsThroughput * kWarp, h->thr_smem, S>>>(h->mpa, bc, h->out, ar[c % lanes], wc, tr, nullptr);
+        } else {
+            const int g = std::min(bc.n, h->num_sms * h->lat_ctas_per_sm);
+            KERNEL_LAT<<<g, kWarp, sizeof(WarpSmem), S>>>(h->mpa, bc, h->out, ar[c % lanes], wc, tr, nullptr);
+        }
+        h->stats.kernel_launches++;
+        if (cudaGetLastError() != cudaSuccess || cudaEventRecord(ev_done, S) != cudaSuccess ||
+            cudaStreamWaitEvent(h->s_out, ev_done, 0) != cudaSuccess)
+            return bail(fail(h, PDMPC_ERR_CUDA, "pipeline: search kernel launch failed"));
+        if (!d2h_started) {
+            cudaEventRecord(h->ev[4], h->s_out);
+            d2h_started = true;
+        }
+        for (int i = 0; i < 13; ++i) {
+            if (!dsts[i]) continue;
+            const size_t o0 = (size_t)s0 * per_search[i], bytes = (size_t)(s1 - s0) * per_search[i];
+            if (cudaMemcpyAsync(static_cast<unsigned char *>(dsts[i]) + o0, dbase + h->out_off[i] + o0, bytes,
+                                cudaMemcpyDeviceToHost, h->s_out) != cudaSuccess)
+                return bail(fail(h, PDMPC_ERR_CUDA, "pipeline D2H failed"));
+            h->stats.d2h_bytes += (int64_t)bytes;
+        }
+    }
+    for (int c = 0; c < C; ++c)   // every chunk joins the handle's stream
+        if (c % lanes != 0 && (int)((long long)n * (c + 1) / C) > (int)((long long)n * c / C))
+            CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_chunk[2 * c + 1], 0));
+    CU_TRY(h, cudaEventRecord(h->ev[1], h->s_in));
+    CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
+    unsigned long long counters[16] = {0};
+    CU_TRY(h, cudaMemcpyAsync(counters, dbase + h->out_off[13], sizeof(counters), cudaMemcpyDeviceToHost, h->s_out));
+    CU_TRY(h, cudaEventRecord(h->ev[5], h->s_out));
+    rc = pipeline_sync_all(h);
+    if (rc != PDMPC_OK) return rc;
+    h->timing_pending_h2d = h->timing_pending_kernel = h->timing_pending_d2h = true;
+    h->stats.total_pops = (int64_t)counters[0];
+    h->stats.total_nodes = (int64_t)counters[1];
+    h->stats.total_obstacle_cols = (int64_t)counters[2];
+    h->staged = true;   // the device holds the whole batch: pdmpc_run_staged / pdmpc_fetch_staged work on it
+    return PDMPC_OK;
+}
+
+int pdmpc_set_pipeline_chunks(pdmpc_handle *h, int32_t chunks) {
+    if (!h) return PDMPC_ERR_BAD_INPUT;
+    if (chunks < 0 || chunks > kPipelineMaxChunks)
+        return fail(h, PDMPC_ERR_BAD_INPUT, "pipeline chunks must be 0 (auto), 1 (off) or 2..16");
+    h->pipeline_chunks = chunks;
+    return PDMPC_OK;
+}
+
 int pdmpc_plan_batch(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc_batch_out *out) {
+    if (h && in && h->has_mpa && h->pipeline_chunks != 1 && h->variant_mode <= 2 &&
+        (h->pipeline_chunks > 1 ? in->n_searches >= 2 * h->pipeline_chunks : in->n_searches >= kPipelineMinSearches)) {
+        const int C = h->pipeline_chunks > 1 ? h->pipeline_chunks : std::min(12, std::max(2, in->n_searches / kPipelineMinSearches));   // measured: profiles/r01h_pipeline.txt
+        return plan_batch_pipelined(h, in, out, C);
+    }
     int rc = pdmpc_stage_batch(h, in);
     if (rc != PDMPC_OK) return rc;
     rc = pdmpc_run_staged(h);

@@ -1011,9 +1011,9 @@ __global__ void __launch_bounds__(WARPS *kWarp, WARPS == 1 ? PDMPC_MIN_CTAS_LAT 
 // append the [NaN; NaN] column.  One thread per polygon.
 __global__ void build_polyline_kernel(int n_polys, const int *__restrict__ poly_ptr,
                                       const double *__restrict__ vx, const double *__restrict__ vy,
-                                      double *__restrict__ px, double *__restrict__ py) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_polys) return;
+                                      double *__restrict__ px, double *__restrict__ py, int p_base = 0) {
+    const int p = p_base + blockIdx.x * blockDim.x + threadIdx.x;   // polygons [p_base, p_base + n_polys)
+    if (p >= p_base + n_polys) return;
     const int v0 = poly_ptr[p], v1 = poly_ptr[p + 1];
     for (int v = v0; v < v1; ++v) {
         px[v + p] = vx[v];

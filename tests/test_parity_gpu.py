@@ -326,3 +326,44 @@ def test_restage_before_fetch_and_knob_validation(planner):
     with pytest.raises(capi.PdmpcError):
         planner.set_variant(9)
     planner.set_variant(0)
+
+
+@pytest.mark.parametrize("chunks", [2, 3, 7, 16])
+def test_pipelined_plan_batch_equals_single_launch(planner, chunks):
+    """Large host batches are cut into chunks whose copies and searches overlap
+    (pdmpc_set_pipeline_chunks): same outputs for any chunk count, both warp launch shapes, both
+    checkers, and the device is left holding the whole batch (run_staged / fetch afterwards)."""
+    cases = [road_records("triple_speed", 8), circle_records(30)]
+    try:
+        for mpa, batch in cases:
+            planner.upload_mpa(mpa)
+            ref = oracle_py.plan_batch(mpa, batch, 4)
+            for variant in (0, 1, 2):
+                planner.set_variant(variant)
+                planner.set_pipeline_chunks(chunks)
+                dev = planner.plan_batch(batch, raise_on_search_error=False)
+                parity.compare(dev, ref)
+                st = planner.stats()
+                assert st.total_pops == int(ref.n_pops.sum()) and st.total_nodes == int(ref.n_expanded.sum())
+                assert st.kernel_launches >= chunks
+            planner.set_variant(0)
+            planner._staged_n, planner._staged_Hp = batch.n, batch.Hp
+            planner.run_staged()
+            parity.compare(planner.fetch(), ref)
+            planner.set_pipeline_chunks(1)
+            parity.compare(planner.plan_batch(batch, raise_on_search_error=False), ref)
+        # malformed input in a LATER chunk is still rejected, and the handle survives
+        mpa, batch = cases[0]
+        planner.upload_mpa(mpa)
+        planner.set_pipeline_chunks(chunks)
+        bad = dataclasses.replace(batch, trim0=batch.trim0.copy())
+        bad.trim0[-1] = 99
+        with pytest.raises(capi.PdmpcError) as e:
+            planner.plan_batch(bad)
+        assert e.value.code == capi.PDMPC_ERR_BAD_INPUT
+        parity.compare(planner.plan_batch(batch, raise_on_search_error=False), oracle_py.plan_batch(mpa, batch, 4))
+    finally:
+        planner.set_variant(0)
+        planner.set_pipeline_chunks(0)
+    with pytest.raises(capi.PdmpcError):
+        planner.set_pipeline_chunks(17)
