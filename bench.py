@@ -454,6 +454,7 @@ def main():
                 traffic = float(cap["dram_bytes_read"]) + float(cap["dram_bytes_write"])
         except Exception:
             pass
+        fp64_peak = planner.measure_fp64_peak()
         alg_bytes = algorithmic_bytes(batch, stats, Hp)
         achieved = alg_bytes / (ms_step * 1e-3) / 1e9
         f64 = fp64_ops(batch, stats, Hp)
@@ -480,6 +481,9 @@ def main():
                          "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                          "kernel": "pdmpc::search_kernel", "algorithmic_bytes_per_launch": alg_bytes,
                          "fp64": {"ops_per_launch": f64, "achieved_tops": f64 / (ms_step * 1e-3) / 1e12,
+                                  "peak_tops_mul_add": fp64_peak[0], "peak_tflops_fma": fp64_peak[1],
+                                  "frac": f64 / (ms_step * 1e-3) / 1e12 / fp64_peak[0],
+                                  "peak_source": "measured in this run (pdmpc_measure_fp64_peak, register-only kernel)",
                                   "note": "mul/add/sqrt without FMA; latency-bound serial search, see DESIGN.md"}},
             "cpu_baseline": cpu,
             "search_stats": {"pops_per_plan": stats.total_pops / max(n, 1),

@@ -291,6 +291,12 @@ typedef struct pdmpc_timestep_deps {
 int pdmpc_plan_timestep(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_timestep_deps *deps,
                         pdmpc_batch_out *out);
 
+/* Diagnostics: the FP64 pipe peak of the handle's device, measured with register-only kernels
+ * (no memory traffic): tera-operations/s of separate multiply + add (what the search executes: FMA
+ * contraction is off for bit-exactness) and TFLOP/s of fused multiply-add.  The denominators of the
+ * FP64 roofline fraction bench.py reports next to the HBM one. */
+int pdmpc_measure_fp64_peak(pdmpc_handle *h, double *mul_add_tops, double *fma_tflops);
+
 /* Pinned host buffers for callers that want full-rate host<->device copies. */
 int pdmpc_host_alloc(void **p, size_t bytes);
 int pdmpc_host_free(void *p);

@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = (
     "pdmpc_trace_staged", "pdmpc_upload_mpa", "pdmpc_plan_batch", "pdmpc_stage_batch",
     "pdmpc_run_staged", "pdmpc_sync", "pdmpc_fetch_staged", "pdmpc_get_stats", "pdmpc_stream",
     "pdmpc_mcts_plan_batch", "pdmpc_mcts_run_staged", "pdmpc_set_cta_heap_smem", "pdmpc_plan_timestep",
-    "pdmpc_set_pipeline_chunks",
+    "pdmpc_set_pipeline_chunks", "pdmpc_measure_fp64_peak",
 )
 
 _p_u8 = C.POINTER(C.c_uint8)
@@ -173,6 +173,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.pdmpc_set_variant.restype = C.c_int
     lib.pdmpc_set_cta_heap_smem.argtypes = [H, C.c_int32]
     lib.pdmpc_set_cta_heap_smem.restype = C.c_int
+    lib.pdmpc_measure_fp64_peak.argtypes = [H, _p_f64, _p_f64]
+    lib.pdmpc_measure_fp64_peak.restype = C.c_int
     lib.pdmpc_set_pipeline_chunks.argtypes = [H, C.c_int32]
     lib.pdmpc_set_pipeline_chunks.restype = C.c_int
     lib.pdmpc_set_lane_limits.argtypes = [H, C.c_int32, C.c_int32]
@@ -255,6 +257,12 @@ class Planner:
     def set_cta_heap_smem(self, entries: int = 0):
         """Shape 4 knob (pdmpc_set_cta_heap_smem); results do not depend on it."""
         self._check(self.lib.pdmpc_set_cta_heap_smem(self.h, int(entries)))
+
+    def measure_fp64_peak(self):
+        """(separate mul+add Tops/s, FMA TFLOP/s) of the device's FP64 pipe (pdmpc_measure_fp64_peak)."""
+        a, b = C.c_double(), C.c_double()
+        self._check(self.lib.pdmpc_measure_fp64_peak(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def set_pipeline_chunks(self, chunks: int = 0):
         """Chunked copy/search pipeline of plan_batch (pdmpc_set_pipeline_chunks); results do not depend on it."""

@@ -171,6 +171,30 @@ static int fail(pdmpc_handle *h, int code, const std::string &msg) {
             return fail(h, PDMPC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
     } while (0)
 
+// FP64 pipe peak of this device, measured (SURVEY.md §8(d) asks for it next to the HBM roofline):
+// 8 independent accumulator chains per thread, no memory traffic; once as separate DMUL + DADD (what
+// the search executes: FMA contraction is off for bit-exactness) and once as DFMA.
+namespace {
+template <bool FMA>
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *sink, int iters, double a, double b2) {
+    double v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (FMA) v[i] = __fma_rn(v[i], a, b2);
+            else v[i] = __dadd_rn(__dmul_rn(v[i], a), b2);
+        }
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc += v[i];
+    if (acc == 123.456) sink[0] = acc;   // never true: keeps the chains alive
+}
+}  // namespace
+
+
 extern "C" {
 
 int pdmpc_abi_version(void) { return PDMPC_ABI_VERSION; }
@@ -1347,6 +1371,29 @@ int pdmpc_trace_staged(pdmpc_handle *h, int32_t search, int64_t *ids, int64_t ca
     const long long m = std::min<long long>(n, cap);
     if (m > 0) CU_TRY(h, cudaMemcpy(ids, h->t_ids.p, (size_t)m * sizeof(long long), cudaMemcpyDeviceToHost));
     *n_out = n;
+    return PDMPC_OK;
+}
+
+int pdmpc_measure_fp64_peak(pdmpc_handle *h, double *mul_add_tops, double *fma_tflops) {
+    if (!h || !mul_add_tops || !fma_tflops) return PDMPC_ERR_BAD_INPUT;
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, h->t_n.reserve(sizeof(double)));
+    const int iters = 4096, grid = h->num_sms * 8, block = 256;
+    float ms[2] = {0.f, 0.f};
+    for (int pass = 0; pass < 2; ++pass)       // pass 0 warms up
+        for (int k = 0; k < 2; ++k) {
+            CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
+            if (k == 0) fp64_peak_kernel<false><<<grid, block, 0, h->stream>>>(h->t_n.as<double>(), iters, 1.0000001, 1e-7);
+            else fp64_peak_kernel<true><<<grid, block, 0, h->stream>>>(h->t_n.as<double>(), iters, 1.0000001, 1e-7);
+            CU_TRY(h, cudaGetLastError());
+            CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
+            CU_TRY(h, cudaStreamSynchronize(h->stream));
+            CU_TRY(h, cudaEventElapsedTime(&ms[k], h->ev[2], h->ev[3]));
+        }
+    const double ops = (double)grid * block * iters * 8.0 * 2.0;   // a multiply and an add per chain step
+    *mul_add_tops = ops / (ms[0] * 1e-3) / 1e12;
+    *fma_tflops = ops / (ms[1] * 1e-3) / 1e12;
+    h->timing_pending_kernel = false;
     return PDMPC_OK;
 }
 

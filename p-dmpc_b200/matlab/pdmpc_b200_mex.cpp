@@ -15,6 +15,15 @@
 //   [same outputs] = mex(PLAN_SAMPLED, h, <the ten PLAN arguments>, seed, n_expansions_max)
 //       MonteCarloTreeSearch.run_optimizer: seed = time_step + vehicle_index (MonteCarloTreeSearch.m:31)
 //   s = mex(STATS, h)
+//   [is_exhausted (1 x N), n_expanded (1 x N), trims (N x Hp+1), y_pred (3 x Hp*N), shapes {N x Hp}] =
+//       mex(PLAN_TIMESTEP, h, x0 [N x 3], trims [N x 1], ref [N x Hp x 2], v_ref [N x Hp],
+//           obstacles {N x S}, dynamic_obstacle_area {N x R*Hp} (row r of step k at column r + R*(k-1)),
+//           left {N x 1}, right {N x 1}, checker, dt, directed_coupling_sequential [N x N],
+//           fallback_shapes {N x Hp})
+//       ALL vehicles of one time step in one call (plan_timestep_cuda.m): replaces the level loop of
+//       PrioritizedSequentialController.controller (PrioritizedSequentialController.m:74-92); vehicle i
+//       waits on the device for the vehicles j with directed_coupling_sequential(j, i) ~= 0 and takes
+//       their planned areas as dynamic obstacles (PrioritizedController.m:449-506); empty cells are skipped.
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -25,7 +34,7 @@
 
 namespace {
 
-enum Command { CREATE = 0, DESTROY = 1, UPLOAD_MPA = 2, PLAN = 3, STATS = 4, PLAN_SAMPLED = 5 };
+enum Command { CREATE = 0, DESTROY = 1, UPLOAD_MPA = 2, PLAN = 3, STATS = 4, PLAN_SAMPLED = 5, PLAN_TIMESTEP = 6 };
 
 std::vector<pdmpc_handle *> g_handles;   // released at `clear mex` (HighLevelController.m:284-303)
 bool g_at_exit_registered = false;
@@ -249,6 +258,139 @@ void plan(pdmpc_handle *h, int nlhs, mxArray *plhs[], const mxArray *prhs[], boo
     }
 }
 
+// PLAN_TIMESTEP: N vehicles, one pdmpc_plan_timestep call.
+void plan_timestep(pdmpc_handle *h, int nlhs, mxArray *plhs[], const mxArray *prhs[]) {
+    const mxArray *x0 = prhs[2], *trim = prhs[3], *ref = prhs[4], *vref = prhs[5], *obst = prhs[6], *dyn = prhs[7];
+    const mxArray *left = prhs[8], *right = prhs[9], *coupling = prhs[12], *fallback = prhs[13];
+    const size_t N = mxGetM(x0);
+    if (N == 0 || mxGetN(x0) < 3) fail("pdmpc:input", "x0 must be N x 3");
+    if (mxGetM(vref) != N) fail("pdmpc:input", "v_ref must be N x Hp");
+    const int Hp = static_cast<int>(mxGetN(vref));
+    if (mxGetNumberOfElements(ref) != N * Hp * 2 || mxGetNumberOfElements(trim) != N)
+        fail("pdmpc:input", "ref must be N x Hp x 2 and trims N x 1");
+    if (mxGetM(coupling) != N || mxGetN(coupling) != N) fail("pdmpc:input", "directed_coupling_sequential must be N x N");
+    const double *px0 = mxGetDoubles(x0), *pref = mxGetDoubles(ref), *pv = mxGetDoubles(vref), *ptrim = mxGetDoubles(trim);
+    const double *pc = mxGetDoubles(coupling);
+
+    std::vector<double> xs(N), ys(N), yaws(N), rx(N * Hp), ry(N * Hp), vr(N * Hp);
+    std::vector<int32_t> trims(N), slot_ptr(1, 0), poly_ptr(1, 0), lane_ptr(1, 0);
+    std::vector<double> vx, vy, lx, ly;
+    const size_t S = mxIsCell(obst) && mxGetM(obst) == N ? mxGetN(obst) : 0;
+    const size_t RH = mxIsCell(dyn) && mxGetM(dyn) == N ? mxGetN(dyn) : 0;
+    if (RH % Hp != 0) fail("pdmpc:input", "dynamic_obstacle_area must be N x (R*Hp)");
+    const size_t R = RH / Hp;
+    for (size_t i = 0; i < N; ++i) {
+        xs[i] = px0[i]; ys[i] = px0[i + N]; yaws[i] = px0[i + 2 * N];
+        trims[i] = static_cast<int32_t>(ptrim[i]);
+        for (int k = 0; k < Hp; ++k) {
+            rx[i * Hp + k] = pref[i + N * k];
+            ry[i * Hp + k] = pref[i + N * k + N * Hp];
+            vr[i * Hp + k] = pv[i + N * k];
+        }
+        for (size_t s = 0; s < S; ++s) append_polygon(mxGetCell(obst, i + N * s), vx, vy, poly_ptr);
+        slot_ptr.push_back(static_cast<int32_t>(poly_ptr.size() - 1));
+        for (int k = 0; k < Hp; ++k) {
+            for (size_t r = 0; r < R; ++r) append_polygon(mxGetCell(dyn, i + N * (r + R * k)), vx, vy, poly_ptr);
+            slot_ptr.push_back(static_cast<int32_t>(poly_ptr.size() - 1));
+        }
+        for (const mxArray *sides : {left, right}) {
+            const mxArray *side = (mxIsCell(sides) && mxGetNumberOfElements(sides) == N) ? mxGetCell(sides, i) : nullptr;
+            if (side && !mxIsEmpty(side)) {
+                if (mxGetM(side) != 2) fail("pdmpc:input", "lanelet bounds must be 2 x n");
+                const double *d = mxGetDoubles(side);
+                for (size_t q = 0; q < mxGetN(side); ++q) {
+                    lx.push_back(d[2 * q]);
+                    ly.push_back(d[2 * q + 1]);
+                }
+            }
+            lane_ptr.push_back(static_cast<int32_t>(lx.size()));
+        }
+    }
+    // predecessors of vehicle i: find(directed_coupling_sequential(:, i)) (PrioritizedController.m:309)
+    std::vector<int32_t> pred_ptr(1, 0), pred_idx;
+    for (size_t i = 0; i < N; ++i) {
+        for (size_t j = 0; j < N; ++j)
+            if (pc[j + N * i] != 0.0) pred_idx.push_back(static_cast<int32_t>(j));
+        pred_ptr.push_back(static_cast<int32_t>(pred_idx.size()));
+    }
+    if (pred_idx.empty()) pred_idx.push_back(0);
+    // what an exhausted vehicle publishes (plan_fallback / handle_graph_search_exhaustion)
+    std::vector<int32_t> fb_npts(N * Hp, 0);
+    std::vector<double> fbx(N * Hp * PDMPC_AREA_STRIDE, 0.0), fby(N * Hp * PDMPC_AREA_STRIDE, 0.0);
+    const bool has_fb = mxIsCell(fallback) && mxGetM(fallback) == N && mxGetN(fallback) == static_cast<size_t>(Hp);
+    if (has_fb)
+        for (size_t i = 0; i < N; ++i)
+            for (int k = 0; k < Hp; ++k) {
+                const mxArray *a = mxGetCell(fallback, i + N * k);
+                if (!a || mxIsEmpty(a)) continue;
+                const size_t m = mxGetN(a);
+                if (mxGetM(a) != 2 || m >= PDMPC_AREA_STRIDE) fail("pdmpc:input", "fallback shapes must be 2 x m, m <= 7");
+                const double *d = mxGetDoubles(a);
+                fb_npts[i * Hp + k] = static_cast<int32_t>(m);
+                for (size_t q = 0; q < m; ++q) {
+                    fbx[(i * Hp + k) * PDMPC_AREA_STRIDE + q] = d[2 * q];
+                    fby[(i * Hp + k) * PDMPC_AREA_STRIDE + q] = d[2 * q + 1];
+                }
+            }
+
+    pdmpc_batch_in in;
+    std::memset(&in, 0, sizeof(in));
+    in.n_searches = static_cast<int32_t>(N);
+    in.checker = static_cast<int32_t>(mxGetScalar(prhs[10]));
+    in.dt_seconds = mxGetScalar(prhs[11]);
+    in.x0 = xs.data(); in.y0 = ys.data(); in.yaw0 = yaws.data(); in.trim0 = trims.data();
+    in.ref_x = rx.data(); in.ref_y = ry.data(); in.v_ref = vr.data();
+    in.slot_ptr = slot_ptr.data(); in.poly_ptr = poly_ptr.data(); in.vert_x = vx.data(); in.vert_y = vy.data();
+    in.lane_ptr = lane_ptr.data(); in.lane_x = lx.data(); in.lane_y = ly.data();
+    pdmpc_timestep_deps deps;
+    std::memset(&deps, 0, sizeof(deps));
+    deps.pred_ptr = pred_ptr.data();
+    deps.pred_idx = pred_idx.data();
+    if (has_fb) { deps.fb_npts = fb_npts.data(); deps.fb_x = fbx.data(); deps.fb_y = fby.data(); }
+
+    std::vector<int32_t> status(N, -1), n_expanded(N, 0), out_trims(N * (Hp + 1)), shape_npts(N * Hp);
+    std::vector<uint8_t> exhausted(N, 0);
+    std::vector<double> ypred(N * Hp * 3), sx(N * Hp * PDMPC_AREA_STRIDE), sy(N * Hp * PDMPC_AREA_STRIDE);
+    pdmpc_batch_out out;
+    std::memset(&out, 0, sizeof(out));
+    out.status = status.data(); out.is_exhausted = exhausted.data(); out.n_expanded = n_expanded.data();
+    out.trims = out_trims.data(); out.y_predicted = ypred.data();
+    out.shape_npts = shape_npts.data(); out.shape_x = sx.data(); out.shape_y = sy.data();
+    check(h, pdmpc_plan_timestep(h, &in, &deps, &out), "pdmpc_plan_timestep");
+    for (size_t i = 0; i < N; ++i)
+        if (status[i] != PDMPC_OK) fail("pdmpc:search", "search " + std::to_string(i + 1) + " failed with status " + std::to_string(status[i]));
+
+    plhs[0] = mxCreateDoubleMatrix(1, N, mxREAL);
+    for (size_t i = 0; i < N; ++i) mxGetDoubles(plhs[0])[i] = exhausted[i];
+    if (nlhs > 1) {
+        plhs[1] = mxCreateDoubleMatrix(1, N, mxREAL);
+        for (size_t i = 0; i < N; ++i) mxGetDoubles(plhs[1])[i] = n_expanded[i];
+    }
+    if (nlhs > 2) {
+        plhs[2] = mxCreateDoubleMatrix(N, Hp + 1, mxREAL);
+        for (size_t i = 0; i < N; ++i)
+            for (int k = 0; k <= Hp; ++k) mxGetDoubles(plhs[2])[i + N * k] = out_trims[i * (Hp + 1) + k];
+    }
+    if (nlhs > 3) {   // 3 x (Hp*N): reshape(y, 3, Hp, N) gives info.y_predicted of vehicle i in (:, :, i)
+        plhs[3] = mxCreateDoubleMatrix(3, Hp * N, mxREAL);
+        std::memcpy(mxGetDoubles(plhs[3]), ypred.data(), sizeof(double) * 3 * Hp * N);
+    }
+    if (nlhs > 4) {
+        plhs[4] = mxCreateCellMatrix(N, Hp);
+        for (size_t i = 0; i < N; ++i)
+            for (int k = 0; k < Hp; ++k) {
+                const int n = shape_npts[i * Hp + k];
+                mxArray *sh = mxCreateDoubleMatrix(2, n, mxREAL);
+                double *d = mxGetDoubles(sh);
+                for (int q = 0; q < n; ++q) {
+                    d[2 * q] = sx[(i * Hp + k) * PDMPC_AREA_STRIDE + q];
+                    d[2 * q + 1] = sy[(i * Hp + k) * PDMPC_AREA_STRIDE + q];
+                }
+                mxSetCell(plhs[4], i + N * k, sh);
+            }
+    }
+}
+
 }  // namespace
 
 void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
@@ -291,6 +433,10 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
     case PLAN_SAMPLED:
         if (nrhs < 14) fail("pdmpc:usage", "PLAN_SAMPLED needs 14 arguments");
         plan(h, nlhs, plhs, prhs, true);
+        return;
+    case PLAN_TIMESTEP:
+        if (nrhs < 14) fail("pdmpc:usage", "PLAN_TIMESTEP needs 14 arguments");
+        plan_timestep(h, nlhs, plhs, prhs);
         return;
     case STATS: {
         pdmpc_stats st;

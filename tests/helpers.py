@@ -86,3 +86,27 @@ def load_golden_mcts(name: str):
         a = z[f"{name}__out__{f.name}"]
         kw[f.name] = a.item() if a.ndim == 0 else a
     return z[name + "__seeds"], int(z[name + "__n_max"]), BatchResult(**kw)
+
+
+def load_golden_timesteps(name: str):
+    """tests/golden/timestep_*.npz (tools/make_golden_timestep.py) ->
+    (mpa, [(batch, deps, expected BatchResult) per time step])."""
+    import dataclasses
+    import os
+
+    from pdmpc_b200.mpa import MotionPrimitiveAutomaton
+    from pdmpc_b200.records import BatchResult, TimestepDeps
+
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+
+    def build(cls, prefix):
+        kw = {}
+        for f in dataclasses.fields(cls):
+            a = z[prefix + f.name]
+            kw[f.name] = a.item() if a.ndim == 0 else a
+        return cls(**kw)
+
+    mpa = build(MotionPrimitiveAutomaton, "mpa__")
+    steps = [(build(SearchBatch, f"s{s}__in__"), build(TimestepDeps, f"s{s}__deps__"), build(BatchResult, f"s{s}__out__"))
+             for s in range(int(z["n_steps"]))]
+    return mpa, steps

@@ -34,7 +34,8 @@ def test_library_exports_every_declared_symbol(built):
 def test_ctypes_structs_match_the_c_layout(tmp_path, built):
     from pdmpc_b200 import capi
     structs = {"pdmpc_mpa_desc": capi.MpaDesc, "pdmpc_batch_in": capi.BatchIn,
-               "pdmpc_batch_out": capi.BatchOut, "pdmpc_stats": capi.Stats}
+               "pdmpc_batch_out": capi.BatchOut, "pdmpc_stats": capi.Stats,
+               "pdmpc_timestep_deps": capi.TimestepDepsC, "pdmpc_mcts_params": capi.MctsParams}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for cname, cls in structs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')

@@ -100,3 +100,62 @@ def test_mex_sampled_path_matches_golden(matlab):
     finally:
         matlab.call(0, mexfake.DESTROY, float(h))
         matlab.clear_mex()
+
+
+def _timestep_args(batch, deps):
+    """The PLAN_TIMESTEP argument list (MATLAB layouts) of one time step's flat batch."""
+    n, Hp = batch.n, batch.Hp
+    iters = batch.to_iters()
+    S = max((len(it.obstacles) for it in iters), default=0)
+    R = max((len(it.dynamic_obstacle_area) for it in iters), default=0)
+    obstacles = [[it.obstacles[s] if s < len(it.obstacles) else None for s in range(max(S, 1))] for it in iters]
+    dyn = [[(it.dynamic_obstacle_area[r][k] if r < len(it.dynamic_obstacle_area) and
+             it.dynamic_obstacle_area[r][k].shape[1] else None)
+            for k in range(Hp) for r in range(max(R, 1))] for it in iters]
+    coupling = np.zeros((n, n))
+    for i in range(n):
+        coupling[deps.preds(i), i] = 1.0
+    fb = [[s if s.shape[1] else None for s in deps.fallback_shapes(i)] for i in range(n)]
+    return (np.stack([batch.x0, batch.y0, batch.yaw0], axis=1), batch.trim0.astype(np.float64).reshape(-1, 1),
+            np.stack([batch.ref_x.reshape(n, Hp), batch.ref_y.reshape(n, Hp)], axis=2), batch.v_ref.reshape(n, Hp),
+            obstacles, dyn, [it.predicted_lanelet_boundary[0] for it in iters],
+            [it.predicted_lanelet_boundary[1] for it in iters], float(batch.checker), float(batch.dt_seconds),
+            coupling, fb)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["timestep_road_triple_speed", "timestep_circle_single_speed"])
+def test_mex_timestep_path_matches_golden(matlab, name):
+    """PLAN_TIMESTEP (plan_timestep_cuda.m: all vehicles of a time step in one call) through the shim
+    against the committed time-step fixtures."""
+    from helpers import load_golden_timesteps
+    mpa, steps = load_golden_timesteps(name)
+    (h,) = matlab.call(1, mexfake.CREATE, 0.0)
+    try:
+        trans, man = mexfake.matlab_mpa(mpa)
+        matlab.call(0, mexfake.UPLOAD_MPA, float(h), trans, man)
+        for batch, deps, exp in steps[::3]:
+            exh, n_exp, trims, y, shapes = matlab.call(5, mexfake.PLAN_TIMESTEP, float(h), *_timestep_args(batch, deps))
+            n, Hp = batch.n, batch.Hp
+            assert exh.reshape(-1).astype(int).tolist() == exp.is_exhausted.tolist()
+            assert n_exp.reshape(-1).astype(int).tolist() == exp.n_expanded.tolist()
+            y = y.reshape(3, Hp, n, order="F")
+            for i in range(n):
+                if exp.is_exhausted[i]:
+                    continue
+                assert trims[i].astype(int).tolist() == exp.trims[i].tolist()
+                assert np.array_equal(y[:, :, i].T.view(np.uint64), exp.y_predicted[i].view(np.uint64))
+                for k in range(Hp):
+                    m = int(exp.shape_npts[i, k])
+                    sh = shapes[i + n * k]
+                    assert sh.shape == (2, m) and np.array_equal(sh[0].view(np.uint64), exp.shape_x[i, k, :m].view(np.uint64))
+    finally:
+        matlab.call(0, mexfake.DESTROY, float(h))
+        matlab.clear_mex()
+
+
+def test_timestep_matlab_helper_present():
+    import os
+    src = open(os.path.join(mexfake.ROOT, "p-dmpc_b200", "matlab", "plan_timestep_cuda.m")).read()
+    assert "PLAN_TIMESTEP = 6" in src and "directed_coupling_sequential" in src
+    assert "create_control_results_info_from_mex" in src

@@ -220,3 +220,20 @@ def test_free_space_and_blocked_world_counts():
         n_children = int(mpa.transition[0, it.trim_indices - 1].sum())
         assert r.is_exhausted[0] == 1 and r.n_expanded[0] == 1 + n_children == r.n_pops[0]
         assert np.isnan(r.y_predicted[0]).all()
+
+
+@pytest.mark.parametrize("name", ["timestep_road_triple_speed", "timestep_circle_single_speed"])
+def test_oracle_reproduces_golden_timesteps(name):
+    """The time-step fixtures (one-call inputs + expected outputs) against the C oracle driven level by
+    level with host-side obstacle assembly — the specification of pdmpc_plan_timestep."""
+    from helpers import load_golden_timesteps
+    from oracle import parity
+    from pdmpc_b200 import scenario
+    mpa, steps = load_golden_timesteps(name)
+    assert len(steps) >= 8
+    edges = 0
+    for batch, deps, exp in steps:
+        got = scenario.plan_timestep_by_levels(lambda b: oracle_py.plan_batch(mpa, b), batch, deps)
+        parity.compare(got, exp)
+        edges += deps.pred_idx.size
+    assert edges > 50

@@ -169,3 +169,17 @@ def test_realistic_mpa_is_refused_loudly(planner):
     with pytest.raises(capi.PdmpcError) as e:
         planner.plan_timestep(batch, TimestepDeps.build([[]], [None], mpa.Hp))
     assert e.value.code == capi.PDMPC_ERR_CAPACITY
+
+
+@pytest.mark.parametrize("name", ["timestep_road_triple_speed", "timestep_circle_single_speed"])
+def test_golden_timestep_fixture(planner, name):
+    """One-call time steps against the committed fixtures (tools/make_golden_timestep.py, written after
+    both CPU restatements agreed on every vehicle of every step): no oracle at run time."""
+    from helpers import load_golden_timesteps
+    mpa, steps = load_golden_timesteps(name)
+    planner.upload_mpa(mpa)
+    for batch, deps, exp in steps:
+        parity.compare(planner.plan_timestep(batch, deps, False), exp)
+    # all steps of the fixture as ONE call
+    batch, deps, exp = concat_timesteps(steps)
+    parity.compare(planner.plan_timestep(batch, deps, False), exp)
