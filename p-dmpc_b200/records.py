@@ -295,6 +295,19 @@ class TimestepDeps:
                 fb_y[i, k, :m] = a[1]
         return TimestepDeps(pred_ptr, pred_idx, fb_npts, fb_x, fb_y)
 
+    @staticmethod
+    def concat(parts: Sequence["TimestepDeps"], sizes: Sequence[int]) -> "TimestepDeps":
+        """Several independent blocks of searches (scenarios, time steps, priority permutations) as ONE call:
+        predecessor indices are shifted by the searches in front of each block."""
+        off, ptr, idx = 0, [np.zeros(1, dtype=np.int32)], []
+        for d, n in zip(parts, sizes):
+            ptr.append(d.pred_ptr[1:] + ptr[-1][-1])
+            idx.append(d.pred_idx + off)
+            off += int(n)
+        return TimestepDeps(np.concatenate(ptr).astype(np.int32), np.concatenate(idx).astype(np.int32),
+                            np.concatenate([d.fb_npts for d in parts]), np.concatenate([d.fb_x for d in parts]),
+                            np.concatenate([d.fb_y for d in parts]))
+
     def preds(self, i: int) -> np.ndarray:
         return self.pred_idx[self.pred_ptr[i]:self.pred_ptr[i + 1]]
 

@@ -622,6 +622,170 @@ class ScenarioRunner:
         return self.records
 
 
+# --------------------------------------------------------------------------- BASELINE config 3
+def computation_level_permutations(n_levels: int, seed: int) -> np.ndarray:
+    """PrioritizedExplorativeController.computation_level_permutations :241-309: n_levels permutations of
+    the computation levels forming a Latin square (every level class is tried at every position once);
+    row 1 is the identity, the others are filled cell by cell — always the cell with the fewest
+    possibilities, one of them at random — and re-drawn on a dead end.  Stream: RandStream('mt19937ar',
+    Seed = time step), which numpy's RandomState reproduces; [dev] randi(stream, n) is taken as
+    floor(n * rand) + 1 (MATLAB's exact rule is not published: parity unpinned)."""
+    n = int(n_levels)
+    result = np.zeros((n, n), dtype=np.int64)
+    result[0] = np.arange(1, n + 1)
+    rs = np.random.RandomState(int(seed) if int(seed) != 0 else 5489)
+    nth = 1
+    while nth < n:
+        perm = np.zeros(n, dtype=np.int64)
+        allowed = np.ones((n, n), dtype=bool)            # [level, class]
+        for col in range(n):
+            picked = result[:, col][result[:, col] != 0]
+            allowed[picked - 1, col] = False
+        filled, valid = 0, True
+        while filled < n:
+            sums = allowed.sum(axis=0)
+            cell = int(np.argmin(sums))                  # first minimum, like min()
+            n_pos = int(sums[cell])
+            if n_pos == 0:
+                valid = False
+                break
+            poss = np.flatnonzero(allowed[:, cell])
+            level = int(poss[int(np.floor(rs.random_sample() * n_pos))])
+            perm[cell] = level + 1
+            allowed[level, :] = False
+            allowed[:, cell] = True                      # never the minimum again
+            filled += 1
+        if not valid:
+            continue
+        result[nth] = perm
+        nth += 1
+    return result
+
+
+def weak_components(D: np.ndarray) -> np.ndarray:
+    """conncomp(digraph(D), 'Type', 'weak'): 1-based component label per vertex, components numbered in
+    the order of their lowest vertex (PrioritizedExplorativeController.m:207)."""
+    n = D.shape[0]
+    und = (D | D.T).astype(bool)
+    label = np.zeros(n, dtype=np.int64)
+    nxt = 0
+    for s0 in range(n):
+        if label[s0]:
+            continue
+        nxt += 1
+        stack = [s0]
+        label[s0] = nxt
+        while stack:
+            u = stack.pop()
+            for v in np.flatnonzero(und[u]):
+                if not label[v]:
+                    label[v] = nxt
+                    stack.append(int(v))
+    return label
+
+
+class ExplorativeRunner(ScenarioRunner):
+    """BASELINE configs[2]: simultaneous multiple prioritizations.  Every time step the n_CL computation
+    levels of the base prioritisation are permuted n_CL times (Latin square), every permutation is solved
+    as a complete time step, the cheapest one per weakly connected sub-graph is applied
+    (PrioritizedExplorativeController.m:21-176, PrioritizedExplorativeSequentialController.m:29-38).
+
+    All permutations a rank owns (sharding.shard_block_cyclic over `world` ranks = GPUs) go into ONE
+    timestep_fn call (len(my permutations) x n searches, predecessor relations block by block); the only
+    exchange between ranks is the cost matrix and the winners' plans (sharding.choose_permutation /
+    gather_winner_plans: one all_gather each, NCCL on GPUs).  The host logic is replicated on every rank.
+    [dev] the cost of an exhausted vehicle is the re-computed cost of its fallback trajectory
+    (plan_fallback :696-711); the winner does not re-seed the prioritizer (:169-173)."""
+
+    def __init__(self, sc: Scenario, timestep_fn, rank: int = 0, world: int = 1, device=None, max_permutations: int = 0):
+        super().__init__(sc, None, timestep_fn=timestep_fn)
+        self.rank, self.world, self.device = rank, world, device
+        self.max_permutations = max_permutations      # 0 = all n_CL (BASELINE: 8, one per GPU)
+        self.explorative_records: List[dict] = []
+
+    def step(self):
+        from . import sharding
+        sc, mpa = self.sc, self.mpa
+        n, Hp = sc.amount, mpa.Hp
+        self.k += 1
+        base = [self._iter_for(i) for i in range(n)]
+        A = couple(sc, self.pose)
+        D = (constant_priorities(A) if sc.priority == "constant" else coloring_priorities(A)).astype(bool)
+        levels = kahn(D.astype(np.int64))
+        n_cl = int(levels.max())
+        perms = computation_level_permutations(n_cl, self.k)
+        if self.max_permutations:
+            perms = perms[: self.max_permutations]
+        P = perms.shape[0]
+        belonging = weak_components(D)
+        fallbacks = [self._fallback_plan(i) for i in range(n)]
+        fb_cost = np.array([float(np.sum((base[i].reference_trajectory_points - fallbacks[i][1][:, :2]) ** 2))
+                            for i in range(n)])
+        mine = sharding.shard_block_cyclic(P, self.rank, self.world)
+        batches, deps = [], []
+        for p in mine:
+            lev_p = perms[p][levels - 1]                   # i11changem(levels, 1:n_CL, permutation), :55-59
+            Dp = D.copy()
+            for i, j in zip(*np.nonzero(D)):               # swap where the permuted levels invert the coupling, :66-78
+                if lev_p[i] > lev_p[j]:
+                    Dp[i, j], Dp[j, i] = False, True
+            its = []
+            for i in range(n):
+                it = dataclasses.replace(base[i], obstacles=list(base[i].obstacles),
+                                         dynamic_obstacle_area=list(base[i].dynamic_obstacle_area))
+                for j in np.flatnonzero(Dp[i, :]):         # consider_successors, area_of_standstill
+                    if abs(mpa.trim_speed[self.trim[j] - 1]) < 0.01:
+                        it.obstacles.append(occupied_area(*self.pose[j]))
+                its.append(it)
+            batches.append(SearchBatch.from_iters(its, Hp, sc.checker, mpa.dt_seconds))
+            deps.append(TimestepDeps.build([np.flatnonzero(Dp[:, i]) for i in range(n)], [f[0] for f in fallbacks], Hp))
+        plan_len = 1 + Hp + 3 * Hp + Hp + 2 * Hp * 8
+        cost_local = np.zeros((len(mine), n))
+        plans_local = np.zeros((len(mine), n, plan_len))
+        res = None
+        if len(mine):
+            batch = SearchBatch.concat(batches)
+            res = self.timestep_fn(batch, TimestepDeps.concat(deps, [n] * len(mine)))
+            for pl in range(len(mine)):
+                for v in range(n):
+                    r = pl * n + v
+                    if res.is_exhausted[r]:
+                        shapes, traj, trims = fallbacks[v]
+                        npts = np.array([s.shape[1] for s in shapes])
+                        sx = np.zeros((Hp, 8)); sy = np.zeros((Hp, 8))
+                        for k2, s2 in enumerate(shapes):
+                            sx[k2, :s2.shape[1]], sy[k2, :s2.shape[1]] = s2[0], s2[1]
+                        cost_local[pl, v] = fb_cost[v]
+                        plans_local[pl, v] = np.concatenate([[1.0], trims, traj.reshape(-1), npts, sx.reshape(-1), sy.reshape(-1)])
+                    else:
+                        cost_local[pl, v] = res.g_path[r, Hp]   # tree.get_cost(tree_path(end)), :100-104
+                        plans_local[pl, v] = np.concatenate([[0.0], res.trims[r, 1:], res.y_predicted[r].reshape(-1),
+                                                             res.shape_npts[r], res.shape_x[r].reshape(-1),
+                                                             res.shape_y[r].reshape(-1)])
+        chosen, solution_cost = sharding.choose_permutation(cost_local, mine, P, belonging, self.device)
+        plans = sharding.gather_winner_plans(plans_local, mine, P, chosen, belonging, self.device)
+        shapes_now: List[Optional[List[np.ndarray]]] = [None] * n
+        new_pose, new_trim = self.pose.copy(), self.trim.copy()
+        for v in range(n):
+            row = plans[v]
+            self.n_fallbacks += int(row[0])
+            o = 1
+            self.prev_trims[v] = row[o:o + Hp].astype(np.int64); o += Hp
+            self.prev_traj[v] = row[o:o + 3 * Hp].reshape(Hp, 3).copy(); o += 3 * Hp
+            npts = row[o:o + Hp].astype(np.int64); o += Hp
+            sx = row[o:o + Hp * 8].reshape(Hp, 8); o += Hp * 8
+            sy = row[o:o + Hp * 8].reshape(Hp, 8)
+            shapes_now[v] = [np.vstack([sx[k2, :npts[k2]], sy[k2, :npts[k2]]]) for k2 in range(Hp)]
+            new_pose[v] = self.prev_traj[v][0]
+            new_trim[v] = self.prev_trims[v][0]
+        self.prev_shapes = shapes_now
+        self.pose, self.trim = new_pose, new_trim
+        self.explorative_records.append({"step": self.k, "n_permutations": P, "n_levels": n_cl, "chosen": chosen,
+                                         "solution_cost": solution_cost, "searches_local": len(mine) * n,
+                                         "result_local": res})
+        return []
+
+
 def _assign_rows(dst: BatchResult, rows, src: BatchResult) -> None:
     for f in dataclasses.fields(dst):
         a = getattr(dst, f.name)

@@ -94,3 +94,75 @@ def test_first_minimum_and_rounding_rule():
         pytest.approx([0.12345679, -0.12345679, 0.0], abs=1e-15)
     with pytest.raises(ValueError):
         sharding.choose_permutation(cost[:2], [0, 1], 4, np.array([1, 2]))
+
+
+def _explorative_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from oracle import oracle_py
+    from pdmpc_b200 import scenario
+    from pdmpc_b200.mpa import get_mpa
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        mpa = get_mpa("single_speed", non_convex=True)
+        plan = lambda b: oracle_py.plan_batch(mpa, b)
+        r = scenario.ExplorativeRunner(scenario.commonroad_scenario(mpa, 12, seed=4),
+                                       lambda b, d: scenario.plan_timestep_by_levels(plan, b, d), rank=rank, world=world)
+        r.run(5)
+        q.put((rank, r.pose.tolist(), r.trim.tolist(), [e["chosen"].tolist() for e in r.explorative_records],
+               [e["solution_cost"].tolist() for e in r.explorative_records],
+               [e["searches_local"] for e in r.explorative_records]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_explorative_priorities_two_ranks_equal_one_process():
+    """BASELINE configs[2]: the permutations of a time step solved by two ranks (one all_gather of the
+    costs, one of the winners' plans) drive the same closed loop as one process solving all of them."""
+    import torch.multiprocessing as mp
+    from oracle import oracle_py
+    from pdmpc_b200 import scenario
+    from pdmpc_b200.mpa import get_mpa
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_explorative_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    mpa = get_mpa("single_speed", non_convex=True)
+    plan = lambda b: oracle_py.plan_batch(mpa, b)
+    one = scenario.ExplorativeRunner(scenario.commonroad_scenario(mpa, 12, seed=4),
+                                     lambda b, d: scenario.plan_timestep_by_levels(plan, b, d))
+    one.run(5)
+    for rank, pose, trim, chosen, cost, local in out:
+        assert pose == one.pose.tolist() and trim == one.trim.tolist()
+        assert chosen == [e["chosen"].tolist() for e in one.explorative_records]
+        assert cost == [e["solution_cost"].tolist() for e in one.explorative_records]
+    # the two ranks split the permutations of every step between them
+    for a, b, e in zip(out[0][5], out[1][5], one.explorative_records):
+        assert a + b == e["searches_local"] and a > 0
+    # some step chose a permutation other than the base prioritisation
+    assert any(any(c) for c in out[0][3])
+    # and differs from the plain prioritized loop
+    plainr = scenario.ScenarioRunner(scenario.commonroad_scenario(mpa, 12, seed=4), plan)
+    plainr.run(5)
+    assert not np.array_equal(plainr.pose, one.pose)
+
+
+def test_computation_level_permutations_form_a_latin_square():
+    from pdmpc_b200 import scenario
+    for n in (1, 2, 3, 5, 8):
+        for seed in (1, 2, 35):
+            r = scenario.computation_level_permutations(n, seed)
+            assert r[0].tolist() == list(range(1, n + 1))
+            assert all(sorted(row) == list(range(1, n + 1)) for row in r)
+            assert all(sorted(col) == list(range(1, n + 1)) for col in r.T)
+    assert np.array_equal(scenario.computation_level_permutations(5, 7), scenario.computation_level_permutations(5, 7))
+    D = np.zeros((5, 5), dtype=bool)
+    D[0, 1] = D[3, 4] = True
+    assert scenario.weak_components(D).tolist() == [1, 1, 2, 3, 3]

@@ -183,3 +183,22 @@ def test_golden_timestep_fixture(planner, name):
     # all steps of the fixture as ONE call
     batch, deps, exp = concat_timesteps(steps)
     parity.compare(planner.plan_timestep(batch, deps, False), exp)
+
+
+def test_explorative_priorities_config2_all_permutations_in_one_call(planner):
+    """BASELINE configs[2]: every priority permutation of a time step (n_CL x 20 searches, one DAG per
+    permutation) as ONE pdmpc_plan_timestep call; closed loop identical to the oracle-driven one."""
+    mpa = get_mpa("triple_speed", non_convex=True)
+    planner.upload_mpa(mpa)
+    plan = lambda b: oracle_py.plan_batch(mpa, b)
+    dev = scenario.ExplorativeRunner(scenario.commonroad_scenario(mpa, 20, seed=2),
+                                     lambda b, d: planner.plan_timestep(b, d, False))
+    ref = scenario.ExplorativeRunner(scenario.commonroad_scenario(mpa, 20, seed=2),
+                                     lambda b, d: scenario.plan_timestep_by_levels(plan, b, d))
+    dev.run(6)
+    ref.run(6)
+    assert np.array_equal(dev.pose, ref.pose) and np.array_equal(dev.trim, ref.trim)
+    for a, b in zip(dev.explorative_records, ref.explorative_records):
+        assert np.array_equal(a["chosen"], b["chosen"]) and np.array_equal(a["solution_cost"], b["solution_cost"])
+        parity.compare(a["result_local"], b["result_local"])
+    assert max(e["n_permutations"] for e in ref.explorative_records) >= 3
