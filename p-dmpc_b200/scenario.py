@@ -762,8 +762,9 @@ class ExplorativeRunner(ScenarioRunner):
                         plans_local[pl, v] = np.concatenate([[0.0], res.trims[r, 1:], res.y_predicted[r].reshape(-1),
                                                              res.shape_npts[r], res.shape_x[r].reshape(-1),
                                                              res.shape_y[r].reshape(-1)])
-        chosen, solution_cost = sharding.choose_permutation(cost_local, mine, P, belonging, self.device)
-        plans = sharding.gather_winner_plans(plans_local, mine, P, chosen, belonging, self.device)
+        coll = self.world > 1
+        chosen, solution_cost = sharding.choose_permutation(cost_local, mine, P, belonging, self.device, coll)
+        plans = sharding.gather_winner_plans(plans_local, mine, P, chosen, belonging, self.device, coll)
         shapes_now: List[Optional[List[np.ndarray]]] = [None] * n
         new_pose, new_trim = self.pose.copy(), self.trim.copy()
         for v in range(n):

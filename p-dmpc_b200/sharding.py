@@ -47,9 +47,10 @@ def _dist():
     return None
 
 
-def _all_gather_rows(local: np.ndarray, device=None) -> np.ndarray:
-    """Concatenate equally shaped float64 arrays of all ranks along a new leading axis."""
-    dist = _dist()
+def _all_gather_rows(local: np.ndarray, device=None, collective: bool = True) -> np.ndarray:
+    """Concatenate equally shaped float64 arrays of all ranks along a new leading axis.
+    collective=False: this caller owns everything (a single-rank computation inside a multi-rank job)."""
+    dist = _dist() if collective else None
     if dist is None:
         return local[None]
     import torch
@@ -62,7 +63,7 @@ def _all_gather_rows(local: np.ndarray, device=None) -> np.ndarray:
 
 
 def choose_permutation(cost_local: np.ndarray, perm_ids_local: Sequence[int], n_permutations: int,
-                       belonging_vector: np.ndarray, device=None):
+                       belonging_vector: np.ndarray, device=None, collective: bool = True):
     """cost_local[p, v]: cost-to-come of vehicle v's goal node in the p-th permutation THIS rank
     solved (perm_ids_local[p] = its global index); belonging_vector[v] = sub-graph (1-based) of v.
     Returns (chosen permutation per sub-graph [n_graphs], rounded cost matrix [n_permutations, n_graphs])."""
@@ -73,7 +74,7 @@ def choose_permutation(cost_local: np.ndarray, perm_ids_local: Sequence[int], n_
     for row, p in zip(np.asarray(cost_local, dtype=np.float64).reshape(len(perm_ids_local), n_veh), perm_ids_local):
         full_local[p] = row
         mask_local[p] = 1.0
-    gathered = _all_gather_rows(np.stack([full_local, mask_local]), device)     # [world, 2, P, V]
+    gathered = _all_gather_rows(np.stack([full_local, mask_local]), device, collective)     # [world, 2, P, V]
     cost = np.zeros((n_permutations, n_veh))
     owned = np.zeros((n_permutations, n_veh))
     for r in range(gathered.shape[0]):           # every permutation is owned by exactly one rank
@@ -92,7 +93,7 @@ def choose_permutation(cost_local: np.ndarray, perm_ids_local: Sequence[int], n_
 
 
 def gather_winner_plans(plans_local: np.ndarray, perm_ids_local: Sequence[int], n_permutations: int,
-                        chosen: np.ndarray, belonging_vector: np.ndarray, device=None) -> np.ndarray:
+                        chosen: np.ndarray, belonging_vector: np.ndarray, device=None, collective: bool = True) -> np.ndarray:
     """plans_local[p, v, :] = flat plan (trims, poses, shapes ...) of vehicle v in local permutation p.
     Returns [n_veh, plan_len]: for every vehicle the plan of its sub-graph's chosen permutation
     (the role of publish_predictions with permutation index 0, :156-162)."""
@@ -102,7 +103,7 @@ def gather_winner_plans(plans_local: np.ndarray, perm_ids_local: Sequence[int], 
     full = np.zeros((n_permutations, n_veh, plans_local.shape[2]))
     for row, p in zip(plans_local, perm_ids_local):
         full[p] = row
-    gathered = _all_gather_rows(full, device).sum(axis=0)        # disjoint ownership: sum == select
+    gathered = _all_gather_rows(full, device, collective).sum(axis=0)        # disjoint ownership: sum == select
     out = np.zeros((n_veh, plans_local.shape[2]))
     for v in range(n_veh):
         out[v] = gathered[chosen[belonging_vector[v] - 1], v]
