@@ -454,6 +454,95 @@ def couple(sc: Scenario, poses: np.ndarray, all_coupled: bool = False) -> np.nda
     return A
 
 
+# --------------------------------------------------------------------------- BASELINE config 4
+_REACH_CACHE: dict = {}
+
+
+def _convex_hull_closed(pts: np.ndarray) -> np.ndarray:
+    """Andrew's monotone chain: counter-clockwise hull of [m, 2] points as a closed [2, h + 1] polygon."""
+    p = np.unique(pts, axis=0)                     # sorted by x, then y
+    if p.shape[0] < 3:
+        return np.vstack([p, p[:1]]).T
+
+    def half(seq):
+        out = []
+        for q in seq:
+            while len(out) >= 2 and ((out[-1][0] - out[-2][0]) * (q[1] - out[-2][1]) -
+                                     (out[-1][1] - out[-2][1]) * (q[0] - out[-2][0])) <= 0:
+                out.pop()
+            out.append(q)
+        return out
+
+    lower, upper = half(p), half(p[::-1])
+    hull = np.array(lower[:-1] + upper[:-1])
+    return np.vstack([hull, hull[:1]]).T
+
+
+def local_reachable_sets_conv(mpa: MotionPrimitiveAutomaton) -> List[List[np.ndarray]]:
+    """reachability_analysis_offline (MotionPrimitiveAutomaton.m:252-392): for every start trim i and step t
+    the convexified union of the offset areas of all maneuvers a vehicle can execute in step t after any trim
+    sequence from i, in the vehicle frame of step 0 (local_reachable_sets_conv{i, t}).  [dev] convhull(union(.))
+    is computed as the hull of the areas' vertices (the same set; polyshape's vertex order is not reproduced)."""
+    key = id(mpa)
+    if key in _REACH_CACHE:
+        return _REACH_CACHE[key]
+    nT, Hp = mpa.n_trims, mpa.Hp
+    out: List[List[np.ndarray]] = []
+    for i in range(nT):
+        st = np.array([[0.0, 0.0, 0.0]])
+        tr = np.array([i])
+        per_step = []
+        for t in range(Hp):
+            pts, nst, ntr = [], [], []
+            for f in np.unique(tr):
+                sel = st[tr == f]
+                c, sn = np.cos(sel[:, 2]), np.sin(sel[:, 2])
+                for to in np.flatnonzero(mpa.transition[t, f]):
+                    e = int(mpa.edge_index[f, to])
+                    m = int(mpa.area_npts[e, 0])
+                    ax, ay = mpa.area_x[e, 0, :m], mpa.area_y[e, 0, :m]
+                    px = c[:, None] * ax[None] - sn[:, None] * ay[None] + sel[:, 0:1]     # translate_global
+                    py = sn[:, None] * ax[None] + c[:, None] * ay[None] + sel[:, 1:2]
+                    pts.append(np.stack([px.reshape(-1), py.reshape(-1)], axis=1))
+                    nst.append(np.stack([c * mpa.edge_dx[e] - sn * mpa.edge_dy[e] + sel[:, 0],
+                                         sn * mpa.edge_dx[e] + c * mpa.edge_dy[e] + sel[:, 1],
+                                         sel[:, 2] + mpa.edge_dyaw[e]], axis=1))
+                    ntr.append(np.full(sel.shape[0], to))
+            per_step.append(_convex_hull_closed(np.round(np.concatenate(pts), 12)))
+            st, tr = np.concatenate(nst), np.concatenate(ntr)
+            # states that coincide (same trim, same pose) need to be expanded once only
+            keyed = np.round(np.column_stack([tr, st]), 9)
+            _, first = np.unique(keyed, axis=0, return_index=True)
+            st, tr = st[np.sort(first)], tr[np.sort(first)]
+        out.append(per_step)
+    _REACH_CACHE[key] = out
+    return out
+
+
+def reachable_sets_at(mpa: MotionPrimitiveAutomaton, x: float, y: float, yaw: float, trim: int) -> List[np.ndarray]:
+    """get_reachable_sets (MotionPrimitiveAutomaton.m:649-687): the local sets of the current trim placed at the pose."""
+    c, s_ = np.cos(yaw), np.sin(yaw)
+    return [np.vstack([c * a[0] - s_ * a[1] + x, s_ * a[0] + c * a[1] + y]) for a in local_reachable_sets_conv(mpa)[trim - 1]]
+
+
+def limit_computation_levels(D: np.ndarray, max_num_CLs: int) -> np.ndarray:
+    """[dev] stand-in for the weigh + cut step (PrioritizedController.group :381-397, GreedyCut): the edges kept as
+    SEQUENTIAL are chosen greedily in topological order so that no vehicle sits deeper than max_num_CLs
+    computation levels; the other predecessors plan in PARALLEL and are considered through their reachable
+    sets (parallel_coupling_reachability :399-415)."""
+    n = D.shape[0]
+    seq = np.zeros_like(D, dtype=bool)
+    level = np.zeros(n, dtype=np.int64)
+    for j in np.argsort(kahn(D.astype(np.int64)), kind="stable"):
+        lv = 1
+        for i in np.flatnonzero(D[:, j]):
+            if level[i] < max_num_CLs:
+                seq[i, j] = True
+                lv = max(lv, level[i] + 1)
+        level[j] = lv
+    return seq
+
+
 # --------------------------------------------------------------------------- closed loop
 PlanFn = Callable[[SearchBatch], BatchResult]
 
@@ -479,6 +568,7 @@ class ScenarioRunner:
         self.sc = sc
         self.plan_fn = plan_fn
         self.timestep_fn = timestep_fn
+        self.max_num_CLs = max_num_CLs              # honoured by the one-call path (timestep_inputs)
         self.timestep_records: List[tuple] = []     # (step, batch, deps, result) of the one-call path
         self.mpa = sc.mpa
         n = sc.amount
@@ -529,7 +619,12 @@ class ScenarioRunner:
             for j in np.flatnonzero(D[i, :]):
                 if abs(mpa.trim_speed[self.trim[j] - 1]) < 0.01:
                     iters[i].obstacles.append(occupied_area(*self.pose[j]))
-        preds = [np.flatnonzero(D[:, i]) for i in range(n)]
+        D = D.astype(bool)
+        seq = limit_computation_levels(D, self.max_num_CLs) if self.max_num_CLs < n else D
+        for i in range(n):   # parallel predecessors: reachable sets as dynamic obstacles, PrioritizedController.m:399-415,493-501
+            for j in np.flatnonzero(D[:, i] & ~seq[:, i]):
+                iters[i].dynamic_obstacle_area.append(reachable_sets_at(mpa, *self.pose[j], int(self.trim[j])))
+        preds = [np.flatnonzero(seq[:, i]) for i in range(n)]
         fallbacks = [self._fallback_plan(i) for i in range(n)]
         return iters, preds, fallbacks
 

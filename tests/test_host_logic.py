@@ -219,3 +219,53 @@ def test_timestep_by_levels_uses_fallback_areas_of_exhausted_predecessors():
     assert not np.array_equal(with_fb.y_predicted[1], without.y_predicted[1]) or \
         with_fb.n_expanded[1] != without.n_expanded[1]
 
+
+
+def test_config4_reachable_sets_and_level_limit():
+    """BASELINE configs[3]: local reachable sets (convexified, MotionPrimitiveAutomaton.m:252-392) and the
+    computation-level limit that turns sequential predecessors into parallel ones."""
+    mpa = get_mpa("single_speed", non_convex=True)
+    sets = scenario.local_reachable_sets_conv(mpa)
+    assert len(sets) == mpa.n_trims and all(len(s) == mpa.Hp for s in sets)
+
+    def inside(poly, pts):   # closed counter-clockwise convex polygon [2, h + 1]
+        ex, ey = np.diff(poly[0]), np.diff(poly[1])
+        cr = ex[:, None] * (pts[None, :, 1] - poly[1, :-1, None]) - ey[:, None] * (pts[None, :, 0] - poly[0, :-1, None])
+        return bool((cr >= -1e-9).all())
+
+    t0 = mpa.trim_from_values(0.0, 0.0)
+    for to in np.flatnonzero(mpa.transition[0, t0 - 1]):          # every first-step area lies in the step-1 set
+        e = int(mpa.edge_index[t0 - 1, to])
+        m = int(mpa.area_npts[e, 0])
+        assert inside(sets[t0 - 1][0], np.column_stack([mpa.area_x[e, 0, :m], mpa.area_y[e, 0, :m]]))
+    for per_step in sets:
+        for a in per_step:
+            assert a.shape[0] == 2 and a.shape[1] >= 5 and np.array_equal(a[:, 0], a[:, -1])
+    placed = scenario.reachable_sets_at(mpa, 1.0, 2.0, np.pi / 2, t0)
+    assert np.allclose(placed[0][0], 1.0 - sets[t0 - 1][0][1]) and np.allclose(placed[0][1], 2.0 + sets[t0 - 1][0][0])
+
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        n = 12
+        prio = rng.permutation(n)
+        A = rng.random((n, n)) < 0.3
+        A = A | A.T
+        D = A & (prio[:, None] < prio[None, :])
+        for cl in (1, 2, 4, 99):
+            seq = scenario.limit_computation_levels(D, cl)
+            assert not (seq & ~D).any()
+            assert scenario.kahn(seq.astype(np.int64)).max() <= max(cl, 1)
+            if cl == 99:
+                assert np.array_equal(seq, D)
+            if cl == 1:
+                assert not seq.any()
+
+    mpa3 = get_mpa("single_speed", non_convex=True)
+    plan = lambda b: oracle_py.plan_batch(mpa3, b)
+    sc = scenario.commonroad_scenario(mpa3, 40, seed=1, allow_shared_paths=True)
+    r = scenario.ScenarioRunner(sc, None, max_num_CLs=2,
+                                timestep_fn=lambda b, d: scenario.plan_timestep_by_levels(plan, b, d))
+    r.run(3)
+    _k, batch, deps, _res = r.timestep_records[-1]
+    assert batch.n == 40 and np.diff(batch.poly_ptr).max() > 8       # reachable sets are many-vertex obstacles
+    assert deps.pred_idx.size > 0

@@ -202,3 +202,32 @@ def test_explorative_priorities_config2_all_permutations_in_one_call(planner):
         assert np.array_equal(a["chosen"], b["chosen"]) and np.array_equal(a["solution_cost"], b["solution_cost"])
         parity.compare(a["result_local"], b["result_local"])
     assert max(e["n_permutations"] for e in ref.explorative_records) >= 3
+
+
+@pytest.mark.parametrize("max_cls", [1, 2, 4])
+def test_config3_40_vehicles_reachable_set_obstacles(planner, max_cls):
+    """BASELINE configs[3] (computation-level-limited planning): 40 vehicles, at most max_cls computation
+    levels, the other predecessors enter as reachable-set obstacles (polygons of up to 25 vertices, hundreds
+    of obstacle columns per search).  One-call time steps in closed loop against the oracle, then every
+    search of the run (with the predecessors' areas assembled on the host) through all launch shapes."""
+    from test_parity_gpu import check
+    mpa = get_mpa("triple_speed", non_convex=True)
+    sc = scenario.commonroad_scenario(mpa, 40, seed=1, allow_shared_paths=True)
+    planner.upload_mpa(mpa)
+    plan = lambda b: oracle_py.plan_batch(mpa, b)
+    runner = scenario.ScenarioRunner(sc, None, max_num_CLs=max_cls,
+                                     timestep_fn=lambda b, d: planner.plan_timestep(b, d, False))
+    level_batches = []
+
+    def capture(b):
+        level_batches.append(b)
+        return plan(b)
+
+    for _ in range(5):
+        dev = runner.step_timestep()
+        _k, batch, deps, _ = runner.timestep_records[-1]
+        parity.compare(dev, scenario.plan_timestep_by_levels(capture, batch, deps))
+    flat = SearchBatch.concat(level_batches)
+    assert flat.n == 200 and np.diff(flat.poly_ptr).max() >= 15
+    info, _dev, _ref = check(planner, mpa, flat)
+    assert info["exhausted"] > 0
