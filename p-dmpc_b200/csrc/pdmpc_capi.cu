@@ -37,6 +37,7 @@ constexpr int kPts = PDMPC_PTS_SMEM;         // polyline points (lanelet bounds 
 constexpr int kWarpsThroughput = 16;
 #define KERNEL_LAT search_kernel<kHeapSmem, kPts, 1, false>
 #define KERNEL_THR search_kernel<kHeapSmem, kPts, kWarpsThroughput, true>
+#define KERNEL_LAT_DEPS search_kernel<kHeapSmem, kPts, 1, false, true>
 using WarpSmem = TileSmem<kHeapSmem, kPts>;
 constexpr size_t kSmemLimit = 227 * 1024;
 // "lanes" = one THREAD per search (pdmpc_lanes.cuh), one CTA per SM; searches that outgrow a
@@ -87,7 +88,8 @@ struct pdmpc_handle {
     bool cta_ok = false;              // the CTA-per-search kernel is launchable (shared memory opt-in granted)
     bool cta_deps_ok = false;         // ... and its pdmpc_plan_timestep instance
     // pdmpc_plan_timestep: dependency CSR, fallback areas, done flags (one packed upload)
-    DBuf d_deps, d_done;
+    DBuf d_deps, d_done, d_depx, d_depy, d_depn;
+    bool lat_deps_ok = false;
     void *pin_deps = nullptr;
     size_t pin_deps_cap = 0;
     DepsDev deps{};
@@ -238,6 +240,8 @@ int pdmpc_create(int device_id, pdmpc_handle **out) {
     h->lat_ctas_per_sm = occ;
     h->cta_ok = cudaFuncSetAttribute(KERNEL_CTA, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(CtaSmemT)) == cudaSuccess;
+    h->lat_deps_ok = cudaFuncSetAttribute(KERNEL_LAT_DEPS, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(WarpSmem)) == cudaSuccess;
     h->cta_deps_ok = cudaFuncSetAttribute(KERNEL_CTA_DEPS, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)sizeof(CtaDepsSmemT)) == cudaSuccess;
     cudaGetLastError();
@@ -260,6 +264,9 @@ int pdmpc_destroy(pdmpc_handle *h) {
     h->d_out_pack.release();
     h->d_deps.release();
     h->d_done.release();
+    h->d_depx.release();
+    h->d_depy.release();
+    h->d_depn.release();
     h->wc_chunks.release();
     if (h->pin_order) cudaFreeHost(h->pin_order);
     for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
@@ -1195,14 +1202,17 @@ int pdmpc_plan_timestep(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_t
     if (!in || !deps || !deps->pred_ptr) return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep: NULL argument");
     const int n = in->n_searches, Hp = h->mpa.Hp;
     if (n < 0) return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep: n_searches < 0");
-    if (!h->cta_deps_ok)
-        return fail(h, PDMPC_ERR_CUDA, "plan_timestep: the one-CTA-per-search kernel is not launchable on this device");
+    // launch shape: one CTA per search (lowest latency) for up to two searches per SM, else — and for search
+    // trees beyond what that kernel holds — one warp per search; pdmpc_set_variant 1..3 / 4..5 force either
+    bool use_cta;
     {
         const int cap = h->user_node_cap ? h->user_node_cap : std::min(h->full_tree_nodes + 8, 1 << 20);
-        if (cap > kCtaFlags)
-            return fail(h, PDMPC_ERR_CAPACITY,
-                        "plan_timestep: the full search tree of this MPA exceeds the 32768 nodes the one-CTA-per-search "
-                        "kernel holds; plan level by level with pdmpc_plan_batch");
+        const bool cta_possible = h->cta_deps_ok && cap <= kCtaFlags;
+        if (h->variant_mode >= 4) use_cta = cta_possible;
+        else if (h->variant_mode >= 1) use_cta = false;
+        else use_cta = cta_possible && n <= 2 * h->num_sms;
+        if (!use_cta && !h->lat_deps_ok)
+            return fail(h, PDMPC_ERR_CUDA, "plan_timestep: search kernel is not launchable on this device");
     }
     // ---- validate the relation, order the searches topologically (utility/kahn.m:1-24) ----------
     if (deps->pred_ptr[0] != 0) return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep: pred_ptr must start at 0");
@@ -1284,15 +1294,28 @@ int pdmpc_plan_timestep(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_t
     dp.fb_x = has_fb ? reinterpret_cast<const double *>(db + off[3]) : nullptr;
     dp.fb_y = has_fb ? reinterpret_cast<const double *>(db + off[4]) : nullptr;
     dp.done = h->d_done.as<int>();
-    // ---- one persistent launch: CTAs take the searches in topological order -----------------------
+    dp.dep_x = dp.dep_y = nullptr;
+    dp.dep_n = nullptr;
+    // ---- one persistent launch: CTAs / warps take the searches in topological order ----------------
     CU_TRY(h, cudaMemsetAsync(h->out.counters, 0, 16 * sizeof(unsigned long long), h->stream));
     CU_TRY(h, cudaMemsetAsync(h->work_counter.p, 0, sizeof(unsigned), h->stream));
-    const int grid = std::min(n, h->num_sms);
+    const int grid = use_cta ? std::min(n, h->num_sms) : std::min(n, h->num_sms * h->lat_ctas_per_sm);
     rc = ensure_arena(h, grid);
     if (rc != PDMPC_OK) return rc;
+    if (!use_cta) {   // per-slot scratch for the predecessors' areas
+        CU_TRY(h, h->d_depx.reserve((size_t)grid * kDepCols * sizeof(double)));
+        CU_TRY(h, h->d_depy.reserve((size_t)grid * kDepCols * sizeof(double)));
+        CU_TRY(h, h->d_depn.reserve((size_t)grid * (kDepCols / kAreaStride) * sizeof(int)));
+        dp.dep_x = h->d_depx.as<double>(); dp.dep_y = h->d_depy.as<double>(); dp.dep_n = h->d_depn.as<int>();
+    }
     CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
-    KERNEL_CTA_DEPS<<<grid, (kCtaHelpers + kCtaHelpers / 3) * kWarp, sizeof(CtaDepsSmemT), h->stream>>>(
-        h->mpa, h->batch, h->out, h->arena, h->work_counter.as<unsigned>(), h->cta_heap_smem, 0, dp);
+    if (use_cta)
+        KERNEL_CTA_DEPS<<<grid, (kCtaHelpers + kCtaHelpers / 3) * kWarp, sizeof(CtaDepsSmemT), h->stream>>>(
+            h->mpa, h->batch, h->out, h->arena, h->work_counter.as<unsigned>(), h->cta_heap_smem, 0, dp);
+    else
+        KERNEL_LAT_DEPS<<<grid, kWarp, sizeof(WarpSmem), h->stream>>>(h->mpa, h->batch, h->out, h->arena,
+                                                                      h->work_counter.as<unsigned>(),
+                                                                      TraceDev{-1, nullptr, 0, nullptr}, nullptr, dp);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
     h->timing_pending_kernel = true;

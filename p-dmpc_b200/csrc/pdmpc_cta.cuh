@@ -70,7 +70,7 @@ constexpr int kCtaHeap = 4096;      // heap entries in shared memory
 constexpr int kCtaPts = 512;        // staged polyline points
 constexpr int kCtaCache = 1024;     // node-record cache entries (direct mapped by id)
 constexpr int kCtaFlags = 32768;    // validity flags (1 byte per node id) — searches need cap <= this
-constexpr int kCtaDepCols = PDMPC_TIMESTEP_COLS;   // columns of predecessors' areas (pdmpc_plan_timestep)
+constexpr int kCtaDepCols = kDepCols;   // columns of predecessors' areas (pdmpc_plan_timestep)
 constexpr int kCtaDepPolys = kCtaDepCols / kAreaStride;
 
 struct __align__(16) CtaJob {       // one expansion: children nid0 .. nid0 + nchild - 1

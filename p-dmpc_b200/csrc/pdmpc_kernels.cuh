@@ -126,7 +126,12 @@ struct DepsDev {
     const int *fb_npts;               // [n*Hp] fallback areas (may be null)
     const double *fb_x, *fb_y;        // [n*Hp*kAreaStride]
     int *done;                        // [n] 0 pending, 1 planned, 2 exhausted (release/acquire at gpu scope)
+    // warp-per-search kernel only: per-slot scratch in HBM for the predecessors' areas (the CTA kernel keeps
+    // them in shared memory): kDepCols columns / kDepCols / 8 point counts per slot
+    double *dep_x, *dep_y;
+    int *dep_n;
 };
+constexpr int kDepCols = PDMPC_TIMESTEP_COLS;
 __device__ __forceinline__ int ld_acquire_gpu(const int *p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -622,10 +627,13 @@ struct __align__(16) TileSmem {
 #ifndef PDMPC_MIN_CTAS_LAT
 #define PDMPC_MIN_CTAS_LAT 12  // resident one-warp CTAs per SM the latency shape is compiled for (register cap)
 #endif
-template <int HS, int SP, int WARPS, bool SMEM_TABLES>
+// DEPS (pdmpc_plan_timestep for batches beyond one CTA per search): a search waits for its predecessors'
+// done flags, copies their planned (or fallback) areas into its slot's scratch and checks against them;
+// work items are handed out in a topological order, so a warp only ever waits for searches taken earlier.
+template <int HS, int SP, int WARPS, bool SMEM_TABLES, bool DEPS = false>
 __global__ void __launch_bounds__(WARPS *kWarp, WARPS == 1 ? PDMPC_MIN_CTAS_LAT : 1) search_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar,
                                                               unsigned *work_counter, TraceDev tr,
-                                                              const unsigned *n_work_dev) {
+                                                              const unsigned *n_work_dev, DepsDev dp = DepsDev{}) {
     constexpr int TILE = kWarp;
     // number of work items: the whole batch, or (second stage after the lane-per-search
     // kernel) the length of the hand-over list b.order, known only on the device
@@ -709,6 +717,14 @@ __global__ void __launch_bounds__(WARPS *kWarp, WARPS == 1 ? PDMPC_MIN_CTAS_LAT 
     // the parent record of the last pop (siblings are usually popped back to back)
     unsigned last_par = 0;
     double ppx = 0.0, ppy = 0.0, pc = 0.0, ps = 0.0;
+    // DEPS: this slot's scratch for the predecessors' areas; lane k - 1 keeps the real column count of step k
+    int n_pred = 0, my_dep_cols = 0;
+    double *dpx = nullptr, *dpy = nullptr;
+    int *dpn = nullptr;
+    if (DEPS) {
+        const size_t sl = (size_t)blockIdx.x * WARPS + warp_id;
+        dpx = dp.dep_x + sl * kDepCols; dpy = dp.dep_y + sl * kDepCols; dpn = dp.dep_n + sl * (kDepCols / kAreaStride);
+    }
 
     for (;;) {
         PROF_MARK(7);
@@ -775,6 +791,11 @@ __global__ void __launch_bounds__(WARPS *kWarp, WARPS == 1 ? PDMPC_MIN_CTAS_LAT 
                     }
                 }
             }
+            if (DEPS) {   // publish_predictions (PrioritizedController.m:355-364): the areas above are final
+                __threadfence();
+                t.sync();
+                if (t.lane == 0) st_release_gpu(dp.done + si, exhausted ? 2 : 1);
+            }
             phase = IDLE;
         }
         if (phase == IDLE) {
@@ -785,6 +806,42 @@ __global__ void __launch_bounds__(WARPS *kWarp, WARPS == 1 ? PDMPC_MIN_CTAS_LAT 
             si = b.order ? __ldg(b.order + si_u) : (int)si_u;
             // ---- per-search set-up ------------------------------------------------
             t.sync();
+            if (DEPS) {   // consider_predecessors (PrioritizedController.m:449-506) on the device
+                const int q0 = __ldg(dp.pred_ptr + si);
+                n_pred = __ldg(dp.pred_ptr + si + 1) - q0;
+                for (int r = t.lane; r < n_pred; r += TILE) {
+                    const int *flag = dp.done + __ldg(dp.pred_idx + q0 + r);
+                    while (ld_acquire_gpu(flag) == 0) __nanosleep(200);
+                }
+                t.sync();
+                const double qn = nan("");
+                for (int idx = t.lane; idx < n_pred * Hp * kAreaStride; idx += TILE) {
+                    const int v = idx % kAreaStride, pk = idx / kAreaStride;   // pk = (k - 1) * n_pred + r
+                    const int r = pk % n_pred, k0 = pk / n_pred;
+                    const int j = __ldg(dp.pred_idx + q0 + r);
+                    const bool planned = ld_acquire_gpu(dp.done + j) == 1;
+                    const size_t os = (size_t)j * Hp + k0;
+                    int np = 0;
+                    double vx = qn, vy = qn;
+                    if (planned) {   // written during this launch: L2, never the read-only path
+                        np = __ldcg(o.shape_npts + os);
+                        if (v < np) { vx = __ldcg(o.shape_x + os * kAreaStride + v); vy = __ldcg(o.shape_y + os * kAreaStride + v); }
+                    } else if (dp.fb_npts) {
+                        np = __ldg(dp.fb_npts + os);
+                        if (v < np) { vx = __ldg(dp.fb_x + os * kAreaStride + v); vy = __ldg(dp.fb_y + os * kAreaStride + v); }
+                    }
+                    dpx[idx] = vx; dpy[idx] = vy;
+                    if (v == 0) dpn[pk] = np;
+                }
+                __threadfence_block();
+                t.sync();
+                my_dep_cols = 0;
+                if (t.lane < Hp)
+                    for (int r = 0; r < n_pred; ++r) {
+                        const int np = dpn[t.lane * n_pred + r];
+                        if (np) my_dep_cols += np + 1;
+                    }
+            }
             for (int k = t.lane; k < Hp; k += TILE) {
                 sm.refx[k] = __ldg(b.ref_x + (size_t)si * Hp + k);
                 sm.refy[k] = __ldg(b.ref_y + (size_t)si * Hp + k);
@@ -911,7 +968,12 @@ __global__ void __launch_bounds__(WARPS *kWarp, WARPS == 1 ? PDMPC_MIN_CTAS_LAT 
                 const int st_lo = obase + sm.rng[0], st_hi = obase + sm.rng[1];
                 const int dy_lo = obase + sm.rng[cK], dy_hi = obase + sm.rng[cK + 1];
                 cols += (unsigned long long)((st_hi - st_lo) + (dy_hi - dy_lo) + (lhi - llo));
+                if (DEPS) cols += (unsigned long long)t.shfl(my_dep_cols, cK - 1);
                 if (interx_dispatch<TILE>(ns, opx, opy, st_lo, st_hi, dy_lo, dy_hi, sm.shx, sm.shy, t))
+                    valid = false;
+                else if (DEPS && n_pred > 0 &&
+                         interx_dispatch<TILE>(ns, dpx, dpy, (cK - 1) * n_pred * kAreaStride, cK * n_pred * kAreaStride,
+                                               0, 0, sm.shx, sm.shy, t))
                     valid = false;
                 else if (interx_dispatch<TILE>(nbs, lpx, lpy, llo, lhi, 0, 0, sm.bhx, sm.bhy, t))
                     valid = false;
@@ -924,6 +986,15 @@ __global__ void __launch_bounds__(WARPS *kWarp, WARPS == 1 ? PDMPC_MIN_CTAS_LAT 
                         const int v0 = __ldg(b.poly_ptr + p), v1 = __ldg(b.poly_ptr + p + 1);
                         cols += (unsigned long long)(v1 - v0);
                         if (sat_collide<TILE>(sm.shx, sm.shy, ns, b.vert_x + v0, b.vert_y + v0, v1 - v0, t))
+                            valid = false;
+                    }
+                }
+                if (DEPS) {
+                    for (int r = 0; r < n_pred && valid; ++r) {
+                        const int pk = (cK - 1) * n_pred + r, nv = dpn[pk];
+                        if (nv < 2) continue;
+                        cols += (unsigned long long)nv;
+                        if (sat_collide<TILE, false>(sm.shx, sm.shy, ns, dpx + pk * kAreaStride, dpy + pk * kAreaStride, nv, t))
                             valid = false;
                     }
                 }

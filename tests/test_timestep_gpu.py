@@ -161,14 +161,65 @@ def test_bad_relations_rejected(planner):
     assert int(ok.status.max()) == 0
 
 
-def test_realistic_mpa_is_refused_loudly(planner):
-    """Search trees beyond 32768 nodes do not fit the one-CTA-per-search kernel: no silent fallback."""
+def test_realistic_mpa_takes_the_warp_kernel(planner):
+    """Search trees beyond 32768 nodes do not fit the one-CTA-per-search kernel: the one-call time step
+    then runs one warp per search (same hand-over, per-slot scratch in HBM) — same answers."""
     mpa = get_mpa("realistic", non_convex=True)
     planner.upload_mpa(mpa)
-    batch = SearchBatch.from_iters([straight_iter(mpa)], mpa.Hp, CHECKER_INTERX, mpa.dt_seconds)
-    with pytest.raises(capi.PdmpcError) as e:
-        planner.plan_timestep(batch, TimestepDeps.build([[]], [None], mpa.Hp))
-    assert e.value.code == capi.PDMPC_ERR_CAPACITY
+    items = collect_timesteps(mpa, scenario.commonroad_scenario(mpa, 12, seed=2), 3)
+    for batch, deps, ref in items:
+        parity.compare(planner.plan_timestep(batch, deps, False), ref)
+
+
+@pytest.mark.parametrize("variant", [1, 4])
+def test_both_launch_shapes_of_the_time_step(planner, variant):
+    """pdmpc_set_variant forces the warp-per-search (1) or the CTA-per-search (4) shape of pdmpc_plan_timestep:
+    fixtures step by step and as one 160-search call, circle/SAT and road/InterX, plus the 40-vehicle
+    reachable-set case (many predecessors' columns next to large own obstacle polylines)."""
+    from helpers import load_golden_timesteps
+    try:
+        planner.set_variant(variant)
+        for name in ("timestep_road_triple_speed", "timestep_circle_single_speed"):
+            mpa, steps = load_golden_timesteps(name)
+            planner.upload_mpa(mpa)
+            for batch, deps, exp in steps:
+                parity.compare(planner.plan_timestep(batch, deps, False), exp)
+            batch, deps, exp = concat_timesteps(steps)
+            parity.compare(planner.plan_timestep(batch, deps, False), exp)
+        mpa = get_mpa("triple_speed", non_convex=True)
+        planner.upload_mpa(mpa)
+        plan = lambda b: oracle_py.plan_batch(mpa, b)
+        runner = scenario.ScenarioRunner(scenario.commonroad_scenario(mpa, 40, seed=3, allow_shared_paths=True), None,
+                                         max_num_CLs=2, timestep_fn=lambda b, d: planner.plan_timestep(b, d, False))
+        for _ in range(4):
+            dev = runner.step_timestep()
+            _k, batch, deps, _ = runner.timestep_records[-1]
+            parity.compare(dev, scenario.plan_timestep_by_levels(plan, batch, deps))
+    finally:
+        planner.set_variant(0)
+
+
+def test_thousands_of_searches_in_one_call(planner):
+    """64 scenarios x 20 vehicles x 2 time steps = 2560 searches with their predecessor DAGs in ONE call
+    (auto shape: one warp per search), in forward and in shuffled index order."""
+    mpa = get_mpa("single_speed", non_convex=True)
+    planner.upload_mpa(mpa)
+    items = []
+    for seed in range(1, 65):
+        items.extend(collect_timesteps(mpa, scenario.commonroad_scenario(mpa, 20, seed=seed), 2))
+    batch, deps, ref = concat_timesteps(items)
+    assert batch.n == 2560
+    dev = planner.plan_timestep(batch, deps, False)
+    parity.compare(dev, ref)
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(batch.n)
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(batch.n)
+    rdeps = TimestepDeps.build([inv[deps.preds(int(i))] for i in perm], [deps.fallback_shapes(int(i)) for i in perm], batch.Hp)
+    rdev = planner.plan_timestep(batch.select(perm), rdeps, False)
+    rref = dataclasses.replace(ref, **{f.name: getattr(ref, f.name)[perm] for f in dataclasses.fields(ref)
+                                       if isinstance(getattr(ref, f.name), np.ndarray)})
+    parity.compare(rdev, rref)
 
 
 @pytest.mark.parametrize("name", ["timestep_road_triple_speed", "timestep_circle_single_speed"])
