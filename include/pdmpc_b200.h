@@ -286,7 +286,7 @@ typedef struct pdmpc_timestep_deps {
 /* Host buffers in, host buffers out (like pdmpc_plan_batch): one host->device copy, one launch,
  * one device->host copy for the whole DAG.  Every output equals what level-by-level calls of
  * pdmpc_plan_batch with host-side obstacle assembly return.  Launch shape: one CTA per search for up to
- * two searches per SM, one warp per search beyond that and for MPAs whose full search tree exceeds the
+ * 48 searches per SM, one warp per search beyond that and for MPAs whose full search tree exceeds the
  * 32768 nodes the CTA kernel holds (pdmpc_set_variant 1..3 / 4..5 force either; results do not depend on
  * it).  Errors: PDMPC_ERR_BAD_INPUT for a cyclic or out-of-range relation or too many predecessors. */
 int pdmpc_plan_timestep(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_timestep_deps *deps,

@@ -1202,7 +1202,7 @@ int pdmpc_plan_timestep(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_t
     if (!in || !deps || !deps->pred_ptr) return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep: NULL argument");
     const int n = in->n_searches, Hp = h->mpa.Hp;
     if (n < 0) return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep: n_searches < 0");
-    // launch shape: one CTA per search (lowest latency) for up to two searches per SM, else — and for search
+    // launch shape: one CTA per search (lowest latency) for up to 48 searches per SM, else — and for search
     // trees beyond what that kernel holds — one warp per search; pdmpc_set_variant 1..3 / 4..5 force either
     bool use_cta;
     {
@@ -1210,7 +1210,10 @@ int pdmpc_plan_timestep(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_t
         const bool cta_possible = h->cta_deps_ok && cap <= kCtaFlags;
         if (h->variant_mode >= 4) use_cta = cta_possible;
         else if (h->variant_mode >= 1) use_cta = false;
-        else use_cta = cta_possible && n <= 2 * h->num_sms;
+        // measured (profiles/r01h_closed_loop_sweep.txt): a time step is bound by its chains of dependent
+        // searches, so the 2.5x lower per-pop latency of the CTA shape beats the 12x higher concurrency of the
+        // warp shape up to several thousand searches per call
+        else use_cta = cta_possible && n <= 48 * h->num_sms;
         if (!use_cta && !h->lat_deps_ok)
             return fail(h, PDMPC_ERR_CUDA, "plan_timestep: search kernel is not launchable on this device");
     }

@@ -637,6 +637,14 @@ class ScenarioRunner:
         batch = SearchBatch.from_iters(iters, Hp, sc.checker, mpa.dt_seconds)
         deps = TimestepDeps.build(preds, [f[0] for f in fallbacks], Hp)
         res = self.timestep_fn(batch, deps)
+        self.apply_timestep(res, fallbacks)
+        self.timestep_records.append((self.k, batch, deps, res))
+        return res
+
+    def apply_timestep(self, res: BatchResult, fallbacks) -> None:
+        """Take the plans of one time step (row i = vehicle i): exhausted vehicles execute their fallback
+        plan, the plant applies the first step (plant/Simulation.m:93-98)."""
+        n = self.sc.amount
         shapes_now: List[Optional[List[np.ndarray]]] = [None] * n
         new_pose, new_trim = self.pose.copy(), self.trim.copy()
         for i in range(n):
@@ -651,8 +659,6 @@ class ScenarioRunner:
             new_trim[i] = self.prev_trims[i][0]
         self.prev_shapes = shapes_now
         self.pose, self.trim = new_pose, new_trim
-        self.timestep_records.append((self.k, batch, deps, res))
-        return res
 
     def step(self) -> List[StepRecord]:
         if self.timestep_fn is not None:
@@ -880,6 +886,28 @@ class ExplorativeRunner(ScenarioRunner):
                                          "solution_cost": solution_cost, "searches_local": len(mine) * n,
                                          "result_local": res})
         return []
+
+
+def lockstep_step(runners: Sequence[ScenarioRunner], timestep_fn) -> BatchResult:
+    """One time step of MANY independent scenarios as ONE optimizer call (BASELINE configs[4] in closed
+    loop): the scenarios' searches and predecessor DAGs are concatenated block by block."""
+    parts, sizes, fbs = [], [], []
+    for r in runners:
+        r.k += 1
+        iters, preds, fallbacks = r.timestep_inputs()
+        parts.append((SearchBatch.from_iters(iters, r.mpa.Hp, r.sc.checker, r.mpa.dt_seconds),
+                      TimestepDeps.build(preds, [f[0] for f in fallbacks], r.mpa.Hp)))
+        sizes.append(r.sc.amount)
+        fbs.append(fallbacks)
+    batch = SearchBatch.concat([b for b, _d in parts])
+    res = timestep_fn(batch, TimestepDeps.concat([d for _b, d in parts], sizes))
+    off = 0
+    for r, n, fallbacks in zip(runners, sizes, fbs):
+        rows = dataclasses.replace(res, **{f.name: getattr(res, f.name)[off:off + n] for f in dataclasses.fields(res)
+                                           if isinstance(getattr(res, f.name), np.ndarray)})
+        r.apply_timestep(rows, fallbacks)
+        off += n
+    return res
 
 
 def _assign_rows(dst: BatchResult, rows, src: BatchResult) -> None:

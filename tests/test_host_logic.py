@@ -269,3 +269,22 @@ def test_config4_reachable_sets_and_level_limit():
     _k, batch, deps, _res = r.timestep_records[-1]
     assert batch.n == 40 and np.diff(batch.poly_ptr).max() > 8       # reachable sets are many-vertex obstacles
     assert deps.pred_idx.size > 0
+
+
+def test_lockstep_scenarios_equal_individual_closed_loops():
+    """Many scenarios advanced together, one optimizer call per time step for all of them."""
+    mpa = get_mpa("single_speed", non_convex=True)
+    plan = lambda b: oracle_py.plan_batch(mpa, b)
+    ts = lambda b, d: scenario.plan_timestep_by_levels(plan, b, d)
+    seeds = (1, 2, 3)
+    alone = []
+    for sd in seeds:
+        r = scenario.ScenarioRunner(scenario.commonroad_scenario(mpa, 10, seed=sd), None, timestep_fn=ts)
+        r.run(5)
+        alone.append(r)
+    together = [scenario.ScenarioRunner(scenario.commonroad_scenario(mpa, 10, seed=sd), None, timestep_fn=ts) for sd in seeds]
+    for _ in range(5):
+        res = scenario.lockstep_step(together, ts)
+        assert res.status.size == 30
+    for a, b in zip(alone, together):
+        assert np.array_equal(a.pose, b.pose) and np.array_equal(a.trim, b.trim) and a.n_fallbacks == b.n_fallbacks

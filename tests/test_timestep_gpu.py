@@ -201,7 +201,7 @@ def test_both_launch_shapes_of_the_time_step(planner, variant):
 
 def test_thousands_of_searches_in_one_call(planner):
     """64 scenarios x 20 vehicles x 2 time steps = 2560 searches with their predecessor DAGs in ONE call
-    (auto shape: one warp per search), in forward and in shuffled index order."""
+    in forward and in shuffled index order, auto shape and both forced shapes."""
     mpa = get_mpa("single_speed", non_convex=True)
     planner.upload_mpa(mpa)
     items = []
@@ -211,6 +211,12 @@ def test_thousands_of_searches_in_one_call(planner):
     assert batch.n == 2560
     dev = planner.plan_timestep(batch, deps, False)
     parity.compare(dev, ref)
+    try:
+        for variant in (1, 4):
+            planner.set_variant(variant)
+            parity.compare(planner.plan_timestep(batch, deps, False), ref)
+    finally:
+        planner.set_variant(0)
     rng = np.random.default_rng(5)
     perm = rng.permutation(batch.n)
     inv = np.empty_like(perm)
