@@ -54,6 +54,8 @@ extern "C" {
 #define PDMPC_MAX_HP 16
 /* Upper bound on the number of trims (realistic MPA: 71). */
 #define PDMPC_MAX_TRIMS 128
+/* Most vehicles of one centralized (joint) search (pdmpc_joint_plan_batch). */
+#define PDMPC_MAX_JOINT 4
 
 enum pdmpc_status {
     PDMPC_OK = 0,
@@ -291,6 +293,22 @@ typedef struct pdmpc_timestep_deps {
  * it).  Errors: PDMPC_ERR_BAD_INPUT for a cyclic or out-of-range relation or too many predecessors. */
 int pdmpc_plan_timestep(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_timestep_deps *deps,
                         pdmpc_batch_out *out);
+
+/* ---- Centralized (joint) search: GraphSearch.do_graph_search with iter.amount = n_vehicles > 1, what
+ *      CentralizedController.controller calls (hlc/controller/centralized/CentralizedController.m:33-59):
+ *      successors = Cartesian product of the vehicles' successors, first vehicle fastest
+ *      (expand_node.m:15-26), costs summed over the vehicles in order (:43-75), every vehicle of a popped
+ *      node checked in order against the static and dynamic obstacles, the vehicles before it and its own
+ *      lanelet boundary (GraphSearch.m:150-192, are_constraints_satisfied_sat.m:15-53).  SAT checker only
+ *      (are_constraints_satisfied_interx.m:12 asserts a single vehicle).
+ *      Rows of `in` / `out` are (search, vehicle): r = search * n_vehicles + v, in->n_searches = number of
+ *      ROWS.  iter.obstacles / iter.dynamic_obstacle_area of a search go into the slots of its first row
+ *      (the other rows' slots must be empty); lanelet bounds, poses, trims, references are per row.  Per-row
+ *      outputs: trims, y_predicted, shapes; status, is_exhausted, n_expanded, n_pops, pop_hash, tree_path,
+ *      g_path and h_path (joint values) are repeated on every row of a search.  Node capacity per search: what
+ *      pdmpc_set_node_capacity says, else what 8 GiB of arena give every resident search (at least 2^17, at
+ *      most 2^28 - 1 nodes: branching is up to 12^n_vehicles per expansion); PDMPC_ERR_CAPACITY beyond it. ---- */
+int pdmpc_joint_plan_batch(pdmpc_handle *h, const pdmpc_batch_in *in, int32_t n_vehicles, pdmpc_batch_out *out);
 
 /* Diagnostics: the FP64 pipe peak of the handle's device, measured with register-only kernels
  * (no memory traffic): tera-operations/s of separate multiply + add (what the search executes: FMA

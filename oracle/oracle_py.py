@@ -70,6 +70,9 @@ def lib() -> C.CDLL:
         L.oracle_plan_batch.argtypes = [C.POINTER(capi.MpaDesc), C.POINTER(capi.BatchIn),
                                         C.POINTER(capi.BatchOut), C.c_int]
         L.oracle_plan_batch.restype = C.c_int
+        L.oracle_joint_plan_batch.argtypes = [C.POINTER(capi.MpaDesc), C.POINTER(capi.BatchIn), C.c_int,
+                                              C.POINTER(capi.BatchOut), C.c_int64]
+        L.oracle_joint_plan_batch.restype = C.c_int
         L.oracle_plan_trace.argtypes = [C.POINTER(capi.MpaDesc), C.POINTER(capi.BatchIn), C.c_int,
                                         _p_i64, C.c_int64, _p_i64]
         L.oracle_plan_trace.restype = C.c_int
@@ -202,6 +205,18 @@ def plan_batch(mpa, batch: SearchBatch, n_threads: int = 1, hash_valid_pops_only
         lib().oracle_set_hash_valid_pops_only(0)
     if rc != 0:
         raise RuntimeError(f"oracle_plan_batch failed: {rc}")
+    del keep
+    return r
+
+
+def joint_plan_batch(mpa, batch: SearchBatch, n_vehicles: int, max_nodes: int = 1 << 21) -> BatchResult:
+    """Centralized (joint) search: rows of the batch = searches x n_vehicles (oracle_joint_plan_batch)."""
+    d, keep = capi.mpa_desc(mpa)
+    r = BatchResult.empty(batch.n, batch.Hp)
+    bi, bo = capi.batch_in(batch), capi.batch_out(r)
+    rc = lib().oracle_joint_plan_batch(C.byref(d), C.byref(bi), int(n_vehicles), C.byref(bo), int(max_nodes))
+    if rc != 0:
+        raise RuntimeError(f"oracle_joint_plan_batch failed: {rc}")
     del keep
     return r
 

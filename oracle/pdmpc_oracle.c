@@ -553,6 +553,207 @@ static int search_one(const pdmpc_mpa_desc *mpa, const pdmpc_batch_in *in, pdmpc
     return 0;
 }
 
+/* ------------------------------------------------------------------------- */
+/* Centralized (joint) search: the same GraphSearch.do_graph_search with iter.amount = nV > 1
+ * (CentralizedController.m:33-59).  Rows of the batch: r = search * nV + vehicle; the obstacle slots of a
+ * search are those of its vehicle-0 row.  expand_node.m:15-26 (Cartesian product of the vehicles'
+ * successors, first vehicle fastest: cartprod), :43-75 (costs summed over the vehicles in order),
+ * GraphSearch.m:150-192 (vehicles checked in order, first failure ends the edge check),
+ * are_constraints_satisfied_sat.m:15-53 (static, dynamic, vehicles i < iVeh, own lanelet boundary). */
+typedef struct {
+    double *x, *y, *yaw, *g, *h;   /* x, y, yaw: [node * nV + v] */
+    int32_t *trim, *k, *parent;    /* trim: [node * nV + v] */
+    int64_t size, cap;
+} jtree_t;
+
+static void jtree_reserve(jtree_t *t, int64_t need, int nV) {
+    if (need + 1 <= t->cap) return;
+    int64_t cap = t->cap ? t->cap : 4096;
+    while (cap < need + 1) cap *= 2;
+    t->x = (double *)realloc(t->x, (size_t)cap * nV * sizeof(double));
+    t->y = (double *)realloc(t->y, (size_t)cap * nV * sizeof(double));
+    t->yaw = (double *)realloc(t->yaw, (size_t)cap * nV * sizeof(double));
+    t->trim = (int32_t *)realloc(t->trim, (size_t)cap * nV * sizeof(int32_t));
+    t->g = (double *)realloc(t->g, (size_t)cap * sizeof(double));
+    t->h = (double *)realloc(t->h, (size_t)cap * sizeof(double));
+    t->k = (int32_t *)realloc(t->k, (size_t)cap * sizeof(int32_t));
+    t->parent = (int32_t *)realloc(t->parent, (size_t)cap * sizeof(int32_t));
+    t->cap = cap;
+}
+
+static int joint_search_one(const pdmpc_mpa_desc *mpa, const pdmpc_batch_in *in, pdmpc_batch_out *out,
+                            int s, int nV, const int32_t *edge_of, int64_t max_nodes) {
+    const int Hp = mpa->Hp, nT = mpa->n_trims;
+    const int r0 = s * nV;
+    jtree_t tt;
+    memset(&tt, 0, sizeof(tt));
+    jtree_t *t = &tt;
+    oracle_pq pq;
+    memset(&pq, 0, sizeof(pq));
+    jtree_reserve(t, 1, nV);
+    t->size = 1;
+    for (int v = 0; v < nV; ++v) {   /* GraphSearch.m:34-41 */
+        t->x[1 * nV + v] = in->x0[r0 + v];
+        t->y[1 * nV + v] = in->y0[r0 + v];
+        t->yaw[1 * nV + v] = in->yaw0[r0 + v];
+        t->trim[1 * nV + v] = in->trim0[r0 + v];
+    }
+    t->k[1] = 0; t->g[1] = 0; t->h[1] = 0; t->parent[1] = 0;
+    oracle_pq_push(&pq, 1, 0.0);
+    int64_t n_pops = 0;
+    uint64_t hash = 0xcbf29ce484222325ULL;
+    int exhausted = 0, status = PDMPC_OK;
+    int64_t goal = 0;
+    const int32_t *slot = in->slot_ptr + (size_t)r0 * (Hp + 1);
+    double sx[PDMPC_MAX_JOINT][PDMPC_AREA_STRIDE], sy[PDMPC_MAX_JOINT][PDMPC_AREA_STRIDE];
+    int nsv[PDMPC_MAX_JOINT];
+
+    for (;;) {
+        int64_t id = oracle_pq_pop(&pq, NULL);
+        if (id == -1) { exhausted = 1; break; }
+        ++n_pops;
+        hash = fnv1a_u32(hash, (uint32_t)id);
+        int is_valid = 1;
+        int32_t par = t->parent[id];
+        if (par) {
+            int cK = t->k[id];
+            for (int v = 0; v < nV && is_valid; ++v) {   /* GraphSearch.m:150-192 */
+                double pX = t->x[par * nV + v], pY = t->y[par * nV + v], pYaw = t->yaw[par * nV + v];
+                int edge = edge_of[(t->trim[par * nV + v] - 1) * nT + (t->trim[id * nV + v] - 1)];
+                double c, sn;
+                oracle_sincos(pYaw, &sn, &c);
+                double bx[PDMPC_AREA_STRIDE], by[PDMPC_AREA_STRIDE];
+                int nb;
+                place_area(mpa, edge, PDMPC_AREA_NORMAL, c, sn, pX, pY, sx[v], sy[v], &nsv[v]);
+                place_area(mpa, edge, cK == Hp ? PDMPC_AREA_LARGE_OFFSET : PDMPC_AREA_WITHOUT_OFFSET, c, sn, pX, pY,
+                           bx, by, &nb);
+                /* are_constraints_satisfied_sat.m:15-35 */
+                for (int pass = 0; pass < 2 && is_valid; ++pass) {
+                    int q = pass == 0 ? 0 : cK;
+                    for (int p = slot[q]; p < slot[q + 1]; ++p) {
+                        int v0 = in->poly_ptr[p], v1 = in->poly_ptr[p + 1];
+                        if (oracle_intersect_sat(sx[v], sy[v], nsv[v], in->vert_x + v0, in->vert_y + v0, v1 - v0)) {
+                            is_valid = 0;
+                            break;
+                        }
+                    }
+                }
+                /* :37-44 vehicles of the same node with a lower index */
+                for (int u = v - 1; u >= 0 && is_valid; --u)
+                    if (oracle_intersect_sat(sx[u], sy[u], nsv[u], sx[v], sy[v], nsv[v])) is_valid = 0;
+                /* :46-53 own lanelet boundary */
+                if (is_valid) {
+                    int r = r0 + v;
+                    int l0 = in->lane_ptr[2 * r], l1 = in->lane_ptr[2 * r + 1], l2 = in->lane_ptr[2 * r + 2];
+                    if (oracle_intersect_lanelet_boundary(bx, by, nb, in->lane_x + l0, in->lane_y + l0, l1 - l0,
+                                                          in->lane_x + l1, in->lane_y + l1, l2 - l1))
+                        is_valid = 0;
+                }
+            }
+        }
+        if (!is_valid) continue;
+        if (t->k[id] == Hp) { goal = id; break; }
+
+        /* expand_node.m */
+        int k_exp = t->k[id] + 1;
+        int succ[PDMPC_MAX_JOINT][PDMPC_MAX_TRIMS], nsucc[PDMPC_MAX_JOINT];
+        int64_t total = 1;
+        for (int v = 0; v < nV; ++v) {   /* :17-26 */
+            const uint8_t *row = mpa->transition + ((size_t)(k_exp - 1) * nT + (t->trim[id * nV + v] - 1)) * nT;
+            nsucc[v] = 0;
+            for (int j = 0; j < nT; ++j)
+                if (row[j]) succ[v][nsucc[v]++] = j + 1;
+            total *= nsucc[v];
+        }
+        if (t->size + total >= max_nodes) { status = PDMPC_ERR_CAPACITY; exhausted = 1; break; }
+        int time_steps_to_go = Hp - k_exp;
+        jtree_reserve(t, t->size + total, nV);
+        double cs[PDMPC_MAX_JOINT], sn[PDMPC_MAX_JOINT];
+        for (int v = 0; v < nV; ++v) oracle_sincos(t->yaw[id * nV + v], &sn[v], &cs[v]);   /* :50-51 */
+        int64_t first_new = t->size + 1;
+        for (int64_t ci = 0; ci < total; ++ci) {   /* cartprod: first vehicle fastest */
+            int64_t nid = ++t->size, rem = ci;
+            double eg = t->g[id], eh = 0;
+            for (int v = 0; v < nV; ++v) {
+                int t2 = succ[v][rem % nsucc[v]];
+                rem /= nsucc[v];
+                int r = r0 + v;
+                const double *rx = in->ref_x + (size_t)r * Hp, *ry = in->ref_y + (size_t)r * Hp;
+                const double *vr = in->v_ref + (size_t)r * Hp;
+                int edge = edge_of[(t->trim[id * nV + v] - 1) * nT + (t2 - 1)];
+                double dx = mpa->edge_dx[edge], dy = mpa->edge_dy[edge], dyaw = mpa->edge_dyaw[edge];
+                double cX = t->x[id * nV + v], cY = t->y[id * nV + v], cYaw = t->yaw[id * nV + v];
+                double ex = cs[v] * dx - sn[v] * dy + cX;
+                double ey = sn[v] * dx + cs[v] * dy + cY;
+                double ddx = ex - rx[k_exp - 1], ddy = ey - ry[k_exp - 1];
+                double nrm = sqrt(ddx * ddx + ddy * ddy);
+                eg = eg + nrm * nrm;   /* :61 */
+                double d_traveled_max = 0;
+                for (int it = 1; it <= time_steps_to_go; ++it) {   /* :66-73 */
+                    d_traveled_max = d_traveled_max + in->dt_seconds * vr[k_exp + it - 1];
+                    double hx = ex - rx[k_exp + it - 1], hy = ey - ry[k_exp + it - 1];
+                    double m = fmax(0.0, sqrt(hx * hx + hy * hy) - d_traveled_max);
+                    eh = eh + m * m;
+                }
+                t->x[nid * nV + v] = ex; t->y[nid * nV + v] = ey; t->yaw[nid * nV + v] = cYaw + dyaw;
+                t->trim[nid * nV + v] = t2;
+            }
+            t->k[nid] = k_exp; t->g[nid] = eg; t->h[nid] = eh; t->parent[nid] = (int32_t)id;
+        }
+        for (int64_t nid = first_new; nid <= t->size; ++nid) oracle_pq_push(&pq, nid, t->g[nid] * 1 + t->h[nid] * 1);
+    }
+
+    int64_t path[PDMPC_MAX_HP + 1];
+    if (!exhausted) {
+        int64_t n = goal;
+        for (int d = Hp; d >= 0; --d) { path[d] = n; n = t->parent[n]; }
+    }
+    for (int v = 0; v < nV; ++v) {
+        int r = r0 + v;
+        if (out->status) out->status[r] = status;
+        if (out->is_exhausted) out->is_exhausted[r] = (uint8_t)exhausted;
+        if (out->n_expanded) out->n_expanded[r] = (int32_t)t->size;
+        if (out->n_pops) out->n_pops[r] = (int32_t)n_pops;
+        if (out->pop_hash) out->pop_hash[r] = hash;
+        for (int d = 0; d <= Hp; ++d) {
+            size_t o = (size_t)r * (Hp + 1) + d;
+            if (out->trims) out->trims[o] = exhausted ? (d == 0 ? in->trim0[r] : 0) : t->trim[path[d] * nV + v];
+            if (out->tree_path) out->tree_path[o] = exhausted ? 0 : (int32_t)path[d];
+            if (out->g_path) out->g_path[o] = exhausted ? NAN : t->g[path[d]];
+            if (out->h_path) out->h_path[o] = exhausted ? NAN : t->h[path[d]];
+        }
+        for (int d = 1; d <= Hp; ++d) {
+            size_t o = (size_t)r * Hp + (d - 1);
+            if (out->y_predicted) {
+                out->y_predicted[o * 3 + 0] = exhausted ? NAN : t->x[path[d] * nV + v];
+                out->y_predicted[o * 3 + 1] = exhausted ? NAN : t->y[path[d] * nV + v];
+                out->y_predicted[o * 3 + 2] = exhausted ? NAN : t->yaw[path[d] * nV + v];
+            }
+            if (out->shape_npts) {
+                double px[PDMPC_AREA_STRIDE], py[PDMPC_AREA_STRIDE];
+                int ns = 0;
+                for (int i = 0; i < PDMPC_AREA_STRIDE; ++i) px[i] = py[i] = 0.0;
+                if (!exhausted) {
+                    int64_t pa = path[d - 1], ch = path[d];
+                    int edge = edge_of[(t->trim[pa * nV + v] - 1) * nT + (t->trim[ch * nV + v] - 1)];
+                    double c, sn2;
+                    oracle_sincos(t->yaw[pa * nV + v], &sn2, &c);
+                    place_area(mpa, edge, PDMPC_AREA_NORMAL, c, sn2, t->x[pa * nV + v], t->y[pa * nV + v], px, py, &ns);
+                }
+                out->shape_npts[o] = ns;
+                if (out->shape_x && out->shape_y)
+                    for (int i = 0; i < PDMPC_AREA_STRIDE; ++i) {
+                        out->shape_x[o * PDMPC_AREA_STRIDE + i] = px[i];
+                        out->shape_y[o * PDMPC_AREA_STRIDE + i] = py[i];
+                    }
+            }
+        }
+    }
+    free(t->x); free(t->y); free(t->yaw); free(t->trim); free(t->g); free(t->h); free(t->k); free(t->parent);
+    free(pq.a);
+    return 0;
+}
+
 static int32_t *build_edge_of(const pdmpc_mpa_desc *mpa) {
     int nT = mpa->n_trims;
     int32_t *e = (int32_t *)malloc((size_t)nT * nT * sizeof(int32_t));
@@ -956,6 +1157,18 @@ int oracle_mcts_plan_batch(const pdmpc_mpa_desc *mpa, const pdmpc_batch_in *in, 
     }
     free(jobs);
     free(th);
+    free(edge_of);
+    return PDMPC_OK;
+}
+
+
+/* Joint searches of the batch, one after the other (rows = searches x n_vehicles). */
+int oracle_joint_plan_batch(const pdmpc_mpa_desc *mpa, const pdmpc_batch_in *in, int n_vehicles,
+                            pdmpc_batch_out *out, int64_t max_nodes) {
+    if (n_vehicles < 1 || n_vehicles > PDMPC_MAX_JOINT || in->n_searches % n_vehicles) return PDMPC_ERR_BAD_INPUT;
+    int32_t *edge_of = build_edge_of(mpa);
+    for (int s = 0; s < in->n_searches / n_vehicles; ++s)
+        joint_search_one(mpa, in, out, s, n_vehicles, edge_of, max_nodes);
     free(edge_of);
     return PDMPC_OK;
 }

@@ -69,6 +69,12 @@ int oracle_plan_trace(const pdmpc_mpa_desc *mpa, const pdmpc_batch_in *in,
                       int trace_search, int64_t *pop_trace, int64_t trace_cap,
                       int64_t *n_trace);
 
+/* Centralized (joint) search, iter.amount = n_vehicles > 1: rows of the batch are searches x vehicles, the
+ * obstacle slots of a search are those of its first row; SAT checker (CentralizedController.m:33-59,
+ * expand_node.m:15-75, are_constraints_satisfied_sat.m:15-53).  max_nodes: node capacity as on the device. */
+int oracle_joint_plan_batch(const pdmpc_mpa_desc *mpa, const pdmpc_batch_in *in, int n_vehicles,
+                            pdmpc_batch_out *out, int64_t max_nodes);
+
 /* pop_hash over the popped nodes that passed their edge check only (CUDA launch shape 5); default off */
 void oracle_set_hash_valid_pops_only(int on);
 

@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = (
     "pdmpc_trace_staged", "pdmpc_upload_mpa", "pdmpc_plan_batch", "pdmpc_stage_batch",
     "pdmpc_run_staged", "pdmpc_sync", "pdmpc_fetch_staged", "pdmpc_get_stats", "pdmpc_stream",
     "pdmpc_mcts_plan_batch", "pdmpc_mcts_run_staged", "pdmpc_set_cta_heap_smem", "pdmpc_plan_timestep",
-    "pdmpc_set_pipeline_chunks", "pdmpc_measure_fp64_peak",
+    "pdmpc_set_pipeline_chunks", "pdmpc_measure_fp64_peak", "pdmpc_joint_plan_batch",
 )
 
 _p_u8 = C.POINTER(C.c_uint8)
@@ -173,6 +173,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.pdmpc_set_variant.restype = C.c_int
     lib.pdmpc_set_cta_heap_smem.argtypes = [H, C.c_int32]
     lib.pdmpc_set_cta_heap_smem.restype = C.c_int
+    lib.pdmpc_joint_plan_batch.argtypes = [H, C.POINTER(BatchIn), C.c_int32, C.POINTER(BatchOut)]
+    lib.pdmpc_joint_plan_batch.restype = C.c_int
     lib.pdmpc_measure_fp64_peak.argtypes = [H, _p_f64, _p_f64]
     lib.pdmpc_measure_fp64_peak.restype = C.c_int
     lib.pdmpc_set_pipeline_chunks.argtypes = [H, C.c_int32]
@@ -307,6 +309,16 @@ class Planner:
         if raise_on_search_error and b.n and int(r.status.max()) != PDMPC_OK:
             bad = int(np.flatnonzero(r.status != PDMPC_OK)[0])
             raise PdmpcError(int(r.status[bad]), f"search {bad} failed")
+        return r
+
+    def joint_plan_batch(self, b: SearchBatch, n_vehicles: int, raise_on_search_error: bool = True) -> BatchResult:
+        """Centralized (joint) searches: rows of `b` are searches x n_vehicles (pdmpc_joint_plan_batch)."""
+        r = BatchResult.empty(b.n, b.Hp)
+        bi, bo = batch_in(b), batch_out(r)
+        self._check(self.lib.pdmpc_joint_plan_batch(self.h, C.byref(bi), int(n_vehicles), C.byref(bo)))
+        if raise_on_search_error and b.n and int(r.status.max()) != PDMPC_OK:
+            bad = int(np.flatnonzero(r.status != PDMPC_OK)[0])
+            raise PdmpcError(int(r.status[bad]), f"row {bad} failed")
         return r
 
     def mcts_plan_batch(self, b: SearchBatch, seeds, n_expansions_max: int = 250,

@@ -18,6 +18,7 @@
 #include "pdmpc_lanes.cuh"
 #include "pdmpc_mcts.cuh"
 #include "pdmpc_cta.cuh"
+#include "pdmpc_joint.cuh"
 
 using namespace pdmpc;
 
@@ -88,6 +89,7 @@ struct pdmpc_handle {
     bool cta_ok = false;              // the CTA-per-search kernel is launchable (shared memory opt-in granted)
     bool cta_deps_ok = false;         // ... and its pdmpc_plan_timestep instance
     // pdmpc_plan_timestep: dependency CSR, fallback areas, done flags (one packed upload)
+    DBuf j_veh, j_node, j_heap;       // centralized (joint) search arena
     DBuf d_deps, d_done, d_depx, d_depy, d_depn;
     bool lat_deps_ok = false;
     void *pin_deps = nullptr;
@@ -264,6 +266,9 @@ int pdmpc_destroy(pdmpc_handle *h) {
     h->d_out_pack.release();
     h->d_deps.release();
     h->d_done.release();
+    h->j_veh.release();
+    h->j_node.release();
+    h->j_heap.release();
     h->d_depx.release();
     h->d_depy.release();
     h->d_depn.release();
@@ -1326,6 +1331,53 @@ int pdmpc_plan_timestep(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_t
     h->stats.lanes_ms = 0.0;
     h->stats.handed_over = 0;
     h->stats.kernel_launches++;
+    return pdmpc_fetch_staged(h, out);
+}
+
+// Centralized (joint) search: rows = searches x n_vehicles (pdmpc_joint.cuh).
+int pdmpc_joint_plan_batch(pdmpc_handle *h, const pdmpc_batch_in *in, int32_t n_vehicles, pdmpc_batch_out *out) {
+    if (!h) return PDMPC_ERR_BAD_INPUT;
+    if (!h->has_mpa) return fail(h, PDMPC_ERR_NO_MPA, "joint: call pdmpc_upload_mpa first");
+    if (!in) return fail(h, PDMPC_ERR_BAD_INPUT, "joint: batch is NULL");
+    if (n_vehicles < 1 || n_vehicles > PDMPC_MAX_JOINT)
+        return fail(h, PDMPC_ERR_BAD_INPUT, "joint: n_vehicles must be 1..PDMPC_MAX_JOINT");
+    if (in->n_searches < 0 || in->n_searches % n_vehicles)
+        return fail(h, PDMPC_ERR_BAD_INPUT, "joint: the number of rows must be a multiple of n_vehicles");
+    if (in->checker != PDMPC_CHECKER_SAT)   // are_constraints_satisfied_interx.m:12 asserts iter.amount == 1
+        return fail(h, PDMPC_ERR_BAD_INPUT, "joint: the InterX checker is defined for single-vehicle searches only");
+    const int Hp = h->mpa.Hp, n = in->n_searches, nj = n / n_vehicles;
+    int rc = pdmpc_stage_batch(h, in);
+    if (rc != PDMPC_OK) return rc;
+    for (int r = 0; r < n; ++r)   // obstacles belong to the search: they sit in the slots of its first row
+        if (r % n_vehicles && in->slot_ptr[(size_t)(r + 1) * (Hp + 1)] != in->slot_ptr[(size_t)r * (Hp + 1)]) {
+            h->staged = false;
+            return fail(h, PDMPC_ERR_BAD_INPUT, "joint: obstacle slots of rows other than a search's first row must be empty");
+        }
+    CU_TRY(h, cudaMemsetAsync(h->out.counters, 0, 16 * sizeof(unsigned long long), h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->work_counter.p, 0, sizeof(unsigned), h->stream));
+    h->stats.kernel_launches = 0;
+    if (nj > 0) {
+        const int grid = std::min(nj, h->num_sms * 4);
+        // default capacity: what 8 GiB of arena give every resident search, at least 2^17 nodes (ids have 21 bits)
+        const double per_node = (double)n_vehicles * sizeof(JVeh) + sizeof(JNode) + sizeof(HEnt);
+        int cap = h->user_node_cap ? h->user_node_cap
+                                   : (int)std::min<double>(kJointMaxCap, std::max<double>(1 << 17, 8.0 * (1 << 30) / (grid * per_node)));
+        cap = std::min(cap, kJointMaxCap);
+        const size_t tot = (size_t)grid * cap;
+        CU_TRY(h, h->j_veh.reserve(tot * n_vehicles * sizeof(JVeh)));
+        CU_TRY(h, h->j_node.reserve(tot * sizeof(JNode)));
+        CU_TRY(h, h->j_heap.reserve(tot * sizeof(HEnt)));
+        JointArena ar;
+        ar.veh = h->j_veh.as<JVeh>(); ar.node = h->j_node.as<JNode>(); ar.heap = h->j_heap.as<HEnt>();
+        ar.cap = cap; ar.nV = n_vehicles;
+        CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
+        joint_search_kernel<<<grid, kWarp, 0, h->stream>>>(h->mpa, h->batch, h->out, ar, h->work_counter.as<unsigned>());
+        CU_TRY(h, cudaGetLastError());
+        CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
+        h->timing_pending_kernel = true;
+        h->timing_pending_lanes = false;
+        h->stats.kernel_launches = 1;
+    }
     return pdmpc_fetch_staged(h, out);
 }
 

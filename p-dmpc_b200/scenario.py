@@ -910,6 +910,29 @@ def lockstep_step(runners: Sequence[ScenarioRunner], timestep_fn) -> BatchResult
     return res
 
 
+class CentralizedRunner(ScenarioRunner):
+    """CentralizedController (hlc/controller/centralized/CentralizedController.m:33-59): ONE joint search over all
+    vehicles per time step (rows of the batch = vehicles), SAT checker, no priorities.  joint_fn(batch, n_vehicles)
+    plans it; an exhausted search makes every vehicle take its fallback plan (:46-54)."""
+
+    def __init__(self, sc: Scenario, joint_fn):
+        super().__init__(sc, None)
+        self.joint_fn = joint_fn
+        self.joint_records: List[tuple] = []
+
+    def step(self):
+        sc, mpa = self.sc, self.mpa
+        n = sc.amount
+        self.k += 1
+        iters = [self._iter_for(i) for i in range(n)]
+        fallbacks = [self._fallback_plan(i) for i in range(n)]
+        batch = SearchBatch.from_iters(iters, mpa.Hp, CHECKER_SAT, mpa.dt_seconds)
+        res = self.joint_fn(batch, n)
+        self.apply_timestep(res, fallbacks)
+        self.joint_records.append((self.k, batch, res))
+        return []
+
+
 def _assign_rows(dst: BatchResult, rows, src: BatchResult) -> None:
     for f in dataclasses.fields(dst):
         a = getattr(dst, f.name)
