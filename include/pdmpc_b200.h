@@ -306,7 +306,7 @@ int pdmpc_plan_timestep(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_t
  *      (the other rows' slots must be empty); lanelet bounds, poses, trims, references are per row.  Per-row
  *      outputs: trims, y_predicted, shapes; status, is_exhausted, n_expanded, n_pops, pop_hash, tree_path,
  *      g_path and h_path (joint values) are repeated on every row of a search.  Node capacity per search: what
- *      pdmpc_set_node_capacity says, else what 8 GiB of arena give every resident search (at least 2^17, at
+ *      pdmpc_set_node_capacity says, else what 2 GiB of arena give every resident search (at least 2^17, at
  *      most 2^28 - 1 nodes: branching is up to 12^n_vehicles per expansion); PDMPC_ERR_CAPACITY beyond it. ---- */
 int pdmpc_joint_plan_batch(pdmpc_handle *h, const pdmpc_batch_in *in, int32_t n_vehicles, pdmpc_batch_out *out);
 

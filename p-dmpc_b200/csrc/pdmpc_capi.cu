@@ -1358,10 +1358,10 @@ int pdmpc_joint_plan_batch(pdmpc_handle *h, const pdmpc_batch_in *in, int32_t n_
     h->stats.kernel_launches = 0;
     if (nj > 0) {
         const int grid = std::min(nj, h->num_sms * 4);
-        // default capacity: what 8 GiB of arena give every resident search, at least 2^17 nodes (ids have 21 bits)
+        // default capacity: what 2 GiB of arena give every resident search, at least 2^17 nodes
         const double per_node = (double)n_vehicles * sizeof(JVeh) + sizeof(JNode) + sizeof(HEnt);
         int cap = h->user_node_cap ? h->user_node_cap
-                                   : (int)std::min<double>(kJointMaxCap, std::max<double>(1 << 17, 8.0 * (1 << 30) / (grid * per_node)));
+                                   : (int)std::min<double>(kJointMaxCap, std::max<double>(1 << 17, 2.0 * (1 << 30) / (grid * per_node)));
         cap = std::min(cap, kJointMaxCap);
         const size_t tot = (size_t)grid * cap;
         CU_TRY(h, h->j_veh.reserve(tot * n_vehicles * sizeof(JVeh)));

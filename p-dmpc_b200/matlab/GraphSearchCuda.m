@@ -17,6 +17,7 @@ classdef GraphSearchCuda < OptimizerInterface
         UPLOAD_MPA = 2;
         PLAN = 3;
         STATS = 4;
+        PLAN_JOINT = 7;
     end
 
     properties (SetAccess = private, Hidden = true)
@@ -50,8 +51,13 @@ classdef GraphSearchCuda < OptimizerInterface
         end
 
         function info = run_optimizer(obj, ~, iter, mpa, options, ~)
-            assert(iter.amount == 1, 'GraphSearchCuda plans one vehicle per call (prioritized controllers)');
             obj.upload_mpa_once(mpa, options);
+
+            if iter.amount > 1
+                % CentralizedController.controller (CentralizedController.m:33-59): one joint search
+                info = obj.run_joint(iter, options);
+                return
+            end
 
             % iter.predicted_lanelet_boundary{1, 1:2}: left / right bound, 2 x n (may be empty)
             left = zeros(2, 0); right = zeros(2, 0);
@@ -91,6 +97,50 @@ classdef GraphSearchCuda < OptimizerInterface
                 info, iter, options, next_nodes, trims, y_full);
             info.shapes = shapes; % 1 x Hp cell of 2 x n (return_path_area.m:5-7)
             info.needs_fallback = false; % GraphSearch.m:88
+        end
+
+        function info = run_joint(obj, iter, options)
+            % iter.amount = nV > 1: expand_node.m:15-75, are_constraints_satisfied_sat.m:15-53 on the GPU
+            nV = iter.amount; Hp = options.Hp;
+            assert(obj.checker == 0, 'joint searches use the SAT checker (are_constraints_satisfied_interx.m:12)');
+            obstacles = cell(nV, max(1, numel(iter.obstacles)));
+            obstacles(1, 1:numel(iter.obstacles)) = iter.obstacles(:)'; % obstacles of the search: row 1
+            R = size(iter.dynamic_obstacle_area, 1);
+            dyn = cell(nV, max(1, R) * Hp);
+
+            for k = 1:Hp
+                dyn(1, (1:R) + max(1, R) * (k - 1)) = iter.dynamic_obstacle_area(:, k)';
+            end
+
+            [is_exhausted, n_expanded, trims, y, shapes, g_path, h_path] = pdmpc_b200_mex( ...
+                GraphSearchCuda.PLAN_JOINT, obj.handle, iter.x0(:, 1:3), iter.trim_indices(:), ...
+                iter.reference_trajectory_points, iter.v_ref, obstacles, dyn, ...
+                iter.predicted_lanelet_boundary(:, 1), iter.predicted_lanelet_boundary(:, 2), 0, options.dt_seconds);
+            y = reshape(y, 3, Hp, nV);
+            info = ControlResultsInfo(nV, Hp);
+            info.is_exhausted = logical(is_exhausted(1));
+            info.n_expanded = n_expanded(1);
+
+            if info.is_exhausted
+                info.tree = OptimizerInterface.create_tree(iter);
+                return
+            end
+
+            next_nodes = cell(1, Hp);
+            y_full = cell(nV, 1);
+
+            for k = 1:Hp % nV x 8 rows in NodeInfo order; g and h are the joint values (Tree.m: one g, h per node)
+                next_nodes{k} = [squeeze(y(1, k, :)), squeeze(y(2, k, :)), squeeze(y(3, k, :)), trims(:, k + 1), ...
+                                     repmat([g_path(k + 1), h_path(k + 1), k, 1], nV, 1)];
+            end
+
+            for v = 1:nV
+                y_full{v} = [y(:, :, v)', trims(v, 2:end)'];
+            end
+
+            info = OptimizerInterface.create_control_results_info_from_mex(info, iter, options, next_nodes, trims, y_full);
+            info.shapes = shapes; % nV x Hp cell
+            info.needs_fallback = false;
         end
 
         function s = stats(obj)

@@ -24,6 +24,11 @@
 //       PrioritizedSequentialController.controller (PrioritizedSequentialController.m:74-92); vehicle i
 //       waits on the device for the vehicles j with directed_coupling_sequential(j, i) ~= 0 and takes
 //       their planned areas as dynamic obstacles (PrioritizedController.m:449-506); empty cells are skipped.
+//   [is_exhausted, n_expanded, trims (nV x Hp+1), y_pred (3 x Hp*nV), shapes {nV x Hp}, g_path (1 x Hp+1), h_path] =
+//       mex(PLAN_JOINT, h, x0 [nV x 3], trims [nV x 1], ref [nV x Hp x 2], v_ref [nV x Hp], obstacles {nV x S},
+//           dynamic_obstacle_area {nV x R*Hp}, left {nV x 1}, right {nV x 1}, checker (0 = SAT), dt)
+//       ONE centralized search over nV vehicles (CentralizedController.m:33-59, GraphSearchCuda.run_optimizer with
+//       iter.amount > 1): iter.obstacles / iter.dynamic_obstacle_area go into ROW 1 of the two cell arrays.
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -34,7 +39,7 @@
 
 namespace {
 
-enum Command { CREATE = 0, DESTROY = 1, UPLOAD_MPA = 2, PLAN = 3, STATS = 4, PLAN_SAMPLED = 5, PLAN_TIMESTEP = 6 };
+enum Command { CREATE = 0, DESTROY = 1, UPLOAD_MPA = 2, PLAN = 3, STATS = 4, PLAN_SAMPLED = 5, PLAN_TIMESTEP = 6, PLAN_JOINT = 7 };
 
 std::vector<pdmpc_handle *> g_handles;   // released at `clear mex` (HighLevelController.m:284-303)
 bool g_at_exit_registered = false;
@@ -258,19 +263,22 @@ void plan(pdmpc_handle *h, int nlhs, mxArray *plhs[], const mxArray *prhs[], boo
     }
 }
 
-// PLAN_TIMESTEP: N vehicles, one pdmpc_plan_timestep call.
-void plan_timestep(pdmpc_handle *h, int nlhs, mxArray *plhs[], const mxArray *prhs[]) {
+// PLAN_TIMESTEP: N vehicles, one pdmpc_plan_timestep call.  PLAN_JOINT (joint == true): the same N rows as ONE
+// centralized search (pdmpc_joint_plan_batch), no coupling / fallback arguments.
+void plan_timestep(pdmpc_handle *h, int nlhs, mxArray *plhs[], const mxArray *prhs[], bool joint) {
     const mxArray *x0 = prhs[2], *trim = prhs[3], *ref = prhs[4], *vref = prhs[5], *obst = prhs[6], *dyn = prhs[7];
-    const mxArray *left = prhs[8], *right = prhs[9], *coupling = prhs[12], *fallback = prhs[13];
+    const mxArray *left = prhs[8], *right = prhs[9], *coupling = joint ? nullptr : prhs[12];
+    const mxArray *fallback = joint ? nullptr : prhs[13];
     const size_t N = mxGetM(x0);
     if (N == 0 || mxGetN(x0) < 3) fail("pdmpc:input", "x0 must be N x 3");
     if (mxGetM(vref) != N) fail("pdmpc:input", "v_ref must be N x Hp");
     const int Hp = static_cast<int>(mxGetN(vref));
     if (mxGetNumberOfElements(ref) != N * Hp * 2 || mxGetNumberOfElements(trim) != N)
         fail("pdmpc:input", "ref must be N x Hp x 2 and trims N x 1");
-    if (mxGetM(coupling) != N || mxGetN(coupling) != N) fail("pdmpc:input", "directed_coupling_sequential must be N x N");
+    if (!joint && (mxGetM(coupling) != N || mxGetN(coupling) != N))
+        fail("pdmpc:input", "directed_coupling_sequential must be N x N");
     const double *px0 = mxGetDoubles(x0), *pref = mxGetDoubles(ref), *pv = mxGetDoubles(vref), *ptrim = mxGetDoubles(trim);
-    const double *pc = mxGetDoubles(coupling);
+    const double *pc = joint ? nullptr : mxGetDoubles(coupling);
 
     std::vector<double> xs(N), ys(N), yaws(N), rx(N * Hp), ry(N * Hp), vr(N * Hp);
     std::vector<int32_t> trims(N), slot_ptr(1, 0), poly_ptr(1, 0), lane_ptr(1, 0);
@@ -309,7 +317,7 @@ void plan_timestep(pdmpc_handle *h, int nlhs, mxArray *plhs[], const mxArray *pr
     // predecessors of vehicle i: find(directed_coupling_sequential(:, i)) (PrioritizedController.m:309)
     std::vector<int32_t> pred_ptr(1, 0), pred_idx;
     for (size_t i = 0; i < N; ++i) {
-        for (size_t j = 0; j < N; ++j)
+        for (size_t j = 0; j < N && pc; ++j)
             if (pc[j + N * i] != 0.0) pred_idx.push_back(static_cast<int32_t>(j));
         pred_ptr.push_back(static_cast<int32_t>(pred_idx.size()));
     }
@@ -317,7 +325,7 @@ void plan_timestep(pdmpc_handle *h, int nlhs, mxArray *plhs[], const mxArray *pr
     // what an exhausted vehicle publishes (plan_fallback / handle_graph_search_exhaustion)
     std::vector<int32_t> fb_npts(N * Hp, 0);
     std::vector<double> fbx(N * Hp * PDMPC_AREA_STRIDE, 0.0), fby(N * Hp * PDMPC_AREA_STRIDE, 0.0);
-    const bool has_fb = mxIsCell(fallback) && mxGetM(fallback) == N && mxGetN(fallback) == static_cast<size_t>(Hp);
+    const bool has_fb = fallback && mxIsCell(fallback) && mxGetM(fallback) == N && mxGetN(fallback) == static_cast<size_t>(Hp);
     if (has_fb)
         for (size_t i = 0; i < N; ++i)
             for (int k = 0; k < Hp; ++k) {
@@ -351,12 +359,15 @@ void plan_timestep(pdmpc_handle *h, int nlhs, mxArray *plhs[], const mxArray *pr
     std::vector<int32_t> status(N, -1), n_expanded(N, 0), out_trims(N * (Hp + 1)), shape_npts(N * Hp);
     std::vector<uint8_t> exhausted(N, 0);
     std::vector<double> ypred(N * Hp * 3), sx(N * Hp * PDMPC_AREA_STRIDE), sy(N * Hp * PDMPC_AREA_STRIDE);
+    std::vector<double> g(N * (Hp + 1)), hh(N * (Hp + 1));
     pdmpc_batch_out out;
     std::memset(&out, 0, sizeof(out));
     out.status = status.data(); out.is_exhausted = exhausted.data(); out.n_expanded = n_expanded.data();
     out.trims = out_trims.data(); out.y_predicted = ypred.data();
+    out.g_path = g.data(); out.h_path = hh.data();
     out.shape_npts = shape_npts.data(); out.shape_x = sx.data(); out.shape_y = sy.data();
-    check(h, pdmpc_plan_timestep(h, &in, &deps, &out), "pdmpc_plan_timestep");
+    if (joint) check(h, pdmpc_joint_plan_batch(h, &in, static_cast<int32_t>(N), &out), "pdmpc_joint_plan_batch");
+    else check(h, pdmpc_plan_timestep(h, &in, &deps, &out), "pdmpc_plan_timestep");
     for (size_t i = 0; i < N; ++i)
         if (status[i] != PDMPC_OK) fail("pdmpc:search", "search " + std::to_string(i + 1) + " failed with status " + std::to_string(status[i]));
 
@@ -388,6 +399,10 @@ void plan_timestep(pdmpc_handle *h, int nlhs, mxArray *plhs[], const mxArray *pr
                 }
                 mxSetCell(plhs[4], i + N * k, sh);
             }
+    }
+    for (int q = 0; q < 2 && nlhs > 5 + q; ++q) {   // joint cost to come / cost to go along the path (row 1 of the search)
+        plhs[5 + q] = mxCreateDoubleMatrix(1, Hp + 1, mxREAL);
+        std::memcpy(mxGetDoubles(plhs[5 + q]), q == 0 ? g.data() : hh.data(), sizeof(double) * (Hp + 1));
     }
 }
 
@@ -436,7 +451,11 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         return;
     case PLAN_TIMESTEP:
         if (nrhs < 14) fail("pdmpc:usage", "PLAN_TIMESTEP needs 14 arguments");
-        plan_timestep(h, nlhs, plhs, prhs);
+        plan_timestep(h, nlhs, plhs, prhs, false);
+        return;
+    case PLAN_JOINT:
+        if (nrhs < 12) fail("pdmpc:usage", "PLAN_JOINT needs 12 arguments");
+        plan_timestep(h, nlhs, plhs, prhs, true);
         return;
     case STATS: {
         pdmpc_stats st;

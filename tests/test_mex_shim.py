@@ -159,3 +159,33 @@ def test_timestep_matlab_helper_present():
     src = open(os.path.join(mexfake.ROOT, "p-dmpc_b200", "matlab", "plan_timestep_cuda.m")).read()
     assert "PLAN_TIMESTEP = 6" in src and "directed_coupling_sequential" in src
     assert "create_control_results_info_from_mex" in src
+
+
+@pytest.mark.gpu
+def test_mex_joint_path_matches_oracle(matlab):
+    """PLAN_JOINT (GraphSearchCuda.run_optimizer with iter.amount > 1, the centralized controller's call)
+    through the shim against the oracle's joint search."""
+    from oracle import oracle_py
+    from pdmpc_b200.mpa import get_mpa
+    from test_joint import joint_cases
+    mpa = get_mpa("single_speed", non_convex=False)
+    (h,) = matlab.call(1, mexfake.CREATE, 0.0)
+    try:
+        trans, man = mexfake.matlab_mpa(mpa)
+        matlab.call(0, mexfake.UPLOAD_MPA, float(h), trans, man)
+        from pdmpc_b200.records import TimestepDeps
+        for name, batch, nV in joint_cases(mpa)[:1] + joint_cases(mpa)[3:4]:
+            n, Hp = batch.n, batch.Hp
+            ref = oracle_py.joint_plan_batch(mpa, batch, nV, max_nodes=1 << 17)
+            args = _timestep_args(batch, TimestepDeps.build([[] for _ in range(n)], [None] * n, Hp))[:10]
+            exh, n_exp, trims, y, shapes, g, hh = matlab.call(7, mexfake.PLAN_JOINT, float(h), *args)
+            assert exh.reshape(-1).astype(int).tolist() == ref.is_exhausted.tolist(), name
+            assert n_exp.reshape(-1).astype(int).tolist() == ref.n_expanded.tolist()
+            y = y.reshape(3, Hp, n, order="F")
+            for i in range(n):
+                assert trims[i].astype(int).tolist() == ref.trims[i].tolist()
+                assert np.array_equal(y[:, :, i].T.view(np.uint64), ref.y_predicted[i].view(np.uint64))
+            assert np.array_equal(g.reshape(-1).view(np.uint64), ref.g_path[0].view(np.uint64))
+    finally:
+        matlab.call(0, mexfake.DESTROY, float(h))
+        matlab.clear_mex()
