@@ -282,6 +282,135 @@ def do_graph_search(it, mpa, checker: int, trig: str = "spec", use_reference_pq:
             pq.push(new_ids, new_vals)                                            # :104
 
 
+# ---------------------------------------------------------------- joint search (iter.amount > 1)
+def cartprod(*sets):
+    """hlc/optimizer/common/cartprod.m:30-61: rows = ind2sub over the sets' sizes, FIRST set fastest."""
+    sizes = [len(x) for x in sets]
+    sets = [np.sort(np.asarray(x)) for x in sets]
+    out = np.zeros((int(np.prod(sizes)), len(sets)), dtype=np.int64)
+    for i in range(out.shape[0]):
+        ix = np.unravel_index(i, sizes, order="F")
+        for j in range(len(sets)):
+            out[i, j] = sets[j][ix[j]]
+    return out
+
+
+@dataclasses.dataclass
+class JointInfo:
+    is_exhausted: bool = False
+    n_expanded: int = 0
+    pops: Optional[List[int]] = None
+    tree_path: Optional[List[int]] = None
+    predicted_trims: Optional[np.ndarray] = None      # [nV, Hp]
+    y_predicted: Optional[np.ndarray] = None          # [nV, Hp, 3]
+    g_path: Optional[List[float]] = None
+
+
+def do_joint_graph_search(iters, mpa, trig: str = "spec", use_reference_pq: bool = True) -> JointInfo:
+    """GraphSearch.m:23-109 with iter.amount = nV > 1, matrix form as the MATLAB code has it: nV x nNodes tree
+    arrays (Tree.m), successor ids through mpa.trim_tuple and cartprod with the per-vehicle radix offsets
+    (expand_node.m:15-31), the vehicles' checks in order with the shapes of the vehicles before them
+    (GraphSearch.m:150-192, are_constraints_satisfied_sat.m:15-53).  iters[0] carries the search's obstacles."""
+    Hp, dt, nV, nT = mpa.Hp, mpa.dt_seconds, len(iters), mpa.n_trims
+    trim_tuple = cartprod(*[np.arange(1, nT + 1)] * nV)                       # MotionPrimitiveAutomaton.m:141
+    X = [np.array([float(it.x0[0]) for it in iters])]
+    Y = [np.array([float(it.x0[1]) for it in iters])]
+    YAW = [np.array([float(it.x0[2]) for it in iters])]
+    TRIM = [np.array([int(it.trim_indices) for it in iters])]
+    K, G, H, PARENT = [0], [0.0], [0.0], [0]
+    ref = np.stack([np.asarray(it.reference_trajectory_points, float) for it in iters])   # [nV, Hp, 2]
+    v_ref = np.stack([np.asarray(it.v_ref, float) for it in iters])
+    pq = _new_pq(use_reference_pq)
+    pq.push([1], [0.0])
+    info = JointInfo(pops=[])
+
+    def area(edge, kind, c, s, px, py):
+        n = int(mpa.area_npts[edge, kind])
+        ax, ay = mpa.area_x[edge, kind, :n], mpa.area_y[edge, kind, :n]
+        return np.vstack([c * ax - s * ay + px, s * ax + c * ay + py])
+
+    while True:
+        nid, _ = pq.pop()
+        if nid == -1:
+            info.n_expanded, info.is_exhausted = len(K), True
+            return info
+        info.pops.append(nid)
+        i = nid - 1
+        par = PARENT[i]
+        valid = True
+        if par:
+            p = par - 1
+            shapes = [None] * nV
+            for v in range(nV):
+                edge = int(mpa.edge_index[TRIM[p][v] - 1, TRIM[i][v] - 1])
+                c, s = _trig(YAW[p][v], trig)
+                shapes[v] = area(edge, 0, c, s, X[p][v], Y[p][v])
+                bshape = area(edge, 2 if K[i] == Hp else 1, c, s, X[p][v], Y[p][v])
+                for o in iters[0].obstacles:
+                    if valid and intersect_sat(shapes[v], np.asarray(o, float)):
+                        valid = False
+                for row in iters[0].dynamic_obstacle_area:
+                    if valid and intersect_sat(shapes[v], np.asarray(row[K[i] - 1], float)):
+                        valid = False
+                for u in range(v - 1, -1, -1):                               # are_constraints_satisfied_sat.m:37-44
+                    if valid and intersect_sat(shapes[u], shapes[v]):
+                        valid = False
+                if valid:
+                    left, right = iters[v].predicted_lanelet_boundary[:2]
+                    if intersect_lanelet_boundary(bshape, np.asarray(left, float).reshape(2, -1),
+                                                  np.asarray(right, float).reshape(2, -1)):
+                        valid = False
+                if not valid:
+                    break                                                     # GraphSearch.m:189-191
+        if not valid:
+            continue
+        if K[i] == Hp:
+            path = []
+            n = nid
+            while n:
+                path.append(n)
+                n = PARENT[n - 1]
+            path = path[::-1]
+            info.tree_path = path
+            info.predicted_trims = np.array([[TRIM[q - 1][v] for q in path[1:]] for v in range(nV)])
+            info.y_predicted = np.array([[[X[q - 1][v], Y[q - 1][v], YAW[q - 1][v]] for q in path[1:]] for v in range(nV)])
+            info.g_path = [G[q - 1] for q in path]
+            info.n_expanded = len(K)
+            return info
+        k_exp = K[i] + 1
+        per_vehicle = []
+        for v in range(nV):                                                   # expand_node.m:17-26
+            tr = np.flatnonzero(mpa.transition[k_exp - 1, TRIM[i][v] - 1]) + 1
+            per_vehicle.append(tr if v == 0 else (tr - 1) * nT ** v)
+        ids = cartprod(*per_vehicle).sum(axis=1)                              # :28
+        new_ids, new_vals = [], []
+        for sid in ids:
+            trims = trim_tuple[sid - 1]                                       # :41
+            ex, ey, eyaw = np.zeros(nV), np.zeros(nV), np.zeros(nV)
+            eg, eh = G[i], 0.0
+            for v in range(nV):
+                edge = int(mpa.edge_index[TRIM[i][v] - 1, trims[v] - 1])
+                c, s = _trig(YAW[i][v], trig)
+                ex[v] = c * mpa.edge_dx[edge] - s * mpa.edge_dy[edge] + X[i][v]
+                ey[v] = s * mpa.edge_dx[edge] + c * mpa.edge_dy[edge] + Y[i][v]
+                eyaw[v] = YAW[i][v] + mpa.edge_dyaw[edge]
+                d0, d1 = ex[v] - ref[v, k_exp - 1, 0], ey[v] - ref[v, k_exp - 1, 1]
+                nrm = float(np.sqrt(d0 * d0 + d1 * d1))
+                eg = eg + nrm * nrm                                           # :61
+                d_max = 0.0
+                for i_t in range(1, Hp - k_exp + 1):                          # :66-73
+                    d_max = d_max + dt * v_ref[v, k_exp + i_t - 1]
+                    w0, w1 = ex[v] - ref[v, k_exp + i_t - 1, 0], ey[v] - ref[v, k_exp + i_t - 1, 1]
+                    m = max(0.0, float(np.sqrt(w0 * w0 + w1 * w1)) - d_max)
+                    eh = eh + m * m
+            X.append(ex); Y.append(ey); YAW.append(eyaw); TRIM.append(np.array(trims))
+            K.append(k_exp); G.append(float(eg)); H.append(float(eh)); PARENT.append(nid)
+            new_ids.append(len(K))
+            new_vals.append(float(eg) * 1 + float(eh) * 1)
+        if new_ids:
+            pq.push(new_ids, new_vals)
+
+
 # ---------------------------------------------------------------- MonteCarloTreeSearch.m:29-251
 def do_mcts(it, mpa, checker: int, seed: int, n_expansions_max: int = 250, trig: str = "spec",
             use_reference_pq: bool = True) -> Info:

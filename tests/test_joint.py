@@ -152,3 +152,33 @@ def test_joint_errors_are_loud(planner):
     rows[1].obstacles.append(rect(3.0, 3.0, 0.1, 0.1))            # obstacle in a non-first row
     with pytest.raises(capi.PdmpcError):
         planner.joint_plan_batch(SearchBatch.from_iters(rows, Hp, CHECKER_SAT, mpa.dt_seconds), 2)
+
+
+def test_joint_oracle_against_matrix_form_restatement():
+    """Second, independent restatement of the joint search (oracle/matlab_literal.py: nV x nNodes arrays,
+    successor ids through trim_tuple / cartprod with the radix offsets, the reference's own priority-queue
+    source): same pop sequence length, node count, trims, poses and joint costs as the C oracle."""
+    from oracle import matlab_literal as ml
+    mpa6 = get_mpa("single_speed", non_convex=False)
+    mpa3 = get_mpa("single_speed", Hp=3, non_convex=False)     # three vehicles: 12^3 children per expansion
+    blocked = crossing_pair(mpa6, 0.35)
+    blocked[0].obstacles.append(rect(0.9, 0.0, 0.05, 0.5))
+    three = [straight_iter(mpa3, x=0.0, y=0.0), straight_iter(mpa3, x=0.45, y=-0.2, yaw=np.pi / 2),
+             straight_iter(mpa3, x=0.9, y=0.1, yaw=np.pi)]
+    for mpa, rows in ((mpa6, crossing_pair(mpa6)), (mpa6, blocked), (mpa3, three)):
+        Hp = mpa.Hp
+        nV = len(rows)
+        batch = SearchBatch.from_iters(rows, Hp, CHECKER_SAT, mpa.dt_seconds)
+        ref = oracle_py.joint_plan_batch(mpa, batch, nV)
+        info = ml.do_joint_graph_search(rows, mpa)
+        assert info.is_exhausted == bool(ref.is_exhausted[0])
+        assert info.n_expanded == int(ref.n_expanded[0]) and len(info.pops) == int(ref.n_pops[0])
+        h = 0xcbf29ce484222325
+        for p in info.pops:
+            h = ((h ^ p) * 0x100000001b3) & 0xFFFFFFFFFFFFFFFF
+        assert h == int(ref.pop_hash[0])                          # identical pop ORDER
+        assert info.tree_path == ref.tree_path[0].tolist()
+        for v in range(nV):
+            assert info.predicted_trims[v].tolist() == ref.trims[v, 1:].tolist()
+            assert np.array_equal(info.y_predicted[v].view(np.uint64), ref.y_predicted[v].view(np.uint64))
+        assert np.array_equal(np.array(info.g_path).view(np.uint64), ref.g_path[0].view(np.uint64))
