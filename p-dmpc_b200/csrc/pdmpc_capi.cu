@@ -1357,7 +1357,7 @@ int pdmpc_joint_plan_batch(pdmpc_handle *h, const pdmpc_batch_in *in, int32_t n_
     CU_TRY(h, cudaMemsetAsync(h->work_counter.p, 0, sizeof(unsigned), h->stream));
     h->stats.kernel_launches = 0;
     if (nj > 0) {
-        const int grid = std::min(nj, h->num_sms * 4);
+        const int grid = std::min(nj, h->num_sms * 2);   // two searches per SM (shared-memory heap tops)
         // default capacity: what 2 GiB of arena give every resident search, at least 2^17 nodes
         const double per_node = (double)n_vehicles * sizeof(JVeh) + sizeof(JNode) + sizeof(HEnt);
         int cap = h->user_node_cap ? h->user_node_cap
@@ -1371,7 +1371,9 @@ int pdmpc_joint_plan_batch(pdmpc_handle *h, const pdmpc_batch_in *in, int32_t n_
         ar.veh = h->j_veh.as<JVeh>(); ar.node = h->j_node.as<JNode>(); ar.heap = h->j_heap.as<HEnt>();
         ar.cap = cap; ar.nV = n_vehicles;
         CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
-        joint_search_kernel<<<grid, kWarp, 0, h->stream>>>(h->mpa, h->batch, h->out, ar, h->work_counter.as<unsigned>());
+        CU_TRY(h, cudaFuncSetAttribute(joint_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JointSmem)));
+        joint_search_kernel<<<grid, kWarp, sizeof(JointSmem), h->stream>>>(h->mpa, h->batch, h->out, ar,
+                                                                           h->work_counter.as<unsigned>());
         CU_TRY(h, cudaGetLastError());
         CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
         h->timing_pending_kernel = true;

@@ -21,7 +21,8 @@
 namespace pdmpc {
 
 constexpr int kMaxJoint = PDMPC_MAX_JOINT;
-constexpr int kJointHeap = 512;   // heap entries in shared memory per search
+constexpr int kJointHeap = 6144;  // heap entries in shared memory per search (100 KB: two searches per SM); joint
+                                  // queues hold 10^4..10^6 entries, every level kept out of HBM shortens the pop chain
 // Joint trees are large (up to 12^nV children per expansion): heap payload = node id in 28 bits | depth << 52; the
 // parent is read from the node record.
 constexpr int kJointMaxCap = (1 << 28) - 1;
@@ -59,7 +60,8 @@ struct __align__(16) JointSmem {
 
 __global__ void __launch_bounds__(kWarp) joint_search_kernel(MpaDev m, BatchDev b, OutDev o, JointArena ar, unsigned *work_counter) {
     constexpr int TILE = kWarp;
-    __shared__ JointSmem sm;
+    extern __shared__ __align__(16) unsigned char joint_smem_raw[];
+    JointSmem &sm = *reinterpret_cast<JointSmem *>(joint_smem_raw);
     Tables tb;
     tb.succ_ptr = m.succ_ptr; tb.succ_te = m.succ_te; tb.edge_d = m.edge_d;
     tb.area_npts = m.area_npts; tb.area_x = m.area_x; tb.area_y = m.area_y;
