@@ -183,6 +183,44 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
             sm.refy[k] = __ldg(b.ref_y + (size_t)si * Hp + k);
             sm.vref[k] = __ldg(b.v_ref + (size_t)si * Hp + k);
         }
+        const int *slot = b.slot_ptr + (size_t)si * (Hp + 1);
+        const int trim0 = __ldg(b.trim0 + si);
+        const int sp0 = __ldg(slot + 0), sp1 = __ldg(slot + 1);
+        const int lp0 = __ldg(b.lane_ptr + 2 * si), lp1 = __ldg(b.lane_ptr + 2 * si + 1),
+                  lp2 = __ldg(b.lane_ptr + 2 * si + 2);
+        const double *opx = nullptr, *opy = nullptr, *lpx = nullptr, *lpy = nullptr;
+        int obase = 0, llo = 0, lhi = 0;
+        if (b.checker == PDMPC_CHECKER_INTERX) {
+            const int spE = __ldg(slot + Hp + 1);
+            const int ob_lo = __ldg(b.poly_ptr + sp0) + sp0, ob_hi = __ldg(b.poly_ptr + spE) + spE;
+            const int ll_lo = lp0 + 2 * si, ll_hi = lp2 + 2 * si + 2;
+            for (int k = threadIdx.x; k <= Hp + 1; k += kThreads) {
+                const int q = __ldg(slot + k);
+                sm.rng[k] = __ldg(b.poly_ptr + q) + q - ob_lo;
+            }
+            const int nl = ll_hi - ll_lo, no = ob_hi - ob_lo;
+            int used = 0;
+            if (nl <= SP) {
+                for (int j = threadIdx.x; j < nl; j += kThreads) {
+                    sm.pts_x[j] = __ldg(b.ll_x + ll_lo + j);
+                    sm.pts_y[j] = __ldg(b.ll_y + ll_lo + j);
+                }
+                lpx = sm.pts_x; lpy = sm.pts_y; llo = 0; lhi = nl;
+                used = nl;
+            } else {
+                lpx = b.ll_x; lpy = b.ll_y; llo = ll_lo; lhi = ll_hi;
+            }
+            if (used + no <= SP) {
+                for (int j = threadIdx.x; j < no; j += kThreads) {
+                    sm.pts_x[used + j] = __ldg(b.pl_x + ob_lo + j);
+                    sm.pts_y[used + j] = __ldg(b.pl_y + ob_lo + j);
+                }
+                opx = sm.pts_x; opy = sm.pts_y; obase = used;
+            } else {
+                opx = b.pl_x; opy = b.pl_y; obase = ob_lo;
+            }
+        }
+        // (everything above is independent of the predecessors: it overlaps their searches)
         if (DEPS) {
             // ---- consider_predecessors (PrioritizedController.m:449-506) on the device ------------
             // Work items are handed out in a topological order of the DAG (the host sorts them), so
@@ -219,43 +257,6 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
                     sm.dep_n[pk] = np;
                     if (np) atomicAdd(&sm.dep_cols[k0 + 1], np + 1);
                 }
-            }
-        }
-        const int *slot = b.slot_ptr + (size_t)si * (Hp + 1);
-        const int trim0 = __ldg(b.trim0 + si);
-        const int sp0 = __ldg(slot + 0), sp1 = __ldg(slot + 1);
-        const int lp0 = __ldg(b.lane_ptr + 2 * si), lp1 = __ldg(b.lane_ptr + 2 * si + 1),
-                  lp2 = __ldg(b.lane_ptr + 2 * si + 2);
-        const double *opx = nullptr, *opy = nullptr, *lpx = nullptr, *lpy = nullptr;
-        int obase = 0, llo = 0, lhi = 0;
-        if (b.checker == PDMPC_CHECKER_INTERX) {
-            const int spE = __ldg(slot + Hp + 1);
-            const int ob_lo = __ldg(b.poly_ptr + sp0) + sp0, ob_hi = __ldg(b.poly_ptr + spE) + spE;
-            const int ll_lo = lp0 + 2 * si, ll_hi = lp2 + 2 * si + 2;
-            for (int k = threadIdx.x; k <= Hp + 1; k += kThreads) {
-                const int q = __ldg(slot + k);
-                sm.rng[k] = __ldg(b.poly_ptr + q) + q - ob_lo;
-            }
-            const int nl = ll_hi - ll_lo, no = ob_hi - ob_lo;
-            int used = 0;
-            if (nl <= SP) {
-                for (int j = threadIdx.x; j < nl; j += kThreads) {
-                    sm.pts_x[j] = __ldg(b.ll_x + ll_lo + j);
-                    sm.pts_y[j] = __ldg(b.ll_y + ll_lo + j);
-                }
-                lpx = sm.pts_x; lpy = sm.pts_y; llo = 0; lhi = nl;
-                used = nl;
-            } else {
-                lpx = b.ll_x; lpy = b.ll_y; llo = ll_lo; lhi = ll_hi;
-            }
-            if (used + no <= SP) {
-                for (int j = threadIdx.x; j < no; j += kThreads) {
-                    sm.pts_x[used + j] = __ldg(b.pl_x + ob_lo + j);
-                    sm.pts_y[used + j] = __ldg(b.pl_y + ob_lo + j);
-                }
-                opx = sm.pts_x; opy = sm.pts_y; obase = used;
-            } else {
-                opx = b.pl_x; opy = b.pl_y; obase = ob_lo;
             }
         }
         __syncthreads();
