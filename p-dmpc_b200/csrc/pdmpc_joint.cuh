@@ -54,7 +54,8 @@ struct __align__(16) JointSmem {
     unsigned long long hw[kJointHeap];
     double refx[kMaxJoint][kMaxHp], refy[kMaxJoint][kMaxHp], vref[kMaxJoint][kMaxHp];
     double shx[kMaxJoint][kAreaStride], shy[kMaxJoint][kAreaStride];
-    double bhx[kAreaStride], bhy[kAreaStride];
+    double bhx[kMaxJoint][kAreaStride], bhy[kMaxJoint][kAreaStride];
+    int edge_of[kMaxJoint];
     unsigned path[kMaxHp + 1];
 };
 
@@ -126,18 +127,23 @@ __global__ void __launch_bounds__(kWarp) joint_search_kernel(MpaDev m, BatchDev 
             bool valid = true;
             if (par != 0) {   // eval_edge_exact, GraphSearch.m:150-192
                 const int sp0 = __ldg(slot + 0), sp1 = __ldg(slot + 1), dp0 = __ldg(slot + cK), dp1 = __ldg(slot + cK + 1);
+                const int bkind = (cK == Hp) ? PDMPC_AREA_LARGE_OFFSET : PDMPC_AREA_WITHOUT_OFFSET;
+                {   // all vehicles' records in ONE round of loads, all areas placed together (8 lanes per vehicle);
+                    // whether an edge is valid does not depend on the order in which its shapes are computed
+                    const int pv_i = t.lane / kAreaStride, pt_i = t.lane % kAreaStride;
+                    if (pv_i < nV) {
+                        const JVeh pv = nv[(size_t)par * nV + pv_i];
+                        const int edge = (int)nv[(size_t)id * nV + pv_i].edge;
+                        place_point(tb, edge, PDMPC_AREA_NORMAL, pt_i, pv.c, pv.s, pv.x, pv.y, sm.shx[pv_i][pt_i], sm.shy[pv_i][pt_i]);
+                        place_point(tb, edge, bkind, pt_i, pv.c, pv.s, pv.x, pv.y, sm.bhx[pv_i][pt_i], sm.bhy[pv_i][pt_i]);
+                        if (pt_i == 0) sm.edge_of[pv_i] = edge;
+                    }
+                    t.sync();
+                }
                 for (int v = 0; v < nV && valid; ++v) {
-                    const JVeh pv = nv[(size_t)par * nV + v];
-                    const int edge = (int)nv[(size_t)id * nV + v].edge;
-                    const int bkind = (cK == Hp) ? PDMPC_AREA_LARGE_OFFSET : PDMPC_AREA_WITHOUT_OFFSET;
+                    const int edge = sm.edge_of[v];
                     const int ns = tb.area_npts[edge * 3 + PDMPC_AREA_NORMAL];
                     const int nbs = tb.area_npts[edge * 3 + bkind];
-                    t.sync();   // bhx/bhy of the previous vehicle are no longer read
-                    if (t.lane < 8)
-                        place_point(tb, edge, PDMPC_AREA_NORMAL, t.lane, pv.c, pv.s, pv.x, pv.y, sm.shx[v][t.lane], sm.shy[v][t.lane]);
-                    else if (t.lane < 16)
-                        place_point(tb, edge, bkind, t.lane - 8, pv.c, pv.s, pv.x, pv.y, sm.bhx[t.lane - 8], sm.bhy[t.lane - 8]);
-                    t.sync();
                     // are_constraints_satisfied_sat.m:15-35: static obstacles, dynamic obstacles of this step
                     for (int pass = 0; pass < 2 && valid; ++pass) {
                         const int q0 = pass == 0 ? sp0 : dp0, q1 = pass == 0 ? sp1 : dp1;
@@ -149,7 +155,7 @@ __global__ void __launch_bounds__(kWarp) joint_search_kernel(MpaDev m, BatchDev 
                     }
                     // :37-44 vehicles of the same node with a lower index
                     for (int u = v - 1; u >= 0 && valid; --u) {
-                        const int eu = (int)nv[(size_t)id * nV + u].edge;
+                        const int eu = sm.edge_of[u];
                         const int nsu = tb.area_npts[eu * 3 + PDMPC_AREA_NORMAL];
                         cols += (unsigned long long)nsu;
                         if (sat_collide<TILE, false>(sm.shx[u], sm.shy[u], nsu, sm.shx[v], sm.shy[v], ns, t)) valid = false;
@@ -158,8 +164,8 @@ __global__ void __launch_bounds__(kWarp) joint_search_kernel(MpaDev m, BatchDev 
                         const int r = r0 + v;
                         const int lp0 = __ldg(b.lane_ptr + 2 * r), lp1 = __ldg(b.lane_ptr + 2 * r + 1), lp2 = __ldg(b.lane_ptr + 2 * r + 2);
                         cols += (unsigned long long)(lp2 - lp0);
-                        if (lanelet_side_sat<TILE>(sm.bhx, sm.bhy, nbs, b.lane_x + lp0, b.lane_y + lp0, lp1 - lp0, t)) valid = false;
-                        else if (lanelet_side_sat<TILE>(sm.bhx, sm.bhy, nbs, b.lane_x + lp1, b.lane_y + lp1, lp2 - lp1, t)) valid = false;
+                        if (lanelet_side_sat<TILE>(sm.bhx[v], sm.bhy[v], nbs, b.lane_x + lp0, b.lane_y + lp0, lp1 - lp0, t)) valid = false;
+                        else if (lanelet_side_sat<TILE>(sm.bhx[v], sm.bhy[v], nbs, b.lane_x + lp1, b.lane_y + lp1, lp2 - lp1, t)) valid = false;
                     }
                 }
             }
