@@ -20,6 +20,10 @@
  *   priority_queue_interface_mex (NEW/PUSH/POP)              hlc/optimizer/graph_search/priority_queue/priority_queue_interface_mex.cpp:19-108
  *   return_path_to / return_path_area                        hlc/optimizer/graph_search/return_path_to.m:1-27, return_path_area.m:1-8
  *   MonteCarloTreeSearch.run_optimizer / do_graph_search     hlc/optimizer/graph_search/MonteCarloTreeSearch.m:29-251
+ *   the same search with iter.amount > 1 (joint)             hlc/controller/centralized/CentralizedController.m:33-59,
+ *                                                            expand_node.m:15-75, are_constraints_satisfied_sat.m:37-44
+ *   level loop + hand-over of predecessors' areas            hlc/controller/prioritized/PrioritizedSequentialController.m:74-92,
+ *   (pdmpc_plan_timestep, optional)                          PrioritizedController.m:297-324,355-364,449-506
  *
  * Conventions
  *   - plain C, no C++ types, no exceptions cross this boundary; every call
