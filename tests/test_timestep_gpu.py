@@ -288,3 +288,20 @@ def test_config3_40_vehicles_reachable_set_obstacles(planner, max_cls):
     assert flat.n == 200 and np.diff(flat.poly_ptr).max() >= 15
     info, _dev, _ref = check(planner, mpa, flat)
     assert info["exhausted"] > 0
+
+
+def test_lockstep_scenarios_one_call_per_time_step(planner):
+    """BASELINE configs[4] in closed loop: several scenarios advanced together, every time step of all of
+    them as ONE pdmpc_plan_timestep call; each ends exactly where it ends when advanced alone."""
+    mpa = get_mpa("triple_speed", non_convex=True)
+    planner.upload_mpa(mpa)
+    ts = lambda b, d: planner.plan_timestep(b, d, False)
+    seeds = (1, 2, 3, 4)
+    together = [scenario.ScenarioRunner(scenario.commonroad_scenario(mpa, 20, seed=s), None, timestep_fn=ts) for s in seeds]
+    for _ in range(4):
+        res = scenario.lockstep_step(together, ts)
+        assert res.status.size == 80 and int(res.status.max()) == 0
+    for s, r in zip(seeds, together):
+        alone = scenario.ScenarioRunner(scenario.commonroad_scenario(mpa, 20, seed=s), None, timestep_fn=ts)
+        alone.run(4)
+        assert np.array_equal(alone.pose, r.pose) and np.array_equal(alone.trim, r.trim)
