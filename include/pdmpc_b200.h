@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define PDMPC_ABI_VERSION 1
+#define PDMPC_ABI_VERSION 2
 
 /* A maneuver area polygon has 5 (straight), 6 (turn, convex build) or 7 (turn,
  * non-convex build) closed points: generate_maneuver.m:73-103.  Fixed stride. */
@@ -171,9 +171,10 @@ typedef struct pdmpc_stats {
     int64_t total_nodes;
     int64_t total_obstacle_cols; /* sum over pops of (V_k + L) columns tested */
     int32_t kernel_launches;
-    int32_t handed_over;     /* shape 3: searches the threads handed to the warp-per-search stage;
-                              * shape 5: searches re-run with the exact queue after a non-unique minimum */
-    double lanes_ms;         /* shape 3: CUDA-event time of the first (lane-per-search) launch alone */
+    int32_t handed_over;     /* shape 5: searches re-run with the exact queue after a non-unique minimum */
+    int32_t shape;           /* the launch shape that actually ran (1..5, see pdmpc_set_variant): a requested
+                              * shape that cannot serve a batch falls back, and says so here */
+    int32_t reserved_;
 } pdmpc_stats;
 
 /* Create a planner bound to CUDA device `device_id`.  Fails (PDMPC_ERR_CUDA)
@@ -188,34 +189,34 @@ int pdmpc_abi_version(void);
  * search that needs more returns PDMPC_ERR_CAPACITY in its status. */
 int pdmpc_set_node_capacity(pdmpc_handle *h, int32_t max_nodes_per_search);
 
-/* Launch shape of the search kernel: 0 = choose from the batch size (default),
- * 1 = latency (one warp-CTA per search slot, tables through L1/L2), 2 = throughput
- * (one 16-warp CTA per SM, MPA tables TMA-staged in shared memory; falls back to 1
- * when the tables do not fit), 3 = lanes (one THREAD per search for large InterX
- * batches; searches that outgrow a thread's slot or pop budget are re-run by shape 1
- * in a second launch; falls back to 2 for SAT batches), 4 = cta (one 13-warp CTA per search: a
- * master warp owns queue and tree, checker warps validate the children of every expansion
- * ahead of their pop; chosen automatically for batches of at most one search per SM; falls
- * back to 1 when the full search tree of the MPA exceeds 32768 nodes), 5 = shape 4 with a
- * VALID-ONLY QUEUE: children whose edge check failed are not pushed; before every pop the
- * minimum must be unique, otherwise the search is re-run with the exact queue (p-dmpc_b200/csrc/
- * pdmpc_cta.cuh has the argument why every output then equals the reference's); opt-in only — it
- * trades the pops of invalid nodes for waiting on the checkers and measured no faster than shape 4.
+/* Launch shape of the search kernel: 0 = choose from the batch size (default);
+ * 1 = one search per one-warp CTA (lowest latency of the warp shapes; every checker);
+ * 2 = tiles, TWO searches per warp, 3 = tiles, FOUR searches per warp (p-dmpc_b200/csrc/pdmpc_tiles.cuh: the
+ *     throughput shapes — one iteration of a warp pops one node for each of its searches, so the warp-uniform
+ *     work is issued once for all of them; InterX batches only, SAT batches fall back to 1);
+ * 4 = cta (one 16-warp CTA per search: a master warp owns queue and tree, checker warps validate the children
+ *     of every expansion ahead of their pop; chosen automatically for batches of at most one search per SM;
+ *     falls back to 1 when the full search tree of the MPA exceeds 32768 nodes);
+ * 5 = shape 4 with a VALID-ONLY QUEUE: children whose edge check failed are not pushed; before every pop the
+ *     minimum must be unique, otherwise the search is re-run with the exact queue (p-dmpc_b200/csrc/
+ *     pdmpc_cta.cuh has the argument why every output then equals the reference's).
+ * 0 picks 4 for n <= #SMs, 2 when there are more searches than shape 1 keeps in flight, else 1.
+ * pdmpc_stats.shape reports the shape that actually ran.
  * Results do not depend on the shape, with ONE exception: pop_hash, a parity trace that is not
  * part of the reference's ControlResultsInfo, covers the popped nodes that passed their edge
  * check only in shape 5 (n_pops is exact in every shape). */
 int pdmpc_set_variant(pdmpc_handle *h, int32_t variant);
 
-/* Shape 3 only: nodes per thread slot (0 = default 4096) and the number of pops after
- * which a thread hands its search over to the warp-per-search kernel (0 = default 1024).
- * Tuning knobs: results do not depend on them. */
-int pdmpc_set_lane_limits(pdmpc_handle *h, int32_t nodes_per_thread, int32_t pop_limit);
+/* Shapes 2, 3 only: polyline points (lanelet bounds + obstacles of all steps) a tile stages in shared
+ * memory per search (0 = what the kernel holds, 256); polylines beyond it are read from HBM/L2.  Test knob:
+ * results do not depend on it. */
+int pdmpc_set_tile_points(pdmpc_handle *h, int32_t points);
 
 /* Shape 4 only: heap entries kept in shared memory (0 = default 4096, even); the rest of the
  * queue spills to the HBM arena.  Tuning/test knob: results do not depend on it. */
 int pdmpc_set_cta_heap_smem(pdmpc_handle *h, int32_t entries);
 
-/* pdmpc_plan_batch on large host batches (>= 16384 searches, launch shapes 0..2) runs as a chunked
+/* pdmpc_plan_batch on large host batches (>= 16384 searches, launch shapes 0..3) runs as a chunked
  * pipeline: host->device copies, searches and device->host copies of consecutive chunks overlap.
  * chunks: 0 = choose from the batch size (default), 1 = off, 2..16 = that many chunks for any batch
  * of at least 2*chunks searches.  Tuning/test knob: results do not depend on it. */

@@ -30,7 +30,7 @@ PDMPC_ERR_ALLOC = 5
 
 EXPORTED_SYMBOLS = (
     "pdmpc_create", "pdmpc_destroy", "pdmpc_last_error", "pdmpc_abi_version",
-    "pdmpc_set_node_capacity", "pdmpc_set_variant", "pdmpc_set_lane_limits", "pdmpc_host_alloc", "pdmpc_host_free",
+    "pdmpc_set_node_capacity", "pdmpc_set_variant", "pdmpc_set_tile_points", "pdmpc_host_alloc", "pdmpc_host_free",
     "pdmpc_trace_staged", "pdmpc_upload_mpa", "pdmpc_plan_batch", "pdmpc_stage_batch",
     "pdmpc_run_staged", "pdmpc_sync", "pdmpc_fetch_staged", "pdmpc_get_stats", "pdmpc_stream",
     "pdmpc_mcts_plan_batch", "pdmpc_mcts_run_staged", "pdmpc_set_cta_heap_smem", "pdmpc_plan_timestep",
@@ -84,7 +84,7 @@ class Stats(C.Structure):
         ("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("total_pops", C.c_int64),
         ("total_nodes", C.c_int64), ("total_obstacle_cols", C.c_int64),
-        ("kernel_launches", C.c_int32), ("handed_over", C.c_int32), ("lanes_ms", C.c_double),
+        ("kernel_launches", C.c_int32), ("handed_over", C.c_int32), ("shape", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -179,8 +179,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.pdmpc_measure_fp64_peak.restype = C.c_int
     lib.pdmpc_set_pipeline_chunks.argtypes = [H, C.c_int32]
     lib.pdmpc_set_pipeline_chunks.restype = C.c_int
-    lib.pdmpc_set_lane_limits.argtypes = [H, C.c_int32, C.c_int32]
-    lib.pdmpc_set_lane_limits.restype = C.c_int
+    lib.pdmpc_set_tile_points.argtypes = [H, C.c_int32]
+    lib.pdmpc_set_tile_points.restype = C.c_int
     lib.pdmpc_trace_staged.argtypes = [H, C.c_int32, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64)]
     lib.pdmpc_trace_staged.restype = C.c_int
     lib.pdmpc_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
@@ -253,7 +253,7 @@ class Planner:
         self._check(self.lib.pdmpc_set_node_capacity(self.h, int(n)))
 
     def set_variant(self, variant: int):
-        """0 = auto, 1 = latency shape, 2 = throughput shape, 3 = lanes (pdmpc_set_variant)."""
+        """0 = auto, 1 = one search per warp, 2 / 3 = tiles (2 / 4 searches per warp), 4 / 5 = one CTA per search (pdmpc_set_variant)."""
         self._check(self.lib.pdmpc_set_variant(self.h, int(variant)))
 
     def set_cta_heap_smem(self, entries: int = 0):
@@ -270,9 +270,9 @@ class Planner:
         """Chunked copy/search pipeline of plan_batch (pdmpc_set_pipeline_chunks); results do not depend on it."""
         self._check(self.lib.pdmpc_set_pipeline_chunks(self.h, int(chunks)))
 
-    def set_lane_limits(self, nodes_per_thread: int = 0, pop_limit: int = 0):
-        """Shape 3 tuning knobs (pdmpc_set_lane_limits); results do not depend on them."""
-        self._check(self.lib.pdmpc_set_lane_limits(self.h, int(nodes_per_thread), int(pop_limit)))
+    def set_tile_points(self, points: int = 0):
+        """Shapes 2, 3 test knob (pdmpc_set_tile_points); results do not depend on it."""
+        self._check(self.lib.pdmpc_set_tile_points(self.h, int(points)))
 
     def trace(self, search: int, cap: int = 1 << 20) -> np.ndarray:
         """Node ids popped by staged search `search`, in order (pdmpc_trace_staged)."""

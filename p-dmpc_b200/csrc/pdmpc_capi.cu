@@ -15,7 +15,7 @@
 #include <vector>
 
 #include "pdmpc_kernels.cuh"
-#include "pdmpc_lanes.cuh"
+#include "pdmpc_tiles.cuh"
 #include "pdmpc_mcts.cuh"
 #include "pdmpc_cta.cuh"
 #include "pdmpc_joint.cuh"
@@ -24,9 +24,8 @@ using namespace pdmpc;
 
 namespace {
 
-// Launch shapes of the search kernel (pdmpc_kernels.cuh): "latency" = one warp
-// per CTA, tables through L1/L2; "throughput" = one 16-warp CTA per SM with the
-// MPA tables TMA-staged into shared memory.
+// Launch shapes of the warp-level search kernels: "latency" = one search per one-warp CTA
+// (pdmpc_kernels.cuh); "tiles" = 2 or 4 searches per warp (pdmpc_tiles.cuh), the throughput shape.
 #ifndef PDMPC_HEAP_SMEM
 #define PDMPC_HEAP_SMEM 256
 #endif
@@ -35,25 +34,30 @@ namespace {
 #endif
 constexpr int kHeapSmem = PDMPC_HEAP_SMEM;   // heap entries kept in shared memory per search
 constexpr int kPts = PDMPC_PTS_SMEM;         // polyline points (lanelet bounds + obstacles of all steps) staged per search
-constexpr int kWarpsThroughput = 16;
-#define KERNEL_LAT search_kernel<kHeapSmem, kPts, 1, false>
-#define KERNEL_THR search_kernel<kHeapSmem, kPts, kWarpsThroughput, true>
-#define KERNEL_LAT_DEPS search_kernel<kHeapSmem, kPts, 1, false, true>
+#define KERNEL_LAT search_kernel<kHeapSmem, kPts, false>
+#define KERNEL_LAT_DEPS search_kernel<kHeapSmem, kPts, true>
 using WarpSmem = TileSmem<kHeapSmem, kPts>;
 constexpr size_t kSmemLimit = 227 * 1024;
-// "lanes" = one THREAD per search (pdmpc_lanes.cuh), one CTA per SM; searches that outgrow a
-// thread's slot or pop budget are re-run by the warp-per-search kernel in a second launch
-constexpr int kLaneThreads = 256;
-#define KERNEL_LANES_SMEM search_lanes_kernel<kLaneThreads, true>
-#define KERNEL_LANES_GMEM search_lanes_kernel<kLaneThreads, false>
+// tiles: TILE lanes per search; heap entries / staged polyline points per search in shared memory;
+// one-warp CTAs per SM the shape is compiled for (register cap) — sized so that the CTAs fill 228 KB
+#ifndef PDMPC_TILE2_CTAS
+#define PDMPC_TILE2_CTAS 12
+#endif
+#ifndef PDMPC_TILE4_CTAS
+#define PDMPC_TILE4_CTAS 8
+#endif
+constexpr int kTile2Heap = 224, kTile2Pts = 256, kTile2Ctas = PDMPC_TILE2_CTAS;
+constexpr int kTile4Heap = 96, kTile4Pts = 256, kTile4Ctas = PDMPC_TILE4_CTAS;
+#define KERNEL_TILE2 search_tile_kernel<16, kTile2Heap, kTile2Pts, kTile2Ctas>
+#define KERNEL_TILE4 search_tile_kernel<8, kTile4Heap, kTile4Pts, kTile4Ctas>
+constexpr size_t kTile2Smem = 2 * sizeof(TileSm<kTile2Heap, kTile2Pts>);
+constexpr size_t kTile4Smem = 4 * sizeof(TileSm<kTile4Heap, kTile4Pts>);
 // "cta" = one 13-warp CTA per search (pdmpc_cta.cuh): master warp + checker warps, lowest latency
 #define KERNEL_CTA search_cta_kernel<kCtaHeap, kCtaPts, kCtaHelpers, false>
 using CtaSmemT = CtaSmem<kCtaHeap, kCtaPts, kCtaHelpers, false>;
 // the same kernel with the dependency prelude/epilogue of pdmpc_plan_timestep
 #define KERNEL_CTA_DEPS search_cta_kernel<kCtaHeap, kCtaPts, kCtaHelpers, true>
 using CtaDepsSmemT = CtaSmem<kCtaHeap, kCtaPts, kCtaHelpers, true>;
-constexpr int kLaneNodeCapDefault = 4096;
-constexpr int kLanePopLimitDefault = 1024;
 
 struct DBuf {
     void *p = nullptr;
@@ -82,9 +86,9 @@ struct pdmpc_handle {
     int device = 0;
     int num_sms = 0;
     int lat_ctas_per_sm = 0;          // occupancy of the latency shape
-    bool thr_ok = false;              // throughput shape usable with the uploaded MPA (tables fit in smem)
-    size_t thr_smem = 0;
-    int variant_mode = 0;             // 0 = auto, 1 = latency, 2 = throughput, 3 = lanes (+ warp second stage), 4 = cta
+    int tile_ctas_per_sm[2] = {0, 0}; // occupancy of the tile shapes (2 / 4 searches per warp); 0 = not launchable
+    int tile_pts_limit = 0;           // staged-points limit of the tile shapes (0 = what the kernel holds; test knob)
+    int variant_mode = 0;             // 0 = auto, 1 = latency, 2 / 3 = tiles (2 / 4 searches per warp), 4 / 5 = cta
     int cta_heap_smem = kCtaHeap;     // heap entries the CTA shape keeps in shared memory (tuning/test knob)
     bool cta_ok = false;              // the CTA-per-search kernel is launchable (shared memory opt-in granted)
     bool cta_deps_ok = false;         // ... and its pdmpc_plan_timestep instance
@@ -105,18 +109,14 @@ struct pdmpc_handle {
     size_t pin_order_cap = 0;
     DBuf wc_chunks;
     int pipeline_chunks = 0;          // 0 = auto, 1 = off (tuning/test knob, pdmpc_set_pipeline_chunks)
-    bool lanes_ok = false;            // every maneuver area has <= 7 points
-    bool lanes_smem_ok = false;       // MPA tables fit in shared memory next to nothing else
-    size_t lanes_smem = 0;
-    int lane_node_cap = kLaneNodeCapDefault, lane_pop_limit = kLanePopLimitDefault;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[7] = {};   // 0/1 h2d, 2/3 kernel, 4/5 d2h, 6 end of the lane-per-search launch
+    cudaEvent_t ev[7] = {};   // 0/1 h2d, 2/3 kernel, 4/5 d2h
     std::string err;
 
     // MPA
     bool has_mpa = false;
     MpaDev mpa{};
-    DBuf m_succ_ptr, m_succ_te, m_edge_d, m_npts, m_ax, m_ay, m_apx, m_apy;
+    DBuf m_succ_ptr, m_succ_te, m_edge_d, m_npts, m_ax, m_ay;
     int full_tree_nodes = 0;
     int user_node_cap = 0;
     int max_branch = 0;               // mpa.maximum_branching_factor()
@@ -126,7 +126,7 @@ struct pdmpc_handle {
     BatchDev batch{};
     int n_polys = 0, n_verts = 0, n_lane = 0;
     DBuf b_x0, b_y0, b_yaw0, b_trim0, b_refx, b_refy, b_vref, b_slot, b_poly, b_vx, b_vy, b_plx, b_ply,
-        b_lane, b_lx, b_ly, b_llx, b_lly, b_order, b_plxy, b_llxy, b_rng, b_seed;
+        b_lane, b_lx, b_ly, b_llx, b_lly, b_order, b_seed;
 
     // small batches (one computation level of a time step): every input array in ONE pinned
     // staging buffer -> one H2D copy; every output array in one device block -> one D2H copy
@@ -147,17 +147,13 @@ struct pdmpc_handle {
     ArenaDev arena{};
     DBuf a_a, a_b, a_cs, a_heap;
     int arena_slots = 0;
-    // lane-per-search arena (small slots, one per thread) and the hand-over list
-    ArenaDev larena{};
-    DBuf la_a, la_b, la_cs, la_heap, ov_count, ov_list, work_counter2;
-    int larena_slots = 0;
 
     // trace (debug / parity tests)
     DBuf t_ids, t_n;
 
     pdmpc_stats stats{};
     bool timing_pending_h2d = false, timing_pending_kernel = false, timing_pending_d2h = false,
-         timing_pending_lanes = false;
+         unused_ = false;
 };
 
 static thread_local std::string g_create_error;
@@ -240,6 +236,12 @@ int pdmpc_create(int device_id, pdmpc_handle **out) {
         return fail(nullptr, PDMPC_ERR_CUDA, msg);
     }
     h->lat_ctas_per_sm = occ;
+    if (cudaFuncSetAttribute(KERNEL_TILE2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile2Smem) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, KERNEL_TILE2, kWarp, kTile2Smem) == cudaSuccess)
+        h->tile_ctas_per_sm[0] = occ;
+    if (cudaFuncSetAttribute(KERNEL_TILE4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile4Smem) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, KERNEL_TILE4, kWarp, kTile4Smem) == cudaSuccess)
+        h->tile_ctas_per_sm[1] = occ;
     h->cta_ok = cudaFuncSetAttribute(KERNEL_CTA, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(CtaSmemT)) == cudaSuccess;
     h->lat_deps_ok = cudaFuncSetAttribute(KERNEL_LAT_DEPS, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -256,8 +258,7 @@ int pdmpc_destroy(pdmpc_handle *h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     DBuf *bufs[] = {&h->m_succ_ptr, &h->m_succ_te, &h->m_edge_d, &h->m_npts, &h->m_ax, &h->m_ay, &h->b_order,
-                    &h->m_apx, &h->m_apy, &h->b_plxy, &h->b_llxy, &h->b_rng, &h->la_a, &h->la_b, &h->la_cs,
-                    &h->la_heap, &h->ov_count, &h->ov_list, &h->work_counter2, &h->b_x0, &h->b_y0, &h->b_yaw0, &h->b_trim0,
+                    &h->b_x0, &h->b_y0, &h->b_yaw0, &h->b_trim0,
                     &h->b_refx, &h->b_refy, &h->b_vref, &h->b_slot, &h->b_poly, &h->b_vx, &h->b_vy,
                     &h->b_plx, &h->b_ply, &h->b_lane, &h->b_lx, &h->b_ly, &h->b_llx, &h->b_lly,
                     &h->work_counter, &h->b_seed, &h->a_a, &h->a_b, &h->a_cs, &h->a_heap, &h->t_ids, &h->t_n};
@@ -306,7 +307,7 @@ int pdmpc_set_variant(pdmpc_handle *h, int32_t variant) {
     if (!h) return PDMPC_ERR_BAD_INPUT;
     if (variant < 0 || variant > 5)
         return fail(h, PDMPC_ERR_BAD_INPUT,
-                    "variant must be 0 (auto), 1 (latency), 2 (throughput), 3 (lanes), 4 (cta) or 5 (cta, valid-only queue)");
+                    "variant must be 0 (auto), 1 (one search per warp), 2 / 3 (tiles: 2 / 4 searches per warp), 4 (cta) or 5 (cta, valid-only queue)");
     h->variant_mode = variant;
     return PDMPC_OK;
 }
@@ -319,12 +320,10 @@ int pdmpc_set_cta_heap_smem(pdmpc_handle *h, int32_t entries) {
     return PDMPC_OK;
 }
 
-int pdmpc_set_lane_limits(pdmpc_handle *h, int32_t node_cap, int32_t pop_limit) {
+int pdmpc_set_tile_points(pdmpc_handle *h, int32_t points) {
     if (!h) return PDMPC_ERR_BAD_INPUT;
-    if (node_cap < 0 || pop_limit < 0 || (node_cap != 0 && node_cap < 64))
-        return fail(h, PDMPC_ERR_BAD_INPUT, "lane limits: node_cap must be 0 (default) or >= 64, pop_limit >= 0");
-    h->lane_node_cap = node_cap ? (node_cap + 1) / 2 * 2 : kLaneNodeCapDefault;
-    h->lane_pop_limit = pop_limit ? pop_limit : kLanePopLimitDefault;
+    if (points < 0) return fail(h, PDMPC_ERR_BAD_INPUT, "tile points: must be 0 (default) or > 0");
+    h->tile_pts_limit = points;
     return PDMPC_OK;
 }
 
@@ -442,20 +441,6 @@ int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *d) {
     UP(h, h->m_npts, npts.data(), npts.size());
     UP(h, h->m_ax, ax.data(), ax.size());
     UP(h, h->m_ay, ay.data(), ay.size());
-    // lane-per-search kernel: areas padded by repeating the last point (zero-length edges
-    // never satisfy InterX's strict inequalities), so every shape is a 7-point polyline
-    std::vector<double> apx(ax), apy(ay);
-    bool lanes_ok = true;
-    for (int e = 0; e < nE * 3; ++e) {
-        const int np = d->area_npts[e];
-        if (np > kLanePts) lanes_ok = false;
-        for (int i = np; i < PDMPC_AREA_STRIDE; ++i) {
-            apx[(size_t)e * PDMPC_AREA_STRIDE + i] = apx[(size_t)e * PDMPC_AREA_STRIDE + np - 1];
-            apy[(size_t)e * PDMPC_AREA_STRIDE + i] = apy[(size_t)e * PDMPC_AREA_STRIDE + np - 1];
-        }
-    }
-    UP(h, h->m_apx, apx.data(), apx.size());
-    UP(h, h->m_apy, apy.data(), apy.size());
     CU_TRY(h, cudaStreamSynchronize(h->stream));   // host vectors go out of scope
     h->stats.h2d_bytes = keep;
     MpaDev &m = h->mpa;
@@ -471,17 +456,6 @@ int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *d) {
     m.bytes_area_npts = (unsigned)(npts.size() * sizeof(int));
     m.bytes_area = (unsigned)(ax.size() * sizeof(double));
     m.table_bytes = m.bytes_succ_ptr + m.bytes_succ_te + m.bytes_edge_d + m.bytes_area_npts + 2 * m.bytes_area;
-    // throughput shape: tables + 16 warps' private state must fit the 227 KB of one SM
-    h->thr_smem = 16 + (size_t)m.table_bytes + (size_t)kWarpsThroughput * sizeof(WarpSmem);
-    h->thr_ok = h->thr_smem <= kSmemLimit;
-    if (h->thr_ok)
-        CU_TRY(h, cudaFuncSetAttribute(KERNEL_THR, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->thr_smem));
-    h->lanes_ok = lanes_ok;
-    h->lanes_smem = 16 + (size_t)m.table_bytes;
-    h->lanes_smem_ok = h->lanes_smem <= kSmemLimit;
-    if (h->lanes_smem_ok)
-        CU_TRY(h, cudaFuncSetAttribute(KERNEL_LANES_SMEM, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)h->lanes_smem));
     h->has_mpa = true;
     h->staged = false;
     return PDMPC_OK;
@@ -678,8 +652,6 @@ int pdmpc_stage_batch(pdmpc_handle *h, const pdmpc_batch_in *in) {
     b.lane_ptr = (const int *)dptr[11]; b.lane_x = (const double *)dptr[12]; b.lane_y = (const double *)dptr[13];
     b.order = n > 1 ? (const int *)dptr[14] : nullptr;
     b.pl_x = b.pl_y = b.ll_x = b.ll_y = nullptr;
-    b.pl_xy = b.ll_xy = nullptr;
-    b.rng = nullptr;
     h->stats.kernel_launches = 0;
     if (in->checker == PDMPC_CHECKER_INTERX) {
         // NaN-separated polylines (vectorize_all_obstacles.m) built on the device
@@ -696,25 +668,6 @@ int pdmpc_stage_batch(pdmpc_handle *h, const pdmpc_batch_in *in) {
             build_polyline_kernel<<<(2 * n + 127) / 128, 128, 0, h->stream>>>(
                 2 * n, b.lane_ptr, b.lane_x, b.lane_y, h->b_llx.as<double>(), h->b_lly.as<double>());
             h->stats.kernel_launches++;
-        }
-        b.pl_xy = b.ll_xy = nullptr;
-        b.rng = nullptr;
-        if (h->lanes_ok && n && h->variant_mode == 3) {   // only the lane-per-search shape reads these
-            CU_TRY(h, h->b_plxy.reserve(((size_t)nv + np + 1) * sizeof(double2)));
-            CU_TRY(h, h->b_llxy.reserve(((size_t)nl + 2 * n + 1) * sizeof(double2)));
-            CU_TRY(h, h->b_rng.reserve((size_t)n * (Hp + 2) * sizeof(int)));
-            if (np) {
-                build_polyline_xy_kernel<<<(np + 127) / 128, 128, 0, h->stream>>>(
-                    np, b.poly_ptr, b.vert_x, b.vert_y, h->b_plxy.as<double2>());
-                h->stats.kernel_launches++;
-            }
-            build_polyline_xy_kernel<<<(2 * n + 127) / 128, 128, 0, h->stream>>>(
-                2 * n, b.lane_ptr, b.lane_x, b.lane_y, h->b_llxy.as<double2>());
-            build_ranges_kernel<<<(n * (Hp + 2) + 127) / 128, 128, 0, h->stream>>>(
-                n, Hp, b.slot_ptr, b.poly_ptr, h->b_rng.as<int>());
-            h->stats.kernel_launches += 2;
-            b.pl_xy = h->b_plxy.as<double2>(); b.ll_xy = h->b_llxy.as<double2>();
-            b.rng = h->b_rng.as<int>();
         }
         CU_TRY(h, cudaGetLastError());
         b.pl_x = h->b_plx.as<double>(); b.pl_y = h->b_ply.as<double>();
@@ -749,88 +702,68 @@ static int ensure_arena(pdmpc_handle *h, int slots) {
     return PDMPC_OK;
 }
 
-static int ensure_lane_arena(pdmpc_handle *h, int slots) {
-    const int cap = h->lane_node_cap;
-    if (slots <= h->larena_slots && cap == h->larena.cap) return PDMPC_OK;
-    slots = std::max(slots, h->larena_slots);
-    const size_t tot = (size_t)slots * cap;
-    CU_TRY(h, h->la_a.reserve(tot * sizeof(NodeA)));
-    CU_TRY(h, h->la_b.reserve(tot * sizeof(NodeB)));
-    CU_TRY(h, h->la_cs.reserve(tot * sizeof(NodeCS)));
-    CU_TRY(h, h->la_heap.reserve(tot * sizeof(HEnt)));
-    h->larena.a = h->la_a.as<NodeA>();
-    h->larena.b = h->la_b.as<NodeB>();
-    h->larena.cs = h->la_cs.as<NodeCS>();
-    h->larena.heap = h->la_heap.as<HEnt>();
-    h->larena.cap = cap;
-    h->larena_slots = slots;
+// ---- warp-level launch shapes -------------------------------------------------------------------------
+//   1 latency   one search per one-warp CTA (search_kernel): every checker, pop traces, dependencies
+//   2 tiles     two searches per warp  (search_tile_kernel<16>): InterX batches, the throughput shape
+//   3 tiles     four searches per warp (search_tile_kernel<8>)
+// Arena slots (concurrently running searches) and grid of shape `shape` for n searches.
+static int warp_shape_grid(const pdmpc_handle *h, int shape, int n, int *slots) {
+    if (shape == 2 || shape == 3) {
+        const int T = shape == 2 ? 2 : 4;
+        const int grid = std::max(1, std::min((n + T - 1) / T, h->num_sms * h->tile_ctas_per_sm[shape - 2]));
+        *slots = grid * T;
+        return grid;
+    }
+    const int grid = std::max(1, std::min(n, h->num_sms * h->lat_ctas_per_sm));
+    *slots = grid;
+    return grid;
+}
+
+// The shape a batch of n searches runs in when the caller asked for `variant` (0 = choose).
+static int resolve_warp_shape(const pdmpc_handle *h, int variant, int n, int checker, bool tracing) {
+    if (tracing) return 1;   // pop traces come from the one-search-per-warp kernel
+    if (variant == 0) {
+        // more searches than the latency shape keeps in flight: share the warps (profiles/r02a_*)
+        variant = n > h->num_sms * h->lat_ctas_per_sm ? 2 : 1;
+    }
+    if ((variant == 2 || variant == 3) && (checker != PDMPC_CHECKER_INTERX || h->tile_ctas_per_sm[variant - 2] < 1))
+        variant = 1;         // the tile shapes hold the InterX checker only
+    return variant;
+}
+
+// One persistent launch of shape 1..3 over batch `bc` on stream S with arena `ar` (sized by warp_shape_grid).
+static int launch_warp_shape(pdmpc_handle *h, int shape, const BatchDev &bc, const ArenaDev &ar, unsigned *wc,
+                             const TraceDev &tr, cudaStream_t S) {
+    int slots = 0;
+    const int grid = warp_shape_grid(h, shape, bc.n, &slots);
+    if (shape == 2) KERNEL_TILE2<<<grid, kWarp, kTile2Smem, S>>>(h->mpa, bc, h->out, ar, wc, tr, h->tile_pts_limit);
+    else if (shape == 3) KERNEL_TILE4<<<grid, kWarp, kTile4Smem, S>>>(h->mpa, bc, h->out, ar, wc, tr, h->tile_pts_limit);
+    else KERNEL_LAT<<<grid, kWarp, sizeof(WarpSmem), S>>>(h->mpa, bc, h->out, ar, wc, tr);
+    if (cudaGetLastError() != cudaSuccess) return fail(h, PDMPC_ERR_CUDA, "search kernel launch failed");
+    h->stats.kernel_launches++;
     return PDMPC_OK;
 }
 
-// Launches the search of the staged batch.  Shapes (results are identical for all):
-//   1 latency    one warp-CTA per search slot, MPA tables through L1/L2
-//   2 throughput one 16-warp CTA per SM, tables TMA-staged in shared memory
-//   3 lanes      one THREAD per search (pdmpc_lanes.cuh), then shape 1 over the searches the
-//                threads handed over (count known only on the device)
+// Launches the search of the staged batch (results are identical for all shapes):
+//   1..3 see above;  4 / 5 one CTA per search (pdmpc_cta.cuh), chosen for at most one search per SM
 static int launch_search(pdmpc_handle *h, const TraceDev &tr) {
     const int n = h->batch.n;
     CU_TRY(h, cudaSetDevice(h->device));
     CU_TRY(h, cudaMemsetAsync(h->out.counters, 0, 16 * sizeof(unsigned long long), h->stream));
     CU_TRY(h, cudaMemsetAsync(h->work_counter.p, 0, sizeof(unsigned), h->stream));
+    h->stats.handed_over = 0;
+    h->stats.shape = 0;
     if (n == 0) return PDMPC_OK;
-    const bool lanes_possible = h->lanes_ok && h->batch.checker == PDMPC_CHECKER_INTERX && h->batch.rng;
     int variant = h->variant_mode;
-    if (tr.search >= 0) variant = 1;   // pop traces come from the warp kernel
-    if (variant == 0) {
-        // measured on B200 (profiles/r01b_variants.txt): the warp-per-search shapes beat the
-        // lane-per-search shape at every batch size of the BASELINE configs (the hand-over
-        // stage costs more than the lane stage saves), so shape 3 is opt-in only
-        variant = (h->thr_ok && n >= 4 * h->num_sms) ? 2 : 1;
-        // fewer searches than SMs (one computation level of a time step): one CTA per search,
-        // edge checks spread over checker warps (profiles/r01e_cta_latency.txt)
-        if (n <= h->num_sms) variant = 4;   // (shape 5, the valid-only queue, measured no faster: opt-in)
-    }
+    if (variant == 0 && n <= h->num_sms && tr.search < 0) variant = 4;   // one computation level of a time step
     if (variant == 4 || variant == 5) {
         const int cap = h->user_node_cap ? h->user_node_cap : std::min(h->full_tree_nodes + 8, 1 << 20);
-        if (!h->cta_ok || cap > kCtaFlags) variant = 1;   // validity flags of a whole tree must fit in shared memory
+        if (!h->cta_ok || cap > kCtaFlags || tr.search >= 0) variant = 1;   // validity flags of a whole tree must fit in shared memory
     }
-    if (variant == 3 && !lanes_possible) variant = 2;
-    if (variant == 2 && !h->thr_ok) variant = 1;
+    if (variant < 4) variant = resolve_warp_shape(h, variant, n, h->batch.checker, tr.search >= 0);
     unsigned *wc = h->work_counter.as<unsigned>();
-    h->timing_pending_lanes = false;
-    h->stats.lanes_ms = 0.0;
-    h->stats.handed_over = 0;
-    if (variant == 3) {
-        const int grid = std::min((n + kLaneThreads - 1) / kLaneThreads, h->num_sms);
-        int rc = ensure_lane_arena(h, grid * kLaneThreads);
-        if (rc != PDMPC_OK) return rc;
-        const int grid2 = std::min(n, h->num_sms * h->lat_ctas_per_sm);
-        rc = ensure_arena(h, grid2);
-        if (rc != PDMPC_OK) return rc;
-        CU_TRY(h, h->ov_count.reserve(sizeof(unsigned)));
-        CU_TRY(h, h->ov_list.reserve((size_t)n * sizeof(int)));
-        CU_TRY(h, h->work_counter2.reserve(sizeof(unsigned)));
-        CU_TRY(h, cudaMemsetAsync(h->ov_count.p, 0, sizeof(unsigned), h->stream));
-        CU_TRY(h, cudaMemsetAsync(h->work_counter2.p, 0, sizeof(unsigned), h->stream));
-        LaneLimits lim{h->lane_pop_limit, h->ov_count.as<unsigned>(), h->ov_list.as<int>()};
-        CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
-        if (h->lanes_smem_ok)
-            KERNEL_LANES_SMEM<<<grid, kLaneThreads, h->lanes_smem, h->stream>>>(
-                h->mpa, h->m_apx.as<double>(), h->m_apy.as<double>(), h->batch, h->out, h->larena, wc, lim);
-        else
-            KERNEL_LANES_GMEM<<<grid, kLaneThreads, 0, h->stream>>>(
-                h->mpa, h->m_apx.as<double>(), h->m_apy.as<double>(), h->batch, h->out, h->larena, wc, lim);
-        CU_TRY(h, cudaGetLastError());
-        CU_TRY(h, cudaEventRecord(h->ev[6], h->stream));
-        h->timing_pending_lanes = true;
-        // second stage: the handed-over searches, from scratch, with full-tree arenas
-        BatchDev b2 = h->batch;
-        b2.order = h->ov_list.as<int>();
-        KERNEL_LAT<<<grid2, kWarp, sizeof(WarpSmem), h->stream>>>(h->mpa, b2, h->out, h->arena,
-                                                                 h->work_counter2.as<unsigned>(), tr,
-                                                                 h->ov_count.as<unsigned>());
-        h->stats.kernel_launches++;
-    } else if (variant == 4 || variant == 5) {
+    h->stats.shape = variant;
+    if (variant == 4 || variant == 5) {
         const int grid = std::min(n, h->num_sms);
         int rc = ensure_arena(h, grid);
         if (rc != PDMPC_OK) return rc;
@@ -838,24 +771,19 @@ static int launch_search(pdmpc_handle *h, const TraceDev &tr) {
         KERNEL_CTA<<<grid, (kCtaHelpers + kCtaHelpers / 3) * kWarp, sizeof(CtaSmemT), h->stream>>>(h->mpa, h->batch, h->out,
                                                                                     h->arena, wc, h->cta_heap_smem,
                                                                                     variant == 5 ? 1 : 0, DepsDev{});
-    } else if (variant == 2) {
-        const int grid = std::min((n + kWarpsThroughput - 1) / kWarpsThroughput, h->num_sms);
-        int rc = ensure_arena(h, grid * kWarpsThroughput);
-        if (rc != PDMPC_OK) return rc;
-        CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
-        KERNEL_THR<<<grid, kWarpsThroughput * kWarp, h->thr_smem, h->stream>>>(h->mpa, h->batch, h->out, h->arena, wc,
-                                                                             tr, nullptr);
+        CU_TRY(h, cudaGetLastError());
+        h->stats.kernel_launches++;
     } else {
-        const int grid = std::min(n, h->num_sms * h->lat_ctas_per_sm);
-        int rc = ensure_arena(h, grid);
+        int slots = 0;
+        warp_shape_grid(h, variant, n, &slots);
+        int rc = ensure_arena(h, slots);
         if (rc != PDMPC_OK) return rc;
         CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
-        KERNEL_LAT<<<grid, kWarp, sizeof(WarpSmem), h->stream>>>(h->mpa, h->batch, h->out, h->arena, wc, tr, nullptr);
+        rc = launch_warp_shape(h, variant, h->batch, h->arena, wc, tr, h->stream);
+        if (rc != PDMPC_OK) return rc;
     }
-    CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
     h->timing_pending_kernel = true;
-    h->stats.kernel_launches++;
     return PDMPC_OK;
 }
 
@@ -1011,14 +939,12 @@ static int plan_batch_pipelined(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc
     rc = ensure_pinned(h, &h->pin_order, &h->pin_order_cap, (size_t)n * sizeof(int));
     if (rc != PDMPC_OK) return rc;
     CU_TRY(h, h->wc_chunks.reserve(kPipelineMaxChunks * sizeof(unsigned)));
-    // one-warp CTAs leave an SM one by one as their searches end, so the next chunk's CTAs move in early; the
-    // 16-warp shape holds its SM until its slowest warp is done (only on request)
-    const bool thr = h->thr_ok && h->variant_mode == 2;
+    // one-warp CTAs leave an SM one by one as their searches end, so the next chunk's CTAs move in early
     constexpr int kLanes = 8;   // most concurrent chunk kernels (streams, arenas)
     const int per_chunk = (n + C - 1) / C;
-    const int grid = thr ? std::min((per_chunk + kWarpsThroughput - 1) / kWarpsThroughput, h->num_sms)
-                         : std::min(per_chunk, h->num_sms * h->lat_ctas_per_sm);
-    const int slots = thr ? grid * kWarpsThroughput : grid;
+    const int shape = resolve_warp_shape(h, h->variant_mode, per_chunk, in->checker, false);
+    int slots = 0;
+    warp_shape_grid(h, shape, per_chunk, &slots);
     int lanes = std::min(C, kLanes);
     {   // node arenas of all lanes within 32 GiB
         const int cap = std::max(64, std::min(h->user_node_cap ? h->user_node_cap : std::min(h->full_tree_nodes + 8, 1 << 20),
@@ -1047,15 +973,12 @@ static int plan_batch_pipelined(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc
     b.order = h->b_order.as<int>();
     b.pl_x = interx ? h->b_plx.as<double>() : nullptr; b.pl_y = interx ? h->b_ply.as<double>() : nullptr;
     b.ll_x = interx ? h->b_llx.as<double>() : nullptr; b.ll_y = interx ? h->b_lly.as<double>() : nullptr;
-    b.pl_xy = b.ll_xy = nullptr;
-    b.rng = nullptr;
     h->n_polys = np; h->n_verts = nv; h->n_lane = nl;
     h->stats.h2d_bytes = 0;
     h->stats.d2h_bytes = 0;
     h->stats.kernel_launches = 0;
-    h->stats.lanes_ms = 0.0;
     h->stats.handed_over = 0;
-    h->timing_pending_lanes = false;
+    h->stats.shape = shape;
 
     CU_TRY(h, cudaMemsetAsync(h->out.counters, 0, 16 * sizeof(unsigned long long), h->stream));
     CU_TRY(h, cudaMemsetAsync(h->wc_chunks.p, 0, kPipelineMaxChunks * sizeof(unsigned), h->stream));
@@ -1136,14 +1059,8 @@ static int plan_batch_pipelined(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc
         bc.n = s1 - s0;
         bc.order = h->b_order.as<int>() + s0;
         unsigned *wc = h->wc_chunks.as<unsigned>() + c;
-        if (thr) {
-            const int g = std::min((bc.n + kWarpsThroughput - 1) / kWarpsThroughput, h->num_sms);
-            KERNEL_THR<<<g, kWarpsThroughput * kWarp, h->thr_smem, S>>>(h->mpa, bc, h->out, ar[c % lanes], wc, tr, nullptr);
-        } else {
-            const int g = std::min(bc.n, h->num_sms * h->lat_ctas_per_sm);
-            KERNEL_LAT<<<g, kWarp, sizeof(WarpSmem), S>>>(h->mpa, bc, h->out, ar[c % lanes], wc, tr, nullptr);
-        }
-        h->stats.kernel_launches++;
+        if (launch_warp_shape(h, shape, bc, ar[c % lanes], wc, tr, S) != PDMPC_OK)
+            return bail(PDMPC_ERR_CUDA);
         if (cudaGetLastError() != cudaSuccess || cudaEventRecord(ev_done, S) != cudaSuccess ||
             cudaStreamWaitEvent(h->s_out, ev_done, 0) != cudaSuccess)
             return bail(fail(h, PDMPC_ERR_CUDA, "pipeline: search kernel launch failed"));
@@ -1187,7 +1104,7 @@ int pdmpc_set_pipeline_chunks(pdmpc_handle *h, int32_t chunks) {
 }
 
 int pdmpc_plan_batch(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc_batch_out *out) {
-    if (h && in && h->has_mpa && h->pipeline_chunks != 1 && h->variant_mode <= 2 &&
+    if (h && in && h->has_mpa && h->pipeline_chunks != 1 && h->variant_mode <= 3 &&
         (h->pipeline_chunks > 1 ? in->n_searches >= 2 * h->pipeline_chunks : in->n_searches >= kPipelineMinSearches)) {
         const int C = h->pipeline_chunks > 1 ? h->pipeline_chunks : std::min(12, std::max(2, in->n_searches / kPipelineMinSearches));   // measured: profiles/r01h_pipeline.txt
         return plan_batch_pipelined(h, in, out, C);
@@ -1323,12 +1240,10 @@ int pdmpc_plan_timestep(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_t
     else
         KERNEL_LAT_DEPS<<<grid, kWarp, sizeof(WarpSmem), h->stream>>>(h->mpa, h->batch, h->out, h->arena,
                                                                       h->work_counter.as<unsigned>(),
-                                                                      TraceDev{-1, nullptr, 0, nullptr}, nullptr, dp);
+                                                                      TraceDev{-1, nullptr, 0, nullptr}, dp);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
     h->timing_pending_kernel = true;
-    h->timing_pending_lanes = false;
-    h->stats.lanes_ms = 0.0;
     h->stats.handed_over = 0;
     h->stats.kernel_launches++;
     return pdmpc_fetch_staged(h, out);
@@ -1377,8 +1292,7 @@ int pdmpc_joint_plan_batch(pdmpc_handle *h, const pdmpc_batch_in *in, int32_t n_
         CU_TRY(h, cudaGetLastError());
         CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
         h->timing_pending_kernel = true;
-        h->timing_pending_lanes = false;
-        h->stats.kernel_launches = 1;
+            h->stats.kernel_launches = 1;
     }
     return pdmpc_fetch_staged(h, out);
 }
@@ -1419,7 +1333,6 @@ int pdmpc_mcts_run_staged(pdmpc_handle *h, const pdmpc_mcts_params *prm) {
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
     h->timing_pending_kernel = true;
-    h->timing_pending_lanes = false;
     h->stats.kernel_launches++;
     return PDMPC_OK;
 }
@@ -1485,12 +1398,6 @@ int pdmpc_get_stats(pdmpc_handle *h, pdmpc_stats *out) {
     if (h->timing_pending_h2d && cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->stats.h2d_ms = ms;
     if (h->timing_pending_kernel && cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) h->stats.kernel_ms = ms;
     if (h->timing_pending_d2h && cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]) == cudaSuccess) h->stats.d2h_ms = ms;
-    if (h->timing_pending_lanes) {
-        if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[6]) == cudaSuccess) h->stats.lanes_ms = ms;
-        unsigned ov = 0;
-        if (cudaMemcpy(&ov, h->ov_count.p, sizeof(ov), cudaMemcpyDeviceToHost) == cudaSuccess)
-            h->stats.handed_over = (int32_t)ov;
-    }
     *out = h->stats;
     return PDMPC_OK;
 }

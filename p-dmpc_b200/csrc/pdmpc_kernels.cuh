@@ -1,9 +1,9 @@
-// pdmpc_kernels.cuh — device code of the B200-native MPA graph search.
+// pdmpc_kernels.cuh — device code of the B200-native MPA graph search: shared device types, the
+// checkers, and the one-search-per-warp kernel (lowest-latency warp shape; also the carrier of pop
+// traces, the SAT checker and the time-step dependencies).  The throughput shape — several searches per
+// warp — is pdmpc_tiles.cuh, the one-CTA-per-search shape pdmpc_cta.cuh.
 //
-// Each search (vehicle x permutation x scenario) is run by one TILE of a warp
-// (TILE = 32: one search per one-warp CTA, lowest latency; TILE = 16 / 8: 2 / 4
-// searches share the warp's instruction stream, highest throughput) and
-// reproduces the reference's best-first loop exactly:
+// Every shape reproduces the reference's best-first loop exactly:
 //   GraphSearch.do_graph_search      hlc/optimizer/graph_search/GraphSearch.m:23-109
 //   eval_edge_exact                  GraphSearch.m:111-196
 //   expand_node                      hlc/optimizer/graph_search/expand_node.m:1-91
@@ -22,16 +22,13 @@
 //     loop (one aligned pair load + one compare per level), the moves along the path are
 //     done by the lanes in parallel.  Pushes of all children go through a one-round fast
 //     path when no child has to sift up.  The resulting array is identical to what
-//     libstdc++'s sequential routines produce.  (`Heap` below is the earlier cooperative
-//     4-level look-ahead walk, kept for the microbenchmark: 2.2x slower per pop.)
+//     libstdc++'s sequential routines produce.
 //   * heap entries carry (f, id, parent id): everything a pop needs is fetched in
 //     ONE round of independent loads (own record + parent record).
 //   * sin/cos of a node's yaw is computed once, when the node is expanded, and
 //     cached for the edge checks of its children.
 //   * the per-search obstacle polylines (lanelet bounds + all steps' obstacle
 //     polygons) are staged once into shared memory; InterX then runs out of smem.
-//   * InterX: lanes are (point slot, pair of shape edges), so a lane keeps two
-//     edges' constants in registers; C2 is evaluated only where C1 holds.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -68,9 +65,8 @@ constexpr int kMaxHp = PDMPC_MAX_HP;
 constexpr int kParentCache = 32;   // entries, power of two
 
 // ---- device views -----------------------------------------------------------
-// MPA tables as the kernel reads them.  All arrays are 16-byte aligned and their
-// byte sizes are multiples of 16 so that one TMA bulk copy each stages them in
-// shared memory (throughput variant); the latency variant reads them from global.
+// MPA tables as the kernels read them (through L1/L2: 10-73 KB, hot in every SM's L1).  All arrays
+// are 16-byte aligned.
 struct MpaDev {
     int nT, Hp, nE;
     const int *succ_ptr;        // [Hp*nT + 1] successors of (step k, trim t) at (k-1)*nT + (t-1)
@@ -100,10 +96,6 @@ struct BatchDev {
     const int *lane_ptr;
     const double *lane_x, *lane_y;
     const double *ll_x, *ll_y;
-    // the same polylines as (x, y) pairs and the per-search polyline offsets of obstacle
-    // slots 0..Hp+1 (lane-per-search kernel, pdmpc_lanes.cuh)
-    const double2 *pl_xy, *ll_xy;
-    const int *rng;
 };
 
 struct OutDev {
@@ -239,146 +231,8 @@ __device__ __forceinline__ void sincos_ref(double x, double &s, double &c) {
     else { s = -cr; c = sr; }
 }
 
-// ---- priority queue ---------------------------------------------------------
-// libstdc++ heap on (f, id), min on f, ties by heap mechanics (stl_heap.h
-// __push_heap :135-147, __adjust_heap :224-249), executed by the whole tile.
-// Entries [0, HS) live in shared memory (the top levels of the array heap are
-// the hottest), the rest in the slot's HBM overflow.  `len` is tile-uniform.
-template <int HS, int TILE>
-struct Heap {
-    static constexpr int LV = 4;                   // levels fetched per round: 2+4+8+16 entries
-    static constexpr int NL = 30;
-    HEnt *sm;
-    HEnt *gl;
-    int len;
-
-    __device__ __forceinline__ HEnt load(int i) const { return i < HS ? sm[i] : gl[i]; }
-    __device__ __forceinline__ void store(int i, const HEnt &e) {
-        if (i < HS) sm[i] = e;
-        else gl[i] = e;
-    }
-
-    // __push_heap(first, p, 0, v): ancestors of p with f > v.f move down one level,
-    // v lands above them.  All lanes hold v; entries are consistent in memory.
-    __device__ __forceinline__ void sift_up_at(int p, const HEnt &v, const Tile<TILE> &t) {
-        const int D = 31 - __clz(p + 1);               // number of ancestors of position p
-        int base = 0, T = 0;
-        for (;;) {
-            const int a = base + t.lane + 1;           // this lane's ancestor, `a` levels up
-            const bool anc = a <= D;
-            HEnt e;
-            e.f = 0.0; e.w = 0;
-            if (anc) e = load(((p + 1) >> a) - 1);
-            const unsigned gt = t.ballot(anc && e.f > v.f);
-            const int run = (gt == Tile<TILE>::kBits) ? TILE : (__ffs(~gt) - 1);   // leading run of greater parents
-            t.sync();
-            if (t.lane < run) store(((p + 1) >> (a - 1)) - 1, e);
-            T = base + run;
-            if (run < TILE || base + TILE >= D) break;
-            base += TILE;
-            t.sync();
-        }
-        if (t.lane == 0) store(((p + 1) >> T) - 1, v);
-    }
-
-    // pq.pop(): returns the top entry; caller guarantees len > 0.
-    __device__ __forceinline__ HEnt pop(const Tile<TILE> &t) {
-        static_assert(TILE == kWarp, "one warp per search");
-        const HEnt top = load(0);
-        const int n = len - 1;   // heap size after the pop; entry[n] is re-inserted
-        if (n > 0) {
-            const HEnt v = load(n);
-            t.sync();            // every lane has read top / v before any entry moves
-            // lane <-> descendant of the hole (level d = 1..4 below it, offset o) for lanes 0..29
-            const int d = 31 - __clz(t.lane + 2);
-            const int o = t.lane + 2 - (1 << d);
-            int hole = 0, sel = 0;
-            double fsel = 0.0;
-            bool moved = false;
-            const int lim = (n - 1) / 2;
-            while (hole < lim) {
-                const int idx = ((hole + 1) << d) - 1 + o;
-                HEnt e;
-                e.f = 0.0; e.w = 0;
-                if (t.lane < NL && idx < n) e = load(idx);
-                // sibling pairs are lanes (2r, 2r+1): the right one is taken unless f_right > f_left
-                const double fs = t.shfl_xor(e.f, 1);
-                const bool pick = (t.lane & 1) ? !(e.f > fs) : (fs > e.f);
-                const unsigned picks = t.ballot(pick);
-                int rel = 0;
-                bool on = false;
-#pragma unroll
-                for (int lv = 1; lv <= LV; ++lv) {
-                    if (hole < lim) {   // both children exist
-                        const int left = (1 << lv) - 2 + 2 * rel;
-                        const int right = (picks >> (left + 1)) & 1;
-                        sel = left + right;
-                        on = on || (t.lane == sel);
-                        hole = 2 * hole + 1 + right;
-                        rel = 2 * rel + right;
-                    }
-                }
-                if (on) store((idx - 1) >> 1, e);      // every picked child moves into its parent's place
-                fsel = e.f;
-                moved = true;
-            }
-            double lastf = moved ? t.shfl(fsel, sel) : 0.0;   // f of the last entry that moved up
-            if ((n & 1) == 0 && hole == (n - 2) / 2) {   // single (left) child at n-1
-                const HEnt e = load(n - 1);
-                if (t.lane == 0) store(hole, e);
-                lastf = e.f;
-                hole = n - 1;
-                moved = true;
-            }
-            if (!moved || !(lastf > v.f)) {
-                if (t.lane == 0) store(hole, v);
-            } else {
-                t.sync();
-                sift_up_at(hole, v, t);
-            }
-        }
-        len = n;
-        t.sync();
-        return top;
-    }
-
-    // pq.push of m <= TILE entries in lane order (lane q holds entry q).  Children
-    // that need no sift-up are appended together; the first one that does is
-    // pushed on its own, then the rest is retried.
-    __device__ __forceinline__ void push_many(const HEnt &mine, int m, const Tile<TILE> &t) {
-        int done = 0;
-        while (done < m) {
-            const bool act = t.lane >= done && t.lane < m;
-            const int p = len + (t.lane - done);
-            const int par = (p - 1) >> 1;
-            bool need = false;
-            const int src = done + max(par - len, 0);
-            const double nf = t.shfl(mine.f, src & (TILE - 1));
-            if (act && p > 0) {
-                const double pf = (par < len) ? load(par).f : nf;
-                need = pf > mine.f;
-            }
-            const unsigned mask = t.ballot(need);
-            const int nfast = mask ? (__ffs(mask) - 1 - done) : (m - done);
-            if (act && t.lane < done + nfast) store(p, mine);
-            len += nfast;
-            done += nfast;
-            t.sync();
-            if (done < m) {
-                HEnt v;
-                v.f = t.shfl(mine.f, done);
-                v.w = t.shfl(mine.w, done);
-                sift_up_at(len, v, t);
-                ++len;
-                ++done;
-                t.sync();
-            }
-        }
-    }
-};
-
 }  // namespace pdmpc
-#include "pdmpc_heap_split.cuh"   // HeapSplit: the layout + pop the kernels use (2x faster pop than Heap)
+#include "pdmpc_heap_split.cuh"   // HeapSplit: the priority queue (libstdc++ heap order, exact array states)
 namespace pdmpc {
 
 // ---- InterX (InterX.m:63-85,108-110) ---------------------------------------
@@ -569,33 +423,6 @@ __device__ __forceinline__ void place_point(const Tables &tb, int edge, int kind
     oy = s * ax + c * ay + py;
 }
 
-// ---- TMA bulk copy (global -> shared) + mbarrier, sm_90+/sm_100 PTX -----------
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@!p bra WAIT_%=;\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-
 template <int HS, int SP>
 struct __align__(16) TileSmem {
     double hf[HS + 2];                           // heap costs, entry i at hf[i + 1] (pdmpc_heap_split.cuh)
@@ -613,63 +440,27 @@ struct __align__(16) TileSmem {
 };
 
 // ============================================================================
-// The search kernel.  Persistent: every warp owns one arena slot and pulls work
-// items from a global counter until the batch is drained.  The body is ONE loop
-// (a small state machine): an iteration is "finish / fetch a search if needed,
-// then one pop".
-//
-// Two launch shapes of the same code:
-//   latency    (WARPS = 1, SMEM_TABLES = false): one warp per CTA, MPA tables read
-//              through L1/L2; used when the batch cannot fill the GPU anyway.
-//   throughput (WARPS = 16, SMEM_TABLES = true): one 16-warp CTA per SM; the MPA
-//              tables are staged once per CTA into shared memory by TMA bulk copies
-//              (cp.async.bulk + mbarrier), each warp still runs its own searches.
+// The one-search-per-warp kernel.  Persistent: every one-warp CTA owns one arena slot and pulls
+// work items from a global counter until the batch is drained.  The body is ONE loop (a small
+// state machine): an iteration is "finish / fetch a search if needed, then one pop".
 #ifndef PDMPC_MIN_CTAS_LAT
-#define PDMPC_MIN_CTAS_LAT 12  // resident one-warp CTAs per SM the latency shape is compiled for (register cap)
+#define PDMPC_MIN_CTAS_LAT 12  // resident one-warp CTAs per SM the kernel is compiled for (register cap)
 #endif
 // DEPS (pdmpc_plan_timestep for batches beyond one CTA per search): a search waits for its predecessors'
 // done flags, copies their planned (or fallback) areas into its slot's scratch and checks against them;
 // work items are handed out in a topological order, so a warp only ever waits for searches taken earlier.
-template <int HS, int SP, int WARPS, bool SMEM_TABLES, bool DEPS = false>
-__global__ void __launch_bounds__(WARPS *kWarp, WARPS == 1 ? PDMPC_MIN_CTAS_LAT : 1) search_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar,
+template <int HS, int SP, bool DEPS = false>
+__global__ void __launch_bounds__(kWarp, PDMPC_MIN_CTAS_LAT) search_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar,
                                                               unsigned *work_counter, TraceDev tr,
-                                                              const unsigned *n_work_dev, DepsDev dp = DepsDev{}) {
+                                                              DepsDev dp = DepsDev{}) {
     constexpr int TILE = kWarp;
-    // number of work items: the whole batch, or (second stage after the lane-per-search
-    // kernel) the length of the hand-over list b.order, known only on the device
-    const unsigned n_work = n_work_dev ? *n_work_dev : (unsigned)b.n;
+    constexpr int WARPS = 1;
+    const unsigned n_work = (unsigned)b.n;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Tables tb;
     unsigned char *warp_base = smem_raw;
-    if (SMEM_TABLES) {
-        // [mbarrier | succ_ptr | succ_te | edge_d | area_npts | area_x | area_y | per-warp state]
-        unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem_raw);
-        unsigned char *q = smem_raw + 16;
-        int *s_succ_ptr = reinterpret_cast<int *>(q); q += m.bytes_succ_ptr;
-        int *s_succ_te = reinterpret_cast<int *>(q); q += m.bytes_succ_te;
-        double *s_edge_d = reinterpret_cast<double *>(q); q += m.bytes_edge_d;
-        int *s_area_npts = reinterpret_cast<int *>(q); q += m.bytes_area_npts;
-        double *s_area_x = reinterpret_cast<double *>(q); q += m.bytes_area;
-        double *s_area_y = reinterpret_cast<double *>(q); q += m.bytes_area;
-        warp_base = q;
-        if (threadIdx.x == 0) {
-            mbar_init(bar, 1);
-            mbar_expect_tx(bar, m.table_bytes);
-            tma_bulk_g2s(s_succ_ptr, m.succ_ptr, m.bytes_succ_ptr, bar);
-            tma_bulk_g2s(s_succ_te, m.succ_te, m.bytes_succ_te, bar);
-            tma_bulk_g2s(s_edge_d, m.edge_d, m.bytes_edge_d, bar);
-            tma_bulk_g2s(s_area_npts, m.area_npts, m.bytes_area_npts, bar);
-            tma_bulk_g2s(s_area_x, m.area_x, m.bytes_area, bar);
-            tma_bulk_g2s(s_area_y, m.area_y, m.bytes_area, bar);
-        }
-        __syncthreads();          // barrier initialised before anyone polls it
-        mbar_wait(bar, 0);        // all table bytes have landed
-        tb.succ_ptr = s_succ_ptr; tb.succ_te = s_succ_te; tb.edge_d = s_edge_d;
-        tb.area_npts = s_area_npts; tb.area_x = s_area_x; tb.area_y = s_area_y;
-    } else {
-        tb.succ_ptr = m.succ_ptr; tb.succ_te = m.succ_te; tb.edge_d = m.edge_d;
-        tb.area_npts = m.area_npts; tb.area_x = m.area_x; tb.area_y = m.area_y;
-    }
+    tb.succ_ptr = m.succ_ptr; tb.succ_te = m.succ_te; tb.edge_d = m.edge_d;
+    tb.area_npts = m.area_npts; tb.area_x = m.area_x; tb.area_y = m.area_y;
     const int warp_id = threadIdx.x / kWarp;
     TileSmem<HS, SP> &sm = reinterpret_cast<TileSmem<HS, SP> *>(warp_base)[warp_id];
 
@@ -683,23 +474,12 @@ __global__ void __launch_bounds__(WARPS *kWarp, WARPS == 1 ? PDMPC_MIN_CTAS_LAT 
     NodeA *__restrict__ na = ar.a + slot_base;
     NodeB *__restrict__ nb = ar.b + slot_base;
     NodeCS *__restrict__ ncs = ar.cs + slot_base;
-#ifdef PDMPC_COOP_HEAP   // comparison builds only: the earlier cooperative look-ahead heap
-    struct CoopHeap : Heap<HS, TILE> {
-        __device__ __forceinline__ void st(int i, const HEnt &e) { this->store(i, e); }
-        __device__ __forceinline__ HEnt pop(int) { Tile<TILE> tt; tt.shift = 0; tt.lane = threadIdx.x % kWarp; tt.mask = 0xffffffffu; return Heap<HS, TILE>::pop(tt); }
-        __device__ __forceinline__ void push_many(const HEnt &m_, int c_, int) { Tile<TILE> tt; tt.shift = 0; tt.lane = threadIdx.x % kWarp; tt.mask = 0xffffffffu; Heap<HS, TILE>::push_many(m_, c_, tt); }
-    } heap;
-    heap.sm = reinterpret_cast<HEnt *>(sm.hf);
-    heap.gl = ar.heap + slot_base;
-    heap.len = 0;
-#else
     HeapSplit heap;
     heap.sf = shared_base_once(sm.hf);
     heap.sw = shared_base_once(sm.hw);
     heap.gl = ar.heap + slot_base;
     heap.hs = HS;
     heap.len = 0;
-#endif
 
     enum { IDLE = 0, RUN = 1, DONE = 2 };
     int phase = IDLE;

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(built):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/pdmpc_b200.h but not exported"
     assert set(names) == set(capi.EXPORTED_SYMBOLS)
-    assert lib.pdmpc_abi_version() == 1
+    assert lib.pdmpc_abi_version() == 2
 
 
 def test_ctypes_structs_match_the_c_layout(tmp_path, built):

@@ -17,8 +17,8 @@ from helpers import GOLDEN_CASES, circle_records, load_golden, rect, road_record
 pytestmark = pytest.mark.gpu
 
 
-# latency / throughput / lane-per-search / CTA-per-search / CTA with valid-only queue: identical results
-# required (shape 5 reports pop_hash over the popped nodes that passed their edge check, pdmpc_b200.h)
+# one search per warp / tiles (2 and 4 searches per warp) / CTA per search / CTA with valid-only queue:
+# identical results required (shape 5 reports pop_hash over the popped nodes that passed their edge check)
 VARIANTS = (1, 2, 3, 4, 5)
 
 
@@ -104,19 +104,22 @@ def test_pop_trace_identical(planner):
         planner.set_variant(0)
 
 
-@pytest.mark.parametrize("nodes,pops", [(64, 0), (0, 6), (128, 40), (0, 0)])
-def test_lane_shape_hand_over(planner, nodes, pops):
-    """Shape 3: threads hand searches that outgrow their slot / pop budget over to the
-    warp-per-search kernel (second launch).  Any split must give the oracle's results."""
+@pytest.mark.parametrize("variant", [2, 3])
+@pytest.mark.parametrize("points", [0, 40, 90, 150])
+def test_tile_shape_unstaged_polylines(planner, variant, points):
+    """Shapes 2, 3: polylines that do not fit a tile's staged points are read from HBM instead (40: neither
+    lanelet bounds nor obstacles staged for most searches; 90 / 150: lanelets staged, obstacles of the crowded
+    searches not).  Any split must give the oracle's results, and the requested shape must really run."""
     mpa, batch = road_records("triple_speed", 8)
-    planner.set_lane_limits(nodes, pops)
+    planner.set_tile_points(points)
     try:
-        info, dev, ref = check(planner, mpa, batch, variants=(3,))
+        info, dev, ref = check(planner, mpa, batch, variants=(variant,))
         assert info["n"] == batch.n
         st = planner.stats()
+        assert st.shape == variant
         assert st.total_pops == int(ref.n_pops.sum()) and st.total_nodes == int(ref.n_expanded.sum())
     finally:
-        planner.set_lane_limits(0, 0)
+        planner.set_tile_points(0)
 
 
 @pytest.mark.parametrize("entries", [2, 16, 64, 0])

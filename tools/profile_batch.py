@@ -28,18 +28,26 @@ def main():
     p = capi.Planner(0)
     p.upload_mpa(mpa)
     p.set_variant(tile)
-    if os.environ.get('PDMPC_LANE_LIMITS'):
-        nodes, pops = (int(x) for x in os.environ['PDMPC_LANE_LIMITS'].split(','))
-        p.set_lane_limits(nodes, pops)
+    if os.environ.get('PDMPC_TILE_POINTS'):
+        p.set_tile_points(int(os.environ['PDMPC_TILE_POINTS']))
     p.stage(b)
     for i in range(runs):
         p.run_staged()
         p.sync()
         st = p.stats()
         print(f"variant {tile} run {i}: {b.n} searches kernel {st.kernel_ms:.3f} ms -> {b.n / st.kernel_ms * 1e3:.0f} plans/s"
-              f" (lane stage {st.lanes_ms:.3f} ms, handed over {st.handed_over})")
+              f" (shape {st.shape}, handed over {st.handed_over})")
     r = p.fetch()
     st = p.stats()
+    if os.environ.get('PDMPC_CHECK'):   # same answers as the one-search-per-warp shape
+        import numpy as np
+        p.set_variant(1)
+        p.run_staged()
+        r1 = p.fetch()
+        for f in ("pop_hash", "n_pops", "n_expanded", "is_exhausted", "trims", "y_predicted", "g_path", "h_path", "shape_x"):
+            a, b_ = getattr(r, f), getattr(r1, f)
+            assert np.array_equal(a, b_, equal_nan=(a.dtype.kind == "f")), f
+        print("identical to shape 1 on", b.n, "searches")
     print("pops", st.total_pops, "nodes", st.total_nodes, "cols", st.total_obstacle_cols,
           "exhausted", int(r.is_exhausted.sum()), "max pops", int(r.n_pops.max()))
 
