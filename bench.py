@@ -375,6 +375,7 @@ def main():
     # Replayed for the first (up to 8) scenarios of the rank, whose records come first.
     lat = []
     lat_levels = 0
+    planner.set_cta_queue(True)   # what the MATLAB drop-in selects: valid-only queue in the CTA-per-search shape
     if rank == 0:
         by_step, off = {}, 0
         for step, _level, cnt in step_recs:
@@ -414,6 +415,8 @@ def main():
         for step, _tb, _td, _pidx, ro, *_ in calls:
             a = np.sort(np.concatenate([r.pop_hash for _lb, r, _i, _o in by_step[step]]))
             assert np.array_equal(a, np.sort(ro.pop_hash)), f"time step {step}: one-call path != level-by-level path"
+
+    planner.set_cta_queue(False)
 
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------
     cpu = None

@@ -207,6 +207,12 @@ int pdmpc_set_node_capacity(pdmpc_handle *h, int32_t max_nodes_per_search);
  * check only in shape 5 (n_pops is exact in every shape). */
 int pdmpc_set_variant(pdmpc_handle *h, int32_t variant);
 
+/* The queue of the CTA shape whenever that shape runs (chosen automatically for small batches and by
+ * pdmpc_plan_timestep, or forced with shape 4): 0 = the reference's lazy queue (default: pop_hash covers every
+ * pop), 1 = the valid-only queue of shape 5 (2-3x lower latency on collision-rich searches; pop_hash covers
+ * the valid pops; pdmpc_stats.shape then reports 5).  The MATLAB drop-in turns it on. */
+int pdmpc_set_cta_queue(pdmpc_handle *h, int32_t valid_only);
+
 /* Shapes 2, 3 only: polyline points (lanelet bounds + obstacles of all steps) a tile stages in shared
  * memory per search (0 = what the kernel holds, 256); polylines beyond it are read from HBM/L2.  Test knob:
  * results do not depend on it. */

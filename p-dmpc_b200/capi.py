@@ -30,7 +30,7 @@ PDMPC_ERR_ALLOC = 5
 
 EXPORTED_SYMBOLS = (
     "pdmpc_create", "pdmpc_destroy", "pdmpc_last_error", "pdmpc_abi_version",
-    "pdmpc_set_node_capacity", "pdmpc_set_variant", "pdmpc_set_tile_points", "pdmpc_host_alloc", "pdmpc_host_free",
+    "pdmpc_set_node_capacity", "pdmpc_set_variant", "pdmpc_set_tile_points", "pdmpc_set_cta_queue", "pdmpc_host_alloc", "pdmpc_host_free",
     "pdmpc_trace_staged", "pdmpc_upload_mpa", "pdmpc_plan_batch", "pdmpc_stage_batch",
     "pdmpc_run_staged", "pdmpc_sync", "pdmpc_fetch_staged", "pdmpc_get_stats", "pdmpc_stream",
     "pdmpc_mcts_plan_batch", "pdmpc_mcts_run_staged", "pdmpc_set_cta_heap_smem", "pdmpc_plan_timestep",
@@ -179,6 +179,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.pdmpc_measure_fp64_peak.restype = C.c_int
     lib.pdmpc_set_pipeline_chunks.argtypes = [H, C.c_int32]
     lib.pdmpc_set_pipeline_chunks.restype = C.c_int
+    lib.pdmpc_set_cta_queue.argtypes = [H, C.c_int32]
+    lib.pdmpc_set_cta_queue.restype = C.c_int
     lib.pdmpc_set_tile_points.argtypes = [H, C.c_int32]
     lib.pdmpc_set_tile_points.restype = C.c_int
     lib.pdmpc_trace_staged.argtypes = [H, C.c_int32, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64)]
@@ -269,6 +271,10 @@ class Planner:
     def set_pipeline_chunks(self, chunks: int = 0):
         """Chunked copy/search pipeline of plan_batch (pdmpc_set_pipeline_chunks); results do not depend on it."""
         self._check(self.lib.pdmpc_set_pipeline_chunks(self.h, int(chunks)))
+
+    def set_cta_queue(self, valid_only: bool):
+        """Valid-only queue whenever the CTA shape runs (pdmpc_set_cta_queue)."""
+        self._check(self.lib.pdmpc_set_cta_queue(self.h, 1 if valid_only else 0))
 
     def set_tile_points(self, points: int = 0):
         """Shapes 2, 3 test knob (pdmpc_set_tile_points); results do not depend on it."""

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -41,13 +42,25 @@ constexpr size_t kSmemLimit = 227 * 1024;
 // tiles: TILE lanes per search; heap entries / staged polyline points per search in shared memory;
 // one-warp CTAs per SM the shape is compiled for (register cap) — sized so that the CTAs fill 228 KB
 #ifndef PDMPC_TILE2_CTAS
-#define PDMPC_TILE2_CTAS 12
+#define PDMPC_TILE2_CTAS 16
 #endif
 #ifndef PDMPC_TILE4_CTAS
 #define PDMPC_TILE4_CTAS 8
 #endif
-constexpr int kTile2Heap = 224, kTile2Pts = 256, kTile2Ctas = PDMPC_TILE2_CTAS;
-constexpr int kTile4Heap = 96, kTile4Pts = 256, kTile4Ctas = PDMPC_TILE4_CTAS;
+#ifndef PDMPC_TILE2_HEAP
+#define PDMPC_TILE2_HEAP 96
+#endif
+#ifndef PDMPC_TILE2_PTS
+#define PDMPC_TILE2_PTS 160
+#endif
+#ifndef PDMPC_TILE4_HEAP
+#define PDMPC_TILE4_HEAP 96
+#endif
+#ifndef PDMPC_TILE4_PTS
+#define PDMPC_TILE4_PTS 256
+#endif
+constexpr int kTile2Heap = PDMPC_TILE2_HEAP, kTile2Pts = PDMPC_TILE2_PTS, kTile2Ctas = PDMPC_TILE2_CTAS;
+constexpr int kTile4Heap = PDMPC_TILE4_HEAP, kTile4Pts = PDMPC_TILE4_PTS, kTile4Ctas = PDMPC_TILE4_CTAS;
 #define KERNEL_TILE2 search_tile_kernel<16, kTile2Heap, kTile2Pts, kTile2Ctas>
 #define KERNEL_TILE4 search_tile_kernel<8, kTile4Heap, kTile4Pts, kTile4Ctas>
 constexpr size_t kTile2Smem = 2 * sizeof(TileSm<kTile2Heap, kTile2Pts>);
@@ -90,6 +103,7 @@ struct pdmpc_handle {
     int tile_pts_limit = 0;           // staged-points limit of the tile shapes (0 = what the kernel holds; test knob)
     int variant_mode = 0;             // 0 = auto, 1 = latency, 2 / 3 = tiles (2 / 4 searches per warp), 4 / 5 = cta
     int cta_heap_smem = kCtaHeap;     // heap entries the CTA shape keeps in shared memory (tuning/test knob)
+    bool cta_valid_only = false;      // pdmpc_set_cta_queue: the CTA shape runs its valid-only queue (shape 5) whenever it is chosen
     bool cta_ok = false;              // the CTA-per-search kernel is launchable (shared memory opt-in granted)
     bool cta_deps_ok = false;         // ... and its pdmpc_plan_timestep instance
     // pdmpc_plan_timestep: dependency CSR, fallback areas, done flags (one packed upload)
@@ -317,6 +331,12 @@ int pdmpc_set_cta_heap_smem(pdmpc_handle *h, int32_t entries) {
     if (entries < 0 || entries > kCtaHeap || (entries & 1))
         return fail(h, PDMPC_ERR_BAD_INPUT, "cta heap: entries must be 0 (default) or an even number <= 4096");
     h->cta_heap_smem = entries ? entries : kCtaHeap;
+    return PDMPC_OK;
+}
+
+int pdmpc_set_cta_queue(pdmpc_handle *h, int32_t valid_only) {
+    if (!h) return PDMPC_ERR_BAD_INPUT;
+    h->cta_valid_only = valid_only != 0;
     return PDMPC_OK;
 }
 
@@ -582,6 +602,9 @@ int pdmpc_stage_batch(pdmpc_handle *h, const pdmpc_batch_in *in) {
     h->deps_staged = false;
     if (n > 1 && (int)h->topo_order.size() == n) {
         order.swap(h->topo_order);   // pdmpc_plan_timestep: a topological order of the dependency DAG
+    } else if (n > 1 && getenv("PDMPC_NO_REORDER")) {   // experiments: work order = batch order
+        order.resize(n);
+        for (int i = 0; i < n; ++i) order[i] = i;
     } else if (n > 1) {
         std::vector<int> key(n);
         order.resize(n);
@@ -760,6 +783,7 @@ static int launch_search(pdmpc_handle *h, const TraceDev &tr) {
         const int cap = h->user_node_cap ? h->user_node_cap : std::min(h->full_tree_nodes + 8, 1 << 20);
         if (!h->cta_ok || cap > kCtaFlags || tr.search >= 0) variant = 1;   // validity flags of a whole tree must fit in shared memory
     }
+    if (variant == 4 && h->cta_valid_only) variant = 5;
     if (variant < 4) variant = resolve_warp_shape(h, variant, n, h->batch.checker, tr.search >= 0);
     unsigned *wc = h->work_counter.as<unsigned>();
     h->stats.shape = variant;
@@ -1233,10 +1257,12 @@ int pdmpc_plan_timestep(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_t
         CU_TRY(h, h->d_depn.reserve((size_t)grid * (kDepCols / kAreaStride) * sizeof(int)));
         dp.dep_x = h->d_depx.as<double>(); dp.dep_y = h->d_depy.as<double>(); dp.dep_n = h->d_depn.as<int>();
     }
+    const bool cta_fast = h->variant_mode == 5 || h->cta_valid_only;
+    h->stats.shape = use_cta ? (cta_fast ? 5 : 4) : 1;
     CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
     if (use_cta)
         KERNEL_CTA_DEPS<<<grid, (kCtaHelpers + kCtaHelpers / 3) * kWarp, sizeof(CtaDepsSmemT), h->stream>>>(
-            h->mpa, h->batch, h->out, h->arena, h->work_counter.as<unsigned>(), h->cta_heap_smem, 0, dp);
+            h->mpa, h->batch, h->out, h->arena, h->work_counter.as<unsigned>(), h->cta_heap_smem, cta_fast ? 1 : 0, dp);
     else
         KERNEL_LAT_DEPS<<<grid, kWarp, sizeof(WarpSmem), h->stream>>>(h->mpa, h->batch, h->out, h->arena,
                                                                       h->work_counter.as<unsigned>(),

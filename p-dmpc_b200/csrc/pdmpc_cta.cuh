@@ -20,25 +20,26 @@
 // The master therefore never runs an edge check; checks of nodes that are never popped are
 // wasted work on SMs that would otherwise idle.
 //
-// VALID-ONLY QUEUE (`fast` launch argument, launch shape 5).  With the answers known early, an
-// invalid child need not enter the queue at all, provided no pop ever has to break a tie:
+// VALID-ONLY QUEUE WITH DEFERRED INSERTION (`fast` launch argument, launch shape 5).  With the answers
+// known early, an invalid child need not enter the queue at all, provided no pop ever has to break a tie:
 //   * the reference's next VALID pop is a minimum of the whole queue, hence a minimum of the valid
 //     entries; if that minimum is unique among the valid entries it is the same node whatever
 //     invalid entries surround it, so the sequence of valid pops — and with it every expansion,
 //     node id, n_expanded, the goal and the path — equals the reference's;
-//   * the master therefore waits for the flags of the children it has just created, pushes the
-//     valid ones only, and before every pop checks that the minimum is strictly below both
-//     children of the root.  On the first non-unique minimum the search is RE-RUN from scratch
-//     with the exact queue (never observed on road-network records: 0 of 4 M pops; 14 of 80
-//     searches of the symmetric circle scenario);
+//   * new children wait in a PENDING buffer (one entry per lane of the master warp) until their flag
+//     arrives: valid ones are then pushed, invalid ones dropped.  The master only blocks on a pending
+//     child whose cost is not above the queue's current minimum — only such a child could be the next pop
+//     (6.5 % of the pops of road-network records are children of the expansion before them); every other
+//     check overlaps the master's pops.  (Round 1 waited for all children of every expansion: equal on
+//     long searches, 1.6x slower on median ones, profiles/r01g_valid_only_queue.txt.)
+//   * before every pop the minimum must be strictly below both children of the root.  On the first
+//     non-unique minimum the search is RE-RUN from scratch with the exact queue (never observed on
+//     road-network records: 0 of 4 M pops; 14 of 80 searches of the symmetric circle scenario);
 //   * n_pops is recovered exactly: an invalid node was popped by the reference iff its f is below
 //     the goal's (an equal f re-runs the search); all nodes are popped when the search exhausts.
 //     pop_hash covers the valid pops only in this shape (documented in include/pdmpc_b200.h).
-// A search then costs one heap pop per EXPANSION instead of one per created node cheaper than the
-// goal, but the master has to wait for the checkers (about 5 400 cycles per job) where shape 4
-// overlaps them with its pops (about 1 100 cycles each, 3 per expansion on the longest search of
-// the sample): measured equal on the long searches and 1.6x slower on median ones
-// (profiles/r01g_valid_only_queue.txt), so the shape is opt-in and shape 4 stays the default.
+// A search then costs one heap pop per EXPANSION instead of one per created node cheaper than the goal
+// (66 % of the pops of the longest road-network search are invalid nodes), on a queue a third the size.
 //
 // Hand-over: a ring of kRing job descriptors in shared memory; job j is published with
 // bar.arrive on named barrier 1 + j % kRing, the checkers wait for it in bar.sync (no
@@ -87,6 +88,7 @@ struct __align__(16) CtaSmem {
     unsigned long long hw[HS];       // heap payloads
     double pts_x[SP], pts_y[SP];
     double refx[kMaxHp], refy[kMaxHp], vref[kMaxHp];
+    double dmax[kMaxHp * kMaxHp];    // [k' * kMaxHp + t] = sum_{tau <= t} dt * v_ref(k' + tau), summed in order (expand_node.m:68)
     NodeA c_a[kCtaCache];
     NodeCS c_cs[kCtaCache];
     unsigned c_tag[kCtaCache];      // id whose (x, y, yaw, g) sits in c_a
@@ -182,6 +184,14 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
             sm.refx[k] = __ldg(b.ref_x + (size_t)si * Hp + k);
             sm.refy[k] = __ldg(b.ref_y + (size_t)si * Hp + k);
             sm.vref[k] = __ldg(b.v_ref + (size_t)si * Hp + k);
+        }
+        if (threadIdx.x >= 1 && threadIdx.x < Hp) {   // d_traveled_max of expand_node.m:68 for children of step k'
+            const int kx = threadIdx.x;
+            double d = 0.0;
+            for (int it = 1; it <= Hp - kx; ++it) {
+                d = d + b.dt * __ldg(b.v_ref + (size_t)si * Hp + kx + it - 1);
+                sm.dmax[kx * kMaxHp + it] = d;
+            }
         }
         const int *slot = b.slot_ptr + (size_t)si * (Hp + 1);
         const int trim0 = __ldg(b.trim0 + si);
@@ -353,14 +363,17 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
                                 NodeCS ecs;
                                 sincos_ref(pyaw + tb.edge_d[edge * 4 + 2], ecs.s, ecs.c);
                                 ncs[nid] = ecs;
-                                // cache entry, seqlock style: the master may be reading this slot for
-                                // an older node (id - kCtaCache) right now
-                                const int cslot = nid & (kCtaCache - 1);
-                                vcs_tag[cslot] = 0u;
-                                fence_cta();
-                                sm.c_cs[cslot] = ecs;
-                                fence_cta();
-                                vcs_tag[cslot] = nid;
+                                if (exact) {
+                                    // cache entry, seqlock style: the master may be reading this slot for
+                                    // an older node (id - kCtaCache) right now.  (The valid-only queue knows
+                                    // the answer before the pop and loads the arena record early instead.)
+                                    const int cslot = nid & (kCtaCache - 1);
+                                    vcs_tag[cslot] = 0u;
+                                    fence_cta();
+                                    sm.c_cs[cslot] = ecs;
+                                    fence_cta();
+                                    vcs_tag[cslot] = nid;
+                                }
                             }
                             fence_cta();
                             vflag[nid] = valid ? 1 : 2;
@@ -392,6 +405,39 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
         unsigned goal = 0, n_jobs = 0;
         int rot = 0;
         double f_last = 0.0;
+        // valid-only queue: children whose flag is not known yet, one per lane
+        bool pocc = false;
+        double pf = 0.0;
+        unsigned long long pw = 0;
+        // flags of the pending children: valid -> pushed, invalid -> dropped (cost parked in the unused cos/sin
+        // record for the n_pops accounting).  Blocks while `need(pf)` holds for a child without an answer.
+        auto resolve_pending = [&](bool wait_all) {
+            for (;;) {
+                const unsigned pid_ = (unsigned)(pw & 0x1fffffu);
+                const unsigned fl = pocc ? (unsigned)vflag[pid_] : 0u;
+                fence_cta();
+                if (pocc && fl == 2u) { NodeCS park; park.c = pf; park.s = 0.0; ncs[pid_] = park; pocc = false; }
+                const bool okv = pocc && fl == 1u;
+                const unsigned vm = __ballot_sync(0xffffffffu, okv);
+                if (vm) {
+                    const int mv = __popc(vm);
+                    unsigned mm = vm;
+                    for (int i = 0; i < t.lane && i < mv; ++i) mm &= mm - 1u;
+                    const int src = t.lane < mv ? __ffs(mm) - 1 : 0;
+                    HEnt hv;
+                    hv.f = __shfl_sync(0xffffffffu, pf, src);
+                    hv.w = __shfl_sync(0xffffffffu, pw, src);
+                    heap.push_many(hv, mv, t.lane);
+                    if (okv) pocc = false;
+                }
+                // only a pending child whose cost is not above the queue's minimum can be the next pop
+                const bool some = heap.len > 0;
+                const double thr = some ? heap.f_at(0) : 0.0;
+                const bool must = pocc && (wait_all || !some || !(pf > thr));
+                if (!__any_sync(0xffffffffu, must)) break;
+                __nanosleep(20);
+            }
+        };
         if (t.lane == 0) {   // root: GraphSearch.m:34-46
             NodeA ra;
             ra.x = __ldg(b.x0 + si); ra.y = __ldg(b.y0 + si); ra.yaw = __ldg(b.yaw0 + si); ra.g = 0.0;
@@ -410,9 +456,33 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
         PROF_DECL
         for (;;) {   // GraphSearch.m:53-107
             PROF_MARK(7);
-            if (heap.len == 0) { exhausted = true; break; }               // :57-61
+            if (!exact) {
+                resolve_pending(false);
+                PROF_MARK(6);   // pending children: flags, pushes, waits
+            }
+            if (heap.len == 0) { exhausted = true; break; }               // :57-61 (no pending child is left either)
             if (!exact && !heap.min_is_unique()) { tie = true; break; }   // tie mechanics would matter: re-run exact
-            const HEnt top = heap.pop(t.lane);
+            // valid-only queue: the node about to be popped is valid, its records are complete: fetch them now,
+            // their latency hides behind the heap walk
+            NodeA ca_e = {0.0, 0.0, 0.0, 0.0};
+            NodeCS ccs_e = {0.0, 0.0};
+            int sb_e = 0, nc_e = 0;
+            if (!exact) {
+                const unsigned long long w0 = lds_u64(heap.sw);
+                const unsigned id0 = (unsigned)(w0 & 0x1fffffu);
+                const int k0 = (int)((w0 >> 52) & 0x1fu), tr0 = (int)(w0 >> 57) + 1;
+                // (L2 loads: the checkers' cos/sin stores come from other warps of this SM, never rely on L1)
+                const double2 a0 = __ldcg(reinterpret_cast<const double2 *>(na + id0));
+                const double2 a1 = __ldcg(reinterpret_cast<const double2 *>(na + id0) + 1);
+                const double2 c0_ = __ldcg(reinterpret_cast<const double2 *>(ncs + id0));
+                ca_e.x = a0.x; ca_e.y = a0.y; ca_e.yaw = a1.x; ca_e.g = a1.y;
+                ccs_e.c = c0_.x; ccs_e.s = c0_.y;
+                if (k0 < Hp) {
+                    sb_e = tb.succ_ptr[k0 * nT + (tr0 - 1)];
+                    nc_e = tb.succ_ptr[k0 * nT + (tr0 - 1) + 1] - sb_e;
+                }
+            }
+            const HEnt top = heap.pop<true>(t.lane);
             PROF_MARK(1);   // heap pop
             const unsigned id = top.id(), par = top.pid();
             const int cK = (int)top.k();
@@ -432,14 +502,14 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
             // ---- expand_node.m:1-91 (nV == 1) ----------------------------------------------
             const int ctrim = (int)top.trim();
             const int k_exp = cK + 1;
-            const int sbase = tb.succ_ptr[(k_exp - 1) * nT + (ctrim - 1)];
-            const int nchild = tb.succ_ptr[(k_exp - 1) * nT + (ctrim - 1) + 1] - sbase;
+            const int sbase = exact ? tb.succ_ptr[(k_exp - 1) * nT + (ctrim - 1)] : sb_e;
+            const int nchild = exact ? tb.succ_ptr[(k_exp - 1) * nT + (ctrim - 1) + 1] - sbase : nc_e;
             if (n_nodes + nchild >= ar.cap || n_nodes + nchild >= kCtaFlags) { status = PDMPC_ERR_CAPACITY; break; }
             const int cslot = id & (kCtaCache - 1);
-            NodeA ca;
-            NodeCS ccs;
-            if (sm.c_tag[cslot] == id) ca = sm.c_a[cslot]; else ca = na[id];
-            {
+            NodeA ca = ca_e;
+            NodeCS ccs = ccs_e;
+            if (exact) {
+                if (sm.c_tag[cslot] == id) ca = sm.c_a[cslot]; else ca = na[id];
                 const unsigned t1 = vcs_tag[cslot];
                 fence_cta();
                 const volatile double *vcs = reinterpret_cast<const volatile double *>(&sm.c_cs[cslot]);
@@ -487,20 +557,19 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
                     const double ddx = ea.x - sm.refx[k_exp - 1], ddy = ea.y - sm.refy[k_exp - 1];
                     const double nrm = sqrt(ddx * ddx + ddy * ddy);
                     ea.g = ca.g + nrm * nrm;            // :61
-                    double eh = 0.0, d_max = 0.0;       // :66-73
-                    for (int it0 = 1; it0 <= to_go; it0 += 4) {
-                        double hn[4];
+                    double eh = 0.0;                    // :66-73
+                    for (int it0 = 1; it0 <= to_go; it0 += 6) {
+                        double hn[6];                   // independent square roots, issued together
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
+                        for (int u = 0; u < 6; ++u) {
                             const int kk = min(k_exp + it0 + u - 1, Hp - 1);
                             const double hx = ea.x - sm.refx[kk], hy = ea.y - sm.refy[kk];
                             hn[u] = sqrt(hx * hx + hy * hy);
                         }
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
+                        for (int u = 0; u < 6; ++u) {
                             if (it0 + u <= to_go) {
-                                d_max = d_max + b.dt * sm.vref[k_exp + it0 + u - 1];
-                                const double mm = fmax(0.0, hn[u] - d_max);
+                                const double mm = fmax(0.0, hn[u] - sm.dmax[k_exp * kMaxHp + it0 + u]);
                                 eh = eh + mm * mm;
                             }
                         }
@@ -520,29 +589,13 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
                 if (exact) {
                     heap.push_many(he, cnt, t.lane);    // :104, one push per child, in order
                 } else {
-                    // valid-only queue: wait for the checkers' answers on these children, push the valid
-                    // ones (in order); an invalid child's f is parked in its unused cos/sin record
-                    // (one uniform poll of the checkers' job counters with a back-off: lanes spinning on
-                    // their own flags starve the checkers' shared-memory traffic, 3x slower jobs measured)
-                    while (true) {
-                        const unsigned d = t.lane < NH ? vdone[t.lane] : n_jobs;
-                        if (__all_sync(0xffffffffu, d >= n_jobs)) break;
-                        __nanosleep(32);
-                    }
-                    fence_cta();
-                    const unsigned fl = ci < nchild ? vflag[nid] : 1u;
-                    PROF_MARK(6);   // wait for the children's answers
-                    const bool ok = ci < nchild && fl == 1u;
-                    if (ci < nchild && !ok) { NodeCS park; park.c = he.f; park.s = 0.0; ncs[nid] = park; }
-                    const unsigned vm = __ballot_sync(0xffffffffu, ok);
-                    const int mv = __popc(vm);
-                    unsigned mm = vm;
-                    for (int i = 0; i < t.lane && i < mv; ++i) mm &= mm - 1u;
-                    const int src = t.lane < mv ? __ffs(mm) - 1 : 0;
-                    HEnt hv;
-                    hv.f = __shfl_sync(0xffffffffu, he.f, src);
-                    hv.w = __shfl_sync(0xffffffffu, he.w, src);
-                    if (mv) heap.push_many(hv, mv, t.lane);
+                    // valid-only queue: the children wait in the pending buffer for their flags
+                    while (__popc(__ballot_sync(0xffffffffu, !pocc)) < cnt) resolve_pending(true);
+                    const unsigned freem = __ballot_sync(0xffffffffu, !pocc);
+                    const int r = __popc(freem & ((1u << t.lane) - 1u));   // this lane's rank among the free lanes
+                    const double nf = __shfl_sync(0xffffffffu, he.f, r & 31);
+                    const unsigned long long nw = __shfl_sync(0xffffffffu, he.w, r & 31);
+                    if (!pocc && r < cnt) { pocc = true; pf = nf; pw = nw; }
                 }
                 PROF_MARK(5);   // heap pushes
             }
@@ -551,6 +604,17 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
         PROF_FLUSH(o, t.lane == 0);
 
         // ---- release the checkers, then write the results (GraphSearch.m:58-60 / :82-89) ------
+        if (!exact && !tie && status == PDMPC_OK) {
+            // the n_pops accounting below needs the flag of every node cheaper than the goal: let the checkers
+            // finish the published jobs, then take the answers of the children still pending
+            while (true) {
+                const unsigned d = t.lane < NH ? vdone[t.lane] : n_jobs;
+                if (__all_sync(0xffffffffu, d >= n_jobs)) break;
+                __nanosleep(32);
+            }
+            fence_cta();
+            resolve_pending(true);
+        }
         if (t.lane == 0) *vabort = 1;
         {
             while (true) {

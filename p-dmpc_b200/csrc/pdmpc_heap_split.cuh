@@ -105,7 +105,9 @@ struct HeapSplit {
         return true;
     }
 
-    // pq.pop(); caller guarantees len > 0
+    // pq.pop(); caller guarantees len > 0.  LOOKAHEAD: two-level walk (lower latency, more instructions:
+    // for a warp that runs alone on its scheduler — the CTA kernel's master)
+    template <bool LOOKAHEAD = false>
     __device__ __forceinline__ HEnt pop(int lane) {
         const int n = len - 1;   // heap size after the pop; entry[n] is re-inserted
         len = n;
@@ -120,6 +122,23 @@ struct HeapSplit {
                 // left.f) while both children exist; one aligned 16-byte load per level
                 int hole = 0, D = 0;
                 const int lim = (n - 1) >> 1;
+                if (LOOKAHEAD) {
+                    // two levels per step: the children pairs of BOTH children are loaded together with the
+                    // hole's own pair (three independent 16-byte loads), so the dependent chain per two levels
+                    // is one load + one compare + index arithmetic.  Same path as the one-level walk.
+                    const int lim2 = (n - 7) >> 2;          // hole <= lim2: all four grandchildren exist
+                    while (hole <= lim2) {
+                        const unsigned a = sf + 16u * (unsigned)hole + 16u;
+                        const double2 p = lds_f64x2(a);
+                        const double2 gl = lds_f64x2(a + 16u * (unsigned)hole + 16u);     // pair of child 2h+1
+                        const double2 gr = lds_f64x2(a + 16u * (unsigned)hole + 32u);     // pair of child 2h+2
+                        const bool left = p.y > p.x;
+                        const int child = 2 * hole + 2 - (left ? 1 : 0);
+                        const bool left2 = left ? (gl.y > gl.x) : (gr.y > gr.x);
+                        hole = 2 * child + 2 - (left2 ? 1 : 0);
+                        D += 2;
+                    }
+                }
                 while (hole < lim) {
                     const double2 p = lds_f64x2(sf + 16u * (unsigned)hole + 16u);
                     hole = 2 * hole + 2 - (p.y > p.x ? 1 : 0);

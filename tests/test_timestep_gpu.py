@@ -171,6 +171,30 @@ def test_realistic_mpa_takes_the_warp_kernel(planner):
         parity.compare(planner.plan_timestep(batch, deps, False), ref)
 
 
+def test_valid_only_queue_of_the_time_step(planner):
+    """pdmpc_set_cta_queue(1): the one-call time step (and small plan_batch calls) run the CTA shape with its
+    valid-only queue.  Every output equals the specification's; pop_hash then covers the valid pops only,
+    which the oracle reproduces in its hash_valid_pops_only mode."""
+    from helpers import load_golden_timesteps
+    try:
+        planner.set_cta_queue(True)
+        for name in ("timestep_road_triple_speed", "timestep_circle_single_speed"):
+            mpa, steps = load_golden_timesteps(name)
+            planner.upload_mpa(mpa)
+            for batch, deps, exp in steps:
+                dev = planner.plan_timestep(batch, deps, False)
+                assert planner.stats().shape == 5
+                parity.compare(dev, exp, skip=("pop_hash",))
+                # the level-by-level specification with the valid-pop hash
+                ref5 = scenario.plan_timestep_by_levels(
+                    lambda x: oracle_py.plan_batch(mpa, x, hash_valid_pops_only=True), batch, deps)
+                parity.compare(dev, ref5)
+                small = planner.plan_batch(batch.select(np.arange(min(batch.n, 5))), False)
+                assert planner.stats().shape == 5 and small.status.max() == 0
+    finally:
+        planner.set_cta_queue(False)
+
+
 @pytest.mark.parametrize("variant", [1, 4])
 def test_both_launch_shapes_of_the_time_step(planner, variant):
     """pdmpc_set_variant forces the warp-per-search (1) or the CTA-per-search (4) shape of pdmpc_plan_timestep:

@@ -27,6 +27,14 @@ def main():
         b = SearchBatch.concat([b] * reps)
     p = capi.Planner(0)
     p.upload_mpa(mpa)
+    if os.environ.get('PDMPC_SORT_BY_POPS'):   # experiment: longest searches first (needs PDMPC_NO_REORDER=1)
+        import numpy as np
+        r0 = p.plan_batch(b)
+        key = r0.n_pops.astype(np.int64)
+        mode = os.environ['PDMPC_SORT_BY_POPS']
+        order = np.argsort(-key, kind='stable') if mode == 'desc' else np.random.default_rng(0).permutation(b.n)
+        b = b.select(order)
+        print('sorted by pops', mode, 'max', key.max())
     p.set_variant(tile)
     if os.environ.get('PDMPC_TILE_POINTS'):
         p.set_tile_points(int(os.environ['PDMPC_TILE_POINTS']))
