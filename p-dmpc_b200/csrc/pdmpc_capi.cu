@@ -65,12 +65,26 @@ constexpr int kTile4Heap = PDMPC_TILE4_HEAP, kTile4Pts = PDMPC_TILE4_PTS, kTile4
 #define KERNEL_TILE4 search_tile_kernel<8, kTile4Heap, kTile4Pts, kTile4Ctas>
 constexpr size_t kTile2Smem = 2 * sizeof(TileSm<kTile2Heap, kTile2Pts>);
 constexpr size_t kTile4Smem = 4 * sizeof(TileSm<kTile4Heap, kTile4Pts>);
-// "cta" = one 13-warp CTA per search (pdmpc_cta.cuh): master warp + checker warps, lowest latency
-#define KERNEL_CTA search_cta_kernel<kCtaHeap, kCtaPts, kCtaHelpers, false>
-using CtaSmemT = CtaSmem<kCtaHeap, kCtaPts, kCtaHelpers, false>;
-// the same kernel with the dependency prelude/epilogue of pdmpc_plan_timestep
-#define KERNEL_CTA_DEPS search_cta_kernel<kCtaHeap, kCtaPts, kCtaHelpers, true>
-using CtaDepsSmemT = CtaSmem<kCtaHeap, kCtaPts, kCtaHelpers, true>;
+// "cta" = masters + shared checker warps, one CTA per SM (pdmpc_cta.cuh).  Two configurations:
+//   1 master, 12 checkers (+ 3 parked warps): a batch of at most one search per SM — lowest latency
+//   NM masters, 12 checkers: larger batches — every SM runs NM searches at (almost) the same latency
+#ifndef PDMPC_CTA_MASTERS
+#define PDMPC_CTA_MASTERS 4
+#endif
+constexpr int kCtaCheckers = 12;
+constexpr int kCtaHeap = 4096, kCtaPts = 512;          // single master: heap entries / polyline points in shared memory
+constexpr int kCtaMHeap = 1024, kCtaMPts = 256;        // several masters: per search
+constexpr int kCtaMasters = PDMPC_CTA_MASTERS, kCtaMastersDeps = 2;
+#define KERNEL_CTA search_cta_kernel<kCtaHeap, kCtaPts, kCtaCheckers, 1, false>
+#define KERNEL_CTA_DEPS search_cta_kernel<kCtaHeap, kCtaPts, kCtaCheckers, 1, true>
+#define KERNEL_CTAM search_cta_kernel<kCtaMHeap, kCtaMPts, kCtaCheckers, kCtaMasters, false>
+#define KERNEL_CTAM_DEPS search_cta_kernel<kCtaMHeap, kCtaMPts, kCtaCheckers, kCtaMastersDeps, true>
+using CtaSmemT = CtaSmem<kCtaHeap, kCtaPts, kCtaCheckers, 1, false>;
+using CtaDepsSmemT = CtaSmem<kCtaHeap, kCtaPts, kCtaCheckers, 1, true>;
+using CtaMSmemT = CtaSmem<kCtaMHeap, kCtaMPts, kCtaCheckers, kCtaMasters, false>;
+using CtaMDepsSmemT = CtaSmem<kCtaMHeap, kCtaMPts, kCtaCheckers, kCtaMastersDeps, true>;
+static_assert(sizeof(CtaSmemT) <= kSmemLimit && sizeof(CtaDepsSmemT) <= kSmemLimit && sizeof(CtaMSmemT) <= kSmemLimit &&
+              sizeof(CtaMDepsSmemT) <= kSmemLimit, "CTA shapes must fit one SM");
 
 struct DBuf {
     void *p = nullptr;
@@ -257,11 +271,15 @@ int pdmpc_create(int device_id, pdmpc_handle **out) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, KERNEL_TILE4, kWarp, kTile4Smem) == cudaSuccess)
         h->tile_ctas_per_sm[1] = occ;
     h->cta_ok = cudaFuncSetAttribute(KERNEL_CTA, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sizeof(CtaSmemT)) == cudaSuccess;
+                                     (int)sizeof(CtaSmemT)) == cudaSuccess &&
+                cudaFuncSetAttribute(KERNEL_CTAM, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(CtaMSmemT)) == cudaSuccess;
     h->lat_deps_ok = cudaFuncSetAttribute(KERNEL_LAT_DEPS, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)sizeof(WarpSmem)) == cudaSuccess;
     h->cta_deps_ok = cudaFuncSetAttribute(KERNEL_CTA_DEPS, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)sizeof(CtaDepsSmemT)) == cudaSuccess;
+                                          (int)sizeof(CtaDepsSmemT)) == cudaSuccess &&
+                     cudaFuncSetAttribute(KERNEL_CTAM_DEPS, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(CtaMDepsSmemT)) == cudaSuccess;
     cudaGetLastError();
     *out = h;
     return PDMPC_OK;
@@ -788,13 +806,19 @@ static int launch_search(pdmpc_handle *h, const TraceDev &tr) {
     unsigned *wc = h->work_counter.as<unsigned>();
     h->stats.shape = variant;
     if (variant == 4 || variant == 5) {
-        const int grid = std::min(n, h->num_sms);
-        int rc = ensure_arena(h, grid);
+        // at most one search per SM: one master per CTA, every checker serves it; else several masters per CTA
+        const bool single = n <= h->num_sms;
+        const int nm = single ? 1 : kCtaMasters;
+        const int grid = std::min((n + nm - 1) / nm, h->num_sms);
+        int rc = ensure_arena(h, grid * nm);
         if (rc != PDMPC_OK) return rc;
         CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
-        KERNEL_CTA<<<grid, (kCtaHelpers + kCtaHelpers / 3) * kWarp, sizeof(CtaSmemT), h->stream>>>(h->mpa, h->batch, h->out,
-                                                                                    h->arena, wc, h->cta_heap_smem,
-                                                                                    variant == 5 ? 1 : 0, DepsDev{});
+        if (single)
+            KERNEL_CTA<<<grid, CtaShape<1, kCtaCheckers>::kThreads, sizeof(CtaSmemT), h->stream>>>(
+                h->mpa, h->batch, h->out, h->arena, wc, h->cta_heap_smem, variant == 5 ? 1 : 0, DepsDev{});
+        else
+            KERNEL_CTAM<<<grid, CtaShape<kCtaMasters, kCtaCheckers>::kThreads, sizeof(CtaMSmemT), h->stream>>>(
+                h->mpa, h->batch, h->out, h->arena, wc, h->cta_heap_smem, variant == 5 ? 1 : 0, DepsDev{});
         CU_TRY(h, cudaGetLastError());
         h->stats.kernel_launches++;
     } else {
@@ -1248,8 +1272,10 @@ int pdmpc_plan_timestep(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_t
     // ---- one persistent launch: CTAs / warps take the searches in topological order ----------------
     CU_TRY(h, cudaMemsetAsync(h->out.counters, 0, 16 * sizeof(unsigned long long), h->stream));
     CU_TRY(h, cudaMemsetAsync(h->work_counter.p, 0, sizeof(unsigned), h->stream));
-    const int grid = use_cta ? std::min(n, h->num_sms) : std::min(n, h->num_sms * h->lat_ctas_per_sm);
-    rc = ensure_arena(h, grid);
+    const bool cta_single = n <= h->num_sms;
+    const int cta_nm = cta_single ? 1 : kCtaMastersDeps;
+    const int grid = use_cta ? std::min((n + cta_nm - 1) / cta_nm, h->num_sms) : std::min(n, h->num_sms * h->lat_ctas_per_sm);
+    rc = ensure_arena(h, use_cta ? grid * cta_nm : grid);
     if (rc != PDMPC_OK) return rc;
     if (!use_cta) {   // per-slot scratch for the predecessors' areas
         CU_TRY(h, h->d_depx.reserve((size_t)grid * kDepCols * sizeof(double)));
@@ -1260,8 +1286,11 @@ int pdmpc_plan_timestep(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_t
     const bool cta_fast = h->variant_mode == 5 || h->cta_valid_only;
     h->stats.shape = use_cta ? (cta_fast ? 5 : 4) : 1;
     CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
-    if (use_cta)
-        KERNEL_CTA_DEPS<<<grid, (kCtaHelpers + kCtaHelpers / 3) * kWarp, sizeof(CtaDepsSmemT), h->stream>>>(
+    if (use_cta && cta_single)
+        KERNEL_CTA_DEPS<<<grid, CtaShape<1, kCtaCheckers>::kThreads, sizeof(CtaDepsSmemT), h->stream>>>(
+            h->mpa, h->batch, h->out, h->arena, h->work_counter.as<unsigned>(), h->cta_heap_smem, cta_fast ? 1 : 0, dp);
+    else if (use_cta)
+        KERNEL_CTAM_DEPS<<<grid, CtaShape<kCtaMastersDeps, kCtaCheckers>::kThreads, sizeof(CtaMDepsSmemT), h->stream>>>(
             h->mpa, h->batch, h->out, h->arena, h->work_counter.as<unsigned>(), h->cta_heap_smem, cta_fast ? 1 : 0, dp);
     else
         KERNEL_LAT_DEPS<<<grid, kWarp, sizeof(WarpSmem), h->stream>>>(h->mpa, h->batch, h->out, h->arena,

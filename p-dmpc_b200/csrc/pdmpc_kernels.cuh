@@ -316,7 +316,8 @@ __device__ __forceinline__ bool interx_dispatch(int ns, const double *px, const 
 // ---- SAT (intersect_sat.m:1-42): polygon 1 in shared memory, polygon 2 in
 // global memory.  Lanes own axes (edges of both polygons incl. the closing one).
 // NC = false: polygon 2 is read with plain loads (it may live in shared memory).
-template <int TILE, bool NC = true>
+// STRIDE: distance between consecutive points of polygon 2 in doubles (2: interleaved (x, y) pairs).
+template <int TILE, bool NC = true, int STRIDE = 1>
 __device__ __forceinline__ bool sat_collide(const double *x1, const double *y1, int n1,
                                             const double *__restrict__ x2, const double *__restrict__ y2,
                                             int n2, const Tile<TILE> &t) {
@@ -329,8 +330,8 @@ __device__ __forceinline__ bool sat_collide(const double *x1, const double *y1, 
             ey = y1[e1] - y1[e];
         } else {
             int f = e - n1, f1 = (f + 1 == n2) ? 0 : f + 1;
-            ex = NC ? __ldg(x2 + f1) - __ldg(x2 + f) : x2[f1] - x2[f];
-            ey = NC ? __ldg(y2 + f1) - __ldg(y2 + f) : y2[f1] - y2[f];
+            ex = NC ? __ldg(x2 + f1 * STRIDE) - __ldg(x2 + f * STRIDE) : x2[f1 * STRIDE] - x2[f * STRIDE];
+            ey = NC ? __ldg(y2 + f1 * STRIDE) - __ldg(y2 + f * STRIDE) : y2[f1 * STRIDE] - y2[f * STRIDE];
         }
         double ax = -ey, ay = ex;
         double nrm = sqrt(ax * ax + ay * ay);
@@ -342,7 +343,7 @@ __device__ __forceinline__ bool sat_collide(const double *x1, const double *y1, 
             mx1 = fmax(mx1, d);
         }
         for (int v = 0; v < n2; ++v) {
-            double d = NC ? nx * __ldg(x2 + v) + ny * __ldg(y2 + v) : nx * x2[v] + ny * y2[v];
+            double d = NC ? nx * __ldg(x2 + v * STRIDE) + ny * __ldg(y2 + v * STRIDE) : nx * x2[v * STRIDE] + ny * y2[v * STRIDE];
             mn2 = fmin(mn2, d);
             mx2 = fmax(mx2, d);
         }
