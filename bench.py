@@ -4,9 +4,11 @@
 Workload at N=1 (BASELINE.json configs[1]): CPM Lab road network, 20 vehicles,
 coloring-based prioritisation, triple_speed MPA, Hp 6, InterX checker, 35 time
 steps per scenario, R scenarios planned concurrently ("parallel_threads
-equivalent on 1 B200").  Scenarios are rolled out closed loop once (untimed) with
-the GPU planner so that every (scenario, step, vehicle) search record is fixed;
-one bench "step" = one pass of the hot path over all records of the rank.
+equivalent on 1 B200").  Scenarios are rolled out closed loop once (untimed) so
+that every (scenario, step, vehicle) search record is fixed; one bench "step" =
+one pass of the hot path over all records of the rank.  Both arms plan the SAME
+records: they come from the same seeds, are rolled out by bit-identical planners
+(GPU library / C oracle) and are shared through a cache under build/.
 
   value     : records already resident in HBM, search kernel timed with CUDA
               events on the library's stream, L2 flushed between steps.
@@ -15,11 +17,17 @@ one bench "step" = one pass of the hot path over all records of the rank.
               timed region.
   roofline  : algorithmic bytes of the search kernel (SURVEY.md §8d formula from
               the kernel's own counters) / its CUDA-event time vs measured HBM peak;
-              plus the FP64-pipe figure, which is the bound that actually bites.
+              plus the FP64-pipe and the warp-instruction-issue figures — the issue
+              rate is the bound that actually bites.
   cpu_baseline : the C oracle (a port of the reference; MATLAB is not available)
-              timed on this box's host cores on a bounded sample of the same records.
+              timed on this box's host cores on a bounded sample of the same records,
+              plus the per-time-step latency of the CPU path (level by level).
 
 `--impl reference` times that CPU implementation alone (all host threads).
+`--scenarios-total T` fixes the total batch (BASELINE configs[4]: 4096) and splits it
+over the ranks (strong scaling).  `--optimizer sampled` times the sampled optimizer
+(MonteCarloTreeSearch) on the same records.  `--config explorative` runs BASELINE
+configs[2] (8 priority permutations per time step, sharded over the GPUs) closed loop.
 """
 from __future__ import annotations
 
@@ -36,6 +44,10 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+BLOCK = 8            # scenarios per record-cache file (the unit of generation and of sharding)
+LAT_SCENARIOS = 8    # scenarios whose time steps are replayed for the per-time-step latency (= block 0)
+L2_NOTE = "GPU arm: flushed between timed steps (256 MiB write); CPU arm: not applicable"
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -43,10 +55,16 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="road", choices=["road", "explorative"],
+                    help="road = BASELINE configs[1]/[4] (default); explorative = configs[2]")
+    ap.add_argument("--optimizer", default="graph", choices=["graph", "sampled"],
+                    help="graph = GraphSearch (default); sampled = MonteCarloTreeSearch")
     ap.add_argument("--scenarios", type=int, default=int(os.environ.get("PDMPC_BENCH_SCENARIOS", "256")),
                     help="scenarios per GPU (weak scaling)")
+    ap.add_argument("--scenarios-total", type=int, default=0,
+                    help="total scenarios, split block-cyclically over the ranks (strong scaling; BASELINE configs[4]: 4096)")
     ap.add_argument("--gen-workers", type=int, default=0,
-                    help="processes that roll the scenarios out (0 = auto: host cores / ranks, at most 12)")
+                    help="processes that roll the scenarios out (0 = auto)")
     ap.add_argument("--sim-steps", type=int, default=35)
     ap.add_argument("--vehicles", type=int, default=20)
     ap.add_argument("--mpa", default="triple_speed")
@@ -54,7 +72,13 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="searches in the CPU sample (0 = auto)")
     ap.add_argument("--pipeline-chunks", type=int, default=0,
                     help="chunks of the e2e call's copy/search pipeline (0 = library default, 1 = off)")
-    return ap.parse_args()
+    ap.add_argument("--permutations", type=int, default=8, help="--config explorative: priority permutations per time step")
+    ap.add_argument("--mcts-expansions", type=int, default=250, help="--optimizer sampled: n_expansions_max")
+    a = ap.parse_args()
+    for v in (a.scenarios, a.scenarios_total):
+        if v % BLOCK:
+            ap.error(f"scenario counts must be multiples of {BLOCK}")
+    return a
 
 
 def dist_env():
@@ -116,21 +140,36 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def _roll_chunk(job):
-    """Worker process: roll a chunk of scenarios out closed loop with its OWN GPU planner."""
-    dev, mpa_type, vehicles, sim_steps, seeds, out_path = job
-    from pdmpc_b200 import capi, scenario
+# ---------------------------------------------------------------------------- records
+def block_path(args, block: int) -> str:
+    return os.path.join(ROOT, "build", "bench_records",
+                        f"{args.mpa}_{args.vehicles}v_{args.sim_steps}t_block{block:04d}.npz")
+
+
+def _roll_block(job):
+    """Worker process: roll one block of BLOCK scenarios (seeds 1 + BLOCK*block ...) out closed loop.
+    planner 'gpu': its own GPU planner; 'oracle': the C oracle (one thread) — bit-identical plans, hence
+    identical records.  Block 0 also keeps the level structure and the one-call inputs of its time steps."""
+    kind, dev, mpa_type, vehicles, sim_steps, block, out_path = job
+    import pickle
+    from pdmpc_b200 import scenario
     from pdmpc_b200.mpa import get_mpa
-    from pdmpc_b200.records import SearchBatch
+    from pdmpc_b200.records import SearchBatch, TimestepDeps
     mpa = get_mpa(mpa_type, non_convex=True)
-    planner = capi.Planner(dev)
-    planner.upload_mpa(mpa)
-    from pdmpc_b200.records import TimestepDeps
+    planner = None
+    if kind == "gpu":
+        from pdmpc_b200 import capi
+        planner = capi.Planner(dev)
+        planner.upload_mpa(mpa)
+        plan = planner.plan_batch
+    else:
+        from oracle import oracle_py
+        plan = lambda b: oracle_py.plan_batch(mpa, b, 1)   # noqa: E731
     batches, levels, timesteps = [], [], []
-    for si, s in enumerate(seeds):
-        sc = scenario.commonroad_scenario(mpa, vehicles, seed=s)
-        runner = scenario.ScenarioRunner(sc, planner.plan_batch)
-        if si < 8:   # level structure + one-call inputs of the first scenarios (per-time-step latency replay)
+    for si in range(BLOCK):
+        sc = scenario.commonroad_scenario(mpa, vehicles, seed=1 + BLOCK * block + si)
+        runner = scenario.ScenarioRunner(sc, plan)
+        if block == 0 and si < LAT_SCENARIOS:
             for _ in range(sim_steps):
                 iters, preds, fbs = runner.timestep_inputs()
                 timesteps.append((si * 100000 + runner.k + 1,
@@ -142,47 +181,71 @@ def _roll_chunk(job):
         else:
             recs = runner.run(sim_steps)
         batches.extend(r.batch for r in recs)
-    planner.close()
-    SearchBatch.concat(batches).save(out_path)
-    return out_path, levels, timesteps
+    if planner is not None:
+        planner.close()
+    os.makedirs(os.path.dirname(out_path), exist_ok=True)
+    tmp = out_path + f".tmp{os.getpid()}.npz"
+    SearchBatch.concat(batches).save(tmp)
+    if block == 0:
+        np.save(out_path + ".levels.npy", np.array(levels, dtype=np.int64))
+        with open(out_path + ".ts.pkl", "wb") as f:
+            pickle.dump(timesteps, f)
+    os.replace(tmp, out_path)
+    return out_path
 
 
-def build_records(dev, mpa_type, n_scen: int, seed0: int, vehicles: int, sim_steps: int, cache: str = "",
-                  workers: int = 1):
-    """Closed-loop roll-out of n_scen road-network scenarios with the GPU planner (untimed),
-    spread over `workers` processes (the scenario logic around the planner is host-side
-    Python).  Returns (flat batch of every search record, [(step, level, n_searches)] of the
-    first scenario, whose records come first in the batch).  Cached under build/
-    (git-ignored) so that profiler runs of the same command skip the generation launches."""
-    from pdmpc_b200.records import SearchBatch
+def rank_blocks(args, rank: int, world: int):
+    """Blocks of BLOCK scenarios this rank owns.  Weak scaling: `--scenarios` per rank, consecutive;
+    strong scaling (`--scenarios-total`): all blocks dealt block-cyclically."""
+    if args.scenarios_total:
+        return [b for b in range(args.scenarios_total // BLOCK) if b % world == rank]
+    per = args.scenarios // BLOCK
+    return list(range(rank * per, (rank + 1) * per))
+
+
+def get_records(args, blocks, kind: str, dev: int, workers: int):
+    """Flat batch of every search record of `blocks` (+ level structure and one-call inputs of block 0 when
+    it is among them).  Missing blocks are rolled out by `workers` processes and cached under build/."""
     import pickle
-    if cache and os.path.exists(cache) and os.path.exists(cache + ".levels.npy") and os.path.exists(cache + ".ts.pkl"):
-        return SearchBatch.load(cache), np.load(cache + ".levels.npy"), pickle.load(open(cache + ".ts.pkl", "rb"))
     import multiprocessing as mp
+    from pdmpc_b200.records import SearchBatch
     import tempfile
-    workers = max(1, min(workers, n_scen))
-    tmp = tempfile.mkdtemp(prefix="pdmpc_gen_")
-    seeds = [seed0 + s for s in range(n_scen)]
-    per = (n_scen + workers - 1) // workers
-    jobs = [(dev, mpa_type, vehicles, sim_steps, seeds[i * per:(i + 1) * per], os.path.join(tmp, f"c{i}.npz"))
-            for i in range(workers) if seeds[i * per:(i + 1) * per]]
-    if len(jobs) == 1:
-        results = [_roll_chunk(jobs[0])]
-    else:
-        with mp.get_context("spawn").Pool(len(jobs)) as pool:
-            results = pool.map(_roll_chunk, jobs)
-    batch = SearchBatch.concat([SearchBatch.load(pth) for pth, _, _ in results])
-    levels = np.array(results[0][1], dtype=np.int64)
-    timesteps = results[0][2]
-    for pth, _, _ in results:
-        os.remove(pth)
-    os.rmdir(tmp)
-    if cache:
-        os.makedirs(os.path.dirname(cache), exist_ok=True)
-        batch.save(cache)
-        np.save(cache + ".levels.npy", levels)
-        pickle.dump(timesteps, open(cache + ".ts.pkl", "wb"))
+    tmpdir = tempfile.mkdtemp(prefix="pdmpc_gen_") if args.no_cache else None
+    path = (lambda b: os.path.join(tmpdir, f"block{b:04d}.npz")) if tmpdir else (lambda b: block_path(args, b))
+    todo = [b for b in blocks if not os.path.exists(path(b)) or
+            (b == 0 and not os.path.exists(path(b) + ".ts.pkl"))]
+    if todo:
+        jobs = [(kind, dev, args.mpa, args.vehicles, args.sim_steps, b, path(b)) for b in todo]
+        w = max(1, min(workers, len(jobs)))
+        if w == 1:
+            for j in jobs:
+                _roll_block(j)
+        else:
+            with mp.get_context("spawn").Pool(w) as pool:
+                pool.map(_roll_block, jobs, chunksize=1)
+    batch = SearchBatch.concat([SearchBatch.load(path(b)) for b in blocks])
+    levels, timesteps = np.zeros((0, 3), dtype=np.int64), []
+    if 0 in blocks:
+        levels = np.load(path(0) + ".levels.npy")
+        timesteps = pickle.load(open(path(0) + ".ts.pkl", "rb"))
+    if tmpdir:
+        import shutil
+        shutil.rmtree(tmpdir, ignore_errors=True)
     return batch, levels, timesteps
+
+
+def workload_config(args, world: int, n: int, Hp: int) -> dict:
+    """`config` of the JSON line — identical in both arms (same records)."""
+    if args.scenarios_total:
+        size = (f"{args.scenarios_total} scenarios in total (BASELINE configs[4]) split block-cyclically over "
+                f"{world} GPU(s) x {args.sim_steps} steps")
+    else:
+        size = f"{args.scenarios} scenarios/GPU x {args.sim_steps} steps"
+    opt = "" if args.optimizer == "graph" else f", sampled optimizer (MonteCarloTreeSearch, n_expansions_max {args.mcts_expansions})"
+    return {"workload": f"CPM Lab road network (BASELINE configs[1]), {args.vehicles} vehicles, coloring priorities, "
+                        f"{args.mpa} MPA, Hp {Hp}, InterX checker{opt}, {size}, pre-rolled closed loop "
+                        f"(seeds 1.., same records in both arms)",
+            "searches_per_step_per_gpu": n, "l2": L2_NOTE}
 
 
 def algorithmic_bytes(batch, stats, Hp: int) -> float:
@@ -203,49 +266,101 @@ def fp64_ops(batch, stats, Hp: int) -> float:
                  stats.total_nodes * (20 + 9 * (Hp - 1) / 2))
 
 
+def cpu_timestep_latency(mpa, batch, step_recs, cores: int, reps: int = 2):
+    """BASELINE.md §2 "CPU-step": wall time of one 20-vehicle time step on the CPU path the way the
+    reference's parallel_threads mode runs it — computation levels one after the other, the vehicles of
+    a level on parallel threads (PrioritizedSequentialController.m:74-92) — over the time steps of the
+    first LAT_SCENARIOS scenarios (the same steps the GPU latency replays)."""
+    from oracle import oracle_py
+    by_step, off = {}, 0
+    for step, _level, cnt in step_recs:
+        by_step.setdefault(int(step), []).append(batch.select(np.arange(off, off + int(cnt))))
+        off += int(cnt)
+    lat = []
+    for rep in range(reps + 1):
+        for _k, levels in sorted(by_step.items()):
+            t0 = time.perf_counter()
+            for lb in levels:
+                oracle_py.plan_batch(mpa, lb, min(cores, lb.n))
+            if rep:
+                lat.append((time.perf_counter() - t0) * 1e3)
+    if not lat:
+        return None
+    return {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)), "max": float(np.max(lat)),
+            "n": len(lat), "levels_per_step": float(np.mean([len(v) for v in by_step.values()])),
+            "what": f"wall time of one {int(sum(b.n for b in next(iter(by_step.values()))))}-vehicle time step on the CPU "
+                    f"path: computation levels one after the other, the vehicles of a level on up to {cores} threads"}
+
+
+# ---------------------------------------------------------------------------- reference arm
 def run_reference(args, rank, world):
-    """--impl reference: the CPU implementation of the path (oracle port; the
-    MATLAB reference cannot run here) on all host threads, bounded sample."""
+    """--impl reference: the CPU implementation of the path (C oracle port; the MATLAB reference cannot
+    run here) on all host threads, over the records of rank 0 of the GPU arm — the same seeds, hence
+    byte-identical search records; each step plans all of them (or a stated prefix on a slow host)."""
     if rank != 0:
         return
+    import __graft_entry__ as entry
     from oracle import oracle_py
-    from pdmpc_b200 import scenario
     from pdmpc_b200.mpa import get_mpa
-    from pdmpc_b200.records import SearchBatch
+    entry.build_oracle()
     mpa = get_mpa(args.mpa, non_convex=True)
     cores = os.cpu_count() or 1
-    plan = lambda b: oracle_py.plan_batch(mpa, b, cores)
-    batches = []
-    for s in range(2):
-        sc = scenario.commonroad_scenario(mpa, args.vehicles, seed=1 + s)
-        batches.append(scenario.roll_out(sc, plan, args.sim_steps))
-    base = SearchBatch.concat(batches)
-    # bounded sample: replicate the two scenarios until one step is ~2 s of wall time
+    t_gen = time.perf_counter()
+    batch, step_recs, _ts = get_records(args, rank_blocks(args, 0, world), "oracle", 0, args.gen_workers or cores)
+    t_gen = time.perf_counter() - t_gen
+    n = batch.n
+    if args.optimizer == "sampled":
+        seeds = (np.arange(n) % 35 + 2).astype(np.uint32)
+        plan = lambda b, s=None: oracle_py.mcts_plan_batch(mpa, b, seeds[: b.n], args.mcts_expansions, cores)   # noqa: E731
+    else:
+        plan = lambda b: oracle_py.plan_batch(mpa, b, cores)   # noqa: E731
+    # bounded: the whole run (warmup + steps passes) within ~3 minutes
+    probe = batch.select(np.arange(min(n, 8000)))
     t0 = time.perf_counter()
-    oracle_py.plan_batch(mpa, base, cores)
-    dt = max(time.perf_counter() - t0, 1e-4)
-    reps = int(min(max(1, round(2.0 / dt)), 256))
-    sample = SearchBatch.concat([base] * reps)
+    plan(probe)
+    rate = probe.n / max(time.perf_counter() - t0, 1e-6)
+    passes = args.steps + args.warmup
+    m = int(min(n, max(2000, rate * 180.0 / max(passes, 1))))
+    sample = batch if m == n else batch.select(np.arange(m))
     for _ in range(args.warmup):
-        oracle_py.plan_batch(mpa, sample, cores)
+        plan(sample)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle_py.plan_batch(mpa, sample, cores)
+        plan(sample)
     el = time.perf_counter() - t0
     val = sample.n * args.steps / el
-    desc = f"{sample.n} searches/step = {reps}x the records of 2 scenarios x {args.sim_steps} steps x {args.vehicles} vehicles"
+    desc = (f"all {n} search records of GPU rank 0 per step" if m == n else
+            f"first {m} of the {n} search records of GPU rank 0 per step (slow host: bounded to ~3 min)")
+    lat = cpu_timestep_latency(mpa, batch, step_recs, cores) if args.optimizer == "graph" else None
     print(json.dumps({
         "impl": "reference", "metric": "vehicle-plans/sec", "value": val, "unit": "plans/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong" if args.scenarios_total else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"CPM Lab road network, {args.vehicles} vehicles, coloring priorities, "
-                               f"{args.mpa} MPA, Hp 6, InterX checker", "cpu_threads": cores},
+        "config": workload_config(args, world, n, mpa.Hp),
         "cpu_baseline": {"value": val, "unit": "plans/s", "cores": cores, "kind": "port", "sample": desc,
-                         "note": "C oracle (gcc -O2, no FMA contraction) restating the MATLAB reference; "
+                         "latency_ms_per_timestep": lat,
+                         "note": "C oracle (gcc -O2, no FMA contraction) restating the MATLAB reference, one pthread per "
+                                 "host core pulling searches from a shared counter (parallel_threads equivalent); "
                                  "MATLAB R2023a itself is unavailable in this image"},
         "e2e": {"value": val, "unit": "plans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "record_generation_s": round(t_gen, 1),
     }))
+
+
+# ---------------------------------------------------------------------------- GPU arm
+def captured_kernel_figures(n: int, mpa: str, shape: int):
+    """DRAM traffic and warp instructions of ONE launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this same launch (tools/gpu_round.sh writes profiles/search_kernel_traffic.json
+    from the capture of the bench's own records); None when the workload or the launch shape differs."""
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "search_kernel_traffic.json")))
+        if int(cap.get("searches", -1)) == n and cap.get("mpa") == mpa and int(cap.get("shape", shape)) == shape:
+            return cap
+    except Exception:
+        pass
+    return None
 
 
 def main():
@@ -264,6 +379,13 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()
+    if args.config == "explorative":
+        from pdmpc_b200 import bench_explorative
+        bench_explorative.run(args, rank, local_rank, world, ClockSampler)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     from pdmpc_b200 import capi
     from pdmpc_b200.mpa import get_mpa
     from pdmpc_b200.records import BatchResult
@@ -273,16 +395,16 @@ def main():
     planner = capi.Planner(dev)        # raises if the CUDA library / device is missing
     mpa = get_mpa(args.mpa, non_convex=True)
     planner.upload_mpa(mpa)
+    planner.set_cta_queue(True)   # what the MATLAB drop-in selects: valid-only queue wherever the CTA shape runs
     Hp = mpa.Hp
 
     t_gen = time.perf_counter()
-    cache = os.path.join(ROOT, "build", f"bench_{args.mpa}_{args.vehicles}v_{args.scenarios}s_{args.sim_steps}t_seed"
-                                        f"{1 + rank * args.scenarios}.npz")
     workers = args.gen_workers or max(1, min(12, (os.cpu_count() or 1) // max(world, 1)))
-    batch, step_recs, ts_recs = build_records(dev, args.mpa, args.scenarios, 1 + rank * args.scenarios,
-                                     args.vehicles, args.sim_steps, "" if args.no_cache else cache, workers)
+    batch, step_recs, ts_recs = get_records(args, rank_blocks(args, rank, world), "gpu", dev, workers)
     t_gen = time.perf_counter() - t_gen
     n = batch.n
+    sampled = args.optimizer == "sampled"
+    seeds = (np.arange(n) % 35 + 2).astype(np.uint32)
 
     stream = torch.cuda.ExternalStream(planner.stream(), device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{dev}")   # > 126 MB L2
@@ -292,40 +414,50 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def run_staged():
+        if sampled:
+            planner.mcts_run_staged(seeds, args.mcts_expansions)
+        else:
+            planner.run_staged()
+
     # ---- device-resident throughput ("value") ------------------------------------
     planner.stage(batch)
     for _ in range(max(args.warmup, 3)):
-        planner.run_staged()
+        run_staged()
     planner.sync()
+    launches_per_step = int(planner.stats().kernel_launches)
     sampler = ClockSampler(dev)
     barrier()
     sampler.start()
     kernel_ms = []
-    t_wall = time.perf_counter()
     for _ in range(args.steps):
         with torch.cuda.stream(stream):
             flush.zero_()                     # L2 flush, outside the per-step events
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            planner.run_staged()
+            run_staged()
             e1.record(stream)
         e1.synchronize()
         kernel_ms.append(e0.elapsed_time(e1))
     barrier()
-    t_wall = time.perf_counter() - t_wall
     clocks = sampler.stop()
     res = planner.fetch()
     stats = planner.stats()
+    shape = int(stats.shape)
     ms_step = float(np.mean(kernel_ms))
     t_local = torch.tensor([sum(kernel_ms)], dtype=torch.float64, device=f"cuda:{dev}")
+    n_all = torch.tensor([n], dtype=torch.int64, device=f"cuda:{dev}")
     if world > 1:
         dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n_all, op=dist.ReduceOp.SUM)
     total_ms = float(t_local.item())
-    value = n * world * args.steps / (total_ms * 1e-3)
+    n_total = int(n_all.item())
+    value = n_total * args.steps / (total_ms * 1e-3)
 
     # ---- end to end through the C ABI with host buffers ("e2e") ------------------
     import dataclasses
+    import ctypes as C
     pinned = []   # keep the pinned torch storages alive
 
     def pinned_like(a: np.ndarray) -> np.ndarray:
@@ -345,26 +477,33 @@ def main():
         a = getattr(out, f.name)
         if isinstance(a, np.ndarray):
             setattr(out, f.name, pinned_like(a))
-    import ctypes as C
     bi, bo = capi.batch_in(hb), capi.batch_out(out)
+    prm, prm_keep = capi.mcts_params(seeds, args.mcts_expansions, n)
     e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_call():
+        if sampled:
+            planner._check(planner.lib.pdmpc_mcts_plan_batch(planner.h, C.byref(bi), C.byref(prm), C.byref(bo)))
+        else:
+            planner._check(planner.lib.pdmpc_plan_batch(planner.h, C.byref(bi), C.byref(bo)))
 
     def time_e2e(chunks: int, steps: int) -> float:
         planner.set_pipeline_chunks(chunks)
         for _ in range(2):
-            planner._check(planner.lib.pdmpc_plan_batch(planner.h, C.byref(bi), C.byref(bo)))
+            e2e_call()
         barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
-            planner._check(planner.lib.pdmpc_plan_batch(planner.h, C.byref(bi), C.byref(bo)))
+            e2e_call()
         torch.cuda.synchronize()
         t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{dev}")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         assert np.array_equal(out.pop_hash, res.pop_hash), "e2e path and staged path disagree"
-        return n * world * steps / float(t.item())
+        assert np.array_equal(out.trims, res.trims), "e2e path and staged path disagree"
+        return n_total * steps / float(t.item())
 
-    e2e_serial = time_e2e(1, 3)                     # copy in, search, copy out, one after the other
+    e2e_serial = None if sampled else time_e2e(1, 3)   # copy in, search, copy out, one after the other
     e2e_val = time_e2e(args.pipeline_chunks, e2e_steps)   # the library's default: chunked pipeline
     st2 = planner.stats()
     planner.set_pipeline_chunks(0)
@@ -372,11 +511,10 @@ def main():
     # ---- per-time-step latency (levels sequential, host buffers) -----------------
     # What the drop-in does for one 20-vehicle time step: one pdmpc_plan_batch call per
     # computation level (host buffers in, host buffers out), levels one after the other.
-    # Replayed for the first (up to 8) scenarios of the rank, whose records come first.
-    lat = []
+    # Replayed for the first LAT_SCENARIOS scenarios of rank 0, whose records come first.
+    lat, lat1 = [], []
     lat_levels = 0
-    planner.set_cta_queue(True)   # what the MATLAB drop-in selects: valid-only queue in the CTA-per-search shape
-    if rank == 0:
+    if rank == 0 and not sampled and len(step_recs):
         by_step, off = {}, 0
         for step, _level, cnt in step_recs:
             lb = batch.select(np.arange(off, off + int(cnt)))
@@ -392,11 +530,9 @@ def main():
                 if rep:
                     lat.append((time.perf_counter() - t0) * 1e3)
 
-    # ---- the same time steps, ONE call each (pdmpc_plan_timestep) ------------------------------
-    # Base iter_v of all 20 vehicles + predecessor lists + fallback areas in, all plans out: one
-    # H2D, one dependency-ordered launch (searches wait for their own predecessors' flags), one D2H.
-    lat1 = []
-    if rank == 0 and ts_recs:
+        # ---- the same time steps, ONE call each (pdmpc_plan_timestep) ------------------------------
+        # Base iter_v of all 20 vehicles + predecessor lists + fallback areas in, all plans out: one
+        # H2D, one dependency-ordered launch (searches wait for their own predecessors' flags), one D2H.
         calls = []
         for step, tb, td in ts_recs:
             ro = BatchResult.empty(tb.n, Hp)
@@ -416,20 +552,25 @@ def main():
             a = np.sort(np.concatenate([r.pop_hash for _lb, r, _i, _o in by_step[step]]))
             assert np.array_equal(a, np.sort(ro.pop_hash)), f"time step {step}: one-call path != level-by-level path"
 
-    planner.set_cta_queue(False)
-
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------
     cpu = None
     if rank == 0 and world == 1:
         from oracle import oracle_py, parity
         cores = os.cpu_count() or 1
-        m = args.cpu_sample or min(n, 14000)
+        m = args.cpu_sample or min(n, 4000 if sampled else 14000)
         sample = batch.select(np.arange(m))
         t0 = time.perf_counter()
-        ref = oracle_py.plan_batch(mpa, sample, cores)
+        if sampled:
+            ref = oracle_py.mcts_plan_batch(mpa, sample, seeds[:m], args.mcts_expansions, cores)
+        else:
+            ref = oracle_py.plan_batch(mpa, sample, cores, hash_valid_pops_only=True)
         t_cpu = time.perf_counter() - t0
+        m1 = min(m, 500 if sampled else 2000)
         t0 = time.perf_counter()
-        oracle_py.plan_batch(mpa, batch.select(np.arange(min(m, 2000))), 1)
+        if sampled:
+            oracle_py.mcts_plan_batch(mpa, batch.select(np.arange(m1)), seeds[:m1], args.mcts_expansions, 1)
+        else:
+            oracle_py.plan_batch(mpa, batch.select(np.arange(m1)), 1)
         t_cpu1 = time.perf_counter() - t0
         # parity of the timed outputs against the checker, on the sample
         sub = dataclasses.replace(res, **{f.name: getattr(res, f.name)[:m] for f in dataclasses.fields(res)
@@ -437,8 +578,10 @@ def main():
         parity.compare(sub, ref)
         cpu = {"value": m / t_cpu, "unit": "plans/s", "cores": cores, "kind": "port",
                "sample": f"first {m} of the {n} timed search records, one pass, {cores} threads",
-               "single_thread_plans_per_s": min(m, 2000) / t_cpu1,
+               "single_thread_plans_per_s": m1 / t_cpu1,
                "parity_checked": True,
+               "latency_ms_per_timestep": (cpu_timestep_latency(mpa, batch, step_recs, cores)
+                                           if not sampled and len(step_recs) else None),
                "note": "C oracle restating the MATLAB reference (MATLAB R2023a unavailable here)"}
 
     if rank == 0:
@@ -448,51 +591,62 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        # DRAM traffic of the dominant kernel: one `ncu --set full` capture of this same launch
-        # (same records, same shape), summarised under profiles/; null when the workload differs
-        traffic = None
-        try:
-            cap = json.load(open(os.path.join(ROOT, "profiles", "search_kernel_traffic.json")))
-            if int(cap.get("searches", -1)) == n and cap.get("mpa") == args.mpa:
-                traffic = float(cap["dram_bytes_read"]) + float(cap["dram_bytes_write"])
-        except Exception:
-            pass
+        kname = ("pdmpc::mcts_kernel" if sampled else
+                 {1: "pdmpc::search_kernel", 2: "pdmpc::search_tile_kernel<16,...>", 3: "pdmpc::search_tile_kernel<8,...>",
+                  4: "pdmpc::search_cta_kernel", 5: "pdmpc::search_cta_kernel"}.get(shape, "pdmpc::search_kernel"))
+        cap = None if sampled else captured_kernel_figures(n, args.mpa, shape)
+        traffic = float(cap["dram_bytes_read"]) + float(cap["dram_bytes_write"]) if cap else None
         fp64_peak = planner.measure_fp64_peak()
         alg_bytes = algorithmic_bytes(batch, stats, Hp)
         achieved = alg_bytes / (ms_step * 1e-3) / 1e9
         f64 = fp64_ops(batch, stats, Hp)
+        roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": traffic,
+                "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
+                "kernel": kname, "launch_shape": shape, "algorithmic_bytes_per_launch": alg_bytes,
+                "note": "neither HBM nor the FP64 pipe binds; the search is a chain of dependent instructions per "
+                        "search, see `issue` and DESIGN.md §4.1"}
+        if not sampled:
+            roof["fp64"] = {"ops_per_launch": f64, "achieved_tops": f64 / (ms_step * 1e-3) / 1e12,
+                            "peak_tops_mul_add": fp64_peak[0], "peak_tflops_fma": fp64_peak[1],
+                            "frac": f64 / (ms_step * 1e-3) / 1e12 / fp64_peak[0],
+                            "peak_source": "measured in this run (pdmpc_measure_fp64_peak, register-only kernel)",
+                            "note": "mul/add/sqrt without FMA"}
+            if cap and cap.get("warp_instructions") and cap.get("pops"):
+                # warp instructions per pop from the ncu capture of this launch x this run's pops / this run's time,
+                # against 4 warp instructions per clock per SM (one per scheduler)
+                sm_clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
+                n_sm = int(cap.get("sms", 148))
+                inst = float(cap["warp_instructions"]) / float(cap["pops"]) * stats.total_pops
+                roof["issue"] = {"warp_inst_per_pop": float(cap["warp_instructions"]) / float(cap["pops"]),
+                                 "warp_inst_per_launch": inst,
+                                 "achieved_ginst_s": inst / (ms_step * 1e-3) / 1e9,
+                                 "peak_ginst_s": 4.0 * n_sm * sm_clk / 1e9,
+                                 "frac": inst / (ms_step * 1e-3) / (4.0 * n_sm * sm_clk),
+                                 "source": f"smsp__inst_executed.sum of the {cap.get('round', '?')} ncu capture "
+                                           "(profiles/search_kernel_traffic.json), 4 issue slots/clk/SM"}
         line = {
             "metric": "vehicle-plans/sec", "value": value, "unit": "plans/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": f"CPM Lab road network (BASELINE configs[1]), {args.vehicles} vehicles, "
-                                   f"coloring priorities, {args.mpa} MPA, Hp {Hp}, InterX checker, "
-                                   f"{args.scenarios} scenarios/GPU x {args.sim_steps} steps, pre-rolled closed loop",
-                       "searches_per_step_per_gpu": n, "l2": "flushed between timed steps (256 MiB write)",
-                       "record_generation_s": round(t_gen, 1)},
+            "higher_is_better": True, "scaling": "strong" if args.scenarios_total else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, world, n, Hp),
             "e2e": {"value": e2e_val, "unit": "plans/s", "h2d_bytes_per_step": int(st2.h2d_bytes),
                     "d2h_bytes_per_step": int(st2.d2h_bytes), "steps": e2e_steps,
                     "pipeline": "chunked copy/search overlap inside pdmpc_plan_batch (pdmpc_set_pipeline_chunks "
                                 f"{args.pipeline_chunks}: 0 = library default)",
                     "value_without_pipeline": e2e_serial,
                     "h2d_ms": st2.h2d_ms, "kernel_ms": st2.kernel_ms, "d2h_ms": st2.d2h_ms},
-            "gpu_launches": int(args.steps * 1),   # one persistent search kernel per timed step (staged path)
+            "gpu_launches": int(args.steps * launches_per_step),   # persistent search kernel(s) per timed step (staged path)
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": traffic,
-                         "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                         "kernel": "pdmpc::search_kernel", "algorithmic_bytes_per_launch": alg_bytes,
-                         "fp64": {"ops_per_launch": f64, "achieved_tops": f64 / (ms_step * 1e-3) / 1e12,
-                                  "peak_tops_mul_add": fp64_peak[0], "peak_tflops_fma": fp64_peak[1],
-                                  "frac": f64 / (ms_step * 1e-3) / 1e12 / fp64_peak[0],
-                                  "peak_source": "measured in this run (pdmpc_measure_fp64_peak, register-only kernel)",
-                                  "note": "mul/add/sqrt without FMA; latency-bound serial search, see DESIGN.md"}},
+            "roofline": roof,
             "cpu_baseline": cpu,
             "search_stats": {"pops_per_plan": stats.total_pops / max(n, 1),
                              "nodes_per_plan": stats.total_nodes / max(n, 1),
                              "exhausted_frac": float(res.is_exhausted.mean()),
-                             "obstacle_cols_per_pop": stats.total_obstacle_cols / max(stats.total_pops, 1)},
+                             "obstacle_cols_per_pop": stats.total_obstacle_cols / max(stats.total_pops, 1),
+                             "max_pops": int(res.n_pops.max()), "searches_total": n_total,
+                             "escalated_to_cta_shape": int(stats.escalated)},
             "latency_ms_per_timestep": ({"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
                                          "max": float(np.max(lat)), "n": len(lat), "levels_per_step": lat_levels,
                                          "what": "wall time of all computation levels of one 20-vehicle time step, one "
@@ -504,6 +658,7 @@ def main():
                                                           "step (predecessor hand-over on the device), host buffers in "
                                                           "and out; same time steps and answers as above"}
                                                  if lat1 else None),
+            "record_generation_s": round(t_gen, 1),
         }
         print(json.dumps(line))
     if world > 1:

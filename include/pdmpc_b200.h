@@ -174,7 +174,7 @@ typedef struct pdmpc_stats {
     int32_t handed_over;     /* shape 5: searches re-run with the exact queue after a non-unique minimum */
     int32_t shape;           /* the launch shape that actually ran (1..5, see pdmpc_set_variant): a requested
                               * shape that cannot serve a batch falls back, and says so here */
-    int32_t reserved_;
+    int32_t escalated;       /* shapes 2, 3: searches given up after pdmpc_set_escalation pops and run by the CTA shape */
 } pdmpc_stats;
 
 /* Create a planner bound to CUDA device `device_id`.  Fails (PDMPC_ERR_CUDA)
@@ -183,6 +183,10 @@ int pdmpc_create(int device_id, pdmpc_handle **out);
 int pdmpc_destroy(pdmpc_handle *h);
 const char *pdmpc_last_error(const pdmpc_handle *h);
 int pdmpc_abi_version(void);
+/* Hp of the uploaded MPA (0: none).  pdmpc_batch_in carries no Hp: every per-step array of a batch is indexed
+ * with this one, so a binding must check its arrays against it before a plan call (the MEX shim and the ctypes
+ * binding do). */
+int pdmpc_get_hp(const pdmpc_handle *h);
 
 /* Node-arena capacity (nodes per concurrently running search).  Default is the
  * full-tree bound of the uploaded MPA when it is below 2^20, else 2^20.  A
@@ -212,6 +216,13 @@ int pdmpc_set_variant(pdmpc_handle *h, int32_t variant);
  * pop), 1 = the valid-only queue of shape 5 (2-3x lower latency on collision-rich searches; pop_hash covers
  * the valid pops; pdmpc_stats.shape then reports 5).  The MATLAB drop-in turns it on. */
 int pdmpc_set_cta_queue(pdmpc_handle *h, int32_t valid_only);
+
+/* Shapes 2, 3 only: ESCALATION of the longest searches.  A tile warp needs ~5 us per pop, so one search of
+ * 8000 pops (1 in 10^5 of the road-network records) would hold a whole launch open for 40 ms.  A search that
+ * reaches `pops` pops in a tile kernel is given up there and run from scratch by the CTA shape (4, or 5 after
+ * pdmpc_set_cta_queue(1)) behind the tile kernel on the same stream.  0 = never; default 3072.  Results do not
+ * depend on it; pdmpc_stats.escalated counts the searches that took this route. */
+int pdmpc_set_escalation(pdmpc_handle *h, int32_t pops);
 
 /* Shapes 2, 3 only: polyline points (lanelet bounds + obstacles of all steps) a tile stages in shared
  * memory per search (0 = what the kernel holds, 256); polylines beyond it are read from HBM/L2.  Test knob:

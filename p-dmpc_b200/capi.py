@@ -30,7 +30,7 @@ PDMPC_ERR_ALLOC = 5
 
 EXPORTED_SYMBOLS = (
     "pdmpc_create", "pdmpc_destroy", "pdmpc_last_error", "pdmpc_abi_version",
-    "pdmpc_set_node_capacity", "pdmpc_set_variant", "pdmpc_set_tile_points", "pdmpc_set_cta_queue", "pdmpc_host_alloc", "pdmpc_host_free",
+    "pdmpc_set_node_capacity", "pdmpc_set_variant", "pdmpc_set_tile_points", "pdmpc_set_cta_queue", "pdmpc_set_escalation", "pdmpc_get_hp", "pdmpc_host_alloc", "pdmpc_host_free",
     "pdmpc_trace_staged", "pdmpc_upload_mpa", "pdmpc_plan_batch", "pdmpc_stage_batch",
     "pdmpc_run_staged", "pdmpc_sync", "pdmpc_fetch_staged", "pdmpc_get_stats", "pdmpc_stream",
     "pdmpc_mcts_plan_batch", "pdmpc_mcts_run_staged", "pdmpc_set_cta_heap_smem", "pdmpc_plan_timestep",
@@ -84,7 +84,7 @@ class Stats(C.Structure):
         ("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("total_pops", C.c_int64),
         ("total_nodes", C.c_int64), ("total_obstacle_cols", C.c_int64),
-        ("kernel_launches", C.c_int32), ("handed_over", C.c_int32), ("shape", C.c_int32), ("reserved_", C.c_int32),
+        ("kernel_launches", C.c_int32), ("handed_over", C.c_int32), ("shape", C.c_int32), ("escalated", C.c_int32),
     ]
 
 
@@ -181,6 +181,10 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.pdmpc_set_pipeline_chunks.restype = C.c_int
     lib.pdmpc_set_cta_queue.argtypes = [H, C.c_int32]
     lib.pdmpc_set_cta_queue.restype = C.c_int
+    lib.pdmpc_get_hp.argtypes = [H]
+    lib.pdmpc_get_hp.restype = C.c_int
+    lib.pdmpc_set_escalation.argtypes = [H, C.c_int32]
+    lib.pdmpc_set_escalation.restype = C.c_int
     lib.pdmpc_set_tile_points.argtypes = [H, C.c_int32]
     lib.pdmpc_set_tile_points.restype = C.c_int
     lib.pdmpc_trace_staged.argtypes = [H, C.c_int32, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64)]
@@ -276,6 +280,10 @@ class Planner:
         """Valid-only queue whenever the CTA shape runs (pdmpc_set_cta_queue)."""
         self._check(self.lib.pdmpc_set_cta_queue(self.h, 1 if valid_only else 0))
 
+    def set_escalation(self, pops: int):
+        """Shapes 2, 3: searches beyond `pops` pops go to the CTA shape (pdmpc_set_escalation; 0 = never)."""
+        self._check(self.lib.pdmpc_set_escalation(self.h, int(pops)))
+
     def set_tile_points(self, points: int = 0):
         """Shapes 2, 3 test knob (pdmpc_set_tile_points); results do not depend on it."""
         self._check(self.lib.pdmpc_set_tile_points(self.h, int(points)))
@@ -294,7 +302,14 @@ class Planner:
         self._mpa_keep = keep
         self._mpa = mpa
 
+    def _check_hp(self, b: SearchBatch):
+        """pdmpc_batch_in carries no Hp: the library indexes the per-step arrays with the MPA's (pdmpc_get_hp)."""
+        hp = int(self.lib.pdmpc_get_hp(self.h))
+        if hp and b.Hp != hp:
+            raise PdmpcError(PDMPC_ERR_BAD_INPUT, f"batch has Hp {b.Hp}, the uploaded MPA has Hp {hp}")
+
     def plan_batch(self, b: SearchBatch, raise_on_search_error: bool = True) -> BatchResult:
+        self._check_hp(b)
         r = BatchResult.empty(b.n, b.Hp)
         bi, bo = batch_in(b), batch_out(r)
         self._check(self.lib.pdmpc_plan_batch(self.h, C.byref(bi), C.byref(bo)))
@@ -306,6 +321,7 @@ class Planner:
     def plan_timestep(self, b: SearchBatch, deps, raise_on_search_error: bool = True) -> BatchResult:
         """All searches of one (or many) time steps in one dependency-ordered launch
         (pdmpc_plan_timestep): PrioritizedController.plan's hand-over of predecessors' areas on the device."""
+        self._check_hp(b)
         r = BatchResult.empty(b.n, b.Hp)
         bi, bo = batch_in(b), batch_out(r)
         pidx = deps.pred_idx if deps.pred_idx.size else np.zeros(1, dtype=np.int32)
@@ -319,6 +335,7 @@ class Planner:
 
     def joint_plan_batch(self, b: SearchBatch, n_vehicles: int, raise_on_search_error: bool = True) -> BatchResult:
         """Centralized (joint) searches: rows of `b` are searches x n_vehicles (pdmpc_joint_plan_batch)."""
+        self._check_hp(b)
         r = BatchResult.empty(b.n, b.Hp)
         bi, bo = batch_in(b), batch_out(r)
         self._check(self.lib.pdmpc_joint_plan_batch(self.h, C.byref(bi), int(n_vehicles), C.byref(bo)))
@@ -330,6 +347,7 @@ class Planner:
     def mcts_plan_batch(self, b: SearchBatch, seeds, n_expansions_max: int = 250,
                         raise_on_search_error: bool = True) -> BatchResult:
         """MonteCarloTreeSearch.run_optimizer for every search (pdmpc_mcts_plan_batch)."""
+        self._check_hp(b)
         r = BatchResult.empty(b.n, b.Hp)
         bi, bo = batch_in(b), batch_out(r)
         prm, keep = mcts_params(seeds, n_expansions_max, b.n)
@@ -346,6 +364,7 @@ class Planner:
         del keep
 
     def stage(self, b: SearchBatch):
+        self._check_hp(b)
         bi = batch_in(b)
         self._check(self.lib.pdmpc_stage_batch(self.h, C.byref(bi)))
         self._staged_n, self._staged_Hp = b.n, b.Hp

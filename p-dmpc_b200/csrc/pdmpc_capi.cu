@@ -71,6 +71,9 @@ constexpr size_t kTile4Smem = 4 * sizeof(TileSm<kTile4Heap, kTile4Pts>);
 #ifndef PDMPC_CTA_MASTERS
 #define PDMPC_CTA_MASTERS 4
 #endif
+#ifndef PDMPC_ESCALATE_POPS
+#define PDMPC_ESCALATE_POPS 3072
+#endif
 constexpr int kCtaCheckers = 12;
 constexpr int kCtaHeap = 4096, kCtaPts = 512;          // single master: heap entries / polyline points in shared memory
 constexpr int kCtaMHeap = 1024, kCtaMPts = 256;        // several masters: per search
@@ -117,6 +120,12 @@ struct pdmpc_handle {
     int tile_pts_limit = 0;           // staged-points limit of the tile shapes (0 = what the kernel holds; test knob)
     int variant_mode = 0;             // 0 = auto, 1 = latency, 2 / 3 = tiles (2 / 4 searches per warp), 4 / 5 = cta
     int cta_heap_smem = kCtaHeap;     // heap entries the CTA shape keeps in shared memory (tuning/test knob)
+    int escalate_pops = PDMPC_ESCALATE_POPS;   // tile shapes give a search up after this many pops (0 = never), pdmpc_set_escalation
+    DBuf esc;                         // [0] count, [4..] escalated search indices
+    DBuf esc_rows;                    // pipeline: packed output rows of the escalated searches
+    void *pin_esc = nullptr;
+    size_t pin_esc_cap = 0;
+
     bool cta_valid_only = false;      // pdmpc_set_cta_queue: the CTA shape runs its valid-only queue (shape 5) whenever it is chosen
     bool cta_ok = false;              // the CTA-per-search kernel is launchable (shared memory opt-in granted)
     bool cta_deps_ok = false;         // ... and its pdmpc_plan_timestep instance
@@ -148,6 +157,7 @@ struct pdmpc_handle {
     int full_tree_nodes = 0;
     int user_node_cap = 0;
     int max_branch = 0;               // mpa.maximum_branching_factor()
+    int max_area_npts = 0;            // most points of any maneuver's normal-offset area
 
     // staged batch
     bool staged = false;
@@ -226,6 +236,8 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *sink, int iters,
 extern "C" {
 
 int pdmpc_abi_version(void) { return PDMPC_ABI_VERSION; }
+
+int pdmpc_get_hp(const pdmpc_handle *h) { return h && h->has_mpa ? h->mpa.Hp : 0; }
 
 const char *pdmpc_last_error(const pdmpc_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
@@ -306,6 +318,10 @@ int pdmpc_destroy(pdmpc_handle *h) {
     h->d_depy.release();
     h->d_depn.release();
     h->wc_chunks.release();
+    h->esc.release();
+    h->esc_rows.release();
+    if (h->pin_esc) cudaFreeHost(h->pin_esc);
+
     if (h->pin_order) cudaFreeHost(h->pin_order);
     for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -407,6 +423,7 @@ int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *d) {
         return fail(h, PDMPC_ERR_BAD_INPUT, "upload_mpa: n_trims/Hp/n_edges out of range");
     CU_TRY(h, cudaSetDevice(h->device));
     std::vector<int16_t> edge_of((size_t)nT * nT, -1);
+    int max_npts = 0;
     for (int e = 0; e < nE; ++e) {
         int f = d->edge_from[e], t = d->edge_to[e];
         if (f < 1 || f > nT || t < 1 || t > nT) return fail(h, PDMPC_ERR_BAD_INPUT, "upload_mpa: edge trim out of range");
@@ -414,6 +431,7 @@ int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *d) {
         for (int k = 0; k < 3; ++k) {
             int np = d->area_npts[e * 3 + k];
             if (np < 2 || np > PDMPC_AREA_STRIDE) return fail(h, PDMPC_ERR_BAD_INPUT, "upload_mpa: area_npts out of range");
+            if (k == PDMPC_AREA_NORMAL) max_npts = std::max(max_npts, np);
         }
     }
     // successor lists: find(transition_matrix_single(t,:,k)) ascending (expand_node.m:18)
@@ -495,6 +513,7 @@ int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *d) {
     m.bytes_area = (unsigned)(ax.size() * sizeof(double));
     m.table_bytes = m.bytes_succ_ptr + m.bytes_succ_te + m.bytes_edge_d + m.bytes_area_npts + 2 * m.bytes_area;
     h->has_mpa = true;
+    h->max_area_npts = max_npts;
     h->staged = false;
     return PDMPC_OK;
 }
@@ -578,7 +597,7 @@ static int ensure_outputs(pdmpc_handle *h, int n) {
     }
     h->out_bytes = off;
     CU_TRY(h, h->d_out_pack.reserve(off));
-    CU_TRY(h, h->work_counter.reserve(sizeof(unsigned)));
+    CU_TRY(h, h->work_counter.reserve(4 * sizeof(unsigned)));   // [0] the search kernel, [1], [2] the escalation kernels
     unsigned char *base = h->d_out_pack.as<unsigned char>();
     OutDev &o = h->out;
     o.status = reinterpret_cast<int *>(base + h->out_off[0]);
@@ -730,6 +749,10 @@ static int ensure_arena(pdmpc_handle *h, int slots) {
     if (slots <= h->arena_slots && cap == h->arena.cap) return PDMPC_OK;
     slots = std::max(slots, h->arena_slots);
     const size_t tot = (size_t)slots * cap;
+    // (DBuf::reserve frees before it allocates: until all four succeed the handle must not keep pointers
+    // into buffers that may be gone — a failed call leaves NO arena, the next one allocates afresh)
+    h->arena = ArenaDev{};
+    h->arena_slots = 0;
     CU_TRY(h, h->a_a.reserve(tot * sizeof(NodeA)));
     CU_TRY(h, h->a_b.reserve(tot * sizeof(NodeB)));
     CU_TRY(h, h->a_cs.reserve(tot * sizeof(NodeCS)));
@@ -785,15 +808,62 @@ static int launch_warp_shape(pdmpc_handle *h, int shape, const BatchDev &bc, con
     return PDMPC_OK;
 }
 
+// ---- escalation: the longest searches of a throughput launch go to the CTA shape ------------------------
+// A tile warp runs a pop in ~5 us, so ONE search of 8000 pops (1 in 10^5 of the road-network records; nothing
+// in its inputs tells it apart beforehand) holds the whole launch open for 40 ms.  The tile kernels therefore
+// give a search up after `escalate_pops` pops and append its index to a list; two gated instances of the CTA
+// kernel (one master per CTA for a short list, several masters for a long one) launched behind the tile kernel
+// on the same stream run the list from scratch at 0.65-1.0 us per pop.  Results are those of any other shape.
+static bool escalation_on(const pdmpc_handle *h, int shape, int n) {
+    const int cap = h->user_node_cap ? h->user_node_cap : std::min(h->full_tree_nodes + 8, 1 << 20);
+    return (shape == 2 || shape == 3) && h->escalate_pops > 0 && h->cta_ok && cap <= kCtaFlags &&
+           n > h->num_sms && h->batch.checker == PDMPC_CHECKER_INTERX;
+}
+
+// Resets the list (count, producers-done counter, entries = -1) on stream S and names it in the batch the tile
+// kernels get.
+static int escalation_prepare(pdmpc_handle *h, int n, BatchDev *bt, cudaStream_t S) {
+    CU_TRY(h, h->esc.reserve(((size_t)n + 4) * sizeof(int)));
+    CU_TRY(h, cudaMemsetAsync(h->esc.p, 0, 4 * sizeof(int), S));
+    CU_TRY(h, cudaMemsetAsync(h->esc.as<int>() + 4, 0xff, (size_t)n * sizeof(int), S));
+    bt->pop_limit = h->escalate_pops;
+    bt->esc_count = h->esc.as<unsigned>();
+    bt->esc_done = h->esc.as<unsigned>() + 1;
+    bt->esc_list = h->esc.as<int>() + 4;
+    return PDMPC_OK;
+}
+
+// The CTA kernel over the escalation list, on stream S behind the `producers` tile CTAs (all of them joined S).
+// Measured (profiles/r02_escalation.txt): launched on a stream of its own BESIDE the tile kernel — the kernel
+// polls the list and ends when every producer has exited — it is no faster: its 16-warp CTAs only fit an SM
+// once most of the SM's tile CTAs have left, i.e. at the end anyway.  The kernel keeps the polling protocol
+// (a list that is complete when it starts is its trivial case); `ar` = arena slots of its own.
+static int launch_escalated(pdmpc_handle *h, const ArenaDev &ar, int producers, cudaStream_t S) {
+    BatchDev be = h->batch;
+    be.order = nullptr;
+    be.esc_count = h->esc.as<unsigned>();
+    be.esc_done = h->esc.as<unsigned>() + 1;
+    be.esc_list = h->esc.as<int>() + 4;
+    be.esc_producers = (unsigned)producers;
+    const int fast = h->cta_valid_only ? 1 : 0;
+    KERNEL_CTAM<<<h->num_sms, CtaShape<kCtaMasters, kCtaCheckers>::kThreads, sizeof(CtaMSmemT), S>>>(
+        h->mpa, be, h->out, ar, h->work_counter.as<unsigned>() + 1, h->cta_heap_smem, fast, DepsDev{});
+    if (cudaGetLastError() != cudaSuccess) return fail(h, PDMPC_ERR_CUDA, "escalation kernel launch failed");
+    h->stats.kernel_launches += 1;
+    return PDMPC_OK;
+}
+
 // Launches the search of the staged batch (results are identical for all shapes):
 //   1..3 see above;  4 / 5 one CTA per search (pdmpc_cta.cuh), chosen for at most one search per SM
 static int launch_search(pdmpc_handle *h, const TraceDev &tr) {
     const int n = h->batch.n;
     CU_TRY(h, cudaSetDevice(h->device));
     CU_TRY(h, cudaMemsetAsync(h->out.counters, 0, 16 * sizeof(unsigned long long), h->stream));
-    CU_TRY(h, cudaMemsetAsync(h->work_counter.p, 0, sizeof(unsigned), h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->work_counter.p, 0, 4 * sizeof(unsigned), h->stream));
     h->stats.handed_over = 0;
+    h->stats.escalated = 0;
     h->stats.shape = 0;
+    h->batch.hash_valid_only = h->cta_valid_only ? 1 : 0;
     if (n == 0) return PDMPC_OK;
     int variant = h->variant_mode;
     if (variant == 0 && n <= h->num_sms && tr.search < 0) variant = 4;   // one computation level of a time step
@@ -824,11 +894,25 @@ static int launch_search(pdmpc_handle *h, const TraceDev &tr) {
     } else {
         int slots = 0;
         warp_shape_grid(h, variant, n, &slots);
-        int rc = ensure_arena(h, slots);
+        const bool esc = escalation_on(h, variant, n) && tr.search < 0;
+        int rc = ensure_arena(h, esc ? slots + h->num_sms * kCtaMasters : slots);
         if (rc != PDMPC_OK) return rc;
+        BatchDev bt = h->batch;
+        if (esc) {
+            rc = escalation_prepare(h, n, &bt, h->stream);
+            if (rc != PDMPC_OK) return rc;
+        }
         CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
-        rc = launch_warp_shape(h, variant, h->batch, h->arena, wc, tr, h->stream);
+        rc = launch_warp_shape(h, variant, bt, h->arena, wc, tr, h->stream);
         if (rc != PDMPC_OK) return rc;
+        if (esc) {
+            ArenaDev ae = h->arena;   // its own slots behind the tile kernel's
+            const size_t off = (size_t)slots * (size_t)h->arena.cap;
+            ae.a += off; ae.b += off; ae.cs += off; ae.heap += off;
+            int dummy = 0;
+            rc = launch_escalated(h, ae, warp_shape_grid(h, variant, n, &dummy), h->stream);
+            if (rc != PDMPC_OK) return rc;
+        }
     }
     CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
     h->timing_pending_kernel = true;
@@ -899,6 +983,7 @@ int pdmpc_fetch_staged(pdmpc_handle *h, pdmpc_batch_out *out) {
     h->stats.total_nodes = (int64_t)counters[1];
     h->stats.total_obstacle_cols = (int64_t)counters[2];
     if (counters[3]) h->stats.handed_over = (int32_t)counters[3];   // shape 5: searches re-run with the exact queue
+    h->stats.escalated = (int32_t)counters[6];
 #ifdef PDMPC_PROFILE
     {
 #ifdef PDMPC_PROFILE_CHECKER
@@ -917,6 +1002,34 @@ int pdmpc_fetch_staged(pdmpc_handle *h, pdmpc_batch_out *out) {
                     (double)counters[4] / (double)counters[5], counters[5]);
     }
 #endif
+    return PDMPC_OK;
+}
+
+// Output rows of the escalated searches, packed (pipeline: their slices went to the host before the CTA
+// kernels wrote them).  One warp per item; row = the 13 output fields of one search, each padded to 8 bytes.
+struct PackDesc {
+    const unsigned char *src[13];
+    int bytes[13], off[13];
+    int row_bytes;
+};
+__global__ void pack_rows_kernel(PackDesc d, const unsigned *count, const int *list, unsigned char *rows) {
+    const unsigned n = *count;
+    const int lane = threadIdx.x % 32;
+    for (unsigned j = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32; j < n; j += gridDim.x * (blockDim.x / 32)) {
+        const size_t si = (size_t)list[j];
+        unsigned char *row = rows + (size_t)j * d.row_bytes;
+        for (int f = 0; f < 13; ++f) {
+            if (!d.src[f]) continue;
+            const unsigned char *s = d.src[f] + si * (size_t)d.bytes[f];
+            for (int q = lane; q < d.bytes[f]; q += 32) row[d.off[f] + q] = s[q];
+        }
+    }
+}
+
+int pdmpc_set_escalation(pdmpc_handle *h, int32_t pops) {
+    if (!h) return PDMPC_ERR_BAD_INPUT;
+    if (pops < 0) return fail(h, PDMPC_ERR_BAD_INPUT, "escalation threshold must be 0 (off) or a pop count");
+    h->escalate_pops = pops;
     return PDMPC_OK;
 }
 
@@ -1000,7 +1113,9 @@ static int plan_batch_pipelined(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc
         const double per_lane = (double)slots * cap * (sizeof(NodeA) + sizeof(NodeB) + sizeof(NodeCS) + sizeof(HEnt));
         lanes = std::max(2, std::min(lanes, (int)(32.0 * 1024 * 1024 * 1024 / per_lane)));
     }
-    rc = ensure_arena(h, lanes * slots);
+    h->batch.checker = in->checker;
+    const bool esc = escalation_on(h, shape, n);
+    rc = ensure_arena(h, esc ? lanes * slots + h->num_sms * kCtaMasters : lanes * slots);
     if (rc != PDMPC_OK) return rc;
     ArenaDev ar[kLanes];
     cudaStream_t comp[kLanes] = {h->stream, h->s_comp[0], h->s_comp[1], h->s_comp[2],
@@ -1026,16 +1141,28 @@ static int plan_batch_pipelined(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc
     h->stats.d2h_bytes = 0;
     h->stats.kernel_launches = 0;
     h->stats.handed_over = 0;
+    h->stats.escalated = 0;
     h->stats.shape = shape;
+    b.hash_valid_only = h->cta_valid_only ? 1 : 0;
+    b.pop_limit = 0; b.esc_list = nullptr; b.esc_count = nullptr; b.esc_done = nullptr; b.esc_producers = 0;
+    BatchDev bproto = b;     // what the chunk kernels see: + the escalation list
 
     CU_TRY(h, cudaMemsetAsync(h->out.counters, 0, 16 * sizeof(unsigned long long), h->stream));
     CU_TRY(h, cudaMemsetAsync(h->wc_chunks.p, 0, kPipelineMaxChunks * sizeof(unsigned), h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->work_counter.p, 0, 4 * sizeof(unsigned), h->stream));
+    if (esc) {
+        rc = escalation_prepare(h, n, &bproto, h->stream);
+        if (rc != PDMPC_OK) return rc;
+        rc = ensure_pinned(h, &h->pin_esc, &h->pin_esc_cap, 4096);
+        if (rc != PDMPC_OK) return rc;
+    }
     CU_TRY(h, cudaEventRecord(h->ev_fork, h->stream));
     for (auto &st : h->s_comp) CU_TRY(h, cudaStreamWaitEvent(st, h->ev_fork, 0));
     CU_TRY(h, cudaStreamWaitEvent(h->s_in, h->ev_fork, 0));
     CU_TRY(h, cudaEventRecord(h->ev[0], h->s_in));
     CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
     bool d2h_started = false;
+    int esc_producers = 0;   // tile CTAs launched: the escalation kernel ends when all of them have
     int *pin_order = static_cast<int *>(h->pin_order);
     const TraceDev tr{-1, nullptr, 0, nullptr};
     void *dsts[13] = {out->status, out->is_exhausted, out->n_expanded, out->n_pops, out->pop_hash, out->trims,
@@ -1103,12 +1230,16 @@ static int plan_batch_pipelined(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc
                                                                           h->b_llx.as<double>(), h->b_lly.as<double>(), 2 * s0);
             h->stats.kernel_launches++;
         }
-        BatchDev bc = b;
+        BatchDev bc = bproto;
         bc.n = s1 - s0;
         bc.order = h->b_order.as<int>() + s0;
         unsigned *wc = h->wc_chunks.as<unsigned>() + c;
         if (launch_warp_shape(h, shape, bc, ar[c % lanes], wc, tr, S) != PDMPC_OK)
             return bail(PDMPC_ERR_CUDA);
+        {
+            int dummy = 0;
+            esc_producers += warp_shape_grid(h, shape, bc.n, &dummy);
+        }
         if (cudaGetLastError() != cudaSuccess || cudaEventRecord(ev_done, S) != cudaSuccess ||
             cudaStreamWaitEvent(h->s_out, ev_done, 0) != cudaSuccess)
             return bail(fail(h, PDMPC_ERR_CUDA, "pipeline: search kernel launch failed"));
@@ -1128,17 +1259,63 @@ static int plan_batch_pipelined(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc
     for (int c = 0; c < C; ++c)   // every chunk joins the handle's stream
         if (c % lanes != 0 && (int)((long long)n * (c + 1) / C) > (int)((long long)n * c / C))
             CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_chunk[2 * c + 1], 0));
+    if (esc) {   // the searches the chunk kernels give up: CTA shape, all chunks' leftovers in one launch
+        ArenaDev ae = h->arena;
+        const size_t off = (size_t)lanes * (size_t)slots * (size_t)h->arena.cap;
+        ae.a += off; ae.b += off; ae.cs += off; ae.heap += off;
+        rc = launch_escalated(h, ae, esc_producers, h->stream);
+        if (rc != PDMPC_OK) return bail(rc);
+        CU_TRY(h, cudaMemcpyAsync(h->pin_esc, h->esc.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    }
     CU_TRY(h, cudaEventRecord(h->ev[1], h->s_in));
     CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
+    if (esc) {   // the counters are complete after the escalated searches
+        CU_TRY(h, cudaEventRecord(h->ev_fork, h->stream));
+        CU_TRY(h, cudaStreamWaitEvent(h->s_out, h->ev_fork, 0));
+    }
     unsigned long long counters[16] = {0};
     CU_TRY(h, cudaMemcpyAsync(counters, dbase + h->out_off[13], sizeof(counters), cudaMemcpyDeviceToHost, h->s_out));
     CU_TRY(h, cudaEventRecord(h->ev[5], h->s_out));
     rc = pipeline_sync_all(h);
     if (rc != PDMPC_OK) return rc;
+    if (esc && *static_cast<const unsigned *>(h->pin_esc) > 0) {
+        // their output rows: packed on the device, one copy, scattered into the caller's arrays
+        const unsigned cnt = *static_cast<const unsigned *>(h->pin_esc);
+        PackDesc pd;
+        int off = 0;
+        for (int i = 0; i < 13; ++i) {
+            pd.src[i] = dsts[i] ? dbase + h->out_off[i] : nullptr;
+            pd.bytes[i] = (int)per_search[i];
+            pd.off[i] = off;
+            off += ((int)per_search[i] + 7) / 8 * 8;
+        }
+        pd.row_bytes = off;
+        const size_t list_bytes = ((size_t)cnt * sizeof(int) + 15) / 16 * 16;
+        CU_TRY(h, h->esc_rows.reserve((size_t)cnt * off));
+        rc = ensure_pinned(h, &h->pin_esc, &h->pin_esc_cap, list_bytes + (size_t)cnt * off);
+        if (rc != PDMPC_OK) return rc;
+        pack_rows_kernel<<<std::min<unsigned>((cnt + 3) / 4, 256u), 128, 0, h->stream>>>(
+            pd, h->esc.as<unsigned>(), h->esc.as<int>() + 4, h->esc_rows.as<unsigned char>());
+        CU_TRY(h, cudaGetLastError());
+        h->stats.kernel_launches++;
+        unsigned char *pin = static_cast<unsigned char *>(h->pin_esc);
+        CU_TRY(h, cudaMemcpyAsync(pin, h->esc.as<int>() + 4, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaMemcpyAsync(pin + list_bytes, h->esc_rows.p, (size_t)cnt * off, cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        const int *list = reinterpret_cast<const int *>(pin);
+        for (unsigned j = 0; j < cnt; ++j) {
+            const unsigned char *row = pin + list_bytes + (size_t)j * off;
+            for (int i = 0; i < 13; ++i)
+                if (dsts[i]) memcpy(static_cast<unsigned char *>(dsts[i]) + (size_t)list[j] * per_search[i], row + pd.off[i], per_search[i]);
+        }
+        h->stats.d2h_bytes += (int64_t)(list_bytes + (size_t)cnt * off);
+    }
     h->timing_pending_h2d = h->timing_pending_kernel = h->timing_pending_d2h = true;
     h->stats.total_pops = (int64_t)counters[0];
     h->stats.total_nodes = (int64_t)counters[1];
     h->stats.total_obstacle_cols = (int64_t)counters[2];
+    if (counters[3]) h->stats.handed_over = (int32_t)counters[3];
+    h->stats.escalated = (int32_t)counters[6];
     h->staged = true;   // the device holds the whole batch: pdmpc_run_staged / pdmpc_fetch_staged work on it
     return PDMPC_OK;
 }
@@ -1229,6 +1406,9 @@ int pdmpc_plan_timestep(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_t
     }
     if ((int)order.size() != n) return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep: the predecessor relation has a cycle");
 
+    if (in->checker == PDMPC_CHECKER_INTERX && h->max_area_npts >= PDMPC_AREA_STRIDE)
+        return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep: the InterX hand-over keeps one NaN column after each planned area: "
+                                            "maneuver areas must have at most PDMPC_AREA_STRIDE - 1 points");
     h->topo_order.swap(order);
     int rc = pdmpc_stage_batch(h, in);
     h->topo_order.clear();
@@ -1284,6 +1464,7 @@ int pdmpc_plan_timestep(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_t
         dp.dep_x = h->d_depx.as<double>(); dp.dep_y = h->d_depy.as<double>(); dp.dep_n = h->d_depn.as<int>();
     }
     const bool cta_fast = h->variant_mode == 5 || h->cta_valid_only;
+    h->batch.hash_valid_only = h->cta_valid_only ? 1 : 0;   // one kind of pop_hash whatever shape runs
     h->stats.shape = use_cta ? (cta_fast ? 5 : 4) : 1;
     CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
     if (use_cta && cta_single)

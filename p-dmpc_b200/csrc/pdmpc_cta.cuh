@@ -153,7 +153,10 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
     const int lane = threadIdx.x % kWarp;
     const int Hp = m.Hp, nT = m.nT;
     volatile unsigned *vdone = sm.done;
-
+    // work items: the batch — or, with b.esc_producers > 0, the escalation list the tile kernel(s) running on
+    // another stream are still appending to (BatchDev): master slot s = blockIdx.x + gridDim.x * master takes
+    // the items s, s + S, s + 2S, ... (S = gridDim.x * NM: a short list puts one search on every SM)
+    const bool polling = b.esc_producers > 0u;
     if (threadIdx.x < NC) sm.done[threadIdx.x] = 0u;
     if (threadIdx.x == 0) { sm.n_jobs = 0u; sm.rot = 0u; sm.masters_done = 0u; }
     for (int s = 0; s < NM; ++s)
@@ -361,6 +364,7 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
     int clear_upto = 0;            // highest node id of the previous search (flags to clear)
     bool redo_exact = false;
     unsigned si_u = 0;
+    unsigned next_item = blockIdx.x + gridDim.x * (unsigned)role_master;   // escalation list: this master's next item
 
     // publish one job (an expansion, or the terminate order) on the shared ring; returns its ticket
     auto publish = [&](const NodeA &ca, double c, double s, unsigned nid0, int nchild, int sbase, int k,
@@ -392,14 +396,42 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
     for (;;) {
         // ---- fetch a search (or run the same one again with the exact queue); set-up by this warp -----------
         bool exact;
+        const bool exact_again = redo_exact;
         if (redo_exact) { redo_exact = false; exact = true; }
         else {
-            if (lane == 0) si_u = atomicAdd(work_counter, 1u);
-            si_u = __shfl_sync(FULL, si_u, 0);
+            if (!polling) {
+                if (lane == 0) si_u = atomicAdd(work_counter, 1u);
+                si_u = __shfl_sync(FULL, si_u, 0);
+            }
             exact = fast == 0;
         }
-        if (si_u >= (unsigned)b.n) break;
-        const int si = b.order ? __ldg(b.order + si_u) : (int)si_u;
+        int si;
+        if (polling) {
+            if (!exact_again) {
+                int got = -1;
+                if (lane == 0) {
+                    for (;;) {
+                        if (ld_acquire_gpu(reinterpret_cast<const int *>(b.esc_count)) > (int)next_item) {
+                            while ((got = ld_acquire_gpu(b.esc_list + next_item)) < 0) __nanosleep(200);
+                            break;
+                        }
+                        if (ld_acquire_gpu(reinterpret_cast<const int *>(b.esc_done)) >= (int)b.esc_producers &&
+                            ld_acquire_gpu(reinterpret_cast<const int *>(b.esc_count)) <= (int)next_item)
+                            break;   // every producer has exited and the list ends before this slot's next item
+                        __nanosleep(2000);
+                    }
+                }
+                got = __shfl_sync(FULL, got, 0);
+                if (got < 0) break;
+                next_item += gridDim.x * NM;
+                si_u = (unsigned)got;
+                if (lane == 0 && o.counters) atomicAdd(o.counters + 6, 1ULL);
+            }
+            si = (int)si_u;
+        } else {
+            if (si_u >= (unsigned)b.n) break;
+            si = b.order ? __ldg(b.order + si_u) : (int)si_u;
+        }
         for (int i = lane; i <= clear_upto / 16; i += kWarp) S.flag2[i] = 0u;
         for (int k = lane; k < Hp; k += kWarp) {
             S.refx[k] = __ldg(b.ref_x + (size_t)si * Hp + k);

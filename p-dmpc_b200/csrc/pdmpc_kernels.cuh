@@ -82,6 +82,17 @@ struct BatchDev {
     int n, checker;
     double dt;
     const int *order;           // work item -> search index (heaviest-looking searches first), or null
+    // pop_hash covers the popped nodes that passed their edge check only (pdmpc_set_cta_queue(1)); else every pop
+    int hash_valid_only = 0;
+    // ESCALATION (throughput shapes -> CTA shape).  A tile kernel gives a search up after `pop_limit` pops and
+    // appends its index to esc_list[atomicAdd(esc_count)] (entries start as -1); every tile CTA counts itself in
+    // esc_done when it exits.  The CTA kernel launched behind it takes its work items from that list
+    // (esc_producers = CTAs of the tile kernel(s) > 0 selects this mode) and ends when all producers are done
+    // and the list is drained — it may also run beside the tile kernel(s) on another stream.
+    int pop_limit = 0;
+    int *esc_list = nullptr;
+    unsigned *esc_count = nullptr, *esc_done = nullptr;
+    unsigned esc_producers = 0;
     const double *x0, *y0, *yaw0;
     const int *trim0;
     const double *ref_x, *ref_y, *v_ref;
@@ -699,7 +710,7 @@ __global__ void __launch_bounds__(kWarp, PDMPC_MIN_CTAS_LAT) search_kernel(MpaDe
         const unsigned id = top.id(), par = top.pid();
         const int cK = (int)top.k();
         ++n_pops;
-        hash = hash_step(hash, id);
+        if (!b.hash_valid_only) hash = hash_step(hash, id);
         if (tr.search == si && t.lane == 0) {
             if (n_pops <= tr.cap) tr.ids[n_pops - 1] = (long long)id;
             *tr.n = n_pops;
@@ -790,6 +801,7 @@ __global__ void __launch_bounds__(kWarp, PDMPC_MIN_CTAS_LAT) search_kernel(MpaDe
         }
         PROF_MARK(3);   // constraint check
         if (!valid) continue;                                   // :75-77
+        if (b.hash_valid_only) hash = hash_step(hash, id);
         if (cK == Hp) { goal = id; phase = DONE; continue; }    // :81-90
 
         // ---- expand_node.m:1-91 (nV == 1) --------------------------------------

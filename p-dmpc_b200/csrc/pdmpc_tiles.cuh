@@ -131,6 +131,15 @@ search_tile_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_c
     int sadj = 0;
 
     for (;;) {
+        if (phase == RUN && b.pop_limit > 0 && n_pops >= b.pop_limit) {
+            // ---- escalation: a search this long is the tail of the launch; the CTA shape behind this kernel
+            //      runs it from scratch at a fraction of the per-pop latency.  Nothing of it is written here.
+            if (tl == 0) {
+                const unsigned q = atomicAdd(b.esc_count, 1u);
+                st_release_gpu(b.esc_list + q, si);
+            }
+            phase = IDLE;
+        }
         if (phase == DONE) {
             // ---- results: GraphSearch.m:58-60 / :82-89 (tile-masked: other tiles wait) ----------
             __syncwarp(tmask);
@@ -297,7 +306,7 @@ search_tile_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_c
                 nbs = __ldg(m.area_npts + edge * 3 + bkind);
             }
             ++n_pops;
-            hash = hash_step(hash, id);
+            if (!b.hash_valid_only) hash = hash_step(hash, id);
             if (tr.search == si && tl == 0) {
                 if (n_pops <= tr.cap) tr.ids[n_pops - 1] = (long long)id;
                 *tr.n = n_pops;
@@ -476,6 +485,7 @@ search_tile_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_c
         __syncwarp();
 
         // ---- :75-90 ------------------------------------------------------------------------------
+        if (has && valid && b.hash_valid_only) hash = hash_step(hash, id);
         if (has && valid && cK == Hp) { goal = id; phase = DONE; }
         bool doexp = has && valid && cK < Hp;
         if (doexp && n_nodes + nchild >= ar.cap) { status = PDMPC_ERR_CAPACITY; phase = DONE; doexp = false; }
@@ -564,6 +574,11 @@ search_tile_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_c
         }
         if (doexp) n_nodes += nchild;
         __syncwarp();
+    }
+    if (b.esc_done) {   // this producer is done: everything it appended to the escalation list is visible
+        __syncwarp();
+        __threadfence();
+        if (lane == 0) atomicAdd(b.esc_done, 1u);
     }
 }
 

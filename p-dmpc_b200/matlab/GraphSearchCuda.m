@@ -67,11 +67,13 @@ classdef GraphSearchCuda < OptimizerInterface
                 right = iter.predicted_lanelet_boundary{1, 2};
             end
 
+            dynamic_obstacle_area = GraphSearchCuda.with_hdv_reachable_sets(iter, obj.checker, options.Hp);
+
             [is_exhausted, n_expanded, trims, y_pred, g_path, h_path, shapes] = pdmpc_b200_mex( ...
                 GraphSearchCuda.PLAN, obj.handle, ...
                 iter.x0(1, 1:3), iter.trim_indices(1), ...
                 squeeze(iter.reference_trajectory_points(1, :, :)), iter.v_ref(1, :), ...
-                iter.obstacles, iter.dynamic_obstacle_area, left, right, ...
+                iter.obstacles, dynamic_obstacle_area, left, right, ...
                 obj.checker, options.dt_seconds);
 
             info = ControlResultsInfo(iter.amount, options.Hp);
@@ -165,6 +167,39 @@ classdef GraphSearchCuda < OptimizerInterface
             pdmpc_b200_mex(GraphSearchCuda.UPLOAD_MPA, obj.handle, ...
                 double(mpa.transition_matrix_single), mpa.maneuvers);
             obj.mpa_key = key;
+        end
+
+    end
+
+    methods (Static)
+
+        function dyn = with_hdv_reachable_sets(iter, checker, Hp)
+            % Manual (human-driven) vehicles.  InterX checker: the reference tests the shape against the
+            % reachable sets of the adjacent HDVs of step k right after the vehicle obstacles of step k
+            % (are_constraints_satisfied_interx.m:23-31, vectorize_all_obstacles.m:47-62); the polygons are
+            % NaN-separated and the answer is "any hit", so appending them as further rows of
+            % dynamic_obstacle_area gives the same boolean.  SAT checker: the reference's HDV block never
+            % tests anything (are_constraints_satisfied_sat.m:55-66 loops over find(adj) only if ~any(adj)),
+            % so nothing is added.
+            dyn = iter.dynamic_obstacle_area;
+            adjacent_hdv = find(iter.hdv_adjacency);
+
+            if checker ~= 1 || isempty(adjacent_hdv) || isempty(iter.hdv_reachable_sets)
+                return
+            end
+
+            n_steps = min(size(iter.hdv_reachable_sets, 2), Hp);
+            rows = cell(numel(adjacent_hdv), Hp);
+            rows(:, 1:n_steps) = iter.hdv_reachable_sets(adjacent_hdv, 1:n_steps);
+            rows(cellfun(@isempty, rows)) = {zeros(2, 0)};
+
+            if isempty(dyn)
+                dyn = rows;
+            else
+                assert(size(dyn, 2) == Hp, 'pdmpc_b200:hdv', 'dynamic_obstacle_area must have Hp columns');
+                dyn = [dyn; rows];
+            end
+
         end
 
     end

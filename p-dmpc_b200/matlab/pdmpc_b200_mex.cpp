@@ -147,6 +147,7 @@ void plan(pdmpc_handle *h, int nlhs, mxArray *plhs[], const mxArray *prhs[], boo
     const mxArray *x0 = prhs[2], *ref = prhs[4], *vref = prhs[5], *obst = prhs[6], *dyn = prhs[7];
     const mxArray *left = prhs[8], *right = prhs[9];
     const int Hp = static_cast<int>(mxGetNumberOfElements(vref));
+    if (Hp != pdmpc_get_hp(h)) fail("pdmpc:input", "v_ref holds " + std::to_string(Hp) + " steps, the uploaded MPA has Hp = " + std::to_string(pdmpc_get_hp(h)));
     if (mxGetNumberOfElements(x0) < 3 || mxGetNumberOfElements(ref) != static_cast<size_t>(2 * Hp))
         fail("pdmpc:input", "x0 must hold (x, y, yaw) and ref must be Hp x 2");
     const double *px0 = mxGetDoubles(x0);
@@ -273,6 +274,7 @@ void plan_timestep(pdmpc_handle *h, int nlhs, mxArray *plhs[], const mxArray *pr
     if (N == 0 || mxGetN(x0) < 3) fail("pdmpc:input", "x0 must be N x 3");
     if (mxGetM(vref) != N) fail("pdmpc:input", "v_ref must be N x Hp");
     const int Hp = static_cast<int>(mxGetN(vref));
+    if (Hp != pdmpc_get_hp(h)) fail("pdmpc:input", "v_ref holds " + std::to_string(Hp) + " steps, the uploaded MPA has Hp = " + std::to_string(pdmpc_get_hp(h)));
     if (mxGetNumberOfElements(ref) != N * Hp * 2 || mxGetNumberOfElements(trim) != N)
         fail("pdmpc:input", "ref must be N x Hp x 2 and trims N x 1");
     if (!joint && (mxGetM(coupling) != N || mxGetN(coupling) != N))
@@ -400,9 +402,15 @@ void plan_timestep(pdmpc_handle *h, int nlhs, mxArray *plhs[], const mxArray *pr
                 mxSetCell(plhs[4], i + N * k, sh);
             }
     }
-    for (int q = 0; q < 2 && nlhs > 5 + q; ++q) {   // joint cost to come / cost to go along the path (row 1 of the search)
-        plhs[5 + q] = mxCreateDoubleMatrix(1, Hp + 1, mxREAL);
-        std::memcpy(mxGetDoubles(plhs[5 + q]), q == 0 ? g.data() : hh.data(), sizeof(double) * (Hp + 1));
+    for (int q = 0; q < 2 && nlhs > 5 + q; ++q) {
+        // cost to come / cost to go along the path: tree.g, tree.h of next_nodes (NodeInfo columns 5, 6), which
+        // PrioritizedExplorativeController.compute_solution_cost reads through tree.get_cost (:100-104).
+        // PLAN_TIMESTEP: N x (Hp+1), row i = vehicle i.  PLAN_JOINT: 1 x (Hp+1), the joint cost (row 1 of the search).
+        const size_t rows = joint ? 1 : N;
+        const std::vector<double> &src = q == 0 ? g : hh;
+        plhs[5 + q] = mxCreateDoubleMatrix(rows, Hp + 1, mxREAL);
+        for (size_t i = 0; i < rows; ++i)
+            for (int k = 0; k <= Hp; ++k) mxGetDoubles(plhs[5 + q])[i + rows * k] = src[i * (Hp + 1) + k];
     }
 }
 

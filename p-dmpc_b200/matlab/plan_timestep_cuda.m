@@ -28,6 +28,7 @@ function infos = plan_timestep_cuda(handle, hlcs, mpa, options)
     obstacles = cell(N, 0); dyn = cell(N, 0, Hp); left = cell(N, 1); right = cell(N, 1);
     fallback_shapes = cell(N, Hp);
     coupling = hlcs(1).iter.directed_coupling_sequential;
+    checker = double(~(options.scenario_type == ScenarioType.circle || ~options.is_prioritized));  % Config.m:71-87
 
     for i = 1:N
         c = hlcs(i);
@@ -39,7 +40,9 @@ function infos = plan_timestep_cuda(handle, hlcs, mpa, options)
         area_parallel = c.consider_predecessors(setdiff(predecessors, sequential), []);
         [obst_succ, area_succ] = c.consider_successors(find(iter_v.directed_coupling(i, :) == 1));
         obst_i = [iter_v.obstacles; obst_succ];
-        dyn_i = [iter_v.dynamic_obstacle_area; area_parallel; area_succ];
+        % (+ the reachable sets of adjacent manual vehicles, InterX only: GraphSearchCuda.with_hdv_reachable_sets)
+        iter_v.dynamic_obstacle_area = [iter_v.dynamic_obstacle_area; area_parallel; area_succ];
+        dyn_i = GraphSearchCuda.with_hdv_reachable_sets(iter_v, checker, Hp);
         x0(i, :) = iter_v.x0(1, 1:3);
         trims(i) = iter_v.trim_indices;
         ref(i, :, :) = iter_v.reference_trajectory_points(1, :, :);
@@ -58,8 +61,7 @@ function infos = plan_timestep_cuda(handle, hlcs, mpa, options)
         end
     end
 
-    checker = double(~(options.scenario_type == ScenarioType.circle || ~options.is_prioritized));  % Config.m:71-87
-    [is_exhausted, n_expanded, trims_out, y, shapes] = pdmpc_b200_mex(PLAN_TIMESTEP, handle, x0, trims, ref, v_ref, ...
+    [is_exhausted, n_expanded, trims_out, y, shapes, g, h] = pdmpc_b200_mex(PLAN_TIMESTEP, handle, x0, trims, ref, v_ref, ...
         obstacles, reshape(dyn, N, []), left, right, checker, options.dt_seconds, double(coupling), fallback_shapes);
     y = reshape(y, 3, Hp, N);
 
@@ -70,8 +72,10 @@ function infos = plan_timestep_cuda(handle, hlcs, mpa, options)
         info.n_expanded = n_expanded(i);
         if ~info.is_exhausted
             % next_nodes: Hp cells of 1 x 8 rows in NodeInfo order [x y yaw trim g h k exactEval]
-            next_nodes = arrayfun(@(k) [y(1, k, i), y(2, k, i), y(3, k, i), trims_out(i, k + 1), 0, 0, k, 1], 1:Hp, ...
-                UniformOutput = false);
+            % (g, h: tree.get_cost(tree_path(end)) is what the explorative / optimal controllers compare,
+            %  PrioritizedExplorativeController.m:100-104)
+            next_nodes = arrayfun(@(k) [y(1, k, i), y(2, k, i), y(3, k, i), trims_out(i, k + 1), g(i, k + 1), h(i, k + 1), k, 1], ...
+                1:Hp, UniformOutput = false);
             y_full = {[y(:, :, i)', trims_out(i, 2:end)']};
             iter_v = IterationData.filter(hlcs(i).iter, (1:options.amount) == i);
             info = OptimizerInterface.create_control_results_info_from_mex(info, iter_v, options, next_nodes, ...

@@ -33,6 +33,7 @@ def test_matlab_side_sources_present():
     assert "classdef GraphSearchCuda < OptimizerInterface" in src
     assert "function info = run_optimizer(obj, ~, iter, mpa, options, ~)" in src
     assert "create_control_results_info_from_mex" in src
+    assert "with_hdv_reachable_sets" in src and "hdv_adjacency" in src
     smp = open(os.path.join(mexfake.ROOT, "p-dmpc_b200", "matlab", "MonteCarloTreeSearchCuda.m")).read()
     assert "classdef MonteCarloTreeSearchCuda < OptimizerInterface" in smp
     assert "function info_v = run_optimizer(obj, vehicle_index, iter, mpa, options, time_step)" in smp
@@ -135,8 +136,9 @@ def test_mex_timestep_path_matches_golden(matlab, name):
         trans, man = mexfake.matlab_mpa(mpa)
         matlab.call(0, mexfake.UPLOAD_MPA, float(h), trans, man)
         for batch, deps, exp in steps[::3]:
-            exh, n_exp, trims, y, shapes = matlab.call(5, mexfake.PLAN_TIMESTEP, float(h), *_timestep_args(batch, deps))
+            exh, n_exp, trims, y, shapes, g, hh = matlab.call(7, mexfake.PLAN_TIMESTEP, float(h), *_timestep_args(batch, deps))
             n, Hp = batch.n, batch.Hp
+            assert g.shape == (n, Hp + 1) and hh.shape == (n, Hp + 1)
             assert exh.reshape(-1).astype(int).tolist() == exp.is_exhausted.tolist()
             assert n_exp.reshape(-1).astype(int).tolist() == exp.n_expanded.tolist()
             y = y.reshape(3, Hp, n, order="F")
@@ -145,6 +147,9 @@ def test_mex_timestep_path_matches_golden(matlab, name):
                     continue
                 assert trims[i].astype(int).tolist() == exp.trims[i].tolist()
                 assert np.array_equal(y[:, :, i].T.view(np.uint64), exp.y_predicted[i].view(np.uint64))
+                # costs along the path (tree.g / tree.h of next_nodes): what compute_solution_cost compares
+                assert np.array_equal(np.ascontiguousarray(g[i]).view(np.uint64), exp.g_path[i].view(np.uint64))
+                assert np.array_equal(np.ascontiguousarray(hh[i]).view(np.uint64), exp.h_path[i].view(np.uint64))
                 for k in range(Hp):
                     m = int(exp.shape_npts[i, k])
                     sh = shapes[i + n * k]
@@ -159,6 +164,8 @@ def test_timestep_matlab_helper_present():
     src = open(os.path.join(mexfake.ROOT, "p-dmpc_b200", "matlab", "plan_timestep_cuda.m")).read()
     assert "PLAN_TIMESTEP = 6" in src and "directed_coupling_sequential" in src
     assert "create_control_results_info_from_mex" in src
+    assert "g(i, k + 1), h(i, k + 1)" in src and "with_hdv_reachable_sets" in src
+    assert "g(i, k + 1), h(i, k + 1)" in src and "hdv_adjacency" in src
 
 
 @pytest.mark.gpu

@@ -370,3 +370,49 @@ def test_pipelined_plan_batch_equals_single_launch(planner, chunks):
         planner.set_pipeline_chunks(0)
     with pytest.raises(capi.PdmpcError):
         planner.set_pipeline_chunks(17)
+
+
+@pytest.mark.parametrize("variant", [2, 3])
+@pytest.mark.parametrize("valid_only", [False, True])
+def test_escalation_of_long_searches(planner, variant, valid_only):
+    """pdmpc_set_escalation: the tile shapes give searches beyond a pop threshold up and the CTA shape runs them
+    behind the tile kernel (both gated instances: a short list -> one master per CTA, a long list -> several).
+    Same outputs as without escalation and as the oracle, staged and pipelined; pdmpc_set_cta_queue(1) makes
+    pop_hash cover the valid pops in every shape, so the batch reports one kind of hash."""
+    mpa, batch = road_records("triple_speed", 8)
+    planner.upload_mpa(mpa)
+    ref = oracle_py.plan_batch(mpa, batch, 4, hash_valid_pops_only=valid_only)
+    pops = ref.n_pops.astype(np.int64)
+    try:
+        planner.set_cta_queue(valid_only)
+        planner.set_variant(variant)
+        for thr in (int(np.percentile(pops, 99.5)), int(np.percentile(pops, 70)), 8):
+            # given up after its thr-th pop unless that pop was the goal
+            expect = int(((pops > thr) | ((pops == thr) & (ref.is_exhausted != 0))).sum())
+            planner.set_escalation(thr)
+            planner.set_pipeline_chunks(1)
+            dev = planner.plan_batch(batch, raise_on_search_error=False)
+            st = planner.stats()
+            parity.compare(dev, ref)
+            assert st.shape == variant and st.escalated == expect, (thr, st.escalated, expect)
+            assert st.total_pops == int(pops.sum()) and st.total_nodes == int(ref.n_expanded.sum())
+            planner.set_pipeline_chunks(3)
+            dev = planner.plan_batch(batch, raise_on_search_error=False)
+            st = planner.stats()
+            parity.compare(dev, ref)
+            assert st.escalated == expect
+            assert st.total_pops == int(pops.sum()) and st.total_nodes == int(ref.n_expanded.sum())
+        planner.set_escalation(0)
+        dev = planner.plan_batch(batch, raise_on_search_error=False)
+        parity.compare(dev, ref)
+        assert planner.stats().escalated == 0
+        # every warp shape reports the same kind of hash
+        planner.set_variant(1)
+        parity.compare(planner.plan_batch(batch, raise_on_search_error=False), ref)
+    finally:
+        planner.set_variant(0)
+        planner.set_pipeline_chunks(0)
+        planner.set_cta_queue(False)
+        planner.set_escalation(3072)
+    with pytest.raises(capi.PdmpcError):
+        planner.set_escalation(-1)
