@@ -165,7 +165,6 @@ def test_timestep_matlab_helper_present():
     assert "PLAN_TIMESTEP = 6" in src and "directed_coupling_sequential" in src
     assert "create_control_results_info_from_mex" in src
     assert "g(i, k + 1), h(i, k + 1)" in src and "with_hdv_reachable_sets" in src
-    assert "g(i, k + 1), h(i, k + 1)" in src and "hdv_adjacency" in src
 
 
 @pytest.mark.gpu
