@@ -220,9 +220,12 @@ int pdmpc_set_cta_queue(pdmpc_handle *h, int32_t valid_only);
 /* Shapes 2, 3 only: ESCALATION of the longest searches.  A tile warp needs ~5 us per pop, so one search of
  * 8000 pops (1 in 10^5 of the road-network records) would hold a whole launch open for 40 ms.  A search that
  * reaches `pops` pops in a tile kernel is given up there and run from scratch by the CTA shape (4, or 5 after
- * pdmpc_set_cta_queue(1)) behind the tile kernel on the same stream.  0 = never; default 3072.  Results do not
- * depend on it; pdmpc_stats.escalated counts the searches that took this route. */
-int pdmpc_set_escalation(pdmpc_handle *h, int32_t pops);
+ * pdmpc_set_cta_queue(1)) behind the tile kernel on the same stream.  0 = never; default 2560.  A list of at
+ * most `short_list_max` searches (-1 = default, 3 per SM) runs with one master warp per CTA, all checker warps
+ * serving it — the launch then ends with its longest search at 0.65 us per pop —, a longer one with several
+ * masters per CTA.  Results do not depend on either; pdmpc_stats.escalated counts the searches that took this
+ * route. */
+int pdmpc_set_escalation(pdmpc_handle *h, int32_t pops, int32_t short_list_max);
 
 /* Shapes 2, 3 only: polyline points (lanelet bounds + obstacles of all steps) a tile stages in shared
  * memory per search (0 = what the kernel holds, 256); polylines beyond it are read from HBM/L2.  Test knob:
@@ -337,6 +340,20 @@ int pdmpc_joint_plan_batch(pdmpc_handle *h, const pdmpc_batch_in *in, int32_t n_
  * contraction is off for bit-exactness) and TFLOP/s of fused multiply-add.  The denominators of the
  * FP64 roofline fraction bench.py reports next to the HBM one. */
 int pdmpc_measure_fp64_peak(pdmpc_handle *h, double *mul_add_tops, double *fma_tflops);
+
+/* The plans of the LAST plan call as flat rows in DEVICE memory, ready for a collective — BASELINE configs[2]
+ * (simultaneous prioritizations): the ranks exchange the cost of every vehicle in every permutation and the
+ * winners' plans (PrioritizedExplorativeController.m:94-109 compute_solution_cost, :124-176 receive / choose /
+ * publish) with one all_gather on these rows; nothing is routed through the host before the exchange.
+ * Row r (search r of the call), L = 2 + 21*Hp doubles:
+ *   [0] cost = g_path[r][Hp] (tree.get_cost of the goal node)   [1] 1.0 if the row is a fallback plan, else 0.0
+ *   [2 .. 2+Hp) trims of steps 1..Hp   [.. +3Hp) y_predicted   [.. +Hp) shape_npts   [.. +8Hp) shape_x   [.. +8Hp) shape_y
+ * For an exhausted search the row of vehicle (r mod n_vehicles) of `fallback_rows` [n_vehicles * L] (host; the
+ * fallback plan and its cost are known before the time step, PrioritizedController.m:678-718) is taken instead
+ * (zeros if fallback_rows is NULL).  `device_dst`: n_rows * L doubles of device memory on the handle's device
+ * (e.g. a torch tensor's data pointer); complete when the call returns. */
+int pdmpc_pack_plan_rows(pdmpc_handle *h, int32_t n_rows, int32_t n_vehicles, const double *fallback_rows,
+                         void *device_dst);
 
 /* Pinned host buffers for callers that want full-rate host<->device copies. */
 int pdmpc_host_alloc(void **p, size_t bytes);

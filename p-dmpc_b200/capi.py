@@ -30,7 +30,7 @@ PDMPC_ERR_ALLOC = 5
 
 EXPORTED_SYMBOLS = (
     "pdmpc_create", "pdmpc_destroy", "pdmpc_last_error", "pdmpc_abi_version",
-    "pdmpc_set_node_capacity", "pdmpc_set_variant", "pdmpc_set_tile_points", "pdmpc_set_cta_queue", "pdmpc_set_escalation", "pdmpc_get_hp", "pdmpc_host_alloc", "pdmpc_host_free",
+    "pdmpc_set_node_capacity", "pdmpc_set_variant", "pdmpc_set_tile_points", "pdmpc_set_cta_queue", "pdmpc_set_escalation", "pdmpc_get_hp", "pdmpc_pack_plan_rows", "pdmpc_host_alloc", "pdmpc_host_free",
     "pdmpc_trace_staged", "pdmpc_upload_mpa", "pdmpc_plan_batch", "pdmpc_stage_batch",
     "pdmpc_run_staged", "pdmpc_sync", "pdmpc_fetch_staged", "pdmpc_get_stats", "pdmpc_stream",
     "pdmpc_mcts_plan_batch", "pdmpc_mcts_run_staged", "pdmpc_set_cta_heap_smem", "pdmpc_plan_timestep",
@@ -181,9 +181,11 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.pdmpc_set_pipeline_chunks.restype = C.c_int
     lib.pdmpc_set_cta_queue.argtypes = [H, C.c_int32]
     lib.pdmpc_set_cta_queue.restype = C.c_int
+    lib.pdmpc_pack_plan_rows.argtypes = [H, C.c_int32, C.c_int32, _p_f64, C.c_void_p]
+    lib.pdmpc_pack_plan_rows.restype = C.c_int
     lib.pdmpc_get_hp.argtypes = [H]
     lib.pdmpc_get_hp.restype = C.c_int
-    lib.pdmpc_set_escalation.argtypes = [H, C.c_int32]
+    lib.pdmpc_set_escalation.argtypes = [H, C.c_int32, C.c_int32]
     lib.pdmpc_set_escalation.restype = C.c_int
     lib.pdmpc_set_tile_points.argtypes = [H, C.c_int32]
     lib.pdmpc_set_tile_points.restype = C.c_int
@@ -280,9 +282,17 @@ class Planner:
         """Valid-only queue whenever the CTA shape runs (pdmpc_set_cta_queue)."""
         self._check(self.lib.pdmpc_set_cta_queue(self.h, 1 if valid_only else 0))
 
-    def set_escalation(self, pops: int):
+    def pack_plan_rows(self, n_rows: int, n_vehicles: int, fallback_rows, device_ptr: int):
+        """Plans of the last plan call as [n_rows, 2 + 21*Hp] doubles in device memory (pdmpc_pack_plan_rows)."""
+        fb = None
+        if fallback_rows is not None:
+            fb = np.ascontiguousarray(fallback_rows, dtype=np.float64)
+        self._check(self.lib.pdmpc_pack_plan_rows(self.h, int(n_rows), int(n_vehicles),
+                                                  _ptr(fb, _p_f64) if fb is not None else None, C.c_void_p(int(device_ptr))))
+
+    def set_escalation(self, pops: int, short_list_max: int = -1):
         """Shapes 2, 3: searches beyond `pops` pops go to the CTA shape (pdmpc_set_escalation; 0 = never)."""
-        self._check(self.lib.pdmpc_set_escalation(self.h, int(pops)))
+        self._check(self.lib.pdmpc_set_escalation(self.h, int(pops), int(short_list_max)))
 
     def set_tile_points(self, points: int = 0):
         """Shapes 2, 3 test knob (pdmpc_set_tile_points); results do not depend on it."""

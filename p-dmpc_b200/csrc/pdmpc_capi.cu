@@ -42,16 +42,16 @@ constexpr size_t kSmemLimit = 227 * 1024;
 // tiles: TILE lanes per search; heap entries / staged polyline points per search in shared memory;
 // one-warp CTAs per SM the shape is compiled for (register cap) — sized so that the CTAs fill 228 KB
 #ifndef PDMPC_TILE2_CTAS
-#define PDMPC_TILE2_CTAS 16
+#define PDMPC_TILE2_CTAS 20
 #endif
 #ifndef PDMPC_TILE4_CTAS
 #define PDMPC_TILE4_CTAS 8
 #endif
 #ifndef PDMPC_TILE2_HEAP
-#define PDMPC_TILE2_HEAP 96
+#define PDMPC_TILE2_HEAP 64
 #endif
 #ifndef PDMPC_TILE2_PTS
-#define PDMPC_TILE2_PTS 160
+#define PDMPC_TILE2_PTS 128
 #endif
 #ifndef PDMPC_TILE4_HEAP
 #define PDMPC_TILE4_HEAP 96
@@ -72,7 +72,7 @@ constexpr size_t kTile4Smem = 4 * sizeof(TileSm<kTile4Heap, kTile4Pts>);
 #define PDMPC_CTA_MASTERS 4
 #endif
 #ifndef PDMPC_ESCALATE_POPS
-#define PDMPC_ESCALATE_POPS 3072
+#define PDMPC_ESCALATE_POPS 2560
 #endif
 constexpr int kCtaCheckers = 12;
 constexpr int kCtaHeap = 4096, kCtaPts = 512;          // single master: heap entries / polyline points in shared memory
@@ -121,7 +121,8 @@ struct pdmpc_handle {
     int variant_mode = 0;             // 0 = auto, 1 = latency, 2 / 3 = tiles (2 / 4 searches per warp), 4 / 5 = cta
     int cta_heap_smem = kCtaHeap;     // heap entries the CTA shape keeps in shared memory (tuning/test knob)
     int escalate_pops = PDMPC_ESCALATE_POPS;   // tile shapes give a search up after this many pops (0 = never), pdmpc_set_escalation
-    DBuf esc;                         // [0] count, [4..] escalated search indices
+    int esc_short_list = -1;          // lists up to this long run with one master per CTA (-1: 3 per SM)
+    DBuf esc;                         // [0] count, [1] producers done, [4..] escalated search indices
     DBuf esc_rows;                    // pipeline: packed output rows of the escalated searches
     void *pin_esc = nullptr;
     size_t pin_esc_cap = 0;
@@ -486,11 +487,15 @@ int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *d) {
     padded(npts, sizeof(int));
     // area points zero padded to the fixed stride (the kernel places all 8 columns)
     std::vector<double> ax((size_t)nE * 3 * PDMPC_AREA_STRIDE, 0.0), ay(ax.size(), 0.0);
-    for (int e = 0; e < nE * 3; ++e)
+    bool closed = true;   // first point == last point, bit for bit (InterX shortcut b_last = b_first)
+    for (int e = 0; e < nE * 3; ++e) {
         for (int i = 0; i < d->area_npts[e]; ++i) {
             ax[(size_t)e * PDMPC_AREA_STRIDE + i] = d->area_x[(size_t)e * PDMPC_AREA_STRIDE + i];
             ay[(size_t)e * PDMPC_AREA_STRIDE + i] = d->area_y[(size_t)e * PDMPC_AREA_STRIDE + i];
         }
+        const size_t f = (size_t)e * PDMPC_AREA_STRIDE, l = f + d->area_npts[e] - 1;
+        if (memcmp(&ax[f], &ax[l], sizeof(double)) != 0 || memcmp(&ay[f], &ay[l], sizeof(double)) != 0) closed = false;
+    }
     UP(h, h->m_succ_ptr, succ_ptr.data(), succ_ptr.size());
     UP(h, h->m_succ_te, succ_te.data(), succ_te.size());
     UP(h, h->m_edge_d, edge_d.data(), edge_d.size());
@@ -505,6 +510,7 @@ int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *d) {
     m.succ_te = h->m_succ_te.as<int>();
     m.edge_d = h->m_edge_d.as<double>();
     m.area_npts = h->m_npts.as<int>();
+    m.areas_closed = closed ? 1 : 0;
     m.area_x = h->m_ax.as<double>(); m.area_y = h->m_ay.as<double>();
     m.bytes_succ_ptr = (unsigned)(succ_ptr.size() * sizeof(int));
     m.bytes_succ_te = (unsigned)(succ_te.size() * sizeof(int));
@@ -846,10 +852,17 @@ static int launch_escalated(pdmpc_handle *h, const ArenaDev &ar, int producers, 
     be.esc_list = h->esc.as<int>() + 4;
     be.esc_producers = (unsigned)producers;
     const int fast = h->cta_valid_only ? 1 : 0;
+    unsigned *wc = h->work_counter.as<unsigned>();
+    // a short list: one master per CTA, all twelve checkers serve it (0.65 us per pop: the launch then ends with
+    // its longest search, ~5 ms for 8000 pops); a long list: several masters per CTA
+    be.esc_gate_lo = 0u; be.esc_gate_hi = (unsigned)(h->esc_short_list >= 0 ? h->esc_short_list : 3 * h->num_sms);
+    KERNEL_CTA<<<h->num_sms, CtaShape<1, kCtaCheckers>::kThreads, sizeof(CtaSmemT), S>>>(
+        h->mpa, be, h->out, ar, wc + 1, h->cta_heap_smem, fast, DepsDev{});
+    be.esc_gate_lo = be.esc_gate_hi; be.esc_gate_hi = 0xffffffffu;
     KERNEL_CTAM<<<h->num_sms, CtaShape<kCtaMasters, kCtaCheckers>::kThreads, sizeof(CtaMSmemT), S>>>(
-        h->mpa, be, h->out, ar, h->work_counter.as<unsigned>() + 1, h->cta_heap_smem, fast, DepsDev{});
+        h->mpa, be, h->out, ar, wc + 2, h->cta_heap_smem, fast, DepsDev{});
     if (cudaGetLastError() != cudaSuccess) return fail(h, PDMPC_ERR_CUDA, "escalation kernel launch failed");
-    h->stats.kernel_launches += 1;
+    h->stats.kernel_launches += 2;
     return PDMPC_OK;
 }
 
@@ -1026,10 +1039,34 @@ __global__ void pack_rows_kernel(PackDesc d, const unsigned *count, const int *l
     }
 }
 
-int pdmpc_set_escalation(pdmpc_handle *h, int32_t pops) {
+// pdmpc_pack_plan_rows: one thread per (row, column).  Row layout (doubles), L = 2 + 21 * Hp:
+//   [0] cost  [1] fallback flag  [2, 2+Hp) trims 1..Hp  [.., +3Hp) y_predicted  [.., +Hp) shape_npts
+//   [.., +8Hp) shape_x  [.., +8Hp) shape_y
+__global__ void pack_plan_rows_kernel(OutDev o, int Hp, int n_rows, int n_veh, const double *fb, double *dst) {
+    const int L = 2 + 21 * Hp;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < (long long)n_rows * L;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(idx / L), c = (int)(idx % L);
+        double v;
+        if (o.is_exhausted[r]) {
+            v = fb ? fb[(size_t)(r % n_veh) * L + c] : 0.0;
+            if (c == 1) v = 1.0;
+        } else if (c == 0) v = o.g_path[(size_t)r * (Hp + 1) + Hp];     // tree.get_cost(tree_path(end))
+        else if (c == 1) v = 0.0;
+        else if (c < 2 + Hp) v = (double)o.trims[(size_t)r * (Hp + 1) + (c - 2) + 1];
+        else if (c < 2 + 4 * Hp) v = o.y_predicted[(size_t)r * Hp * 3 + (c - 2 - Hp)];
+        else if (c < 2 + 5 * Hp) v = (double)o.shape_npts[(size_t)r * Hp + (c - 2 - 4 * Hp)];
+        else if (c < 2 + 13 * Hp) v = o.shape_x[(size_t)r * Hp * kAreaStride + (c - 2 - 5 * Hp)];
+        else v = o.shape_y[(size_t)r * Hp * kAreaStride + (c - 2 - 13 * Hp)];
+        dst[idx] = v;
+    }
+}
+
+int pdmpc_set_escalation(pdmpc_handle *h, int32_t pops, int32_t short_list_max) {
     if (!h) return PDMPC_ERR_BAD_INPUT;
     if (pops < 0) return fail(h, PDMPC_ERR_BAD_INPUT, "escalation threshold must be 0 (off) or a pop count");
     h->escalate_pops = pops;
+    h->esc_short_list = short_list_max;
     return PDMPC_OK;
 }
 
@@ -1623,6 +1660,31 @@ int pdmpc_measure_fp64_peak(pdmpc_handle *h, double *mul_add_tops, double *fma_t
     *mul_add_tops = ops / (ms[0] * 1e-3) / 1e12;
     *fma_tflops = ops / (ms[1] * 1e-3) / 1e12;
     h->timing_pending_kernel = false;
+    return PDMPC_OK;
+}
+
+int pdmpc_pack_plan_rows(pdmpc_handle *h, int32_t n_rows, int32_t n_vehicles, const double *fallback_rows,
+                         void *device_dst) {
+    if (!h) return PDMPC_ERR_BAD_INPUT;
+    if (!h->staged || n_rows < 0 || n_rows > h->batch.n || n_vehicles < 1 || !device_dst)
+        return fail(h, PDMPC_ERR_BAD_INPUT, "pack_plan_rows: needs the results of a plan call, 0 <= n_rows <= its searches, "
+                                            "n_vehicles >= 1 and a device destination");
+    if (n_rows == 0) return PDMPC_OK;
+    CU_TRY(h, cudaSetDevice(h->device));
+    const int Hp = h->mpa.Hp, L = 2 + 21 * Hp;
+    const double *fb = nullptr;
+    if (fallback_rows) {
+        const size_t bytes = (size_t)n_vehicles * L * sizeof(double);
+        CU_TRY(h, h->esc_rows.reserve(bytes));   // (scratch: no escalation rows are pending between calls)
+        CU_TRY(h, cudaMemcpyAsync(h->esc_rows.p, fallback_rows, bytes, cudaMemcpyHostToDevice, h->stream));
+        fb = h->esc_rows.as<double>();
+    }
+    const long long tot = (long long)n_rows * L;
+    pack_plan_rows_kernel<<<(unsigned)std::min<long long>((tot + 255) / 256, 1184), 256, 0, h->stream>>>(
+        h->out, Hp, n_rows, n_vehicles, fb, static_cast<double *>(device_dst));
+    CU_TRY(h, cudaGetLastError());
+    h->stats.kernel_launches++;
+    CU_TRY(h, cudaStreamSynchronize(h->stream));   // the caller hands device_dst to its collective next
     return PDMPC_OK;
 }
 

@@ -153,9 +153,12 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
     const int lane = threadIdx.x % kWarp;
     const int Hp = m.Hp, nT = m.nT;
     volatile unsigned *vdone = sm.done;
-    // work items: the batch — or, with b.esc_producers > 0, the escalation list the tile kernel(s) running on
-    // another stream are still appending to (BatchDev): master slot s = blockIdx.x + gridDim.x * master takes
-    // the items s, s + S, s + 2S, ... (S = gridDim.x * NM: a short list puts one search on every SM)
+    // work items: the batch — or, with b.esc_producers > 0, the escalation list of the tile kernel(s) (BatchDev;
+    // they may still be appending to it): master slot s = blockIdx.x + gridDim.x * master takes item s first
+    // (a short list puts one search on every SM before any SM gets two), then whatever item is next on the
+    // shared ticket counter (S, S + 1, ...; S = gridDim.x * NM).  This instance runs only if the list ends up
+    // with esc_gate_lo < count <= esc_gate_hi items (two instances with different NM share one list; the gate
+    // is evaluated when the producers are done — until then the instance only waits).
     const bool polling = b.esc_producers > 0u;
     if (threadIdx.x < NC) sm.done[threadIdx.x] = 0u;
     if (threadIdx.x == 0) { sm.n_jobs = 0u; sm.rot = 0u; sm.masters_done = 0u; }
@@ -263,18 +266,8 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
                                 const double dx2 = p1.x - p0.x, dy2 = p1.y - p0.y;          // InterX.m:64
                                 const double S2 = dx2 * p0.y - dy2 * p0.x;                  // :68
                                 const unsigned vb = sshp + 128u * (unsigned)sel;
-                                unsigned c2 = 0;
-                                double2 vv = lds_f64x2(vb);
-                                double bprev = (vv.y * dx2 - vv.x * dy2) - S2;              // :71
-#pragma unroll
-                                for (int i = 0; i < kAreaStride - 1; ++i) {
-                                    if (i < ne) {
-                                        vv = lds_f64x2(vb + 16u * (unsigned)(i + 1));
-                                        const double bn = (vv.y * dx2 - vv.x * dy2) - S2;
-                                        if (bprev * bn < 0) c2 |= 1u << i;
-                                        bprev = bn;
-                                    }
-                                }
+                                unsigned c2 = m.areas_closed ? interx_c2_dispatch<true>(ne, vb, dx2, dy2, S2)
+                                                             : interx_c2_dispatch<false>(ne, vb, dx2, dy2, S2);   // :71
                                 while (c2) {                                                // C1 of the edges with C2, :70
                                     const int i = __ffs(c2) - 1;
                                     c2 &= c2 - 1u;
@@ -364,7 +357,8 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
     int clear_upto = 0;            // highest node id of the previous search (flags to clear)
     bool redo_exact = false;
     unsigned si_u = 0;
-    unsigned next_item = blockIdx.x + gridDim.x * (unsigned)role_master;   // escalation list: this master's next item
+    unsigned next_item = blockIdx.x + gridDim.x * (unsigned)role_master;   // escalation list: this master's first item
+    bool first_item = true;
 
     // publish one job (an expansion, or the terminate order) on the shared ring; returns its ticket
     auto publish = [&](const NodeA &ca, double c, double s, unsigned nid0, int nchild, int sbase, int k,
@@ -410,20 +404,19 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
             if (!exact_again) {
                 int got = -1;
                 if (lane == 0) {
-                    for (;;) {
-                        if (ld_acquire_gpu(reinterpret_cast<const int *>(b.esc_count)) > (int)next_item) {
+                    const int *cnt = reinterpret_cast<const int *>(b.esc_count);
+                    // the gate needs the final count: wait for the producers (same stream: they are done)
+                    while (ld_acquire_gpu(reinterpret_cast<const int *>(b.esc_done)) < (int)b.esc_producers) __nanosleep(2000);
+                    const int total = ld_acquire_gpu(cnt);
+                    if ((unsigned)total > b.esc_gate_lo && (unsigned)total <= b.esc_gate_hi) {
+                        if (!first_item) next_item = atomicAdd(work_counter, 1u) + gridDim.x * NM;
+                        if ((int)next_item < total)
                             while ((got = ld_acquire_gpu(b.esc_list + next_item)) < 0) __nanosleep(200);
-                            break;
-                        }
-                        if (ld_acquire_gpu(reinterpret_cast<const int *>(b.esc_done)) >= (int)b.esc_producers &&
-                            ld_acquire_gpu(reinterpret_cast<const int *>(b.esc_count)) <= (int)next_item)
-                            break;   // every producer has exited and the list ends before this slot's next item
-                        __nanosleep(2000);
                     }
                 }
+                first_item = false;
                 got = __shfl_sync(FULL, got, 0);
                 if (got < 0) break;
-                next_item += gridDim.x * NM;
                 si_u = (unsigned)got;
                 if (lane == 0 && o.counters) atomicAdd(o.counters + 6, 1ULL);
             }

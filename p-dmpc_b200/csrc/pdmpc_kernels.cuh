@@ -76,6 +76,7 @@ struct MpaDev {
     const double *area_x, *area_y;  // [nE*3*8], zero padded
     unsigned bytes_succ_ptr, bytes_succ_te, bytes_edge_d, bytes_area_npts, bytes_area;   // multiples of 16
     unsigned table_bytes;       // sum of the above (area counted twice)
+    int areas_closed;           // every maneuver area repeats its first point as its last (the reference's are)
 };
 
 struct BatchDev {
@@ -87,12 +88,12 @@ struct BatchDev {
     // ESCALATION (throughput shapes -> CTA shape).  A tile kernel gives a search up after `pop_limit` pops and
     // appends its index to esc_list[atomicAdd(esc_count)] (entries start as -1); every tile CTA counts itself in
     // esc_done when it exits.  The CTA kernel launched behind it takes its work items from that list
-    // (esc_producers = CTAs of the tile kernel(s) > 0 selects this mode) and ends when all producers are done
-    // and the list is drained — it may also run beside the tile kernel(s) on another stream.
+    // (esc_producers = CTAs of the tile kernel(s) > 0 selects this mode) once all producers are done.
     int pop_limit = 0;
     int *esc_list = nullptr;
     unsigned *esc_count = nullptr, *esc_done = nullptr;
     unsigned esc_producers = 0;
+    unsigned esc_gate_lo = 0, esc_gate_hi = 0xffffffffu;   // the CTA kernel instance runs iff lo < count <= hi
     const double *x0, *y0, *yaw0;
     const int *trim0;
     const double *ref_x, *ref_y, *v_ref;

@@ -44,6 +44,40 @@ __device__ __forceinline__ void sts_f64x2(unsigned a, double x, double y) {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
 }
 
+// C2 row of InterX.m:71 for ONE obstacle segment against the NE edges of a placed shape (vertices at `vb`, 16 bytes
+// each, padded behind the shape's last point by copies of it): bit i = b_i * b_{i+1} < 0 with
+// b_i = (y1_i*dx2 - x1_i*dy2) - S2.  All vertex loads first, then NE independent chains — no branch between
+// them, so their latencies overlap (the loop with `if (i < ne)` compiled to one serial load->5 FP64 ops->compare
+// block per vertex).  CLOSED: vertex NE is a copy of vertex 0 (closed polygon with at most NE edges, padded by
+// its last = first point), so b_NE is b_0, bit for bit, without being computed.
+template <int NE, bool CLOSED>
+__device__ __forceinline__ unsigned interx_c2_row(unsigned vb, double dx2, double dy2, double S2) {
+    double b[NE + 1];
+#pragma unroll
+    for (int i = 0; i < NE + (CLOSED ? 0 : 1); ++i) {
+        const double2 vv = lds_f64x2(vb + 16u * (unsigned)i);
+        b[i] = (vv.y * dx2 - vv.x * dy2) - S2;
+    }
+    if (CLOSED) b[NE] = b[0];
+    unsigned c2 = 0;
+#pragma unroll
+    for (int i = 0; i < NE; ++i)
+        if (b[i] * b[i + 1] < 0) c2 |= 1u << i;
+    return c2;
+}
+// ne edges, 1 <= ne <= kAreaStride - 1 (warp-uniform): the instance with the next even edge count is exact as
+// well (padded vertices repeat the last one: b_i = b_{i+1} there, b*b >= 0 never sets a bit)
+template <bool CLOSED>
+__device__ __forceinline__ unsigned interx_c2_dispatch(int ne, unsigned vb, double dx2, double dy2, double S2) {
+    static_assert(kAreaStride == 8, "edge-count dispatch");
+    switch (ne) {
+    case 7: return interx_c2_row<7, CLOSED>(vb, dx2, dy2, S2);
+    case 6: return interx_c2_row<6, CLOSED>(vb, dx2, dy2, S2);
+    case 5: return interx_c2_row<5, CLOSED>(vb, dx2, dy2, S2);
+    default: return interx_c2_row<4, CLOSED>(vb, dx2, dy2, S2) & ((1u << ne) - 1u);
+    }
+}
+
 template <int HS, int SP>
 struct __align__(16) TileSm {
     double hf[HS + 2];                      // heap costs, entry i at hf[i + 1] (pdmpc_heap_split.cuh layout)
@@ -454,21 +488,10 @@ search_tile_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_c
                     const double dx2 = p1.x - p0.x, dy2 = p1.y - p0.y;          // InterX.m:64
                     const double S2 = dx2 * p0.y - dy2 * p0.x;                  // :68
                     const unsigned vb = sshp + 128u * (unsigned)sel;
-                    unsigned c2 = 0;
-                    double2 vv = lds_f64x2(vb);
-                    double bprev = (vv.y * dx2 - vv.x * dy2) - S2;              // :71
-#pragma unroll
-                    for (int i = 0; i < kAreaStride - 1; ++i) {
-                        if (i < ne_max) {
-                            vv = lds_f64x2(vb + 16u * (unsigned)(i + 1));
-                            const double bn = (vv.y * dx2 - vv.x * dy2) - S2;
-                            if (bprev * bn < 0) c2 |= 1u << i;
-                            bprev = bn;
-                        }
-                    }
-                    while (c2) {                                                // C1 of the edges with C2, :70
-                        const int i = __ffs(c2) - 1;
-                        c2 &= c2 - 1u;
+                    const unsigned c2 = m.areas_closed ? interx_c2_dispatch<true>(ne_max, vb, dx2, dy2, S2)
+                                                       : interx_c2_dispatch<false>(ne_max, vb, dx2, dy2, S2);   // :71
+                    for (unsigned cc = c2; cc; cc &= cc - 1u) {                 // C1 of the edges with C2, :70
+                        const int i = __ffs(cc) - 1;
                         const unsigned eb = sec + 32u * (unsigned)(sel * 8 + i);
                         const double2 d1 = lds_f64x2(eb);
                         const double S1 = lds_f64(eb + 16u);

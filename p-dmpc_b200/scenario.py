@@ -763,6 +763,33 @@ def computation_level_permutations(n_levels: int, seed: int) -> np.ndarray:
     return result
 
 
+def fixed_permutation_set(n_levels: int, seed: int, count: int) -> np.ndarray:
+    """BASELINE configs[2] asks for a FIXED number of priority permutations per time step (8, one per GPU), the
+    reference generates n_CL of them (one Latin square).  [dev] pad / truncate:
+      n_CL >= count  the first `count` rows of the reference's Latin square;
+      n_CL <  count  the reference's n_CL rows first, then uniformly drawn permutations of the levels (MT19937 stream
+                     seeded seed + 7919) that are not in the set yet; if the n_CL! distinct permutations run out
+                     (n_CL <= 3), the identity is repeated.
+    The reference's own rows always come first and the choice takes the FIRST minimum, so a padded row only wins
+    when it is strictly cheaper than every reference row."""
+    perms = computation_level_permutations(n_levels, seed)
+    if perms.shape[0] >= count:
+        return perms[:count]
+    rows = [tuple(int(x) for x in r) for r in perms]
+    seen = set(rows)
+    import math
+    limit = min(count, math.factorial(n_levels))
+    rs = np.random.RandomState(int(seed) + 7919)
+    while len(rows) < limit:
+        r = tuple(int(x) + 1 for x in rs.permutation(n_levels))
+        if r not in seen:
+            seen.add(r)
+            rows.append(r)
+    while len(rows) < count:
+        rows.append(rows[0])
+    return np.array(rows, dtype=np.int64)
+
+
 def weak_components(D: np.ndarray) -> np.ndarray:
     """conncomp(digraph(D), 'Type', 'weak'): 1-based component label per vertex, components numbered in
     the order of their lowest vertex (PrioritizedExplorativeController.m:207)."""
@@ -798,10 +825,17 @@ class ExplorativeRunner(ScenarioRunner):
     [dev] the cost of an exhausted vehicle is the re-computed cost of its fallback trajectory
     (plan_fallback :696-711); the winner does not re-seed the prioritizer (:169-173)."""
 
-    def __init__(self, sc: Scenario, timestep_fn, rank: int = 0, world: int = 1, device=None, max_permutations: int = 0):
+    def __init__(self, sc: Scenario, timestep_fn, rank: int = 0, world: int = 1, device=None, max_permutations: int = 0,
+                 fixed_permutations: int = 0, exchange=None):
+        """fixed_permutations: exactly that many permutations per time step (fixed_permutation_set: BASELINE's 8).
+        exchange(n_rows_local, n, fallback_rows, mine, P, belonging) -> (chosen, solution_cost, plans): replaces the
+        host-side exchange below by one that starts from the plans in DEVICE memory (bench: pdmpc_pack_plan_rows +
+        one NCCL all_gather); fallback_rows [n, 2 + 21*Hp] = cost and plan a vehicle takes when its search is exhausted."""
         super().__init__(sc, None, timestep_fn=timestep_fn)
         self.rank, self.world, self.device = rank, world, device
-        self.max_permutations = max_permutations      # 0 = all n_CL (BASELINE: 8, one per GPU)
+        self.max_permutations = max_permutations      # 0 = all n_CL
+        self.fixed_permutations = fixed_permutations
+        self.exchange = exchange
         self.explorative_records: List[dict] = []
 
     def step(self):
@@ -814,7 +848,10 @@ class ExplorativeRunner(ScenarioRunner):
         D = (constant_priorities(A) if sc.priority == "constant" else coloring_priorities(A)).astype(bool)
         levels = kahn(D.astype(np.int64))
         n_cl = int(levels.max())
-        perms = computation_level_permutations(n_cl, self.k)
+        if self.fixed_permutations:
+            perms = fixed_permutation_set(n_cl, self.k, self.fixed_permutations)
+        else:
+            perms = computation_level_permutations(n_cl, self.k)
         if self.max_permutations:
             perms = perms[: self.max_permutations]
         P = perms.shape[0]
@@ -841,31 +878,41 @@ class ExplorativeRunner(ScenarioRunner):
             batches.append(SearchBatch.from_iters(its, Hp, sc.checker, mpa.dt_seconds))
             deps.append(TimestepDeps.build([np.flatnonzero(Dp[:, i]) for i in range(n)], [f[0] for f in fallbacks], Hp))
         plan_len = 1 + Hp + 3 * Hp + Hp + 2 * Hp * 8
-        cost_local = np.zeros((len(mine), n))
-        plans_local = np.zeros((len(mine), n, plan_len))
+
+        def fallback_row(v):
+            shapes, traj, trims = fallbacks[v]
+            npts = np.array([s.shape[1] for s in shapes])
+            sx = np.zeros((Hp, 8)); sy = np.zeros((Hp, 8))
+            for k2, s2 in enumerate(shapes):
+                sx[k2, :s2.shape[1]], sy[k2, :s2.shape[1]] = s2[0], s2[1]
+            return np.concatenate([[1.0], trims, traj.reshape(-1), npts, sx.reshape(-1), sy.reshape(-1)])
+
         res = None
+        batch = dep_all = None
         if len(mine):
             batch = SearchBatch.concat(batches)
-            res = self.timestep_fn(batch, TimestepDeps.concat(deps, [n] * len(mine)))
+            dep_all = TimestepDeps.concat(deps, [n] * len(mine))
+            res = self.timestep_fn(batch, dep_all)
+        if self.exchange is not None:
+            fb_rows = np.stack([np.concatenate([[fb_cost[v]], fallback_row(v)]) for v in range(n)])
+            chosen, solution_cost, plans = self.exchange(len(mine) * n, n, fb_rows, mine, P, belonging)
+        else:
+            cost_local = np.zeros((len(mine), n))
+            plans_local = np.zeros((len(mine), n, plan_len))
             for pl in range(len(mine)):
                 for v in range(n):
                     r = pl * n + v
                     if res.is_exhausted[r]:
-                        shapes, traj, trims = fallbacks[v]
-                        npts = np.array([s.shape[1] for s in shapes])
-                        sx = np.zeros((Hp, 8)); sy = np.zeros((Hp, 8))
-                        for k2, s2 in enumerate(shapes):
-                            sx[k2, :s2.shape[1]], sy[k2, :s2.shape[1]] = s2[0], s2[1]
                         cost_local[pl, v] = fb_cost[v]
-                        plans_local[pl, v] = np.concatenate([[1.0], trims, traj.reshape(-1), npts, sx.reshape(-1), sy.reshape(-1)])
+                        plans_local[pl, v] = fallback_row(v)
                     else:
                         cost_local[pl, v] = res.g_path[r, Hp]   # tree.get_cost(tree_path(end)), :100-104
                         plans_local[pl, v] = np.concatenate([[0.0], res.trims[r, 1:], res.y_predicted[r].reshape(-1),
                                                              res.shape_npts[r], res.shape_x[r].reshape(-1),
                                                              res.shape_y[r].reshape(-1)])
-        coll = self.world > 1
-        chosen, solution_cost = sharding.choose_permutation(cost_local, mine, P, belonging, self.device, coll)
-        plans = sharding.gather_winner_plans(plans_local, mine, P, chosen, belonging, self.device, coll)
+            coll = self.world > 1
+            chosen, solution_cost = sharding.choose_permutation(cost_local, mine, P, belonging, self.device, coll)
+            plans = sharding.gather_winner_plans(plans_local, mine, P, chosen, belonging, self.device, coll)
         shapes_now: List[Optional[List[np.ndarray]]] = [None] * n
         new_pose, new_trim = self.pose.copy(), self.trim.copy()
         for v in range(n):

@@ -62,6 +62,21 @@ def _all_gather_rows(local: np.ndarray, device=None, collective: bool = True) ->
     return np.stack([o.cpu().numpy() for o in out])
 
 
+def solution_costs(cost: np.ndarray, belonging_vector: np.ndarray):
+    """cost[p, v] -> (chosen permutation per sub-graph, rounded cost matrix [P, n_graphs]): summed per weakly
+    connected sub-graph in vehicle order (receive_solution_cost :124-144), round(., 8) and first minimum
+    (choose_solution :153-154).  Deterministic on every rank: the order of the additions is fixed here, not
+    left to a reduction collective."""
+    belonging_vector = np.asarray(belonging_vector)
+    n_graphs = int(belonging_vector.max())
+    solution_cost = np.zeros((cost.shape[0], n_graphs))
+    for g in range(1, n_graphs + 1):
+        for v in np.flatnonzero(belonging_vector == g):
+            solution_cost[:, g - 1] = solution_cost[:, g - 1] + cost[:, v]
+    solution_cost = matlab_round(solution_cost, 8)
+    return np.argmin(solution_cost, axis=0), solution_cost
+
+
 def choose_permutation(cost_local: np.ndarray, perm_ids_local: Sequence[int], n_permutations: int,
                        belonging_vector: np.ndarray, device=None, collective: bool = True):
     """cost_local[p, v]: cost-to-come of vehicle v's goal node in the p-th permutation THIS rank
@@ -82,13 +97,7 @@ def choose_permutation(cost_local: np.ndarray, perm_ids_local: Sequence[int], n_
         owned += gathered[r, 1]
     if not np.all(owned == 1.0):
         raise ValueError("every permutation must be solved by exactly one rank")
-    n_graphs = int(belonging_vector.max())
-    solution_cost = np.zeros((n_permutations, n_graphs))
-    for g in range(1, n_graphs + 1):
-        for v in np.flatnonzero(belonging_vector == g):                         # vehicle order, :124-144
-            solution_cost[:, g - 1] = solution_cost[:, g - 1] + cost[:, v]
-    solution_cost = matlab_round(solution_cost, 8)                             # :153
-    chosen = np.argmin(solution_cost, axis=0)                                   # first minimum, :154
+    chosen, solution_cost = solution_costs(cost, belonging_vector)
     return chosen, solution_cost
 
 

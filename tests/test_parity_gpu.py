@@ -386,10 +386,10 @@ def test_escalation_of_long_searches(planner, variant, valid_only):
     try:
         planner.set_cta_queue(valid_only)
         planner.set_variant(variant)
-        for thr in (int(np.percentile(pops, 99.5)), int(np.percentile(pops, 70)), 8):
+        for thr, short in ((int(np.percentile(pops, 99.5)), -1), (int(np.percentile(pops, 70)), 10), (8, -1), (8, 20)):
             # given up after its thr-th pop unless that pop was the goal
             expect = int(((pops > thr) | ((pops == thr) & (ref.is_exhausted != 0))).sum())
-            planner.set_escalation(thr)
+            planner.set_escalation(thr, short)   # short: lists up to that long -> one master per CTA, else several
             planner.set_pipeline_chunks(1)
             dev = planner.plan_batch(batch, raise_on_search_error=False)
             st = planner.stats()
@@ -413,6 +413,6 @@ def test_escalation_of_long_searches(planner, variant, valid_only):
         planner.set_variant(0)
         planner.set_pipeline_chunks(0)
         planner.set_cta_queue(False)
-        planner.set_escalation(3072)
+        planner.set_escalation(2560)
     with pytest.raises(capi.PdmpcError):
         planner.set_escalation(-1)

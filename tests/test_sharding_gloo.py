@@ -166,3 +166,63 @@ def test_computation_level_permutations_form_a_latin_square():
     D = np.zeros((5, 5), dtype=bool)
     D[0, 1] = D[3, 4] = True
     assert scenario.weak_components(D).tolist() == [1, 1, 2, 3, 3]
+
+
+def test_fixed_permutation_set_pads_and_truncates():
+    """BASELINE configs[2] fixes 8 permutations per time step: the reference's Latin-square rows first, then rows
+    of further squares (distinct while n_CL! allows), truncated when n_CL > 8."""
+    import math
+    from pdmpc_b200 import scenario
+    for n in (1, 2, 3, 4, 5, 8, 9):
+        for seed in (1, 17):
+            base = scenario.computation_level_permutations(n, seed)
+            r = scenario.fixed_permutation_set(n, seed, 8)
+            assert r.shape == (8, n)
+            m = min(n, 8)
+            assert np.array_equal(r[:m], base[:m])                       # the reference's rows come first
+            assert all(sorted(row) == list(range(1, n + 1)) for row in r)
+            distinct = len({tuple(row) for row in r})
+            assert distinct == min(8, math.factorial(n))
+            assert np.array_equal(r, scenario.fixed_permutation_set(n, seed, 8))
+
+
+def test_explorative_exchange_hook_equals_host_exchange():
+    """ExplorativeRunner(exchange=...) — the bench's device-side exchange starts from rows
+    [cost, fallback flag, trims, poses, shape sizes, shapes] per (permutation, vehicle) as pdmpc_pack_plan_rows
+    writes them; fed with the same rows built on the host it must drive the same closed loop as the built-in
+    host exchange, with 8 fixed permutations per step."""
+    from oracle import oracle_py
+    from pdmpc_b200 import scenario, sharding
+    from pdmpc_b200.mpa import get_mpa
+    mpa = get_mpa("single_speed", non_convex=True)
+    Hp = mpa.Hp
+    plan = lambda b: oracle_py.plan_batch(mpa, b)
+    last = {}
+
+    def ts(b, d):
+        last["res"] = scenario.plan_timestep_by_levels(plan, b, d)
+        return last["res"]
+
+    def exchange(n_rows, n, fb_rows, mine, P, belonging):
+        res = last["res"]
+        L = 2 + 21 * Hp
+        rows = np.zeros((n_rows, L))
+        for r in range(n_rows):
+            if res.is_exhausted[r]:
+                rows[r] = fb_rows[r % n]
+                rows[r, 1] = 1.0
+            else:
+                rows[r] = np.concatenate([[res.g_path[r, Hp], 0.0], res.trims[r, 1:], res.y_predicted[r].reshape(-1),
+                                          res.shape_npts[r], res.shape_x[r].reshape(-1), res.shape_y[r].reshape(-1)])
+        rows = rows.reshape(P, n, L)
+        chosen, cost = sharding.solution_costs(rows[:, :, 0], belonging)
+        return chosen, cost, np.stack([rows[chosen[belonging[v] - 1], v, 1:] for v in range(n)])
+
+    a = scenario.ExplorativeRunner(scenario.commonroad_scenario(mpa, 12, seed=4), ts, fixed_permutations=8, exchange=exchange)
+    b = scenario.ExplorativeRunner(scenario.commonroad_scenario(mpa, 12, seed=4), ts, fixed_permutations=8)
+    a.run(4)
+    b.run(4)
+    assert np.array_equal(a.pose, b.pose) and np.array_equal(a.trim, b.trim)
+    for x, y in zip(a.explorative_records, b.explorative_records):
+        assert x["n_permutations"] == 8 and np.array_equal(x["chosen"], y["chosen"])
+        assert np.array_equal(x["solution_cost"], y["solution_cost"])

@@ -329,3 +329,39 @@ def test_lockstep_scenarios_one_call_per_time_step(planner):
         alone = scenario.ScenarioRunner(scenario.commonroad_scenario(mpa, 20, seed=s), None, timestep_fn=ts)
         alone.run(4)
         assert np.array_equal(alone.pose, r.pose) and np.array_equal(alone.trim, r.trim)
+
+
+def test_pack_plan_rows_on_device(planner):
+    """pdmpc_pack_plan_rows: costs + plans of the last call as rows in DEVICE memory (what the ranks all_gather
+    for BASELINE configs[2]); exhausted searches take the caller's fallback rows."""
+    import torch
+    from helpers import load_golden_timesteps
+    mpa, steps = load_golden_timesteps("timestep_road_triple_speed")
+    planner.upload_mpa(mpa)
+    Hp = mpa.Hp
+    L = 2 + 21 * Hp
+    batch, deps, exp = concat_timesteps(steps[:3])
+    n_veh = steps[0][0].n
+    res = planner.plan_timestep(batch, deps, False)
+    parity.compare(res, exp)
+    assert res.is_exhausted.any() and not res.is_exhausted.all()
+    rng = np.random.default_rng(0)
+    fb = rng.normal(size=(n_veh, L))
+    dst = torch.full((batch.n, L), -7.0, dtype=torch.float64, device="cuda:0")
+    planner.pack_plan_rows(batch.n, n_veh, fb, dst.data_ptr())
+    rows = dst.cpu().numpy()
+    for r in range(batch.n):
+        if res.is_exhausted[r]:
+            want = fb[r % n_veh].copy()
+            want[1] = 1.0
+        else:
+            want = np.concatenate([[res.g_path[r, Hp], 0.0], res.trims[r, 1:], res.y_predicted[r].reshape(-1),
+                                   res.shape_npts[r], res.shape_x[r].reshape(-1), res.shape_y[r].reshape(-1)])
+        assert np.array_equal(rows[r].view(np.uint64), want.view(np.uint64)), r
+    # a prefix of the rows, no fallback rows: exhausted searches give zeros (flag 1)
+    dst.fill_(-7.0)
+    planner.pack_plan_rows(5, n_veh, None, dst.data_ptr())
+    rows = dst.cpu().numpy()
+    assert (rows[5:] == -7.0).all()
+    with pytest.raises(capi.PdmpcError):
+        planner.pack_plan_rows(batch.n + 1, n_veh, None, dst.data_ptr())

@@ -8,6 +8,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 from pdmpc_b200 import capi  # noqa: E402
+if os.environ.get('PDMPC_LIB'):
+    capi.LIB_PATH = os.environ['PDMPC_LIB']
+    capi.load_library.__defaults__ = (capi.LIB_PATH,)
 from pdmpc_b200.mpa import get_mpa  # noqa: E402
 from pdmpc_b200.records import SearchBatch  # noqa: E402
 
@@ -39,9 +42,9 @@ def main():
     pops = r.n_pops.astype(np.int64)
     t_all, sh = timed(p, b, 2)
     print(f"all {b.n}: shape {sh} {t_all:.2f} ms -> {b.n / t_all / 1e3:.3f} M plans/s; max pops {pops.max()}")
-    for vo in (False, True):
+    for vo in (True,):
         p.set_cta_queue(vo)
-        for esc in (0, 512, 768, 1024, 1536, 2048, 3072):
+        for esc in (0, 2560):
             p.set_escalation(esc)
             t, sh = timed(p, b, 2)
             p.fetch()
@@ -49,7 +52,7 @@ def main():
             print(f"valid-only {vo} escalation {esc}: {t:.2f} ms -> {b.n / t / 1e3:.3f} M plans/s (escalated {st.escalated}, launches {st.kernel_launches})")
     p.set_cta_queue(False)
     p.set_escalation(0)
-    for thr in (2000,):
+    for thr in ():
         lo = b.select(np.nonzero(pops <= thr)[0])
         hi = b.select(np.nonzero(pops > thr)[0])
         t_lo, _ = timed(p, lo, 2)

@@ -22,7 +22,9 @@ def main():
     tile = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     mpa_type = "triple_speed" if "triple" in path else "single_speed"
     mpa = get_mpa(mpa_type, non_convex=True)
-    b = SearchBatch.load(path)
+    import glob
+    files = sorted(glob.glob(path))
+    b = SearchBatch.concat([SearchBatch.load(f) for f in files]) if len(files) > 1 else SearchBatch.load(files[0])
     if reps > 1:
         b = SearchBatch.concat([b] * reps)
     p = capi.Planner(0)
@@ -36,6 +38,7 @@ def main():
         b = b.select(order)
         print('sorted by pops', mode, 'max', key.max())
     p.set_variant(tile)
+    p.set_cta_queue(True)   # as bench.py
     if os.environ.get('PDMPC_TILE_POINTS'):
         p.set_tile_points(int(os.environ['PDMPC_TILE_POINTS']))
     p.stage(b)
@@ -56,6 +59,10 @@ def main():
             a, b_ = getattr(r, f), getattr(r1, f)
             assert np.array_equal(a, b_, equal_nan=(a.dtype.kind == "f")), f
         print("identical to shape 1 on", b.n, "searches")
+    if os.environ.get('PDMPC_STATS_JSON'):
+        import json
+        json.dump({"searches": int(b.n), "mpa": mpa_type, "shape": int(st.shape), "pops": int(st.total_pops),
+                   "nodes": int(st.total_nodes), "escalated": int(st.escalated)}, open(os.environ['PDMPC_STATS_JSON'], "w"))
     print("pops", st.total_pops, "nodes", st.total_nodes, "cols", st.total_obstacle_cols,
           "exhausted", int(r.is_exhausted.sum()), "max pops", int(r.n_pops.max()))
 
