@@ -209,12 +209,17 @@ def plan_batch(mpa, batch: SearchBatch, n_threads: int = 1, hash_valid_pops_only
     return r
 
 
-def joint_plan_batch(mpa, batch: SearchBatch, n_vehicles: int, max_nodes: int = 1 << 21) -> BatchResult:
+def joint_plan_batch(mpa, batch: SearchBatch, n_vehicles: int, max_nodes: int = 1 << 21,
+                     hash_valid_pops_only: bool = False) -> BatchResult:
     """Centralized (joint) search: rows of the batch = searches x n_vehicles (oracle_joint_plan_batch)."""
     d, keep = capi.mpa_desc(mpa)
     r = BatchResult.empty(batch.n, batch.Hp)
     bi, bo = capi.batch_in(batch), capi.batch_out(r)
-    rc = lib().oracle_joint_plan_batch(C.byref(d), C.byref(bi), int(n_vehicles), C.byref(bo), int(max_nodes))
+    lib().oracle_set_hash_valid_pops_only(1 if hash_valid_pops_only else 0)
+    try:
+        rc = lib().oracle_joint_plan_batch(C.byref(d), C.byref(bi), int(n_vehicles), C.byref(bo), int(max_nodes))
+    finally:
+        lib().oracle_set_hash_valid_pops_only(0)
     if rc != 0:
         raise RuntimeError(f"oracle_joint_plan_batch failed: {rc}")
     del keep

@@ -612,7 +612,7 @@ static int joint_search_one(const pdmpc_mpa_desc *mpa, const pdmpc_batch_in *in,
         int64_t id = oracle_pq_pop(&pq, NULL);
         if (id == -1) { exhausted = 1; break; }
         ++n_pops;
-        hash = fnv1a_u32(hash, (uint32_t)id);
+        if (!g_hash_valid_only) hash = fnv1a_u32(hash, (uint32_t)id);
         int is_valid = 1;
         int32_t par = t->parent[id];
         if (par) {
@@ -652,6 +652,7 @@ static int joint_search_one(const pdmpc_mpa_desc *mpa, const pdmpc_batch_in *in,
             }
         }
         if (!is_valid) continue;
+        if (g_hash_valid_only) hash = fnv1a_u32(hash, (uint32_t)id);
         if (t->k[id] == Hp) { goal = id; break; }
 
         /* expand_node.m */

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kWarp) joint_search_kernel(MpaDev m, BatchDev 
             const JNode cn = nn[id];
             const unsigned par = cn.parent;
             ++n_pops;
-            hash = hash_step(hash, id);
+            if (!b.hash_valid_only) hash = hash_step(hash, id);
             bool valid = true;
             if (par != 0) {   // eval_edge_exact, GraphSearch.m:150-192
                 const int sp0 = __ldg(slot + 0), sp1 = __ldg(slot + 1), dp0 = __ldg(slot + cK), dp1 = __ldg(slot + cK + 1);
@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(kWarp) joint_search_kernel(MpaDev m, BatchDev 
                 }
             }
             if (!valid) continue;                         // :75-77
+            if (b.hash_valid_only) hash = hash_step(hash, id);
             if (cK == Hp) { goal = id; break; }           // :81-90
 
             // ---- expand_node.m -----------------------------------------------------------------

@@ -69,23 +69,46 @@ def test_centralized_closed_loop_on_the_oracle():
     assert (np.hypot(*(r.pose[:, :2] - start[:, :2]).T) > 0.3).all() and r.n_fallbacks == 0
 
 
+# the three ways a joint search runs on the device: one CTA per search with the factorized expansion and the
+# reference's exact queue (default) or the valid-only queue (pdmpc_set_cta_queue(1): pop_hash then covers the
+# popped nodes that passed their check), and the one-warp kernel that follows the reference statement by statement
+JOINT_MODES = ("cta_exact", "cta_valid_only", "warp")
+
+
+class joint_mode:
+    def __init__(self, planner, mode):
+        self.planner, self.mode = planner, mode
+
+    def __enter__(self):
+        self.planner.set_variant(1 if self.mode == "warp" else 0)
+        self.planner.set_cta_queue(self.mode == "cta_valid_only")
+        return self.mode == "cta_valid_only"      # -> hash_valid_pops_only of the oracle
+
+    def __exit__(self, *a):
+        self.planner.set_variant(0)
+        self.planner.set_cta_queue(False)
+
+
 @pytest.mark.gpu
-def test_joint_search_matches_oracle(planner):
+@pytest.mark.parametrize("mode", JOINT_MODES)
+def test_joint_search_matches_oracle(planner, mode):
     mpa = get_mpa("single_speed", non_convex=False)
     planner.upload_mpa(mpa)
     CAP = 1 << 23
     planner.set_node_capacity(CAP)
     try:
-        solved = 0
-        for name, batch, nV in joint_cases(mpa):
-            ref = oracle_py.joint_plan_batch(mpa, batch, nV, max_nodes=CAP)
-            dev = planner.joint_plan_batch(batch, nV, raise_on_search_error=False)
-            try:
-                parity.compare(dev, ref)
-            except AssertionError as e:
-                raise AssertionError(f"{name}: {e}")
-            solved += int((ref.status == 0).sum())
-        assert solved >= 10 and ref.n_expanded[0] > 1000
+        with joint_mode(planner, mode) as hv:
+            solved = 0
+            for name, batch, nV in joint_cases(mpa):
+                ref = oracle_py.joint_plan_batch(mpa, batch, nV, max_nodes=CAP, hash_valid_pops_only=hv)
+                dev = planner.joint_plan_batch(batch, nV, raise_on_search_error=False)
+                try:
+                    parity.compare(dev, ref)
+                except AssertionError as e:
+                    raise AssertionError(f"{name}: {e}")
+                solved += int((ref.status == 0).sum())
+                assert planner.stats().shape == {"cta_exact": 4, "cta_valid_only": 5, "warp": 1}[mode]
+            assert solved >= 10 and ref.n_expanded[0] > 1000
     finally:
         planner.set_node_capacity(0)
 
@@ -107,7 +130,8 @@ def test_joint_nv1_equals_plain_search_and_triple_speed(planner):
 
 
 @pytest.mark.gpu
-def test_centralized_closed_loop_circle(planner):
+@pytest.mark.parametrize("mode", JOINT_MODES)
+def test_centralized_closed_loop_circle(planner, mode):
     """Circle scenario, 2 and 3 vehicles, centralized (the reference's system tests run these sizes,
     tests/systemtests/systemtests.m:16-34): closed loop on the device equals the oracle-driven one."""
     mpa = get_mpa("single_speed", non_convex=False)
@@ -115,16 +139,18 @@ def test_centralized_closed_loop_circle(planner):
     CAP = 1 << 23
     planner.set_node_capacity(CAP)
     try:
-        for amount, steps in ((2, 12), (3, 2)):
-            dev = scenario.CentralizedRunner(scenario.circle_scenario(mpa, amount), lambda b, n: planner.joint_plan_batch(b, n, False))
-            ref = scenario.CentralizedRunner(scenario.circle_scenario(mpa, amount),
-                                             lambda b, n: oracle_py.joint_plan_batch(mpa, b, n, max_nodes=CAP))
-            dev.run(steps)
-            ref.run(steps)
-            assert np.array_equal(dev.pose, ref.pose) and np.array_equal(dev.trim, ref.trim)
-            for (_k, _b, a), (_k2, _b2, e) in zip(dev.joint_records, ref.joint_records):
-                parity.compare(a, e)
-            assert sum(int(e.status[0] == 0) for _k, _b, e in ref.joint_records) >= steps - 1
+        with joint_mode(planner, mode) as hv:
+            for amount, steps in ((2, 12), (3, 2 if mode != "warp" else 1)):
+                dev = scenario.CentralizedRunner(scenario.circle_scenario(mpa, amount), lambda b, n: planner.joint_plan_batch(b, n, False))
+                ref = scenario.CentralizedRunner(scenario.circle_scenario(mpa, amount),
+                                                 lambda b, n: oracle_py.joint_plan_batch(mpa, b, n, max_nodes=CAP,
+                                                                                         hash_valid_pops_only=hv))
+                dev.run(steps)
+                ref.run(steps)
+                assert np.array_equal(dev.pose, ref.pose) and np.array_equal(dev.trim, ref.trim)
+                for (_k, _b, a), (_k2, _b2, e) in zip(dev.joint_records, ref.joint_records):
+                    parity.compare(a, e)
+                assert sum(int(e.status[0] == 0) for _k, _b, e in ref.joint_records) >= steps - 1
     finally:
         planner.set_node_capacity(0)
 
@@ -137,9 +163,11 @@ def test_joint_errors_are_loud(planner):
     b2 = SearchBatch.from_iters(crossing_pair(mpa), Hp, CHECKER_SAT, mpa.dt_seconds)
     planner.set_node_capacity(512)
     try:
-        r = planner.joint_plan_batch(b2, 2, raise_on_search_error=False)
-        assert (r.status == capi.PDMPC_ERR_CAPACITY).all()
-        parity.compare(r, oracle_py.joint_plan_batch(mpa, b2, 2, max_nodes=512))
+        for mode in JOINT_MODES:
+            with joint_mode(planner, mode) as hv:
+                r = planner.joint_plan_batch(b2, 2, raise_on_search_error=False)
+                assert (r.status == capi.PDMPC_ERR_CAPACITY).all()
+                parity.compare(r, oracle_py.joint_plan_batch(mpa, b2, 2, max_nodes=512, hash_valid_pops_only=hv))
     finally:
         planner.set_node_capacity(0)
     for bad_nv in (0, 5, 3):

@@ -23,6 +23,11 @@ p = capi.Planner(0)
 p.upload_mpa(mpa)
 CAP = 1 << 23
 p.set_node_capacity(CAP)
+MODE = sys.argv[1] if len(sys.argv) > 1 else "cta_valid_only"   # cta_exact | cta_valid_only | warp
+p.set_variant(1 if MODE == "warp" else 0)
+p.set_cta_queue(MODE == "cta_valid_only")
+HV = MODE == "cta_valid_only"
+print("mode", MODE)
 rng = np.random.default_rng(1)
 for J in (1, 64, 512):
     rows = []
@@ -38,12 +43,13 @@ for J in (1, 64, 512):
     wall = time.perf_counter() - t0
     st = p.stats()
     t0 = time.perf_counter()
-    ref = oracle_py.joint_plan_batch(mpa, b, 2, max_nodes=cap)
+    ref = oracle_py.joint_plan_batch(mpa, b, 2, max_nodes=cap, hash_valid_pops_only=HV)
     t_cpu = time.perf_counter() - t0
     parity.compare(r, ref)
     print(json.dumps({"joint_searches": J, "vehicles": 2, "nodes_per_search": float(ref.n_expanded[::2].mean()),
                       "pops_per_search": float(ref.n_pops[::2].mean()), "kernel_ms": st.kernel_ms, "call_ms": wall * 1e3,
-                      "gpu_joint_plans_per_s": J / (st.kernel_ms * 1e-3), "oracle_1thread_joint_plans_per_s": J / t_cpu}))
+                      "gpu_joint_plans_per_s": J / (st.kernel_ms * 1e-3), "oracle_1thread_joint_plans_per_s": J / t_cpu,
+                      "rerun_exact": int(st.handed_over)}))
 p.set_node_capacity(CAP)
 sc = scenario.circle_scenario(mpa, 3)
 run = scenario.CentralizedRunner(sc, None)
@@ -53,8 +59,46 @@ p.joint_plan_batch(b, 3, False)
 r = p.joint_plan_batch(b, 3, False)
 st = p.stats()
 t0 = time.perf_counter()
-ref = oracle_py.joint_plan_batch(mpa, b, 3, max_nodes=CAP)
+ref = oracle_py.joint_plan_batch(mpa, b, 3, max_nodes=CAP, hash_valid_pops_only=HV)
 t_cpu = time.perf_counter() - t0
 parity.compare(r, ref)
 print(json.dumps({"joint_searches": 1, "vehicles": 3, "nodes": int(ref.n_expanded[0]), "pops": int(ref.n_pops[0]),
                   "kernel_ms": st.kernel_ms, "oracle_1thread_ms": t_cpu * 1e3}))
+
+# --- vehicles a little off their reference lines (no exact left/right mirror ties) and the circle closed loop ----
+rows = []
+for _ in range(64):
+    gap, off = rng.uniform(0.2, 0.6), rng.uniform(0.4, 0.9)
+    e = rng.normal(scale=2e-3, size=6)
+    a, c = straight_iter(mpa, x=0.0, y=0.0, yaw=0.0), straight_iter(mpa, x=off, y=-gap, yaw=np.pi / 2)
+    a.x0[:3] += e[:3]
+    c.x0[:3] += e[3:]
+    rows += [a, c]
+for J in (1, 64):
+    b = SearchBatch.from_iters(rows[: 2 * J], mpa.Hp, CHECKER_SAT, mpa.dt_seconds)
+    p.joint_plan_batch(b, 2, False)
+    r = p.joint_plan_batch(b, 2, False)
+    st = p.stats()
+    t0 = time.perf_counter()
+    ref = oracle_py.joint_plan_batch(mpa, b, 2, max_nodes=CAP, hash_valid_pops_only=HV)
+    t_cpu = time.perf_counter() - t0
+    parity.compare(r, ref)
+    print(json.dumps({"perturbed": True, "joint_searches": J, "vehicles": 2, "nodes_per_search": float(ref.n_expanded[::2].mean()),
+                      "pops_per_search": float(ref.n_pops[::2].mean()), "kernel_ms": st.kernel_ms,
+                      "oracle_1thread_ms": t_cpu * 1e3, "rerun_exact": int(st.handed_over)}))
+for amount, steps in ((2, 10), (3, 4)):
+    kms, reruns, cpu_ms = [], [], []
+
+    def jp(b, n):
+        r = p.joint_plan_batch(b, n, False)
+        st = p.stats()
+        kms.append(st.kernel_ms)
+        reruns.append(int(st.handed_over))
+        t0 = time.perf_counter()
+        oracle_py.joint_plan_batch(mpa, b, n, max_nodes=CAP)
+        cpu_ms.append((time.perf_counter() - t0) * 1e3)
+        return r
+    run = scenario.CentralizedRunner(scenario.circle_scenario(mpa, amount), jp)
+    run.run(steps)
+    print(json.dumps({"closed_loop_circle": amount, "kernel_ms_per_step": [round(x, 2) for x in kms], "rerun_exact": reruns,
+                      "oracle_1thread_ms_per_step": [round(x, 2) for x in cpu_ms]}))
