@@ -20,7 +20,6 @@
 #include "pdmpc_mcts.cuh"
 #include "pdmpc_cta.cuh"
 #include "pdmpc_joint.cuh"
-#include "pdmpc_joint_cta.cuh"
 
 using namespace pdmpc;
 
@@ -122,7 +121,6 @@ struct pdmpc_handle {
     int variant_mode = 0;             // 0 = auto, 1 = latency, 2 / 3 = tiles (2 / 4 searches per warp), 4 / 5 = cta
     int cta_heap_smem = kCtaHeap;     // heap entries the CTA shape keeps in shared memory (tuning/test knob)
     int escalate_pops = PDMPC_ESCALATE_POPS;   // tile shapes give a search up after this many pops (0 = never), pdmpc_set_escalation
-    bool joint_warp_kernel = false;   // pdmpc_set_variant(1): joint searches by the one-warp kernel (cross-check)
     int esc_short_list = -1;          // lists up to this long run with one master per CTA (-1: 3 per SM)
     DBuf esc;                         // [0] count, [1] producers done, [4..] escalated search indices
     DBuf esc_rows;                    // pipeline: packed output rows of the escalated searches
@@ -360,7 +358,6 @@ int pdmpc_set_variant(pdmpc_handle *h, int32_t variant) {
         return fail(h, PDMPC_ERR_BAD_INPUT,
                     "variant must be 0 (auto), 1 (one search per warp), 2 / 3 (tiles: 2 / 4 searches per warp), 4 (cta) or 5 (cta, valid-only queue)");
     h->variant_mode = variant;
-    h->joint_warp_kernel = variant == 1;
     return PDMPC_OK;
 }
 
@@ -1006,7 +1003,6 @@ int pdmpc_fetch_staged(pdmpc_handle *h, pdmpc_batch_out *out) {
         static const char *names[8] = {"c:wait_job", "c:tables+place", "c:interx_obstacles", "c:interx_rest", "c:sincos+publish", "-", "-", "c:other"};
 #else
         static const char *names[8] = {"setup", "heap_pop", "loads+place", "check", "expand", "heap_push", "wait_children", "loop"};
-        // (joint CTA kernel: setup, pop, node state, phase A items, phase B pairs, phase C children + pushes, accounting)
 #endif
         double tot = 0;
         for (int i = 0; i < 8; ++i) tot += (double)counters[8 + i];
@@ -1549,35 +1545,9 @@ int pdmpc_joint_plan_batch(pdmpc_handle *h, const pdmpc_batch_in *in, int32_t n_
     CU_TRY(h, cudaMemsetAsync(h->work_counter.p, 0, sizeof(unsigned), h->stream));
     h->stats.kernel_launches = 0;
     h->batch.hash_valid_only = h->cta_valid_only ? 1 : 0;
-    if (nj > 0 && h->max_branch <= kJSucc && !h->joint_warp_kernel) {
-        // one CTA per search, factorized expansion (pdmpc_joint_cta.cuh); valid-only queue after pdmpc_set_cta_queue(1)
-        const int grid = std::min(nj, h->num_sms);
-        // default capacity: what 4 GiB of arena give every resident search, at least 2^17 nodes
-        const double per_node = (double)sizeof(JNode2) + sizeof(HEnt);
-        int cap = h->user_node_cap ? h->user_node_cap
-                                   : (int)std::min<double>(kJointMaxCap, std::max<double>(1 << 17, 4.0 * (1 << 30) / (grid * per_node)));
-        cap = std::min(cap, kJointMaxCap);
-        JointCtaArena ar;
-        ar.cap = cap; ar.nV = n_vehicles;
-        ar.xstride = (int)(sizeof(JXHdr) + (size_t)n_vehicles * sizeof(JVeh));
-        ar.xcap = std::max(1024, std::min(cap, 1 << 20));      // expanded nodes: a small fraction of the created ones
-        const size_t tot = (size_t)grid * cap;
-        CU_TRY(h, h->j_veh.reserve((size_t)grid * ar.xcap * ar.xstride));
-        CU_TRY(h, h->j_node.reserve(tot * sizeof(JNode2)));
-        CU_TRY(h, h->j_heap.reserve(tot * sizeof(HEnt)));
-        ar.xrec = h->j_veh.as<unsigned char>(); ar.node = h->j_node.as<JNode2>(); ar.heap = h->j_heap.as<HEnt>();
-        CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
-        CU_TRY(h, cudaFuncSetAttribute(joint_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JointCtaSmem)));
-        joint_cta_kernel<<<grid, kJThreads, sizeof(JointCtaSmem), h->stream>>>(h->mpa, h->batch, h->out, ar,
-                                                                              h->work_counter.as<unsigned>());
-        CU_TRY(h, cudaGetLastError());
-        CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
-        h->timing_pending_kernel = true;
-        h->stats.kernel_launches = 1;
-        h->stats.shape = h->cta_valid_only ? 5 : 4;
-    } else if (nj > 0) {
-        // one warp per search, the reference's loop statement by statement (pdmpc_joint.cuh): MPAs whose
-        // branching exceeds what the factorized tables hold, and the cross-check of the CTA kernel in the tests
+    if (nj > 0) {
+        // one warp per search, the reference's loop statement by statement (pdmpc_joint.cuh; a CTA-per-search kernel
+        // with factorized expansion was measured no faster: profiles/r02_joint_factorized_experiment.txt)
         const int grid = std::min(nj, h->num_sms * 2);   // two searches per SM (shared-memory heap tops)
         // default capacity: what 2 GiB of arena give every resident search, at least 2^17 nodes
         const double per_node = (double)n_vehicles * sizeof(JVeh) + sizeof(JNode) + sizeof(HEnt);

@@ -69,10 +69,8 @@ def test_centralized_closed_loop_on_the_oracle():
     assert (np.hypot(*(r.pose[:, :2] - start[:, :2]).T) > 0.3).all() and r.n_fallbacks == 0
 
 
-# the three ways a joint search runs on the device: one CTA per search with the factorized expansion and the
-# reference's exact queue (default) or the valid-only queue (pdmpc_set_cta_queue(1): pop_hash then covers the
-# popped nodes that passed their check), and the one-warp kernel that follows the reference statement by statement
-JOINT_MODES = ("cta_exact", "cta_valid_only", "warp")
+# pop_hash over every pop (default) or, after pdmpc_set_cta_queue(1), over the popped nodes that passed their check
+JOINT_MODES = ("full_hash", "valid_hash")
 
 
 class joint_mode:
@@ -80,12 +78,10 @@ class joint_mode:
         self.planner, self.mode = planner, mode
 
     def __enter__(self):
-        self.planner.set_variant(1 if self.mode == "warp" else 0)
-        self.planner.set_cta_queue(self.mode == "cta_valid_only")
-        return self.mode == "cta_valid_only"      # -> hash_valid_pops_only of the oracle
+        self.planner.set_cta_queue(self.mode == "valid_hash")
+        return self.mode == "valid_hash"      # -> hash_valid_pops_only of the oracle
 
     def __exit__(self, *a):
-        self.planner.set_variant(0)
         self.planner.set_cta_queue(False)
 
 
@@ -107,7 +103,6 @@ def test_joint_search_matches_oracle(planner, mode):
                 except AssertionError as e:
                     raise AssertionError(f"{name}: {e}")
                 solved += int((ref.status == 0).sum())
-                assert planner.stats().shape == {"cta_exact": 4, "cta_valid_only": 5, "warp": 1}[mode]
             assert solved >= 10 and ref.n_expanded[0] > 1000
     finally:
         planner.set_node_capacity(0)
@@ -140,7 +135,7 @@ def test_centralized_closed_loop_circle(planner, mode):
     planner.set_node_capacity(CAP)
     try:
         with joint_mode(planner, mode) as hv:
-            for amount, steps in ((2, 12), (3, 2 if mode != "warp" else 1)):
+            for amount, steps in ((2, 12), (3, 2 if mode == "full_hash" else 1)):
                 dev = scenario.CentralizedRunner(scenario.circle_scenario(mpa, amount), lambda b, n: planner.joint_plan_batch(b, n, False))
                 ref = scenario.CentralizedRunner(scenario.circle_scenario(mpa, amount),
                                                  lambda b, n: oracle_py.joint_plan_batch(mpa, b, n, max_nodes=CAP,

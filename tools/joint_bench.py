@@ -23,10 +23,9 @@ p = capi.Planner(0)
 p.upload_mpa(mpa)
 CAP = 1 << 23
 p.set_node_capacity(CAP)
-MODE = sys.argv[1] if len(sys.argv) > 1 else "cta_valid_only"   # cta_exact | cta_valid_only | warp
-p.set_variant(1 if MODE == "warp" else 0)
-p.set_cta_queue(MODE == "cta_valid_only")
-HV = MODE == "cta_valid_only"
+MODE = sys.argv[1] if len(sys.argv) > 1 else "full_hash"   # full_hash | valid_hash (pdmpc_set_cta_queue 1)
+p.set_cta_queue(MODE == "valid_hash")
+HV = MODE == "valid_hash"
 print("mode", MODE)
 rng = np.random.default_rng(1)
 for J in (1, 64, 512):
