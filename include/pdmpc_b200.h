@@ -60,6 +60,7 @@ extern "C" {
 #define PDMPC_MAX_TRIMS 128
 /* Most vehicles of one centralized (joint) search (pdmpc_joint_plan_batch). */
 #define PDMPC_MAX_JOINT 4
+#define PDMPC_MAX_PRED_LANELETS 8   /* predicted lanelets per vehicle: at most Hp + 1 distinct ones */
 
 enum pdmpc_status {
     PDMPC_OK = 0,
@@ -354,6 +355,43 @@ int pdmpc_measure_fp64_peak(pdmpc_handle *h, double *mul_add_tops, double *fma_t
  * (e.g. a torch tensor's data pointer); complete when the call returns. */
 int pdmpc_pack_plan_rows(pdmpc_handle *h, int32_t n_rows, int32_t n_vehicles, const double *fallback_rows,
                          void *device_dst);
+
+/* ---- The input side of a time step on the device: per vehicle the reference trajectory over
+ *      the horizon and the lanelet boundary of the predicted lanelets — what HighLevelController fills into
+ *      iter.reference_trajectory_points / v_ref / predicted_lanelets / predicted_lanelet_boundary before the
+ *      optimizer runs (get_reference_trajectory.m:28-46, sample_reference_trajectory.m:24-97,
+ *      get_arc_distance_to_endpoint.m:41-113, projection_2d.m, get_predicted_lanelets.m:25-62,
+ *      get_lanelets_boundary.m:19-68).  Road + reference paths are uploaded once (cached in the handle). ----- */
+typedef struct pdmpc_road_desc {
+    int32_t n_lanelets;
+    const int32_t *bound_ptr;       /* [2*n_lanelets+1]: left bound of lanelet l (0-based) at [bound_ptr[2l], bound_ptr[2l+1]),
+                                     *   right bound at [bound_ptr[2l+1], bound_ptr[2l+2]) — lanelet_boundaries{l}{1:2} */
+    const double *bound_x, *bound_y;
+    int32_t n_paths;                /* reference paths (one per vehicle of every scenario) */
+    const int32_t *path_ptr;        /* [n_paths+1] into path_x / path_y: reference_path (n x 2) */
+    const double *path_x, *path_y;
+    const int32_t *lan_ptr;         /* [n_paths+1] into lanelets_index / points_index */
+    const int32_t *lanelets_index;  /* lanelet ids (1-based) along the path: reference_path_struct.lanelets_index */
+    const int32_t *points_index;    /* 1-based index of the last path point of each of them: .points_index */
+    const uint8_t *is_loop;         /* [n_paths] */
+    const double *reference_speed;  /* [n_paths] */
+} pdmpc_road_desc;
+
+typedef struct pdmpc_inputs_out {   /* caller-owned host buffers; NULL fields are not copied back */
+    double *ref_x, *ref_y, *v_ref;  /* [n*Hp] iter.reference_trajectory_points(:, :, 1:2), iter.v_ref */
+    int32_t *ref_index;             /* [n*Hp] reference_trajectory_struct.points_index (1-based) */
+    int32_t *current_index;         /* [n] current_point_index */
+    int32_t *predicted_lanelets;    /* [n*PDMPC_MAX_PRED_LANELETS] 1-based lanelet ids, 0 padded */
+    int32_t *lane_ptr;              /* [2n+1] as pdmpc_batch_in.lane_ptr */
+    double *lane_x, *lane_y;        /* [lane_capacity] as pdmpc_batch_in.lane_x / lane_y */
+    int32_t lane_capacity;          /* PDMPC_ERR_CAPACITY if the bounds need more points */
+} pdmpc_inputs_out;
+
+int pdmpc_upload_road(pdmpc_handle *h, const pdmpc_road_desc *road);
+/* Row i: the vehicle on reference path path_id[i] (0-based) stands at (x[i], y[i]) and drives at speed[i]
+ * (mpa.trims(trim).speed).  Needs an uploaded MPA (Hp) and road.  One warp per row. */
+int pdmpc_sample_inputs(pdmpc_handle *h, int32_t n, const int32_t *path_id, const double *x, const double *y,
+                        const double *speed, double dt_seconds, pdmpc_inputs_out *out);
 
 /* Pinned host buffers for callers that want full-rate host<->device copies. */
 int pdmpc_host_alloc(void **p, size_t bytes);

@@ -30,7 +30,7 @@ PDMPC_ERR_ALLOC = 5
 
 EXPORTED_SYMBOLS = (
     "pdmpc_create", "pdmpc_destroy", "pdmpc_last_error", "pdmpc_abi_version",
-    "pdmpc_set_node_capacity", "pdmpc_set_variant", "pdmpc_set_tile_points", "pdmpc_set_cta_queue", "pdmpc_set_escalation", "pdmpc_get_hp", "pdmpc_pack_plan_rows", "pdmpc_host_alloc", "pdmpc_host_free",
+    "pdmpc_set_node_capacity", "pdmpc_set_variant", "pdmpc_set_tile_points", "pdmpc_set_cta_queue", "pdmpc_set_escalation", "pdmpc_get_hp", "pdmpc_pack_plan_rows", "pdmpc_upload_road", "pdmpc_sample_inputs", "pdmpc_host_alloc", "pdmpc_host_free",
     "pdmpc_trace_staged", "pdmpc_upload_mpa", "pdmpc_plan_batch", "pdmpc_stage_batch",
     "pdmpc_run_staged", "pdmpc_sync", "pdmpc_fetch_staged", "pdmpc_get_stats", "pdmpc_stream",
     "pdmpc_mcts_plan_batch", "pdmpc_mcts_run_staged", "pdmpc_set_cta_heap_smem", "pdmpc_plan_timestep",
@@ -77,6 +77,22 @@ class BatchOut(C.Structure):
         ("g_path", _p_f64), ("h_path", _p_f64), ("shape_npts", _p_i32),
         ("shape_x", _p_f64), ("shape_y", _p_f64),
     ]
+
+
+class RoadDescC(C.Structure):
+    _fields_ = [("n_lanelets", C.c_int32), ("bound_ptr", _p_i32), ("bound_x", _p_f64), ("bound_y", _p_f64),
+                ("n_paths", C.c_int32), ("path_ptr", _p_i32), ("path_x", _p_f64), ("path_y", _p_f64),
+                ("lan_ptr", _p_i32), ("lanelets_index", _p_i32), ("points_index", _p_i32),
+                ("is_loop", C.POINTER(C.c_uint8)), ("reference_speed", _p_f64)]
+
+
+class InputsOutC(C.Structure):
+    _fields_ = [("ref_x", _p_f64), ("ref_y", _p_f64), ("v_ref", _p_f64), ("ref_index", _p_i32), ("current_index", _p_i32),
+                ("predicted_lanelets", _p_i32), ("lane_ptr", _p_i32), ("lane_x", _p_f64), ("lane_y", _p_f64),
+                ("lane_capacity", C.c_int32)]
+
+
+MAX_PRED_LANELETS = 8
 
 
 class Stats(C.Structure):
@@ -183,6 +199,10 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.pdmpc_set_cta_queue.restype = C.c_int
     lib.pdmpc_pack_plan_rows.argtypes = [H, C.c_int32, C.c_int32, _p_f64, C.c_void_p]
     lib.pdmpc_pack_plan_rows.restype = C.c_int
+    lib.pdmpc_upload_road.argtypes = [H, C.POINTER(RoadDescC)]
+    lib.pdmpc_upload_road.restype = C.c_int
+    lib.pdmpc_sample_inputs.argtypes = [H, C.c_int32, _p_i32, _p_f64, _p_f64, _p_f64, C.c_double, C.POINTER(InputsOutC)]
+    lib.pdmpc_sample_inputs.restype = C.c_int
     lib.pdmpc_get_hp.argtypes = [H]
     lib.pdmpc_get_hp.restype = C.c_int
     lib.pdmpc_set_escalation.argtypes = [H, C.c_int32, C.c_int32]
@@ -289,6 +309,40 @@ class Planner:
             fb = np.ascontiguousarray(fallback_rows, dtype=np.float64)
         self._check(self.lib.pdmpc_pack_plan_rows(self.h, int(n_rows), int(n_vehicles),
                                                   _ptr(fb, _p_f64) if fb is not None else None, C.c_void_p(int(device_ptr))))
+
+    def upload_road(self, tables: dict):
+        """Road boundaries + reference paths (scenario.road_tables) for pdmpc_sample_inputs (pdmpc_upload_road)."""
+        t = {k: np.ascontiguousarray(v) for k, v in tables.items()}
+        d = RoadDescC(n_lanelets=int(t["bound_ptr"].size // 2), bound_ptr=_ptr(t["bound_ptr"], _p_i32),
+                      bound_x=_ptr(t["bound_x"], _p_f64), bound_y=_ptr(t["bound_y"], _p_f64),
+                      n_paths=int(t["path_ptr"].size - 1), path_ptr=_ptr(t["path_ptr"], _p_i32),
+                      path_x=_ptr(t["path_x"], _p_f64), path_y=_ptr(t["path_y"], _p_f64),
+                      lan_ptr=_ptr(t["lan_ptr"], _p_i32), lanelets_index=_ptr(t["lanelets_index"], _p_i32),
+                      points_index=_ptr(t["points_index"], _p_i32), is_loop=_ptr(t["is_loop"], C.POINTER(C.c_uint8)),
+                      reference_speed=_ptr(t["reference_speed"], _p_f64))
+        self._check(self.lib.pdmpc_upload_road(self.h, C.byref(d)))
+
+    def sample_inputs(self, path_id, x, y, speed, dt_seconds: float, lane_capacity: int = 0) -> dict:
+        """Reference trajectories and lanelet boundaries of n vehicles on the device (pdmpc_sample_inputs):
+        ref_x, ref_y, v_ref [n, Hp], ref_index [n, Hp], current_index [n], predicted_lanelets [n, 8],
+        lane_ptr [2n + 1], lane_x, lane_y."""
+        path_id = np.ascontiguousarray(path_id, dtype=np.int32)
+        x, y, speed = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, speed))
+        n, Hp = int(path_id.size), int(self.lib.pdmpc_get_hp(self.h))
+        cap = int(lane_capacity) or 512 * max(n, 1)
+        o = {"ref_x": np.zeros((n, Hp)), "ref_y": np.zeros((n, Hp)), "v_ref": np.zeros((n, Hp)),
+             "ref_index": np.zeros((n, Hp), dtype=np.int32), "current_index": np.zeros(n, dtype=np.int32),
+             "predicted_lanelets": np.zeros((n, MAX_PRED_LANELETS), dtype=np.int32),
+             "lane_ptr": np.zeros(2 * n + 1, dtype=np.int32), "lane_x": np.zeros(cap), "lane_y": np.zeros(cap)}
+        oc = InputsOutC(ref_x=_ptr(o["ref_x"], _p_f64), ref_y=_ptr(o["ref_y"], _p_f64), v_ref=_ptr(o["v_ref"], _p_f64),
+                        ref_index=_ptr(o["ref_index"], _p_i32), current_index=_ptr(o["current_index"], _p_i32),
+                        predicted_lanelets=_ptr(o["predicted_lanelets"], _p_i32), lane_ptr=_ptr(o["lane_ptr"], _p_i32),
+                        lane_x=_ptr(o["lane_x"], _p_f64), lane_y=_ptr(o["lane_y"], _p_f64), lane_capacity=cap)
+        self._check(self.lib.pdmpc_sample_inputs(self.h, n, _ptr(path_id, _p_i32), _ptr(x, _p_f64), _ptr(y, _p_f64),
+                                                 _ptr(speed, _p_f64), float(dt_seconds), C.byref(oc)))
+        tot = int(o["lane_ptr"][-1])
+        o["lane_x"], o["lane_y"] = o["lane_x"][:tot], o["lane_y"][:tot]
+        return o
 
     def set_escalation(self, pops: int, short_list_max: int = -1):
         """Shapes 2, 3: searches beyond `pops` pops go to the CTA shape (pdmpc_set_escalation; 0 = never)."""

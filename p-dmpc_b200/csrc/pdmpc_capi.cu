@@ -20,6 +20,7 @@
 #include "pdmpc_mcts.cuh"
 #include "pdmpc_cta.cuh"
 #include "pdmpc_joint.cuh"
+#include "pdmpc_inputs.cuh"
 
 using namespace pdmpc;
 
@@ -187,6 +188,13 @@ struct pdmpc_handle {
     DBuf a_a, a_b, a_cs, a_heap;
     int arena_slots = 0;
 
+    // road + reference paths (pdmpc_upload_road) and the buffers of pdmpc_sample_inputs
+    bool has_road = false;
+    RoadDev road{};
+    std::vector<int> road_bound_ptr;   // host copy (capacity checks)
+    DBuf r_bptr, r_bx, r_by, r_pptr, r_px, r_py, r_lptr, r_lidx, r_pidx, r_loop, r_speed;
+    DBuf i_pid, i_x, i_y, i_speed, i_refx, i_refy, i_vref, i_ridx, i_cur, i_pred, i_pre, i_cnt, i_lptr, i_lx, i_ly;
+
     // trace (debug / parity tests)
     DBuf t_ids, t_n;
 
@@ -319,6 +327,10 @@ int pdmpc_destroy(pdmpc_handle *h) {
     h->d_depy.release();
     h->d_depn.release();
     h->wc_chunks.release();
+    for (DBuf *b : {&h->r_bptr, &h->r_bx, &h->r_by, &h->r_pptr, &h->r_px, &h->r_py, &h->r_lptr, &h->r_lidx, &h->r_pidx,
+                    &h->r_loop, &h->r_speed, &h->i_pid, &h->i_x, &h->i_y, &h->i_speed, &h->i_refx, &h->i_refy, &h->i_vref,
+                    &h->i_ridx, &h->i_cur, &h->i_pred, &h->i_pre, &h->i_cnt, &h->i_lptr, &h->i_lx, &h->i_ly})
+        b->release();
     h->esc.release();
     h->esc_rows.release();
     if (h->pin_esc) cudaFreeHost(h->pin_esc);
@@ -1689,6 +1701,116 @@ int pdmpc_pack_plan_rows(pdmpc_handle *h, int32_t n_rows, int32_t n_vehicles, co
     CU_TRY(h, cudaGetLastError());
     h->stats.kernel_launches++;
     CU_TRY(h, cudaStreamSynchronize(h->stream));   // the caller hands device_dst to its collective next
+    return PDMPC_OK;
+}
+
+int pdmpc_upload_road(pdmpc_handle *h, const pdmpc_road_desc *r) {
+    if (!h) return PDMPC_ERR_BAD_INPUT;
+    if (!r || r->n_lanelets < 1 || r->n_paths < 1 || !r->bound_ptr || !r->bound_x || !r->bound_y || !r->path_ptr ||
+        !r->path_x || !r->path_y || !r->lan_ptr || !r->lanelets_index || !r->points_index || !r->is_loop || !r->reference_speed)
+        return fail(h, PDMPC_ERR_BAD_INPUT, "upload_road: NULL table or empty road");
+    h->has_road = false;
+    const int nb = 2 * r->n_lanelets, np = r->n_paths;
+    for (int i = 0; i < nb; ++i)
+        if (r->bound_ptr[i + 1] - r->bound_ptr[i] < 2 || r->bound_ptr[0] != 0)
+            return fail(h, PDMPC_ERR_BAD_INPUT, "upload_road: every lanelet bound needs at least two points");
+    for (int p = 0; p < np; ++p) {
+        if (r->path_ptr[p + 1] - r->path_ptr[p] < 2 || r->lan_ptr[p + 1] - r->lan_ptr[p] < 1)
+            return fail(h, PDMPC_ERR_BAD_INPUT, "upload_road: a reference path needs two points and one lanelet");
+        for (int j = r->lan_ptr[p]; j < r->lan_ptr[p + 1]; ++j)
+            if (r->lanelets_index[j] < 1 || r->lanelets_index[j] > r->n_lanelets)
+                return fail(h, PDMPC_ERR_BAD_INPUT, "upload_road: lanelet id out of range");
+    }
+    CU_TRY(h, cudaSetDevice(h->device));
+    UP(h, h->r_bptr, r->bound_ptr, nb + 1);
+    UP(h, h->r_bx, r->bound_x, r->bound_ptr[nb]);
+    UP(h, h->r_by, r->bound_y, r->bound_ptr[nb]);
+    UP(h, h->r_pptr, r->path_ptr, np + 1);
+    UP(h, h->r_px, r->path_x, r->path_ptr[np]);
+    UP(h, h->r_py, r->path_y, r->path_ptr[np]);
+    UP(h, h->r_lptr, r->lan_ptr, np + 1);
+    UP(h, h->r_lidx, r->lanelets_index, r->lan_ptr[np]);
+    UP(h, h->r_pidx, r->points_index, r->lan_ptr[np]);
+    UP(h, h->r_loop, r->is_loop, np);
+    UP(h, h->r_speed, r->reference_speed, np);
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    RoadDev &d = h->road;
+    d.n_lanelets = r->n_lanelets; d.n_paths = np;
+    d.bound_ptr = h->r_bptr.as<int>(); d.bound_x = h->r_bx.as<double>(); d.bound_y = h->r_by.as<double>();
+    d.path_ptr = h->r_pptr.as<int>(); d.path_x = h->r_px.as<double>(); d.path_y = h->r_py.as<double>();
+    d.lan_ptr = h->r_lptr.as<int>(); d.lanelets_index = h->r_lidx.as<int>(); d.points_index = h->r_pidx.as<int>();
+    d.is_loop = h->r_loop.as<unsigned char>(); d.reference_speed = h->r_speed.as<double>();
+    h->has_road = true;
+    return PDMPC_OK;
+}
+
+int pdmpc_sample_inputs(pdmpc_handle *h, int32_t n, const int32_t *path_id, const double *x, const double *y,
+                        const double *speed, double dt_seconds, pdmpc_inputs_out *out) {
+    if (!h) return PDMPC_ERR_BAD_INPUT;
+    if (!h->has_mpa) return fail(h, PDMPC_ERR_NO_MPA, "sample_inputs: call pdmpc_upload_mpa first (Hp)");
+    if (!h->has_road) return fail(h, PDMPC_ERR_BAD_INPUT, "sample_inputs: call pdmpc_upload_road first");
+    if (n < 0 || !out || (n && (!path_id || !x || !y || !speed)) || out->lane_capacity < 0)
+        return fail(h, PDMPC_ERR_BAD_INPUT, "sample_inputs: NULL argument");
+    for (int i = 0; i < n; ++i)
+        if (path_id[i] < 0 || path_id[i] >= h->road.n_paths)
+            return fail(h, PDMPC_ERR_BAD_INPUT, "sample_inputs: path_id out of range");
+    if (n == 0) {
+        if (out->lane_ptr) out->lane_ptr[0] = 0;
+        return PDMPC_OK;
+    }
+    CU_TRY(h, cudaSetDevice(h->device));
+    const int Hp = h->mpa.Hp;
+    const size_t nh = (size_t)n * Hp;
+    h->stats.h2d_bytes = 0;
+    h->stats.d2h_bytes = 0;
+    h->stats.kernel_launches = 0;
+    UP(h, h->i_pid, path_id, n);
+    UP(h, h->i_x, x, n);
+    UP(h, h->i_y, y, n);
+    UP(h, h->i_speed, speed, n);
+    CU_TRY(h, h->i_refx.reserve(nh * sizeof(double)));
+    CU_TRY(h, h->i_refy.reserve(nh * sizeof(double)));
+    CU_TRY(h, h->i_vref.reserve(nh * sizeof(double)));
+    CU_TRY(h, h->i_ridx.reserve(nh * sizeof(int)));
+    CU_TRY(h, h->i_cur.reserve((size_t)n * sizeof(int)));
+    CU_TRY(h, h->i_pred.reserve((size_t)n * PDMPC_MAX_PRED_LANELETS * sizeof(int)));
+    CU_TRY(h, h->i_pre.reserve((size_t)n * sizeof(int)));
+    CU_TRY(h, h->i_cnt.reserve((size_t)2 * n * sizeof(int)));
+    CU_TRY(h, h->i_lptr.reserve(((size_t)2 * n + 1) * sizeof(int)));
+    CU_TRY(h, h->i_lx.reserve(std::max<size_t>(out->lane_capacity, 1) * sizeof(double)));
+    CU_TRY(h, h->i_ly.reserve(std::max<size_t>(out->lane_capacity, 1) * sizeof(double)));
+    InputsDev in;
+    in.n = n; in.Hp = Hp; in.dt = dt_seconds;
+    in.path_id = h->i_pid.as<int>(); in.x = h->i_x.as<double>(); in.y = h->i_y.as<double>(); in.speed = h->i_speed.as<double>();
+    in.ref_x = h->i_refx.as<double>(); in.ref_y = h->i_refy.as<double>(); in.v_ref = h->i_vref.as<double>();
+    in.ref_index = h->i_ridx.as<int>(); in.current_index = h->i_cur.as<int>(); in.pred_lanelets = h->i_pred.as<int>();
+    in.pre_lanelet = h->i_pre.as<int>(); in.lane_cnt = h->i_cnt.as<int>(); in.lane_ptr = h->i_lptr.as<int>();
+    in.lane_x = h->i_lx.as<double>(); in.lane_y = h->i_ly.as<double>();
+    const int blocks = (n + 3) / 4;   // 4 warps per block
+    CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
+    sample_inputs_kernel<<<blocks, 128, 0, h->stream>>>(h->road, in);
+    scan_counts_kernel<<<1, 1024, 0, h->stream>>>(in.lane_cnt, in.lane_ptr, 2 * n);
+    copy_bounds_kernel<<<blocks, 128, 0, h->stream>>>(h->road, in, out->lane_capacity);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
+    h->timing_pending_kernel = true;
+    h->stats.kernel_launches = 3;
+    int total = 0;
+    CU_TRY(h, cudaMemcpyAsync(&total, in.lane_ptr + 2 * n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    DOWN(h, out->ref_x, h->i_refx, nh);
+    DOWN(h, out->ref_y, h->i_refy, nh);
+    DOWN(h, out->v_ref, h->i_vref, nh);
+    DOWN(h, out->ref_index, h->i_ridx, nh);
+    DOWN(h, out->current_index, h->i_cur, n);
+    DOWN(h, out->predicted_lanelets, h->i_pred, (size_t)n * PDMPC_MAX_PRED_LANELETS);
+    DOWN(h, out->lane_ptr, h->i_lptr, 2 * (size_t)n + 1);
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    if (total > out->lane_capacity)
+        return fail(h, PDMPC_ERR_CAPACITY, "sample_inputs: the lanelet bounds need " + std::to_string(total) +
+                                               " points, lane_capacity is " + std::to_string(out->lane_capacity));
+    DOWN(h, out->lane_x, h->i_lx, total);
+    DOWN(h, out->lane_y, h->i_ly, total);
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
     return PDMPC_OK;
 }
 

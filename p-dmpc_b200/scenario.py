@@ -37,6 +37,8 @@ import dataclasses
 import os
 from typing import Callable, List, Optional, Sequence
 
+import math
+
 import numpy as np
 
 from .mpa import VEH_LENGTH, VEH_WIDTH, MotionPrimitiveAutomaton
@@ -211,28 +213,40 @@ def commonroad_scenario(mpa: MotionPrimitiveAutomaton, amount: int = 20, seed: i
 
 
 # --------------------------------------------------------------------------- reference trajectory
-def _projection_2d(x1, y1, x2, y2, px, py):
-    dx, dy = x2 - x1, y2 - y1
-    lam = ((px - x1) * dx + (py - y1) * dy) / (dx * dx + dy * dy)
-    xp, yp = x1 + lam * dx, y1 + lam * dy
-    return xp, yp, lam
+def _norm2(dx: float, dy: float) -> float:
+    """norm([dx dy], 2) as the arithmetic specification of this path states it: sqrt(dx*dx + dy*dy), no FMA
+    (the device kernel prepare_inputs_kernel and this restatement share it; MATLAB's own norm is closed source)."""
+    return math.sqrt(dx * dx + dy * dy)
+
+
+def _projection_2d(x1, y1, x2, y2, x3, y3):
+    """projection_2d.m:1-27, operation by operation -> (xp, yp, lambda)."""
+    b = _norm2(x2 - x1, y2 - y1)
+    if b != 0:
+        xn, yn = (x2 - x1) / b, (y2 - y1) / b
+        x31, y31 = x3 - x1, y3 - y1
+        dot = xn * x31 + yn * y31
+        return x1 + dot * xn, y1 + dot * yn, dot / b
+    return x1, y1, 0.0
 
 
 def _closest_point(path: np.ndarray, x: float, y: float):
-    """get_arc_distance_to_endpoint.m: projected point and idx_next (1-based)."""
+    """get_arc_distance_to_endpoint.m:41-113: projected point and idx_next (1-based)."""
     n = path.shape[0]
-    d2 = (path[:, 0] - x) ** 2 + (path[:, 1] - y) ** 2
-    ic = int(np.argmin(d2)) + 1
+    dxs, dys = path[:, 0] - x, path[:, 1] - y
+    d2 = dxs * dxs + dys * dys
+    ic = int(np.argmin(d2)) + 1                     # first minimum, like min()
     if ic == 1:
         a, b = 1, 2
     elif ic == n:
         a, b = n - 1, n
     else:
-        if d2[ic - 2] <= d2[ic]:
+        if d2[ic - 2] <= d2[ic]:                    # min([left, right]): the left one on a tie
             a, b = ic - 1, ic
         else:
             a, b = ic, ic + 1
-    xp, yp, lam = _projection_2d(path[a - 1, 0], path[a - 1, 1], path[b - 1, 0], path[b - 1, 1], x, y)
+    xp, yp, lam = _projection_2d(float(path[a - 1, 0]), float(path[a - 1, 1]), float(path[b - 1, 0]), float(path[b - 1, 1]),
+                                 float(x), float(y))
     idx_next = ic
     if (0 <= lam <= 0.5) or lam >= 1:
         idx_next = ic + 1 if ic < n else 1
@@ -240,40 +254,43 @@ def _closest_point(path: np.ndarray, x: float, y: float):
 
 
 def sample_reference_trajectory(n_samples: int, path: np.ndarray, x: float, y: float, step_distances):
-    """sample_reference_trajectory.m:24-97 -> (points [n,2], points_index [n], current_point_index)."""
+    """sample_reference_trajectory.m:24-97 -> (points [n,2], points_index [n], current_point_index).
+    Scalar arithmetic in the reference's order (the device kernel pdmpc_sample_inputs is compared bit for bit)."""
     out = np.zeros((n_samples, 2))
     out_idx = np.zeros(n_samples, dtype=np.int64)
-    xp, yp, point_index = _closest_point(path, x, y)
+    cx, cy, point_index = _closest_point(path, x, y)
     current_point_index = point_index
     n_pts = path.shape[0]
-    cur = np.array([xp, yp])
-    is_loop = np.hypot(*(path[0] - path[-1])) < 1e-8
+    px = [float(v) for v in path[:, 0]]
+    py = [float(v) for v in path[:, 1]]
+    is_loop = _norm2(px[0] - px[-1], py[0] - py[-1]) < 1e-8
     point_index_last = point_index - 1
     if is_loop and point_index == n_pts:
         point_index = 1
-
-    def unit(v):
-        return v / np.hypot(v[0], v[1])
-
     for i in range(n_samples):
-        remaining = np.hypot(*(cur - path[point_index - 1]))
-        if remaining > step_distances[i] or point_index == n_pts:
-            while (path[point_index - 1, 0] == path[point_index_last - 1, 0]
-                   and path[point_index - 1, 1] == path[point_index_last - 1, 1] and point_index_last > 1):
+        step = float(step_distances[i])
+        remaining = _norm2(cx - px[point_index - 1], cy - py[point_index - 1])
+        if remaining > step or point_index == n_pts:
+            while (px[point_index - 1] == px[point_index_last - 1] and py[point_index - 1] == py[point_index_last - 1]
+                   and point_index_last > 1):
                 point_index_last -= 1
-            cur = cur + step_distances[i] * unit(path[point_index - 1] - path[point_index_last - 1])
+            ux, uy = px[point_index - 1] - px[point_index_last - 1], py[point_index - 1] - py[point_index_last - 1]
+            nrm = _norm2(ux, uy)
+            cx, cy = cx + step * (ux / nrm), cy + step * (uy / nrm)
         else:
             reflength = remaining
-            while remaining < step_distances[i]:
+            while remaining < step:
                 reflength = remaining
-                cur = path[point_index - 1].copy()
+                cx, cy = px[point_index - 1], py[point_index - 1]
                 point_index_last = point_index
                 point_index = min(point_index + 1, n_pts)
                 if is_loop and point_index == n_pts:
                     point_index = 1
-                remaining = remaining + np.hypot(*(cur - path[point_index - 1]))
-            cur = cur + (step_distances[i] - reflength) * unit(path[point_index - 1] - path[point_index_last - 1])
-        out[i] = cur
+                remaining = remaining + _norm2(cx - px[point_index - 1], cy - py[point_index - 1])
+            ux, uy = px[point_index - 1] - px[point_index_last - 1], py[point_index - 1] - py[point_index_last - 1]
+            nrm = _norm2(ux, uy)
+            cx, cy = cx + (step - reflength) * (ux / nrm), cy + (step - reflength) * (uy / nrm)
+        out[i, 0], out[i, 1] = cx, cy
         out_idx[i] = point_index
     return out, out_idx, current_point_index
 
@@ -323,6 +340,33 @@ def get_lanelets_boundary(predicted: np.ndarray, road: RoadMap, veh: Vehicle):
         lefts.insert(0, pl[-1 - k:-1])
         rights.insert(0, pr[-1 - k:-1])
     return np.ascontiguousarray(np.vstack(lefts).T), np.ascontiguousarray(np.vstack(rights).T)
+
+
+def road_tables(scenarios: Sequence["Scenario"]) -> dict:
+    """Flat tables of pdmpc_upload_road for the vehicles of `scenarios` (path id = running vehicle index): the map's
+    lanelet boundaries (RoadMap.boundary, lanelet_boundaries{l}{1:2}) and every vehicle's reference path with its
+    lanelets_index / points_index (reference_path_struct)."""
+    road = scenarios[0].road
+    bptr, bx, by = [0], [], []
+    for left, right in road.boundary:
+        for side in (left, right):
+            bx.append(side[:, 0]); by.append(side[:, 1])
+            bptr.append(bptr[-1] + side.shape[0])
+    pptr, px, py, lptr, lidx, pidx, loop, speed = [0], [], [], [0], [], [], [], []
+    for sc in scenarios:
+        for v in sc.vehicles:
+            px.append(v.reference_path[:, 0]); py.append(v.reference_path[:, 1])
+            pptr.append(pptr[-1] + v.reference_path.shape[0])
+            lidx.append(np.asarray(v.lanelets_index)); pidx.append(np.asarray(v.points_index))
+            lptr.append(lptr[-1] + len(v.lanelets_index))
+            loop.append(1 if v.is_loop else 0)
+            speed.append(v.reference_speed)
+    return {"bound_ptr": np.array(bptr, dtype=np.int32), "bound_x": np.concatenate(bx).astype(np.float64),
+            "bound_y": np.concatenate(by).astype(np.float64), "path_ptr": np.array(pptr, dtype=np.int32),
+            "path_x": np.concatenate(px).astype(np.float64), "path_y": np.concatenate(py).astype(np.float64),
+            "lan_ptr": np.array(lptr, dtype=np.int32), "lanelets_index": np.concatenate(lidx).astype(np.int32),
+            "points_index": np.concatenate(pidx).astype(np.int32), "is_loop": np.array(loop, dtype=np.uint8),
+            "reference_speed": np.array(speed, dtype=np.float64)}
 
 
 # --------------------------------------------------------------------------- coupling / priorities
@@ -562,12 +606,18 @@ class ScenarioRunner:
     computation level (vehicles of one level are independent,
     PrioritizedSequentialController.m:83-92)."""
 
-    def __init__(self, sc: Scenario, plan_fn: PlanFn, max_num_CLs: int = 99, timestep_fn=None):
+    def __init__(self, sc: Scenario, plan_fn: PlanFn, max_num_CLs: int = 99, timestep_fn=None, inputs_fn=None,
+                 path_id0: int = 0):
         """plan_fn(batch) plans one computation level; with timestep_fn(batch, deps) the whole time
-        step is ONE call and the predecessors' areas are handed over behind it (pdmpc_plan_timestep)."""
+        step is ONE call and the predecessors' areas are handed over behind it (pdmpc_plan_timestep).
+        inputs_fn(path_id, x, y, speed, dt) -> dict (capi.Planner.sample_inputs): reference trajectories and lanelet
+        boundaries of all vehicles come from the device in one call per time step instead of the host functions
+        above; path_id0 = path id of vehicle 0 in the uploaded road tables (road_tables of several scenarios)."""
         self.sc = sc
         self.plan_fn = plan_fn
         self.timestep_fn = timestep_fn
+        self.inputs_fn = inputs_fn
+        self.path_id0 = path_id0
         self.max_num_CLs = max_num_CLs              # honoured by the one-call path (timestep_inputs)
         self.timestep_records: List[tuple] = []     # (step, batch, deps, result) of the one-call path
         self.mpa = sc.mpa
@@ -595,6 +645,25 @@ class ScenarioRunner:
                              trim_indices=int(self.trim[i]), reference_trajectory_points=pts, v_ref=v_ref,
                              predicted_lanelet_boundary=boundary)
 
+    def _iters(self) -> List[IterationData]:
+        """iter_v of every vehicle for this time step (HighLevelController.m:167-270), host or device side."""
+        n = self.sc.amount
+        if self.inputs_fn is None or self.sc.kind != "commonroad":
+            return [self._iter_for(i) for i in range(n)]
+        mpa = self.mpa
+        speed = np.array([mpa.trim_speed[self.trim[i] - 1] for i in range(n)], dtype=np.float64)
+        o = self.inputs_fn(self.path_id0 + np.arange(n), self.pose[:, 0], self.pose[:, 1], speed, mpa.dt_seconds)
+        out = []
+        for i in range(n):
+            x, y, yaw = self.pose[i]
+            l0, l1, l2 = (int(v) for v in o["lane_ptr"][2 * i:2 * i + 3])
+            boundary = (np.ascontiguousarray(np.vstack([o["lane_x"][l0:l1], o["lane_y"][l0:l1]])),
+                        np.ascontiguousarray(np.vstack([o["lane_x"][l1:l2], o["lane_y"][l1:l2]])))
+            out.append(IterationData(x0=np.array([x, y, yaw, speed[i]]), trim_indices=int(self.trim[i]),
+                                     reference_trajectory_points=np.column_stack([o["ref_x"][i], o["ref_y"][i]]),
+                                     v_ref=o["v_ref"][i].copy(), predicted_lanelet_boundary=boundary))
+        return out
+
     def _fallback_plan(self, i: int):
         """What vehicle i does (and publishes) when its search is exhausted — known before the time
         step starts.  [dev] local fallback: PrioritizedController.m:568-621 (standstill), :678-718
@@ -612,7 +681,7 @@ class ScenarioRunner:
         sequential predecessors' areas, the predecessor lists and the fallback plans."""
         sc, mpa = self.sc, self.mpa
         n = sc.amount
-        iters = [self._iter_for(i) for i in range(n)]
+        iters = self._iters()
         A = couple(sc, self.pose)
         D = constant_priorities(A) if sc.priority == "constant" else coloring_priorities(A)
         for i in range(n):   # consider_successors, area_of_standstill: PrioritizedController.m:508-540
@@ -667,7 +736,7 @@ class ScenarioRunner:
         sc, mpa = self.sc, self.mpa
         n, Hp = sc.amount, mpa.Hp
         self.k += 1
-        iters = [self._iter_for(i) for i in range(n)]
+        iters = self._iters()
         A = couple(sc, self.pose)
         D = constant_priorities(A) if sc.priority == "constant" else coloring_priorities(A)
         levels = kahn(D.astype(np.int64))
@@ -843,7 +912,7 @@ class ExplorativeRunner(ScenarioRunner):
         sc, mpa = self.sc, self.mpa
         n, Hp = sc.amount, mpa.Hp
         self.k += 1
-        base = [self._iter_for(i) for i in range(n)]
+        base = self._iters()
         A = couple(sc, self.pose)
         D = (constant_priorities(A) if sc.priority == "constant" else coloring_priorities(A)).astype(bool)
         levels = kahn(D.astype(np.int64))

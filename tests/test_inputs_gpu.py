@@ -1,0 +1,104 @@
+"""The input side of a time step on the device (pdmpc_upload_road / pdmpc_sample_inputs):
+reference-trajectory sampling, predicted lanelets and lanelet boundaries of every vehicle in one call, bit for bit
+against the host restatement of the reference's functions in pdmpc_b200/scenario.py
+(sample_reference_trajectory.m, get_arc_distance_to_endpoint.m, projection_2d.m, get_predicted_lanelets.m,
+get_lanelets_boundary.m), on start poses, on poses off the path and along closed loops."""
+import numpy as np
+import pytest
+
+from oracle import oracle_py, parity
+from pdmpc_b200 import capi, scenario
+from pdmpc_b200.mpa import get_mpa
+
+
+def host_inputs(mpa, veh, road, x, y, trim):
+    pts, v_ref, idx, cur = scenario.get_reference_trajectory(mpa, veh, x, y, trim, mpa.dt_seconds)
+    lan = scenario.get_predicted_lanelets(veh, idx)
+    left, right = scenario.get_lanelets_boundary(lan, road, veh)
+    return pts, v_ref, idx, cur, lan, left, right
+
+
+def check_rows(mpa, vehicles, road, poses, trims, o):
+    for i, veh in enumerate(vehicles):
+        pts, v_ref, idx, cur, lan, left, right = host_inputs(mpa, veh, road, poses[i, 0], poses[i, 1], int(trims[i]))
+        assert np.array_equal(o["ref_x"][i].view(np.uint64), np.ascontiguousarray(pts[:, 0]).view(np.uint64)), i
+        assert np.array_equal(o["ref_y"][i].view(np.uint64), np.ascontiguousarray(pts[:, 1]).view(np.uint64)), i
+        assert np.array_equal(o["v_ref"][i], v_ref) and o["ref_index"][i].tolist() == idx.tolist()
+        assert int(o["current_index"][i]) == cur
+        got = o["predicted_lanelets"][i]
+        assert got[got > 0].tolist() == lan.tolist()
+        l0, l1, l2 = (int(v) for v in o["lane_ptr"][2 * i:2 * i + 3])
+        assert np.array_equal(np.vstack([o["lane_x"][l0:l1], o["lane_y"][l0:l1]]), left)
+        assert np.array_equal(np.vstack([o["lane_x"][l1:l2], o["lane_y"][l1:l2]]), right)
+
+
+def test_road_tables_shape():
+    mpa = get_mpa("single_speed", non_convex=True)
+    scs = [scenario.commonroad_scenario(mpa, 20, seed=s) for s in (1, 2)]
+    t = scenario.road_tables(scs)
+    assert t["path_ptr"].size == 41 and t["bound_ptr"].size == 2 * scs[0].road.n + 1
+    assert t["lan_ptr"][-1] == t["lanelets_index"].size == t["points_index"].size
+    v = scs[1].vehicles[3]
+    p = 20 + 3
+    assert np.array_equal(t["path_x"][t["path_ptr"][p]:t["path_ptr"][p + 1]], v.reference_path[:, 0])
+    assert t["reference_speed"][p] == v.reference_speed
+
+
+@pytest.mark.gpu
+def test_sample_inputs_matches_the_host_functions(planner):
+    mpa = get_mpa("triple_speed", non_convex=True)
+    planner.upload_mpa(mpa)
+    scs = [scenario.commonroad_scenario(mpa, 20, seed=s) for s in (1, 2, 3)]
+    planner.upload_road(scenario.road_tables(scs))
+    vehicles = [v for sc in scs for v in sc.vehicles]
+    n = len(vehicles)
+    rng = np.random.default_rng(0)
+    poses = np.array([[v.x_start, v.y_start] for v in vehicles])
+    trims = np.full(n, mpa.trim_from_values(0.0, 0.0))
+    speed = lambda tr: np.array([mpa.trim_speed[t - 1] for t in tr])
+    o = planner.sample_inputs(np.arange(n), poses[:, 0], poses[:, 1], speed(trims), mpa.dt_seconds)
+    check_rows(mpa, vehicles, scs[0].road, poses, trims, o)
+    # anywhere along the paths, off the centre line, any trim, rows in any order / repeated
+    for _ in range(4):
+        rows = rng.integers(0, n, size=97)
+        poses = np.zeros((rows.size, 2))
+        for r, p in enumerate(rows):
+            path = vehicles[p].reference_path
+            j = rng.integers(0, path.shape[0])
+            poses[r] = path[j] + rng.normal(scale=0.03, size=2)
+        trims = rng.integers(1, mpa.trim_speed.size + 1, size=rows.size)
+        o = planner.sample_inputs(rows, poses[:, 0], poses[:, 1], speed(trims), mpa.dt_seconds)
+        check_rows(mpa, [vehicles[p] for p in rows], scs[0].road, poses, trims, o)
+    # exactly ON path points (ties of the closest-point search, lambda == 0 / 1)
+    rows = np.arange(n)
+    poses = np.array([vehicles[p].reference_path[rng.integers(1, vehicles[p].reference_path.shape[0] - 1)] for p in rows])
+    o = planner.sample_inputs(rows, poses[:, 0], poses[:, 1], speed(trims[:n]), mpa.dt_seconds)
+    check_rows(mpa, vehicles, scs[0].road, poses, trims[:n], o)
+    # errors are loud
+    with pytest.raises(capi.PdmpcError) as e:
+        planner.sample_inputs(np.array([n]), poses[:1, 0], poses[:1, 1], speed(trims[:1]), mpa.dt_seconds)
+    assert e.value.code == capi.PDMPC_ERR_BAD_INPUT
+    with pytest.raises(capi.PdmpcError) as e:
+        planner.sample_inputs(rows, poses[:, 0], poses[:, 1], speed(trims[:n]), mpa.dt_seconds, lane_capacity=100)
+    assert e.value.code == capi.PDMPC_ERR_CAPACITY
+
+
+@pytest.mark.gpu
+def test_closed_loop_with_device_side_inputs(planner):
+    """ScenarioRunner(inputs_fn = Planner.sample_inputs): the whole time step (inputs + one-call planning) on the device
+    drives the same closed loop as the host input functions + oracle planner."""
+    mpa = get_mpa("triple_speed", non_convex=True)
+    planner.upload_mpa(mpa)
+    scs = [scenario.commonroad_scenario(mpa, 20, seed=s) for s in (5, 6)]
+    planner.upload_road(scenario.road_tables(scs))
+    for k, sc in enumerate(scs):
+        dev = scenario.ScenarioRunner(sc, None, timestep_fn=lambda b, d: planner.plan_timestep(b, d, False),
+                                      inputs_fn=planner.sample_inputs, path_id0=20 * k)
+        ref = scenario.ScenarioRunner(scenario.commonroad_scenario(mpa, 20, seed=5 + k),
+                                      lambda b: oracle_py.plan_batch(mpa, b, 4))
+        for _ in range(8):
+            dev.step()
+            ref.step()
+            assert np.array_equal(dev.pose.view(np.uint64), ref.pose.view(np.uint64)) and np.array_equal(dev.trim, ref.trim)
+        _k, tb, td, got = dev.timestep_records[-1]
+        parity.compare(got, scenario.plan_timestep_by_levels(lambda x: oracle_py.plan_batch(mpa, x), tb, td))
