@@ -1015,6 +1015,7 @@ int pdmpc_fetch_staged(pdmpc_handle *h, pdmpc_batch_out *out) {
         static const char *names[8] = {"c:wait_job", "c:tables+place", "c:interx_obstacles", "c:interx_rest", "c:sincos+publish", "-", "-", "c:other"};
 #else
         static const char *names[8] = {"setup", "heap_pop", "loads+place", "check", "expand", "heap_push", "wait_children", "loop"};
+        // (CTA kernel master: set-up, pending children, loads + heap pop, flag wait, job hand-over, children, pushes, end)
 #endif
         double tot = 0;
         for (int i = 0; i < 8; ++i) tot += (double)counters[8 + i];

@@ -356,6 +356,7 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
     const unsigned hf_addr = shared_base_once(S.hf), hw_addr = shared_base_once(S.hw);
     int clear_upto = 0;            // highest node id of the previous search (flags to clear)
     bool redo_exact = false;
+    PROF_DECL
     unsigned si_u = 0;
     unsigned next_item = blockIdx.x + gridDim.x * (unsigned)role_master;   // escalation list: this master's first item
     bool first_item = true;
@@ -573,8 +574,10 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
         __threadfence_block();
         __syncwarp();
 
+        PROF_MARK(0);   // fetch + set-up
         for (;;) {   // GraphSearch.m:53-107
             if (!exact) resolve_pending(false);
+            PROF_MARK(1);   // pending children: flags, pushes of the valid ones, waits
             if (heap.len == 0) { exhausted = true; break; }               // :57-61 (no pending child is left either)
             if (!exact && !heap.min_is_unique()) { tie = true; break; }   // tie mechanics would matter: re-run exact
             // the node about to be popped: fetch its records now, their latency hides behind the heap walk
@@ -593,6 +596,7 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
                 nchild = tb.succ_ptr[k0 * nT + (tr0 - 1) + 1] - sbase;
             }
             const HEnt top = heap.pop<true>(lane);
+            PROF_MARK(2);   // early loads + heap pop
             const unsigned id = top.id(), par = top.pid();
             const int cK = (int)top.k();
             ++n_pops;
@@ -615,8 +619,10 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
             ca.x = a0.x; ca.y = a0.y; ca.yaw = a1.x; ca.g = a1.y;
             const double c = cs0.x, s = cs0.y;
             // publish the job first: the checkers work while the master computes costs and pushes
+            PROF_MARK(3);   // flag wait (exact queue), record use
             last_ticket = publish(ca, c, s, (unsigned)(n_nodes + 1), nchild, sbase, k_exp, 0);
             any_job = true;
+            PROF_MARK(4);   // job hand-over
             const int to_go = Hp - k_exp;               // :37
             for (int c0 = 0; c0 < nchild; c0 += kWarp) {
                 const int ci = c0 + lane;
@@ -661,6 +667,7 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
                     he.f = ea.g + eh;                   // GraphSearch.m:102 (weights 1)
                     he.w = HEnt::pack(nid, id, (unsigned)cedge, (unsigned)k_exp, (unsigned)t2);
                 }
+                PROF_MARK(5);   // children: poses, costs, records
                 if (exact) {
                     heap.push_many(he, cnt, lane);      // :104, one push per child, in order
                 } else {
@@ -672,9 +679,11 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
                     const unsigned long long nw = __shfl_sync(FULL, he.w, r & 31);
                     if (!pocc && r < cnt) { pocc = true; pf = nf; pw = nw; }
                 }
+                PROF_MARK(6);   // pushes / pending insertion
             }
             n_nodes += nchild;
         }
+        PROF_MARK(7);
 
         // ---- let the checkers finish this search's jobs, then write the results (GraphSearch.m:58-60 / :82-89)
         const bool account = !exact && !tie && status == PDMPC_OK;
@@ -711,6 +720,8 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
             if (__any_sync(FULL, amb)) tie = true;
             n_pops += extra;
         }
+        PROF_MARK(7);   // wait for the checkers, accounting
+        PROF_FLUSH(o, lane == 0);
         clear_upto = n_nodes;
         if (tie) {   // undecidable without the reference's tie mechanics: same search again, exact queue
             if (lane == 0) atomicAdd(o.counters + 3, 1ULL);

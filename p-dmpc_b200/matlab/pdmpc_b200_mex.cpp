@@ -431,6 +431,10 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
             const char *txt = pdmpc_last_error(nullptr);
             fail("pdmpc:create", std::string("pdmpc_create failed: ") + (txt ? txt : ""));
         }
+        // valid-only queue wherever the CTA shape runs (one search per call, PLAN_TIMESTEP): 2-3x lower latency on
+        // collision-rich searches; every field the shim returns is unaffected (pop_hash, which it does not return,
+        // then covers the popped nodes that passed their check)
+        pdmpc_set_cta_queue(h, 1);
         g_handles.push_back(h);
         plhs[0] = mxCreateNumericMatrix(1, 1, mxUINT64_CLASS, mxREAL);
         *static_cast<uint64_t *>(mxGetData(plhs[0])) = g_handles.size();   // 1-based; 0 = none
