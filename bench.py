@@ -3,8 +3,8 @@
 
 Workload at N=1 (BASELINE.json configs[1]): CPM Lab road network, 20 vehicles,
 coloring-based prioritisation, triple_speed MPA, Hp 6, InterX checker, 35 time
-steps per scenario, R scenarios planned concurrently ("parallel_threads
-equivalent on 1 B200").  Scenarios are rolled out closed loop once (untimed) so
+steps per scenario, R = 512 scenarios per GPU planned concurrently ("parallel_threads
+equivalent on 1 B200"; 8 GPUs x 512 = the 4096 scenarios of configs[4]).  Scenarios are rolled out closed loop once (untimed) so
 that every (scenario, step, vehicle) search record is fixed; one bench "step" =
 one pass of the hot path over all records of the rank.  Both arms plan the SAME
 records: they come from the same seeds, are rolled out by bit-identical planners
@@ -59,8 +59,8 @@ def parse_args():
                     help="road = BASELINE configs[1]/[4] (default); explorative = configs[2]")
     ap.add_argument("--optimizer", default="graph", choices=["graph", "sampled"],
                     help="graph = GraphSearch (default); sampled = MonteCarloTreeSearch")
-    ap.add_argument("--scenarios", type=int, default=int(os.environ.get("PDMPC_BENCH_SCENARIOS", "256")),
-                    help="scenarios per GPU (weak scaling)")
+    ap.add_argument("--scenarios", type=int, default=int(os.environ.get("PDMPC_BENCH_SCENARIOS", "512")),
+                    help="scenarios per GPU (weak scaling; 512 = what BASELINE configs[4], 4096 scenarios, gives each of 8 GPUs)")
     ap.add_argument("--scenarios-total", type=int, default=0,
                     help="total scenarios, split block-cyclically over the ranks (strong scaling; BASELINE configs[4]: 4096)")
     ap.add_argument("--gen-workers", type=int, default=0,
@@ -399,7 +399,7 @@ def main():
     Hp = mpa.Hp
 
     t_gen = time.perf_counter()
-    workers = args.gen_workers or max(1, min(12, (os.cpu_count() or 1) // max(world, 1)))
+    workers = args.gen_workers or max(1, (os.cpu_count() or 1) // max(world, 1))
     batch, step_recs, ts_recs = get_records(args, rank_blocks(args, rank, world), "gpu", dev, workers)
     t_gen = time.perf_counter() - t_gen
     n = batch.n

@@ -239,7 +239,7 @@ int pdmpc_set_cta_heap_smem(pdmpc_handle *h, int32_t entries);
 
 /* pdmpc_plan_batch on large host batches (>= 16384 searches, launch shapes 0..3) runs as a chunked
  * pipeline: host->device copies, searches and device->host copies of consecutive chunks overlap.
- * chunks: 0 = choose from the batch size (default), 1 = off, 2..16 = that many chunks for any batch
+ * chunks: 0 = choose from the batch size (default: ~60 k searches per chunk, 2..12 chunks), 1 = off, 2..16 = that many chunks for any batch
  * of at least 2*chunks searches.  Tuning/test knob: results do not depend on it. */
 int pdmpc_set_pipeline_chunks(pdmpc_handle *h, int32_t chunks);
 

@@ -1381,7 +1381,7 @@ int pdmpc_set_pipeline_chunks(pdmpc_handle *h, int32_t chunks) {
 int pdmpc_plan_batch(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc_batch_out *out) {
     if (h && in && h->has_mpa && h->pipeline_chunks != 1 && h->variant_mode <= 3 &&
         (h->pipeline_chunks > 1 ? in->n_searches >= 2 * h->pipeline_chunks : in->n_searches >= kPipelineMinSearches)) {
-        const int C = h->pipeline_chunks > 1 ? h->pipeline_chunks : std::min(12, std::max(2, in->n_searches / kPipelineMinSearches));   // measured: profiles/r01h_pipeline.txt
+        const int C = h->pipeline_chunks > 1 ? h->pipeline_chunks : std::min(12, std::max(2, in->n_searches / 60000));   // ~60 k searches per chunk: profiles/r02_pipeline_chunks.txt
         return plan_batch_pipelined(h, in, out, C);
     }
     int rc = pdmpc_stage_batch(h, in);

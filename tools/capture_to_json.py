@@ -41,7 +41,7 @@ def main():
     t_ms = num("gpu__time_duration.sum") * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}[tu]
     out = {
         "what": f"one launch of {best['Kernel Name'].split('(')[0]} from the ncu --set full capture profiles/{tag}_search_ncu.md "
-                "(tools/gpu_round.sh: the bench's own 256-scenario records, auto launch shape)",
+                "(tools/gpu_round.sh: the bench's own 512-scenario records, auto launch shape)",
         "round": tag, "kernel": best["Kernel Name"].split("(")[0], "searches": st["searches"], "mpa": st["mpa"],
         "shape": st["shape"], "pops": st["pops"], "escalated": st["escalated"],
         "dram_bytes_read": to_bytes("dram__bytes_read.sum"), "dram_bytes_write": to_bytes("dram__bytes_write.sum"),
@@ -49,8 +49,8 @@ def main():
         "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
         "sms": 148, "kernel_ms_under_ncu": t_ms,
     }
-    if st["searches"] != 179200:
-        sys.exit(f"capture is of {st['searches']} searches, the bench launches 179200")
+    if st["searches"] != 358400:
+        sys.exit(f"capture is of {st['searches']} searches, the bench launches 358400 (512 scenarios x 35 steps x 20 vehicles)")
     json.dump(out, open(os.path.join(ROOT, "profiles", "search_kernel_traffic.json"), "w"), indent=1)
     print(json.dumps(out))
 

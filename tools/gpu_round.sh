@@ -14,7 +14,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 2 --warmup 1 > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
 PDMPC_STATS_JSON=gpurun_out/prof_search_${TAG}_stats.json timeout 900 ncu --set full --clock-control none --import-source on \
     -k regex:search_tile_kernel -s 1 -c 1 -o gpurun_out/prof_search_${TAG} -f \
-    python tools/profile_batch.py "build/bench_records/triple_speed_20v_35t_block*.npz" 2 1 0 > gpurun_out/prof_search_${TAG}.log 2>&1
+    python tools/profile_batch.py "build/bench_records/triple_speed_20v_35t_block00[0-6]*.npz" 2 1 0 > gpurun_out/prof_search_${TAG}.log 2>&1
 tail -5 gpurun_out/prof_search_${TAG}.log
 python tools/capture_to_json.py ${TAG} gpurun_out/prof_search_${TAG}.ncu-rep gpurun_out/prof_search_${TAG}_stats.json || echo "CAPTURE DOES NOT MATCH THE BENCH LAUNCH"
 cp profiles/search_kernel_traffic.json gpurun_out/search_kernel_traffic_${TAG}.json
