@@ -29,6 +29,13 @@
 //           dynamic_obstacle_area {nV x R*Hp}, left {nV x 1}, right {nV x 1}, checker (0 = SAT), dt)
 //       ONE centralized search over nV vehicles (CentralizedController.m:33-59, GraphSearchCuda.run_optimizer with
 //       iter.amount > 1): iter.obstacles / iter.dynamic_obstacle_area go into ROW 1 of the two cell arrays.
+//       mex(UPLOAD_ROAD, h, lanelet_boundaries {nL x 2} (left, right; each n x 2), reference_paths {nP x 1} (n x 2),
+//           lanelets_index {nP x 1}, points_index {nP x 1}, is_loop [nP], reference_speed [nP])
+//   [ref (N x Hp x 2), v_ref (N x Hp), points_index (N x Hp), current_point_index (N x 1), predicted_lanelets {N x 1},
+//    left {N x 1} (2 x n), right {N x 1} (2 x n)] = mex(SAMPLE_INPUTS, h, path_id [N] (1-based), x [N], y [N], speed [N], dt)
+//       reference trajectories and lanelet boundaries of ALL vehicles of a time step in one call
+//       (sample_inputs_cuda.m): get_reference_trajectory / sample_reference_trajectory / get_predicted_lanelets /
+//       get_lanelets_boundary of hlc/controller/common, as HighLevelController fills them into iter.
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -39,7 +46,8 @@
 
 namespace {
 
-enum Command { CREATE = 0, DESTROY = 1, UPLOAD_MPA = 2, PLAN = 3, STATS = 4, PLAN_SAMPLED = 5, PLAN_TIMESTEP = 6, PLAN_JOINT = 7 };
+enum Command { CREATE = 0, DESTROY = 1, UPLOAD_MPA = 2, PLAN = 3, STATS = 4, PLAN_SAMPLED = 5, PLAN_TIMESTEP = 6, PLAN_JOINT = 7, UPLOAD_ROAD = 8,
+               SAMPLE_INPUTS = 9 };
 
 std::vector<pdmpc_handle *> g_handles;   // released at `clear mex` (HighLevelController.m:284-303)
 bool g_at_exit_registered = false;
@@ -414,6 +422,105 @@ void plan_timestep(pdmpc_handle *h, int nlhs, mxArray *plhs[], const mxArray *pr
     }
 }
 
+// UPLOAD_ROAD: the map's lanelet boundaries and every vehicle's reference path -> pdmpc_upload_road
+void upload_road(pdmpc_handle *h, const mxArray *prhs[]) {
+    const mxArray *bounds = prhs[2], *paths = prhs[3], *lidx = prhs[4], *pidx = prhs[5], *loop = prhs[6], *speed = prhs[7];
+    if (!mxIsCell(bounds) || mxGetN(bounds) < 2) fail("pdmpc:input", "lanelet_boundaries must be an nL x 2 cell (left, right)");
+    const size_t nL = mxGetM(bounds), nP = mxGetNumberOfElements(paths);
+    if (!mxIsCell(paths) || !mxIsCell(lidx) || !mxIsCell(pidx) || mxGetNumberOfElements(lidx) != nP ||
+        mxGetNumberOfElements(pidx) != nP || mxGetNumberOfElements(loop) != nP || mxGetNumberOfElements(speed) != nP)
+        fail("pdmpc:input", "reference_paths, lanelets_index, points_index, is_loop, reference_speed must have one entry per path");
+    std::vector<int32_t> bptr(1, 0), pptr(1, 0), lptr(1, 0), li, pi;
+    std::vector<double> bx, by, px, py, spd(nP);
+    std::vector<uint8_t> lp(nP);
+    auto append_rows = [&](const mxArray *a, std::vector<double> &x, std::vector<double> &y) {   // n x 2, column-major
+        if (!a || mxGetN(a) != 2) fail("pdmpc:input", "polylines must be n x 2");
+        const size_t n = mxGetM(a);
+        const double *d = mxGetDoubles(a);
+        for (size_t i = 0; i < n; ++i) { x.push_back(d[i]); y.push_back(d[i + n]); }
+        return static_cast<int32_t>(n);
+    };
+    for (size_t l = 0; l < nL; ++l)
+        for (size_t side = 0; side < 2; ++side)
+            bptr.push_back(bptr.back() + append_rows(mxGetCell(bounds, l + nL * side), bx, by));
+    for (size_t p = 0; p < nP; ++p) {
+        pptr.push_back(pptr.back() + append_rows(mxGetCell(paths, p), px, py));
+        const mxArray *a = mxGetCell(lidx, p), *b = mxGetCell(pidx, p);
+        if (!a || !b || mxGetNumberOfElements(a) != mxGetNumberOfElements(b)) fail("pdmpc:input", "lanelets_index / points_index mismatch");
+        for (size_t j = 0; j < mxGetNumberOfElements(a); ++j) {
+            li.push_back(static_cast<int32_t>(mxGetDoubles(a)[j]));
+            pi.push_back(static_cast<int32_t>(mxGetDoubles(b)[j]));
+        }
+        lptr.push_back(static_cast<int32_t>(li.size()));
+        lp[p] = mxGetDoubles(loop)[p] != 0;
+        spd[p] = mxGetDoubles(speed)[p];
+    }
+    pdmpc_road_desc d;
+    std::memset(&d, 0, sizeof(d));
+    d.n_lanelets = static_cast<int32_t>(nL); d.bound_ptr = bptr.data(); d.bound_x = bx.data(); d.bound_y = by.data();
+    d.n_paths = static_cast<int32_t>(nP); d.path_ptr = pptr.data(); d.path_x = px.data(); d.path_y = py.data();
+    d.lan_ptr = lptr.data(); d.lanelets_index = li.data(); d.points_index = pi.data();
+    d.is_loop = lp.data(); d.reference_speed = spd.data();
+    check(h, pdmpc_upload_road(h, &d), "pdmpc_upload_road");
+}
+
+// SAMPLE_INPUTS: reference trajectories + lanelet boundaries of N vehicles -> pdmpc_sample_inputs
+void sample_inputs(pdmpc_handle *h, int nlhs, mxArray *plhs[], const mxArray *prhs[]) {
+    const size_t N = mxGetNumberOfElements(prhs[2]);
+    if (mxGetNumberOfElements(prhs[3]) != N || mxGetNumberOfElements(prhs[4]) != N || mxGetNumberOfElements(prhs[5]) != N)
+        fail("pdmpc:input", "path_id, x, y, speed must have N entries each");
+    const int Hp = pdmpc_get_hp(h);
+    std::vector<int32_t> pid(N), ridx(N * Hp), cur(N), pred(N * PDMPC_MAX_PRED_LANELETS), lane_ptr(2 * N + 1);
+    for (size_t i = 0; i < N; ++i) pid[i] = static_cast<int32_t>(mxGetDoubles(prhs[2])[i]) - 1;
+    std::vector<double> rx(N * Hp), ry(N * Hp), vr(N * Hp), lx(512 * N + 1), ly(512 * N + 1);
+    pdmpc_inputs_out out;
+    std::memset(&out, 0, sizeof(out));
+    out.ref_x = rx.data(); out.ref_y = ry.data(); out.v_ref = vr.data(); out.ref_index = ridx.data();
+    out.current_index = cur.data(); out.predicted_lanelets = pred.data(); out.lane_ptr = lane_ptr.data();
+    out.lane_x = lx.data(); out.lane_y = ly.data(); out.lane_capacity = static_cast<int32_t>(512 * N);
+    check(h, pdmpc_sample_inputs(h, static_cast<int32_t>(N), pid.data(), mxGetDoubles(prhs[3]), mxGetDoubles(prhs[4]),
+                                 mxGetDoubles(prhs[5]), mxGetScalar(prhs[6]), &out), "pdmpc_sample_inputs");
+    const size_t dims[3] = {N, static_cast<size_t>(Hp), 2};
+    plhs[0] = mxCreateNumericArray(3, dims, mxDOUBLE_CLASS, mxREAL);      // iter.reference_trajectory_points
+    for (size_t i = 0; i < N; ++i)
+        for (int k = 0; k < Hp; ++k) {
+            mxGetDoubles(plhs[0])[i + N * k] = rx[i * Hp + k];
+            mxGetDoubles(plhs[0])[i + N * k + N * Hp] = ry[i * Hp + k];
+        }
+    auto matrix = [&](int slot, const double *src_d, const int32_t *src_i, size_t cols) {
+        if (nlhs <= slot) return;
+        plhs[slot] = mxCreateDoubleMatrix(N, cols, mxREAL);
+        for (size_t i = 0; i < N; ++i)
+            for (size_t k = 0; k < cols; ++k)
+                mxGetDoubles(plhs[slot])[i + N * k] = src_d ? src_d[i * cols + k] : static_cast<double>(src_i[i * cols + k]);
+    };
+    matrix(1, vr.data(), nullptr, Hp);
+    matrix(2, nullptr, ridx.data(), Hp);
+    matrix(3, nullptr, cur.data(), 1);
+    if (nlhs > 4) {
+        plhs[4] = mxCreateCellMatrix(N, 1);
+        for (size_t i = 0; i < N; ++i) {
+            size_t m = 0;
+            while (m < PDMPC_MAX_PRED_LANELETS && pred[i * PDMPC_MAX_PRED_LANELETS + m]) ++m;
+            mxArray *a = mxCreateDoubleMatrix(1, m, mxREAL);
+            for (size_t j = 0; j < m; ++j) mxGetDoubles(a)[j] = pred[i * PDMPC_MAX_PRED_LANELETS + j];
+            mxSetCell(plhs[4], i, a);
+        }
+    }
+    for (int side = 0; side < 2 && nlhs > 5 + side; ++side) {               // predicted_lanelet_boundary{i, 1:2}
+        plhs[5 + side] = mxCreateCellMatrix(N, 1);
+        for (size_t i = 0; i < N; ++i) {
+            const int a = lane_ptr[2 * i + side], b = lane_ptr[2 * i + side + 1];
+            mxArray *m = mxCreateDoubleMatrix(2, b - a, mxREAL);
+            for (int j = a; j < b; ++j) {
+                mxGetDoubles(m)[2 * (j - a)] = lx[j];
+                mxGetDoubles(m)[2 * (j - a) + 1] = ly[j];
+            }
+            mxSetCell(plhs[5 + side], i, m);
+        }
+    }
+}
+
 }  // namespace
 
 void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
@@ -468,6 +575,14 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
     case PLAN_JOINT:
         if (nrhs < 12) fail("pdmpc:usage", "PLAN_JOINT needs 12 arguments");
         plan_timestep(h, nlhs, plhs, prhs, true);
+        return;
+    case UPLOAD_ROAD:
+        if (nrhs < 8) fail("pdmpc:usage", "UPLOAD_ROAD needs 8 arguments");
+        upload_road(h, prhs);
+        return;
+    case SAMPLE_INPUTS:
+        if (nrhs < 7) fail("pdmpc:usage", "SAMPLE_INPUTS needs 7 arguments");
+        sample_inputs(h, nlhs, plhs, prhs);
         return;
     case STATS: {
         pdmpc_stats st;

@@ -88,6 +88,16 @@ mxArray *mxCreateNumericMatrix(mwSize m, mwSize n, mxClassID cls, mxComplexity) 
     else a->real.assign(m * n, 0.0);
     return a;
 }
+mxArray *mxCreateNumericArray(mwSize ndim, const mwSize *dims, mxClassID cls, mxComplexity) {
+    mxArray *a = new mxArray;
+    a->cls = cls;
+    a->dims.assign(dims, dims + ndim);
+    size_t n = 1;
+    for (mwSize i = 0; i < ndim; ++i) n *= dims[i];
+    if (cls == mxUINT64_CLASS) a->u64.assign(n, 0);
+    else a->real.assign(n, 0.0);
+    return a;
+}
 mxArray *mxCreateCellMatrix(mwSize m, mwSize n) {
     mxArray *a = new mxArray;
     a->cls = mxCELL_CLASS;

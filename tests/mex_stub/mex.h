@@ -40,6 +40,7 @@ mxArray *mxCreateLogicalScalar(bool v);
 mxArray *mxCreateDoubleScalar(double v);
 mxArray *mxCreateDoubleMatrix(mwSize m, mwSize n, mxComplexity c);
 mxArray *mxCreateNumericMatrix(mwSize m, mwSize n, mxClassID cls, mxComplexity c);
+mxArray *mxCreateNumericArray(mwSize ndim, const mwSize *dims, mxClassID cls, mxComplexity c);
 mxArray *mxCreateCellMatrix(mwSize m, mwSize n);
 mxArray *mxCreateStructMatrix(mwSize m, mwSize n, int nfields, const char **names);
 int mexAtExit(void (*fn)(void));

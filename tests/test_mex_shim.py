@@ -195,3 +195,50 @@ def test_mex_joint_path_matches_oracle(matlab):
     finally:
         matlab.call(0, mexfake.DESTROY, float(h))
         matlab.clear_mex()
+
+
+@pytest.mark.gpu
+def test_mex_sample_inputs_matches_the_host_functions(matlab):
+    """UPLOAD_ROAD + SAMPLE_INPUTS (sample_inputs_cuda.m): reference trajectories and lanelet boundaries of all vehicles of
+    a time step through the shim, bit for bit against the host restatement of the reference's functions."""
+    from pdmpc_b200 import scenario
+    from pdmpc_b200.mpa import get_mpa
+    mpa = get_mpa("triple_speed", non_convex=True)
+    sc = scenario.commonroad_scenario(mpa, 20, seed=2)
+    (h,) = matlab.call(1, mexfake.CREATE, 0.0)
+    try:
+        trans, man = mexfake.matlab_mpa(mpa)
+        matlab.call(0, mexfake.UPLOAD_MPA, float(h), trans, man)
+        bounds = [[np.ascontiguousarray(l), np.ascontiguousarray(r)] for l, r in sc.road.boundary]      # {nL x 2} of n x 2
+        veh = sc.vehicles
+        matlab.call(0, mexfake.UPLOAD_ROAD, float(h), bounds, [v.reference_path for v in veh],
+                    [np.asarray(v.lanelets_index, dtype=np.float64) for v in veh],
+                    [np.asarray(v.points_index, dtype=np.float64) for v in veh],
+                    np.array([float(v.is_loop) for v in veh]), np.array([v.reference_speed for v in veh]))
+        rng = np.random.default_rng(5)
+        n = len(veh)
+        poses = np.array([v.reference_path[rng.integers(0, v.reference_path.shape[0])] + rng.normal(scale=0.02, size=2) for v in veh])
+        trims = rng.integers(1, mpa.trim_speed.size + 1, size=n)
+        speed = np.array([mpa.trim_speed[t - 1] for t in trims])
+        ref, v_ref, pidx, cur, pred, left, right = matlab.call(7, mexfake.SAMPLE_INPUTS, float(h), np.arange(1, n + 1, dtype=np.float64),
+                                                               poses[:, 0], poses[:, 1], speed, mpa.dt_seconds)
+        assert ref.shape == (n, mpa.Hp, 2) and v_ref.shape == (n, mpa.Hp)
+        for i, v in enumerate(veh):
+            pts, vr, idx, c = scenario.get_reference_trajectory(mpa, v, poses[i, 0], poses[i, 1], int(trims[i]), mpa.dt_seconds)
+            lan = scenario.get_predicted_lanelets(v, idx)
+            lft, rgt = scenario.get_lanelets_boundary(lan, sc.road, v)
+            assert np.array_equal(np.ascontiguousarray(ref[i]).view(np.uint64), np.ascontiguousarray(pts).view(np.uint64))
+            assert np.array_equal(v_ref[i], vr) and pidx[i].astype(int).tolist() == idx.tolist() and int(cur[i, 0]) == c
+            assert pred[i].reshape(-1).astype(int).tolist() == lan.tolist()
+            assert np.array_equal(left[i], lft) and np.array_equal(right[i], rgt)
+        with pytest.raises(mexfake.MexError):
+            matlab.call(1, mexfake.SAMPLE_INPUTS, float(h), np.array([n + 1.0]), poses[:1, 0], poses[:1, 1], speed[:1], mpa.dt_seconds)
+    finally:
+        matlab.call(0, mexfake.DESTROY, float(h))
+        matlab.clear_mex()
+
+
+def test_sample_inputs_matlab_helper_present():
+    import os
+    src = open(os.path.join(mexfake.ROOT, "p-dmpc_b200", "matlab", "sample_inputs_cuda.m")).read()
+    assert "UPLOAD_ROAD = 8" in src and "SAMPLE_INPUTS = 9" in src and "predicted_lanelet_boundary" in src
