@@ -393,6 +393,22 @@ int pdmpc_upload_road(pdmpc_handle *h, const pdmpc_road_desc *road);
 int pdmpc_sample_inputs(pdmpc_handle *h, int32_t n, const int32_t *path_id, const double *x, const double *y,
                         const double *speed, double dt_seconds, pdmpc_inputs_out *out);
 
+/* ---- The output side of a time step on the device: the plan a vehicle falls back to when
+ *      its search is exhausted — standstill at its pose (handle_graph_search_exhaustion,
+ *      PrioritizedController.m:568-621, area = get_occupied_areas.m:21-25) or the previous plan shifted by one step
+ *      (plan_fallback :678-718, del_first_rpt_last) — needs the previous time step's plans; they stay on the device,
+ *      one SLOT per vehicle (of every scenario the handle serves).
+ *      pdmpc_closed_loop_reset: forget all plans (scenario start).  half_length / half_width = Length/2 + offset,
+ *      Width/2 + offset of the standstill rectangle.
+ *      pdmpc_plan_timestep_closed_loop = pdmpc_plan_timestep, except that (i) deps->fb_* are ignored: the fallback
+ *      areas exhausted predecessors publish are built on the device from the slots' previous plans (standstill[i] != 0,
+ *      or no previous plan: the standstill rectangle at (x0, y0, yaw0), trims = trim0), (ii) on return trims[1..Hp],
+ *      y_predicted and shape_* of an exhausted row hold its FALLBACK plan (is_exhausted still says so; g_path, h_path,
+ *      tree_path keep their "no plan" values), (iii) every row's final plan is stored in its slot for the next call. */
+int pdmpc_closed_loop_reset(pdmpc_handle *h, int32_t n_slots, double half_length, double half_width);
+int pdmpc_plan_timestep_closed_loop(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_timestep_deps *deps,
+                                    const int32_t *slot, const uint8_t *standstill, pdmpc_batch_out *out);
+
 /* Pinned host buffers for callers that want full-rate host<->device copies. */
 int pdmpc_host_alloc(void **p, size_t bytes);
 int pdmpc_host_free(void *p);

@@ -30,7 +30,7 @@ PDMPC_ERR_ALLOC = 5
 
 EXPORTED_SYMBOLS = (
     "pdmpc_create", "pdmpc_destroy", "pdmpc_last_error", "pdmpc_abi_version",
-    "pdmpc_set_node_capacity", "pdmpc_set_variant", "pdmpc_set_tile_points", "pdmpc_set_cta_queue", "pdmpc_set_escalation", "pdmpc_get_hp", "pdmpc_pack_plan_rows", "pdmpc_upload_road", "pdmpc_sample_inputs", "pdmpc_host_alloc", "pdmpc_host_free",
+    "pdmpc_set_node_capacity", "pdmpc_set_variant", "pdmpc_set_tile_points", "pdmpc_set_cta_queue", "pdmpc_set_escalation", "pdmpc_get_hp", "pdmpc_pack_plan_rows", "pdmpc_upload_road", "pdmpc_sample_inputs", "pdmpc_closed_loop_reset", "pdmpc_plan_timestep_closed_loop", "pdmpc_host_alloc", "pdmpc_host_free",
     "pdmpc_trace_staged", "pdmpc_upload_mpa", "pdmpc_plan_batch", "pdmpc_stage_batch",
     "pdmpc_run_staged", "pdmpc_sync", "pdmpc_fetch_staged", "pdmpc_get_stats", "pdmpc_stream",
     "pdmpc_mcts_plan_batch", "pdmpc_mcts_run_staged", "pdmpc_set_cta_heap_smem", "pdmpc_plan_timestep",
@@ -203,6 +203,11 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.pdmpc_upload_road.restype = C.c_int
     lib.pdmpc_sample_inputs.argtypes = [H, C.c_int32, _p_i32, _p_f64, _p_f64, _p_f64, C.c_double, C.POINTER(InputsOutC)]
     lib.pdmpc_sample_inputs.restype = C.c_int
+    lib.pdmpc_closed_loop_reset.argtypes = [H, C.c_int32, C.c_double, C.c_double]
+    lib.pdmpc_closed_loop_reset.restype = C.c_int
+    lib.pdmpc_plan_timestep_closed_loop.argtypes = [H, C.POINTER(BatchIn), C.POINTER(TimestepDepsC), _p_i32,
+                                                    C.POINTER(C.c_uint8), C.POINTER(BatchOut)]
+    lib.pdmpc_plan_timestep_closed_loop.restype = C.c_int
     lib.pdmpc_get_hp.argtypes = [H]
     lib.pdmpc_get_hp.restype = C.c_int
     lib.pdmpc_set_escalation.argtypes = [H, C.c_int32, C.c_int32]
@@ -392,6 +397,27 @@ class Planner:
         d = TimestepDepsC(pred_ptr=_ptr(deps.pred_ptr, _p_i32), pred_idx=_ptr(pidx, _p_i32),
                           fb_npts=_ptr(deps.fb_npts, _p_i32), fb_x=_ptr(deps.fb_x, _p_f64), fb_y=_ptr(deps.fb_y, _p_f64))
         self._check(self.lib.pdmpc_plan_timestep(self.h, C.byref(bi), C.byref(d), C.byref(bo)))
+        if raise_on_search_error and b.n and int(r.status.max()) != PDMPC_OK:
+            bad = int(np.flatnonzero(r.status != PDMPC_OK)[0])
+            raise PdmpcError(int(r.status[bad]), f"search {bad} failed")
+        return r
+
+    def closed_loop_reset(self, n_slots: int, half_length: float, half_width: float):
+        """Forget the previous plans of all vehicle slots (pdmpc_closed_loop_reset)."""
+        self._check(self.lib.pdmpc_closed_loop_reset(self.h, int(n_slots), float(half_length), float(half_width)))
+
+    def plan_timestep_closed_loop(self, b: SearchBatch, deps, slot, standstill, raise_on_search_error: bool = True) -> BatchResult:
+        """pdmpc_plan_timestep_closed_loop: like plan_timestep, but the fallback plans of exhausted vehicles are built on
+        the device from the previous time step's plans kept there; exhausted rows return their fallback plan."""
+        self._check_hp(b)
+        r = BatchResult.empty(b.n, b.Hp)
+        bi, bo = batch_in(b), batch_out(r)
+        pidx = deps.pred_idx if deps.pred_idx.size else np.zeros(1, dtype=np.int32)
+        d = TimestepDepsC(pred_ptr=_ptr(deps.pred_ptr, _p_i32), pred_idx=_ptr(pidx, _p_i32), fb_npts=None, fb_x=None, fb_y=None)
+        slot = np.ascontiguousarray(slot, dtype=np.int32)
+        still = np.ascontiguousarray(standstill, dtype=np.uint8)
+        self._check(self.lib.pdmpc_plan_timestep_closed_loop(self.h, C.byref(bi), C.byref(d), _ptr(slot, _p_i32),
+                                                             _ptr(still, C.POINTER(C.c_uint8)), C.byref(bo)))
         if raise_on_search_error and b.n and int(r.status.max()) != PDMPC_OK:
             bad = int(np.flatnonzero(r.status != PDMPC_OK)[0])
             raise PdmpcError(int(r.status[bad]), f"search {bad} failed")

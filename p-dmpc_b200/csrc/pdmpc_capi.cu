@@ -21,6 +21,7 @@
 #include "pdmpc_cta.cuh"
 #include "pdmpc_joint.cuh"
 #include "pdmpc_inputs.cuh"
+#include "pdmpc_fallback.cuh"
 
 using namespace pdmpc;
 
@@ -195,6 +196,11 @@ struct pdmpc_handle {
     DBuf r_bptr, r_bx, r_by, r_pptr, r_px, r_py, r_lptr, r_lidx, r_pidx, r_loop, r_speed;
     DBuf i_pid, i_x, i_y, i_speed, i_refx, i_refy, i_vref, i_ridx, i_cur, i_pred, i_pre, i_cnt, i_lptr, i_lx, i_ly;
 
+    // closed loop on the device (pdmpc_closed_loop_reset / pdmpc_plan_timestep_closed_loop)
+    ClosedLoopDev cl{};
+    DBuf cl_valid, cl_trims, cl_traj, cl_npts, cl_sx, cl_sy;
+    DBuf cf_slot, cf_still, cf_npts, cf_x, cf_y, cf_traj, cf_trims;
+
     // trace (debug / parity tests)
     DBuf t_ids, t_n;
 
@@ -330,6 +336,9 @@ int pdmpc_destroy(pdmpc_handle *h) {
     for (DBuf *b : {&h->r_bptr, &h->r_bx, &h->r_by, &h->r_pptr, &h->r_px, &h->r_py, &h->r_lptr, &h->r_lidx, &h->r_pidx,
                     &h->r_loop, &h->r_speed, &h->i_pid, &h->i_x, &h->i_y, &h->i_speed, &h->i_refx, &h->i_refy, &h->i_vref,
                     &h->i_ridx, &h->i_cur, &h->i_pred, &h->i_pre, &h->i_cnt, &h->i_lptr, &h->i_lx, &h->i_ly})
+        b->release();
+    for (DBuf *b : {&h->cl_valid, &h->cl_trims, &h->cl_traj, &h->cl_npts, &h->cl_sx, &h->cl_sy, &h->cf_slot, &h->cf_still,
+                    &h->cf_npts, &h->cf_x, &h->cf_y, &h->cf_traj, &h->cf_trims})
         b->release();
     h->esc.release();
     h->esc_rows.release();
@@ -1392,8 +1401,10 @@ int pdmpc_plan_batch(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc_batch_out 
 }
 
 // One whole time step (or many) as ONE dependency-ordered launch: see include/pdmpc_b200.h.
-int pdmpc_plan_timestep(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_timestep_deps *deps,
-                        pdmpc_batch_out *out) {
+// slot / standstill != NULL: the closed-loop variant — fallback plans come from (and final plans go to) the state on
+// the device (pdmpc_fallback.cuh); deps->fb_* are then ignored.
+static int plan_timestep_impl(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_timestep_deps *deps,
+                              pdmpc_batch_out *out, const int32_t *slot, const uint8_t *standstill) {
     if (!h) return PDMPC_ERR_BAD_INPUT;
     if (!h->has_mpa) return fail(h, PDMPC_ERR_NO_MPA, "plan_timestep: call pdmpc_upload_mpa first");
     if (!in || !deps || !deps->pred_ptr) return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep: NULL argument");
@@ -1469,7 +1480,8 @@ int pdmpc_plan_timestep(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_t
     }
     // ---- dependency CSR + fallback areas: one pinned block, one copy ------------------------------
     const size_t nhp = (size_t)n * Hp;
-    const bool has_fb = deps->fb_npts != nullptr;
+    const bool closed_loop = slot != nullptr;
+    const bool has_fb = !closed_loop && deps->fb_npts != nullptr;
     const size_t sz[5] = {((size_t)n + 1) * sizeof(int), (size_t)std::max(total, 1) * sizeof(int),
                           has_fb ? nhp * sizeof(int) : 0, has_fb ? nhp * PDMPC_AREA_STRIDE * sizeof(double) : 0,
                           has_fb ? nhp * PDMPC_AREA_STRIDE * sizeof(double) : 0};
@@ -1499,6 +1511,24 @@ int pdmpc_plan_timestep(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_t
     dp.done = h->d_done.as<int>();
     dp.dep_x = dp.dep_y = nullptr;
     dp.dep_n = nullptr;
+    FallbackDev fbd{};
+    if (closed_loop) {
+        // fallback plans of all rows from the previous time step's plans on the device (known before the searches start)
+        UP(h, h->cf_slot, slot, n);
+        UP(h, h->cf_still, standstill, n);
+        CU_TRY(h, h->cf_npts.reserve(nhp * sizeof(int)));
+        CU_TRY(h, h->cf_x.reserve(nhp * PDMPC_AREA_STRIDE * sizeof(double)));
+        CU_TRY(h, h->cf_y.reserve(nhp * PDMPC_AREA_STRIDE * sizeof(double)));
+        CU_TRY(h, h->cf_traj.reserve(nhp * 3 * sizeof(double)));
+        CU_TRY(h, h->cf_trims.reserve(nhp * sizeof(int)));
+        fbd.slot = h->cf_slot.as<int>(); fbd.still = h->cf_still.as<unsigned char>();
+        fbd.fb_npts = h->cf_npts.as<int>(); fbd.fb_x = h->cf_x.as<double>(); fbd.fb_y = h->cf_y.as<double>();
+        fbd.fb_traj = h->cf_traj.as<double>(); fbd.fb_trims = h->cf_trims.as<int>();
+        make_fallback_kernel<<<(unsigned)((nhp + 127) / 128), 128, 0, h->stream>>>(h->batch, h->cl, fbd);
+        CU_TRY(h, cudaGetLastError());
+        h->stats.kernel_launches++;
+        dp.fb_npts = fbd.fb_npts; dp.fb_x = fbd.fb_x; dp.fb_y = fbd.fb_y;
+    }
     // ---- one persistent launch: CTAs / warps take the searches in topological order ----------------
     CU_TRY(h, cudaMemsetAsync(h->out.counters, 0, 16 * sizeof(unsigned long long), h->stream));
     CU_TRY(h, cudaMemsetAsync(h->work_counter.p, 0, sizeof(unsigned), h->stream));
@@ -1528,11 +1558,61 @@ int pdmpc_plan_timestep(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_t
                                                                       h->work_counter.as<unsigned>(),
                                                                       TraceDev{-1, nullptr, 0, nullptr}, dp);
     CU_TRY(h, cudaGetLastError());
+    h->stats.kernel_launches++;
+    if (closed_loop) {
+        finalize_closed_loop_kernel<<<(unsigned)((nhp + 127) / 128), 128, 0, h->stream>>>(n, h->out, h->cl, fbd);
+        CU_TRY(h, cudaGetLastError());
+        h->stats.kernel_launches++;
+    }
     CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
     h->timing_pending_kernel = true;
     h->stats.handed_over = 0;
-    h->stats.kernel_launches++;
     return pdmpc_fetch_staged(h, out);
+}
+
+int pdmpc_plan_timestep(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_timestep_deps *deps,
+                        pdmpc_batch_out *out) {
+    return plan_timestep_impl(h, in, deps, out, nullptr, nullptr);
+}
+
+int pdmpc_closed_loop_reset(pdmpc_handle *h, int32_t n_slots, double half_length, double half_width) {
+    if (!h) return PDMPC_ERR_BAD_INPUT;
+    if (!h->has_mpa) return fail(h, PDMPC_ERR_NO_MPA, "closed_loop_reset: call pdmpc_upload_mpa first (Hp)");
+    if (n_slots < 1 || !(half_length > 0) || !(half_width > 0))
+        return fail(h, PDMPC_ERR_BAD_INPUT, "closed_loop_reset: n_slots >= 1, half_length > 0, half_width > 0");
+    CU_TRY(h, cudaSetDevice(h->device));
+    const size_t sh = (size_t)n_slots * h->mpa.Hp;
+    CU_TRY(h, h->cl_valid.reserve((size_t)n_slots * sizeof(int)));
+    CU_TRY(h, h->cl_trims.reserve(sh * sizeof(int)));
+    CU_TRY(h, h->cl_traj.reserve(sh * 3 * sizeof(double)));
+    CU_TRY(h, h->cl_npts.reserve(sh * sizeof(int)));
+    CU_TRY(h, h->cl_sx.reserve(sh * PDMPC_AREA_STRIDE * sizeof(double)));
+    CU_TRY(h, h->cl_sy.reserve(sh * PDMPC_AREA_STRIDE * sizeof(double)));
+    CU_TRY(h, cudaMemsetAsync(h->cl_valid.p, 0, (size_t)n_slots * sizeof(int), h->stream));
+    ClosedLoopDev &c = h->cl;
+    c.n_slots = n_slots; c.Hp = h->mpa.Hp; c.half_len = half_length; c.half_wid = half_width;
+    c.valid = h->cl_valid.as<int>(); c.trims = h->cl_trims.as<int>(); c.traj = h->cl_traj.as<double>();
+    c.npts = h->cl_npts.as<int>(); c.sx = h->cl_sx.as<double>(); c.sy = h->cl_sy.as<double>();
+    return PDMPC_OK;
+}
+
+int pdmpc_plan_timestep_closed_loop(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_timestep_deps *deps,
+                                    const int32_t *slot, const uint8_t *standstill, pdmpc_batch_out *out) {
+    if (!h) return PDMPC_ERR_BAD_INPUT;
+    if (h->cl.n_slots < 1 || h->cl.Hp != h->mpa.Hp)
+        return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep_closed_loop: call pdmpc_closed_loop_reset first (after pdmpc_upload_mpa)");
+    if (!in || !slot || !standstill || !out || !out->is_exhausted || !out->trims || !out->y_predicted || !out->shape_npts ||
+        !out->shape_x || !out->shape_y)
+        return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep_closed_loop: slot, standstill and the plan outputs are required");
+    {
+        std::vector<char> seen((size_t)h->cl.n_slots, 0);
+        for (int i = 0; i < in->n_searches; ++i) {
+            if (slot[i] < 0 || slot[i] >= h->cl.n_slots || seen[slot[i]])
+                return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep_closed_loop: slots must be distinct and below n_slots");
+            seen[slot[i]] = 1;
+        }
+    }
+    return plan_timestep_impl(h, in, deps, out, slot, standstill);
 }
 
 // Centralized (joint) search: rows = searches x n_vehicles (pdmpc_joint.cuh).

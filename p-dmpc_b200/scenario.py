@@ -370,11 +370,41 @@ def road_tables(scenarios: Sequence["Scenario"]) -> dict:
 
 
 # --------------------------------------------------------------------------- coupling / priorities
+_SC_TWO_OVER_PI = float.fromhex("0x1.45f306dc9c883p-1")
+_SC_P = tuple(float.fromhex(v) for v in ("0x1.921fb54400000p+0", "0x1.0b4611a600000p-34", "0x1.3198a2e037073p-69"))
+_SC_S = tuple(float.fromhex(v) for v in (
+    "-0x1.5555555555555p-3", "0x1.1111111111111p-7", "-0x1.a01a01a01a01ap-13", "0x1.71de3a556c734p-19",
+    "-0x1.ae64567f544e4p-26", "0x1.6124613a86d09p-33", "-0x1.ae7f3e733b81fp-41", "0x1.952c77030ad4ap-49",
+    "-0x1.2f49b46814157p-57", "0x1.71b8ef6dcf572p-66"))
+_SC_C = tuple(float.fromhex(v) for v in (
+    "-0x1.0000000000000p-1", "0x1.5555555555555p-5", "-0x1.6c16c16c16c17p-10", "0x1.a01a01a01a01ap-16",
+    "-0x1.27e4fb7789f5cp-22", "0x1.1eed8eff8d898p-29", "-0x1.93974a8c07c9dp-37", "0x1.ae7f3e733b81fp-45",
+    "-0x1.6827863b97d97p-53", "0x1.e542ba4020225p-62"))
+
+
+def sincos_spec(x: float):
+    """(sin x, cos x) by the arithmetic specification of DESIGN.md §2 (three-term Cody-Waite reduction, degree-10
+    polynomials, no FMA) — the algorithm of sincos_ref in pdmpc_kernels.cuh, operation by operation, so that areas
+    placed on the host and on the device agree bit for bit."""
+    x = float(x)
+    n = float(round(x * _SC_TWO_OVER_PI))                       # rint: ties to even
+    r = ((x - n * _SC_P[0]) - n * _SC_P[1]) - n * _SC_P[2]
+    z = r * r
+    ps, pc = _SC_S[9], _SC_C[9]
+    for i in range(8, -1, -1):
+        ps = ps * z + _SC_S[i]
+        pc = pc * z + _SC_C[i]
+    sr = r + (r * z) * ps
+    cr = 1.0 + z * pc
+    q = int(n) & 3
+    return ((sr, cr), (cr, -sr), (-sr, -cr), (-cr, sr))[q]
+
+
 def occupied_area(x, y, yaw, offset=0.01) -> np.ndarray:
     """get_occupied_areas.m:21-25 (normal_offset, closed 5-point rectangle)"""
-    xl = np.array([-1, -1, 1, 1, -1]) * (VEH_LENGTH / 2 + offset)
-    yl = np.array([-1, 1, 1, -1, -1]) * (VEH_WIDTH / 2 + offset)
-    c, s = np.cos(yaw), np.sin(yaw)
+    xl = np.array([-1.0, -1.0, 1.0, 1.0, -1.0]) * (VEH_LENGTH / 2 + offset)
+    yl = np.array([-1.0, 1.0, 1.0, -1.0, -1.0]) * (VEH_WIDTH / 2 + offset)
+    s, c = sincos_spec(yaw)
     return np.vstack([c * xl - s * yl + x, s * xl + c * yl + y])
 
 
@@ -607,7 +637,7 @@ class ScenarioRunner:
     PrioritizedSequentialController.m:83-92)."""
 
     def __init__(self, sc: Scenario, plan_fn: PlanFn, max_num_CLs: int = 99, timestep_fn=None, inputs_fn=None,
-                 path_id0: int = 0):
+                 path_id0: int = 0, closed_loop_fn=None):
         """plan_fn(batch) plans one computation level; with timestep_fn(batch, deps) the whole time
         step is ONE call and the predecessors' areas are handed over behind it (pdmpc_plan_timestep).
         inputs_fn(path_id, x, y, speed, dt) -> dict (capi.Planner.sample_inputs): reference trajectories and lanelet
@@ -618,6 +648,9 @@ class ScenarioRunner:
         self.timestep_fn = timestep_fn
         self.inputs_fn = inputs_fn
         self.path_id0 = path_id0
+        # closed_loop_fn(batch, deps, slot, standstill) -> BatchResult with the FINAL plan of every vehicle
+        # (capi.Planner.plan_timestep_closed_loop): fallback plans are built and kept on the device, slot = path_id0 + i
+        self.closed_loop_fn = closed_loop_fn
         self.max_num_CLs = max_num_CLs              # honoured by the one-call path (timestep_inputs)
         self.timestep_records: List[tuple] = []     # (step, batch, deps, result) of the one-call path
         self.mpa = sc.mpa
@@ -704,11 +737,30 @@ class ScenarioRunner:
         self.k += 1
         iters, preds, fallbacks = self.timestep_inputs()
         batch = SearchBatch.from_iters(iters, Hp, sc.checker, mpa.dt_seconds)
-        deps = TimestepDeps.build(preds, [f[0] for f in fallbacks], Hp)
-        res = self.timestep_fn(batch, deps)
-        self.apply_timestep(res, fallbacks)
+        if self.closed_loop_fn is not None:
+            deps = TimestepDeps.build(preds, [None] * n, Hp)
+            still = np.array([abs(mpa.trim_speed[self.trim[i] - 1]) < 0.01 for i in range(n)], dtype=np.uint8)
+            res = self.closed_loop_fn(batch, deps, self.path_id0 + np.arange(n), still)
+            self.apply_final(res)
+        else:
+            deps = TimestepDeps.build(preds, [f[0] for f in fallbacks], Hp)
+            res = self.timestep_fn(batch, deps)
+            self.apply_timestep(res, fallbacks)
         self.timestep_records.append((self.k, batch, deps, res))
         return res
+
+    def apply_final(self, res: BatchResult) -> None:
+        """Plans of one time step whose exhausted rows already hold the fallback plan (device-side closed loop)."""
+        n = self.sc.amount
+        shapes_now: List[Optional[List[np.ndarray]]] = [None] * n
+        for i in range(n):
+            self.n_fallbacks += int(res.is_exhausted[i])
+            shapes_now[i] = res.shapes(i)
+            self.prev_traj[i] = res.y_predicted[i].copy()
+            self.prev_trims[i] = res.trims[i, 1:].copy()
+            self.pose[i] = self.prev_traj[i][0]
+            self.trim[i] = self.prev_trims[i][0]
+        self.prev_shapes = shapes_now
 
     def apply_timestep(self, res: BatchResult, fallbacks) -> None:
         """Take the plans of one time step (row i = vehicle i): exhausted vehicles execute their fallback
@@ -730,7 +782,7 @@ class ScenarioRunner:
         self.pose, self.trim = new_pose, new_trim
 
     def step(self) -> List[StepRecord]:
-        if self.timestep_fn is not None:
+        if self.timestep_fn is not None or self.closed_loop_fn is not None:
             self.step_timestep()
             return []
         sc, mpa = self.sc, self.mpa

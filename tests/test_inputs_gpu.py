@@ -102,3 +102,47 @@ def test_closed_loop_with_device_side_inputs(planner):
             assert np.array_equal(dev.pose.view(np.uint64), ref.pose.view(np.uint64)) and np.array_equal(dev.trim, ref.trim)
         _k, tb, td, got = dev.timestep_records[-1]
         parity.compare(got, scenario.plan_timestep_by_levels(lambda x: oracle_py.plan_batch(mpa, x), tb, td))
+
+
+def test_host_sincos_follows_the_arithmetic_specification():
+    """scenario.sincos_spec (areas placed on the host: standstill rectangles) == the oracle's / the device's sin/cos."""
+    import math
+    rng = np.random.default_rng(0)
+    for x in list(rng.uniform(-60, 60, 3000)) + [0.0, math.pi / 2, math.pi, -math.pi, 1e-300, 3 * math.pi / 2, 2.5, -2.5]:
+        assert scenario.sincos_spec(x) == oracle_py.sincos(x), x
+
+
+@pytest.mark.gpu
+def test_closed_loop_with_fallback_plans_on_the_device(planner):
+    """pdmpc_plan_timestep_closed_loop: the fallback plan of an exhausted vehicle (standstill, or the previous plan
+    shifted by one step: PrioritizedController.m:568-621, :678-718) is built on the device from the plans of the previous
+    time step kept there; together with pdmpc_sample_inputs a time step needs the host only for coupling and priorities.
+    Same closed loop as the host fallback logic driven by the oracle, with exhausted searches along the way."""
+    mpa = get_mpa("triple_speed", non_convex=True)
+    planner.upload_mpa(mpa)
+    seeds = (1, 7)
+    scs = [scenario.commonroad_scenario(mpa, 20, seed=s) for s in seeds]
+    planner.upload_road(scenario.road_tables(scs))
+    planner.closed_loop_reset(40, scenario.VEH_LENGTH / 2 + 0.01, scenario.VEH_WIDTH / 2 + 0.01)
+    fallbacks = 0
+    for k, sc in enumerate(scs):
+        dev = scenario.ScenarioRunner(sc, None, inputs_fn=planner.sample_inputs, path_id0=20 * k,
+                                      closed_loop_fn=lambda b, d, s, st: planner.plan_timestep_closed_loop(b, d, s, st, False))
+        ref = scenario.ScenarioRunner(scenario.commonroad_scenario(mpa, 20, seed=seeds[k]),
+                                      lambda b: oracle_py.plan_batch(mpa, b, 4))
+        for step in range(14):
+            dev.step()
+            ref.step()
+            assert np.array_equal(dev.pose.view(np.uint64), ref.pose.view(np.uint64)), (k, step)
+            assert np.array_equal(dev.trim, ref.trim)
+            for i in range(20):   # what every vehicle published: planned or fallback areas
+                for a, b in zip(dev.prev_shapes[i], ref.prev_shapes[i]):
+                    assert np.array_equal(a, b)
+        assert dev.n_fallbacks == ref.n_fallbacks
+        fallbacks += dev.n_fallbacks
+    assert fallbacks > 5
+    # a fresh scenario in used slots needs a reset: stale plans would be shifted into it
+    planner.closed_loop_reset(40, scenario.VEH_LENGTH / 2 + 0.01, scenario.VEH_WIDTH / 2 + 0.01)
+    with pytest.raises(capi.PdmpcError):
+        b = dev.timestep_records[-1][1]
+        planner.plan_timestep_closed_loop(b, dev.timestep_records[-1][2], np.zeros(b.n, dtype=np.int32), np.zeros(b.n, dtype=np.uint8))
