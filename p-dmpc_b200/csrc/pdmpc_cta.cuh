@@ -361,16 +361,23 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
     unsigned next_item = blockIdx.x + gridDim.x * (unsigned)role_master;   // escalation list: this master's first item
     bool first_item = true;
 
+    unsigned my_jobs = 0, my_rot = 0;   // NM == 1: ticket and child counters of the only master
     // publish one job (an expansion, or the terminate order) on the shared ring; returns its ticket
     auto publish = [&](const NodeA &ca, double c, double s, unsigned nid0, int nchild, int sbase, int k,
                        int terminate) -> unsigned {
         unsigned tk = 0, rt = 0;
-        if (lane == 0) {
-            tk = atomicAdd(&sm.n_jobs, 1u);
-            rt = atomicAdd(&sm.rot, (unsigned)max(nchild, 0));
+        if (NM == 1) {   // the only producer: its tickets need no atomics
+            tk = my_jobs++;
+            rt = my_rot;
+            my_rot += (unsigned)max(nchild, 0);
+        } else {
+            if (lane == 0) {
+                tk = atomicAdd(&sm.n_jobs, 1u);
+                rt = atomicAdd(&sm.rot, (unsigned)max(nchild, 0));
+            }
+            tk = __shfl_sync(FULL, tk, 0);
+            rt = __shfl_sync(FULL, rt, 0);
         }
-        tk = __shfl_sync(FULL, tk, 0);
-        rt = __shfl_sync(FULL, rt, 0);
         while (true) {   // ring slot free: every checker is done with ticket tk - kRing
             const unsigned d = lane < NC ? vdone[lane] : tk;
             if (__all_sync(FULL, d + kRing > tk)) break;
@@ -382,7 +389,7 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
             jb.nid0 = nid0; jb.nchild = nchild; jb.sbase = sbase; jb.k = k;
             jb.terminate = terminate; jb.rot = (int)(rt % NC); jb.slot = ms;
         }
-        fence_cta();
+        // (no fence: the barrier orders the descriptor against the checkers that wait in bar.sync on it)
         __syncwarp();
         named_bar_arrive(1 + (int)(tk % kRing), kBarThreads);
         return tk;

@@ -46,7 +46,7 @@ def main():
         p.set_cta_queue(vo)
         for esc in (0, 2560):
             p.set_escalation(esc)
-            t, sh = timed(p, b, 2)
+            t, sh = timed(p, b, int(os.environ.get("PDMPC_SHAPE", "2")))
             p.fetch()
             st = p.stats()
             print(f"valid-only {vo} escalation {esc}: {t:.2f} ms -> {b.n / t / 1e3:.3f} M plans/s (escalated {st.escalated}, launches {st.kernel_launches})")
