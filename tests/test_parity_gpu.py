@@ -31,6 +31,11 @@ def check(planner, mpa, batch, variants=VARIANTS, **kw):
         for variant in variants:
             planner.set_variant(variant)
             dev = planner.plan_batch(batch, raise_on_search_error=False)
+            ran = int(planner.stats().shape)
+            if variant:   # a requested shape runs, or falls back to shape 1 for a documented reason — never silently
+                why = ((variant in (2, 3) and batch.checker != CHECKER_INTERX) or
+                       (variant in (4, 5) and mpa.full_tree_nodes() + 8 > 32768))
+                assert ran == (1 if why else variant), (variant, ran)
             if variant == 5:
                 # pop_hash covers the valid pops only — unless the shape fell back to shape 1 (search
                 # trees beyond 32768 nodes), which hashes every pop
