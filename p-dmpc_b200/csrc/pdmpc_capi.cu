@@ -506,13 +506,16 @@ int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *d) {
     }
     std::vector<int> npts(d->area_npts, d->area_npts + (size_t)nE * 3);
     padded(npts, sizeof(int));
-    // area points zero padded to the fixed stride (the kernel places all 8 columns)
+    // area points padded to the fixed stride by REPEATING THE LAST POINT: the kernels place all 8 columns without
+    // looking at the point count first (one dependent table load less per pop), and the InterX row of a padded column
+    // equals that of the last = first vertex
     std::vector<double> ax((size_t)nE * 3 * PDMPC_AREA_STRIDE, 0.0), ay(ax.size(), 0.0);
     bool closed = true;   // first point == last point, bit for bit (InterX shortcut b_last = b_first)
     for (int e = 0; e < nE * 3; ++e) {
-        for (int i = 0; i < d->area_npts[e]; ++i) {
-            ax[(size_t)e * PDMPC_AREA_STRIDE + i] = d->area_x[(size_t)e * PDMPC_AREA_STRIDE + i];
-            ay[(size_t)e * PDMPC_AREA_STRIDE + i] = d->area_y[(size_t)e * PDMPC_AREA_STRIDE + i];
+        for (int i = 0; i < PDMPC_AREA_STRIDE; ++i) {
+            const int src = std::min(i, d->area_npts[e] - 1);
+            ax[(size_t)e * PDMPC_AREA_STRIDE + i] = d->area_x[(size_t)e * PDMPC_AREA_STRIDE + src];
+            ay[(size_t)e * PDMPC_AREA_STRIDE + i] = d->area_y[(size_t)e * PDMPC_AREA_STRIDE + src];
         }
         const size_t f = (size_t)e * PDMPC_AREA_STRIDE, l = f + d->area_npts[e] - 1;
         if (memcmp(&ax[f], &ax[l], sizeof(double)) != 0 || memcmp(&ay[f], &ay[l], sizeof(double)) != 0) closed = false;

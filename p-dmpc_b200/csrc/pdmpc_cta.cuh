@@ -206,8 +206,7 @@ search_cta_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_co
                     // place both areas by the PARENT pose (GraphSearch.m:155-160); the tail repeats the last vertex
                     if (lane < 16) {
                         const int sel = lane >> 3, i = lane & 7;
-                        const int np = sel ? nbs : ns;
-                        const int ab = (edge * 3 + (sel ? bkind : PDMPC_AREA_NORMAL)) * kAreaStride + min(i, np - 1);
+                        const int ab = (edge * 3 + (sel ? bkind : PDMPC_AREA_NORMAL)) * kAreaStride + i;   // (padded by the last point)
                         const double ax = tb.area_x[ab], ay = tb.area_y[ab];
                         sts_f64x2(sshp + 16u * (unsigned)lane, pc * ax - ps * ay + ppx, ps * ax + pc * ay + ppy);
                     }

@@ -325,6 +325,20 @@ search_tile_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_c
         double2 pxy = make_double2(0.0, 0.0);
         int sbase = 0, nchild = 0, ns = 0, nbs = 0;
         const int bkind = (cK == Hp) ? PDMPC_AREA_LARGE_OFFSET : PDMPC_AREA_WITHOUT_OFFSET;   // :166-174
+        // the maneuver's area points this lane places (tables are padded by the last point: no count needed first)
+        double ax0 = 0.0, ay0 = 0.0, ax1 = 0.0, ay1 = 0.0;
+        if (chk) {
+            if (TILE >= 16) {
+                if (tl < 16) {
+                    const int ab = (edge * 3 + ((tl >> 3) ? bkind : PDMPC_AREA_NORMAL)) * kAreaStride + (tl & 7);
+                    ax0 = __ldg(m.area_x + ab); ay0 = __ldg(m.area_y + ab);
+                }
+            } else {
+                const int a0 = (edge * 3 + PDMPC_AREA_NORMAL) * kAreaStride + tl, a1 = (edge * 3 + bkind) * kAreaStride + tl;
+                ax0 = __ldg(m.area_x + a0); ay0 = __ldg(m.area_y + a0);
+                ax1 = __ldg(m.area_x + a1); ay1 = __ldg(m.area_y + a1);
+            }
+        }
         if (has) {
             ca = na[id];
             ccs = ncs[id];
@@ -409,24 +423,11 @@ search_tile_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_c
         // ---- eval_edge_exact :141-192: place the maneuver's areas by the PARENT pose ---------------
         bool valid = has;
         if (TILE >= 16) {
-            if (chk && tl < 16) {
-                const int sel = tl >> 3, i = tl & 7;
-                const int np = sel ? nbs : ns;
-                const int ab = (edge * 3 + (sel ? bkind : PDMPC_AREA_NORMAL)) * kAreaStride + min(i, np - 1);
-                const double ax = __ldg(m.area_x + ab), ay = __ldg(m.area_y + ab);
-                sts_f64x2(sshp + 16u * (unsigned)tl, pcs.c * ax - pcs.s * ay + pxy.x, pcs.s * ax + pcs.c * ay + pxy.y);
-            }
-        } else {
-#pragma unroll
-            for (int sel = 0; sel < 2; ++sel) {
-                if (chk) {
-                    const int np = sel ? nbs : ns;
-                    const int ab = (edge * 3 + (sel ? bkind : PDMPC_AREA_NORMAL)) * kAreaStride + min(tl, np - 1);
-                    const double ax = __ldg(m.area_x + ab), ay = __ldg(m.area_y + ab);
-                    sts_f64x2(sshp + 16u * (unsigned)(sel * 8 + tl), pcs.c * ax - pcs.s * ay + pxy.x,
-                              pcs.s * ax + pcs.c * ay + pxy.y);
-                }
-            }
+            if (chk && tl < 16)
+                sts_f64x2(sshp + 16u * (unsigned)tl, pcs.c * ax0 - pcs.s * ay0 + pxy.x, pcs.s * ax0 + pcs.c * ay0 + pxy.y);
+        } else if (chk) {
+            sts_f64x2(sshp + 16u * (unsigned)tl, pcs.c * ax0 - pcs.s * ay0 + pxy.x, pcs.s * ax0 + pcs.c * ay0 + pxy.y);
+            sts_f64x2(sshp + 16u * (unsigned)(8 + tl), pcs.c * ax1 - pcs.s * ay1 + pxy.x, pcs.s * ax1 + pcs.c * ay1 + pxy.y);
         }
         __syncwarp();
         // edge constants of InterX.m:63,67 — dx1, dy1, S1 = dx1*y1 - dy1*x1 — one edge per lane
