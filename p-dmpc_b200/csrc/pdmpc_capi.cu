@@ -166,7 +166,7 @@ struct pdmpc_handle {
     bool staged = false;
     BatchDev batch{};
     int n_polys = 0, n_verts = 0, n_lane = 0;
-    DBuf b_x0, b_y0, b_yaw0, b_trim0, b_refx, b_refy, b_vref, b_slot, b_poly, b_vx, b_vy, b_plx, b_ply,
+    DBuf b_x0, b_y0, b_yaw0, b_trim0, b_refx, b_refy, b_vref, b_slot, b_poly, b_vx, b_vy, b_plx, b_ply, b_plxy, b_llxy,
         b_lane, b_lx, b_ly, b_llx, b_lly, b_order, b_seed;
 
     // small batches (one computation level of a time step): every input array in ONE pinned
@@ -319,7 +319,7 @@ int pdmpc_destroy(pdmpc_handle *h) {
     DBuf *bufs[] = {&h->m_succ_ptr, &h->m_succ_te, &h->m_edge_d, &h->m_npts, &h->m_ax, &h->m_ay, &h->b_order,
                     &h->b_x0, &h->b_y0, &h->b_yaw0, &h->b_trim0,
                     &h->b_refx, &h->b_refy, &h->b_vref, &h->b_slot, &h->b_poly, &h->b_vx, &h->b_vy,
-                    &h->b_plx, &h->b_ply, &h->b_lane, &h->b_lx, &h->b_ly, &h->b_llx, &h->b_lly,
+                    &h->b_plx, &h->b_ply, &h->b_plxy, &h->b_llxy, &h->b_lane, &h->b_lx, &h->b_ly, &h->b_llx, &h->b_lly,
                     &h->work_counter, &h->b_seed, &h->a_a, &h->a_b, &h->a_cs, &h->a_heap, &h->t_ids, &h->t_n};
     for (DBuf *b : bufs) b->release();
     h->d_in_pack.release();
@@ -742,6 +742,7 @@ int pdmpc_stage_batch(pdmpc_handle *h, const pdmpc_batch_in *in) {
     b.lane_ptr = (const int *)dptr[11]; b.lane_x = (const double *)dptr[12]; b.lane_y = (const double *)dptr[13];
     b.order = n > 1 ? (const int *)dptr[14] : nullptr;
     b.pl_x = b.pl_y = b.ll_x = b.ll_y = nullptr;
+    b.pl_xy = b.ll_xy = nullptr;
     h->stats.kernel_launches = 0;
     if (in->checker == PDMPC_CHECKER_INTERX) {
         // NaN-separated polylines (vectorize_all_obstacles.m) built on the device
@@ -749,19 +750,22 @@ int pdmpc_stage_batch(pdmpc_handle *h, const pdmpc_batch_in *in) {
         CU_TRY(h, h->b_ply.reserve(((size_t)nv + np + 1) * sizeof(double)));
         CU_TRY(h, h->b_llx.reserve(((size_t)nl + 2 * n + 1) * sizeof(double)));
         CU_TRY(h, h->b_lly.reserve(((size_t)nl + 2 * n + 1) * sizeof(double)));
+        CU_TRY(h, h->b_plxy.reserve(((size_t)nv + np + 1) * sizeof(double2)));
+        CU_TRY(h, h->b_llxy.reserve(((size_t)nl + 2 * n + 1) * sizeof(double2)));
         if (np) {
             build_polyline_kernel<<<(np + 127) / 128, 128, 0, h->stream>>>(
-                np, b.poly_ptr, b.vert_x, b.vert_y, h->b_plx.as<double>(), h->b_ply.as<double>());
+                np, b.poly_ptr, b.vert_x, b.vert_y, h->b_plx.as<double>(), h->b_ply.as<double>(), 0, h->b_plxy.as<double2>());
             h->stats.kernel_launches++;
         }
         if (n) {
             build_polyline_kernel<<<(2 * n + 127) / 128, 128, 0, h->stream>>>(
-                2 * n, b.lane_ptr, b.lane_x, b.lane_y, h->b_llx.as<double>(), h->b_lly.as<double>());
+                2 * n, b.lane_ptr, b.lane_x, b.lane_y, h->b_llx.as<double>(), h->b_lly.as<double>(), 0, h->b_llxy.as<double2>());
             h->stats.kernel_launches++;
         }
         CU_TRY(h, cudaGetLastError());
         b.pl_x = h->b_plx.as<double>(); b.pl_y = h->b_ply.as<double>();
         b.ll_x = h->b_llx.as<double>(); b.ll_y = h->b_lly.as<double>();
+        b.pl_xy = h->b_plxy.as<double2>(); b.ll_xy = h->b_llxy.as<double2>();
     }
     h->n_polys = np; h->n_verts = nv; h->n_lane = nl;
     rc = ensure_outputs(h, n);
@@ -1156,6 +1160,8 @@ static int plan_batch_pipelined(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc
         CU_TRY(h, h->b_ply.reserve(((size_t)nv + np + 1) * sizeof(double)));
         CU_TRY(h, h->b_llx.reserve(((size_t)nl + 2 * n + 1) * sizeof(double)));
         CU_TRY(h, h->b_lly.reserve(((size_t)nl + 2 * n + 1) * sizeof(double)));
+        CU_TRY(h, h->b_plxy.reserve(((size_t)nv + np + 1) * sizeof(double2)));
+        CU_TRY(h, h->b_llxy.reserve(((size_t)nl + 2 * n + 1) * sizeof(double2)));
     }
     rc = ensure_outputs(h, n);
     if (rc != PDMPC_OK) return rc;
@@ -1164,7 +1170,21 @@ static int plan_batch_pipelined(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc
     CU_TRY(h, h->wc_chunks.reserve(kPipelineMaxChunks * sizeof(unsigned)));
     // one-warp CTAs leave an SM one by one as their searches end, so the next chunk's CTAs move in early
     constexpr int kLanes = 8;   // most concurrent chunk kernels (streams, arenas)
-    const int per_chunk = (n + C - 1) / C;
+    // chunk c covers the searches [bound(c), bound(c + 1)).  Nothing overlaps the first chunk's validation and copy,
+    // so it is a fraction of the others' size (pdmpc_first_chunk, experiment knob PDMPC_FIRST_CHUNK).
+    static const double first_frac = [] {
+        const char *e = getenv("PDMPC_FIRST_CHUNK");
+        const double f = e ? atof(e) : 0.25;
+        return f > 0.0 && f <= 1.0 ? f : 1.0;
+    }();
+    auto bound = [&](int c) -> int {
+        if (C < 3 || first_frac >= 1.0) return (int)((long long)n * c / C);
+        if (c <= 0) return 0;
+        if (c >= C) return n;
+        return (int)((double)n * ((double)(c - 1) + first_frac) / ((double)(C - 1) + first_frac));
+    };
+    int per_chunk = 1;
+    for (int c = 0; c < C; ++c) per_chunk = std::max(per_chunk, bound(c + 1) - bound(c));
     const int shape = resolve_warp_shape(h, h->variant_mode, per_chunk, in->checker, false);
     int slots = 0;
     warp_shape_grid(h, shape, per_chunk, &slots);
@@ -1198,6 +1218,7 @@ static int plan_batch_pipelined(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc
     b.order = h->b_order.as<int>();
     b.pl_x = interx ? h->b_plx.as<double>() : nullptr; b.pl_y = interx ? h->b_ply.as<double>() : nullptr;
     b.ll_x = interx ? h->b_llx.as<double>() : nullptr; b.ll_y = interx ? h->b_lly.as<double>() : nullptr;
+    b.pl_xy = interx ? h->b_plxy.as<double2>() : nullptr; b.ll_xy = interx ? h->b_llxy.as<double2>() : nullptr;
     h->n_polys = np; h->n_verts = nv; h->n_lane = nl;
     h->stats.h2d_bytes = 0;
     h->stats.d2h_bytes = 0;
@@ -1242,7 +1263,7 @@ static int plan_batch_pipelined(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc
         return code;
     };
     for (int c = 0; c < C; ++c) {
-        const int s0 = (int)((long long)n * c / C), s1 = (int)((long long)n * (c + 1) / C);
+        const int s0 = bound(c), s1 = bound(c + 1);
         if (s1 == s0) continue;
         rc = validate_range(h, in, s0, s1);
         if (rc != PDMPC_OK) return bail(rc);
@@ -1285,11 +1306,13 @@ static int plan_batch_pipelined(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc
         if (interx) {
             if (p1 > p0) {
                 build_polyline_kernel<<<(p1 - p0 + 127) / 128, 128, 0, S>>>(p1 - p0, b.poly_ptr, b.vert_x, b.vert_y,
-                                                                          h->b_plx.as<double>(), h->b_ply.as<double>(), p0);
+                                                                          h->b_plx.as<double>(), h->b_ply.as<double>(), p0,
+                                                                          h->b_plxy.as<double2>());
                 h->stats.kernel_launches++;
             }
             build_polyline_kernel<<<(2 * (s1 - s0) + 127) / 128, 128, 0, S>>>(2 * (s1 - s0), b.lane_ptr, b.lane_x, b.lane_y,
-                                                                          h->b_llx.as<double>(), h->b_lly.as<double>(), 2 * s0);
+                                                                          h->b_llx.as<double>(), h->b_lly.as<double>(), 2 * s0,
+                                                                          h->b_llxy.as<double2>());
             h->stats.kernel_launches++;
         }
         BatchDev bc = bproto;
@@ -1319,7 +1342,7 @@ static int plan_batch_pipelined(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc
         }
     }
     for (int c = 0; c < C; ++c)   // every chunk joins the handle's stream
-        if (c % lanes != 0 && (int)((long long)n * (c + 1) / C) > (int)((long long)n * c / C))
+        if (c % lanes != 0 && bound(c + 1) > bound(c))
             CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_chunk[2 * c + 1], 0));
     if (esc) {   // the searches the chunk kernels give up: CTA shape, all chunks' leftovers in one launch
         ArenaDev ae = h->arena;

@@ -103,6 +103,8 @@ struct BatchDev {
     // NaN-separated polylines (InterX checker), vectorize_all_obstacles.m:36-63:
     // vertex v of polygon p sits at v + p, a NaN column at poly_ptr[p+1] + p.
     const double *pl_x, *pl_y;
+    // the same columns as (x, y) pairs: what the tile shape reads (one 16-byte load per point); may be null
+    const double2 *pl_xy = nullptr, *ll_xy = nullptr;
     // lanelet bounds: raw (SAT) and [left, NaN, right, NaN] per search (InterX),
     // side s of search i at lane_ptr[2i+s] + 2i + s.
     const int *lane_ptr;
@@ -876,16 +878,20 @@ __global__ void __launch_bounds__(kWarp, PDMPC_MIN_CTAS_LAT) search_kernel(MpaDe
 // append the [NaN; NaN] column.  One thread per polygon.
 __global__ void build_polyline_kernel(int n_polys, const int *__restrict__ poly_ptr,
                                       const double *__restrict__ vx, const double *__restrict__ vy,
-                                      double *__restrict__ px, double *__restrict__ py, int p_base = 0) {
+                                      double *__restrict__ px, double *__restrict__ py, int p_base = 0,
+                                      double2 *__restrict__ pxy = nullptr) {
     const int p = p_base + blockIdx.x * blockDim.x + threadIdx.x;   // polygons [p_base, p_base + n_polys)
     if (p >= p_base + n_polys) return;
     const int v0 = poly_ptr[p], v1 = poly_ptr[p + 1];
     for (int v = v0; v < v1; ++v) {
-        px[v + p] = vx[v];
-        py[v + p] = vy[v];
+        const double x = vx[v], y = vy[v];
+        px[v + p] = x;
+        py[v + p] = y;
+        if (pxy) pxy[v + p] = make_double2(x, y);
     }
     px[v1 + p] = nan("");
     py[v1 + p] = nan("");
+    if (pxy) pxy[v1 + p] = make_double2(nan(""), nan(""));
 }
 
 }  // namespace pdmpc

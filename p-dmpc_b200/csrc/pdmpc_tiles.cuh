@@ -36,10 +36,17 @@
 // Limits (fail over, never silently): SAT batches and pop traces are served by search_kernel.
 #pragma once
 
+#include <type_traits>
+
 #include "pdmpc_kernels.cuh"
 
 namespace pdmpc {
 
+__device__ __forceinline__ unsigned keep_u32(unsigned a) {
+    unsigned b;
+    asm volatile("mov.u32 %0, %1;" : "=r"(b) : "r"(a));   // not rematerialisable
+    return b;
+}
 __device__ __forceinline__ void sts_f64x2(unsigned a, double x, double y) {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
 }
@@ -102,7 +109,9 @@ search_tile_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_c
     static_assert(HS % 2 == 0, "aligned child pairs");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
-    const int tile = lane / TILE, tl = lane % TILE, shift = tile * TILE;
+    const int tile = lane / TILE;
+    // read once: nvcc otherwise re-derives them from SR_TID.X (a slow special-register read) all over the pop loop
+    const int tl = (int)keep_u32((unsigned)(lane % TILE)), shift = (int)keep_u32((unsigned)(tile * TILE));
     const unsigned tmask = TB << shift;
     TileSm<HS, SP> &sm = reinterpret_cast<TileSm<HS, SP> *>(smem_raw)[tile];
     const unsigned sf = shared_base_once(sm.hf), sw = shared_base_once(sm.hw);
@@ -155,14 +164,14 @@ search_tile_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_c
     enum { IDLE = 0, RUN = 1, DONE = 2, EXIT = 3 };
     int phase = IDLE;
     int si = 0, trim0 = 0, len = 0;
-    int obase = 0, llo = 0, lhi = 0;
-    // polylines of the current search that are NOT staged: read through these (index as if staged)
-    const double *gx0 = nullptr, *gy0 = nullptr, *gx1 = nullptr, *gy1 = nullptr;   // 0: obstacles, 1: lanelet bounds
+    // polylines of the current search as (x, y) pairs, read through GENERIC pointers: the staged copy in shared
+    // memory or, when a polyline does not fit, the batch's interleaved arrays (L1 / L2) — one code path for both
+    const double2 *Op = nullptr, *Lp = nullptr;   // obstacle slot s at Op + rng[s]; lanelet bounds [Lp, Lp + nlan)
+    int nlan = 0;
     int n_nodes = 0, n_pops = 0, status = PDMPC_OK;
     unsigned long long hash = 0, cols = 0;
     bool exhausted = false;
     unsigned goal = 0;
-    int sadj = 0;
 
     for (;;) {
         if (phase == RUN && b.pop_limit > 0 && n_pops >= b.pop_limit) {
@@ -271,17 +280,14 @@ search_tile_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_c
                 const int q = __ldg(slot + k);
                 sm.rng[k] = __ldg(b.poly_ptr + q) + q - ob_lo;
             }
-            // layout as if everything were staged: lanelets at [0, nl), obstacle slot s at nl + rng[s]
+            // lanelet bounds first (they are tested at every pop), then the obstacle slots
             if (lst)
-                for (int j = tl; j < nl; j += TILE)
-                    sm.pts[j] = make_double2(__ldg(b.ll_x + ll_lo + j), __ldg(b.ll_y + ll_lo + j));
+                for (int j = tl; j < nl; j += TILE) sm.pts[j] = __ldg(b.ll_xy + ll_lo + j);
             if (ost)
-                for (int j = tl; j < no; j += TILE)
-                    sm.pts[(lst ? nl : 0) + j] = make_double2(__ldg(b.pl_x + ob_lo + j), __ldg(b.pl_y + ob_lo + j));
-            llo = 0; lhi = nl; obase = nl;
-            gx1 = lst ? nullptr : b.ll_x + ll_lo; gy1 = lst ? nullptr : b.ll_y + ll_lo;
-            gx0 = ost ? nullptr : b.pl_x + (ob_lo - nl); gy0 = ost ? nullptr : b.pl_y + (ob_lo - nl);
-            sadj = lst ? 0 : -nl;        // staged obstacles sit at the front when the lanelets are not staged
+                for (int j = tl; j < no; j += TILE) sm.pts[(lst ? nl : 0) + j] = __ldg(b.pl_xy + ob_lo + j);
+            Lp = lst ? sm.pts : b.ll_xy + ll_lo;
+            Op = ost ? sm.pts + (lst ? nl : 0) : b.pl_xy + ob_lo;
+            nlan = nl;
             trim0 = __ldg(b.trim0 + si);
             if (tl == 0) {   // root: GraphSearch.m:34-46
                 NodeA ra;
@@ -323,7 +329,7 @@ search_tile_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_c
         NodeA ca = {0.0, 0.0, 0.0, 0.0};
         NodeCS ccs = {0.0, 0.0}, pcs = {0.0, 0.0};
         double2 pxy = make_double2(0.0, 0.0);
-        int sbase = 0, nchild = 0, ns = 0, nbs = 0;
+        int sbase = 0, send = 0, ns = 0, nbs = 0;   // consumed after the heap walk (their loads overlap it)
         const int bkind = (cK == Hp) ? PDMPC_AREA_LARGE_OFFSET : PDMPC_AREA_WITHOUT_OFFSET;   // :166-174
         // the maneuver's area points this lane places (tables are padded by the last point: no count needed first)
         double ax0 = 0.0, ay0 = 0.0, ax1 = 0.0, ay1 = 0.0;
@@ -345,7 +351,7 @@ search_tile_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_c
             if (cK < Hp) {
                 const int q = cK * nT + (ctrim - 1);      // step k_exp = cK + 1
                 sbase = __ldg(m.succ_ptr + q);
-                nchild = __ldg(m.succ_ptr + q + 1) - sbase;
+                send = __ldg(m.succ_ptr + q + 1);
             }
             if (par != 0) {
                 pxy = *reinterpret_cast<const double2 *>(na + par);
@@ -378,13 +384,13 @@ search_tile_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_c
                     }
                 } else {
                     while (hole < lim) {
-                        double fl, fr;
                         if (2 * hole + 2 < HS) {
                             const double2 p = lds_f64x2(sf + 16u * (unsigned)hole + 16u);
-                            fl = p.x; fr = p.y;
-                        } else {
-                            fl = h_f(2 * hole + 1); fr = h_f(2 * hole + 2);
+                            hole = 2 * hole + 2 - (p.y > p.x ? 1 : 0);
+                            ++D;
+                            continue;
                         }
+                        const double fl = h_f(2 * hole + 1), fr = h_f(2 * hole + 2);
                         hole = 2 * hole + 2 - (fr > fl ? 1 : 0);
                         ++D;
                     }
@@ -421,6 +427,7 @@ search_tile_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_c
         }
 
         // ---- eval_edge_exact :141-192: place the maneuver's areas by the PARENT pose ---------------
+        const int nchild = send - sbase;
         bool valid = has;
         if (TILE >= 16) {
             if (chk && tl < 16)
@@ -452,48 +459,41 @@ search_tile_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_c
                 }
             }
         }
-        // ---- InterX item list of this pop -----------------------------------------------------------
-        int n0 = 0, n01 = 0, ntot = 0, off0 = 0, off1 = 0, off2 = 0;
+        // ---- InterX item list of this pop: item e < n0 is segment e of the static obstacles, n0 <= e < n01 a
+        //      segment of the dynamic obstacles of step cK, e >= n01 a segment of [left, NaN, right, NaN] -----------
+        int n0 = 0, n01 = 0, ntot = 0;
+        const double2 *P0 = nullptr, *P1 = nullptr, *P2 = nullptr;   // first point of item e: P[range of e] + e
         if (chk) {
-            const int st_lo = obase + sm.rng[0], st_hi = obase + sm.rng[1];
-            const int dy_lo = obase + sm.rng[cK], dy_hi = obase + sm.rng[cK + 1];
-            cols += (unsigned long long)((st_hi - st_lo) + (dy_hi - dy_lo) + (lhi - llo));
+            const int st_lo = sm.rng[0], st_hi = sm.rng[1];
+            const int dy_lo = sm.rng[cK], dy_hi = sm.rng[cK + 1];
+            cols += (unsigned long long)((st_hi - st_lo) + (dy_hi - dy_lo) + nlan);
             n0 = max(st_hi - st_lo - 1, 0);                       // InterX.m:48-52 and single-column inputs
             n01 = n0 + max(dy_hi - dy_lo - 1, 0);
-            ntot = n01 + max(lhi - llo - 1, 0);
-            off0 = st_lo; off1 = dy_lo - n0; off2 = llo - n01;
+            ntot = n01 + max(nlan - 1, 0);
+            P0 = Op + st_lo; P1 = Op + (dy_lo - n0); P2 = Lp - n01;
         }
         // widest shape of the warp: edges evaluated per item (others see their padded last vertex)
         const int ne_max = __reduce_max_sync(FULL, chk ? max(ns, nbs) - 1 : 0);
         __syncwarp();
-        {
+        // one instance of the loop per edge count (warp-uniform), so the C2 row needs no dispatch per round
+        auto interx_items = [&](auto ne_c, auto closed_c) {
+            constexpr int NE = decltype(ne_c)::value;
+            constexpr bool CLOSED = decltype(closed_c)::value;
             bool hit = false;
-            int e = tl;
-            for (;;) {
+            for (int e = tl;; e += TILE) {
                 const bool act = e < ntot;
                 if (!__any_sync(FULL, act)) break;
                 if (act) {
-                    const int sel = e >= n01 ? 1 : 0;
-                    const int j = e + (e < n0 ? off0 : (sel ? off2 : off1));
-                    double2 p0, p1;
-                    const double *gxs = sel ? gx1 : gx0;
-                    if (gxs == nullptr) {
-                        const unsigned pa = spts + 16u * (unsigned)(j + (sel ? 0 : sadj));
-                        p0 = lds_f64x2(pa);
-                        p1 = lds_f64x2(pa + 16u);
-                    } else {
-                        const double *gys = sel ? gy1 : gy0;
-                        p0 = make_double2(__ldg(gxs + j), __ldg(gys + j));
-                        p1 = make_double2(__ldg(gxs + j + 1), __ldg(gys + j + 1));
-                    }
+                    const bool lb = e >= n01;                                   // lanelet boundary item
+                    const double2 *pp = (lb ? P2 : (e < n0 ? P0 : P1)) + e;
+                    const double2 p0 = pp[0], p1 = pp[1];
                     const double dx2 = p1.x - p0.x, dy2 = p1.y - p0.y;          // InterX.m:64
                     const double S2 = dx2 * p0.y - dy2 * p0.x;                  // :68
-                    const unsigned vb = sshp + 128u * (unsigned)sel;
-                    const unsigned c2 = m.areas_closed ? interx_c2_dispatch<true>(ne_max, vb, dx2, dy2, S2)
-                                                       : interx_c2_dispatch<false>(ne_max, vb, dx2, dy2, S2);   // :71
+                    unsigned c2 = interx_c2_row<NE, CLOSED>(lb ? sshp + 128u : sshp, dx2, dy2, S2);   // :71
+                    if (NE == 4) c2 &= (1u << ne_max) - 1u;                     // ne_max < 4: the instance is wider
+                    const unsigned ebase = lb ? sec + 256u : sec;
                     for (unsigned cc = c2; cc; cc &= cc - 1u) {                 // C1 of the edges with C2, :70
-                        const int i = __ffs(cc) - 1;
-                        const unsigned eb = sec + 32u * (unsigned)(sel * 8 + i);
+                        const unsigned eb = ebase + 32u * (unsigned)(__ffs(cc) - 1);
                         const double2 d1 = lds_f64x2(eb);
                         const double S1 = lds_f64(eb + 16u);
                         const double a0 = (d1.x * p0.y - d1.y * p0.x) - S1;
@@ -503,7 +503,22 @@ search_tile_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_c
                 }
                 const unsigned hm = (__ballot_sync(FULL, hit) >> shift) & TB;
                 if (hm) { valid = false; ntot = 0; }                            // :17/:34 -> is_valid = false
-                e += TILE;
+            }
+        };
+        static_assert(kAreaStride == 8, "edge-count dispatch");
+        if (m.areas_closed) {
+            switch (ne_max) {
+            case 7: interx_items(std::integral_constant<int, 7>{}, std::true_type{}); break;
+            case 6: interx_items(std::integral_constant<int, 6>{}, std::true_type{}); break;
+            case 5: interx_items(std::integral_constant<int, 5>{}, std::true_type{}); break;
+            default: interx_items(std::integral_constant<int, 4>{}, std::true_type{}); break;
+            }
+        } else {
+            switch (ne_max) {
+            case 7: interx_items(std::integral_constant<int, 7>{}, std::false_type{}); break;
+            case 6: interx_items(std::integral_constant<int, 6>{}, std::false_type{}); break;
+            case 5: interx_items(std::integral_constant<int, 5>{}, std::false_type{}); break;
+            default: interx_items(std::integral_constant<int, 4>{}, std::false_type{}); break;
             }
         }
         __syncwarp();

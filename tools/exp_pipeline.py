@@ -13,6 +13,9 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 from pdmpc_b200 import capi  # noqa: E402
+if os.environ.get('PDMPC_LIB'):
+    capi.LIB_PATH = os.environ['PDMPC_LIB']
+    capi.load_library.__defaults__ = (capi.LIB_PATH,)
 from pdmpc_b200.mpa import get_mpa  # noqa: E402
 from pdmpc_b200.records import BatchResult, SearchBatch  # noqa: E402
 
@@ -45,7 +48,7 @@ for f in dataclasses.fields(out):
         setattr(out, f.name, pinned_like(a))
 bi, bo = capi.batch_in(hb), capi.batch_out(out)
 print(batch.n, "searches")
-for chunks in (1, 2, 3, 4, 5, 6, 8, 12):
+for chunks in [int(c) for c in os.environ.get('PDMPC_CHUNKS', '1,2,3,4,5,6,8,12').split(',')]:
     p.set_pipeline_chunks(chunks)
     ts = []
     for _ in range(5):
