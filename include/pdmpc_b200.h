@@ -221,7 +221,8 @@ int pdmpc_set_cta_queue(pdmpc_handle *h, int32_t valid_only);
 /* Shapes 2, 3 only: ESCALATION of the longest searches.  A tile warp needs ~5 us per pop, so one search of
  * 8000 pops (1 in 10^5 of the road-network records) would hold a whole launch open for 40 ms.  A search that
  * reaches `pops` pops in a tile kernel is given up there and run from scratch by the CTA shape (4, or 5 after
- * pdmpc_set_cta_queue(1)) behind the tile kernel on the same stream.  0 = never; default 2560.  A list of at
+ * pdmpc_set_cta_queue(1)) behind the tile kernel on the same stream.  0 = never; -1 (default) = by batch size:
+ * 2560 pops, 3072 from 120 000 and 4096 from 300 000 searches per call (measured optima).  A list of at
  * most `short_list_max` searches (-1 = default, 3 per SM) runs with one master warp per CTA, all checker warps
  * serving it — the launch then ends with its longest search at 0.65 us per pop —, a longer one with several
  * masters per CTA.  Results do not depend on either; pdmpc_stats.escalated counts the searches that took this

@@ -122,7 +122,7 @@ struct pdmpc_handle {
     int tile_pts_limit = 0;           // staged-points limit of the tile shapes (0 = what the kernel holds; test knob)
     int variant_mode = 0;             // 0 = auto, 1 = latency, 2 / 3 = tiles (2 / 4 searches per warp), 4 / 5 = cta
     int cta_heap_smem = kCtaHeap;     // heap entries the CTA shape keeps in shared memory (tuning/test knob)
-    int escalate_pops = PDMPC_ESCALATE_POPS;   // tile shapes give a search up after this many pops (0 = never), pdmpc_set_escalation
+    int escalate_pops = -1;           // tile shapes give a search up after this many pops (0 = never, -1 = by batch size), pdmpc_set_escalation
     int esc_short_list = -1;          // lists up to this long run with one master per CTA (-1: 3 per SM)
     DBuf esc;                         // [0] count, [1] producers done, [4..] escalated search indices
     DBuf esc_rows;                    // pipeline: packed output rows of the escalated searches
@@ -848,9 +848,16 @@ static int launch_warp_shape(pdmpc_handle *h, int shape, const BatchDev &bc, con
 // give a search up after `escalate_pops` pops and append its index to a list; two gated instances of the CTA
 // kernel (one master per CTA for a short list, several masters for a long one) launched behind the tile kernel
 // on the same stream run the list from scratch at 0.65-1.0 us per pop.  Results are those of any other shape.
+// The threshold for a launch over n searches.  Measured after the tile kernel's InterX loop was rewritten
+// (profiles/r02j_escalation_threshold.txt): the larger the batch, the smaller the launch's tail is against its
+// body and the later giving up pays — 2560 pops is best at 56 k searches, 2560-3072 at 168 k, 4096 at 358 k.
+static int escalation_pops(const pdmpc_handle *h, int n) {
+    if (h->escalate_pops >= 0) return h->escalate_pops;
+    return n >= 300000 ? 4096 : n >= 120000 ? 3072 : PDMPC_ESCALATE_POPS;
+}
 static bool escalation_on(const pdmpc_handle *h, int shape, int n) {
     const int cap = h->user_node_cap ? h->user_node_cap : std::min(h->full_tree_nodes + 8, 1 << 20);
-    return (shape == 2 || shape == 3) && h->escalate_pops > 0 && h->cta_ok && cap <= kCtaFlags &&
+    return (shape == 2 || shape == 3) && escalation_pops(h, n) > 0 && h->cta_ok && cap <= kCtaFlags &&
            n > h->num_sms && h->batch.checker == PDMPC_CHECKER_INTERX;
 }
 
@@ -860,7 +867,7 @@ static int escalation_prepare(pdmpc_handle *h, int n, BatchDev *bt, cudaStream_t
     CU_TRY(h, h->esc.reserve(((size_t)n + 4) * sizeof(int)));
     CU_TRY(h, cudaMemsetAsync(h->esc.p, 0, 4 * sizeof(int), S));
     CU_TRY(h, cudaMemsetAsync(h->esc.as<int>() + 4, 0xff, (size_t)n * sizeof(int), S));
-    bt->pop_limit = h->escalate_pops;
+    bt->pop_limit = escalation_pops(h, n);
     bt->esc_count = h->esc.as<unsigned>();
     bt->esc_done = h->esc.as<unsigned>() + 1;
     bt->esc_list = h->esc.as<int>() + 4;
@@ -1093,7 +1100,7 @@ __global__ void pack_plan_rows_kernel(OutDev o, int Hp, int n_rows, int n_veh, c
 
 int pdmpc_set_escalation(pdmpc_handle *h, int32_t pops, int32_t short_list_max) {
     if (!h) return PDMPC_ERR_BAD_INPUT;
-    if (pops < 0) return fail(h, PDMPC_ERR_BAD_INPUT, "escalation threshold must be 0 (off) or a pop count");
+    if (pops < -1) return fail(h, PDMPC_ERR_BAD_INPUT, "escalation threshold must be -1 (by batch size), 0 (off) or a pop count");
     h->escalate_pops = pops;
     h->esc_short_list = short_list_max;
     return PDMPC_OK;
@@ -1174,7 +1181,7 @@ static int plan_batch_pipelined(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc
     // so it is a fraction of the others' size (pdmpc_first_chunk, experiment knob PDMPC_FIRST_CHUNK).
     static const double first_frac = [] {
         const char *e = getenv("PDMPC_FIRST_CHUNK");
-        const double f = e ? atof(e) : 0.25;
+        const double f = e ? atof(e) : 0.5;
         return f > 0.0 && f <= 1.0 ? f : 1.0;
     }();
     auto bound = [&](int c) -> int {

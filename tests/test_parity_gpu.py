@@ -418,6 +418,6 @@ def test_escalation_of_long_searches(planner, variant, valid_only):
         planner.set_variant(0)
         planner.set_pipeline_chunks(0)
         planner.set_cta_queue(False)
-        planner.set_escalation(2560)
+        planner.set_escalation(-1)           # back to the default: by batch size
     with pytest.raises(capi.PdmpcError):
-        planner.set_escalation(-1)
+        planner.set_escalation(-2)

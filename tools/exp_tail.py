@@ -44,12 +44,14 @@ def main():
     print(f"all {b.n}: shape {sh} {t_all:.2f} ms -> {b.n / t_all / 1e3:.3f} M plans/s; max pops {pops.max()}")
     for vo in (True,):
         p.set_cta_queue(vo)
-        for esc in (0, 2560):
-            p.set_escalation(esc)
-            t, sh = timed(p, b, int(os.environ.get("PDMPC_SHAPE", "2")))
-            p.fetch()
-            st = p.stats()
-            print(f"valid-only {vo} escalation {esc}: {t:.2f} ms -> {b.n / t / 1e3:.3f} M plans/s (escalated {st.escalated}, launches {st.kernel_launches})")
+        for esc in [int(v) for v in os.environ.get("PDMPC_ESC_SWEEP", "0,2560").split(",")]:
+            for gate in [int(v) for v in os.environ.get("PDMPC_ESC_GATES", "-1").split(",")]:
+                p.set_escalation(esc, gate)
+                t, sh = timed(p, b, int(os.environ.get("PDMPC_SHAPE", "2")))
+                p.fetch()
+                st = p.stats()
+                print(f"valid-only {vo} escalation {esc} short-list gate {gate}: {t:.2f} ms -> {b.n / t / 1e3:.3f} M plans/s "
+                      f"(escalated {st.escalated}, launches {st.kernel_launches})")
     p.set_cta_queue(False)
     p.set_escalation(0)
     for thr in ():
