@@ -394,6 +394,48 @@ int pdmpc_upload_road(pdmpc_handle *h, const pdmpc_road_desc *road);
 int pdmpc_sample_inputs(pdmpc_handle *h, int32_t n, const int32_t *path_id, const double *x, const double *y,
                         const double *speed, double dt_seconds, pdmpc_inputs_out *out);
 
+/* ---- Obstacle assembly of a time step on the device (the part that does not depend on this
+ *      time step's plans): what PrioritizedController.plan puts into iter_v.obstacles / iter_v.dynamic_obstacle_area
+ *      before the optimizer runs, for all vehicles (of all scenarios) in one call:
+ *        - a coupled vehicle of LOWER priority that stands (|speed| < 0.01) is a static obstacle, its area the offset
+ *          rectangle at its pose (consider_successors with ConstraintFromSuccessor.area_of_standstill,
+ *          hlc/controller/prioritized/PrioritizedController.m:508-540; get_occupied_areas.m:19-25);
+ *        - a coupled vehicle of HIGHER priority that plans in PARALLEL enters through its reachable sets, one dynamic
+ *          obstacle per step (parallel_coupling_reachability :391-407 via consider_predecessors :449-506): the local
+ *          reachable sets of its current trim placed at its pose (MotionPrimitiveAutomaton.reachable_sets_at_pose,
+ *          hlc/model/motion_primitive_automaton/MotionPrimitiveAutomaton.m:649-687, utility/translate_global.m:20-23).
+ *      (The areas of SEQUENTIAL predecessors are handed over inside pdmpc_plan_timestep.)  The reference also clips a
+ *      reachable set by the predicted lanelets' polyshape (HighLevelController.m:241-246, a MATLAB polyshape
+ *      intersection): not done here, the caller uploads the sets it wants placed. ---- */
+typedef struct pdmpc_reach_desc {    /* mpa.local_reachable_sets_conv{trim, t} as closed polygons (first point repeated) */
+    int32_t n_trims, Hp;             /* must equal the uploaded MPA's */
+    const int32_t *ptr;              /* [n_trims*Hp+1] into x / y: set of (trim i, step t) (0-based) at ptr[i*Hp+t] */
+    const double *x, *y;
+} pdmpc_reach_desc;
+int pdmpc_upload_reachable_sets(pdmpc_handle *h, const pdmpc_reach_desc *sets);
+
+typedef struct pdmpc_coupling_in {
+    int32_t n;                       /* rows: the vehicles of every scenario of the time step */
+    const double *x, *y, *yaw;       /* [n] measured pose (iter.x0(:, 1:3)) */
+    const double *speed;             /* [n] iter.x0(:, 4) */
+    const int32_t *trim;             /* [n] iter.trim_indices, 1-based */
+    const int32_t *succ_ptr;         /* [n+1] CSR: coupled rows of lower priority (directed_coupling(i, :)) */
+    const int32_t *succ_idx;
+    const int32_t *par_ptr;          /* [n+1] CSR: coupled rows of higher priority in another group (they plan in parallel) */
+    const int32_t *par_idx;
+    double half_length, half_width;  /* Length/2 + offset, Width/2 + offset (get_occupied_areas.m:21-22) */
+} pdmpc_coupling_in;
+
+typedef struct pdmpc_obstacles_out { /* caller-owned host buffers in the layout of pdmpc_batch_in's obstacle CSR */
+    int32_t *slot_ptr;               /* [n*(Hp+1)+1]: slot i*(Hp+1) = standing successors of row i (in succ order), slot
+                                      *   i*(Hp+1)+k = step-k reachable set of every parallel predecessor (in par order) */
+    int32_t *poly_ptr;               /* [poly_capacity+1] */
+    double *vert_x, *vert_y;         /* [vert_capacity] */
+    int32_t poly_capacity, vert_capacity;   /* PDMPC_ERR_CAPACITY if the time step needs more (n_polys / n_verts say how much) */
+    int32_t n_polys, n_verts;        /* out: polygons and vertices written */
+} pdmpc_obstacles_out;
+int pdmpc_assemble_obstacles(pdmpc_handle *h, const pdmpc_coupling_in *in, pdmpc_obstacles_out *out);
+
 /* ---- The output side of a time step on the device: the plan a vehicle falls back to when
  *      its search is exhausted — standstill at its pose (handle_graph_search_exhaustion,
  *      PrioritizedController.m:568-621, area = get_occupied_areas.m:21-25) or the previous plan shifted by one step

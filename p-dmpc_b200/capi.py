@@ -30,7 +30,7 @@ PDMPC_ERR_ALLOC = 5
 
 EXPORTED_SYMBOLS = (
     "pdmpc_create", "pdmpc_destroy", "pdmpc_last_error", "pdmpc_abi_version",
-    "pdmpc_set_node_capacity", "pdmpc_set_variant", "pdmpc_set_tile_points", "pdmpc_set_cta_queue", "pdmpc_set_escalation", "pdmpc_get_hp", "pdmpc_pack_plan_rows", "pdmpc_upload_road", "pdmpc_sample_inputs", "pdmpc_closed_loop_reset", "pdmpc_plan_timestep_closed_loop", "pdmpc_host_alloc", "pdmpc_host_free",
+    "pdmpc_set_node_capacity", "pdmpc_set_variant", "pdmpc_set_tile_points", "pdmpc_set_cta_queue", "pdmpc_set_escalation", "pdmpc_get_hp", "pdmpc_pack_plan_rows", "pdmpc_upload_road", "pdmpc_sample_inputs", "pdmpc_upload_reachable_sets", "pdmpc_assemble_obstacles", "pdmpc_closed_loop_reset", "pdmpc_plan_timestep_closed_loop", "pdmpc_host_alloc", "pdmpc_host_free",
     "pdmpc_trace_staged", "pdmpc_upload_mpa", "pdmpc_plan_batch", "pdmpc_stage_batch",
     "pdmpc_run_staged", "pdmpc_sync", "pdmpc_fetch_staged", "pdmpc_get_stats", "pdmpc_stream",
     "pdmpc_mcts_plan_batch", "pdmpc_mcts_run_staged", "pdmpc_set_cta_heap_smem", "pdmpc_plan_timestep",
@@ -90,6 +90,21 @@ class InputsOutC(C.Structure):
     _fields_ = [("ref_x", _p_f64), ("ref_y", _p_f64), ("v_ref", _p_f64), ("ref_index", _p_i32), ("current_index", _p_i32),
                 ("predicted_lanelets", _p_i32), ("lane_ptr", _p_i32), ("lane_x", _p_f64), ("lane_y", _p_f64),
                 ("lane_capacity", C.c_int32)]
+
+
+class ReachDescC(C.Structure):
+    _fields_ = [("n_trims", C.c_int32), ("Hp", C.c_int32), ("ptr", _p_i32), ("x", _p_f64), ("y", _p_f64)]
+
+
+class CouplingInC(C.Structure):
+    _fields_ = [("n", C.c_int32), ("x", _p_f64), ("y", _p_f64), ("yaw", _p_f64), ("speed", _p_f64), ("trim", _p_i32),
+                ("succ_ptr", _p_i32), ("succ_idx", _p_i32), ("par_ptr", _p_i32), ("par_idx", _p_i32),
+                ("half_length", C.c_double), ("half_width", C.c_double)]
+
+
+class ObstaclesOutC(C.Structure):
+    _fields_ = [("slot_ptr", _p_i32), ("poly_ptr", _p_i32), ("vert_x", _p_f64), ("vert_y", _p_f64),
+                ("poly_capacity", C.c_int32), ("vert_capacity", C.c_int32), ("n_polys", C.c_int32), ("n_verts", C.c_int32)]
 
 
 MAX_PRED_LANELETS = 8
@@ -203,6 +218,10 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.pdmpc_upload_road.restype = C.c_int
     lib.pdmpc_sample_inputs.argtypes = [H, C.c_int32, _p_i32, _p_f64, _p_f64, _p_f64, C.c_double, C.POINTER(InputsOutC)]
     lib.pdmpc_sample_inputs.restype = C.c_int
+    lib.pdmpc_upload_reachable_sets.argtypes = [H, C.POINTER(ReachDescC)]
+    lib.pdmpc_upload_reachable_sets.restype = C.c_int
+    lib.pdmpc_assemble_obstacles.argtypes = [H, C.POINTER(CouplingInC), C.POINTER(ObstaclesOutC)]
+    lib.pdmpc_assemble_obstacles.restype = C.c_int
     lib.pdmpc_closed_loop_reset.argtypes = [H, C.c_int32, C.c_double, C.c_double]
     lib.pdmpc_closed_loop_reset.restype = C.c_int
     lib.pdmpc_plan_timestep_closed_loop.argtypes = [H, C.POINTER(BatchIn), C.POINTER(TimestepDepsC), _p_i32,
@@ -347,6 +366,55 @@ class Planner:
                                                  _ptr(speed, _p_f64), float(dt_seconds), C.byref(oc)))
         tot = int(o["lane_ptr"][-1])
         o["lane_x"], o["lane_y"] = o["lane_x"][:tot], o["lane_y"][:tot]
+        return o
+
+    def upload_reachable_sets(self, sets):
+        """mpa.local_reachable_sets_conv as sets[trim][step] = closed (2, m) polygon (scenario.local_reachable_sets_conv)
+        for pdmpc_assemble_obstacles (pdmpc_upload_reachable_sets)."""
+        nT, Hp = len(sets), len(sets[0])
+        ptr = np.zeros(nT * Hp + 1, dtype=np.int32)
+        xs, ys = [], []
+        for i in range(nT):
+            for t in range(Hp):
+                a = np.asarray(sets[i][t], dtype=np.float64)
+                ptr[i * Hp + t + 1] = ptr[i * Hp + t] + a.shape[1]
+                xs.append(a[0]); ys.append(a[1])
+        x, y = np.ascontiguousarray(np.concatenate(xs)), np.ascontiguousarray(np.concatenate(ys))
+        d = ReachDescC(n_trims=nT, Hp=Hp, ptr=_ptr(ptr, _p_i32), x=_ptr(x, _p_f64), y=_ptr(y, _p_f64))
+        self._check(self.lib.pdmpc_upload_reachable_sets(self.h, C.byref(d)))
+
+    def assemble_obstacles(self, x, y, yaw, speed, trim, successors, parallel, half_length: float, half_width: float,
+                           poly_capacity: int = 0, vert_capacity: int = 0) -> dict:
+        """Static obstacles (standing successors) and dynamic obstacles (reachable sets of parallel predecessors) of every
+        row as the obstacle CSR of a SearchBatch (pdmpc_assemble_obstacles): slot_ptr [n(Hp+1)+1], poly_ptr, vert_x,
+        vert_y.  successors / parallel: per row a sequence of row indices."""
+        x, y, yaw, speed = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, yaw, speed))
+        trim = np.ascontiguousarray(trim, dtype=np.int32)
+        n, Hp = int(x.size), int(self.lib.pdmpc_get_hp(self.h))
+
+        def csr(rows):
+            ptr = np.zeros(n + 1, dtype=np.int32)
+            for i in range(n):
+                ptr[i + 1] = ptr[i] + len(rows[i])
+            idx = np.ascontiguousarray(np.concatenate([np.asarray(r, dtype=np.int32) for r in rows] + [np.zeros(0, np.int32)]),
+                                       dtype=np.int32)
+            return ptr, idx
+
+        sp, si = csr(successors)
+        pp, pi = csr(parallel)
+        pc = int(poly_capacity) or max(1, si.size + Hp * pi.size)
+        vc = int(vert_capacity) or max(1, 5 * si.size + 256 * Hp * pi.size)
+        o = {"slot_ptr": np.zeros(n * (Hp + 1) + 1, dtype=np.int32), "poly_ptr": np.zeros(pc + 1, dtype=np.int32),
+             "vert_x": np.zeros(vc), "vert_y": np.zeros(vc)}
+        ci = CouplingInC(n=n, x=_ptr(x, _p_f64), y=_ptr(y, _p_f64), yaw=_ptr(yaw, _p_f64), speed=_ptr(speed, _p_f64),
+                         trim=_ptr(trim, _p_i32), succ_ptr=_ptr(sp, _p_i32), succ_idx=_ptr(si, _p_i32),
+                         par_ptr=_ptr(pp, _p_i32), par_idx=_ptr(pi, _p_i32),
+                         half_length=float(half_length), half_width=float(half_width))
+        oc = ObstaclesOutC(slot_ptr=_ptr(o["slot_ptr"], _p_i32), poly_ptr=_ptr(o["poly_ptr"], _p_i32),
+                           vert_x=_ptr(o["vert_x"], _p_f64), vert_y=_ptr(o["vert_y"], _p_f64), poly_capacity=pc, vert_capacity=vc)
+        self._check(self.lib.pdmpc_assemble_obstacles(self.h, C.byref(ci), C.byref(oc)))
+        o["poly_ptr"] = o["poly_ptr"][: oc.n_polys + 1]
+        o["vert_x"], o["vert_y"] = o["vert_x"][: oc.n_verts], o["vert_y"][: oc.n_verts]
         return o
 
     def set_escalation(self, pops: int, short_list_max: int = -1):

@@ -36,6 +36,15 @@
 //       reference trajectories and lanelet boundaries of ALL vehicles of a time step in one call
 //       (sample_inputs_cuda.m): get_reference_trajectory / sample_reference_trajectory / get_predicted_lanelets /
 //       get_lanelets_boundary of hlc/controller/common, as HighLevelController fills them into iter.
+//       mex(UPLOAD_REACHABLE_SETS, h, local_reachable_sets {nT x Hp} (2 x m closed polygons: the Vertices of
+//           mpa.local_reachable_sets_conv{trim, t} with the first vertex repeated))
+//   [obstacles {N x 1} of {s_i x 1} (2 x 5), dynamic_obstacle_area {N x 1} of {p_i x Hp} (2 x m)] =
+//       mex(ASSEMBLE_OBSTACLES, h, x0 [N x 4] (x, y, yaw, speed), trims [N], successors {N x 1} (1-based indices),
+//           parallel_predecessors {N x 1}, half_length, half_width)
+//       the obstacles of ALL vehicles of a time step that do not depend on this time step's plans
+//       (assemble_obstacles_cuda.m): standing successors' occupied areas (PrioritizedController.m:508-540,
+//       get_occupied_areas.m:19-25) and parallel predecessors' reachable sets (:391-407,
+//       MotionPrimitiveAutomaton.m:649-687).
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -47,7 +56,7 @@
 namespace {
 
 enum Command { CREATE = 0, DESTROY = 1, UPLOAD_MPA = 2, PLAN = 3, STATS = 4, PLAN_SAMPLED = 5, PLAN_TIMESTEP = 6, PLAN_JOINT = 7, UPLOAD_ROAD = 8,
-               SAMPLE_INPUTS = 9 };
+               SAMPLE_INPUTS = 9, UPLOAD_REACHABLE_SETS = 10, ASSEMBLE_OBSTACLES = 11 };
 
 std::vector<pdmpc_handle *> g_handles;   // released at `clear mex` (HighLevelController.m:284-303)
 bool g_at_exit_registered = false;
@@ -521,6 +530,90 @@ void sample_inputs(pdmpc_handle *h, int nlhs, mxArray *plhs[], const mxArray *pr
     }
 }
 
+// UPLOAD_REACHABLE_SETS: mpa.local_reachable_sets_conv as closed 2 x m polygons -> pdmpc_upload_reachable_sets
+void upload_reachable_sets(pdmpc_handle *h, const mxArray *prhs[]) {
+    const mxArray *sets = prhs[2];
+    if (!mxIsCell(sets)) fail("pdmpc:input", "local_reachable_sets must be an nT x Hp cell");
+    const size_t nT = mxGetM(sets), Hp = mxGetN(sets);
+    std::vector<int32_t> ptr(1, 0);
+    std::vector<double> x, y;
+    for (size_t i = 0; i < nT; ++i)
+        for (size_t t = 0; t < Hp; ++t) {
+            const mxArray *p = mxGetCell(sets, i + nT * t);
+            if (!p || mxGetM(p) != 2) fail("pdmpc:input", "a reachable set must be a 2 x m polygon");
+            const double *d = mxGetDoubles(p);
+            for (size_t j = 0; j < mxGetN(p); ++j) {
+                x.push_back(d[2 * j]);
+                y.push_back(d[2 * j + 1]);
+            }
+            ptr.push_back(static_cast<int32_t>(x.size()));
+        }
+    pdmpc_reach_desc r;
+    r.n_trims = static_cast<int32_t>(nT); r.Hp = static_cast<int32_t>(Hp);
+    r.ptr = ptr.data(); r.x = x.data(); r.y = y.data();
+    check(h, pdmpc_upload_reachable_sets(h, &r), "pdmpc_upload_reachable_sets");
+}
+
+// ASSEMBLE_OBSTACLES: standing successors' areas + parallel predecessors' reachable sets -> pdmpc_assemble_obstacles
+void assemble_obstacles(pdmpc_handle *h, int nlhs, mxArray *plhs[], const mxArray *prhs[]) {
+    const size_t N = mxGetM(prhs[2]);
+    if (mxGetN(prhs[2]) < 4 || mxGetNumberOfElements(prhs[3]) != N || !mxIsCell(prhs[4]) || !mxIsCell(prhs[5]) ||
+        mxGetNumberOfElements(prhs[4]) != N || mxGetNumberOfElements(prhs[5]) != N)
+        fail("pdmpc:input", "ASSEMBLE_OBSTACLES: x0 [N x 4], trims [N], successors {N x 1}, parallel_predecessors {N x 1}");
+    const int Hp = pdmpc_get_hp(h);
+    const double *x0 = mxGetDoubles(prhs[2]);
+    std::vector<int32_t> trim(N), sp(1, 0), si, pp(1, 0), pi;
+    for (size_t i = 0; i < N; ++i) trim[i] = static_cast<int32_t>(mxGetDoubles(prhs[3])[i]);
+    auto csr = [&](const mxArray *cells, std::vector<int32_t> &ptr, std::vector<int32_t> &idx) {
+        for (size_t i = 0; i < N; ++i) {
+            const mxArray *c = mxGetCell(cells, i);
+            const size_t m = c ? mxGetNumberOfElements(c) : 0;
+            for (size_t j = 0; j < m; ++j) idx.push_back(static_cast<int32_t>(mxGetDoubles(c)[j]) - 1);
+            ptr.push_back(static_cast<int32_t>(idx.size()));
+        }
+    };
+    csr(prhs[4], sp, si);
+    csr(prhs[5], pp, pi);
+    pdmpc_coupling_in in;
+    std::memset(&in, 0, sizeof(in));
+    in.n = static_cast<int32_t>(N);
+    in.x = x0; in.y = x0 + N; in.yaw = x0 + 2 * N; in.speed = x0 + 3 * N;      // column-major N x 4
+    in.trim = trim.data();
+    in.succ_ptr = sp.data(); in.succ_idx = si.data(); in.par_ptr = pp.data(); in.par_idx = pi.data();
+    in.half_length = mxGetScalar(prhs[6]); in.half_width = mxGetScalar(prhs[7]);
+    std::vector<int32_t> slot(N * (Hp + 1) + 1), poly(si.size() + static_cast<size_t>(Hp) * pi.size() + 1);
+    std::vector<double> vx(5 * si.size() + 256 * static_cast<size_t>(Hp) * pi.size() + 1), vy(vx.size());
+    pdmpc_obstacles_out out;
+    std::memset(&out, 0, sizeof(out));
+    out.slot_ptr = slot.data(); out.poly_ptr = poly.data(); out.vert_x = vx.data(); out.vert_y = vy.data();
+    out.poly_capacity = static_cast<int32_t>(poly.size() - 1); out.vert_capacity = static_cast<int32_t>(vx.size() - 1);
+    check(h, pdmpc_assemble_obstacles(h, &in, &out), "pdmpc_assemble_obstacles");
+    auto polygon = [&](int p) {
+        const int a = poly[p], b = poly[p + 1];
+        mxArray *m = mxCreateDoubleMatrix(2, b - a, mxREAL);
+        for (int j = a; j < b; ++j) {
+            mxGetDoubles(m)[2 * (j - a)] = vx[j];
+            mxGetDoubles(m)[2 * (j - a) + 1] = vy[j];
+        }
+        return m;
+    };
+    plhs[0] = mxCreateCellMatrix(N, 1);
+    if (nlhs > 1) plhs[1] = mxCreateCellMatrix(N, 1);
+    for (size_t i = 0; i < N; ++i) {
+        const int32_t *s = slot.data() + i * (Hp + 1);
+        mxArray *st = mxCreateCellMatrix(s[1] - s[0], 1);                   // iter.obstacles rows
+        for (int p = s[0]; p < s[1]; ++p) mxSetCell(st, p - s[0], polygon(p));
+        mxSetCell(plhs[0], i, st);
+        if (nlhs > 1) {
+            const int rows = s[2] - s[1];                                   // one row per parallel predecessor
+            mxArray *dy = mxCreateCellMatrix(rows, Hp);                     // iter.dynamic_obstacle_area rows
+            for (int k = 1; k <= Hp; ++k)
+                for (int q = 0; q < rows; ++q) mxSetCell(dy, q + static_cast<size_t>(rows) * (k - 1), polygon(s[k] + q));
+            mxSetCell(plhs[1], i, dy);
+        }
+    }
+}
+
 }  // namespace
 
 void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
@@ -583,6 +676,14 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
     case SAMPLE_INPUTS:
         if (nrhs < 7) fail("pdmpc:usage", "SAMPLE_INPUTS needs 7 arguments");
         sample_inputs(h, nlhs, plhs, prhs);
+        return;
+    case UPLOAD_REACHABLE_SETS:
+        if (nrhs < 3) fail("pdmpc:usage", "UPLOAD_REACHABLE_SETS needs 3 arguments");
+        upload_reachable_sets(h, prhs);
+        return;
+    case ASSEMBLE_OBSTACLES:
+        if (nrhs < 8) fail("pdmpc:usage", "ASSEMBLE_OBSTACLES needs 8 arguments");
+        assemble_obstacles(h, nlhs, plhs, prhs);
         return;
     case STATS: {
         pdmpc_stats st;

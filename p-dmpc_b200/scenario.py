@@ -595,8 +595,41 @@ def local_reachable_sets_conv(mpa: MotionPrimitiveAutomaton) -> List[List[np.nda
 
 def reachable_sets_at(mpa: MotionPrimitiveAutomaton, x: float, y: float, yaw: float, trim: int) -> List[np.ndarray]:
     """get_reachable_sets (MotionPrimitiveAutomaton.m:649-687): the local sets of the current trim placed at the pose."""
-    c, s_ = np.cos(yaw), np.sin(yaw)
+    s_, c = sincos_spec(yaw)   # the arithmetic specification (DESIGN.md §2): the device places them with the same bits
     return [np.vstack([c * a[0] - s_ * a[1] + x, s_ * a[0] + c * a[1] + y]) for a in local_reachable_sets_conv(mpa)[trim - 1]]
+
+
+def assemble_obstacles_host(mpa: MotionPrimitiveAutomaton, x, y, yaw, speed, trim, successors, parallel,
+                            half_length: float, half_width: float) -> dict:
+    """Host restatement of pdmpc_assemble_obstacles (same arguments and result as capi.Planner.assemble_obstacles):
+    slot i*(Hp+1) = the offset rectangles of row i's standing successors (PrioritizedController.m:508-540,
+    get_occupied_areas.m:19-25), slot i*(Hp+1)+k = the step-k reachable set of each parallel predecessor
+    (:391-407, MotionPrimitiveAutomaton.m:649-687), as the obstacle CSR of a SearchBatch."""
+    n, Hp = len(x), mpa.Hp
+    xl = np.array([-1.0, -1.0, 1.0, 1.0, -1.0]) * half_length
+    yl = np.array([-1.0, 1.0, 1.0, -1.0, -1.0]) * half_width
+    slot_ptr, poly_ptr, vx, vy = [0], [0], [], []
+
+    def put(px, py):
+        vx.append(px); vy.append(py)
+        poly_ptr.append(poly_ptr[-1] + len(px))
+
+    for i in range(n):
+        cnt = 0
+        for j in successors[i]:
+            if abs(speed[j]) < 0.01:
+                s_, c = sincos_spec(yaw[j])
+                put(c * xl - s_ * yl + x[j], s_ * xl + c * yl + y[j])
+                cnt += 1
+        slot_ptr.append(slot_ptr[-1] + cnt)
+        sets = [reachable_sets_at(mpa, x[j], y[j], yaw[j], int(trim[j])) for j in parallel[i]]
+        for k in range(Hp):
+            for rs in sets:
+                put(rs[k][0], rs[k][1])
+            slot_ptr.append(slot_ptr[-1] + len(sets))
+    cat = lambda parts: np.ascontiguousarray(np.concatenate(parts)) if parts else np.zeros(0)
+    return {"slot_ptr": np.array(slot_ptr, dtype=np.int32), "poly_ptr": np.array(poly_ptr, dtype=np.int32),
+            "vert_x": cat(vx), "vert_y": cat(vy)}
 
 
 def limit_computation_levels(D: np.ndarray, max_num_CLs: int) -> np.ndarray:
@@ -637,7 +670,7 @@ class ScenarioRunner:
     PrioritizedSequentialController.m:83-92)."""
 
     def __init__(self, sc: Scenario, plan_fn: PlanFn, max_num_CLs: int = 99, timestep_fn=None, inputs_fn=None,
-                 path_id0: int = 0, closed_loop_fn=None):
+                 path_id0: int = 0, closed_loop_fn=None, obstacles_fn=None):
         """plan_fn(batch) plans one computation level; with timestep_fn(batch, deps) the whole time
         step is ONE call and the predecessors' areas are handed over behind it (pdmpc_plan_timestep).
         inputs_fn(path_id, x, y, speed, dt) -> dict (capi.Planner.sample_inputs): reference trajectories and lanelet
@@ -648,6 +681,10 @@ class ScenarioRunner:
         self.timestep_fn = timestep_fn
         self.inputs_fn = inputs_fn
         self.path_id0 = path_id0
+        # obstacles_fn(x, y, yaw, speed, trim, successors, parallel, half_length, half_width) -> obstacle CSR dict
+        # (capi.Planner.assemble_obstacles): the standstill areas of successors and the reachable sets of parallel
+        # predecessors of all vehicles are placed on the device in one call per time step (one-call path)
+        self.obstacles_fn = obstacles_fn
         # closed_loop_fn(batch, deps, slot, standstill) -> BatchResult with the FINAL plan of every vehicle
         # (capi.Planner.plan_timestep_closed_loop): fallback plans are built and kept on the device, slot = path_id0 + i
         self.closed_loop_fn = closed_loop_fn
@@ -717,15 +754,32 @@ class ScenarioRunner:
         iters = self._iters()
         A = couple(sc, self.pose)
         D = constant_priorities(A) if sc.priority == "constant" else coloring_priorities(A)
-        for i in range(n):   # consider_successors, area_of_standstill: PrioritizedController.m:508-540
-            for j in np.flatnonzero(D[i, :]):
-                if abs(mpa.trim_speed[self.trim[j] - 1]) < 0.01:
-                    iters[i].obstacles.append(occupied_area(*self.pose[j]))
-        D = D.astype(bool)
-        seq = limit_computation_levels(D, self.max_num_CLs) if self.max_num_CLs < n else D
-        for i in range(n):   # parallel predecessors: reachable sets as dynamic obstacles, PrioritizedController.m:399-415,493-501
-            for j in np.flatnonzero(D[:, i] & ~seq[:, i]):
-                iters[i].dynamic_obstacle_area.append(reachable_sets_at(mpa, *self.pose[j], int(self.trim[j])))
+        Db = D.astype(bool)
+        seq = limit_computation_levels(Db, self.max_num_CLs) if self.max_num_CLs < n else Db
+        if self.obstacles_fn is not None:
+            # the same two rules on the device (pdmpc_assemble_obstacles), all vehicles in one call
+            speed = np.array([mpa.trim_speed[self.trim[j] - 1] for j in range(n)], dtype=np.float64)
+            o = self.obstacles_fn(self.pose[:, 0], self.pose[:, 1], self.pose[:, 2], speed, self.trim,
+                                  [np.flatnonzero(D[i, :]) for i in range(n)],
+                                  [np.flatnonzero(Db[:, i] & ~seq[:, i]) for i in range(n)],
+                                  VEH_LENGTH / 2 + 0.01, VEH_WIDTH / 2 + 0.01)
+            sp, pp = o["slot_ptr"], o["poly_ptr"]
+            poly = lambda p: np.ascontiguousarray(np.vstack([o["vert_x"][pp[p]:pp[p + 1]], o["vert_y"][pp[p]:pp[p + 1]]]))
+            Hp = mpa.Hp
+            for i in range(n):
+                s0 = i * (Hp + 1)
+                iters[i].obstacles.extend(poly(p) for p in range(sp[s0], sp[s0 + 1]))
+                for q in range(sp[s0 + 2] - sp[s0 + 1]):     # one row per parallel predecessor, a column per step
+                    iters[i].dynamic_obstacle_area.append([poly(sp[s0 + k] + q) for k in range(1, Hp + 1)])
+        else:
+            for i in range(n):   # consider_successors, area_of_standstill: PrioritizedController.m:508-540
+                for j in np.flatnonzero(D[i, :]):
+                    if abs(mpa.trim_speed[self.trim[j] - 1]) < 0.01:
+                        iters[i].obstacles.append(occupied_area(*self.pose[j]))
+            for i in range(n):   # parallel predecessors: reachable sets as dynamic obstacles, PrioritizedController.m:399-415,493-501
+                for j in np.flatnonzero(Db[:, i] & ~seq[:, i]):
+                    iters[i].dynamic_obstacle_area.append(reachable_sets_at(mpa, *self.pose[j], int(self.trim[j])))
+        D = Db
         preds = [np.flatnonzero(seq[:, i]) for i in range(n)]
         fallbacks = [self._fallback_plan(i) for i in range(n)]
         return iters, preds, fallbacks

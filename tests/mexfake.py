@@ -15,7 +15,8 @@ LIB = os.path.join(STUB, "libpdmpc_mex_fake.so")
 SRC = [os.path.join(ROOT, "p-dmpc_b200", "matlab", "pdmpc_b200_mex.cpp"), os.path.join(STUB, "fake_matlab.cpp")]
 CSRC = os.path.join(ROOT, "p-dmpc_b200", "csrc")
 
-CREATE, DESTROY, UPLOAD_MPA, PLAN, STATS, PLAN_SAMPLED, PLAN_TIMESTEP, PLAN_JOINT, UPLOAD_ROAD, SAMPLE_INPUTS = range(10)
+(CREATE, DESTROY, UPLOAD_MPA, PLAN, STATS, PLAN_SAMPLED, PLAN_TIMESTEP, PLAN_JOINT, UPLOAD_ROAD, SAMPLE_INPUTS,
+ UPLOAD_REACHABLE_SETS, ASSEMBLE_OBSTACLES) = range(12)
 _CELL, _STRUCT, _LOGICAL, _DOUBLE, _UINT64 = 1, 2, 3, 6, 13
 
 

@@ -288,3 +288,30 @@ def test_lockstep_scenarios_equal_individual_closed_loops():
         assert res.status.size == 30
     for a, b in zip(alone, together):
         assert np.array_equal(a.pose, b.pose) and np.array_equal(a.trim, b.trim) and a.n_fallbacks == b.n_fallbacks
+
+
+def test_obstacle_assembly_hook_equals_the_inline_host_rules():
+    """ScenarioRunner(obstacles_fn = ...) — the one-call path with the obstacle assembly behind one function (on the GPU
+    box: pdmpc_assemble_obstacles) builds the same iter_v obstacles as the inline host rules: here with the host
+    restatement of the kernel (scenario.assemble_obstacles_host), 40 vehicles, computation levels limited to 1."""
+    import numpy as np
+    from pdmpc_b200 import scenario
+    from pdmpc_b200.mpa import get_mpa
+    from pdmpc_b200.records import SearchBatch
+    mpa = get_mpa("triple_speed", non_convex=True)
+    sc = scenario.commonroad_scenario(mpa, 40, seed=2, allow_shared_paths=True)
+    runner = scenario.ScenarioRunner(sc, None, max_num_CLs=1)
+    # a few vehicles drive, the others stand, so both rules fire
+    drive = mpa.trim_from_values(mpa.get_straight_speeds_of_mpa()[-1], 0.0)
+    runner.trim[::3] = drive
+    iters_a, preds_a, _ = runner.timestep_inputs()
+    runner.obstacles_fn = lambda *a: scenario.assemble_obstacles_host(mpa, *a)
+    iters_b, preds_b, _ = runner.timestep_inputs()
+    ba = SearchBatch.from_iters(iters_a, mpa.Hp, sc.checker, mpa.dt_seconds)
+    bb = SearchBatch.from_iters(iters_b, mpa.Hp, sc.checker, mpa.dt_seconds)
+    for f in ("slot_ptr", "poly_ptr", "vert_x", "vert_y"):
+        a, b = getattr(ba, f), getattr(bb, f)
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), f
+    per_slot = np.diff(ba.slot_ptr.reshape(-1)).reshape(sc.amount, mpa.Hp + 1)
+    assert per_slot[:, 0].sum() > 0 and per_slot[:, 1:].sum() > 0
+    assert all(np.array_equal(p, q) for p, q in zip(preds_a, preds_b))

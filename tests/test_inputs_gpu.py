@@ -146,3 +146,79 @@ def test_closed_loop_with_fallback_plans_on_the_device(planner):
     with pytest.raises(capi.PdmpcError):
         b = dev.timestep_records[-1][1]
         planner.plan_timestep_closed_loop(b, dev.timestep_records[-1][2], np.zeros(b.n, dtype=np.int32), np.zeros(b.n, dtype=np.uint8))
+
+
+def _obstacle_csr(batch):
+    return batch.slot_ptr, batch.poly_ptr, batch.vert_x, batch.vert_y
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("max_cls", [1, 2])
+def test_assemble_obstacles_equals_the_host_assembly(planner, max_cls):
+    """pdmpc_assemble_obstacles: standstill rectangles of standing successors
+    (PrioritizedController.m:508-540, get_occupied_areas.m:19-25) and reachable sets of parallel predecessors
+    (:391-407, MotionPrimitiveAutomaton.m:649-687) of all 40 vehicles in one call — the obstacle CSR equals the host
+    assembly bit for bit at every time step of a closed loop that runs on the device-assembled obstacles."""
+    from pdmpc_b200.records import SearchBatch
+    mpa = get_mpa("triple_speed", non_convex=True)
+    planner.upload_mpa(mpa)
+    planner.upload_reachable_sets(scenario.local_reachable_sets_conv(mpa))
+    sc = scenario.commonroad_scenario(mpa, 40, seed=2, allow_shared_paths=True)
+    runner = scenario.ScenarioRunner(sc, None, max_num_CLs=max_cls,
+                                     timestep_fn=lambda b, d: planner.plan_timestep(b, d, False),
+                                     obstacles_fn=planner.assemble_obstacles)
+    seen_static = seen_dynamic = 0
+    for _ in range(6):
+        fn, runner.obstacles_fn = runner.obstacles_fn, None
+        iters_h, preds_h, _ = runner.timestep_inputs()
+        runner.obstacles_fn = fn
+        iters_d, preds_d, _ = runner.timestep_inputs()
+        bh = SearchBatch.from_iters(iters_h, mpa.Hp, sc.checker, mpa.dt_seconds)
+        bd = SearchBatch.from_iters(iters_d, mpa.Hp, sc.checker, mpa.dt_seconds)
+        for a, b_ in zip(_obstacle_csr(bh), _obstacle_csr(bd)):
+            assert a.dtype == b_.dtype and np.array_equal(a.view(np.uint8), b_.view(np.uint8))
+        assert all(np.array_equal(p, q) for p, q in zip(preds_h, preds_d))
+        sp = bh.slot_ptr.reshape(-1)
+        per_slot = (sp[1:] - sp[:-1]).reshape(sc.amount, mpa.Hp + 1)
+        seen_static += int(per_slot[:, 0].sum())
+        seen_dynamic += int(per_slot[:, 1:].sum())
+        dev = runner.step_timestep()                      # the loop advances on the device-assembled obstacles
+        _k, batch, deps, _ = runner.timestep_records[-1]
+        parity.compare(dev, scenario.plan_timestep_by_levels(lambda x: oracle_py.plan_batch(mpa, x), batch, deps))
+    assert seen_static > 0 and seen_dynamic > 0
+
+
+@pytest.mark.gpu
+def test_assemble_obstacles_errors_and_empty_rows(planner):
+    mpa = get_mpa("triple_speed", non_convex=True)
+    planner.upload_mpa(mpa)
+    sets = scenario.local_reachable_sets_conv(mpa)
+    planner.upload_reachable_sets(sets)
+    n, Hp = 3, mpa.Hp
+    x, y, yaw = np.array([0.5, 1.0, 2.0]), np.array([0.25, 1.5, 3.0]), np.array([0.0, 1.25, -2.5])
+    speed, trim = np.array([0.0, 0.5, 0.005]), np.array([1, 5, 2], dtype=np.int32)
+    # row 0 sees rows 1 (driving: no obstacle) and 2 (standing) as successors; row 2 has row 1 as parallel predecessor
+    o = planner.assemble_obstacles(x, y, yaw, speed, trim, [[1, 2], [], []], [[], [], [1]], 0.12, 0.0625)
+    sp = o["slot_ptr"]
+    assert sp[1] - sp[0] == 1 and all(sp[k + 1] - sp[k] == 0 for k in range(1, 2 * (Hp + 1)))
+    assert all(sp[2 * (Hp + 1) + k + 1] - sp[2 * (Hp + 1) + k] == 1 for k in range(1, Hp + 1))
+    rect = scenario.occupied_area(x[2], y[2], yaw[2], offset=0.0)   # half sizes passed explicitly below
+    s_, c = scenario.sincos_spec(yaw[2])
+    xl = np.array([-1.0, -1.0, 1.0, 1.0, -1.0]) * 0.12
+    yl = np.array([-1.0, 1.0, 1.0, -1.0, -1.0]) * 0.0625
+    assert rect.shape == (2, 5)
+    assert np.array_equal(o["vert_x"][:5], c * xl - s_ * yl + x[2]) and np.array_equal(o["vert_y"][:5], s_ * xl + c * yl + y[2])
+    want = scenario.reachable_sets_at(mpa, x[1], y[1], yaw[1], 5)
+    pp = o["poly_ptr"]
+    for k in range(Hp):
+        p = sp[2 * (Hp + 1) + k + 1]
+        assert np.array_equal(o["vert_x"][pp[p]:pp[p + 1]], want[k][0]) and np.array_equal(o["vert_y"][pp[p]:pp[p + 1]], want[k][1])
+    with pytest.raises(capi.PdmpcError) as e:      # capacities are checked, nothing is truncated
+        planner.assemble_obstacles(x, y, yaw, speed, trim, [[1, 2], [], []], [[], [], [1]], 0.12, 0.0625, poly_capacity=2, vert_capacity=4096)
+    assert e.value.code == capi.PDMPC_ERR_CAPACITY
+    with pytest.raises(capi.PdmpcError):
+        planner.assemble_obstacles(x, y, yaw, speed, trim, [[7], [], []], [[], [], []], 0.12, 0.0625)
+    with pytest.raises(capi.PdmpcError):            # open polygon
+        bad = [[a.copy() for a in row] for row in sets]
+        bad[0][0] = bad[0][0][:, :-1]
+        planner.upload_reachable_sets(bad)

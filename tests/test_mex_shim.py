@@ -242,3 +242,54 @@ def test_sample_inputs_matlab_helper_present():
     import os
     src = open(os.path.join(mexfake.ROOT, "p-dmpc_b200", "matlab", "sample_inputs_cuda.m")).read()
     assert "UPLOAD_ROAD = 8" in src and "SAMPLE_INPUTS = 9" in src and "predicted_lanelet_boundary" in src
+
+
+@pytest.mark.gpu
+def test_mex_assemble_obstacles_matches_the_host_assembly(matlab):
+    """UPLOAD_REACHABLE_SETS + ASSEMBLE_OBSTACLES (assemble_obstacles_cuda.m): standing successors' areas and parallel
+    predecessors' reachable sets of all vehicles through the shim, bit for bit against the host restatement."""
+    from pdmpc_b200 import scenario
+    from pdmpc_b200.mpa import get_mpa
+    mpa = get_mpa("triple_speed", non_convex=True)
+    (h,) = matlab.call(1, mexfake.CREATE, 0.0)
+    try:
+        trans, man = mexfake.matlab_mpa(mpa)
+        matlab.call(0, mexfake.UPLOAD_MPA, float(h), trans, man)
+        sets = scenario.local_reachable_sets_conv(mpa)
+        matlab.call(0, mexfake.UPLOAD_REACHABLE_SETS, float(h), [[np.ascontiguousarray(a) for a in row] for row in sets])
+        rng = np.random.default_rng(11)
+        n = 6
+        x0 = np.column_stack([rng.uniform(0.5, 4.0, n), rng.uniform(0.5, 3.5, n), rng.uniform(-3.0, 3.0, n),
+                              np.array([0.0, 0.6, 0.0, 0.3, 0.005, 0.9])])
+        trims = rng.integers(1, mpa.n_trims + 1, size=n)
+        succ = [[1, 2], [2, 4], [], [4, 5], [], []]
+        par = [[], [0], [0, 1], [], [3], [0, 3, 4]]
+        obs, dyn = matlab.call(2, mexfake.ASSEMBLE_OBSTACLES, float(h), x0, trims.astype(np.float64),
+                               [np.array(s, dtype=np.float64) + 1 for s in succ], [np.array(p, dtype=np.float64) + 1 for p in par],
+                               0.12, 0.0625)
+        want = scenario.assemble_obstacles_host(mpa, x0[:, 0], x0[:, 1], x0[:, 2], x0[:, 3], trims, succ, par, 0.12, 0.0625)
+        sp, pp = want["slot_ptr"], want["poly_ptr"]
+        poly = lambda p: np.vstack([want["vert_x"][pp[p]:pp[p + 1]], want["vert_y"][pp[p]:pp[p + 1]]])
+        for i in range(n):
+            s0 = i * (mpa.Hp + 1)
+            got_static = list(obs[i])                       # {s_i x 1} cell
+            assert len(got_static) == sp[s0 + 1] - sp[s0]
+            for q, a in enumerate(got_static):
+                assert np.array_equal(a, poly(sp[s0] + q))
+            rows = len(par[i])
+            assert len(dyn[i]) == rows * mpa.Hp             # {p_i x Hp} cell, column-major
+            for q in range(rows):
+                for k in range(mpa.Hp):
+                    assert np.array_equal(dyn[i][q + rows * k], poly(sp[s0 + 1 + k] + q))
+        with pytest.raises(mexfake.MexError):
+            matlab.call(2, mexfake.ASSEMBLE_OBSTACLES, float(h), x0, trims.astype(np.float64),
+                        [np.array([n + 1.0])] + [np.zeros(0)] * (n - 1), [np.zeros(0)] * n, 0.12, 0.0625)
+    finally:
+        matlab.call(0, mexfake.DESTROY, float(h))
+        matlab.clear_mex()
+
+
+def test_assemble_obstacles_matlab_helper_present():
+    import os
+    src = open(os.path.join(mexfake.ROOT, "p-dmpc_b200", "matlab", "assemble_obstacles_cuda.m")).read()
+    assert "UPLOAD_REACHABLE_SETS = 10" in src and "ASSEMBLE_OBSTACLES = 11" in src and "local_reachable_sets_conv" in src
