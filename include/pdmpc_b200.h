@@ -244,6 +244,12 @@ int pdmpc_set_cta_heap_smem(pdmpc_handle *h, int32_t entries);
  * of at least 2*chunks searches.  Tuning/test knob: results do not depend on it. */
 int pdmpc_set_pipeline_chunks(pdmpc_handle *h, int32_t chunks);
 
+/* Diagnostics: the timeline of the LAST pipelined pdmpc_plan_batch call, per chunk: host_ms = host time since the start
+ * of the call at which the chunk's copies and kernel had been enqueued (after its validation), in_ms / done_ms = device
+ * time since the first copy started at which its inputs had landed / its searches were done.  Arrays of `cap` entries
+ * (NULL = not wanted); *n_chunks = chunks of that call (0: the last call was not pipelined). */
+int pdmpc_get_pipeline_timeline(pdmpc_handle *h, int32_t cap, double *host_ms, double *in_ms, double *done_ms, int32_t *n_chunks);
+
 /* Stage the MPA tables in HBM (once per MPA; cached in the handle). */
 int pdmpc_upload_mpa(pdmpc_handle *h, const pdmpc_mpa_desc *mpa);
 

@@ -30,7 +30,7 @@ PDMPC_ERR_ALLOC = 5
 
 EXPORTED_SYMBOLS = (
     "pdmpc_create", "pdmpc_destroy", "pdmpc_last_error", "pdmpc_abi_version",
-    "pdmpc_set_node_capacity", "pdmpc_set_variant", "pdmpc_set_tile_points", "pdmpc_set_cta_queue", "pdmpc_set_escalation", "pdmpc_get_hp", "pdmpc_pack_plan_rows", "pdmpc_upload_road", "pdmpc_sample_inputs", "pdmpc_upload_reachable_sets", "pdmpc_assemble_obstacles", "pdmpc_closed_loop_reset", "pdmpc_plan_timestep_closed_loop", "pdmpc_host_alloc", "pdmpc_host_free",
+    "pdmpc_set_node_capacity", "pdmpc_set_variant", "pdmpc_set_tile_points", "pdmpc_set_cta_queue", "pdmpc_set_escalation", "pdmpc_get_hp", "pdmpc_pack_plan_rows", "pdmpc_upload_road", "pdmpc_sample_inputs", "pdmpc_upload_reachable_sets", "pdmpc_assemble_obstacles", "pdmpc_get_pipeline_timeline", "pdmpc_closed_loop_reset", "pdmpc_plan_timestep_closed_loop", "pdmpc_host_alloc", "pdmpc_host_free",
     "pdmpc_trace_staged", "pdmpc_upload_mpa", "pdmpc_plan_batch", "pdmpc_stage_batch",
     "pdmpc_run_staged", "pdmpc_sync", "pdmpc_fetch_staged", "pdmpc_get_stats", "pdmpc_stream",
     "pdmpc_mcts_plan_batch", "pdmpc_mcts_run_staged", "pdmpc_set_cta_heap_smem", "pdmpc_plan_timestep",
@@ -222,6 +222,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.pdmpc_upload_reachable_sets.restype = C.c_int
     lib.pdmpc_assemble_obstacles.argtypes = [H, C.POINTER(CouplingInC), C.POINTER(ObstaclesOutC)]
     lib.pdmpc_assemble_obstacles.restype = C.c_int
+    lib.pdmpc_get_pipeline_timeline.argtypes = [H, C.c_int32, _p_f64, _p_f64, _p_f64, C.POINTER(C.c_int32)]
+    lib.pdmpc_get_pipeline_timeline.restype = C.c_int
     lib.pdmpc_closed_loop_reset.argtypes = [H, C.c_int32, C.c_double, C.c_double]
     lib.pdmpc_closed_loop_reset.restype = C.c_int
     lib.pdmpc_plan_timestep_closed_loop.argtypes = [H, C.POINTER(BatchIn), C.POINTER(TimestepDepsC), _p_i32,
@@ -367,6 +369,14 @@ class Planner:
         tot = int(o["lane_ptr"][-1])
         o["lane_x"], o["lane_y"] = o["lane_x"][:tot], o["lane_y"][:tot]
         return o
+
+    def pipeline_timeline(self):
+        """Per chunk of the last pipelined plan_batch call: (host_ms, in_ms, done_ms) arrays (pdmpc_get_pipeline_timeline)."""
+        cap = 32
+        a, b, c = np.zeros(cap), np.zeros(cap), np.zeros(cap)
+        n = C.c_int32()
+        self._check(self.lib.pdmpc_get_pipeline_timeline(self.h, cap, _ptr(a, _p_f64), _ptr(b, _p_f64), _ptr(c, _p_f64), C.byref(n)))
+        return a[: n.value], b[: n.value], c[: n.value]
 
     def upload_reachable_sets(self, sets):
         """mpa.local_reachable_sets_conv as sets[trim][step] = closed (2, m) polygon (scenario.local_reachable_sets_conv)

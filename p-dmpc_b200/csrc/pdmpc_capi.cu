@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <new>
 #include <string>
 #include <vector>
@@ -145,6 +146,8 @@ struct pdmpc_handle {
     // pipelined pdmpc_plan_batch (large host batches): copy-in, two compute and copy-out streams
     cudaStream_t s_in = nullptr, s_out = nullptr, s_comp[7] = {};   // + the handle's stream
     std::vector<cudaEvent_t> ev_chunk;   // 2 per chunk: inputs landed, searches done
+    std::vector<double> chunk_host_ms;   // host time at which chunk c's launch was enqueued (pdmpc_get_pipeline_timeline)
+    int chunks_last = 0;
     cudaEvent_t ev_fork = nullptr;
     void *pin_order = nullptr;
     size_t pin_order_cap = 0;
@@ -1155,7 +1158,7 @@ static int plan_batch_pipelined(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc
     }
     while ((int)h->ev_chunk.size() < 2 * C) {
         cudaEvent_t e;
-        CU_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CU_TRY(h, cudaEventCreate(&e));
         h->ev_chunk.push_back(e);
     }
     // ---- device arrays for the whole batch ----------------------------------------------------
@@ -1272,20 +1275,25 @@ static int plan_batch_pipelined(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc
         pipeline_sync_all(h);
         return code;
     };
+    const auto t_call = std::chrono::steady_clock::now();
+    h->chunk_host_ms.assign(C, 0.0);
+    h->chunks_last = C;
     for (int c = 0; c < C; ++c) {
         const int s0 = bound(c), s1 = bound(c + 1);
         if (s1 == s0) continue;
-        rc = validate_range(h, in, s0, s1);
-        if (rc != PDMPC_OK) return bail(rc);
         const int p0 = in->slot_ptr[(size_t)s0 * (Hp + 1)], p1 = in->slot_ptr[(size_t)s1 * (Hp + 1)];
         const int v0 = in->poly_ptr[p0], v1 = in->poly_ptr[p1];
         const int l0 = in->lane_ptr[2 * s0], l1 = in->lane_ptr[2 * s1];
-        if (p0 < 0 || p1 > np || v0 < 0 || v1 > nv || l0 < 0 || l1 > nl)   // the arrays were sized from the totals
+        if (p0 < 0 || p1 > np || p1 < p0 || v0 < 0 || v1 > nv || v1 < v0 || l0 < 0 || l1 > nl || l1 < l0)   // the arrays were sized from the totals
             return bail(fail(h, PDMPC_ERR_BAD_INPUT, "plan: CSR offsets exceed their totals"));
         {   // work order inside the chunk: most obstacle polygons first (counting sort, stable)
-            int kmax = 0;
-            for (int i = s0; i < s1; ++i)
-                kmax = std::max(kmax, in->slot_ptr[(size_t)(i + 1) * (Hp + 1)] - in->slot_ptr[(size_t)i * (Hp + 1)]);
+            int kmax = 0, kmin = 0;
+            for (int i = s0; i < s1; ++i) {
+                const int d = in->slot_ptr[(size_t)(i + 1) * (Hp + 1)] - in->slot_ptr[(size_t)i * (Hp + 1)];
+                kmax = std::max(kmax, d);
+                kmin = std::min(kmin, d);
+            }
+            if (kmin < 0) return bail(fail(h, PDMPC_ERR_BAD_INPUT, "plan: slot_ptr not monotone"));   // (validated in full below)
             std::vector<int> cnt(kmax + 2, 0);
             for (int i = s0; i < s1; ++i)
                 cnt[kmax - (in->slot_ptr[(size_t)(i + 1) * (Hp + 1)] - in->slot_ptr[(size_t)i * (Hp + 1)]) + 1]++;
@@ -1309,6 +1317,10 @@ static int plan_batch_pipelined(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc
                 return bail(fail(h, PDMPC_ERR_CUDA, std::string("pipeline H2D: ") + cudaGetErrorString(cudaGetLastError())));
             h->stats.h2d_bytes += (int64_t)bytes;
         }
+        // the slice is validated while it is on its way (its copies only needed the offsets checked above); nothing of
+        // the chunk runs before that
+        rc = validate_range(h, in, s0, s1);
+        if (rc != PDMPC_OK) return bail(rc);
         cudaEvent_t ev_in = h->ev_chunk[2 * c], ev_done = h->ev_chunk[2 * c + 1];
         cudaStream_t S = comp[c % lanes];
         if (cudaEventRecord(ev_in, h->s_in) != cudaSuccess || cudaStreamWaitEvent(S, ev_in, 0) != cudaSuccess)
@@ -1338,6 +1350,7 @@ static int plan_batch_pipelined(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc
         if (cudaGetLastError() != cudaSuccess || cudaEventRecord(ev_done, S) != cudaSuccess ||
             cudaStreamWaitEvent(h->s_out, ev_done, 0) != cudaSuccess)
             return bail(fail(h, PDMPC_ERR_CUDA, "pipeline: search kernel launch failed"));
+        h->chunk_host_ms[c] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count();
         if (!d2h_started) {
             cudaEventRecord(h->ev[4], h->s_out);
             d2h_started = true;
@@ -1412,6 +1425,25 @@ static int plan_batch_pipelined(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc
     if (counters[3]) h->stats.handed_over = (int32_t)counters[3];
     h->stats.escalated = (int32_t)counters[6];
     h->staged = true;   // the device holds the whole batch: pdmpc_run_staged / pdmpc_fetch_staged work on it
+    return PDMPC_OK;
+}
+
+int pdmpc_get_pipeline_timeline(pdmpc_handle *h, int32_t cap, double *host_ms, double *in_ms, double *done_ms, int32_t *n_chunks) {
+    if (!h || !n_chunks) return PDMPC_ERR_BAD_INPUT;
+    CU_TRY(h, cudaSetDevice(h->device));
+    if (pipeline_sync_all(h) != PDMPC_OK) return PDMPC_ERR_CUDA;
+    *n_chunks = h->chunks_last;
+    for (int c = 0; c < h->chunks_last && c < cap; ++c) {
+        float a = 0.f, b = 0.f;
+        if ((int)h->ev_chunk.size() < 2 * c + 2 || cudaEventElapsedTime(&a, h->ev[0], h->ev_chunk[2 * c]) != cudaSuccess ||
+            cudaEventElapsedTime(&b, h->ev[0], h->ev_chunk[2 * c + 1]) != cudaSuccess) {
+            cudaGetLastError();
+            a = b = -1.f;
+        }
+        if (host_ms) host_ms[c] = h->chunk_host_ms[c];
+        if (in_ms) in_ms[c] = a;
+        if (done_ms) done_ms[c] = b;
+    }
     return PDMPC_OK;
 }
 

@@ -50,11 +50,17 @@ bi, bo = capi.batch_in(hb), capi.batch_out(out)
 print(batch.n, "searches")
 for chunks in [int(c) for c in os.environ.get('PDMPC_CHUNKS', '1,2,3,4,5,6,8,12').split(',')]:
     p.set_pipeline_chunks(chunks)
-    ts = []
-    for _ in range(5):
-        t0 = time.perf_counter()
-        p._check(p.lib.pdmpc_plan_batch(p.h, C.byref(bi), C.byref(bo)))
-        ts.append((time.perf_counter() - t0) * 1e3)
-    st = p.stats()
-    print(f"chunks {chunks:2d}: {min(ts[2:]):.1f} ms -> {batch.n / min(ts[2:]) / 1e3:.3f} M plans/s  "
-          f"(h2d {st.h2d_ms:.1f} kernel {st.kernel_ms:.1f} d2h {st.d2h_ms:.1f} ms, escalated {st.escalated})")
+    for esc in [int(v) for v in os.environ.get('PDMPC_ESC_SWEEP', '-1').split(',')]:
+        p.set_escalation(esc)
+        ts = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            p._check(p.lib.pdmpc_plan_batch(p.h, C.byref(bi), C.byref(bo)))
+            ts.append((time.perf_counter() - t0) * 1e3)
+        st = p.stats()
+        print(f"chunks {chunks:2d} escalation {esc}: {min(ts[2:]):.1f} ms -> {batch.n / min(ts[2:]) / 1e3:.3f} M plans/s  "
+              f"(h2d {st.h2d_ms:.1f} kernel {st.kernel_ms:.1f} d2h {st.d2h_ms:.1f} ms, escalated {st.escalated})")
+        if chunks != 1 and hasattr(p, "pipeline_timeline"):
+            hm, im, dm = p.pipeline_timeline()
+            print("   chunk: enqueued by the host at / inputs landed at / searches done at [ms]:",
+                  "  ".join(f"{a:.1f}/{b:.1f}/{c:.1f}" for a, b, c in zip(hm, im, dm)))
