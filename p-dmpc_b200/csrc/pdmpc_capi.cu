@@ -148,7 +148,6 @@ struct pdmpc_handle {
     std::vector<cudaEvent_t> ev_chunk;   // 2 per chunk: inputs landed, searches done
     std::vector<double> chunk_host_ms;   // host time at which chunk c's launch was enqueued (pdmpc_get_pipeline_timeline)
     int chunks_last = 0;
-    int grid_div = 1;                  // EXPERIMENT: chunk kernels of the pipeline take 1/grid_div of the tile slots
     cudaEvent_t ev_fork = nullptr;
     void *pin_order = nullptr;
     size_t pin_order_cap = 0;
@@ -819,7 +818,7 @@ static int ensure_arena(pdmpc_handle *h, int slots) {
 static int warp_shape_grid(const pdmpc_handle *h, int shape, int n, int *slots) {
     if (shape == 2 || shape == 3) {
         const int T = shape == 2 ? 2 : 4;
-        const int grid = std::max(1, std::min((n + T - 1) / T, h->num_sms * h->tile_ctas_per_sm[shape - 2] / std::max(1, h->grid_div)));
+        const int grid = std::max(1, std::min((n + T - 1) / T, h->num_sms * h->tile_ctas_per_sm[shape - 2]));
         *slots = grid * T;
         return grid;
     }
@@ -1339,7 +1338,6 @@ static int plan_batch_pipelined(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc
             h->stats.kernel_launches++;
         }
         BatchDev bc = bproto;
-        h->grid_div = (c == 0 || !getenv("PDMPC_GRID_DIV")) ? 1 : atoi(getenv("PDMPC_GRID_DIV"));
         bc.n = s1 - s0;
         bc.order = h->b_order.as<int>() + s0;
         unsigned *wc = h->wc_chunks.as<unsigned>() + c;
@@ -1366,7 +1364,6 @@ static int plan_batch_pipelined(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc
             h->stats.d2h_bytes += (int64_t)bytes;
         }
     }
-    h->grid_div = 1;
     for (int c = 0; c < C; ++c)   // every chunk joins the handle's stream
         if (c % lanes != 0 && bound(c + 1) > bound(c))
             CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_chunk[2 * c + 1], 0));
