@@ -421,3 +421,38 @@ def test_escalation_of_long_searches(planner, variant, valid_only):
         planner.set_escalation(-1)           # back to the default: by batch size
     with pytest.raises(capi.PdmpcError):
         planner.set_escalation(-2)
+
+
+def _with_areas(mpa, transform):
+    """A copy of `mpa` whose maneuver areas (all three kinds) went through transform(x[:n], y[:n]) -> (x', y')."""
+    npts, ax, ay = mpa.area_npts.copy(), np.zeros_like(mpa.area_x), np.zeros_like(mpa.area_y)
+    for e in range(mpa.n_edges):
+        for k in range(3):
+            n = int(mpa.area_npts[e, k])
+            x, y = transform(mpa.area_x[e, k, :n].copy(), mpa.area_y[e, k, :n].copy())
+            npts[e, k] = x.size
+            ax[e, k, :x.size], ay[e, k, :x.size] = x, y
+    return dataclasses.replace(mpa, area_npts=npts, area_x=ax, area_y=ay)
+
+
+@pytest.mark.gpu
+def test_open_and_eight_point_maneuver_areas(planner):
+    """The InterX loop instances no reference MPA reaches: areas that are NOT closed polygons (the closing vertex
+    dropped: the C2 row then computes its last vertex instead of reusing the first) and areas of 8 points (7 edges, the
+    widest row; only plan_batch takes them, the hand-over of a time step needs a free column).  Every launch shape
+    against the oracle on road-network records."""
+    base, batch = road_records("single_speed", 3)
+    batch = batch.select(np.arange(min(batch.n, 120)))
+    open_mpa = _with_areas(base, lambda x, y: (x[:-1], y[:-1]))
+    assert int(open_mpa.area_npts.max()) == int(base.area_npts.max()) - 1
+
+    def eight(x, y):   # one more vertex in the middle of the longest-index edge of a 7-point area: same polygon, 7 edges
+        if x.size != 7:
+            return x, y
+        return (np.concatenate([x[:1], [(x[0] + x[1]) / 2], x[1:]]), np.concatenate([y[:1], [(y[0] + y[1]) / 2], y[1:]]))
+
+    wide_mpa = _with_areas(base, eight)
+    assert int(wide_mpa.area_npts.max()) == 8
+    for mpa in (open_mpa, wide_mpa):
+        info, dev, ref = check(planner, mpa, batch)
+        assert info["n"] == batch.n and info["pops"] > 0
