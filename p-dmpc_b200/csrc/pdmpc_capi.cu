@@ -1135,12 +1135,44 @@ static int pipeline_sync_all(pdmpc_handle *h) {
     return e == cudaSuccess ? PDMPC_OK : fail(h, PDMPC_ERR_CUDA, std::string("pipeline sync: ") + cudaGetErrorString(e));
 }
 
-static int plan_batch_pipelined(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc_batch_out *out, int C) {
+// Chunk boundaries of the pipeline: bnd[c] .. bnd[c + 1] are the searches of chunk c.
+//   C_req > 1 (pdmpc_set_pipeline_chunks): C_req chunks of equal size, the first one half of that.
+//   C_req == 0: sizes double from ~24 k searches up to max(192 k, n / 12) — nothing overlaps the first chunk's validation and
+//   copy, so it is small; every chunk boundary costs (a chunk kernel's one-warp CTAs leave only when both of their searches
+//   are over), so there are few; the last chunk's results come back behind the escalated searches, so it must not be
+//   huge.  Measured at 358 400 records (profiles/r02k_pipeline_timeline.txt): 86.8 ms with 5 chunks of 40 k + 4 x 80 k,
+//   83.4 ms with 24 k / 48 k / 96 k / 191 k.
+static std::vector<int> pipeline_bounds(int n, int C_req) {
+    std::vector<int> bnd(1, 0);
+    if (C_req > 1) {
+        constexpr double first_frac = 0.5;
+        for (int c = 1; c < C_req; ++c)
+            bnd.push_back(C_req < 3 ? (int)((long long)n * c / C_req)
+                                    : (int)((double)n * ((double)(c - 1) + first_frac) / ((double)(C_req - 1) + first_frac)));
+        bnd.push_back(n);
+        return bnd;
+    }
+    const int smax = std::max(192000, n / 12);
+    int size = std::max(16384, std::min(24000, n / 2));
+    while (bnd.back() + size < n && (int)bnd.size() < kPipelineMaxChunks) {
+        bnd.push_back(bnd.back() + size);
+        size = std::min(2 * size, smax);
+    }
+    // a short remainder joins the chunk before it
+    if (bnd.size() > 2 && n - bnd.back() < (bnd.back() - bnd[bnd.size() - 2]) / 2) bnd.pop_back();
+    if (bnd.size() == 1 && n >= 2) bnd.push_back(n / 2);   // at least two chunks
+    bnd.push_back(n);
+    return bnd;
+}
+
+static int plan_batch_pipelined(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc_batch_out *out, int C_req) {
     int rc = validate_header(h, in);
     if (rc != PDMPC_OK) return rc;
     if (!out || !out->status) return fail(h, PDMPC_ERR_BAD_INPUT, "fetch: out/status is NULL");
     CU_TRY(h, cudaSetDevice(h->device));
     const int n = in->n_searches, Hp = h->mpa.Hp;
+    const std::vector<int> bnd = pipeline_bounds(n, C_req);
+    const int C = (int)bnd.size() - 1;
     const size_t ns = (size_t)n * (Hp + 1);
     const int np = in->slot_ptr[ns];
     if (np < 0 || (np > 0 && (!in->vert_x || !in->vert_y)))
@@ -1187,15 +1219,7 @@ static int plan_batch_pipelined(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc
     CU_TRY(h, h->wc_chunks.reserve(kPipelineMaxChunks * sizeof(unsigned)));
     // one-warp CTAs leave an SM one by one as their searches end, so the next chunk's CTAs move in early
     constexpr int kLanes = 8;   // most concurrent chunk kernels (streams, arenas)
-    // chunk c covers the searches [bound(c), bound(c + 1)).  Nothing overlaps the first chunk's validation and copy,
-    // so it is half the others' size (measured: 92.5 -> 89.6 ms per call of 358 400 records; a quarter: 90.9 ms).
-    constexpr double first_frac = 0.5;
-    auto bound = [&](int c) -> int {
-        if (C < 3) return (int)((long long)n * c / C);
-        if (c <= 0) return 0;
-        if (c >= C) return n;
-        return (int)((double)n * ((double)(c - 1) + first_frac) / ((double)(C - 1) + first_frac));
-    };
+    auto bound = [&](int c) -> int { return bnd[c]; };   // chunk c covers the searches [bound(c), bound(c + 1))
     int per_chunk = 1;
     for (int c = 0; c < C; ++c) per_chunk = std::max(per_chunk, bound(c + 1) - bound(c));
     const int shape = resolve_warp_shape(h, h->variant_mode, per_chunk, in->checker, false);
@@ -1458,8 +1482,7 @@ int pdmpc_set_pipeline_chunks(pdmpc_handle *h, int32_t chunks) {
 int pdmpc_plan_batch(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc_batch_out *out) {
     if (h && in && h->has_mpa && h->pipeline_chunks != 1 && h->variant_mode <= 3 &&
         (h->pipeline_chunks > 1 ? in->n_searches >= 2 * h->pipeline_chunks : in->n_searches >= kPipelineMinSearches)) {
-        const int C = h->pipeline_chunks > 1 ? h->pipeline_chunks : std::min(12, std::max(2, in->n_searches / 60000));   // ~60 k searches per chunk: profiles/r02_pipeline_chunks.txt
-        return plan_batch_pipelined(h, in, out, C);
+        return plan_batch_pipelined(h, in, out, h->pipeline_chunks > 1 ? h->pipeline_chunks : 0);
     }
     int rc = pdmpc_stage_batch(h, in);
     if (rc != PDMPC_OK) return rc;
