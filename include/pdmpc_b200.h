@@ -244,6 +244,12 @@ int pdmpc_set_cta_heap_smem(pdmpc_handle *h, int32_t entries);
  * of at least 2*chunks searches.  Tuning/test knob: results do not depend on it. */
 int pdmpc_set_pipeline_chunks(pdmpc_handle *h, int32_t chunks);
 
+/* The chunk boundaries pdmpc_plan_batch uses for a batch of n_searches (host-only, needs no device): chunk c = searches
+ * [bounds[c], bounds[c+1]).  chunks = 0: the automatic schedule (sizes double from ~24 000 searches up to
+ * max(192 000, n/12)); chunks = 2..16: what pdmpc_set_pipeline_chunks(chunks) gives (equal sizes, the first one half).
+ * bounds: cap >= *n_chunks + 1 entries (PDMPC_ERR_CAPACITY otherwise, *n_chunks is still set). */
+int pdmpc_pipeline_bounds(int32_t n_searches, int32_t chunks, int32_t cap, int32_t *bounds, int32_t *n_chunks);
+
 /* Diagnostics: the timeline of the LAST pipelined pdmpc_plan_batch call, per chunk: host_ms = host time since the start
  * of the call at which the chunk's copies and kernel had been enqueued (after its validation), in_ms / done_ms = device
  * time since the first copy started at which its inputs had landed / its searches were done.  Arrays of `cap` entries

@@ -30,7 +30,7 @@ PDMPC_ERR_ALLOC = 5
 
 EXPORTED_SYMBOLS = (
     "pdmpc_create", "pdmpc_destroy", "pdmpc_last_error", "pdmpc_abi_version",
-    "pdmpc_set_node_capacity", "pdmpc_set_variant", "pdmpc_set_tile_points", "pdmpc_set_cta_queue", "pdmpc_set_escalation", "pdmpc_get_hp", "pdmpc_pack_plan_rows", "pdmpc_upload_road", "pdmpc_sample_inputs", "pdmpc_upload_reachable_sets", "pdmpc_assemble_obstacles", "pdmpc_get_pipeline_timeline", "pdmpc_closed_loop_reset", "pdmpc_plan_timestep_closed_loop", "pdmpc_host_alloc", "pdmpc_host_free",
+    "pdmpc_set_node_capacity", "pdmpc_set_variant", "pdmpc_set_tile_points", "pdmpc_set_cta_queue", "pdmpc_set_escalation", "pdmpc_get_hp", "pdmpc_pack_plan_rows", "pdmpc_upload_road", "pdmpc_sample_inputs", "pdmpc_upload_reachable_sets", "pdmpc_assemble_obstacles", "pdmpc_get_pipeline_timeline", "pdmpc_pipeline_bounds", "pdmpc_closed_loop_reset", "pdmpc_plan_timestep_closed_loop", "pdmpc_host_alloc", "pdmpc_host_free",
     "pdmpc_trace_staged", "pdmpc_upload_mpa", "pdmpc_plan_batch", "pdmpc_stage_batch",
     "pdmpc_run_staged", "pdmpc_sync", "pdmpc_fetch_staged", "pdmpc_get_stats", "pdmpc_stream",
     "pdmpc_mcts_plan_batch", "pdmpc_mcts_run_staged", "pdmpc_set_cta_heap_smem", "pdmpc_plan_timestep",
@@ -224,6 +224,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.pdmpc_assemble_obstacles.restype = C.c_int
     lib.pdmpc_get_pipeline_timeline.argtypes = [H, C.c_int32, _p_f64, _p_f64, _p_f64, C.POINTER(C.c_int32)]
     lib.pdmpc_get_pipeline_timeline.restype = C.c_int
+    lib.pdmpc_pipeline_bounds.argtypes = [C.c_int32, C.c_int32, C.c_int32, _p_i32, C.POINTER(C.c_int32)]
+    lib.pdmpc_pipeline_bounds.restype = C.c_int
     lib.pdmpc_closed_loop_reset.argtypes = [H, C.c_int32, C.c_double, C.c_double]
     lib.pdmpc_closed_loop_reset.restype = C.c_int
     lib.pdmpc_plan_timestep_closed_loop.argtypes = [H, C.POINTER(BatchIn), C.POINTER(TimestepDepsC), _p_i32,
@@ -265,6 +267,17 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.pdmpc_stream.restype = C.c_void_p
     _LIB = lib
     return lib
+
+
+def pipeline_bounds(n_searches: int, chunks: int = 0, lib=None) -> np.ndarray:
+    """Chunk boundaries of the copy/search pipeline for a batch of n_searches (pdmpc_pipeline_bounds; host-only)."""
+    lib = lib or load_library()
+    out = np.zeros(64, dtype=np.int32)
+    n = C.c_int32()
+    rc = lib.pdmpc_pipeline_bounds(int(n_searches), int(chunks), out.size, _ptr(out, _p_i32), C.byref(n))
+    if rc != PDMPC_OK:
+        raise PdmpcError(rc, "pdmpc_pipeline_bounds")
+    return out[: n.value + 1].copy()
 
 
 class PdmpcError(RuntimeError):

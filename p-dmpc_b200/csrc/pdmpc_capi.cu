@@ -1452,6 +1452,15 @@ static int plan_batch_pipelined(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc
     return PDMPC_OK;
 }
 
+int pdmpc_pipeline_bounds(int32_t n_searches, int32_t chunks, int32_t cap, int32_t *bounds, int32_t *n_chunks) {
+    if (n_searches < 2 || chunks < 0 || chunks == 1 || chunks > kPipelineMaxChunks || !bounds || !n_chunks) return PDMPC_ERR_BAD_INPUT;
+    const std::vector<int> bnd = pipeline_bounds(n_searches, chunks);
+    *n_chunks = (int32_t)bnd.size() - 1;
+    if ((int)bnd.size() > cap) return PDMPC_ERR_CAPACITY;
+    for (size_t i = 0; i < bnd.size(); ++i) bounds[i] = bnd[i];
+    return PDMPC_OK;
+}
+
 int pdmpc_get_pipeline_timeline(pdmpc_handle *h, int32_t cap, double *host_ms, double *in_ms, double *done_ms, int32_t *n_chunks) {
     if (!h || !n_chunks) return PDMPC_ERR_BAD_INPUT;
     CU_TRY(h, cudaSetDevice(h->device));

@@ -85,3 +85,27 @@ def test_product_never_imports_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
                 assert not re.search(r'#\s*include\s*[<"][^>"]*oracle', txt), f
                 assert not re.search(r"\boracle_(plan|pq|interx|intersect|sincos)\w*\s*\(", txt), f
+
+
+def test_pipeline_chunk_schedule_host_side():
+    """pdmpc_pipeline_bounds (host-only): the chunks of the copy/search pipeline cover the batch exactly, in order, in
+    at most 16 chunks; the automatic schedule starts small, doubles, and never ends in a sliver."""
+    from pdmpc_b200 import capi
+    import numpy as np
+    for n in (2, 3, 1000, 16384, 16385, 20000, 47999, 56000, 168000, 179200, 358400, 716800, 2867200, 10_000_000):
+        b = capi.pipeline_bounds(n)
+        sizes = np.diff(b)
+        assert b[0] == 0 and b[-1] == n and (sizes > 0).all() and 2 <= sizes.size <= 16, (n, b)
+        if n >= 100000:
+            assert sizes[0] <= 24000 and (sizes[1:-1] >= sizes[:-2]).all(), (n, sizes)      # small first chunk, growing
+            assert sizes[-1] >= sizes[-2] // 2, (n, sizes)                                   # no sliver at the end
+            assert sizes.max() <= max(192000, n // 12) * 3 // 2 + 1 or sizes.size == 16, (n, sizes)
+        for c in (2, 3, 5, 16):
+            if n >= 2 * c:
+                e = capi.pipeline_bounds(n, c)
+                assert e.size == c + 1 and e[0] == 0 and e[-1] == n and (np.diff(e) > 0).all()
+    assert capi.pipeline_bounds(358400).tolist() == [0, 24000, 72000, 168000, 358400]
+    with pytest.raises(capi.PdmpcError):
+        capi.pipeline_bounds(100, 1)
+    with pytest.raises(capi.PdmpcError):
+        capi.pipeline_bounds(100, 17)
