@@ -31,8 +31,11 @@
 // Shapes are padded to the widest shape of the warp by repeating their last vertex (= the first one,
 // closed polygon): b_i = b_0 there, b_0*b_0 >= 0 never satisfies the strict inequality.
 //
-// Polylines that do not fit the SP staged points of a tile (3 % of the road records at SP = 256) are read
-// from the batch arrays in HBM/L2 instead (lanelet bounds are staged first, they are tested at every pop).
+// A point of a polyline is an (x, y) pair read with one 16-byte load through a GENERIC pointer: the copy staged in the
+// tile's shared memory or — for the searches whose polylines exceed the SP staged points (48 % of the road records at
+// SP = 128; lanelet bounds are staged first, they are tested at every pop) — the batch's interleaved polyline arrays
+// (BatchDev::pl_xy / ll_xy, L1 / L2).  One item loop serves both; it is instantiated once per edge count of the widest
+// shape of the warp (4..7), so a round pays no dispatch.
 // Limits (fail over, never silently): SAT batches and pop traces are served by search_kernel.
 #pragma once
 
