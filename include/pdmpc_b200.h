@@ -464,6 +464,29 @@ int pdmpc_closed_loop_reset(pdmpc_handle *h, int32_t n_slots, double half_length
 int pdmpc_plan_timestep_closed_loop(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_timestep_deps *deps,
                                     const int32_t *slot, const uint8_t *standstill, pdmpc_batch_out *out);
 
+/* ---- One whole time step from the vehicles' MEASURED STATES in one call: pdmpc_sample_inputs, pdmpc_assemble_obstacles
+ *      and pdmpc_plan_timestep_closed_loop chained on the device — the reference trajectories, lanelet boundaries and
+ *      obstacle polygons never visit the host; what the host still supplies is what it decides: coupling and priorities
+ *      (HighLevelController / PrioritizedController up to :324), as three relations over the rows.
+ *      Needs pdmpc_upload_mpa, pdmpc_upload_road, pdmpc_upload_reachable_sets (if any row has parallel predecessors) and
+ *      pdmpc_closed_loop_reset.  Outputs as pdmpc_plan_timestep_closed_loop: an exhausted row holds its fallback plan.
+ *      The lanelet bounds of a vehicle may have at most 512 points (PDMPC_ERR_CAPACITY). ---- */
+typedef struct pdmpc_timestep_states {
+    int32_t n;                       /* rows: the vehicles of every scenario of the time step */
+    const int32_t *path_id;          /* [n] 0-based reference path of the row (pdmpc_upload_road) */
+    const double *x, *y, *yaw;       /* [n] measured pose */
+    const double *speed;             /* [n] speed of the current trim; |speed| < 0.01 = the vehicle stands */
+    const int32_t *trim;             /* [n] current trim, 1-based */
+    const int32_t *succ_ptr, *succ_idx;   /* CSR: coupled rows of lower priority (pdmpc_coupling_in) */
+    const int32_t *par_ptr, *par_idx;     /* CSR: coupled rows of higher priority that plan in parallel */
+    const int32_t *pred_ptr, *pred_idx;   /* CSR: sequential predecessors (pdmpc_timestep_deps) */
+    const int32_t *slot;             /* [n] closed-loop slot of the row (pdmpc_closed_loop_reset) */
+    double half_length, half_width;  /* Length/2 + offset, Width/2 + offset */
+    double dt_seconds;
+    int32_t checker;                 /* PDMPC_CHECKER_* */
+} pdmpc_timestep_states;
+int pdmpc_plan_timestep_from_states(pdmpc_handle *h, const pdmpc_timestep_states *states, pdmpc_batch_out *out);
+
 /* Pinned host buffers for callers that want full-rate host<->device copies. */
 int pdmpc_host_alloc(void **p, size_t bytes);
 int pdmpc_host_free(void *p);

@@ -30,7 +30,7 @@ PDMPC_ERR_ALLOC = 5
 
 EXPORTED_SYMBOLS = (
     "pdmpc_create", "pdmpc_destroy", "pdmpc_last_error", "pdmpc_abi_version",
-    "pdmpc_set_node_capacity", "pdmpc_set_variant", "pdmpc_set_tile_points", "pdmpc_set_cta_queue", "pdmpc_set_escalation", "pdmpc_get_hp", "pdmpc_pack_plan_rows", "pdmpc_upload_road", "pdmpc_sample_inputs", "pdmpc_upload_reachable_sets", "pdmpc_assemble_obstacles", "pdmpc_get_pipeline_timeline", "pdmpc_pipeline_bounds", "pdmpc_closed_loop_reset", "pdmpc_plan_timestep_closed_loop", "pdmpc_host_alloc", "pdmpc_host_free",
+    "pdmpc_set_node_capacity", "pdmpc_set_variant", "pdmpc_set_tile_points", "pdmpc_set_cta_queue", "pdmpc_set_escalation", "pdmpc_get_hp", "pdmpc_pack_plan_rows", "pdmpc_upload_road", "pdmpc_sample_inputs", "pdmpc_upload_reachable_sets", "pdmpc_assemble_obstacles", "pdmpc_get_pipeline_timeline", "pdmpc_pipeline_bounds", "pdmpc_plan_timestep_from_states", "pdmpc_closed_loop_reset", "pdmpc_plan_timestep_closed_loop", "pdmpc_host_alloc", "pdmpc_host_free",
     "pdmpc_trace_staged", "pdmpc_upload_mpa", "pdmpc_plan_batch", "pdmpc_stage_batch",
     "pdmpc_run_staged", "pdmpc_sync", "pdmpc_fetch_staged", "pdmpc_get_stats", "pdmpc_stream",
     "pdmpc_mcts_plan_batch", "pdmpc_mcts_run_staged", "pdmpc_set_cta_heap_smem", "pdmpc_plan_timestep",
@@ -105,6 +105,13 @@ class CouplingInC(C.Structure):
 class ObstaclesOutC(C.Structure):
     _fields_ = [("slot_ptr", _p_i32), ("poly_ptr", _p_i32), ("vert_x", _p_f64), ("vert_y", _p_f64),
                 ("poly_capacity", C.c_int32), ("vert_capacity", C.c_int32), ("n_polys", C.c_int32), ("n_verts", C.c_int32)]
+
+
+class TimestepStatesC(C.Structure):
+    _fields_ = [("n", C.c_int32), ("path_id", _p_i32), ("x", _p_f64), ("y", _p_f64), ("yaw", _p_f64), ("speed", _p_f64),
+                ("trim", _p_i32), ("succ_ptr", _p_i32), ("succ_idx", _p_i32), ("par_ptr", _p_i32), ("par_idx", _p_i32),
+                ("pred_ptr", _p_i32), ("pred_idx", _p_i32), ("slot", _p_i32),
+                ("half_length", C.c_double), ("half_width", C.c_double), ("dt_seconds", C.c_double), ("checker", C.c_int32)]
 
 
 MAX_PRED_LANELETS = 8
@@ -226,6 +233,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.pdmpc_get_pipeline_timeline.restype = C.c_int
     lib.pdmpc_pipeline_bounds.argtypes = [C.c_int32, C.c_int32, C.c_int32, _p_i32, C.POINTER(C.c_int32)]
     lib.pdmpc_pipeline_bounds.restype = C.c_int
+    lib.pdmpc_plan_timestep_from_states.argtypes = [H, C.POINTER(TimestepStatesC), C.POINTER(BatchOut)]
+    lib.pdmpc_plan_timestep_from_states.restype = C.c_int
     lib.pdmpc_closed_loop_reset.argtypes = [H, C.c_int32, C.c_double, C.c_double]
     lib.pdmpc_closed_loop_reset.restype = C.c_int
     lib.pdmpc_plan_timestep_closed_loop.argtypes = [H, C.POINTER(BatchIn), C.POINTER(TimestepDepsC), _p_i32,
@@ -510,6 +519,39 @@ class Planner:
         self._check(self.lib.pdmpc_plan_timestep_closed_loop(self.h, C.byref(bi), C.byref(d), _ptr(slot, _p_i32),
                                                              _ptr(still, C.POINTER(C.c_uint8)), C.byref(bo)))
         if raise_on_search_error and b.n and int(r.status.max()) != PDMPC_OK:
+            bad = int(np.flatnonzero(r.status != PDMPC_OK)[0])
+            raise PdmpcError(int(r.status[bad]), f"search {bad} failed")
+        return r
+
+    def plan_timestep_from_states(self, path_id, x, y, yaw, speed, trim, successors, parallel, predecessors, slot,
+                                  half_length: float, half_width: float, dt_seconds: float, checker: int,
+                                  raise_on_search_error: bool = True) -> BatchResult:
+        """One whole time step from the measured states (pdmpc_plan_timestep_from_states): inputs, obstacle assembly,
+        dependency-ordered searches and fallback plans chained on the device.  successors / parallel / predecessors:
+        per row a sequence of row indices.  Exhausted rows return their fallback plan."""
+        path_id, trim, slot = (np.ascontiguousarray(a, dtype=np.int32) for a in (path_id, trim, slot))
+        x, y, yaw, speed = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, yaw, speed))
+        n, Hp = int(x.size), int(self.lib.pdmpc_get_hp(self.h))
+
+        def csr(rows):
+            ptr = np.zeros(n + 1, dtype=np.int32)
+            for i in range(n):
+                ptr[i + 1] = ptr[i] + len(rows[i])
+            idx = np.ascontiguousarray(np.concatenate([np.asarray(r, dtype=np.int32) for r in rows] + [np.zeros(1, np.int32)]),
+                                       dtype=np.int32)
+            return ptr, idx
+
+        (sp, si), (pp, pi), (dp, di) = csr(successors), csr(parallel), csr(predecessors)
+        r = BatchResult.empty(n, Hp)
+        bo = batch_out(r)
+        st = TimestepStatesC(n=n, path_id=_ptr(path_id, _p_i32), x=_ptr(x, _p_f64), y=_ptr(y, _p_f64), yaw=_ptr(yaw, _p_f64),
+                             speed=_ptr(speed, _p_f64), trim=_ptr(trim, _p_i32), succ_ptr=_ptr(sp, _p_i32),
+                             succ_idx=_ptr(si, _p_i32), par_ptr=_ptr(pp, _p_i32), par_idx=_ptr(pi, _p_i32),
+                             pred_ptr=_ptr(dp, _p_i32), pred_idx=_ptr(di, _p_i32), slot=_ptr(slot, _p_i32),
+                             half_length=float(half_length), half_width=float(half_width), dt_seconds=float(dt_seconds),
+                             checker=int(checker))
+        self._check(self.lib.pdmpc_plan_timestep_from_states(self.h, C.byref(st), C.byref(bo)))
+        if raise_on_search_error and n and int(r.status.max()) != PDMPC_OK:
             bad = int(np.flatnonzero(r.status != PDMPC_OK)[0])
             raise PdmpcError(int(r.status[bad]), f"search {bad} failed")
         return r

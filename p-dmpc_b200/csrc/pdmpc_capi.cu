@@ -197,6 +197,7 @@ struct pdmpc_handle {
     bool has_road = false;
     RoadDev road{};
     bool has_reach = false;           // pdmpc_upload_reachable_sets
+    int reach_max_pts = 0;            // points of the largest uploaded reachable set
     ReachDev reach{};
     DBuf q_rptr, q_rx, q_ry, q_x, q_y, q_yaw, q_speed, q_trim, q_sptr, q_sidx, q_pptr, q_pidx, q_cs, q_cntp, q_cntv,
         q_slot, q_vbase, q_poly, q_vx, q_vy;
@@ -657,6 +658,55 @@ static int ensure_outputs(pdmpc_handle *h, int n) {
     return PDMPC_OK;
 }
 
+// The device side of staging: `dptr` = the fifteen batch arrays in device memory (order of pdmpc_stage_batch's `srcs`);
+// polylines of the InterX checker, output block.  Shared by the host-buffer path and pdmpc_plan_timestep_from_states.
+static int stage_finish(pdmpc_handle *h, int n, int checker, double dt, const void *const dptr[15], int np, int nv, int nl) {
+    int rc = PDMPC_OK;
+    BatchDev &b = h->batch;
+    b.n = n; b.checker = checker; b.dt = dt;
+    b.x0 = (const double *)dptr[0]; b.y0 = (const double *)dptr[1]; b.yaw0 = (const double *)dptr[2];
+    b.trim0 = (const int *)dptr[3];
+    b.ref_x = (const double *)dptr[4]; b.ref_y = (const double *)dptr[5]; b.v_ref = (const double *)dptr[6];
+    b.slot_ptr = (const int *)dptr[7]; b.poly_ptr = (const int *)dptr[8];
+    b.vert_x = (const double *)dptr[9]; b.vert_y = (const double *)dptr[10];
+    b.lane_ptr = (const int *)dptr[11]; b.lane_x = (const double *)dptr[12]; b.lane_y = (const double *)dptr[13];
+    b.order = n > 1 ? (const int *)dptr[14] : nullptr;
+    b.pl_x = b.pl_y = b.ll_x = b.ll_y = nullptr;
+    b.pl_xy = b.ll_xy = nullptr;
+    h->stats.kernel_launches = 0;
+    if (checker == PDMPC_CHECKER_INTERX) {
+        // NaN-separated polylines (vectorize_all_obstacles.m) built on the device
+        CU_TRY(h, h->b_plx.reserve(((size_t)nv + np + 1) * sizeof(double)));
+        CU_TRY(h, h->b_ply.reserve(((size_t)nv + np + 1) * sizeof(double)));
+        CU_TRY(h, h->b_llx.reserve(((size_t)nl + 2 * n + 1) * sizeof(double)));
+        CU_TRY(h, h->b_lly.reserve(((size_t)nl + 2 * n + 1) * sizeof(double)));
+        CU_TRY(h, h->b_plxy.reserve(((size_t)nv + np + 1) * sizeof(double2)));
+        CU_TRY(h, h->b_llxy.reserve(((size_t)nl + 2 * n + 1) * sizeof(double2)));
+        if (np) {
+            build_polyline_kernel<<<(np + 127) / 128, 128, 0, h->stream>>>(
+                np, b.poly_ptr, b.vert_x, b.vert_y, h->b_plx.as<double>(), h->b_ply.as<double>(), 0, h->b_plxy.as<double2>());
+            h->stats.kernel_launches++;
+        }
+        if (n) {
+            build_polyline_kernel<<<(2 * n + 127) / 128, 128, 0, h->stream>>>(
+                2 * n, b.lane_ptr, b.lane_x, b.lane_y, h->b_llx.as<double>(), h->b_lly.as<double>(), 0, h->b_llxy.as<double2>());
+            h->stats.kernel_launches++;
+        }
+        CU_TRY(h, cudaGetLastError());
+        b.pl_x = h->b_plx.as<double>(); b.pl_y = h->b_ply.as<double>();
+        b.ll_x = h->b_llx.as<double>(); b.ll_y = h->b_lly.as<double>();
+        b.pl_xy = h->b_plxy.as<double2>(); b.ll_xy = h->b_llxy.as<double2>();
+    }
+    h->n_polys = np; h->n_verts = nv; h->n_lane = nl;
+    rc = ensure_outputs(h, n);
+    if (rc != PDMPC_OK) return rc;
+    // (caller-owned source buffers were either copied into the pinned block or their copies
+    // have completed above: the caller may reuse them)
+    h->staged = true;
+    return PDMPC_OK;
+}
+
+
 int pdmpc_stage_batch(pdmpc_handle *h, const pdmpc_batch_in *in) {
     if (!h) return PDMPC_ERR_BAD_INPUT;
     if (!h->has_mpa) return fail(h, PDMPC_ERR_NO_MPA, "plan: call pdmpc_upload_mpa first");
@@ -742,48 +792,7 @@ int pdmpc_stage_batch(pdmpc_handle *h, const pdmpc_batch_in *in) {
     CU_TRY(h, cudaEventRecord(h->ev[1], h->stream));
     h->timing_pending_h2d = true;
 
-    BatchDev &b = h->batch;
-    b.n = n; b.checker = in->checker; b.dt = in->dt_seconds;
-    b.x0 = (const double *)dptr[0]; b.y0 = (const double *)dptr[1]; b.yaw0 = (const double *)dptr[2];
-    b.trim0 = (const int *)dptr[3];
-    b.ref_x = (const double *)dptr[4]; b.ref_y = (const double *)dptr[5]; b.v_ref = (const double *)dptr[6];
-    b.slot_ptr = (const int *)dptr[7]; b.poly_ptr = (const int *)dptr[8];
-    b.vert_x = (const double *)dptr[9]; b.vert_y = (const double *)dptr[10];
-    b.lane_ptr = (const int *)dptr[11]; b.lane_x = (const double *)dptr[12]; b.lane_y = (const double *)dptr[13];
-    b.order = n > 1 ? (const int *)dptr[14] : nullptr;
-    b.pl_x = b.pl_y = b.ll_x = b.ll_y = nullptr;
-    b.pl_xy = b.ll_xy = nullptr;
-    h->stats.kernel_launches = 0;
-    if (in->checker == PDMPC_CHECKER_INTERX) {
-        // NaN-separated polylines (vectorize_all_obstacles.m) built on the device
-        CU_TRY(h, h->b_plx.reserve(((size_t)nv + np + 1) * sizeof(double)));
-        CU_TRY(h, h->b_ply.reserve(((size_t)nv + np + 1) * sizeof(double)));
-        CU_TRY(h, h->b_llx.reserve(((size_t)nl + 2 * n + 1) * sizeof(double)));
-        CU_TRY(h, h->b_lly.reserve(((size_t)nl + 2 * n + 1) * sizeof(double)));
-        CU_TRY(h, h->b_plxy.reserve(((size_t)nv + np + 1) * sizeof(double2)));
-        CU_TRY(h, h->b_llxy.reserve(((size_t)nl + 2 * n + 1) * sizeof(double2)));
-        if (np) {
-            build_polyline_kernel<<<(np + 127) / 128, 128, 0, h->stream>>>(
-                np, b.poly_ptr, b.vert_x, b.vert_y, h->b_plx.as<double>(), h->b_ply.as<double>(), 0, h->b_plxy.as<double2>());
-            h->stats.kernel_launches++;
-        }
-        if (n) {
-            build_polyline_kernel<<<(2 * n + 127) / 128, 128, 0, h->stream>>>(
-                2 * n, b.lane_ptr, b.lane_x, b.lane_y, h->b_llx.as<double>(), h->b_lly.as<double>(), 0, h->b_llxy.as<double2>());
-            h->stats.kernel_launches++;
-        }
-        CU_TRY(h, cudaGetLastError());
-        b.pl_x = h->b_plx.as<double>(); b.pl_y = h->b_ply.as<double>();
-        b.ll_x = h->b_llx.as<double>(); b.ll_y = h->b_lly.as<double>();
-        b.pl_xy = h->b_plxy.as<double2>(); b.ll_xy = h->b_llxy.as<double2>();
-    }
-    h->n_polys = np; h->n_verts = nv; h->n_lane = nl;
-    rc = ensure_outputs(h, n);
-    if (rc != PDMPC_OK) return rc;
-    // (caller-owned source buffers were either copied into the pinned block or their copies
-    // have completed above: the caller may reuse them)
-    h->staged = true;
-    return PDMPC_OK;
+    return stage_finish(h, n, in->checker, in->dt_seconds, dptr, np, nv, nl);
 }
 
 static int ensure_arena(pdmpc_handle *h, int slots) {
@@ -1503,8 +1512,16 @@ int pdmpc_plan_batch(pdmpc_handle *h, const pdmpc_batch_in *in, pdmpc_batch_out 
 // One whole time step (or many) as ONE dependency-ordered launch: see include/pdmpc_b200.h.
 // slot / standstill != NULL: the closed-loop variant — fallback plans come from (and final plans go to) the state on
 // the device (pdmpc_fallback.cuh); deps->fb_* are then ignored.
+// `dev` != NULL: the batch is in device memory already (pdmpc_plan_timestep_from_states: dev->dptr = its fourteen arrays
+// in the order of pdmpc_stage_batch, totals = polygons, vertices, lanelet points); `in` then only carries n_searches,
+// checker and dt_seconds.
+struct DeviceBatch {
+    const void *dptr[14];
+    int np, nv, nl;
+};
 static int plan_timestep_impl(pdmpc_handle *h, const pdmpc_batch_in *in, const pdmpc_timestep_deps *deps,
-                              pdmpc_batch_out *out, const int32_t *slot, const uint8_t *standstill) {
+                              pdmpc_batch_out *out, const int32_t *slot, const uint8_t *standstill,
+                              const DeviceBatch *dev = nullptr) {
     if (!h) return PDMPC_ERR_BAD_INPUT;
     if (!h->has_mpa) return fail(h, PDMPC_ERR_NO_MPA, "plan_timestep: call pdmpc_upload_mpa first");
     if (!in || !deps || !deps->pred_ptr) return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep: NULL argument");
@@ -1570,9 +1587,25 @@ static int plan_timestep_impl(pdmpc_handle *h, const pdmpc_batch_in *in, const p
     if (in->checker == PDMPC_CHECKER_INTERX && h->max_area_npts >= PDMPC_AREA_STRIDE)
         return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep: the InterX hand-over keeps one NaN column after each planned area: "
                                             "maneuver areas must have at most PDMPC_AREA_STRIDE - 1 points");
-    h->topo_order.swap(order);
-    int rc = pdmpc_stage_batch(h, in);
-    h->topo_order.clear();
+    int rc;
+    if (dev) {
+        CU_TRY(h, cudaSetDevice(h->device));
+        h->staged = false;
+        h->deps_staged = false;
+        CU_TRY(h, cudaEventRecord(h->ev[0], h->stream));
+        UP(h, h->b_order, order.data(), n);      // the only array that still comes from the host
+        CU_TRY(h, cudaStreamSynchronize(h->stream));   // `order` is pageable
+        CU_TRY(h, cudaEventRecord(h->ev[1], h->stream));
+        h->timing_pending_h2d = true;
+        const void *dptr[15];
+        for (int i = 0; i < 14; ++i) dptr[i] = dev->dptr[i];
+        dptr[14] = h->b_order.p;
+        rc = stage_finish(h, n, in->checker, in->dt_seconds, dptr, dev->np, dev->nv, dev->nl);
+    } else {
+        h->topo_order.swap(order);
+        rc = pdmpc_stage_batch(h, in);
+        h->topo_order.clear();
+    }
     if (rc != PDMPC_OK) return rc;
     if (n == 0) {
         rc = pdmpc_run_staged(h);
@@ -1713,6 +1746,76 @@ int pdmpc_plan_timestep_closed_loop(pdmpc_handle *h, const pdmpc_batch_in *in, c
         }
     }
     return plan_timestep_impl(h, in, deps, out, slot, standstill);
+}
+
+static int run_sample_inputs(pdmpc_handle *h, int n, const int32_t *path_id, const double *x, const double *y,
+                             const double *speed, double dt_seconds, int lane_capacity);
+static int run_assemble_obstacles(pdmpc_handle *h, const pdmpc_coupling_in *in, int poly_capacity, int vert_capacity, int totals[2]);
+
+// One whole time step from the vehicles' measured states: inputs (pdmpc_inputs.cuh), obstacles that do not depend on this
+// step's plans (pdmpc_obstacles.cuh), dependency-ordered searches, fallback plans (pdmpc_fallback.cuh) — nothing of the
+// batch passes through the host.
+int pdmpc_plan_timestep_from_states(pdmpc_handle *h, const pdmpc_timestep_states *st, pdmpc_batch_out *out) {
+    if (!h) return PDMPC_ERR_BAD_INPUT;
+    if (!h->has_mpa) return fail(h, PDMPC_ERR_NO_MPA, "plan_timestep_from_states: call pdmpc_upload_mpa first");
+    if (!h->has_road) return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep_from_states: call pdmpc_upload_road first");
+    if (h->cl.n_slots < 1 || h->cl.Hp != h->mpa.Hp)
+        return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep_from_states: call pdmpc_closed_loop_reset first (after pdmpc_upload_mpa)");
+    if (!st || !out || st->n < 0 || !out->status || !out->is_exhausted || !out->trims || !out->y_predicted || !out->shape_npts ||
+        !out->shape_x || !out->shape_y)
+        return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep_from_states: states and the plan outputs are required");
+    const int n = st->n, Hp = h->mpa.Hp;
+    if (n == 0) return PDMPC_OK;
+    if (!st->path_id || !st->x || !st->y || !st->yaw || !st->speed || !st->trim || !st->succ_ptr || !st->par_ptr || !st->pred_ptr ||
+        !st->slot)
+        return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep_from_states: NULL argument");
+    if (st->checker != PDMPC_CHECKER_INTERX && st->checker != PDMPC_CHECKER_SAT)
+        return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep_from_states: unknown checker");
+    std::vector<uint8_t> still((size_t)n);
+    {
+        std::vector<char> seen((size_t)h->cl.n_slots, 0);
+        for (int i = 0; i < n; ++i) {
+            if (st->path_id[i] < 0 || st->path_id[i] >= h->road.n_paths)
+                return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep_from_states: path_id out of range");
+            if (st->slot[i] < 0 || st->slot[i] >= h->cl.n_slots || seen[st->slot[i]])
+                return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep_from_states: slots must be distinct and below n_slots");
+            seen[st->slot[i]] = 1;
+            still[i] = fabs(st->speed[i]) < kStandstillSpeed ? 1 : 0;   // PrioritizedController.m:580 / :527
+        }
+    }
+    // ---- inputs and obstacles on the device; capacities from the relations -----------------------------------------
+    const int lane_cap = 512 * n;
+    int rc = run_sample_inputs(h, n, st->path_id, st->x, st->y, st->speed, st->dt_seconds, lane_cap);
+    if (rc != PDMPC_OK) return rc;
+    pdmpc_coupling_in ci;
+    memset(&ci, 0, sizeof(ci));
+    ci.n = n; ci.x = st->x; ci.y = st->y; ci.yaw = st->yaw; ci.speed = st->speed; ci.trim = st->trim;
+    ci.succ_ptr = st->succ_ptr; ci.succ_idx = st->succ_idx; ci.par_ptr = st->par_ptr; ci.par_idx = st->par_idx;
+    ci.half_length = st->half_length; ci.half_width = st->half_width;
+    if (st->succ_ptr[0] != 0 || st->par_ptr[0] != 0 || st->succ_ptr[n] < 0 || st->par_ptr[n] < 0)
+        return fail(h, PDMPC_ERR_BAD_INPUT, "plan_timestep_from_states: malformed relation");
+    const long long poly_cap = (long long)st->succ_ptr[n] + (long long)Hp * st->par_ptr[n];
+    const long long vert_cap = 5LL * st->succ_ptr[n] + (long long)Hp * st->par_ptr[n] * std::max(h->reach_max_pts, 1);
+    if (poly_cap > 0x3fffffff || vert_cap > 0x3fffffff) return fail(h, PDMPC_ERR_CAPACITY, "plan_timestep_from_states: too many obstacles");
+    int totals[2] = {0, 0}, nl = 0;
+    rc = run_assemble_obstacles(h, &ci, (int)poly_cap, (int)vert_cap, totals);
+    if (rc != PDMPC_OK) return rc;
+    CU_TRY(h, cudaMemcpyAsync(&nl, h->i_lptr.as<int>() + 2 * n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    if (nl > lane_cap) return fail(h, PDMPC_ERR_CAPACITY, "plan_timestep_from_states: the lanelet bounds need more than 512 points per vehicle");
+    if (totals[0] > poly_cap || totals[1] > vert_cap) return fail(h, PDMPC_ERR_CAPACITY, "plan_timestep_from_states: obstacle capacity");
+    DeviceBatch dev;
+    const void *d[14] = {h->q_x.p, h->q_y.p, h->q_yaw.p, h->q_trim.p, h->i_refx.p, h->i_refy.p, h->i_vref.p,
+                         h->q_slot.p, h->q_poly.p, h->q_vx.p, h->q_vy.p, h->i_lptr.p, h->i_lx.p, h->i_ly.p};
+    for (int i = 0; i < 14; ++i) dev.dptr[i] = d[i];
+    dev.np = totals[0]; dev.nv = totals[1]; dev.nl = nl;
+    pdmpc_batch_in stub;
+    memset(&stub, 0, sizeof(stub));
+    stub.n_searches = n; stub.checker = st->checker; stub.dt_seconds = st->dt_seconds;
+    pdmpc_timestep_deps deps;
+    memset(&deps, 0, sizeof(deps));
+    deps.pred_ptr = st->pred_ptr; deps.pred_idx = st->pred_idx;
+    return plan_timestep_impl(h, &stub, &deps, out, st->slot, still.data(), &dev);
 }
 
 // Centralized (joint) search: rows = searches x n_vehicles (pdmpc_joint.cuh).
@@ -1925,20 +2028,9 @@ int pdmpc_upload_road(pdmpc_handle *h, const pdmpc_road_desc *r) {
     return PDMPC_OK;
 }
 
-int pdmpc_sample_inputs(pdmpc_handle *h, int32_t n, const int32_t *path_id, const double *x, const double *y,
-                        const double *speed, double dt_seconds, pdmpc_inputs_out *out) {
-    if (!h) return PDMPC_ERR_BAD_INPUT;
-    if (!h->has_mpa) return fail(h, PDMPC_ERR_NO_MPA, "sample_inputs: call pdmpc_upload_mpa first (Hp)");
-    if (!h->has_road) return fail(h, PDMPC_ERR_BAD_INPUT, "sample_inputs: call pdmpc_upload_road first");
-    if (n < 0 || !out || (n && (!path_id || !x || !y || !speed)) || out->lane_capacity < 0)
-        return fail(h, PDMPC_ERR_BAD_INPUT, "sample_inputs: NULL argument");
-    for (int i = 0; i < n; ++i)
-        if (path_id[i] < 0 || path_id[i] >= h->road.n_paths)
-            return fail(h, PDMPC_ERR_BAD_INPUT, "sample_inputs: path_id out of range");
-    if (n == 0) {
-        if (out->lane_ptr) out->lane_ptr[0] = 0;
-        return PDMPC_OK;
-    }
+// The device side of pdmpc_sample_inputs: uploads the rows, runs the three kernels; results stay in the handle's i_* buffers.
+static int run_sample_inputs(pdmpc_handle *h, int n, const int32_t *path_id, const double *x, const double *y,
+                             const double *speed, double dt_seconds, int lane_capacity) {
     CU_TRY(h, cudaSetDevice(h->device));
     const int Hp = h->mpa.Hp;
     const size_t nh = (size_t)n * Hp;
@@ -1958,8 +2050,8 @@ int pdmpc_sample_inputs(pdmpc_handle *h, int32_t n, const int32_t *path_id, cons
     CU_TRY(h, h->i_pre.reserve((size_t)n * sizeof(int)));
     CU_TRY(h, h->i_cnt.reserve((size_t)2 * n * sizeof(int)));
     CU_TRY(h, h->i_lptr.reserve(((size_t)2 * n + 1) * sizeof(int)));
-    CU_TRY(h, h->i_lx.reserve(std::max<size_t>(out->lane_capacity, 1) * sizeof(double)));
-    CU_TRY(h, h->i_ly.reserve(std::max<size_t>(out->lane_capacity, 1) * sizeof(double)));
+    CU_TRY(h, h->i_lx.reserve(std::max<size_t>(lane_capacity, 1) * sizeof(double)));
+    CU_TRY(h, h->i_ly.reserve(std::max<size_t>(lane_capacity, 1) * sizeof(double)));
     InputsDev in;
     in.n = n; in.Hp = Hp; in.dt = dt_seconds;
     in.path_id = h->i_pid.as<int>(); in.x = h->i_x.as<double>(); in.y = h->i_y.as<double>(); in.speed = h->i_speed.as<double>();
@@ -1971,13 +2063,35 @@ int pdmpc_sample_inputs(pdmpc_handle *h, int32_t n, const int32_t *path_id, cons
     CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
     sample_inputs_kernel<<<blocks, 128, 0, h->stream>>>(h->road, in);
     scan_counts_kernel<<<1, 1024, 0, h->stream>>>(in.lane_cnt, in.lane_ptr, 2 * n);
-    copy_bounds_kernel<<<blocks, 128, 0, h->stream>>>(h->road, in, out->lane_capacity);
+    copy_bounds_kernel<<<blocks, 128, 0, h->stream>>>(h->road, in, lane_capacity);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
     h->timing_pending_kernel = true;
     h->stats.kernel_launches = 3;
+    return PDMPC_OK;
+}
+
+int pdmpc_sample_inputs(pdmpc_handle *h, int32_t n, const int32_t *path_id, const double *x, const double *y,
+                        const double *speed, double dt_seconds, pdmpc_inputs_out *out) {
+    if (!h) return PDMPC_ERR_BAD_INPUT;
+    if (!h->has_mpa) return fail(h, PDMPC_ERR_NO_MPA, "sample_inputs: call pdmpc_upload_mpa first (Hp)");
+    if (!h->has_road) return fail(h, PDMPC_ERR_BAD_INPUT, "sample_inputs: call pdmpc_upload_road first");
+    if (n < 0 || !out || (n && (!path_id || !x || !y || !speed)) || out->lane_capacity < 0)
+        return fail(h, PDMPC_ERR_BAD_INPUT, "sample_inputs: NULL argument");
+    for (int i = 0; i < n; ++i)
+        if (path_id[i] < 0 || path_id[i] >= h->road.n_paths)
+            return fail(h, PDMPC_ERR_BAD_INPUT, "sample_inputs: path_id out of range");
+    if (n == 0) {
+        if (out->lane_ptr) out->lane_ptr[0] = 0;
+        return PDMPC_OK;
+    }
+    int rc_run = run_sample_inputs(h, n, path_id, x, y, speed, dt_seconds, out->lane_capacity);
+    if (rc_run != PDMPC_OK) return rc_run;
+    const int Hp = h->mpa.Hp;
+    const size_t nh = (size_t)n * Hp;
+    const int *d_lane_ptr = h->i_lptr.as<int>();
     int total = 0;
-    CU_TRY(h, cudaMemcpyAsync(&total, in.lane_ptr + 2 * n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(&total, d_lane_ptr + 2 * n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     DOWN(h, out->ref_x, h->i_refx, nh);
     DOWN(h, out->ref_y, h->i_refy, nh);
     DOWN(h, out->v_ref, h->i_vref, nh);
@@ -2016,23 +2130,17 @@ int pdmpc_upload_reachable_sets(pdmpc_handle *h, const pdmpc_reach_desc *r) {
     UP(h, h->q_ry, r->y, r->ptr[m]);
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     h->reach.nT = r->n_trims; h->reach.Hp = r->Hp;
+    h->reach_max_pts = 0;
+    for (int i = 0; i < m; ++i) h->reach_max_pts = std::max(h->reach_max_pts, r->ptr[i + 1] - r->ptr[i]);
     h->reach.ptr = h->q_rptr.as<int>(); h->reach.x = h->q_rx.as<double>(); h->reach.y = h->q_ry.as<double>();
     h->has_reach = true;
     return PDMPC_OK;
 }
 
-int pdmpc_assemble_obstacles(pdmpc_handle *h, const pdmpc_coupling_in *in, pdmpc_obstacles_out *out) {
-    if (!h) return PDMPC_ERR_BAD_INPUT;
-    if (!h->has_mpa) return fail(h, PDMPC_ERR_NO_MPA, "assemble_obstacles: call pdmpc_upload_mpa first (Hp)");
-    if (!in || !out || in->n < 0 || out->poly_capacity < 0 || out->vert_capacity < 0 || !out->slot_ptr ||
-        (in->n && (!in->x || !in->y || !in->yaw || !in->speed || !in->trim || !in->succ_ptr || !in->par_ptr)))
-        return fail(h, PDMPC_ERR_BAD_INPUT, "assemble_obstacles: NULL argument");
+// Validation + the device side of pdmpc_assemble_obstacles; results stay in the handle's q_* buffers, the totals
+// (polygons, vertices) come back in totals[2].
+static int run_assemble_obstacles(pdmpc_handle *h, const pdmpc_coupling_in *in, int poly_capacity, int vert_capacity, int totals[2]) {
     const int n = in->n, Hp = h->mpa.Hp;
-    if (n == 0) {
-        out->slot_ptr[0] = 0;
-        if (out->poly_ptr) out->poly_ptr[0] = 0;
-        return PDMPC_OK;
-    }
     if (in->succ_ptr[0] != 0 || in->par_ptr[0] != 0) return fail(h, PDMPC_ERR_BAD_INPUT, "assemble_obstacles: CSR must start at 0");
     for (int i = 0; i < n; ++i)
         if (in->succ_ptr[i + 1] < in->succ_ptr[i] || in->par_ptr[i + 1] < in->par_ptr[i])
@@ -2052,8 +2160,6 @@ int pdmpc_assemble_obstacles(pdmpc_handle *h, const pdmpc_coupling_in *in, pdmpc
         if (in->trim[i] < 1 || in->trim[i] > h->mpa.nT) return fail(h, PDMPC_ERR_BAD_INPUT, "assemble_obstacles: trim out of range");
     CU_TRY(h, cudaSetDevice(h->device));
     const int S = n * (Hp + 1);
-    h->stats.h2d_bytes = 0;
-    h->stats.d2h_bytes = 0;
     UP(h, h->q_x, in->x, n);
     UP(h, h->q_y, in->y, n);
     UP(h, h->q_yaw, in->yaw, n);
@@ -2068,9 +2174,9 @@ int pdmpc_assemble_obstacles(pdmpc_handle *h, const pdmpc_coupling_in *in, pdmpc
     CU_TRY(h, h->q_cntv.reserve((size_t)S * sizeof(int)));
     CU_TRY(h, h->q_slot.reserve(((size_t)S + 1) * sizeof(int)));
     CU_TRY(h, h->q_vbase.reserve(((size_t)S + 1) * sizeof(int)));
-    CU_TRY(h, h->q_poly.reserve(((size_t)out->poly_capacity + 1) * sizeof(int)));
-    CU_TRY(h, h->q_vx.reserve(std::max<size_t>(out->vert_capacity, 1) * sizeof(double)));
-    CU_TRY(h, h->q_vy.reserve(std::max<size_t>(out->vert_capacity, 1) * sizeof(double)));
+    CU_TRY(h, h->q_poly.reserve(((size_t)poly_capacity + 1) * sizeof(int)));
+    CU_TRY(h, h->q_vx.reserve(std::max<size_t>(vert_capacity, 1) * sizeof(double)));
+    CU_TRY(h, h->q_vy.reserve(std::max<size_t>(vert_capacity, 1) * sizeof(double)));
     CouplingDev c;
     c.n = n; c.Hp = Hp;
     c.x = h->q_x.as<double>(); c.y = h->q_y.as<double>(); c.yaw = h->q_yaw.as<double>(); c.speed = h->q_speed.as<double>();
@@ -2082,18 +2188,38 @@ int pdmpc_assemble_obstacles(pdmpc_handle *h, const pdmpc_coupling_in *in, pdmpc
     c.cnt_poly = h->q_cntp.as<int>(); c.cnt_vert = h->q_cntv.as<int>();
     c.slot_ptr = h->q_slot.as<int>(); c.vert_base = h->q_vbase.as<int>();
     c.poly_ptr = h->q_poly.as<int>(); c.vert_x = h->q_vx.as<double>(); c.vert_y = h->q_vy.as<double>();
-    CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
     count_obstacles_kernel<<<(S + 127) / 128, 128, 0, h->stream>>>(h->reach, c);
     scan_counts_kernel<<<1, 1024, 0, h->stream>>>(c.cnt_poly, c.slot_ptr, S);
     scan_counts_kernel<<<1, 1024, 0, h->stream>>>(c.cnt_vert, c.vert_base, S);
-    fill_obstacles_kernel<<<(S + 3) / 4, 128, 0, h->stream>>>(h->reach, c, out->poly_capacity, out->vert_capacity);
+    fill_obstacles_kernel<<<(S + 3) / 4, 128, 0, h->stream>>>(h->reach, c, poly_capacity, vert_capacity);
     CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaMemcpyAsync(&totals[0], c.slot_ptr + S, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(&totals[1], c.vert_base + S, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    return PDMPC_OK;
+}
+
+int pdmpc_assemble_obstacles(pdmpc_handle *h, const pdmpc_coupling_in *in, pdmpc_obstacles_out *out) {
+    if (!h) return PDMPC_ERR_BAD_INPUT;
+    if (!h->has_mpa) return fail(h, PDMPC_ERR_NO_MPA, "assemble_obstacles: call pdmpc_upload_mpa first (Hp)");
+    if (!in || !out || in->n < 0 || out->poly_capacity < 0 || out->vert_capacity < 0 || !out->slot_ptr ||
+        (in->n && (!in->x || !in->y || !in->yaw || !in->speed || !in->trim || !in->succ_ptr || !in->par_ptr)))
+        return fail(h, PDMPC_ERR_BAD_INPUT, "assemble_obstacles: NULL argument");
+    const int n = in->n, Hp = h->mpa.Hp;
+    if (n == 0) {
+        out->slot_ptr[0] = 0;
+        if (out->poly_ptr) out->poly_ptr[0] = 0;
+        return PDMPC_OK;
+    }
+    const int S = n * (Hp + 1);
+    h->stats.h2d_bytes = 0;
+    h->stats.d2h_bytes = 0;
+    CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
+    int totals[2] = {0, 0};
+    int rc = run_assemble_obstacles(h, in, out->poly_capacity, out->vert_capacity, totals);
+    if (rc != PDMPC_OK) return rc;
     CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
     h->timing_pending_kernel = true;
     h->stats.kernel_launches = 4;
-    int totals[2] = {0, 0};
-    CU_TRY(h, cudaMemcpyAsync(&totals[0], c.slot_ptr + S, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(h, cudaMemcpyAsync(&totals[1], c.vert_base + S, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     DOWN(h, out->slot_ptr, h->q_slot, (size_t)S + 1);
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     out->n_polys = totals[0];

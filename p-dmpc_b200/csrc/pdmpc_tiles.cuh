@@ -349,9 +349,9 @@ search_tile_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_c
             }
         }
         if (has) {
-            ca = na[id];
-            ccs = ncs[id];
-            if (cK < Hp) {
+            if (cK < Hp) {                                // own record and successor list: only an expansion reads them
+                ca = na[id];
+                ccs = ncs[id];
                 const int q = cK * nT + (ctrim - 1);      // step k_exp = cK + 1
                 sbase = __ldg(m.succ_ptr + q);
                 send = __ldg(m.succ_ptr + q + 1);
@@ -577,11 +577,13 @@ search_tile_kernel(MpaDev m, BatchDev b, OutDev o, ArenaDev ar, unsigned *work_c
                 NodeB eb;
                 eb.h = eh; eb.parent = id; eb.edge = (unsigned short)cedge;
                 eb.trim = (unsigned char)t2; eb.k = (unsigned char)k_exp;
-                NodeCS ecs;                                 // for the child's own expansion
-                sincos_ref(ea.yaw, ecs.s, ecs.c);
                 na[nid] = ea;                               // Tree.m:54-70 add_nodes
                 nb[nid] = eb;
-                ncs[nid] = ecs;
+                if (k_exp < Hp) {                           // cos/sin of the child's yaw: for ITS expansion and for placing
+                    NodeCS ecs;                             // its children's areas — a node of depth Hp has neither
+                    sincos_ref(ea.yaw, ecs.s, ecs.c);
+                    ncs[nid] = ecs;
+                }
                 he.f = ea.g + eh;                           // GraphSearch.m:102 (weights 1)
                 he.w = HEnt::pack(nid, id, (unsigned)cedge, (unsigned)k_exp, (unsigned)t2);
             }

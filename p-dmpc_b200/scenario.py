@@ -670,7 +670,7 @@ class ScenarioRunner:
     PrioritizedSequentialController.m:83-92)."""
 
     def __init__(self, sc: Scenario, plan_fn: PlanFn, max_num_CLs: int = 99, timestep_fn=None, inputs_fn=None,
-                 path_id0: int = 0, closed_loop_fn=None, obstacles_fn=None):
+                 path_id0: int = 0, closed_loop_fn=None, obstacles_fn=None, states_fn=None):
         """plan_fn(batch) plans one computation level; with timestep_fn(batch, deps) the whole time
         step is ONE call and the predecessors' areas are handed over behind it (pdmpc_plan_timestep).
         inputs_fn(path_id, x, y, speed, dt) -> dict (capi.Planner.sample_inputs): reference trajectories and lanelet
@@ -685,6 +685,11 @@ class ScenarioRunner:
         # (capi.Planner.assemble_obstacles): the standstill areas of successors and the reachable sets of parallel
         # predecessors of all vehicles are placed on the device in one call per time step (one-call path)
         self.obstacles_fn = obstacles_fn
+        # states_fn(path_id, x, y, yaw, speed, trim, successors, parallel, predecessors, slot, half_length, half_width, dt,
+        # checker) -> BatchResult with the FINAL plan of every vehicle (capi.Planner.plan_timestep_from_states): inputs,
+        # obstacle assembly, planning and fallback plans of a time step in ONE call; the host only decides coupling and
+        # priorities
+        self.states_fn = states_fn
         # closed_loop_fn(batch, deps, slot, standstill) -> BatchResult with the FINAL plan of every vehicle
         # (capi.Planner.plan_timestep_closed_loop): fallback plans are built and kept on the device, slot = path_id0 + i
         self.closed_loop_fn = closed_loop_fn
@@ -789,6 +794,20 @@ class ScenarioRunner:
         sc, mpa = self.sc, self.mpa
         n, Hp = sc.amount, mpa.Hp
         self.k += 1
+        if self.states_fn is not None:
+            A = couple(sc, self.pose)
+            D = (constant_priorities(A) if sc.priority == "constant" else coloring_priorities(A)).astype(bool)
+            seq = limit_computation_levels(D, self.max_num_CLs) if self.max_num_CLs < n else D
+            speed = np.array([mpa.trim_speed[self.trim[i] - 1] for i in range(n)], dtype=np.float64)
+            ids = self.path_id0 + np.arange(n)
+            res = self.states_fn(ids, self.pose[:, 0], self.pose[:, 1], self.pose[:, 2], speed, self.trim,
+                                 [np.flatnonzero(D[i, :]) for i in range(n)],
+                                 [np.flatnonzero(D[:, i] & ~seq[:, i]) for i in range(n)],
+                                 [np.flatnonzero(seq[:, i]) for i in range(n)], ids,
+                                 VEH_LENGTH / 2 + 0.01, VEH_WIDTH / 2 + 0.01, mpa.dt_seconds, sc.checker)
+            self.apply_final(res)
+            self.timestep_records.append((self.k, None, None, res))
+            return res
         iters, preds, fallbacks = self.timestep_inputs()
         batch = SearchBatch.from_iters(iters, Hp, sc.checker, mpa.dt_seconds)
         if self.closed_loop_fn is not None:
@@ -836,7 +855,7 @@ class ScenarioRunner:
         self.pose, self.trim = new_pose, new_trim
 
     def step(self) -> List[StepRecord]:
-        if self.timestep_fn is not None or self.closed_loop_fn is not None:
+        if self.timestep_fn is not None or self.closed_loop_fn is not None or self.states_fn is not None:
             self.step_timestep()
             return []
         sc, mpa = self.sc, self.mpa

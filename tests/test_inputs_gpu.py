@@ -222,3 +222,43 @@ def test_assemble_obstacles_errors_and_empty_rows(planner):
         bad = [[a.copy() for a in row] for row in sets]
         bad[0][0] = bad[0][0][:, :-1]
         planner.upload_reachable_sets(bad)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("amount,max_cls,seed", [(20, 99, 7), (40, 2, 3)])
+def test_whole_time_step_from_states_in_one_call(planner, amount, max_cls, seed):
+    """pdmpc_plan_timestep_from_states: inputs, obstacle assembly, dependency-ordered planning and fallback plans of a
+    time step chained on the device (the host only decides coupling and priorities) drive the same closed loop as the
+    three separate device calls and as the host functions + oracle; every row of every step equals the separate calls."""
+    mpa = get_mpa("triple_speed", non_convex=True)
+    planner.upload_mpa(mpa)
+    mk = lambda: scenario.commonroad_scenario(mpa, amount, seed=seed, allow_shared_paths=amount > 33)
+    sc = mk()
+    planner.upload_road(scenario.road_tables([sc]))
+    planner.upload_reachable_sets(scenario.local_reachable_sets_conv(mpa))
+    hl, hw = scenario.VEH_LENGTH / 2 + 0.01, scenario.VEH_WIDTH / 2 + 0.01
+    # (a) one call per time step
+    planner.closed_loop_reset(amount, hl, hw)
+    one = scenario.ScenarioRunner(sc, None, max_num_CLs=max_cls,
+                                  states_fn=lambda *a: planner.plan_timestep_from_states(*a, raise_on_search_error=False))
+    res_one = [one.step_timestep() for _ in range(7)]
+    poses_one, trims_one = one.pose.copy(), one.trim.copy()
+    # (b) the three separate device calls (own closed-loop state: reset)
+    planner.closed_loop_reset(amount, hl, hw)
+    sep = scenario.ScenarioRunner(mk(), None, max_num_CLs=max_cls, inputs_fn=planner.sample_inputs,
+                                  obstacles_fn=planner.assemble_obstacles,
+                                  closed_loop_fn=lambda b, d, s, st: planner.plan_timestep_closed_loop(b, d, s, st, False))
+    for k in range(7):
+        got = sep.step_timestep()
+        parity.compare(res_one[k], got)
+    assert np.array_equal(poses_one.view(np.uint64), sep.pose.view(np.uint64)) and np.array_equal(trims_one, sep.trim)
+    assert one.n_fallbacks == sep.n_fallbacks
+    # (c) host functions + oracle, level by level
+    ref = scenario.ScenarioRunner(mk(), lambda b: oracle_py.plan_batch(mpa, b, 4), max_num_CLs=max_cls) if max_cls >= amount else None
+    if ref is not None:
+        for _ in range(7):
+            ref.step()
+        assert np.array_equal(poses_one.view(np.uint64), ref.pose.view(np.uint64)) and np.array_equal(trims_one, ref.trim)
+    with pytest.raises(capi.PdmpcError):     # slots must be distinct
+        planner.plan_timestep_from_states([0, 1], [1.0, 2.0], [1.0, 2.0], [0.0, 0.0], [0.0, 0.0], [1, 1], [[], []], [[], []],
+                                          [[], []], [3, 3], hl, hw, mpa.dt_seconds, sc.checker)
