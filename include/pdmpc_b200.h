@@ -245,8 +245,8 @@ int pdmpc_set_cta_heap_smem(pdmpc_handle *h, int32_t entries);
 int pdmpc_set_pipeline_chunks(pdmpc_handle *h, int32_t chunks);
 
 /* The chunk boundaries pdmpc_plan_batch uses for a batch of n_searches (host-only, needs no device): chunk c = searches
- * [bounds[c], bounds[c+1]).  chunks = 0: the automatic schedule (sizes double from ~24 000 searches up to
- * max(192 000, n/12)); chunks = 2..16: what pdmpc_set_pipeline_chunks(chunks) gives (equal sizes, the first one half).
+ * [bounds[c], bounds[c+1]).  chunks = 0: the default (~60 000 searches per chunk, 2..12 chunks); chunks = 2..16: what
+ * pdmpc_set_pipeline_chunks(chunks) gives.  Chunks are of equal size, the first one half of that.
  * bounds: cap >= *n_chunks + 1 entries (PDMPC_ERR_CAPACITY otherwise, *n_chunks is still set). */
 int pdmpc_pipeline_bounds(int32_t n_searches, int32_t chunks, int32_t cap, int32_t *bounds, int32_t *n_chunks);
 

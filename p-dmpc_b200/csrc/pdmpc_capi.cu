@@ -1144,32 +1144,20 @@ static int pipeline_sync_all(pdmpc_handle *h) {
     return e == cudaSuccess ? PDMPC_OK : fail(h, PDMPC_ERR_CUDA, std::string("pipeline sync: ") + cudaGetErrorString(e));
 }
 
-// Chunk boundaries of the pipeline: bnd[c] .. bnd[c + 1] are the searches of chunk c.
-//   C_req > 1 (pdmpc_set_pipeline_chunks): C_req chunks of equal size, the first one half of that.
-//   C_req == 0: sizes double from ~24 k searches up to max(192 k, n / 12) — nothing overlaps the first chunk's validation and
-//   copy, so it is small; every chunk boundary costs (a chunk kernel's one-warp CTAs leave only when both of their searches
-//   are over), so there are few; the last chunk's results come back behind the escalated searches, so it must not be
-//   huge.  Measured at 358 400 records (profiles/r02k_pipeline_timeline.txt): 86.8 ms with 5 chunks of 40 k + 4 x 80 k,
-//   83.4 ms with 24 k / 48 k / 96 k / 191 k.
+// Chunk boundaries of the pipeline: bnd[c] .. bnd[c + 1] are the searches of chunk c.  C chunks of equal size, the first
+// one half of that (nothing overlaps the first chunk's validation and copy); C = C_req (pdmpc_set_pipeline_chunks) or, by
+// default, ~60 k searches per chunk (at most 12 chunks).
+// Measured and NOT the default (profiles/r02k_pipeline_timeline.txt): sizes doubling from 24 k searches (24 k / 48 k / 96 k /
+// 190 k at 358 400 records) are 4 % faster on ONE GPU (83.1 against 86.8 ms per call) and 17 % SLOWER when eight processes
+// share one host (25.4 M against 30.7 M plans/s end to end on 8 GPUs): the copies of the large last chunk run at a
+// fraction of the bandwidth then, its results come back exposed behind the last searches.
 static std::vector<int> pipeline_bounds(int n, int C_req) {
+    const int C = C_req > 1 ? C_req : std::min(12, std::max(2, n / 60000));
+    constexpr double first_frac = 0.5;
     std::vector<int> bnd(1, 0);
-    if (C_req > 1) {
-        constexpr double first_frac = 0.5;
-        for (int c = 1; c < C_req; ++c)
-            bnd.push_back(C_req < 3 ? (int)((long long)n * c / C_req)
-                                    : (int)((double)n * ((double)(c - 1) + first_frac) / ((double)(C_req - 1) + first_frac)));
-        bnd.push_back(n);
-        return bnd;
-    }
-    const int smax = std::max(192000, n / 12);
-    int size = std::max(16384, std::min(24000, n / 2));
-    while (bnd.back() + size < n && (int)bnd.size() < kPipelineMaxChunks) {
-        bnd.push_back(bnd.back() + size);
-        size = std::min(2 * size, smax);
-    }
-    // a short remainder joins the chunk before it
-    if (bnd.size() > 2 && n - bnd.back() < (bnd.back() - bnd[bnd.size() - 2]) / 2) bnd.pop_back();
-    if (bnd.size() == 1 && n >= 2) bnd.push_back(n / 2);   // at least two chunks
+    for (int c = 1; c < C; ++c)
+        bnd.push_back(C < 3 ? (int)((long long)n * c / C)
+                            : (int)((double)n * ((double)(c - 1) + first_frac) / ((double)(C - 1) + first_frac)));
     bnd.push_back(n);
     return bnd;
 }

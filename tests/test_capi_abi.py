@@ -89,22 +89,21 @@ def test_product_never_imports_the_oracle():
 
 def test_pipeline_chunk_schedule_host_side():
     """pdmpc_pipeline_bounds (host-only): the chunks of the copy/search pipeline cover the batch exactly, in order, in
-    at most 16 chunks; the automatic schedule starts small, doubles, and never ends in a sliver."""
+    at most 16 chunks; the default is ~60 000 searches per chunk with a first chunk of half the size."""
     from pdmpc_b200 import capi
     import numpy as np
-    for n in (2, 3, 1000, 16384, 16385, 20000, 47999, 56000, 168000, 179200, 358400, 716800, 2867200, 10_000_000):
+    for n in (4, 1000, 16384, 16385, 20000, 47999, 56000, 168000, 179200, 358400, 716800, 2867200, 10_000_000):
         b = capi.pipeline_bounds(n)
         sizes = np.diff(b)
-        assert b[0] == 0 and b[-1] == n and (sizes > 0).all() and 2 <= sizes.size <= 16, (n, b)
-        if n >= 100000:
-            assert sizes[0] <= 24000 and (sizes[1:-1] >= sizes[:-2]).all(), (n, sizes)      # small first chunk, growing
-            assert sizes[-1] >= sizes[-2] // 2, (n, sizes)                                   # no sliver at the end
-            assert sizes.max() <= max(192000, n // 12) * 3 // 2 + 1 or sizes.size == 16, (n, sizes)
+        assert b[0] == 0 and b[-1] == n and (sizes > 0).all() and 2 <= sizes.size <= 12, (n, b)
+        assert sizes.size == min(12, max(2, n // 60000)), (n, sizes)
+        if sizes.size >= 3:
+            assert abs(int(sizes[0]) * 2 - int(sizes[1])) <= 2 and int(sizes[1:].max()) - int(sizes[1:].min()) <= 2, (n, sizes)
         for c in (2, 3, 5, 16):
             if n >= 2 * c:
                 e = capi.pipeline_bounds(n, c)
                 assert e.size == c + 1 and e[0] == 0 and e[-1] == n and (np.diff(e) > 0).all()
-    assert capi.pipeline_bounds(358400).tolist() == [0, 24000, 72000, 168000, 358400]
+    assert capi.pipeline_bounds(358400).tolist() == [0, 39822, 119466, 199111, 278755, 358400]
     with pytest.raises(capi.PdmpcError):
         capi.pipeline_bounds(100, 1)
     with pytest.raises(capi.PdmpcError):
