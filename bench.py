@@ -266,6 +266,35 @@ def fp64_ops(batch, stats, Hp: int) -> float:
                  stats.total_nodes * (20 + 9 * (Hp - 1) / 2))
 
 
+def states_latency(planner, mpa, args, n_scenarios: int = 4, steps: int = 35):
+    """Wall time of pdmpc_plan_timestep_from_states per 20-vehicle time step over live closed loops (seeds 1..)."""
+    from pdmpc_b200 import scenario
+    hl, hw = scenario.VEH_LENGTH / 2 + 0.01, scenario.VEH_WIDTH / 2 + 0.01
+    planner.upload_reachable_sets(scenario.local_reachable_sets_conv(mpa))
+    ts, fallbacks = [], 0
+    for seed in range(1, 1 + n_scenarios):
+        sc = scenario.commonroad_scenario(mpa, args.vehicles, seed=seed)
+        planner.upload_road(scenario.road_tables([sc]))
+        planner.closed_loop_reset(args.vehicles, hl, hw)
+
+        def call(*a):
+            t0 = time.perf_counter()
+            r = planner.plan_timestep_from_states(*a, raise_on_search_error=False)
+            ts.append((time.perf_counter() - t0) * 1e3)
+            return r
+
+        runner = scenario.ScenarioRunner(sc, None, states_fn=call)
+        for _ in range(steps):
+            runner.step_timestep()
+        fallbacks += runner.n_fallbacks
+    t = np.array(ts)
+    return {"p50": float(np.percentile(t, 50)), "p99": float(np.percentile(t, 99)), "max": float(t.max()), "n": int(t.size),
+            "fallback_plans": int(fallbacks),
+            "what": "wall time of ONE pdmpc_plan_timestep_from_states call per 20-vehicle time step: inputs, obstacle "
+                    "assembly, dependency-ordered searches and fallback plans on the device, measured states in, plans out; "
+                    f"live closed loops of {n_scenarios} scenarios"}
+
+
 def cpu_timestep_latency(mpa, batch, step_recs, cores: int, reps: int = 2):
     """BASELINE.md §2 "CPU-step": wall time of one 20-vehicle time step on the CPU path the way the
     reference's parallel_threads mode runs it — computation levels one after the other, the vehicles of
@@ -552,6 +581,18 @@ def main():
             a = np.sort(np.concatenate([r.pop_hash for _lb, r, _i, _o in by_step[step]]))
             assert np.array_equal(a, np.sort(ro.pop_hash)), f"time step {step}: one-call path != level-by-level path"
 
+    # ---- the whole time step from the measured states, ONE call (pdmpc_plan_timestep_from_states) -----------------
+    # Inputs (reference trajectories, lanelet boundaries), obstacle assembly, dependency-ordered searches and fallback
+    # plans chained on the device; the host only decides coupling and priorities.  A live closed loop over the first
+    # scenarios of rank 0 (the latency legs above replay recorded time steps); only the device call is timed.
+    lat_states = None
+    if rank == 0 and not sampled and len(step_recs):
+        try:
+            lat_states = states_latency(planner, mpa, args)
+        except Exception as e:   # a diagnostic leg: it must never take the bench line down
+            lat_states = {"error": f"{type(e).__name__}: {e}"}
+        planner.upload_mpa(mpa)
+
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------
     cpu = None
     if rank == 0 and world == 1:
@@ -658,6 +699,7 @@ def main():
                                                           "step (predecessor hand-over on the device), host buffers in "
                                                           "and out; same time steps and answers as above"}
                                                  if lat1 else None),
+            "latency_ms_per_timestep_from_states": lat_states,
             "record_generation_s": round(t_gen, 1),
         }
         print(json.dumps(line))
